@@ -1,0 +1,252 @@
+// f9_process_batch: the MainComponent/AppState batch job flow (Source/MainComponent.cpp:705-805; Swift
+// processFiles AudioProcessingService.swift:66-113, :339-536) for a list of captured recordings:
+//     capture -> [reverb-tail scan] -> trimLatency -> [removeDCOffset] -> [sample-rate conversion] -> float / 24-bit PCM
+// One H2D pass per capture, batched kernels over the whole chunk, one D2H pass per output.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+
+#include "f9_internal.cuh"
+
+using namespace f9;
+
+namespace {
+
+inline long long pad64(long long frames) { return (std::max<long long>(frames, 1) + 63) / 64 * 64; }
+
+struct JobPlan {
+    int latency_frames = 0, start = 0, copied = 0, out_frames = 0;
+    bool convert = false;
+    double ratio = 1.0;
+    DevBuf cap{}, trimmed{}, out{};
+    unsigned char* d_pcm = nullptr;
+    size_t bytes = 0;
+    int polls = 0;
+};
+
+int validate(const f9_job& j) {
+    if (j.numCh <= 0 || j.captured_frames < 0 || j.original_length < 0 || !j.captured) return F9_ERR_INVALID;
+    for (int c = 0; c < j.numCh; ++c) if (j.captured_frames > 0 && !j.captured[c]) return F9_ERR_INVALID;
+    if (!(j.fs_in > 0.0) || !(j.fs_out > 0.0)) return F9_ERR_INVALID;
+    if (interp_memory(j.interp_kind) == 0) return F9_ERR_INVALID;
+    if ((j.flags & F9_JOB_TAIL_SCAN) && (j.tail_window <= 0 || j.tail_hop <= 0 || j.tail_required <= 0 ||
+        (j.tail_mode != F9_TAIL_RMS && j.tail_mode != F9_TAIL_PEAK))) return F9_ERR_INVALID;
+    if ((j.flags & F9_JOB_PCM24) && !j.out_pcm24) return F9_ERR_INVALID;
+    return F9_OK;
+}
+
+int run_chunk(f9_context* ctx, const f9_job* jobs, f9_result* results, const std::vector<int>& idx, std::vector<JobPlan>& plans) {
+    const int n = (int) idx.size();
+    size_t d_bytes = 1 << 20, h_bytes = 1 << 20;
+    int maxPolls = 0, nTail = 0;
+    for (int t = 0; t < n; ++t) {
+        d_bytes += plans[(size_t) t].bytes;
+        if (jobs[idx[(size_t) t]].flags & F9_JOB_TAIL_SCAN) { ++nTail; maxPolls = std::max(maxPolls, plans[(size_t) t].polls); }
+    }
+    size_t totalCh = 0;
+    for (int t = 0; t < n; ++t) totalCh += (size_t) jobs[idx[(size_t) t]].numCh;
+    d_bytes += (size_t) nTail * ((size_t) maxPolls * sizeof(int) + 64) + (size_t) n * 2048 + totalCh * 256;
+    h_bytes += (size_t) n * 2048 + (size_t) nTail * 16 + totalCh * 256;
+    int rc = ctx->arena_reserve(d_bytes, h_bytes); if (rc) return rc;
+    cudaStream_t s = ctx->stream;
+
+    // ---- upload captures, carve outputs ----
+    for (int t = 0; t < n; ++t) {
+        const f9_job& J = jobs[idx[(size_t) t]];
+        JobPlan& P = plans[(size_t) t];
+        const long long cs = pad64(J.captured_frames);
+        float* d_cap = (float*) ctx->d_alloc(sizeof(float) * (size_t) cs * J.numCh);
+        for (int c = 0; c < J.numCh; ++c)
+            if (J.captured_frames > 0)
+                F9_TRY_CUDA(ctx, cudaMemcpyAsync(d_cap + c * cs, J.captured[c], sizeof(float) * (size_t) J.captured_frames, cudaMemcpyHostToDevice, s));
+        P.cap = DevBuf{d_cap, cs, J.numCh, J.captured_frames};
+        const bool needTrimmed = !P.convert || (J.flags & F9_JOB_REMOVE_DC);
+        if (P.convert && needTrimmed) {
+            const long long ts = pad64(J.original_length);
+            P.trimmed = DevBuf{(float*) ctx->d_alloc(sizeof(float) * (size_t) ts * J.numCh), ts, J.numCh, J.original_length};
+        }
+        const long long os = pad64(P.out_frames);
+        P.out = DevBuf{(float*) ctx->d_alloc(sizeof(float) * (size_t) os * J.numCh), os, J.numCh, P.out_frames};
+        if (!P.convert) P.trimmed = P.out;
+        if (J.flags & F9_JOB_PCM24) P.d_pcm = (unsigned char*) ctx->d_alloc((size_t) P.out_frames * J.numCh * 3 + 16);
+    }
+
+    // ---- reverb-tail scan (Swift :423-453): starts once source + latency frames are captured ----
+    long long* h_stop = nullptr; std::vector<int> tailJobs;
+    if (nTail > 0) {
+        std::vector<DevBuf> tb; std::vector<TailParams> tp;
+        for (int t = 0; t < n; ++t) {
+            const f9_job& J = jobs[idx[(size_t) t]];
+            if (!(J.flags & F9_JOB_TAIL_SCAN)) continue;
+            const JobPlan& P = plans[(size_t) t];
+            TailParams T{};
+            T.startFrame = (long long) J.original_length + std::max(P.latency_frames, 0);
+            T.window = J.tail_window; T.hop = J.tail_hop; T.required = J.tail_required; T.mode = J.tail_mode;
+            if (J.tail_mode == F9_TAIL_PEAK) {
+                if (!J.has_nf) { T.noNf = 1; T.rstar = -1.0f; }
+                else T.rstar = largest_peak_below(J.nf_db + (J.nf_db * J.margin_pct / 100.0f), &T.below0);
+            } else T.rstar = largest_rms_below(nf_threshold_db(J.has_nf, J.nf_db, J.margin_pct), 1e-10f);
+            tb.push_back(P.cap); tp.push_back(T); tailJobs.push_back(t);
+        }
+        DevBuf* d_tb = (DevBuf*) ctx->d_alloc(sizeof(DevBuf) * tb.size());
+        TailParams* d_tp = (TailParams*) ctx->d_alloc(sizeof(TailParams) * tp.size());
+        DevBuf* h_tb = (DevBuf*) ctx->h_alloc(sizeof(DevBuf) * tb.size());
+        TailParams* h_tp = (TailParams*) ctx->h_alloc(sizeof(TailParams) * tp.size());
+        std::memcpy(h_tb, tb.data(), sizeof(DevBuf) * tb.size());
+        std::memcpy(h_tp, tp.data(), sizeof(TailParams) * tp.size());
+        F9_TRY_CUDA(ctx, cudaMemcpyAsync(d_tb, h_tb, sizeof(DevBuf) * tb.size(), cudaMemcpyHostToDevice, s));
+        F9_TRY_CUDA(ctx, cudaMemcpyAsync(d_tp, h_tp, sizeof(TailParams) * tp.size(), cudaMemcpyHostToDevice, s));
+        int* d_flags = (int*) ctx->d_alloc(sizeof(int) * (size_t) std::max(maxPolls, 1) * tb.size());
+        long long* d_stop = (long long*) ctx->d_alloc(sizeof(long long) * tb.size());
+        F9_TRY_CUDA(ctx, launch_tail_scan(d_tb, d_tp, (int) tb.size(), maxPolls, d_stop, d_flags, s, &ctx->launches));
+        h_stop = (long long*) ctx->h_alloc(sizeof(long long) * tb.size());
+        F9_TRY_CUDA(ctx, cudaMemcpyAsync(h_stop, d_stop, sizeof(long long) * tb.size(), cudaMemcpyDeviceToHost, s));
+    }
+
+    // ---- trim (+DC) where a trimmed buffer is materialised ----
+    {
+        std::vector<DevBuf> tc, to; std::vector<int> lat, dcMask;
+        int maxCh = 0, maxFrames = 0;
+        for (int t = 0; t < n; ++t) {
+            const f9_job& J = jobs[idx[(size_t) t]];
+            const JobPlan& P = plans[(size_t) t];
+            if (P.convert && !(J.flags & F9_JOB_REMOVE_DC)) continue;      // fused into the resampler by pointer offset
+            tc.push_back(P.cap); to.push_back(P.trimmed); lat.push_back(J.latency_samples);
+            dcMask.push_back((J.flags & F9_JOB_REMOVE_DC) ? 1 : 0);
+            maxCh = std::max(maxCh, J.numCh); maxFrames = std::max(maxFrames, J.original_length);
+        }
+        if (!tc.empty()) {
+            const size_t m = tc.size();
+            DevBuf* d_c = (DevBuf*) ctx->d_alloc(sizeof(DevBuf) * m); DevBuf* d_o = (DevBuf*) ctx->d_alloc(sizeof(DevBuf) * m);
+            int* d_l = (int*) ctx->d_alloc(sizeof(int) * m);
+            DevBuf* h_c = (DevBuf*) ctx->h_alloc(sizeof(DevBuf) * m); DevBuf* h_o = (DevBuf*) ctx->h_alloc(sizeof(DevBuf) * m);
+            int* h_l = (int*) ctx->h_alloc(sizeof(int) * m);
+            std::memcpy(h_c, tc.data(), sizeof(DevBuf) * m); std::memcpy(h_o, to.data(), sizeof(DevBuf) * m); std::memcpy(h_l, lat.data(), sizeof(int) * m);
+            F9_TRY_CUDA(ctx, cudaMemcpyAsync(d_c, h_c, sizeof(DevBuf) * m, cudaMemcpyHostToDevice, s));
+            F9_TRY_CUDA(ctx, cudaMemcpyAsync(d_o, h_o, sizeof(DevBuf) * m, cudaMemcpyHostToDevice, s));
+            F9_TRY_CUDA(ctx, cudaMemcpyAsync(d_l, h_l, sizeof(int) * m, cudaMemcpyHostToDevice, s));
+            F9_TRY_CUDA(ctx, launch_trim(d_c, d_l, d_o, (int) m, maxFrames, maxCh, s, &ctx->launches));
+            // DC removal on the subset that asked for it (contiguous copy of their descriptors)
+            std::vector<DevBuf> dcb;
+            for (size_t i = 0; i < m; ++i) if (dcMask[i]) dcb.push_back(to[i]);
+            if (!dcb.empty()) {
+                DevBuf* d_d = (DevBuf*) ctx->d_alloc(sizeof(DevBuf) * dcb.size());
+                DevBuf* h_d = (DevBuf*) ctx->h_alloc(sizeof(DevBuf) * dcb.size());
+                std::memcpy(h_d, dcb.data(), sizeof(DevBuf) * dcb.size());
+                F9_TRY_CUDA(ctx, cudaMemcpyAsync(d_d, h_d, sizeof(DevBuf) * dcb.size(), cudaMemcpyHostToDevice, s));
+                double* d_sums = (double*) ctx->d_alloc(sizeof(double) * dcb.size() * (size_t) maxCh);
+                F9_TRY_CUDA(ctx, launch_remove_dc(d_d, (int) dcb.size(), maxCh, maxFrames, d_sums, s, &ctx->launches));
+            }
+        }
+    }
+
+    // ---- sample-rate conversion, one launch per (kind, ratio) group ----
+    {
+        std::map<std::pair<int, double>, std::vector<Seg>> groups;
+        for (int t = 0; t < n; ++t) {
+            const f9_job& J = jobs[idx[(size_t) t]];
+            const JobPlan& P = plans[(size_t) t];
+            if (!P.convert || P.out_frames <= 0) continue;
+            auto& g = groups[std::make_pair(J.interp_kind, P.ratio)];
+            for (int c = 0; c < J.numCh; ++c) {
+                Seg S{};
+                if (J.flags & F9_JOB_REMOVE_DC) { S.in = P.trimmed.base + c * P.trimmed.chStride; S.inAvail = J.original_length; }
+                else { S.in = P.cap.base + c * P.cap.chStride + std::max(P.start, 0); S.inAvail = P.copied; }
+                S.inOffset = 0;
+                S.out = const_cast<float*>(P.out.base) + c * P.out.chStride; S.n0 = 0; S.numOut = P.out_frames;
+                g.push_back(S);
+            }
+        }
+        for (auto& kv : groups) {
+            ResampleLaunch L;
+            L.kind = kv.first.first; L.ratio = kv.first.second; L.pos0 = 1.0;
+            L.d_sinc_table = ctx->d_sinc_table; L.tile_out = choose_tile_out(L.ratio);
+            long long p = 0, q = 0;
+            if (find_rational(L.ratio, 4096, &p, &q) && p <= (1 << 20)) {
+                rc = ctx->get_poly(L.kind, p, q, &L.poly); if (rc) return rc;
+                L.rational = true;
+            }
+            if ((double) L.tile_out * L.ratio > 45000.0) return ctx->fail(F9_ERR_UNSUPPORTED, "speed ratio too large for the tile buffer");
+            std::vector<Seg>& segs = kv.second;
+            std::vector<int> prefix(segs.size() + 1, 0);
+            for (size_t i = 0; i < segs.size(); ++i)
+                prefix[i + 1] = prefix[i] + (int) ((segs[i].numOut + L.tile_out - 1) / L.tile_out);
+            Seg* d_s = (Seg*) ctx->d_alloc(sizeof(Seg) * segs.size()); int* d_p = (int*) ctx->d_alloc(sizeof(int) * prefix.size());
+            Seg* h_s = (Seg*) ctx->h_alloc(sizeof(Seg) * segs.size()); int* h_p = (int*) ctx->h_alloc(sizeof(int) * prefix.size());
+            std::memcpy(h_s, segs.data(), sizeof(Seg) * segs.size()); std::memcpy(h_p, prefix.data(), sizeof(int) * prefix.size());
+            F9_TRY_CUDA(ctx, cudaMemcpyAsync(d_s, h_s, sizeof(Seg) * segs.size(), cudaMemcpyHostToDevice, s));
+            F9_TRY_CUDA(ctx, cudaMemcpyAsync(d_p, h_p, sizeof(int) * prefix.size(), cudaMemcpyHostToDevice, s));
+            L.d_segs = d_s; L.d_tile_prefix = d_p; L.n_segs = (int) segs.size(); L.n_tiles = prefix.back();
+            F9_TRY_CUDA(ctx, launch_resample(L, s, &ctx->launches));
+        }
+    }
+
+    // ---- 24-bit payload + downloads ----
+    for (int t = 0; t < n; ++t) {
+        const f9_job& J = jobs[idx[(size_t) t]];
+        const JobPlan& P = plans[(size_t) t];
+        if ((J.flags & F9_JOB_PCM24) && P.out_frames > 0) {
+            F9_TRY_CUDA(ctx, launch_planar_to_pcm24(P.out.base, P.out.chStride, J.numCh, P.out_frames, P.d_pcm, s, &ctx->launches));
+            F9_TRY_CUDA(ctx, cudaMemcpyAsync(J.out_pcm24, P.d_pcm, (size_t) P.out_frames * J.numCh * 3, cudaMemcpyDeviceToHost, s));
+        }
+        if (J.out && P.out_frames > 0)
+            for (int c = 0; c < J.numCh; ++c)
+                F9_TRY_CUDA(ctx, cudaMemcpyAsync(J.out[c], P.out.base + c * P.out.chStride, sizeof(float) * (size_t) P.out_frames, cudaMemcpyDeviceToHost, s));
+    }
+    F9_FINISH(ctx);
+
+    for (size_t i = 0; i < tailJobs.size(); ++i) results[idx[(size_t) tailJobs[i]]].tail_stop_frame = h_stop[i];
+    return F9_OK;
+}
+
+}  // namespace
+
+extern "C" int f9_process_batch(f9_context* ctx, const f9_job* jobs, int n_jobs, f9_result* results) {
+    if (!ctx) return F9_ERR_INVALID;
+    if (n_jobs < 0 || (n_jobs > 0 && (!jobs || !results))) return ctx->fail(F9_ERR_INVALID, "bad job array");
+    F9_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    size_t freeB = 0, totalB = 0;
+    F9_TRY_CUDA(ctx, cudaMemGetInfo(&freeB, &totalB));
+    const size_t budget = std::max<size_t>((freeB + ctx->d_cap) / 2, 64u << 20);   // device bytes per chunk
+
+    std::vector<int> idx; std::vector<JobPlan> plans; size_t used = 0;
+    auto flush = [&]() -> int {
+        if (idx.empty()) return F9_OK;
+        int rc = run_chunk(ctx, jobs, results, idx, plans);
+        if (rc) for (int i : idx) results[i].status = rc;
+        idx.clear(); plans.clear(); used = 0;
+        return rc;
+    };
+    int worst = F9_OK;
+    for (int i = 0; i < n_jobs; ++i) {
+        const f9_job& J = jobs[i];
+        f9_result& R = results[i];
+        R = f9_result{}; R.tail_stop_frame = -1;
+        R.status = validate(J);
+        if (R.status) { worst = R.status; ctx->err = "invalid job"; continue; }
+        JobPlan P;
+        // trimLatency arithmetic (Source/MainComponent.cpp:833-845)
+        P.latency_frames = J.latency_samples / J.numCh;
+        P.start = P.latency_frames;
+        P.copied = J.original_length;
+        if (P.start + P.copied > J.captured_frames) P.copied = std::max(0, J.captured_frames - P.start);
+        if (P.start < 0) P.copied = 0;
+        P.convert = (J.fs_in != J.fs_out);
+        P.ratio = J.fs_in / J.fs_out;
+        P.out_frames = P.convert ? (int) f9_resampled_length(J.original_length, J.fs_in, J.fs_out) : J.original_length;
+        if (J.out && J.out_capacity < P.out_frames) { R.status = F9_ERR_INVALID; worst = R.status; ctx->err = "out_capacity too small"; continue; }
+        if (J.flags & F9_JOB_TAIL_SCAN) {
+            const long long startFrame = (long long) J.original_length + std::max(P.latency_frames, 0);
+            P.polls = (int) std::max<long long>(0, (J.captured_frames - startFrame) / J.tail_hop);
+        }
+        P.bytes = sizeof(float) * (size_t) J.numCh * (size_t) (pad64(J.captured_frames) + pad64(P.out_frames) + pad64(J.original_length))
+                  + (size_t) P.out_frames * J.numCh * 3 + 4096;
+        R.latency_frames = P.latency_frames; R.trim_start = P.start; R.frames_copied = P.copied;
+        R.out_frames = P.out_frames; R.tail_polls = P.polls;
+        if (used + P.bytes > budget && !idx.empty()) { int rc = flush(); if (rc) worst = rc; }
+        idx.push_back(i); plans.push_back(P); used += P.bytes;
+    }
+    int rc = flush(); if (rc) worst = rc;
+    return worst;
+}

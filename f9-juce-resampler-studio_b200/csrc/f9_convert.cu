@@ -1,0 +1,253 @@
+// Trim, DC removal and the deinterleave / format-convert stage.  Pure streaming copies: 4 B read + 4 B written
+// per sample (3 + 4 for 24-bit PCM), coalesced, grid sized from the data.
+#include "f9_internal.cuh"
+
+namespace f9 {
+namespace {
+
+constexpr int kThreads = 256;
+
+// ---- trimLatency (Source/MainComponent.cpp:824-861), batched ------------------------------------------
+// grid: (tiles over frames, channel, buffer).  out = zeros, then captured[start .. start+n) when n > 0 && start >= 0.
+__global__ void __launch_bounds__(kThreads)
+trim_kernel(const DevBuf* __restrict__ cap, const int* __restrict__ latency, const DevBuf* __restrict__ out) {
+    const int b = blockIdx.z, ch = blockIdx.y;
+    const DevBuf C = cap[b];
+    const DevBuf O = out[b];
+    if (ch >= O.numCh) return;
+    const int start = latency[b] / C.numCh;                  // truncating division (:835)
+    int n = O.numFrames;                                     // originalLength
+    if (start + n > C.numFrames) n = max(0, C.numFrames - start);
+    if (start < 0) n = 0;
+    const float* __restrict__ src = C.base + (long long) ch * C.chStride + start;
+    float* __restrict__ dst = const_cast<float*>(O.base) + (long long) ch * O.chStride;
+    for (int i = blockIdx.x * kThreads + threadIdx.x; i < O.numFrames; i += gridDim.x * kThreads)
+        dst[i] = (i < n) ? __ldg(src + i) : 0.0f;
+}
+
+// ---- removeDCOffset (Source/MainComponent.cpp:884-902) -------------------------------------------------
+// The reference sums sequentially in float; a parallel sum can only match to tolerance.
+// Pass 1: per (buffer, channel) sum in double, deterministic tree.  Pass 2: subtract (float)(sum) / numFrames.
+__global__ void __launch_bounds__(kThreads)
+dc_sum_kernel(const DevBuf* __restrict__ bufs, int maxCh, double* __restrict__ sums) {
+    const int b = blockIdx.y, ch = blockIdx.x;
+    const DevBuf B = bufs[b];
+    if (ch >= B.numCh) return;
+    const float* __restrict__ x = B.base + (long long) ch * B.chStride;
+    double s = 0.0;
+    for (int i = threadIdx.x; i < B.numFrames; i += kThreads) s += (double) __ldg(x + i);
+    #pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    __shared__ double sh[kThreads / 32];
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < kThreads / 32; ++w) t += sh[w];
+        sums[(size_t) b * maxCh + ch] = t;
+    }
+}
+__global__ void __launch_bounds__(kThreads)
+dc_sub_kernel(const DevBuf* __restrict__ bufs, int maxCh, const double* __restrict__ sums) {
+    const int b = blockIdx.z, ch = blockIdx.y;
+    const DevBuf B = bufs[b];
+    if (ch >= B.numCh || B.numFrames <= 0) return;
+    const float dc = (float) sums[(size_t) b * maxCh + ch] / (float) B.numFrames;
+    float* __restrict__ x = const_cast<float*>(B.base) + (long long) ch * B.chStride;
+    for (int i = blockIdx.x * kThreads + threadIdx.x; i < B.numFrames; i += gridDim.x * kThreads) x[i] = __fsub_rn(x[i], dc);
+}
+
+// ---- PCM -> planar float (JUCE reader: left-justify to int32, * 1/0x7fffffff) ---------------------------
+__device__ __forceinline__ float pcm_load(const unsigned char* __restrict__ src, int fmt, long long s) {
+    const float scale = 1.0f / 0x7fffffff;
+    switch (fmt) {
+        case F9_PCM_U8:  { const int v = (int) ((unsigned) (src[s] - 128) << 24); return __fmul_rn((float) v, scale); }
+        case F9_PCM_S16LE: { const unsigned u = (unsigned) src[2 * s] | ((unsigned) src[2 * s + 1] << 8);
+                             return __fmul_rn((float) (int) (u << 16), scale); }
+        case F9_PCM_S24LE: { const unsigned u = (unsigned) src[3 * s] | ((unsigned) src[3 * s + 1] << 8) | ((unsigned) src[3 * s + 2] << 16);
+                             return __fmul_rn((float) (int) (u << 8), scale); }
+        case F9_PCM_S32LE: { const unsigned u = (unsigned) src[4 * s] | ((unsigned) src[4 * s + 1] << 8) | ((unsigned) src[4 * s + 2] << 16) | ((unsigned) src[4 * s + 3] << 24);
+                             return __fmul_rn((float) (int) u, scale); }
+        default: { const unsigned u = (unsigned) src[4 * s] | ((unsigned) src[4 * s + 1] << 8) | ((unsigned) src[4 * s + 2] << 16) | ((unsigned) src[4 * s + 3] << 24);
+                   return __uint_as_float(u); }
+    }
+}
+// One thread per frame; the CTA's frames are staged through shared memory so both the interleaved read and the
+// planar writes are coalesced.
+// frames per CTA: sized by the launcher so the staging tile stays under ~40 KB for any channel count
+__host__ __device__ inline int cvt_frames(int bytesPerFrame) { int f = 40960 / (bytesPerFrame > 0 ? bytesPerFrame : 1); f = f > 1024 ? 1024 : f; f &= ~31; return f < 32 ? 32 : f; }
+__global__ void __launch_bounds__(kThreads)
+pcm_to_planar_kernel(const unsigned char* __restrict__ src, int fmt, int srcCh, long long frames,
+                     float* __restrict__ dst, long long dstStride, int dstCh, int kCvtFrames) {
+    extern __shared__ unsigned char raw[];
+    const int bps = (fmt == F9_PCM_U8) ? 1 : (fmt == F9_PCM_S16LE) ? 2 : (fmt == F9_PCM_S24LE) ? 3 : 4;
+    const long long f0 = (long long) blockIdx.x * kCvtFrames;
+    const int nf = (int) min((long long) kCvtFrames, frames - f0);
+    const long long byte0 = f0 * srcCh * bps;
+    const int nbytes = nf * srcCh * bps;
+    // coalesced byte copy (32-bit words where the tile start is aligned)
+    if ((byte0 & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 3) == 0) {
+        const unsigned* __restrict__ s4 = reinterpret_cast<const unsigned*>(src + byte0);
+        unsigned* r4 = reinterpret_cast<unsigned*>(raw);
+        const int nw = nbytes >> 2;
+        for (int i = threadIdx.x; i < nw; i += kThreads) r4[i] = __ldg(s4 + i);
+        for (int i = (nw << 2) + threadIdx.x; i < nbytes; i += kThreads) raw[i] = src[byte0 + i];
+    } else {
+        for (int i = threadIdx.x; i < nbytes; i += kThreads) raw[i] = src[byte0 + i];
+    }
+    __syncthreads();
+    for (int c = 0; c < dstCh; ++c) {
+        const int sc = min(c, srcCh - 1);       // mono -> stereo duplication (AudioProcessingService.swift:579-580)
+        float* __restrict__ d = dst + (long long) c * dstStride + f0;
+        for (int f = threadIdx.x; f < nf; f += kThreads) d[f] = pcm_load(raw, fmt, (long long) f * srcCh + sc);
+    }
+}
+
+// ---- planar float -> interleaved 24-bit LE (JUCE writer: clip, roundToInt(INT_MAX * (double) x), top 24 bits) ---
+__device__ __forceinline__ int float_to_i32(float x) {
+    const double samp = (double) x;
+    if (samp <= -1.0) return (int) 0x80000000;
+    if (samp >= 1.0) return 0x7fffffff;
+    return __double2int_rn(__dmul_rn(2147483647.0, samp));
+}
+__global__ void __launch_bounds__(kThreads)
+planar_to_pcm24_kernel(const float* __restrict__ src, long long srcStride, int numCh, long long frames, unsigned char* __restrict__ dst, int kCvtFrames) {
+    extern __shared__ unsigned char raw[];
+    const long long f0 = (long long) blockIdx.x * kCvtFrames;
+    const int nf = (int) min((long long) kCvtFrames, frames - f0);
+    for (int c = 0; c < numCh; ++c) {
+        const float* __restrict__ s = src + (long long) c * srcStride + f0;
+        for (int f = threadIdx.x; f < nf; f += kThreads) {
+            const int t = float_to_i32(__ldg(s + f)) >> 8;
+            unsigned char* r = raw + 3 * (f * numCh + c);
+            r[0] = (unsigned char) (t & 0xff); r[1] = (unsigned char) ((t >> 8) & 0xff); r[2] = (unsigned char) ((t >> 16) & 0xff);
+        }
+    }
+    __syncthreads();
+    const long long byte0 = f0 * numCh * 3;
+    const int nbytes = nf * numCh * 3;
+    if ((byte0 & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 3) == 0) {
+        unsigned* __restrict__ d4 = reinterpret_cast<unsigned*>(dst + byte0);
+        const unsigned* r4 = reinterpret_cast<const unsigned*>(raw);
+        const int nw = nbytes >> 2;
+        for (int i = threadIdx.x; i < nw; i += kThreads) d4[i] = r4[i];
+        for (int i = (nw << 2) + threadIdx.x; i < nbytes; i += kThreads) dst[byte0 + i] = raw[i];
+    } else {
+        for (int i = threadIdx.x; i < nbytes; i += kThreads) dst[byte0 + i] = raw[i];
+    }
+}
+
+// ---- planar <-> interleaved float (AudioProcessingService.swift:361-365, :524-531) ----------------------
+__global__ void __launch_bounds__(kThreads)
+interleave_kernel(const float* __restrict__ src, long long srcStride, int numCh, long long frames, float* __restrict__ dst, int kCvtFrames) {
+    extern __shared__ float tile[];          // [numCh][kCvtFrames + 1]
+    const long long f0 = (long long) blockIdx.x * kCvtFrames;
+    const int nf = (int) min((long long) kCvtFrames, frames - f0);
+    for (int c = 0; c < numCh; ++c)
+        for (int f = threadIdx.x; f < nf; f += kThreads) tile[c * (kCvtFrames + 1) + f] = __ldg(src + (long long) c * srcStride + f0 + f);
+    __syncthreads();
+    const int total = nf * numCh;
+    float* __restrict__ d = dst + f0 * numCh;
+    for (int i = threadIdx.x; i < total; i += kThreads) { const int f = i / numCh, c = i - f * numCh; d[i] = tile[c * (kCvtFrames + 1) + f]; }
+}
+__global__ void __launch_bounds__(kThreads)
+deinterleave_kernel(const float* __restrict__ src, int numCh, long long frames, float* __restrict__ dst, long long dstStride, int kCvtFrames) {
+    extern __shared__ float tile[];
+    const long long f0 = (long long) blockIdx.x * kCvtFrames;
+    const int nf = (int) min((long long) kCvtFrames, frames - f0);
+    const int total = nf * numCh;
+    const float* __restrict__ s = src + f0 * numCh;
+    for (int i = threadIdx.x; i < total; i += kThreads) { const int f = i / numCh, c = i - f * numCh; tile[c * (kCvtFrames + 1) + f] = __ldg(s + i); }
+    __syncthreads();
+    for (int c = 0; c < numCh; ++c)
+        for (int f = threadIdx.x; f < nf; f += kThreads) dst[(long long) c * dstStride + f0 + f] = tile[c * (kCvtFrames + 1) + f];
+}
+
+template <typename K>
+cudaError_t allow_smem(K kernel, size_t bytes) {
+    if (bytes <= 48 * 1024) return cudaSuccess;
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+}
+
+}  // namespace
+
+cudaError_t launch_trim(const DevBuf* d_captured, const int* d_latency, const DevBuf* d_out, int n, int maxOutFrames,
+                        int maxCh, cudaStream_t s, long long* launches) {
+    if (n <= 0 || maxCh <= 0) return cudaSuccess;
+    const int tiles = std::max(1, std::min((maxOutFrames + kThreads * 8 - 1) / (kThreads * 8), 4096));
+    for (int b0 = 0; b0 < n; b0 += 65535) {
+        const int nb = std::min(65535, n - b0);
+        dim3 grid(tiles, maxCh, nb);
+        trim_kernel<<<grid, kThreads, 0, s>>>(d_captured + b0, d_latency + b0, d_out + b0);
+        ++*launches;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_remove_dc(const DevBuf* d_bufs, int n, int maxCh, int maxFrames, double* d_sums, cudaStream_t s, long long* launches) {
+    if (n <= 0 || maxCh <= 0) return cudaSuccess;
+    for (int b0 = 0; b0 < n; b0 += 65535) {
+        const int nb = std::min(65535, n - b0);
+        dc_sum_kernel<<<dim3(maxCh, nb), kThreads, 0, s>>>(d_bufs + b0, maxCh, d_sums + (size_t) b0 * maxCh);
+        ++*launches;
+        const int tiles = std::max(1, std::min((maxFrames + kThreads * 8 - 1) / (kThreads * 8), 4096));
+        dc_sub_kernel<<<dim3(tiles, maxCh, nb), kThreads, 0, s>>>(d_bufs + b0, maxCh, d_sums + (size_t) b0 * maxCh);
+        ++*launches;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pcm_to_planar(const void* d_src, int fmt, int srcCh, long long frames, float* d_dst,
+                                 long long dstStride, int dstCh, cudaStream_t s, long long* launches) {
+    if (frames <= 0) return cudaSuccess;
+    const int bps = (fmt == F9_PCM_U8) ? 1 : (fmt == F9_PCM_S16LE) ? 2 : (fmt == F9_PCM_S24LE) ? 3 : 4;
+    const int kCvtFrames = cvt_frames(srcCh * bps);
+    const size_t smem = (size_t) kCvtFrames * srcCh * bps + 16;
+    cudaError_t e = allow_smem(pcm_to_planar_kernel, smem);
+    if (e != cudaSuccess) return e;
+    const long long ctas = (frames + kCvtFrames - 1) / kCvtFrames;
+    pcm_to_planar_kernel<<<(unsigned) ctas, kThreads, smem, s>>>((const unsigned char*) d_src, fmt, srcCh, frames, d_dst, dstStride, dstCh, kCvtFrames);
+    ++*launches;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_planar_to_pcm24(const float* d_src, long long srcStride, int numCh, long long frames,
+                                   unsigned char* d_dst, cudaStream_t s, long long* launches) {
+    if (frames <= 0) return cudaSuccess;
+    const int kCvtFrames = cvt_frames(numCh * 3);
+    const size_t smem = (size_t) kCvtFrames * numCh * 3 + 16;
+    cudaError_t e = allow_smem(planar_to_pcm24_kernel, smem);
+    if (e != cudaSuccess) return e;
+    const long long ctas = (frames + kCvtFrames - 1) / kCvtFrames;
+    planar_to_pcm24_kernel<<<(unsigned) ctas, kThreads, smem, s>>>(d_src, srcStride, numCh, frames, d_dst, kCvtFrames);
+    ++*launches;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_interleave(const float* d_src, long long srcStride, int numCh, long long frames, float* d_dst,
+                              cudaStream_t s, long long* launches) {
+    if (frames <= 0) return cudaSuccess;
+    const int kCvtFrames = cvt_frames(numCh * 4);
+    const size_t smem = sizeof(float) * (size_t) numCh * (kCvtFrames + 1);
+    cudaError_t e = allow_smem(interleave_kernel, smem);
+    if (e != cudaSuccess) return e;
+    const long long ctas = (frames + kCvtFrames - 1) / kCvtFrames;
+    interleave_kernel<<<(unsigned) ctas, kThreads, smem, s>>>(d_src, srcStride, numCh, frames, d_dst, kCvtFrames);
+    ++*launches;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_deinterleave(const float* d_src, int numCh, long long frames, float* d_dst, long long dstStride,
+                                cudaStream_t s, long long* launches) {
+    if (frames <= 0) return cudaSuccess;
+    const int kCvtFrames = cvt_frames(numCh * 4);
+    const size_t smem = sizeof(float) * (size_t) numCh * (kCvtFrames + 1);
+    cudaError_t e = allow_smem(deinterleave_kernel, smem);
+    if (e != cudaSuccess) return e;
+    const long long ctas = (frames + kCvtFrames - 1) / kCvtFrames;
+    deinterleave_kernel<<<(unsigned) ctas, kThreads, smem, s>>>(d_src, numCh, frames, d_dst, dstStride, kCvtFrames);
+    ++*launches;
+    return cudaGetLastError();
+}
+
+}  // namespace f9

@@ -1,0 +1,159 @@
+// Internal declarations shared by the translation units of libf9dsp.so.
+// Product code: nothing here may include or link anything under oracle/.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "f9dsp.h"
+
+namespace f9 {
+
+// ----------------------------------------------------------------------------- tables (host, f9_tables.cpp)
+constexpr int kSincTableSize = 10001;
+constexpr int kSincTaps = 200;       // WindowedSinc memory (taps i = -100 .. 99 contribute)
+constexpr int kLagrangeTaps = 5;
+
+void make_default_sinc_table(float* t);                 // sinc * Hann stand-in for JUCE's lookupTable
+int  interp_memory(int kind);                           // ring size: 200, 5, 4, 2, 1
+float interp_latency(int kind);
+// Find p/q (q <= max_q) with (double)p/(double)q == ratio bit for bit.  Returns false if none.
+bool  find_rational(double ratio, int max_q, long long* p, long long* q);
+// Per-tap weights of one output at sub-sample offset `offset` (oldest input first).
+// For WindowedSinc this walks JUCE's valueAtOffset index/frac logic tap by tap.
+void  tap_weights(int kind, const float* sinc_table, float offset, float* w /* interp_memory(kind) */);
+
+// Polyphase description of a rational ratio p/q: output n = a*q + k reads inputs ending at
+// m = a*p + B[k] with weights W[tap][k].
+struct PolyHost {
+    int p = 0, q = 0, taps = 0, qpad = 0;
+    std::vector<int>   B;        // q
+    std::vector<float> W;        // taps * qpad, tap-major
+};
+void build_poly(int kind, const float* sinc_table, long long p, long long q, PolyHost* out);
+
+// host scalars with the reference's rounding (f9_tables.cpp, compiled with -ffp-contract=off)
+float largest_rms_below(float thrDb, float floorv);
+float largest_peak_below(float thrDb, int* below0);
+float noise_floor_db_from_rms(float rms);
+float nf_threshold_db(int has_nf, float nf_db, float margin_pct);
+float threshold_linear(float db);
+int   run_position_chain(double* pos_io, double ratio, int num_out);
+void  position_closed_form(double pos0, double ratio, long long n, long long* c, double* frac_out);
+
+// ----------------------------------------------------------------------------- device-side job records
+struct DevBuf {                    // planar float32 buffer
+    const float* base; long long chStride; int numCh; int numFrames;
+};
+struct Seg {                       // one resample segment (mirror of f9_resample_seg)
+    const float* in; long long inOffset; long long inAvail;
+    float* out;      long long n0;       long long numOut;
+};
+struct TailParams {
+    long long startFrame; int window, hop, required, mode;
+    int noNf;           // 1: Swift fallback (peak < 0.0001f) / C++ -80 dB handled through rstar
+    float rstar;        // largest value (rms or peak) for which the predicate is true; <0: never
+    int below0;         // predicate value at exactly 0 (peak mode: -160 dB branch)
+};
+
+struct PeakPartial { float v; int ch; int pos; };
+struct XcPartial   { double v; int ch; int lag; int pad; };
+
+// ----------------------------------------------------------------------------- launchers
+// All take the stream; none synchronise.  *launches is bumped once per kernel launched.
+constexpr int kStatPartialsPerBuf = 64;     // stage-1 CTAs per buffer of launch_stats
+
+int         peak_prefix(const DevBuf* h_bufs, int n, std::vector<int>* prefix);          // returns total CTAs
+cudaError_t launch_find_peak(const DevBuf* d_bufs, int n, int total_ctas, const int* d_prefix, float threshold,
+                             PeakPartial* d_partials /* total_ctas */, int* d_out_pos, cudaStream_t s, long long* launches);
+
+cudaError_t launch_stats(const DevBuf* d_bufs, int n, double* d_psum, float* d_pmax /* n*kStatPartialsPerBuf each */,
+                         double* d_sumsq, float* d_peak, cudaStream_t s, long long* launches);
+
+cudaError_t launch_tail_scan(const DevBuf* d_bufs, const TailParams* d_params, int n, int max_polls,
+                             long long* d_stop, int* d_flags /* n*max_polls, required */, cudaStream_t s, long long* launches);
+
+int         xcorr_prefix(const DevBuf* h_bufs, int n, int lagMin, int lagMax, std::vector<int>* prefix);
+cudaError_t launch_xcorr(const DevBuf* d_bufs, int n, int total_ctas, const int* d_prefix, const float* d_stim, int stimLen,
+                         int lagMin, int lagMax, XcPartial* d_partials /* total_ctas */, XcPartial* d_best /* n */,
+                         cudaStream_t s, long long* launches);
+
+cudaError_t launch_trim(const DevBuf* d_captured, const int* d_latency, const DevBuf* d_out, int n, int maxOutFrames,
+                        int maxCh, cudaStream_t s, long long* launches);
+cudaError_t launch_remove_dc(const DevBuf* d_bufs /* writable */, int n, int maxCh, int maxFrames, double* d_sums /* n*maxCh */,
+                             cudaStream_t s, long long* launches);
+
+cudaError_t launch_pcm_to_planar(const void* d_src, int fmt, int srcCh, long long frames, float* d_dst,
+                                 long long dstStride, int dstCh, cudaStream_t s, long long* launches);
+cudaError_t launch_planar_to_pcm24(const float* d_src, long long srcStride, int numCh, long long frames,
+                                   unsigned char* d_dst, cudaStream_t s, long long* launches);
+cudaError_t launch_interleave(const float* d_src, long long srcStride, int numCh, long long frames, float* d_dst,
+                              cudaStream_t s, long long* launches);
+cudaError_t launch_deinterleave(const float* d_src, int numCh, long long frames, float* d_dst, long long dstStride,
+                                cudaStream_t s, long long* launches);
+
+// resampling ---------------------------------------------------------------
+struct PolyDev {                   // device copy of PolyHost
+    int p = 0, q = 0, taps = 0, qpad = 0;
+    int* B = nullptr; float* W = nullptr;
+};
+struct ResampleLaunch {
+    int kind = 0;
+    double ratio = 1.0;
+    double pos0 = 1.0;             // sub-sample position before output 0 (1.0 = reset state)
+    bool rational = false;
+    PolyDev poly;                  // valid when rational
+    const float* d_sinc_table = nullptr;   // generic WindowedSinc path
+    const Seg* d_segs = nullptr;
+    const int* d_tile_prefix = nullptr;    // n_segs + 1
+    int n_segs = 0;
+    int n_tiles = 0;
+    int tile_out = 0;              // outputs per tile
+    int adding = 0; float gain = 1.0f;
+};
+int         choose_tile_out(double ratio);
+cudaError_t launch_resample(const ResampleLaunch& L, cudaStream_t s, long long* launches);
+
+}  // namespace f9
+
+// ----------------------------------------------------------------------------- context
+struct f9_context {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    long long launches = 0;
+
+    // bump arenas, reset at the start of every blocking call
+    char* d_arena = nullptr;  size_t d_cap = 0, d_used = 0;
+    char* h_arena = nullptr;  size_t h_cap = 0, h_used = 0;     // pinned
+
+    std::vector<float> sinc_table;      // host copy (10001 + 1 guard)
+    float* d_sinc_table = nullptr;
+    unsigned sinc_epoch = 0;            // bumped by f9_sinc_table_set
+
+    struct PolyKey { int kind; long long p, q; unsigned epoch; bool operator<(const PolyKey& o) const {
+        if (kind != o.kind) return kind < o.kind; if (p != o.p) return p < o.p; if (q != o.q) return q < o.q; return epoch < o.epoch; } };
+    std::map<PolyKey, f9::PolyDev> poly_cache;
+
+    int fail(int code, const char* msg) { err = msg; return code; }
+    int fail_cuda(cudaError_t e, const char* what) {
+        err = std::string(what) + ": " + cudaGetErrorString(e); return F9_ERR_CUDA;
+    }
+    bool  quiescent = true;             // nothing enqueued by this context can still touch the arenas
+    void  arena_reset() { d_used = 0; h_used = 0; }
+    int   arena_reserve(size_t d_bytes, size_t h_bytes, bool async_call = false);
+    void* d_alloc(size_t bytes) { size_t o = (d_used + 255) & ~size_t(255); d_used = o + bytes; return d_arena + o; }
+    void* h_alloc(size_t bytes) { size_t o = (h_used + 255) & ~size_t(255); h_used = o + bytes; return h_arena + o; }
+    int   get_poly(int kind, long long p, long long q, f9::PolyDev* out);
+};
+
+#define F9_TRY_CUDA(ctx, call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return (ctx)->fail_cuda(e__, #call); } while (0)
+// end of a blocking entry point: wait for the stream, after which the arenas may be reused from offset 0
+#define F9_FINISH(ctx) do { cudaError_t e__ = cudaStreamSynchronize((ctx)->stream); \
+    if (e__ != cudaSuccess) return (ctx)->fail_cuda(e__, "cudaStreamSynchronize"); (ctx)->quiescent = true; } while (0)

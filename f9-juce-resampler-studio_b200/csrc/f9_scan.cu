@@ -1,0 +1,418 @@
+// Reductions of the detection / trimming path: |x| argmax with the reference's tie-breaking, RMS / peak
+// window statistics, the offline reverb-tail scan and the bounded-lag cross-correlation.
+// All are HBM-bound streaming reads (4 B per sample); the work is warp-shuffle + block reductions.
+#include "f9_internal.cuh"
+
+namespace f9 {
+
+namespace {
+
+constexpr int kPeakThreads = 256;
+constexpr int kPeakChunk = 16384;          // frames per CTA (64 KB of input)
+
+__device__ __forceinline__ bool peak_better(float v, int ch, int pos, float bv, int bch, int bpos) {
+    // order of MainComponent::findPeakPosition (Source/MainComponent.cpp:950-975): strict '>' while scanning
+    // channel 0 first => larger value wins, ties go to the lower channel, then the earlier frame.
+    if (v > bv) return true;
+    if (v < bv) return false;
+    if (ch != bch) return ch < bch;
+    return pos < bpos;
+}
+
+// ---- stage 1: one CTA per (buffer, channel, chunk) ---------------------------------------------------
+__global__ void __launch_bounds__(kPeakThreads)
+peak_partial_kernel(const DevBuf* __restrict__ bufs, const int* __restrict__ prefix, int n, PeakPartial* __restrict__ partials) {
+    // locate the buffer of this CTA: prefix[b] <= blockIdx.x < prefix[b+1]
+    int lo = 0, hi = n;
+    const int bid = blockIdx.x;
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (prefix[mid] <= bid) lo = mid; else hi = mid; }
+    const DevBuf B = bufs[lo];
+    const int local = bid - prefix[lo];
+    const int chunksPerCh = (B.numFrames + kPeakChunk - 1) / kPeakChunk;
+    const int ch = local / chunksPerCh;
+    const int chunk = local - ch * chunksPerCh;
+    const int start = chunk * kPeakChunk;
+    const int len = min(kPeakChunk, B.numFrames - start);
+    const float* __restrict__ x = B.base + (long long) ch * B.chStride + start;
+
+    float bv = 0.0f; int bpos = -1;
+    // head to 16-byte alignment, float4 body, scalar tail; each thread visits increasing indices so a strict
+    // '>' keeps its earliest maximum.
+    const int mis = (int) ((reinterpret_cast<uintptr_t>(x) >> 2) & 3);
+    const int head = min(len, (4 - mis) & 3);
+    if ((int) threadIdx.x < head) {
+        float a = fabsf(x[threadIdx.x]);
+        if (a > bv) { bv = a; bpos = threadIdx.x; }
+    }
+    const int nvec = (len - head) >> 2;
+    const float4* __restrict__ xv = reinterpret_cast<const float4*>(x + head);
+    #pragma unroll 4
+    for (int i = threadIdx.x; i < nvec; i += kPeakThreads) {
+        const float4 v = __ldg(xv + i);
+        const int p = head + 4 * i;
+        float a;
+        a = fabsf(v.x); if (a > bv) { bv = a; bpos = p; }
+        a = fabsf(v.y); if (a > bv) { bv = a; bpos = p + 1; }
+        a = fabsf(v.z); if (a > bv) { bv = a; bpos = p + 2; }
+        a = fabsf(v.w); if (a > bv) { bv = a; bpos = p + 3; }
+    }
+    const int tail0 = head + 4 * nvec;
+    if (tail0 + (int) threadIdx.x < len) {
+        // tail indices are larger than everything in the body: strict '>' again keeps the earliest
+        float a = fabsf(x[tail0 + threadIdx.x]);
+        if (a > bv) { bv = a; bpos = tail0 + threadIdx.x; }
+    }
+    // a thread's head index is smaller than its body indices only for threads < head; handled by ordering above.
+
+    // warp reduce (value desc, position asc; -1 = none, loses to any real position with equal value only when v == 0)
+    unsigned bposu = (bpos < 0) ? 0x7fffffffu : (unsigned) bpos;
+    #pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+        const unsigned op = __shfl_xor_sync(0xffffffffu, bposu, off);
+        if (ov > bv || (ov == bv && op < bposu)) { bv = ov; bposu = op; }
+    }
+    __shared__ float sv[kPeakThreads / 32];
+    __shared__ unsigned sp[kPeakThreads / 32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { sv[warp] = bv; sp[warp] = bposu; }
+    __syncthreads();
+    if (warp == 0) {
+        bv = (lane < kPeakThreads / 32) ? sv[lane] : 0.0f;
+        bposu = (lane < kPeakThreads / 32) ? sp[lane] : 0x7fffffffu;
+        #pragma unroll
+        for (int off = 4; off > 0; off >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+            const unsigned op = __shfl_xor_sync(0xffffffffu, bposu, off);
+            if (ov > bv || (ov == bv && op < bposu)) { bv = ov; bposu = op; }
+        }
+        if (lane == 0) {
+            PeakPartial r;
+            r.v = bv; r.ch = ch;
+            r.pos = (bposu == 0x7fffffffu || bv == 0.0f) ? -1 : (int) bposu + start;
+            partials[bid] = r;
+        }
+    }
+}
+
+// ---- stage 2: one CTA per buffer folds its partials in scan order ----------------------------------
+__global__ void __launch_bounds__(128)
+peak_final_kernel(const PeakPartial* __restrict__ partials, const int* __restrict__ prefix, float threshold, int* __restrict__ out_pos) {
+    const int b = blockIdx.x;
+    const int p0 = prefix[b], p1 = prefix[b + 1];
+    float bv = 0.0f; int bch = 0x7fffffff, bpos = 0x7fffffff;
+    for (int i = p0 + threadIdx.x; i < p1; i += blockDim.x) {
+        const PeakPartial r = partials[i];
+        if (r.pos >= 0 && peak_better(r.v, r.ch, r.pos, bv, bch, bpos)) { bv = r.v; bch = r.ch; bpos = r.pos; }
+    }
+    #pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+        const int oc = __shfl_xor_sync(0xffffffffu, bch, off);
+        const int op = __shfl_xor_sync(0xffffffffu, bpos, off);
+        if (peak_better(ov, oc, op, bv, bch, bpos)) { bv = ov; bch = oc; bpos = op; }
+    }
+    __shared__ float sv[4]; __shared__ int sc[4], sp[4];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { sv[warp] = bv; sc[warp] = bch; sp[warp] = bpos; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int) blockDim.x / 32; ++w)
+            if (peak_better(sv[w], sc[w], sp[w], bv, bch, bpos)) { bv = sv[w]; bch = sc[w]; bpos = sp[w]; }
+        out_pos[b] = (bv > threshold && bpos != 0x7fffffff) ? bpos : -1;
+    }
+}
+
+// ---- per-buffer sum of squares (double) + peak -----------------------------------------------------
+// calculateRMS (Source/MainComponent.cpp:983-1004): float product, widened, double sum.  The tree order here
+// differs from the sequential reference; callers that need the reference's decision bit for bit use the
+// guard band in tail_window_kernel.
+constexpr int kStatThreads = 256;
+
+__device__ __forceinline__ void block_sum_max(double& s, float& m, double* sh_s, float* sh_m) {
+    #pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, off);
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { sh_s[warp] = s; sh_m[warp] = m; }
+    __syncthreads();
+    if (warp == 0) {
+        const int nw = blockDim.x >> 5;
+        s = (lane < nw) ? sh_s[lane] : 0.0;
+        m = (lane < nw) ? sh_m[lane] : 0.0f;
+        #pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, off);
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+        }
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void accum_range(const float* __restrict__ x, int len, double& s, float& m) {
+    // float product rounded to float (no contraction), widened, accumulated in double
+    const int mis = (int) ((reinterpret_cast<uintptr_t>(x) >> 2) & 3);
+    const int head = min(len, (4 - mis) & 3);
+    if ((int) threadIdx.x < head) { const float v = x[threadIdx.x]; s += (double) __fmul_rn(v, v); m = fmaxf(m, fabsf(v)); }
+    const int nvec = (len - head) >> 2;
+    const float4* __restrict__ xv = reinterpret_cast<const float4*>(x + head);
+    #pragma unroll 4
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+        const float4 v = __ldg(xv + i);
+        s += (double) __fmul_rn(v.x, v.x); s += (double) __fmul_rn(v.y, v.y);
+        s += (double) __fmul_rn(v.z, v.z); s += (double) __fmul_rn(v.w, v.w);
+        m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    }
+    const int tail0 = head + 4 * nvec;
+    if (tail0 + (int) threadIdx.x < len) { const float v = x[tail0 + threadIdx.x]; s += (double) __fmul_rn(v, v); m = fmaxf(m, fabsf(v)); }
+}
+
+constexpr int kStatChunk = 32768;
+constexpr int kStatPartials = kStatPartialsPerBuf;
+
+// grid: (chunks, n).  Partial sums are combined with double atomics?  No: order must be deterministic, so
+// stage 1 writes per-chunk partials and stage 2 folds them in index order.
+__global__ void __launch_bounds__(kStatThreads)
+stats_partial_kernel(const DevBuf* __restrict__ bufs, double* __restrict__ psum, float* __restrict__ pmax, int maxChunks) {
+    const DevBuf B = bufs[blockIdx.y];
+    const long long total = (long long) B.numCh * B.numFrames;   // channel-major linear index
+    const int chunksPerCh = (B.numFrames + kStatChunk - 1) / kStatChunk;
+    const int nChunks = chunksPerCh * B.numCh;
+    (void) total;
+    double s = 0.0; float m = 0.0f;
+    __shared__ double sh_s[kStatThreads / 32]; __shared__ float sh_m[kStatThreads / 32];
+    for (int c = blockIdx.x; c < nChunks; c += gridDim.x) {
+        const int ch = c / chunksPerCh, k = c - ch * chunksPerCh;
+        const int start = k * kStatChunk, len = min(kStatChunk, B.numFrames - start);
+        accum_range(B.base + (long long) ch * B.chStride + start, len, s, m);
+    }
+    block_sum_max(s, m, sh_s, sh_m);
+    if (threadIdx.x == 0) {
+        psum[(size_t) blockIdx.y * maxChunks + blockIdx.x] = s;
+        pmax[(size_t) blockIdx.y * maxChunks + blockIdx.x] = m;
+    }
+}
+__global__ void stats_final_kernel(const double* __restrict__ psum, const float* __restrict__ pmax, int maxChunks,
+                                   double* __restrict__ sumsq, float* __restrict__ peak, int n) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n) return;
+    double s = 0.0; float m = 0.0f;
+    for (int i = 0; i < maxChunks; ++i) { s += psum[(size_t) b * maxChunks + i]; m = fmaxf(m, pmax[(size_t) b * maxChunks + i]); }
+    sumsq[b] = s; peak[b] = m;
+}
+
+// ---- reverb-tail windows ------------------------------------------------------------------------------
+// One CTA per (poll, buffer).  Poll i tests frames [e-window, e), e = start + (i+1)*hop
+// (AudioProcessingService.swift:436-446).  Writes flag -1 skipped / 0 / 1.
+__global__ void __launch_bounds__(kStatThreads)
+tail_window_kernel(const DevBuf* __restrict__ bufs, const TailParams* __restrict__ params, int max_polls, int* __restrict__ flags) {
+    const int b = blockIdx.y, i = blockIdx.x;
+    const DevBuf B = bufs[b];
+    const TailParams P = params[b];
+    const long long e = P.startFrame + (long long) (i + 1) * P.hop;
+    if (e > B.numFrames) return;                       // past the data: no such poll (flag stays -2)
+    int* out = flags + (size_t) b * max_polls + i;
+    if (e < P.window) { if (threadIdx.x == 0) *out = -1; return; }
+    double s = 0.0; float m = 0.0f;
+    __shared__ double sh_s[kStatThreads / 32]; __shared__ float sh_m[kStatThreads / 32];
+    for (int c = 0; c < B.numCh; ++c)
+        accum_range(B.base + (long long) c * B.chStride + (e - P.window), P.window, s, m);
+    block_sum_max(s, m, sh_s, sh_m);
+    if (threadIdx.x != 0) return;
+    int below;
+    if (P.mode == F9_TAIL_PEAK) {
+        // Swift predicate (AudioProcessingService.swift:710-737); the max is order independent => exact.
+        if (P.noNf) below = m < 0.0001f;
+        else below = (m == 0.0f) ? P.below0 : (m <= P.rstar);
+    } else {
+        // C++ predicate (Source/MainComponent.cpp:863-882) folded to the linear domain on the host:
+        // below <=> rms <= rstar.  rms from the tree sum can differ from the sequential reference by one float
+        // ulp only when it lands next to rstar; those windows are re-summed in the reference's order.
+        const long long count = (long long) B.numCh * P.window;
+        float rms = (float) sqrt(s / (double) count);
+        const float up = __int_as_float(__float_as_int(P.rstar) + 1);
+        if (P.rstar >= 0.0f && (rms == P.rstar || rms == up)) {
+            double ss = 0.0;
+            for (int c = 0; c < B.numCh; ++c) {
+                const float* x = B.base + (long long) c * B.chStride + (e - P.window);
+                for (int k = 0; k < P.window; ++k) ss = __dadd_rn(ss, (double) __fmul_rn(x[k], x[k]));
+            }
+            rms = (float) sqrt(ss / (double) count);
+        }
+        below = (P.rstar >= 0.0f) && (rms <= P.rstar);
+    }
+    *out = below;
+}
+
+// One thread per buffer walks its flags: `required` consecutive silent polls => stop frame.
+__global__ void tail_runs_kernel(const DevBuf* __restrict__ bufs, const TailParams* __restrict__ params, int n, int max_polls,
+                                 const int* __restrict__ flags, long long* __restrict__ stop) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n) return;
+    const TailParams P = params[b];
+    const DevBuf B = bufs[b];
+    int consecutive = 0; long long st = -1;
+    for (int i = 0; i < max_polls; ++i) {
+        const long long e = P.startFrame + (long long) (i + 1) * P.hop;
+        if (e > B.numFrames) break;
+        const int f = flags[(size_t) b * max_polls + i];
+        if (f < 0) continue;                              // skipped poll leaves the counter alone
+        consecutive = f ? consecutive + 1 : 0;
+        if (consecutive >= P.required) { st = e; break; }
+    }
+    stop[b] = st;
+}
+
+__global__ void fill_int_kernel(int* p, size_t n, int v) {
+    for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) p[i] = v;
+}
+
+// ---- bounded-lag cross-correlation -----------------------------------------------------------------
+// r_c[lag] = sum_i (double) x[i] * (double) y_c[i+lag], i ascending.  The float*float product is exact in
+// double and fma(x, y, acc) rounds once, so a thread that walks i in order reproduces the sequential CPU
+// sum bit for bit; the argmax below then needs no guard band.  One thread per lag, one CTA per
+// (buffer, channel, tile of kXcLags lags); y staged through shared memory in stimulus-sized chunks.
+constexpr int kXcLags = 256;
+constexpr int kXcChunk = 512;
+
+__device__ __forceinline__ bool xc_better(double v, int ch, int lag, double bv, int bch, int blag) {
+    if (v > bv) return true;
+    if (v < bv) return false;
+    if (ch != bch) return ch < bch;
+    return lag < blag;
+}
+
+__global__ void __launch_bounds__(kXcLags)
+xcorr_partial_kernel(const DevBuf* __restrict__ bufs, const int* __restrict__ prefix, int n,
+                     const float* __restrict__ stim, int stimLen, int lagMin, int lagMax, XcPartial* __restrict__ partials) {
+    int lo = 0, hi = n;
+    const int bid = blockIdx.x;
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (prefix[mid] <= bid) lo = mid; else hi = mid; }
+    const DevBuf B = bufs[lo];
+    const int local = bid - prefix[lo];
+    const int nLags = lagMax - lagMin + 1;
+    const int tiles = (nLags + kXcLags - 1) / kXcLags;
+    const int ch = local / tiles, tile = local - ch * tiles;
+    const int lag0 = lagMin + tile * kXcLags;
+    const int lag = lag0 + threadIdx.x;
+    const float* __restrict__ y = B.base + (long long) ch * B.chStride;
+
+    __shared__ float xs[kXcChunk];
+    __shared__ float ys[kXcChunk + kXcLags];
+    double acc = 0.0;
+    for (int c0 = 0; c0 < stimLen; c0 += kXcChunk) {
+        const int clen = min(kXcChunk, stimLen - c0);
+        for (int i = threadIdx.x; i < clen; i += kXcLags) xs[i] = stim[c0 + i];
+        for (int i = threadIdx.x; i < clen + kXcLags; i += kXcLags) {
+            const long long g = (long long) c0 + lag0 + i;
+            ys[i] = (g >= 0 && g < B.numFrames) ? y[g] : 0.0f;
+        }
+        __syncthreads();
+        #pragma unroll 4
+        for (int i = 0; i < clen; ++i) acc = fma((double) xs[i], (double) ys[i + threadIdx.x], acc);
+        __syncthreads();
+    }
+    double v = (lag <= lagMax) ? fabs(acc) : -1.0;
+    int blag = lag;
+    #pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, v, off);
+        const int ol = __shfl_xor_sync(0xffffffffu, blag, off);
+        if (ov > v || (ov == v && ol < blag)) { v = ov; blag = ol; }
+    }
+    __shared__ double sv[kXcLags / 32]; __shared__ int sl[kXcLags / 32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { sv[warp] = v; sl[warp] = blag; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < kXcLags / 32; ++w) if (sv[w] > v || (sv[w] == v && sl[w] < blag)) { v = sv[w]; blag = sl[w]; }
+        XcPartial r; r.v = v; r.ch = ch; r.lag = blag; r.pad = 0;
+        partials[bid] = r;
+    }
+}
+
+__global__ void xcorr_final_kernel(const XcPartial* __restrict__ partials, const int* __restrict__ prefix, int n, XcPartial* __restrict__ best) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n) return;
+    // "maxValue starts at 0, strict >": a candidate must be > 0 to register (bch = -1 otherwise)
+    double bv = 0.0; int bch = -1, blag = 0;
+    for (int i = prefix[b]; i < prefix[b + 1]; ++i) {
+        const XcPartial r = partials[i];
+        if (r.v > 0.0 && (bch < 0 || xc_better(r.v, r.ch, r.lag, bv, bch, blag))) { bv = r.v; bch = r.ch; blag = r.lag; }
+    }
+    XcPartial o; o.v = bv; o.ch = bch; o.lag = blag; o.pad = 0;
+    best[b] = o;
+}
+
+}  // namespace
+
+// =============================================================================================== launchers
+int peak_prefix(const DevBuf* h_bufs, int n, std::vector<int>* prefix) {
+    prefix->assign((size_t) n + 1, 0);
+    for (int i = 0; i < n; ++i) {
+        const int chunks = (h_bufs[i].numFrames + kPeakChunk - 1) / kPeakChunk;
+        (*prefix)[(size_t) i + 1] = (*prefix)[(size_t) i] + chunks * h_bufs[i].numCh;
+    }
+    return (*prefix)[(size_t) n];
+}
+
+cudaError_t launch_find_peak(const DevBuf* d_bufs, int n, int total_ctas, const int* d_prefix, float threshold,
+                             PeakPartial* d_partials, int* d_out_pos, cudaStream_t s, long long* launches) {
+    if (n <= 0) return cudaSuccess;
+    if (total_ctas > 0) {
+        peak_partial_kernel<<<total_ctas, kPeakThreads, 0, s>>>(d_bufs, d_prefix, n, d_partials);
+        ++*launches;
+    }
+    peak_final_kernel<<<n, 128, 0, s>>>(d_partials, d_prefix, threshold, d_out_pos);
+    ++*launches;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_stats(const DevBuf* d_bufs, int n, double* d_psum, float* d_pmax,
+                         double* d_sumsq, float* d_peak, cudaStream_t s, long long* launches) {
+    if (n <= 0) return cudaSuccess;
+    dim3 grid(kStatPartials, n);
+    stats_partial_kernel<<<grid, kStatThreads, 0, s>>>(d_bufs, d_psum, d_pmax, kStatPartials);
+    ++*launches;
+    stats_final_kernel<<<(n + 127) / 128, 128, 0, s>>>(d_psum, d_pmax, kStatPartials, d_sumsq, d_peak, n);
+    ++*launches;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_tail_scan(const DevBuf* d_bufs, const TailParams* d_params, int n, int max_polls,
+                             long long* d_stop, int* d_flags, cudaStream_t s, long long* launches) {
+    if (n <= 0) return cudaSuccess;
+    if (max_polls > 0) {
+        fill_int_kernel<<<256, 256, 0, s>>>(d_flags, (size_t) n * max_polls, -2);
+        ++*launches;
+        dim3 grid(max_polls, n);
+        tail_window_kernel<<<grid, kStatThreads, 0, s>>>(d_bufs, d_params, max_polls, d_flags);
+        ++*launches;
+    }
+    tail_runs_kernel<<<(n + 127) / 128, 128, 0, s>>>(d_bufs, d_params, n, max_polls, d_flags, d_stop);
+    ++*launches;
+    return cudaGetLastError();
+}
+
+int xcorr_prefix(const DevBuf* h_bufs, int n, int lagMin, int lagMax, std::vector<int>* prefix) {
+    const int tiles = (lagMax - lagMin + 1 + kXcLags - 1) / kXcLags;
+    prefix->assign((size_t) n + 1, 0);
+    for (int i = 0; i < n; ++i) (*prefix)[(size_t) i + 1] = (*prefix)[(size_t) i] + tiles * h_bufs[i].numCh;
+    return (*prefix)[(size_t) n];
+}
+
+cudaError_t launch_xcorr(const DevBuf* d_bufs, int n, int total_ctas, const int* d_prefix, const float* d_stim, int stimLen,
+                         int lagMin, int lagMax, XcPartial* d_partials, XcPartial* d_best, cudaStream_t s, long long* launches) {
+    if (n <= 0) return cudaSuccess;
+    if (total_ctas > 0) {
+        xcorr_partial_kernel<<<total_ctas, kXcLags, 0, s>>>(d_bufs, d_prefix, n, d_stim, stimLen, lagMin, lagMax, d_partials);
+        ++*launches;
+    }
+    xcorr_final_kernel<<<(n + 127) / 128, 128, 0, s>>>(d_partials, d_prefix, n, d_best);
+    ++*launches;
+    return cudaGetLastError();
+}
+
+}  // namespace f9

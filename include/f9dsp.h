@@ -1,0 +1,284 @@
+/* =============================================================================
+ * f9dsp.h -- C ABI of the B200-native DSP path of F9 Batch Resampler.
+ *
+ * This is the drop-in boundary.  Plain C: pointers, sizes, POD
+ * structs, int status codes; no C++ exceptions, no torch types.  The reference is
+ * a single-process JUCE/C++ app whose DSP helpers are private members of
+ * MainComponent called on the message thread; every entry point below names the
+ * reference interface it replaces (paths relative to the reference checkout).
+ *
+ * Threading: one f9_context per host thread / GPU.  A context is not thread-safe;
+ * the library is re-entrant across contexts.  Calls block until the result is in
+ * the caller's buffers unless the name ends in _async or takes device pointers
+ * (section F), which only enqueue on the context's stream.
+ *
+ * Ownership: the caller owns and allocates every input and output buffer.  The
+ * library never frees caller memory.  Handles are opaque.
+ *
+ * There is NO CPU fallback: every compute entry point runs CUDA kernels built for
+ * sm_100a and fails with F9_ERR_NO_DEVICE / F9_ERR_CUDA when it cannot.
+ * ============================================================================= */
+#ifndef F9DSP_H
+#define F9DSP_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define F9_API __attribute__((visibility("default")))
+#else
+#define F9_API
+#endif
+
+#define F9_VERSION_MAJOR 0
+#define F9_VERSION_MINOR 1
+
+/* ---- status codes (reference: sentinels + log lines, Source/MainComponent.cpp:974, :777-782;
+ *      Swift typed errors AudioProcessingService.swift:16-52) ---------------------------- */
+enum {
+    F9_OK              = 0,
+    F9_ERR_INVALID     = -1,  /* bad argument                                   */
+    F9_ERR_CUDA        = -2,  /* a CUDA call failed; see f9_last_error          */
+    F9_ERR_NOMEM       = -3,  /* host or device allocation failed               */
+    F9_ERR_NO_DEVICE   = -4,  /* no usable sm_100 device                        */
+    F9_ERR_UNSUPPORTED = -5   /* valid request this build does not implement    */
+};
+
+/* interpolator kinds: juce::Interpolators::{WindowedSinc, Lagrange, CatmullRom, Linear, ZeroOrderHold}
+ * (JUCE 8.0.10 juce_audio_basics/utilities/juce_Interpolators.h; linked by the reference at
+ * JuceLibraryCode/JuceHeader.h:16) */
+enum { F9_WINDOWED_SINC = 0, F9_LAGRANGE = 1, F9_CATMULL_ROM = 2, F9_LINEAR = 3, F9_ZERO_ORDER_HOLD = 4 };
+
+/* PCM sample formats of the deinterleave / format-convert stage (JUCE AudioFormatReader::read at
+ * Source/MainComponent.cpp:734-739; 24-bit writer at :784-801) */
+enum { F9_PCM_U8 = 1, F9_PCM_S16LE = 2, F9_PCM_S24LE = 3, F9_PCM_S32LE = 4, F9_PCM_F32LE = 5 };
+
+/* tail-silence predicate: C++ RMS form (Source/MainComponent.cpp:863-882) or Swift peak form
+ * (AudioProcessingService.swift:710-737) */
+enum { F9_TAIL_RMS = 0, F9_TAIL_PEAK = 1 };
+
+typedef struct f9_context f9_context;
+typedef struct f9_interp  f9_interp;
+typedef struct f9_plan    f9_plan;
+
+/* =============================== A. context ================================== */
+/* device: CUDA ordinal.  Fails with F9_ERR_NO_DEVICE when there is no GPU. */
+F9_API int  f9_context_create(int device, f9_context** out);
+F9_API void f9_context_destroy(f9_context* ctx);
+/* Human-readable text of the last failure on this context (ctx may be NULL for creation errors). */
+F9_API const char* f9_last_error(const f9_context* ctx);
+/* Run on a caller-owned CUDA stream (a cudaStream_t, e.g. torch's current stream); NULL restores
+ * the context's own stream. */
+F9_API int  f9_set_stream(f9_context* ctx, void* cuda_stream);
+F9_API int  f9_synchronize(f9_context* ctx);
+/* Kernels launched by this context since creation (bench.py's gpu_launches claim). */
+F9_API long long f9_launch_count(const f9_context* ctx);
+/* Pinned host memory for full-speed H2D/D2H of caller buffers (optional; any host pointer works). */
+F9_API int  f9_host_alloc(f9_context* ctx, void** out, size_t bytes);
+F9_API int  f9_host_free(f9_context* ctx, void* p);
+F9_API int  f9_version(void);                 /* major*100 + minor */
+F9_API int  f9_device_count(void);            /* 0 when there is no usable device; never fails */
+
+/* ============================ B. settings math =============================== */
+/* Host scalars; mirror ProcessingSettings (Source/AppState.h:183-259). */
+F9_API int    f9_recording_length(int source_frames, int latency_frames);              /* AppState.h:240-243 */
+F9_API float  f9_noise_floor_threshold_db(int has_nf, float nf_db, float margin_pct);  /* AppState.h:252-258 */
+F9_API float  f9_threshold_linear(float threshold_db);                                 /* AppState.h:246-249 */
+F9_API double f9_latency_ms(int measured_latency_samples, double sample_rate);         /* AppState.h:231-237 */
+F9_API int    f9_needs_latency_remeasurement(int measured_latency_samples,
+                                             int last_buffer_size, int buffer_size);   /* AppState.h:221-228 */
+
+/* ============== C. reference-shaped helpers on HOST planar buffers =========== */
+/* `ch` = numCh pointers to numFrames float32 each (juce::AudioBuffer<float> read pointers). */
+
+/* MainComponent::findPeakPosition, Source/MainComponent.cpp:950-975.  *out_pos = frame index of the
+ * first maximum of |x| in channel-major scan order, or -1 when max <= threshold. */
+F9_API int f9_find_peak_position(f9_context* ctx, const float* const* ch, int numCh, int numFrames,
+                                 float threshold, int* out_pos);
+/* Swift analyzeCapturedAudio, LatencyMeasurementService.swift:147-171 (interleaved index, default 0;
+ * *out_found = 0 where Swift throws noImpulseDetected). */
+F9_API int f9_find_peak_interleaved(f9_context* ctx, const float* audio, long long n, float threshold,
+                                    long long* out_index, int* out_found);
+/* MainComponent::calculateRMS, Source/MainComponent.cpp:983-1004. */
+F9_API int f9_calculate_rms(f9_context* ctx, const float* const* ch, int numCh, int numFrames, float* out_rms);
+/* MainComponent::calculateNoiseFloorDb, Source/MainComponent.cpp:977-981. */
+F9_API int f9_calculate_noise_floor_db(f9_context* ctx, const float* const* ch, int numCh, int numFrames,
+                                       float* out_db);
+/* MainComponent::isReverbTailBelowNoiseFloor, Source/MainComponent.cpp:863-882 (threshold from
+ * AppState.h:252-258). */
+F9_API int f9_is_reverb_tail_below_noise_floor(f9_context* ctx, const float* const* ch, int numCh, int numFrames,
+                                               int has_nf, float nf_db, float margin_pct, int* out_below);
+/* Swift isReverbTailBelowNoiseFloor, AudioProcessingService.swift:710-737 (peak based, interleaved). */
+F9_API int f9_is_reverb_tail_below_noise_floor_swift(f9_context* ctx, const float* window, long long n,
+                                                     int has_nf, float nf_db, float margin_pct, int* out_below);
+/* MainComponent::trimLatency, Source/MainComponent.cpp:824-861.  latency_samples is INTERLEAVED samples
+ * (:828); out = numCh x original_length, zero padded; *out_copied = frames actually copied. */
+F9_API int f9_trim_latency(f9_context* ctx, const float* const* captured, int numCh, int captured_frames,
+                           int latency_samples, int original_length, float* const* out, int* out_copied);
+/* Swift trimLatency, AudioProcessingService.swift:681-703 (interleaved, no padding).  out must hold
+ * source_frames*channels floats; *out_count = samples written. */
+F9_API int f9_trim_latency_swift(f9_context* ctx, const float* captured, long long count, long long latency_samples,
+                                 long long source_frames, int channels, float* out, long long* out_count);
+/* MainComponent::removeDCOffset, Source/MainComponent.cpp:884-902 (in place).  Tolerance parity only:
+ * the reference accumulates the mean sequentially in float. */
+F9_API int f9_remove_dc_offset(f9_context* ctx, float* const* ch, int numCh, int numFrames);
+
+/* Offline form of the reverb-mode stop loop (Swift AudioProcessingService.swift:423-453; C++ intent
+ * claude.md:346-367).  Poll i tests the last `window` frames before e_i = start_frame + (i+1)*hop;
+ * the first poll that makes `required` consecutive silent polls gives *out_stop_frame = e_i (else -1).
+ * flags (optional, capacity max_flags) receives -1 skipped / 0 / 1 per poll; *out_polls the poll count. */
+F9_API int f9_tail_scan(f9_context* ctx, const float* const* ch, int numCh, long long numFrames,
+                        long long start_frame, int window, int hop, int required, int mode,
+                        int has_nf, float nf_db, float margin_pct,
+                        long long* out_stop_frame, int* flags, int max_flags, int* out_polls);
+
+/* Bounded-lag cross-correlation with argmax (north_star (b); the reference peak-picks an impulse,
+ * LatencyMeasurementService.swift:164).  r_c[lag] = sum_i x[i]*y_c[i+lag] over lag in [lag_min, lag_max],
+ * scan order channel-major / lag ascending, strict '>' on |r| (ties keep the earliest lag of the lowest
+ * channel, as findPeakPosition).  *out_found = max|r| > threshold*||x||_2. */
+F9_API int f9_xcorr_peak(f9_context* ctx, const float* const* y, int numCh, int numFrames,
+                         const float* x, int stim_len, int lag_min, int lag_max, float threshold,
+                         int* out_found, int* out_lag, int* out_ch, double* out_value);
+
+/* ============ D. juce::Interpolators-shaped stateful objects ================ */
+/* [JUCE 8.0.10 juce_GenericInterpolator.h]  One object per channel, as JUCE.  State (the last
+ * memorySize inputs and the sub-sample position) lives on the host; each process() runs the FIR on
+ * the GPU.  `in` must hold at least the returned number of samples. */
+F9_API int   f9_interp_create(f9_context* ctx, int kind, f9_interp** out);
+F9_API void  f9_interp_destroy(f9_interp* h);
+F9_API int   f9_interp_reset(f9_interp* h);                                     /* reset()          */
+F9_API float f9_interp_base_latency(const f9_interp* h);                        /* getBaseLatency() */
+/* int process(double speedRatio, const float* in, float* out, int numOut) -> inputs consumed (<0: error) */
+F9_API int   f9_interp_process(f9_interp* h, double speed_ratio, const float* in, float* out, int num_out);
+/* processAdding(..., gain) */
+F9_API int   f9_interp_process_adding(f9_interp* h, double speed_ratio, const float* in, float* out,
+                                      int num_out, float gain);
+/* process(..., numInputSamplesAvailable, wrapAround) */
+F9_API int   f9_interp_process_wrap(f9_interp* h, double speed_ratio, const float* in, float* out,
+                                    int num_out, int num_in_available, int wrap_around);
+/* WindowedSincTraits::lookupTable[10001].  JUCE's literal table is not in the reference; the built-in
+ * default is sinc*Hann.  A host that has JUCE can install the real table here. */
+F9_API int   f9_sinc_table_set(f9_context* ctx, const float* table10001);
+F9_API int   f9_sinc_table_get(const f9_context* ctx, float* table10001);
+
+/* ======================= E. batch job flow (host buffers) =================== */
+/* One job = one file of the MainComponent/AppState batch flow (Source/MainComponent.cpp:705-805;
+ * Swift processFiles AudioProcessingService.swift:66-113, :339-536): captured recording ->
+ * [tail-silence scan] -> trimLatency -> [removeDCOffset] -> [sample-rate conversion] -> planar float
+ * (and optionally interleaved 24-bit PCM, the WAV payload). */
+typedef struct f9_job {
+    const float* const* captured;   /* numCh planar channels, captured_frames each (host)          */
+    int   numCh;
+    int   captured_frames;
+    int   latency_samples;          /* interleaved samples, as measuredLatencySamples (AppState.h:197) */
+    int   original_length;          /* source length in frames (trimLatency's originalLength)       */
+    double fs_in, fs_out;           /* conversion ratio = fs_in / fs_out; equal => no conversion     */
+    int   interp_kind;              /* F9_WINDOWED_SINC / F9_LAGRANGE / ...                          */
+    int   flags;                    /* F9_JOB_* below                                               */
+    /* tail scan (used when F9_JOB_TAIL_SCAN): */
+    int   tail_window, tail_hop, tail_required, tail_mode;
+    int   has_nf; float nf_db; float margin_pct;
+    /* outputs (caller-allocated): */
+    float* const* out;              /* numCh channels, out_capacity frames each                     */
+    int   out_capacity;
+    unsigned char* out_pcm24;       /* optional: numCh*out_frames*3 bytes interleaved, or NULL      */
+} f9_job;
+
+enum { F9_JOB_TAIL_SCAN = 1, F9_JOB_REMOVE_DC = 2, F9_JOB_PCM24 = 4 };
+
+typedef struct f9_result {
+    int status;                     /* F9_OK or an error for this job                               */
+    int latency_frames;             /* latency_samples / numCh (MainComponent.cpp:835)              */
+    int trim_start;                 /* first captured frame used                                    */
+    int frames_copied;              /* frames taken from the capture (rest of original_length is 0) */
+    int out_frames;                 /* frames written per output channel                            */
+    long long tail_stop_frame;      /* stop frame of the tail scan, -1 none / not requested         */
+    int tail_polls;
+} f9_result;
+
+/* Output length of a conversion of n_in frames: ceil(n_in * fs_out / fs_in) in exact integers. */
+F9_API long long f9_resampled_length(long long n_in, double fs_in, double fs_out);
+F9_API int f9_process_batch(f9_context* ctx, const f9_job* jobs, int n_jobs, f9_result* results);
+
+/* ============== F. device-resident entry points (pointers in HBM) =========== */
+/* Same operations on buffers that already live on the device; they enqueue on the context's stream
+ * and return without synchronising.  Used for pipelining, for sharding one batch over several GPUs
+ * (one context per GPU) and by bench.py's HBM-resident leg. */
+typedef struct f9_dev_buffer {      /* planar float32 on the device                                 */
+    const float* base;              /* channel c starts at base + c*ch_stride                       */
+    long long ch_stride;            /* in floats                                                    */
+    int numCh;
+    int numFrames;
+} f9_dev_buffer;
+
+/* batched findPeakPosition: d_out_pos[i] (device int) for each buffer */
+F9_API int f9_dev_find_peak_batch(f9_context* ctx, const f9_dev_buffer* bufs, int n, float threshold, int* d_out_pos);
+/* batched sum of squares (double) and peak per buffer: d_sumsq[i], d_peak[i] (device) */
+F9_API int f9_dev_stats_batch(f9_context* ctx, const f9_dev_buffer* bufs, int n, double* d_sumsq, float* d_peak);
+
+/* batched bounded-lag cross-correlation argmax against one stimulus (device float array):
+ * d_out[i] = { max |r|, channel (-1: all zero), lag } per buffer; the threshold test
+ * (value > threshold*||x||_2) is the caller's scalar. */
+typedef struct f9_xcorr_result { double value; int ch; int lag; int reserved; } f9_xcorr_result;
+F9_API int f9_dev_xcorr_peak_batch(f9_context* ctx, const f9_dev_buffer* bufs, int n, const float* d_stim,
+                                   int stim_len, int lag_min, int lag_max, f9_xcorr_result* d_out);
+
+/* One channel-segment of a sample-rate conversion.  Output samples [n0, n0+num_out) of the conversion
+ * of a channel from reset state are written to out[0..num_out).  in[0] is sample `in_offset` of the
+ * channel and in_avail samples are present; samples outside [in_offset, in_offset+in_avail) read as 0
+ * (before 0: interpolator reset state; after the end: the 6-argument process() pushes zeros).
+ * Time-segmenting a long file = several segments with different n0 whose `in` windows overlap by the
+ * interpolator memory (halo 199 for WindowedSinc, 4 for Lagrange). */
+typedef struct f9_resample_seg {
+    const float* in;   long long in_offset; long long in_avail;
+    float* out;        long long n0;        long long num_out;
+} f9_resample_seg;
+
+/* Build a reusable plan: segment table + per-ratio polyphase tables uploaded once. */
+F9_API int  f9_resample_plan_create(f9_context* ctx, int kind, double speed_ratio,
+                                    const f9_resample_seg* segs, int n_segs, f9_plan** out);
+F9_API int  f9_resample_plan_run(f9_plan* plan);          /* enqueue; no sync */
+F9_API void f9_plan_destroy(f9_plan* plan);
+/* Input halo a segment starting at output n0 needs before its first fresh input, and the index of
+ * the first input sample it touches (for host-side segmentation across GPUs). */
+F9_API int  f9_resample_segment_input_range(int kind, double speed_ratio, long long n0, long long num_out,
+                                            long long* first_in, long long* last_in_plus1);
+
+/* Tail-scan plan over device buffers: d_stop_frame[i] (device long long), d_flags optional
+ * (n * max_polls ints). */
+typedef struct f9_tail_params {
+    long long start_frame; int window, hop, required, mode; int has_nf; float nf_db, margin_pct;
+} f9_tail_params;
+F9_API int f9_dev_tail_scan_batch(f9_context* ctx, const f9_dev_buffer* bufs, const f9_tail_params* params, int n,
+                                  long long* d_stop_frame, int* d_flags, int max_polls);
+
+/* fused trim (+ optional DC removal) on device: out buffer i = trimLatency(bufs[i], latency_samples[i],
+ * original_length[i]); out numFrames must equal original_length[i]. */
+F9_API int f9_dev_trim_batch(f9_context* ctx, const f9_dev_buffer* captured, const int* latency_samples,
+                             const f9_dev_buffer* out, int n, int remove_dc);
+
+/* ======================= G. deinterleave / format convert =================== */
+/* interleaved PCM (host) -> planar float (host): JUCE reader semantics (left-justify to int32, scale by
+ * 1/0x7fffffff); destination channel c reads source channel min(c, src_ch-1). */
+F9_API int f9_pcm_to_planar(f9_context* ctx, const void* src, int fmt, int src_ch, long long num_frames,
+                            float* const* dst, int dst_ch);
+/* planar float (host) -> interleaved 24-bit LE PCM (host): JUCE writer semantics (clip, round half even
+ * of INT_MAX*x in double, keep top 24 bits). */
+F9_API int f9_planar_to_pcm24(f9_context* ctx, const float* const* src, int numCh, long long num_frames,
+                              unsigned char* dst);
+/* planar <-> interleaved float (AudioProcessingService.swift:361-365, :524-531). */
+F9_API int f9_interleave(f9_context* ctx, const float* const* src, int numCh, long long num_frames, float* dst);
+F9_API int f9_deinterleave(f9_context* ctx, const float* src, int numCh, long long num_frames, float* const* dst);
+/* device-resident forms */
+F9_API int f9_dev_pcm_to_planar(f9_context* ctx, const void* d_src, int fmt, int src_ch, long long num_frames,
+                                float* d_dst, long long dst_ch_stride, int dst_ch);
+F9_API int f9_dev_planar_to_pcm24(f9_context* ctx, const float* d_src, long long src_ch_stride, int numCh,
+                                  long long num_frames, unsigned char* d_dst);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* F9DSP_H */

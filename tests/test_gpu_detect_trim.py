@@ -1,0 +1,214 @@
+"""GPU parity (through the C ABI) for latency detection, tail silence, trimming and format conversion.
+
+Integer / index / byte results are compared bit for bit with the oracle; float scalars (RMS, noise floor)
+to one float ulp; DC removal to the stated tolerance (the reference sums sequentially in float).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+SIZES = [(1, 1), (2, 7), (2, 255), (2, 4096), (3, 16385), (2, 220500), (5, 70001)]
+
+
+def rnd(shape, seed, scale=0.5):
+    return np.random.default_rng(seed).uniform(-scale, scale, shape).astype(np.float32)
+
+
+# ---------------------------------------------------------------- findPeakPosition
+@pytest.mark.parametrize("shape", SIZES)
+def test_find_peak_random(ctx, O, shape):
+    x = rnd(shape, sum(shape))
+    for thr in (0.1, 0.49999, 2.0):
+        assert ctx.find_peak_position(x, thr) == O.find_peak_position(x, thr)
+
+
+def test_find_peak_ties_zero_nan(ctx, O):
+    x = np.zeros((2, 50000), np.float32)
+    assert ctx.find_peak_position(x, 0.1) == -1
+    x[1, 100] = 0.5; x[0, 40000] = 0.5                      # equal peaks in ch0 and ch1, far apart in chunks
+    assert ctx.find_peak_position(x, 0.1) == O.find_peak_position(x, 0.1) == 40000
+    x[0, 41000] = -0.5; x[0, 16384] = 0.5                   # more ties, chunk boundary
+    assert ctx.find_peak_position(x, 0.1) == O.find_peak_position(x, 0.1) == 16384
+    x[0, 3] = np.nan; x[1, 77] = np.inf
+    assert ctx.find_peak_position(x, 0.1) == O.find_peak_position(x, 0.1) == 77
+    assert ctx.find_peak_position(np.zeros((2, 0), np.float32), 0.1) == -1
+
+
+def test_find_peak_every_alignment(ctx, O):
+    base = rnd((1, 4200), 11)
+    for off in range(0, 9):
+        for n in (1, 2, 3, 4, 5, 63, 64, 65, 1023, 4100):
+            x = np.ascontiguousarray(base[:, off:off + n])
+            assert ctx.find_peak_position(x, 0.0) == O.find_peak_position(x, 0.0)
+
+
+def test_find_peak_interleaved(ctx, O):
+    a = rnd(100001, 5)
+    assert ctx.find_peak_interleaved(a, 0.1) == O.find_peak_interleaved(a, 0.1)
+    assert ctx.find_peak_interleaved(a, 0.6) == O.find_peak_interleaved(a, 0.6)
+    z = np.zeros(1000, np.float32)
+    assert ctx.find_peak_interleaved(z, 0.1) == O.find_peak_interleaved(z, 0.1) == (0, False)
+
+
+def test_latency_measurement_flow(ctx, O):
+    """Source/MainComponent.cpp:265-294: impulse capture -> peak -> *2 -> noise floor."""
+    fs = 48000
+    rng = np.random.default_rng(0)
+    for d in (0, 7, 512, 65535):
+        cap = (rng.standard_normal((2, 5 * fs)) * 1e-4).astype(np.float32)      # -80 dBFS noise
+        cap[:, d] += 0.9
+        pk = ctx.find_peak_position(cap, 0.1)
+        assert pk == O.find_peak_position(cap, 0.1) == d
+        nf_gpu, nf_cpu = ctx.calculate_noise_floor_db(cap), O.noise_floor_db(cap)
+        assert abs(float(nf_gpu) - float(nf_cpu)) <= 1e-5
+
+
+# ---------------------------------------------------------------- RMS
+@pytest.mark.parametrize("shape", SIZES)
+def test_rms_one_ulp(ctx, O, shape):
+    x = rnd(shape, 3 + sum(shape))
+    g, c = ctx.calculate_rms(x), O.calculate_rms(x)
+    assert abs(int(g.view(np.int32)) - int(c.view(np.int32))) <= 1
+    assert float(ctx.calculate_rms(np.zeros((2, 0), np.float32))) == 0.0
+
+
+# ---------------------------------------------------------------- tail predicates and scan
+def test_tail_predicates_match(ctx, O):
+    rng = np.random.default_rng(2)
+    for trial in range(40):
+        db = rng.uniform(-130, -60)
+        w = (rng.standard_normal((2, 2048)) * 10 ** (db / 20)).astype(np.float32)
+        for has_nf, nf, mg in ((True, -96.0, 10.0), (True, -98.0, 15.0), (False, 0.0, 10.0), (True, -70.0, 0.0)):
+            assert ctx.is_reverb_tail_below_noise_floor(w, has_nf, nf, mg) == O.tail_below_floor(w, has_nf, nf, mg)
+            iw = O.interleave(w)
+            assert ctx.is_reverb_tail_below_noise_floor_swift(iw, has_nf, nf, mg) == O.tail_below_floor_swift(iw, has_nf, nf, mg)
+    z = np.zeros((2, 2048), np.float32)
+    assert ctx.is_reverb_tail_below_noise_floor(z, True, -96.0, 10.0) == O.tail_below_floor(z, True, -96.0, 10.0)
+    assert ctx.is_reverb_tail_below_noise_floor_swift(z.ravel(), True, -96.0, 10.0) == O.tail_below_floor_swift(z.ravel(), True, -96.0, 10.0)
+    assert ctx.is_reverb_tail_below_noise_floor_swift(z.ravel(), True, -200.0, 0.0) == O.tail_below_floor_swift(z.ravel(), True, -200.0, 0.0)
+
+
+def test_tail_predicate_on_the_threshold(ctx, O):
+    """Windows whose RMS sits within an ulp of the decision boundary: the guard band must reproduce the
+    sequential reference decision exactly."""
+    rng = np.random.default_rng(4)
+    nf, mg = -96.0, 10.0
+    thr_db = float(O.noise_floor_threshold_db(True, nf, mg))
+    target = 10 ** (thr_db / 20)
+    mismatches = 0
+    for trial in range(200):
+        w = rng.standard_normal((2, 2048)).astype(np.float32)
+        w *= np.float32(target / np.sqrt(np.mean(w.astype(np.float64) ** 2)))
+        w *= np.float32(1.0 + rng.uniform(-3e-7, 3e-7))
+        mismatches += ctx.is_reverb_tail_below_noise_floor(w, True, nf, mg) != O.tail_below_floor(w, True, nf, mg)
+    assert mismatches == 0
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_tail_scan_matches(ctx, O, mode):
+    fs = 44100
+    rng = np.random.default_rng(6 + mode)
+    n = fs * 3
+    t = np.arange(n) / fs
+    x = (0.5 * np.sin(2 * np.pi * 1000 * t) * np.exp(-t * 6.0)).astype(np.float32)
+    x = np.stack([x, x * 0.7]).astype(np.float32)
+    x += (rng.standard_normal(x.shape) * 10 ** (-96 / 20)).astype(np.float32)
+    for (win, hop, req, start) in ((4410, 2205, 3, 0), (2048, 256, 4, 30000), (2048, 1000, 2, 777), (4410, 2205, 3, n - 100)):
+        for has_nf, nf, mg in ((True, -93.0, -3.0), (True, -96.0, 10.0), (False, 0.0, 10.0)):
+            gs, gf = ctx.tail_scan(x, start, win, hop, req, mode, has_nf, nf, mg)
+            cs, cf = O.tail_scan(x, start, win, hop, req, mode, has_nf, nf, mg)
+            assert gs == cs and np.array_equal(gf, cf), (win, hop, req, start, has_nf, nf, mg)
+
+
+# ---------------------------------------------------------------- cross-correlation
+def test_xcorr_impulse_equals_find_peak(ctx, O):
+    rng = np.random.default_rng(8)
+    stim = np.array([0.9], np.float32)
+    for d in (0, 1, 255, 256, 4097, 65535):
+        y = (rng.standard_normal((2, 70000)) * 1e-4).astype(np.float32)
+        y[:, d] += 0.8
+        g = ctx.xcorr_peak(y, stim, 0, 65536, 0.1)
+        c = O.xcorr_peak(y, stim, 0, 65536, 0.1)
+        assert g[:3] == c[:3] and g[3] == c[3]
+        assert g[1] == ctx.find_peak_position(y[:, :65537], 0.1) == d
+
+
+def test_xcorr_sweep_and_ties(ctx, O):
+    rng = np.random.default_rng(9)
+    m = 700
+    tt = np.arange(m) / 48000.0
+    stim = (0.5 * np.sin(2 * np.pi * (200 + 4000 * tt / tt[-1]) * tt)).astype(np.float32)
+    y = (rng.standard_normal((2, 6000)) * 1e-3).astype(np.float32)
+    y[0, 1234:1234 + m] += 0.5 * stim
+    y[1, 1300:1300 + m] += 0.4 * stim
+    g = ctx.xcorr_peak(y, stim, -1024, 4096, 0.01)
+    c = O.xcorr_peak(y, stim, -1024, 4096, 0.01)
+    assert g == c and g[1] == 1234 and g[2] == 0
+    # exact ties: identical copies in both channels and twice in channel 0
+    y = np.zeros((2, 6000), np.float32)
+    y[1, 100:100 + m] = stim; y[0, 2000:2000 + m] = stim; y[0, 4000:4000 + m] = stim
+    g = ctx.xcorr_peak(y, stim, -300, 5000, 0.01)
+    c = O.xcorr_peak(y, stim, -300, 5000, 0.01)
+    assert g == c and (g[1], g[2]) == (2000, 0)
+    # nothing there
+    g = ctx.xcorr_peak(np.zeros((2, 512), np.float32), stim, -16, 16, 0.1)
+    assert g[0] is False and g[2] == -1
+    # negative lag wins
+    y = np.zeros((1, 2000), np.float32); y[0, :m - 50] = stim[50:]
+    assert ctx.xcorr_peak(y, stim, -200, 200, 0.01) == O.xcorr_peak(y, stim, -200, 200, 0.01)
+
+
+# ---------------------------------------------------------------- trimLatency
+def test_trim_doc_vector(ctx, O):
+    cap = rnd((2, 46660), 1)
+    g, gn = ctx.trim_latency(cap, 1024, 44100)
+    c, cn = O.trim_latency(cap, 1024, 44100)
+    assert gn == cn == 44100 and np.array_equal(g, c)
+
+
+@pytest.mark.parametrize("lat,orig", [(180, 50), (400, 50), (-4, 50), (3, 20), (0, 100), (0, 150), (199, 1), (0, 0)])
+def test_trim_edge_cases(ctx, O, lat, orig):
+    cap = rnd((2, 100), 2)
+    g, gn = ctx.trim_latency(cap, lat, orig)
+    c, cn = O.trim_latency(cap, lat, orig)
+    assert gn == cn and np.array_equal(g, c)
+
+
+def test_trim_swift(ctx, O):
+    a = rnd(93320, 3)
+    for lat, frames, ch in ((1024, 44100, 2), (93000, 44100, 2), (200000, 100, 2), (6, 4, 2), (0, 0, 2)):
+        assert np.array_equal(ctx.trim_latency_swift(a, lat, frames, ch), O.trim_latency_swift(a, lat, frames, ch))
+
+
+def test_remove_dc_tolerance(ctx, O):
+    x = (rnd((2, 100000), 4, 0.3) + np.float32(0.01)).astype(np.float32)
+    g, c = ctx.remove_dc_offset(x), O.remove_dc_offset(x)
+    assert np.max(np.abs(g - c)) <= 2.0 ** -20           # tolerance parity: float sequential mean vs parallel mean
+
+
+# ---------------------------------------------------------------- format conversion (bit exact)
+@pytest.mark.parametrize("fmt,dt", [(1, np.uint8), (2, np.int16), (3, None), (4, np.int32), (5, np.float32)])
+@pytest.mark.parametrize("src_ch,dst_ch,frames", [(1, 2, 1000), (2, 2, 4099), (6, 6, 333), (2, 1, 64)])
+def test_pcm_to_planar(ctx, O, fmt, dt, src_ch, dst_ch, frames):
+    rng = np.random.default_rng(fmt * 100 + frames)
+    nbytes = {1: 1, 2: 2, 3: 3, 4: 4, 5: 4}[fmt] * src_ch * frames
+    raw = rng.integers(0, 256, nbytes, dtype=np.uint8)
+    if fmt == 5:
+        raw = rng.uniform(-1, 1, src_ch * frames).astype(np.float32).view(np.uint8)
+    assert np.array_equal(ctx.pcm_to_planar(raw, fmt, src_ch, dst_ch), O.pcm_to_planar(raw, fmt, src_ch, dst_ch))
+
+
+@pytest.mark.parametrize("ch,frames", [(1, 5), (2, 4099), (2, 44100), (7, 1001), (64, 300)])
+def test_planar_to_pcm24(ctx, O, ch, frames):
+    x = rnd((ch, frames), ch + frames, 1.2)               # includes clipping on both sides
+    x[0, :4] = [1.0, -1.0, 0.0, -0.0][:min(4, frames)] if frames >= 4 else x[0, :4]
+    assert np.array_equal(ctx.planar_to_pcm24(x), O.planar_to_pcm24(x))
+
+
+@pytest.mark.parametrize("ch,frames", [(1, 5), (2, 4099), (3, 70000), (64, 300)])
+def test_interleave_round_trip(ctx, O, ch, frames):
+    x = rnd((ch, frames), 10 + ch)
+    inter = ctx.interleave(x)
+    assert np.array_equal(inter, O.interleave(x))
+    assert np.array_equal(ctx.deinterleave(inter, ch), x)

@@ -1,0 +1,257 @@
+"""GPU parity (through the C ABI) for the sample-rate conversion path against the oracle.
+
+Tolerances are the north_star's: max-abs-error <= 2^-20 full scale and SNR >= 120 dB against the
+sequential interpolator; inputs consumed, output lengths and interpolator state are exact.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL = 2.0 ** -20
+KINDS = [0, 1, 2, 3, 4]
+RATIONAL = [(44100, 48000), (48000, 44100), (96000, 44100), (48000, 192000), (96000, 48000), (192000, 48000),
+            (88200, 48000), (44100, 96000)]
+
+
+def signal(n, seed, kind="noise"):
+    rng = np.random.default_rng(seed)
+    if kind == "noise":
+        return rng.uniform(-0.5, 0.5, n).astype(np.float32)
+    if kind == "sweep":
+        t = np.arange(n) / n
+        return (0.5 * np.sin(2 * np.pi * (20 * n / 48000.0) * t * (1000.0 ** t) / np.log(1000.0))).astype(np.float32)
+    x = np.zeros(n, np.float32); x[0] = 0.9
+    return x
+
+
+def snr_db(ref, got):
+    err = np.sqrt(np.mean((ref.astype(np.float64) - got.astype(np.float64)) ** 2))
+    sig = np.sqrt(np.mean(ref.astype(np.float64) ** 2))
+    return np.inf if err == 0 else 20 * np.log10(sig / err)
+
+
+# ---------------------------------------------------------------- juce::Interpolators-shaped objects
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("ratio", [147 / 160, 320 / 147, 0.25, 2.0, 1.0, 0.731234567, 3.3333])
+def test_process_matches_oracle(ctx, O, kind, ratio):
+    n_out = 5000
+    x = signal(int(n_out * ratio) + 300, 1)
+    g = ctx.interpolator(kind)
+    c = O.Interpolator(kind)
+    assert g.base_latency == c.base_latency
+    yg, ug = g.process(ratio, x, n_out)
+    yc, uc = c.process(ratio, x, n_out)
+    assert ug == uc
+    assert np.max(np.abs(yg - yc)) <= TOL
+    assert snr_db(yc, yg) >= 120.0
+
+
+@pytest.mark.parametrize("kind", [0, 1])
+def test_process_streaming_state(ctx, O, kind):
+    ratio = 147 / 160
+    x = signal(20000, 2)
+    g, c = ctx.interpolator(kind), O.Interpolator(kind)
+    pos_g = pos_c = 0
+    outs_g, outs_c = [], []
+    for chunk in (1, 2, 199, 200, 201, 1024, 4096, 3):
+        yg, ug = g.process(ratio, x[pos_g:], chunk)
+        yc, uc = c.process(ratio, x[pos_c:], chunk)
+        assert ug == uc
+        pos_g += ug; pos_c += uc
+        outs_g.append(yg); outs_c.append(yc)
+    yg, yc = np.concatenate(outs_g), np.concatenate(outs_c)
+    assert np.max(np.abs(yg - yc)) <= TOL
+    g.reset(); c.reset()
+    yg, ug = g.process(ratio, x, 100)
+    yc, uc = c.process(ratio, x, 100)
+    assert ug == uc and np.max(np.abs(yg - yc)) <= TOL
+
+
+def test_generic_path_is_mostly_bit_exact(ctx, O):
+    """The arbitrary-ratio kernels evaluate the traits in the scalar operation order, so wherever the closed-form
+    position agrees with the sequential recurrence the samples are identical bit for bit."""
+    for kind in (0, 1, 2, 3):
+        x = signal(9000, 3)
+        yg, _ = ctx.interpolator(kind).process(0.731234567, x, 10000)
+        yc, _ = O.Interpolator(kind).process(0.731234567, x, 10000)
+        assert np.mean(yg == yc) > 0.995
+
+
+def test_process_adding_and_wrap(ctx, O):
+    x = signal(3000, 4)
+    for kind in (0, 1):
+        base = signal(2000, 5)
+        og, oc = base.copy(), base.copy()
+        ug = ctx.interpolator(kind).process_adding(0.9, x, og, 0.25)
+        uc = O.Interpolator(kind).process_adding(0.9, x, oc, 0.25)
+        assert ug == uc and np.max(np.abs(og - oc)) <= TOL
+        yg, ug = ctx.interpolator(kind).process_wrap(1.3, x[:500], 2000, 500, 0)      # runs out: zeros
+        yc, uc = O.Interpolator(kind).process_wrap(1.3, x[:500], 2000, 500, 0)
+        assert ug == uc and np.max(np.abs(yg - yc)) <= TOL
+        yg, ug = ctx.interpolator(kind).process_wrap(1.3, x[:500], 2000, 500, 300)    # loops the last 300
+        yc, uc = O.Interpolator(kind).process_wrap(1.3, x[:500], 2000, 500, 300)
+        assert ug == uc and np.max(np.abs(yg - yc)) <= TOL
+
+
+# ---------------------------------------------------------------- whole-file conversion (polyphase kernels)
+@pytest.mark.parametrize("kind", [0, 1])
+@pytest.mark.parametrize("fs", RATIONAL)
+@pytest.mark.parametrize("sig", ["noise", "sweep", "impulse"])
+def test_file_conversion(ctx, O, f9, kind, fs, sig):
+    fs_in, fs_out = fs
+    n_in = 30011
+    x = np.stack([signal(n_in, 6, sig), signal(n_in, 7, sig)])
+    y = ctx.resample(x, fs_in, fs_out, kind)
+    n_out = f9.resampled_length(n_in, fs_in, fs_out)
+    assert y.shape == (2, n_out)
+    assert n_out == -((-n_in * fs_out) // fs_in)          # ceil(n_in * fs_out / fs_in), exact integers
+    for c in range(2):
+        ref, used = O.resample_channel(kind, fs_in / fs_out, x[c], n_out)
+        assert np.max(np.abs(y[c] - ref)) <= TOL, (kind, fs, sig)
+        if sig != "impulse":
+            assert snr_db(ref, y[c]) >= 120.0
+
+
+def test_file_conversion_irrational(ctx, O):
+    x = signal(20000, 8)[None, :]
+    for kind in (0, 1):
+        y = ctx.resample(x, 44100.0, 47999.37, kind)
+        ref, _ = O.resample_channel(kind, 44100.0 / 47999.37, x[0], y.shape[1])
+        assert np.max(np.abs(y[0] - ref)) <= TOL
+
+
+def test_custom_sinc_table(ctx, O, f9):
+    """The WindowedSinc lookup table is a parameter on both sides (JUCE's literal table can be installed)."""
+    t = O.sinc_table()
+    k = np.arange(10001) / 100.0
+    alt = (t * (0.42 + 0.5 * np.cos(np.pi * k / 100) + 0.08 * np.cos(2 * np.pi * k / 100)) / np.maximum(0.5 * (1 + np.cos(np.pi * k / 100)), 1e-9)).astype(np.float32)
+    alt[0] = 1.0
+    c2 = f9.Context(0)
+    try:
+        c2.sinc_table_set(alt)
+        assert np.array_equal(c2.sinc_table_get(), alt)
+        x = signal(8000, 9)[None, :]
+        y = c2.resample(x, 44100, 48000, 0)
+        ref, _ = O.resample_channel(0, 44100 / 48000, x[0], y.shape[1], table=alt)
+        assert np.max(np.abs(y[0] - ref)) <= TOL
+        yg, _ = c2.interpolator(0).process(0.77, x[0], 5000)
+        yc, _ = O.Interpolator(0, alt).process(0.77, x[0], 5000)
+        assert np.max(np.abs(yg - yc)) <= TOL
+    finally:
+        c2.close()
+
+
+# ---------------------------------------------------------------- batch job flow
+def test_batch_flow_trim_tail_convert(ctx, O, f9):
+    fs_in, fs_out = 96000, 44100
+    rng = np.random.default_rng(10)
+    jobs, expect = [], []
+    for i in range(6):
+        src = 20000 + 997 * i
+        lat_frames = 128 * i + 7
+        cap_frames = O.recording_length(src, lat_frames) + 30000
+        t = np.arange(cap_frames) / fs_in
+        sig = np.zeros(cap_frames, np.float32)
+        body = (0.5 * np.sin(2 * np.pi * 1000 * t[:src]) * np.exp(-t[:src] * 40)).astype(np.float32)
+        sig[lat_frames:lat_frames + src] = body
+        cap = np.stack([sig, 0.8 * sig]).astype(np.float32)
+        cap += (rng.standard_normal(cap.shape) * 10 ** (-96 / 20)).astype(np.float32)
+        kind = i % 2
+        jobs.append(dict(captured=cap, latency_samples=lat_frames * 2 + (i % 2), original_length=src, fs_in=fs_in, fs_out=fs_out,
+                         kind=kind, tail=(9600, 4800, 3, i % 2, True, -90.0, 0.0), pcm24=True))
+        trimmed, copied = O.trim_latency(cap, lat_frames * 2 + (i % 2), src)
+        n_out = f9.resampled_length(src, fs_in, fs_out)
+        ref = np.stack([O.resample_channel(kind, fs_in / fs_out, trimmed[c], n_out)[0] for c in range(2)])
+        stop, _ = O.tail_scan(cap, src + lat_frames, 9600, 4800, 3, i % 2, True, -90.0, 0.0)
+        expect.append((ref, copied, lat_frames, stop, n_out))
+    outs, pcms, res = ctx.process_batch(jobs)
+    for i, (ref, copied, lat_frames, stop, n_out) in enumerate(expect):
+        r = res[i]
+        assert r["status"] == 0
+        assert (r["latency_frames"], r["trim_start"], r["frames_copied"], r["out_frames"]) == (lat_frames, lat_frames, copied, n_out)
+        assert r["tail_stop_frame"] == stop
+        assert outs[i].shape == ref.shape and np.max(np.abs(outs[i] - ref)) <= TOL
+        assert np.array_equal(pcms[i], O.planar_to_pcm24(outs[i]))       # payload of exactly what was produced
+
+
+def test_batch_flow_no_conversion_with_dc(ctx, O):
+    """The reference's own flow (44.1 kHz in and out): trimLatency + removeDCOffset, short capture zero padded."""
+    cap = (np.random.default_rng(11).uniform(-0.3, 0.3, (2, 46000)) + 0.02).astype(np.float32)
+    outs, _, res = ctx.process_batch([dict(captured=cap, latency_samples=1024, original_length=44100,
+                                           fs_in=44100, fs_out=44100, kind=0, remove_dc=True),
+                                      dict(captured=cap[:, :30000], latency_samples=1024, original_length=44100,
+                                           fs_in=44100, fs_out=44100, kind=0)])
+    t0, _ = O.trim_latency(cap, 1024, 44100)
+    assert np.max(np.abs(outs[0] - O.remove_dc_offset(t0))) <= TOL
+    t1, c1 = O.trim_latency(cap[:, :30000], 1024, 44100)
+    assert np.array_equal(outs[1], t1) and res[1]["frames_copied"] == c1 == 30000 - 512
+
+
+def test_batch_invalid_jobs_report_status(ctx, f9):
+    cap = np.zeros((2, 100), np.float32)
+    outs, _, res = ctx.process_batch([dict(captured=cap, latency_samples=0, original_length=50, fs_in=0.0, fs_out=48000.0, kind=0),
+                                      dict(captured=cap, latency_samples=0, original_length=50, fs_in=44100, fs_out=44100, kind=1)])
+    assert res[0]["status"] == f9.ERR_INVALID and res[1]["status"] == 0
+    assert np.array_equal(outs[1], cap[:, :50])
+
+
+# ---------------------------------------------------------------- time segmentation with halos (device plans)
+def test_time_segments_equal_whole(ctx, O, f9):
+    torch = pytest.importorskip("torch")
+    import ctypes as C
+    fs_in, fs_out = 48000, 192000
+    n_in = 50000
+    for kind in (0, 1):
+        x = signal(n_in, 12)
+        n_out = f9.resampled_length(n_in, fs_in, fs_out)
+        ref, _ = O.resample_channel(kind, fs_in / fs_out, x, n_out)
+        d_in = torch.from_numpy(x).cuda()
+        d_out = torch.zeros(n_out, dtype=torch.float32, device="cuda")
+        seg_len = 37777
+        segs = []
+        keep = []
+        for n0 in range(0, n_out, seg_len):
+            cnt = min(seg_len, n_out - n0)
+            first, last = f9.segment_input_range(kind, fs_in / fs_out, n0, cnt)
+            lo, hi = max(first, 0), min(last, n_in)
+            halo = d_in[lo:hi].clone()                                   # the segment travels with its own halo
+            keep.append(halo)
+            segs.append(f9.ResampleSeg(halo.data_ptr(), lo, hi - lo, d_out.data_ptr() + 4 * n0, n0, cnt))
+        arr = (f9.ResampleSeg * len(segs))(*segs)
+        plan = C.c_void_p(None)
+        torch.cuda.synchronize()
+        assert f9.lib().f9_resample_plan_create(ctx.handle, kind, fs_in / fs_out, arr, len(segs), C.byref(plan)) == 0
+        assert f9.lib().f9_resample_plan_run(plan) == 0
+        ctx.synchronize()
+        f9.lib().f9_plan_destroy(plan)
+        got = d_out.cpu().numpy()
+        assert np.max(np.abs(got - ref)) <= TOL
+
+
+# ---------------------------------------------------------------- size-independent properties at BASELINE sizes
+def test_full_size_properties_config1(ctx, O, f9):
+    """configs[0]: 60 s stereo 44.1 kHz -> 48 kHz, WindowedSinc.  Checked through properties the domain offers:
+    exact output length, linearity, and agreement with the oracle on slices resampled as independent segments."""
+    fs_in, fs_out = 44100, 48000
+    n_in = 60 * fs_in
+    n_out = f9.resampled_length(n_in, fs_in, fs_out)
+    assert n_out == 60 * fs_out
+    a = np.stack([signal(n_in, 20, "sweep"), signal(n_in, 21)])
+    b = np.stack([signal(n_in, 22), signal(n_in, 23, "sweep")])
+    ya, yb = ctx.resample(a, fs_in, fs_out, 0), ctx.resample(b, fs_in, fs_out, 0)
+    yab = ctx.resample((0.5 * a + 0.25 * b).astype(np.float32), fs_in, fs_out, 0)
+    assert ya.shape == (2, n_out)
+    assert np.max(np.abs(yab - (0.5 * ya + 0.25 * yb))) <= 4 * TOL        # linearity (input mix rounds once more)
+    # oracle on three windows of the long file.  The phase pattern repeats every 160 outputs / 147 inputs, so the
+    # oracle restarted two periods (294 inputs = 320 outputs) before a window reproduces it once its 200-sample
+    # memory has filled.
+    cnt = 20000
+    for n0 in (0, 160 * 9000, 160 * ((n_out - cnt) // 160)):
+        if n0 == 0:
+            ref, _ = O.resample_channel(0, fs_in / fs_out, a[1], cnt)
+        else:
+            shift_in = (n0 // 160) * 147 - 294
+            ref, _ = O.resample_channel(0, fs_in / fs_out, a[1][shift_in:], cnt + 320)
+            ref = ref[320:]
+        assert np.max(np.abs(ref - ya[1][n0:n0 + cnt])) <= TOL, n0
