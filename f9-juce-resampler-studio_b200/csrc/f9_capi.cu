@@ -29,14 +29,14 @@ int f9_context::arena_reserve(size_t d_bytes, size_t h_bytes, bool async_call) {
     quiescent = false;          // work is about to be enqueued; F9_FINISH sets it back
     if (d_bytes > d_cap) {
         if (d_arena) { cudaStreamSynchronize(stream); cudaFree(d_arena); d_arena = nullptr; d_cap = 0; }
-        size_t want = std::max(d_bytes, d_cap + d_cap / 2);
+        size_t want = std::max(std::max(d_bytes, d_cap + d_cap / 2), size_t(8) << 20);
         cudaError_t e = cudaMalloc((void**) &d_arena, want);
         if (e != cudaSuccess) { err = std::string("cudaMalloc(arena): ") + cudaGetErrorString(e); cudaGetLastError(); return F9_ERR_NOMEM; }
         d_cap = want;
     }
     if (h_bytes > h_cap) {
         if (h_arena) { cudaStreamSynchronize(stream); cudaFreeHost(h_arena); h_arena = nullptr; h_cap = 0; }
-        size_t want = std::max(h_bytes, h_cap + h_cap / 2);
+        size_t want = std::max(std::max(h_bytes, h_cap + h_cap / 2), size_t(4) << 20);
         cudaError_t e = cudaHostAlloc((void**) &h_arena, want, cudaHostAllocDefault);
         if (e != cudaSuccess) { err = std::string("cudaHostAlloc(arena): ") + cudaGetErrorString(e); cudaGetLastError(); return F9_ERR_NOMEM; }
         h_cap = want;

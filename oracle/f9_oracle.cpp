@@ -159,10 +159,12 @@ ORC_API int orc_trim_latency(const float* const* captured, int numCh, int captur
         framesToCopy = std::max(0, capturedFrames - startFrame);
     for (int c = 0; c < numCh; ++c)
         for (int i = 0; i < originalLength; ++i) out[c][i] = 0.0f;
-    if (framesToCopy > 0 && startFrame >= 0)
+    if (framesToCopy > 0 && startFrame >= 0) {
         for (int c = 0; c < numCh; ++c)
             std::memcpy(out[c], captured[c] + startFrame, sizeof(float) * (size_t) framesToCopy);
-    return framesToCopy;
+        return framesToCopy;
+    }
+    return 0;      // nothing copied (the reference returns only the buffer; the count is this wrapper's)
 }
 
 // AudioProcessingService.swift:681-703  trimLatency (interleaved, NO padding).

@@ -1,0 +1,55 @@
+"""The C++ host mirror (host/F9Dsp.hpp): it must compile against the C ABI with plain g++ (CPU test) and, on a GPU,
+give the oracle's answers through the reference-shaped calls (gpu test)."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "f9-juce-resampler-studio_b200")
+EXE = os.path.join(PKG, "build", "host_mirror_main")
+
+
+def build_exe():
+    os.makedirs(os.path.dirname(EXE), exist_ok=True)
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(PKG, "host"),
+                           os.path.join(ROOT, "tests", "cpp", "host_mirror_main.cpp"), "-o", EXE,
+                           "-L", os.path.join(PKG, "lib"), "-lf9dsp", "-Wl,-rpath," + os.path.join(PKG, "lib")])
+
+
+def test_host_mirror_compiles_with_plain_gxx(f9):
+    f9.lib()
+    build_exe()
+    assert os.path.exists(EXE)
+
+
+@pytest.mark.gpu
+def test_host_mirror_matches_oracle(O, tmp_path):
+    build_exe()
+    rng = np.random.default_rng(0)
+    frames, playback, lat = 60000, 44100, 777
+    cap = (rng.standard_normal((2, frames)) * 1e-4 + 0.003).astype(np.float32)
+    cap[:, lat] += 0.9
+    inp, outp = tmp_path / "in.bin", tmp_path / "out.bin"
+    with open(inp, "wb") as f:
+        f.write(struct.pack("<ii", frames, playback)); f.write(cap.tobytes())
+    subprocess.check_call([EXE, str(inp), str(outp)])
+    raw = open(outp, "rb").read()
+    hdr = struct.unpack("<8i", raw[:32]); rms, nf = struct.unpack("<2f", raw[32:40])
+    body = np.frombuffer(raw[40:], np.float32)
+    trimmed = body[: 2 * playback].reshape(2, playback)
+    trimmed_only = body[2 * playback: 4 * playback].reshape(2, playback)
+    o1, o2 = body[4 * playback: 4 * playback + 4000], body[4 * playback + 4000:]
+    assert hdr[0] == 1 and hdr[1] == 2 * O.find_peak_position(cap, 0.1) == 2 * lat
+    assert abs(nf - float(O.noise_floor_db(cap))) <= 1e-5 and abs(rms - float(O.calculate_rms(cap))) <= 1e-9
+    t, _ = O.trim_latency(cap, 2 * lat, playback)
+    assert np.array_equal(trimmed_only, t)
+    assert np.max(np.abs(trimmed - O.remove_dc_offset(t))) <= 2.0 ** -20
+    assert hdr[2] == int(O.tail_below_floor(t, True, float(np.float32(nf)), 10.0))
+    y1, u1 = O.Interpolator(0).process(0.91875, cap[0], 4000)
+    y2, u2 = O.Interpolator(1).process(0.91875, cap[1], 4000)
+    assert (hdr[3], hdr[4], hdr[5], hdr[6]) == (u1, u2, 4000, playback)
+    assert hdr[7] == O.recording_length(playback, lat)
+    assert np.max(np.abs(o1 - y1)) <= 2.0 ** -20 and np.max(np.abs(o2 - y2)) <= 2.0 ** -20
