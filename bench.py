@@ -249,6 +249,12 @@ def run_gpu(args, rank: int, local_rank: int, world: int):
     clocks = sampler.stop(t_wall0, t_wall1)
     ms_l, kms_l, _ = timed(f9.LAGRANGE, args.steps, args.warmup)
 
+    if args.kernel_only:            # development aid: kernel times only, no JSON contract line
+        if rank == 0:
+            print(json.dumps({"cfg": os.environ.get("F9_BANDED_CFG", ""), "sinc_kernel_ms": sum(kms) / len(kms),
+                              "lagrange_kernel_ms": sum(kms_l) / len(kms_l), "step_ms": ms / args.steps}), flush=True)
+        return
+
     # ---- e2e: host buffers through f9_process_batch, H2D + D2H inside the timed region ----
     caps_h = torch.empty(caps.shape, dtype=torch.float32, pin_memory=True)
     caps_h.copy_(caps)
@@ -358,6 +364,7 @@ def main():
     ap.add_argument("--files", type=int, default=None, help="files per GPU (default: the config's)")
     ap.add_argument("--ref-files", type=int, default=16, help="files in the CPU baseline sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--kernel-only", action="store_true", help="development: print kernel times only")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -160,18 +160,10 @@ int run_chunk(f9_context* ctx, const f9_job* jobs, f9_result* results, const std
         }
         for (auto& kv : groups) {
             ResampleLaunch L;
-            L.kind = kv.first.first; L.ratio = kv.first.second; L.pos0 = 1.0;
-            L.d_sinc_table = ctx->d_sinc_table; L.tile_out = choose_tile_out(L.ratio);
-            long long p = 0, q = 0;
-            if (find_rational(L.ratio, 4096, &p, &q) && p <= (1 << 20)) {
-                rc = ctx->get_poly(L.kind, p, q, &L.poly); if (rc) return rc;
-                L.rational = true;
-            }
-            if ((double) L.tile_out * L.ratio > 45000.0) return ctx->fail(F9_ERR_UNSUPPORTED, "speed ratio too large for the tile buffer");
+            rc = ctx->prepare_resample(kv.first.first, kv.first.second, 1.0, true, &L); if (rc) return rc;
             std::vector<Seg>& segs = kv.second;
-            std::vector<int> prefix(segs.size() + 1, 0);
-            for (size_t i = 0; i < segs.size(); ++i)
-                prefix[i + 1] = prefix[i] + (int) ((segs[i].numOut + L.tile_out - 1) / L.tile_out);
+            std::vector<int> prefix;
+            if (resample_build_tiles(L, segs.data(), (int) segs.size(), &prefix) < 0) return ctx->fail(F9_ERR_INVALID, "too many tiles");
             Seg* d_s = (Seg*) ctx->d_alloc(sizeof(Seg) * segs.size()); int* d_p = (int*) ctx->d_alloc(sizeof(int) * prefix.size());
             Seg* h_s = (Seg*) ctx->h_alloc(sizeof(Seg) * segs.size()); int* h_p = (int*) ctx->h_alloc(sizeof(int) * prefix.size());
             std::memcpy(h_s, segs.data(), sizeof(Seg) * segs.size()); std::memcpy(h_p, prefix.data(), sizeof(int) * prefix.size());

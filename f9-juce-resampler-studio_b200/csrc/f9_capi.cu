@@ -462,43 +462,6 @@ int f9_xcorr_peak(f9_context* ctx, const float* const* y, int numCh, int numFram
 }  // extern "C"
 
 // ------------------------------------------------------------------------------------------------ resample plumbing
-namespace {
-
-struct ResampleSetup {
-    ResampleLaunch L;
-};
-
-// Fill the launch descriptor for (kind, ratio, pos0): rational detection, polyphase tables, tile size.
-int prepare_resample(f9_context* ctx, int kind, double ratio, double pos0, bool allow_rational, ResampleLaunch* L) {
-    if (interp_memory(kind) == 0) return ctx->fail(F9_ERR_INVALID, "unknown interpolator kind");
-    if (!(ratio > 0.0) || !std::isfinite(ratio)) return ctx->fail(F9_ERR_INVALID, "speed ratio must be positive and finite");
-    L->kind = kind; L->ratio = ratio; L->pos0 = pos0;
-    L->d_sinc_table = ctx->d_sinc_table;
-    L->tile_out = choose_tile_out(ratio);
-    L->rational = false;
-    long long p = 0, q = 0;
-    if (allow_rational && pos0 == 1.0 && find_rational(ratio, 4096, &p, &q) && p <= (1 << 20)) {
-        int rc = ctx->get_poly(kind, p, q, &L->poly); if (rc) return rc;
-        L->rational = true;
-    }
-    if ((double) L->tile_out * ratio > 45000.0) return ctx->fail(F9_ERR_UNSUPPORTED, "speed ratio too large for the tile buffer");
-    return F9_OK;
-}
-
-int build_tiles(const Seg* segs, int n, int tile_out, std::vector<int>* prefix) {
-    prefix->assign((size_t) n + 1, 0);
-    long long total = 0;
-    for (int i = 0; i < n; ++i) {
-        const long long t = segs[i].numOut > 0 ? (segs[i].numOut + tile_out - 1) / tile_out : 0;
-        total += t;
-        if (total > 0x7fffffffLL) return -1;
-        (*prefix)[(size_t) i + 1] = (int) total;
-    }
-    return (int) total;
-}
-
-}  // namespace
-
 struct f9_interp {
     f9_context* ctx = nullptr;
     int kind = 0;
@@ -534,12 +497,12 @@ int interp_run(f9_interp* h, double ratio, const float* lin, int n_used, float* 
     if (adding) F9_TRY_CUDA(ctx, cudaMemcpyAsync(d_out, out, sizeof(float) * (size_t) num_out, cudaMemcpyHostToDevice, ctx->stream));
 
     ResampleLaunch L;
-    rc = prepare_resample(ctx, h->kind, ratio, h->pos, /*allow_rational=*/false, &L); if (rc) return rc;
+    rc = ctx->prepare_resample(h->kind, ratio, h->pos, /*allow_rational=*/false, &L); if (rc) return rc;
     Seg seg{};
     seg.in = d_in; seg.inOffset = -(long long) M; seg.inAvail = (long long) n_in;
     seg.out = d_out; seg.n0 = 0; seg.numOut = num_out;
     std::vector<int> prefix;
-    const int tiles = build_tiles(&seg, 1, L.tile_out, &prefix);
+    const int tiles = resample_build_tiles(L, &seg, 1, &prefix);
     Seg* d_seg; int* d_prefix;
     rc = upload_array(ctx, &seg, 1, &d_seg); if (rc) return rc;
     rc = upload_array(ctx, prefix.data(), prefix.size(), &d_prefix); if (rc) return rc;
@@ -757,7 +720,7 @@ int f9_resample_plan_create(f9_context* ctx, int kind, double speed_ratio, const
     f9_plan* P = new (std::nothrow) f9_plan();
     if (!P) return F9_ERR_NOMEM;
     P->ctx = ctx;
-    int rc = prepare_resample(ctx, kind, speed_ratio, 1.0, true, &P->L);
+    int rc = ctx->prepare_resample(kind, speed_ratio, 1.0, true, &P->L);
     if (rc) { delete P; return rc; }
     const Seg* hs = reinterpret_cast<const Seg*>(segs);
     for (int i = 0; i < n_segs; ++i)
@@ -765,7 +728,7 @@ int f9_resample_plan_create(f9_context* ctx, int kind, double speed_ratio, const
             delete P; return ctx->fail(F9_ERR_INVALID, "bad resample segment");
         }
     std::vector<int> prefix;
-    const int tiles = build_tiles(hs, n_segs, P->L.tile_out, &prefix);
+    const int tiles = resample_build_tiles(P->L, hs, n_segs, &prefix);
     if (tiles < 0) { delete P; return ctx->fail(F9_ERR_INVALID, "too many tiles"); }
     cudaError_t e;
     if ((e = cudaMalloc((void**) &P->d_segs, sizeof(Seg) * (size_t) std::max(n_segs, 1))) != cudaSuccess ||

@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <map>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "f9dsp.h"
@@ -101,8 +102,30 @@ struct PolyDev {                   // device copy of PolyHost
     int p = 0, q = 0, taps = 0, qpad = 0;
     int* B = nullptr; float* W = nullptr;
 };
+// Band-aligned polyphase tables for the register-tiled FIR (banded_kernel): slots are grouped TK at a time, every
+// group walks one shared window of Tmax input samples and slot j of the group has its `taps` weights placed at
+// offset B[k] - B[g*TK] inside it (zeros elsewhere), so one input register feeds TK accumulators.
+struct BandedDev {
+    int p = 0, q = 0;              // scaled ratio p/q (q multiplied up so that a group is at least 16 slots)
+    int taps = 0, TK = 0, G = 0;   // slots per group, groups (G*TK >= q)
+    int Tmax = 0;                  // window steps per group (same for all groups, even)
+    float* C = nullptr;            // [Gpad][Tmax][TK]
+    int* wmin = nullptr;           // [Gpad] first window sample relative to the period base: B[g*TK] - (taps-1)
+    int Gpad = 0;
+};
+struct BandedHost {
+    int p = 0, q = 0, taps = 0, TK = 0, G = 0, Gpad = 0, Tmax = 0;
+    std::vector<float> C; std::vector<int> wmin;
+};
+void build_banded(int kind, const float* sinc_table, long long p, long long q, int TK, int Gpad, BandedHost* out);
+
 struct ResampleLaunch {
     int kind = 0;
+    // banded (register-tiled) path
+    bool banded = false;
+    BandedDev band;
+    int TA = 1, PB = 1, GB = 1, nGB = 1, halo = 0, Pstride = 0;
+    size_t banded_smem = 0; int sm_count = 148;
     double ratio = 1.0;
     double pos0 = 1.0;             // sub-sample position before output 0 (1.0 = reset state)
     bool rational = false;
@@ -117,6 +140,10 @@ struct ResampleLaunch {
 };
 int         choose_tile_out(double ratio);
 cudaError_t launch_resample(const ResampleLaunch& L, cudaStream_t s, long long* launches);
+// CTAs one segment needs under launch configuration L (tile_out outputs each, or period blocks x group blocks)
+long long   resample_ctas_for_segment(const ResampleLaunch& L, long long n0, long long numOut);
+// Fill tile_prefix (n+1 ints) for the segments; returns the CTA total or -1 on overflow.
+int         resample_build_tiles(const ResampleLaunch& L, const Seg* segs, int n, std::vector<int>* prefix);
 
 }  // namespace f9
 
@@ -140,6 +167,12 @@ struct f9_context {
     struct PolyKey { int kind; long long p, q; unsigned epoch; bool operator<(const PolyKey& o) const {
         if (kind != o.kind) return kind < o.kind; if (p != o.p) return p < o.p; if (q != o.q) return q < o.q; return epoch < o.epoch; } };
     std::map<PolyKey, f9::PolyDev> poly_cache;
+    struct BandKey { int kind; long long p, q; int TK, Gpad; unsigned epoch; bool operator<(const BandKey& o) const {
+        return std::tie(kind, p, q, TK, Gpad, epoch) < std::tie(o.kind, o.p, o.q, o.TK, o.Gpad, o.epoch); } };
+    std::map<BandKey, f9::BandedDev> band_cache;
+    int   get_banded(int kind, long long p, long long q, int TK, int Gpad, f9::BandedDev* out);
+    // Choose kernel + tables for (kind, ratio, pos0); fills everything in L except the segment table.
+    int   prepare_resample(int kind, double ratio, double pos0, bool allow_rational, f9::ResampleLaunch* L);
 
     int fail(int code, const char* msg) { err = msg; return code; }
     int fail_cuda(cudaError_t e, const char* what) {

@@ -8,6 +8,11 @@
 // (n = a*q + k  ->  newest input a*p + B[k], B[k] = floor(k*p/q), phase (k*p) mod q) and per-phase weights
 // tabulated on the host; other ratios use a double-double product.  See DESIGN.md "Position arithmetic" for
 // why this stays inside the 2^-20 sample tolerance of the sequential recurrence.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+
 #include "f9_internal.cuh"
 
 namespace f9 {
@@ -183,6 +188,160 @@ generic_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix,
     }
 }
 
+// --------------------------------------------------------------------------------------------- banded, register-tiled
+// WindowedSinc is FP32-FMA bound (400 FLOP per output against 5-13 bytes), so this kernel is built like an SGEMM
+// micro-kernel rather than a streaming copy:
+//   * outputs are indexed (period a, slot k): n = a*q + k reads the inputs ending at a*p + B[k];
+//   * a warp owns one group of TK adjacent slots and 32*TA periods; lane l holds periods l, l+32, ... so the TK
+//     weights of a step are the same for the whole warp: one broadcast LDS.128 per 4 weights;
+//   * the group walks one shared window of Tmax input samples; slot j's taps sit at offset B[k]-B[g*TK] in it
+//     (zero weights elsewhere), so each input register feeds TK FFMAs;
+//   * inputs live in shared memory as whole periods with an odd stride (Pstride) so the 32 lanes of a load hit
+//     32 different banks for any p (p = 320 would otherwise be a 32-way conflict).
+// Per step and warp: TA LDS.32 + TK/4 broadcast LDS.128 wavefronts for TA*TK FFMAs.
+// Stage `total` consecutive input samples starting at channel index gStart into period rows of Xs
+// (element e -> Xs[(e / p) * Pstride + e % p]).  Global reads are 16-byte vectors on the address's own alignment
+// grid (the channel pointer is only float aligned once trimLatency's offset is folded in), four vectors in
+// flight per thread; samples outside the segment's window read as zero.
+__device__ __forceinline__ void stage_rows(const Seg& S, long long gStart, int total, int p, int Pstride, float* __restrict__ Xs) {
+    const long long l0 = gStart - S.inOffset;                       // window index of element 0 (may be negative)
+    const long long addrEl = (long long) (reinterpret_cast<uintptr_t>(S.in) >> 2) + l0;
+    const int a0 = (int) (((addrEl % 4) + 4) % 4);
+    const int head = min(total, (4 - a0) & 3);
+    if ((int) threadIdx.x < head) {
+        const int e = threadIdx.x;
+        Xs[(e / p) * Pstride + (e % p)] = load_in(S, gStart + e);
+    }
+    const int nq = (total - head) >> 2;
+    for (int v0 = threadIdx.x; v0 < nq; v0 += 4 * 256) {
+        float4 val[4];
+        #pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int v = v0 + k * 256;
+            val[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (v < nq) {
+                const long long l = l0 + head + 4LL * v;
+                if (l >= 0 && l + 3 < S.inAvail) val[k] = __ldg(reinterpret_cast<const float4*>(S.in + l));
+                else {
+                    val[k].x = load_in(S, gStart + head + 4 * v);     val[k].y = load_in(S, gStart + head + 4 * v + 1);
+                    val[k].z = load_in(S, gStart + head + 4 * v + 2); val[k].w = load_in(S, gStart + head + 4 * v + 3);
+                }
+            }
+        }
+        #pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int v = v0 + k * 256;
+            if (v < nq) {
+                const int e = head + 4 * v;
+                int al = e / p, u = e - al * p;
+                float* row = Xs + al * Pstride;
+                row[u] = val[k].x; if (++u == p) { u = 0; row += Pstride; }
+                row[u] = val[k].y; if (++u == p) { u = 0; row += Pstride; }
+                row[u] = val[k].z; if (++u == p) { u = 0; row += Pstride; }
+                row[u] = val[k].w;
+            }
+        }
+    }
+    const int tail0 = head + 4 * nq;
+    if (tail0 + (int) threadIdx.x < total) {
+        const int e = tail0 + threadIdx.x;
+        Xs[(e / p) * Pstride + (e % p)] = load_in(S, gStart + e);
+    }
+}
+
+template <int TA, int TK>
+__global__ void __launch_bounds__(256, 1)
+banded_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix, int nSegs, int nTiles, BandedDev P,
+              int PB, int GB, int nGB, int halo, int Pstride, int adding, float gain) {
+    extern __shared__ __align__(16) float smem[];
+    const int Tmax = P.Tmax, p = P.p, q = P.q;
+    float* Cs = smem;                                      // [GB][Tmax][TK]
+    float* Xs = smem + (size_t) GB * Tmax * TK;            // [(halo + NPc + 1) periods][Pstride]
+    const int NPc = 32 * TA * PB;
+
+    // Persistent CTA: gridDim.x is a multiple of nGB, so every tile this CTA visits has the same group block and
+    // the weights are staged exactly once (contiguous in global, 16-byte copies).
+    const int gbIdx = blockIdx.x % nGB;
+    {
+        const float4* __restrict__ src = reinterpret_cast<const float4*>(P.C + (size_t) gbIdx * GB * Tmax * TK);
+        float4* dst = reinterpret_cast<float4*>(Cs);
+        const int n4 = GB * Tmax * TK / 4;
+        for (int i = threadIdx.x; i < n4; i += 256) dst[i] = __ldg(src + i);
+    }
+
+  for (int tileId = blockIdx.x; tileId < nTiles; tileId += gridDim.x) {
+    const int sidx = find_seg(tilePrefix, nSegs, tileId);
+    const Seg S = segs[sidx];
+    const int tile = tileId - tilePrefix[sidx];
+    const int pbIdx = tile / nGB;
+    const long long aFirst = S.n0 / q;
+    const long long A0 = aFirst + (long long) pbIdx * NPc;  // first period of this tile
+
+    __syncthreads();                                        // previous tile's readers are done with Xs
+    stage_rows(S, (A0 - halo) * (long long) p, (NPc + halo + 1) * p, p, Pstride, Xs);
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int item = warp; item < GB * PB; item += 8) {
+        const int gl = item % GB, pl = item / GB;
+        const int g = gbIdx * GB + gl;
+        const int wmin = __ldg(P.wmin + g);
+        // window start inside the period grid: wmin = ashift*p + u0 with 0 <= u0 < p (wmin may be negative)
+        int ashift = wmin / p; if (ashift * p > wmin) --ashift;
+        int u = wmin - ashift * p;
+        const float* xp = Xs + (size_t) (halo + pl * 32 * TA + lane + ashift) * Pstride + u;
+        const float* cp = Cs + (size_t) gl * Tmax * TK;
+
+        // Accumulators are float2 pairs over adjacent slots: Blackwell issues a scalar FFMA every other cycle but a packed
+        // FFMA2 (fma.rn.f32x2) at the same rate, so the pairs are what reaches the FP32 peak.  (x, x) * (c_j, c_j+1).
+        float2 acc[TA][TK / 2];
+        #pragma unroll
+        for (int i = 0; i < TA; ++i)
+            #pragma unroll
+            for (int j = 0; j < TK / 2; ++j) acc[i][j] = make_float2(0.0f, 0.0f);
+
+        // The window is walked in runs that stay inside one period row, so the hot loop carries no boundary test.
+        for (int t = 0; t < Tmax;) {
+            const int run = min(p - u, Tmax - t);
+            #pragma unroll 2
+            for (int r = 0; r < run; ++r) {
+                float2 x[TA];
+                #pragma unroll
+                for (int i = 0; i < TA; ++i) { const float v = xp[(size_t) i * 32 * Pstride + r]; x[i] = make_float2(v, v); }
+                float2 c[TK / 2];
+                #pragma unroll
+                for (int j4 = 0; j4 < TK / 4; ++j4) {
+                    const float4 v = *reinterpret_cast<const float4*>(cp + (size_t) r * TK + 4 * j4);
+                    c[2 * j4] = make_float2(v.x, v.y); c[2 * j4 + 1] = make_float2(v.z, v.w);
+                }
+                #pragma unroll
+                for (int i = 0; i < TA; ++i)
+                    #pragma unroll
+                    for (int j = 0; j < TK / 2; ++j) acc[i][j] = __ffma2_rn(x[i], c[j], acc[i][j]);
+            }
+            t += run; cp += (size_t) run * TK;
+            xp += run + (Pstride - p); u = 0;               // next period row (warp-uniform)
+        }
+
+        // outputs: n = a*q + g*TK + j
+        #pragma unroll
+        for (int i = 0; i < TA; ++i) {
+            const long long a = A0 + pl * 32 * TA + lane + 32 * i;
+            const long long nBase = a * q + (long long) g * TK - S.n0;      // offset into the segment's outputs
+            #pragma unroll
+            for (int j = 0; j < TK; ++j) {
+                const long long o = nBase + j;
+                if (g * TK + j < q && o >= 0 && o < S.numOut) {
+                    float v = (j & 1) ? acc[i][j >> 1].y : acc[i][j >> 1].x;
+                    if (adding) v = __fadd_rn(S.out[o], __fmul_rn(gain, v));
+                    S.out[o] = v;
+                }
+            }
+        }
+    }
+  }
+}
+
 template <typename K>
 cudaError_t set_smem(K kernel, size_t bytes) {
     if (bytes <= 48 * 1024) return cudaSuccess;
@@ -204,6 +363,26 @@ cudaError_t run_generic(const ResampleLaunch& L, size_t smem, cudaStream_t s) {
                                                              L.d_sinc_table, L.tile_out, L.adding, L.gain);
     return cudaGetLastError();
 }
+template <int TA, int TK>
+cudaError_t run_banded(const ResampleLaunch& L, cudaStream_t s) {
+    cudaError_t e = set_smem(banded_kernel<TA, TK>, L.banded_smem);
+    if (e != cudaSuccess) return e;
+    const int perSm = L.banded_smem <= 110 * 1024 ? 2 : 1;           // co-resident CTAs overlap staging with compute
+    int grid = std::min(L.n_tiles, std::max(L.sm_count * perSm, L.nGB));
+    grid -= grid % L.nGB;
+    banded_kernel<TA, TK><<<grid, 256, L.banded_smem, s>>>(L.d_segs, L.d_tile_prefix, L.n_segs, L.n_tiles, L.band, L.PB, L.GB, L.nGB,
+                                                           L.halo, L.Pstride, L.adding, L.gain);
+    return cudaGetLastError();
+}
+template <int TK>
+cudaError_t run_banded_ta(const ResampleLaunch& L, cudaStream_t s) {
+    switch (L.TA) {
+        case 1: return run_banded<1, TK>(L, s);
+        case 2: return run_banded<2, TK>(L, s);
+        case 4: return run_banded<4, TK>(L, s);
+        default: return cudaErrorInvalidValue;
+    }
+}
 
 }  // namespace
 
@@ -215,12 +394,43 @@ int choose_tile_out(double ratio) {
     return tile;
 }
 
+long long resample_ctas_for_segment(const ResampleLaunch& L, long long n0, long long numOut) {
+    if (numOut <= 0) return 0;
+    if (!L.banded) return (numOut + L.tile_out - 1) / L.tile_out;
+    const long long q = L.band.q;
+    const long long aFirst = n0 / q, aLast = (n0 + numOut - 1) / q;
+    const long long NPc = 32LL * L.TA * L.PB;
+    return ((aLast - aFirst + 1 + NPc - 1) / NPc) * L.nGB;
+}
+
+int resample_build_tiles(const ResampleLaunch& L, const Seg* segs, int n, std::vector<int>* prefix) {
+    prefix->assign((size_t) n + 1, 0);
+    long long total = 0;
+    for (int i = 0; i < n; ++i) {
+        total += resample_ctas_for_segment(L, segs[i].n0, segs[i].numOut);
+        if (total > 0x7fffffffLL) return -1;
+        (*prefix)[(size_t) i + 1] = (int) total;
+    }
+    return (int) total;
+}
+
 cudaError_t launch_resample(const ResampleLaunch& L, cudaStream_t s, long long* launches) {
     if (L.n_tiles <= 0) return cudaSuccess;
+    cudaError_t e;
+    if (L.banded) {
+        switch (L.band.TK) {
+            case 8:  e = run_banded_ta<8>(L, s); break;
+            case 12: e = run_banded_ta<12>(L, s); break;
+            case 16: e = run_banded_ta<16>(L, s); break;
+            case 20: e = run_banded_ta<20>(L, s); break;
+            default: return cudaErrorInvalidValue;
+        }
+        if (e == cudaSuccess) ++*launches;
+        return e;
+    }
     const int taps = interp_memory(L.kind);
     const size_t smem = sizeof(float) * ((size_t) ((double) L.tile_out * L.ratio) + (size_t) taps + 8);
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
-    cudaError_t e;
     if (L.rational) {
         switch (L.kind) {
             case F9_WINDOWED_SINC: e = run_poly<200>(L, smem, s); break;
@@ -245,3 +455,82 @@ cudaError_t launch_resample(const ResampleLaunch& L, cudaStream_t s, long long* 
 }
 
 }  // namespace f9
+
+// ------------------------------------------------------------------------------------------------ planning (host)
+using namespace f9;
+
+int f9_context::get_banded(int kind, long long p, long long q, int TK, int Gpad, BandedDev* out) {
+    BandKey key{kind, p, q, TK, Gpad, sinc_epoch};
+    auto it = band_cache.find(key);
+    if (it != band_cache.end()) { *out = it->second; return F9_OK; }
+    BandedHost H;
+    build_banded(kind, sinc_table.data(), p, q, TK, Gpad, &H);
+    BandedDev D; D.p = H.p; D.q = H.q; D.taps = H.taps; D.TK = H.TK; D.G = H.G; D.Gpad = H.Gpad; D.Tmax = H.Tmax;
+    F9_TRY_CUDA(this, cudaMalloc((void**) &D.C, sizeof(float) * H.C.size()));
+    F9_TRY_CUDA(this, cudaMalloc((void**) &D.wmin, sizeof(int) * H.wmin.size()));
+    F9_TRY_CUDA(this, cudaMemcpy(D.C, H.C.data(), sizeof(float) * H.C.size(), cudaMemcpyHostToDevice));
+    F9_TRY_CUDA(this, cudaMemcpy(D.wmin, H.wmin.data(), sizeof(int) * H.wmin.size(), cudaMemcpyHostToDevice));
+    band_cache[key] = D;
+    *out = D;
+    return F9_OK;
+}
+
+// Pick the kernel for (kind, ratio, pos0).  WindowedSinc at a rational ratio from reset state goes to the
+// register-tiled banded kernel; other rational cases to poly_kernel; everything else to generic_kernel.
+int f9_context::prepare_resample(int kind, double ratio, double pos0, bool allow_rational, ResampleLaunch* L) {
+    if (interp_memory(kind) == 0) return fail(F9_ERR_INVALID, "unknown interpolator kind");
+    if (!(ratio > 0.0) || !std::isfinite(ratio)) return fail(F9_ERR_INVALID, "speed ratio must be positive and finite");
+    *L = ResampleLaunch();
+    L->kind = kind; L->ratio = ratio; L->pos0 = pos0;
+    L->d_sinc_table = d_sinc_table;
+    L->tile_out = choose_tile_out(ratio);
+    long long p = 0, q = 0;
+    if (allow_rational && pos0 == 1.0 && find_rational(ratio, 4096, &p, &q) && p <= (1 << 20)) {
+        int rc = get_poly(kind, p, q, &L->poly); if (rc) return rc;
+        L->rational = true;
+        if (kind == F9_WINDOWED_SINC && getenv("F9_NO_BANDED") == nullptr) {
+            // scale p/q so a group of slots is at least 16 wide, then choose TK / TA / block shape for shared memory
+            long long m = 1;
+            while (q * m < 16) m *= 2;
+            const long long ps = p * m, qs = q * m;
+            const int taps = 200;
+            const size_t budget = 200 * 1024;
+            double bestScore = -1.0; int bTK = 0, bTA = 0, bPB = 0, bGB = 0, bnGB = 0, bHalo = 0, bPs = 0; size_t bSmem = 0;
+            int fTK = 0, fTA = 0, fnGB = 0;                      // F9_BANDED_CFG="TK,TA,nGB": force a configuration (experiments)
+            if (const char* cfg = getenv("F9_BANDED_CFG")) sscanf(cfg, "%d,%d,%d", &fTK, &fTA, &fnGB);
+            for (int TK : {20, 16, 12, 8}) {
+                if (fTK && TK != fTK) continue;
+                const int G = (int) ((qs + TK - 1) / TK);
+                for (int nGB = (G + 7) / 8; nGB <= std::min(G, (G + 7) / 8 + 3); ++nGB) {
+                    if (fnGB && nGB != fnGB) continue;
+                    const int GB = (G + nGB - 1) / nGB;
+                    const int PB = std::max(1, 8 / GB);
+                    const int maxShift = (int) (((long long) (TK - 1) * ps) / qs) + 1;
+                    const int Tmax = (taps + maxShift + 1) & ~1;
+                    const int halo = (int) ((taps - 1 + ps - 1) / ps);
+                    const int Ps = (int) ((ps & 1) ? ps : ps + 1);
+                    for (int TA : {4, 2, 1}) {
+                        if (fTA && TA != fTA) continue;
+                        const size_t smem = sizeof(float) * ((size_t) GB * Tmax * TK + (size_t) (32 * TA * PB + halo + 1) * Ps) + 64;
+                        if (smem > budget) continue;
+                        const double useful = (double) qs * taps / ((double) nGB * GB * TK * Tmax);  // band + slot padding
+                        const double warps = (double) (GB * PB) / (8.0 * ((GB * PB + 7) / 8));       // warp balance
+                        const double smemRate = std::min(1.0, (TA * TK / 4.0) / (TA + TK / 4.0));    // FFMA clk / smem clk
+                        const double issue = (double) (TA * TK) / (TA * TK + TA + TK / 4 + 2);       // FFMA share of issue slots
+                        const double restage = 1.0 / (1.0 + 0.15 * (nGB - 1));                       // rows staged once per group block
+                        const double overlap = smem <= 110 * 1024 ? 1.25 : 1.0;                      // two CTAs per SM hide the staging
+                        const double score = useful * warps * smemRate * issue * restage * overlap;
+                        if (score > bestScore) { bestScore = score; bTK = TK; bTA = TA; bPB = PB; bGB = GB; bnGB = nGB; bHalo = halo; bPs = Ps; bSmem = smem; }
+                    }
+                }
+            }
+            if (bestScore > 0.0 && ps <= 8192) {
+                rc = get_banded(kind, ps, qs, bTK, bGB * bnGB, &L->band); if (rc) return rc;
+                L->banded = true; L->TA = bTA; L->PB = bPB; L->GB = bGB; L->nGB = bnGB; L->halo = bHalo; L->Pstride = bPs;
+                L->banded_smem = bSmem; L->sm_count = sm_count;
+            }
+        }
+    }
+    if (!L->banded && (double) L->tile_out * ratio > 45000.0) return fail(F9_ERR_UNSUPPORTED, "speed ratio too large for the tile buffer");
+    return F9_OK;
+}

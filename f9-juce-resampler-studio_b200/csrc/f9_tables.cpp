@@ -5,6 +5,7 @@
 // [JUCE 8.0.10 juce_audio_basics/utilities/juce_WindowedSincInterpolator.cpp, juce_LagrangeInterpolator.cpp,
 //  juce_Interpolators.h -- not vendored by the reference (JuceLibraryCode/JuceHeader.h:16 links the module);
 //  algorithm as recorded in SURVEY.md Appendix A.]
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 
@@ -214,6 +215,43 @@ void position_closed_form(double pos0, double ratio, long long n, long long* c, 
     else if (frac >= 1.0) { fl += 1.0; frac -= 1.0; }
     *c = (long long) fl;
     if (frac_out) *frac_out = frac;
+}
+
+}  // namespace f9
+
+// ---- band-aligned polyphase tables for the register-tiled FIR (see BandedDev in f9_internal.cuh) ----------
+namespace f9 {
+
+void build_banded(int kind, const float* sinc_table, long long p, long long q, int TK, int Gpad, BandedHost* out) {
+    const int taps = interp_memory(kind);
+    const int G = (int) ((q + TK - 1) / TK);
+    if (Gpad < G) Gpad = G;
+    std::vector<int> B((size_t) q);
+    for (long long k = 0; k < q; ++k) B[(size_t) k] = (int) ((k * p) / q);
+    int maxShift = 0;
+    for (int g = 0; g < G; ++g) {
+        const long long k0 = (long long) g * TK, k1 = std::min<long long>(q, k0 + TK) - 1;
+        maxShift = std::max(maxShift, B[(size_t) k1] - B[(size_t) k0]);
+    }
+    const int Tmax = (taps + maxShift + 1) & ~1;
+    out->p = (int) p; out->q = (int) q; out->taps = taps; out->TK = TK; out->G = G; out->Gpad = Gpad; out->Tmax = Tmax;
+    out->C.assign((size_t) Gpad * Tmax * TK, 0.0f);
+    out->wmin.assign((size_t) Gpad, 0);
+    std::vector<float> w((size_t) taps);
+    for (int g = 0; g < G; ++g) {
+        const long long k0 = (long long) g * TK;
+        out->wmin[(size_t) g] = B[(size_t) k0] - (taps - 1);
+        for (int j = 0; j < TK; ++j) {
+            const long long k = k0 + j;
+            if (k >= q) break;                                           // padding slots keep zero weights
+            const long long phi = (k * p) % q;
+            const float offset = (float) ((double) phi / (double) q);    // what (float) subSamplePos is at this phase
+            tap_weights(kind, sinc_table, offset, w.data());
+            const int shift = B[(size_t) k] - B[(size_t) k0];
+            for (int t = 0; t < taps; ++t)
+                out->C[((size_t) g * Tmax + (size_t) (t + shift)) * TK + (size_t) j] = w[(size_t) t];
+        }
+    }
 }
 
 }  // namespace f9
