@@ -114,6 +114,9 @@ void f9_context_destroy(f9_context* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (auto& kv : ctx->poly_cache) { cudaFree(kv.second.B); cudaFree(kv.second.W); }
+    for (auto& kv : ctx->band_cache) { cudaFree(kv.second.C); cudaFree(kv.second.wmin); }
+    for (auto& kv : ctx->umma_cache) { cudaFree((void*) kv.second.W); cudaFree((void*) kv.second.sched); cudaFree((void*) kv.second.ksCount); }
+    if (ctx->d_ovf) cudaFree(ctx->d_ovf);
     if (ctx->d_sinc_table) cudaFree(ctx->d_sinc_table);
     if (ctx->d_arena) cudaFree(ctx->d_arena);
     if (ctx->h_arena) cudaFreeHost(ctx->h_arena);

@@ -119,8 +119,48 @@ struct BandedHost {
 };
 void build_banded(int kind, const float* sinc_table, long long p, long long q, int TK, int Gpad, BandedHost* out);
 
+// Tensor-core polyphase FIR (umma_fir_kernel, f9_umma.cu).  Outputs are indexed (period a, slot k) as above; a tile is
+// 128 periods (the M rows of a tcgen05.mma) x one block of <= 14 groups of 16 slots (N).  K runs over the input window of a
+// period in steps of 16 samples.  Samples and weights are split into an fp16 head and an fp16 tail scaled by 2^11
+// (x = x0 + x1/2048, w = w0 + w1/2048), three products are kept:  D0 += x0*w0,  D1 += x0*w1 + x1*w0,  out = D0 + D1/2048.
+constexpr int kUmmaMaxBlocks = 8;        // group blocks per ratio (passes over the same rows)
+constexpr int kUmmaMaxGroups = 14;       // groups per block: 32 TMEM columns each, 448 of 512
+struct UmmaBlockInfo {
+    int U0;            // K index 0 is input sample a*p + U0 (multiple of 16, <= every window start of the block)
+    int nK;            // K steps (16 samples each) the block's windows span
+    int nStages;       // 32-sample stages staged per tile: covers the last window sample + 3 (loader funnel shift)
+    int nGroups;       // groups in this block
+    int slot0;         // first slot of the block
+    int nEntries;      // MMA schedule entries (one per active (K step, group)); weight tile e is 1 KB at wOff + 1024*e
+    int entryOff;      // offset into sched[]
+    int ksOff;         // offset into ksCount[]
+    int wOff;          // byte offset into W
+};
+struct UmmaHost {
+    int p = 0, q = 0, taps = 0, G = 0, GBL = 0, nGB = 0;
+    int maxEntries = 0, maxNK = 0;
+    UmmaBlockInfo blk[kUmmaMaxBlocks] = {};
+    std::vector<uint8_t> W;              // fp16 weight tiles [2 K chunks][32 rows: 16 x w0, 16 x w1*2048][8], schedule order
+    std::vector<uint16_t> sched;         // bits 0-5 local group, bit 6 first K step of the group, bit 7 last
+    std::vector<uint8_t> ksCount;        // entries per K step
+};
+struct UmmaDev {
+    int p = 0, q = 0, taps = 0, G = 0, GBL = 0, nGB = 0;
+    int maxEntries = 0, maxNK = 0;
+    UmmaBlockInfo blk[kUmmaMaxBlocks] = {};
+    const uint8_t* W = nullptr; const uint16_t* sched = nullptr; const uint8_t* ksCount = nullptr;
+};
+bool build_umma(int kind, const float* sinc_table, long long p, long long q, int GBL, UmmaHost* out);
+size_t umma_smem_bytes(int maxEntries, int maxNK, int stages);
+double umma_cost_per_output(int taps, long long p, long long q, int GBL, size_t* smem2);   // model used to pick the scaling
+
 struct ResampleLaunch {
     int kind = 0;
+    // tensor-core path (takes priority over banded when set; never used with adding)
+    bool umma = false;
+    UmmaDev um;
+    int um_stages = 0; size_t um_smem = 0;
+    unsigned* d_ovf = nullptr;     // device flag: an input sample was outside the fp16 split's range -> fp32 redo
     // banded (register-tiled) path
     bool banded = false;
     BandedDev band;
@@ -140,6 +180,7 @@ struct ResampleLaunch {
 };
 int         choose_tile_out(double ratio);
 cudaError_t launch_resample(const ResampleLaunch& L, cudaStream_t s, long long* launches);
+cudaError_t launch_umma(const ResampleLaunch& L, cudaStream_t s, long long* launches);     // f9_umma.cu
 // CTAs one segment needs under launch configuration L (tile_out outputs each, or period blocks x group blocks)
 long long   resample_ctas_for_segment(const ResampleLaunch& L, long long n0, long long numOut);
 // Fill tile_prefix (n+1 ints) for the segments; returns the CTA total or -1 on overflow.
@@ -171,6 +212,11 @@ struct f9_context {
         return std::tie(kind, p, q, TK, Gpad, epoch) < std::tie(o.kind, o.p, o.q, o.TK, o.Gpad, o.epoch); } };
     std::map<BandKey, f9::BandedDev> band_cache;
     int   get_banded(int kind, long long p, long long q, int TK, int Gpad, f9::BandedDev* out);
+    struct UmmaKey { int kind; long long p, q; int GBL; unsigned epoch; bool operator<(const UmmaKey& o) const {
+        return std::tie(kind, p, q, GBL, epoch) < std::tie(o.kind, o.p, o.q, o.GBL, o.epoch); } };
+    std::map<UmmaKey, f9::UmmaDev> umma_cache;
+    int   get_umma(int kind, long long p, long long q, int GBL, f9::UmmaDev* out);
+    unsigned* d_ovf = nullptr;          // see ResampleLaunch::d_ovf
     // Choose kernel + tables for (kind, ratio, pos0); fills everything in L except the segment table.
     int   prepare_resample(int kind, double ratio, double pos0, bool allow_rational, f9::ResampleLaunch* L);
 

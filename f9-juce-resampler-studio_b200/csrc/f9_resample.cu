@@ -396,6 +396,11 @@ int choose_tile_out(double ratio) {
 
 long long resample_ctas_for_segment(const ResampleLaunch& L, long long n0, long long numOut) {
     if (numOut <= 0) return 0;
+    if (L.umma) {
+        const long long q = L.um.q;
+        const long long aFirst = n0 / q, aLast = (n0 + numOut - 1) / q;
+        return ((aLast - aFirst + 1 + 127) / 128) * L.um.nGB;
+    }
     if (!L.banded) return (numOut + L.tile_out - 1) / L.tile_out;
     const long long q = L.band.q;
     const long long aFirst = n0 / q, aLast = (n0 + numOut - 1) / q;
@@ -417,6 +422,7 @@ int resample_build_tiles(const ResampleLaunch& L, const Seg* segs, int n, std::v
 cudaError_t launch_resample(const ResampleLaunch& L, cudaStream_t s, long long* launches) {
     if (L.n_tiles <= 0) return cudaSuccess;
     cudaError_t e;
+    if (L.umma) return launch_umma(L, s, launches);
     if (L.banded) {
         switch (L.band.TK) {
             case 8:  e = run_banded_ta<8>(L, s); break;
@@ -459,6 +465,27 @@ cudaError_t launch_resample(const ResampleLaunch& L, cudaStream_t s, long long* 
 // ------------------------------------------------------------------------------------------------ planning (host)
 using namespace f9;
 
+int f9_context::get_umma(int kind, long long p, long long q, int GBL, UmmaDev* out) {
+    UmmaKey key{kind, p, q, GBL, sinc_epoch};
+    auto it = umma_cache.find(key);
+    if (it != umma_cache.end()) { *out = it->second; return F9_OK; }
+    UmmaHost H;
+    if (!build_umma(kind, sinc_table.data(), p, q, GBL, &H)) return fail(F9_ERR_INVALID, "umma table build failed");
+    UmmaDev D; D.p = H.p; D.q = H.q; D.taps = H.taps; D.G = H.G; D.GBL = H.GBL; D.nGB = H.nGB; D.maxEntries = H.maxEntries; D.maxNK = H.maxNK;
+    for (int b = 0; b < kUmmaMaxBlocks; ++b) D.blk[b] = H.blk[b];
+    uint8_t* dW = nullptr; uint16_t* dS = nullptr; uint8_t* dK = nullptr;
+    F9_TRY_CUDA(this, cudaMalloc((void**) &dW, H.W.size()));
+    F9_TRY_CUDA(this, cudaMalloc((void**) &dS, sizeof(uint16_t) * H.sched.size()));
+    F9_TRY_CUDA(this, cudaMalloc((void**) &dK, H.ksCount.size()));
+    F9_TRY_CUDA(this, cudaMemcpy(dW, H.W.data(), H.W.size(), cudaMemcpyHostToDevice));
+    F9_TRY_CUDA(this, cudaMemcpy(dS, H.sched.data(), sizeof(uint16_t) * H.sched.size(), cudaMemcpyHostToDevice));
+    F9_TRY_CUDA(this, cudaMemcpy(dK, H.ksCount.data(), H.ksCount.size(), cudaMemcpyHostToDevice));
+    D.W = dW; D.sched = dS; D.ksCount = dK;
+    umma_cache[key] = D;
+    *out = D;
+    return F9_OK;
+}
+
 int f9_context::get_banded(int kind, long long p, long long q, int TK, int Gpad, BandedDev* out) {
     BandKey key{kind, p, q, TK, Gpad, sinc_epoch};
     auto it = band_cache.find(key);
@@ -488,6 +515,36 @@ int f9_context::prepare_resample(int kind, double ratio, double pos0, bool allow
     if (allow_rational && pos0 == 1.0 && find_rational(ratio, 4096, &p, &q) && p <= (1 << 20)) {
         int rc = get_poly(kind, p, q, &L->poly); if (rc) return rc;
         L->rational = true;
+        L->sm_count = sm_count;
+        if (getenv("F9_NO_UMMA") == nullptr && interp_memory(kind) >= 2) {
+            // Tensor-core path: scale p/q by m so that a period has 64..224 slots, choose the scaling / block size with the
+            // lowest modelled cost whose tables fit shared memory with at least two staging buffers.
+            const int taps = interp_memory(kind);
+            double best = 1e30; long long bm = 0; int bGBL = 0;
+            for (long long m = 1; m * q <= 16LL * kUmmaMaxGroups * kUmmaMaxBlocks && m * p <= 8192; ++m) {
+                const long long ps = p * m, qs = q * m;
+                if (qs < 48 && (m + 1) * q <= 224) continue;                       // too few slots per period: keep scaling
+                const int G = (int) ((qs + 15) / 16);
+                for (int nGB = (G + kUmmaMaxGroups - 1) / kUmmaMaxGroups; nGB <= kUmmaMaxBlocks && nGB <= G; ++nGB) {
+                    const int GBL = (G + nGB - 1) / nGB;
+                    size_t smem2 = 0;
+                    const double c = umma_cost_per_output(taps, ps, qs, GBL, &smem2);
+                    if (smem2 > 227 * 1024) continue;
+                    if (c < best) { best = c; bm = m; bGBL = GBL; }
+                    break;                                                          // more blocks only cost more
+                }
+                if (qs >= 224) break;
+            }
+            if (bm > 0) {
+                if (!d_ovf) F9_TRY_CUDA(this, cudaMalloc((void**) &d_ovf, sizeof(unsigned)));
+                rc = get_umma(kind, p * bm, q * bm, bGBL, &L->um); if (rc) return rc;
+                int stages = 2;
+                while (stages < 4 && umma_smem_bytes(L->um.maxEntries, L->um.maxNK, stages + 1) <= 227 * 1024) ++stages;
+                L->um_stages = stages; L->um_smem = umma_smem_bytes(L->um.maxEntries, L->um.maxNK, stages);
+                L->d_ovf = d_ovf; L->umma = true;
+                return F9_OK;
+            }
+        }
         if (kind == F9_WINDOWED_SINC && getenv("F9_NO_BANDED") == nullptr) {
             // scale p/q so a group of slots is at least 16 wide, then choose TK / TA / block shape for shared memory
             long long m = 1;

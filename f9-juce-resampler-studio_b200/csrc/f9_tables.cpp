@@ -255,3 +255,159 @@ void build_banded(int kind, const float* sinc_table, long long p, long long q, i
 }
 
 }  // namespace f9
+
+// ---- tensor-core FIR tables (see UmmaHost in f9_internal.cuh) ---------------------------------------------
+namespace f9 {
+namespace {
+
+// float -> IEEE binary16 bits, round to nearest even (normals, subnormals, overflow to infinity).
+uint16_t f32_to_f16_bits(float f) {
+    uint32_t x; std::memcpy(&x, &f, 4);
+    const uint32_t sign = (x >> 16) & 0x8000u;
+    x &= 0x7fffffffu;
+    if (x >= 0x7f800000u) return (uint16_t) (sign | (x > 0x7f800000u ? 0x7e00u : 0x7c00u));
+    if (x >= 0x477ff000u) return (uint16_t) (sign | 0x7c00u);                   // rounds to >= 65520 -> inf
+    if (x < 0x33000001u) return (uint16_t) sign;                               // < 2^-25 (or exactly 2^-25: ties to even 0)
+    const int e = (int) (x >> 23) - 127;
+    uint32_t m = (x & 0x7fffffu) | 0x800000u;                                  // 24-bit significand
+    int shift;                                                                 // bits dropped from m
+    uint32_t base;
+    if (e >= -14) { shift = 13; base = (uint32_t) (e + 15) << 10; m &= 0x7fffffu; }
+    else { shift = 13 + (-14 - e); base = 0; }                                 // subnormal: keep the leading one
+    const uint32_t q = m >> shift, rem = m & ((1u << shift) - 1), half = 1u << (shift - 1);
+    uint32_t r = base + q;
+    if (rem > half || (rem == half && (r & 1))) ++r;                           // carries ripple into the exponent correctly
+    return (uint16_t) (sign | r);
+}
+float f16_bits_to_f32(uint16_t h) {
+    const uint32_t sign = (uint32_t) (h & 0x8000u) << 16;
+    const int e = (h >> 10) & 31; const uint32_t m = h & 0x3ffu;
+    float v;
+    if (e == 0) v = std::ldexp((float) m, -24);
+    else if (e == 31) v = m ? NAN : INFINITY;
+    else v = std::ldexp((float) (m | 0x400u), e - 25);
+    uint32_t b; std::memcpy(&b, &v, 4); b |= sign; std::memcpy(&v, &b, 4);
+    return v;
+}
+inline long long floor16(long long x) { return x >= 0 ? (x / 16) * 16 : -(((-x) + 15) / 16) * 16; }
+
+struct GroupGeom { long long t0; int ksteps; long long wend; };   // K origin of the group's first step (multiple of 16), steps, window end
+void group_geom(long long p, long long q, int taps, int g, GroupGeom* out) {
+    const long long k0 = 16LL * g, k1 = std::min<long long>(q, k0 + 16) - 1;
+    const long long wmin = (k0 * p) / q - (taps - 1), wend = (k1 * p) / q + 1;
+    out->t0 = floor16(wmin);
+    out->ksteps = (int) ((wend - out->t0 + 15) / 16);
+    out->wend = wend;
+}
+
+}  // namespace
+
+size_t umma_smem_bytes(int maxEntries, int maxNK, int stages) {
+    const size_t w = (size_t) maxEntries * 1024;
+    const size_t ring = (size_t) stages * 8 * (128 * 16 + 32);
+    const size_t epi = 128 * 36 * 4;
+    const size_t sched = ((size_t) maxEntries * 2 + 15) / 16 * 16 + ((size_t) maxNK + 15) / 16 * 16;
+    const size_t bars = (size_t) (2 * stages + 2 * kUmmaMaxGroups) * 8 + 16;
+    return w + ring + epi + sched + bars + 128;       // + alignment slack
+}
+
+// Relative cost (SM cycles per output) of running ratio p/q with GBL groups per block: the tensor pipe
+// (tcgen05.cp 64 clk per 4 KB operand tile, 24 clk of MMAs per active (K step, group)) against the load/store unit
+// (one wavefront per 128 bytes loaded, stored to shared memory, and three per 128 bytes of output).
+double umma_cost_per_output(int taps, long long p, long long q, int GBL, size_t* smem2) {
+    const int G = (int) ((q + 15) / 16);
+    const int nGB = (G + GBL - 1) / GBL;
+    double tensor = 0.0, lsu = 0.0; int maxEntries = 0, maxNK = 0;
+    for (int b = 0; b < nGB; ++b) {
+        long long lo = (1LL << 60), hi = -(1LL << 60); int entries = 0;
+        for (int g = b * GBL; g < std::min(G, (b + 1) * GBL); ++g) {
+            GroupGeom gg; group_geom(p, q, taps, g, &gg);
+            lo = std::min(lo, gg.t0); hi = std::max(hi, gg.t0 + 16LL * gg.ksteps); entries += gg.ksteps;
+        }
+        const int nK = (int) ((hi - lo) / 16);
+        tensor += 128.0 * nK + 24.0 * entries;
+        lsu += 2.0 * nK * 16 * 128 * 4 / 128.0;
+        maxEntries = std::max(maxEntries, entries); maxNK = std::max(maxNK, nK);
+    }
+    lsu += 3.0 * (double) q * 128 * 4 / 128.0;
+    if (smem2) *smem2 = umma_smem_bytes(maxEntries, maxNK + 1, 2);
+    return std::max(tensor, lsu) / (128.0 * (double) q);
+}
+
+bool build_umma(int kind, const float* sinc_table, long long p, long long q, int GBL, UmmaHost* out) {
+    const int taps = interp_memory(kind);
+    const int G = (int) ((q + 15) / 16);
+    if (GBL < 1 || GBL > kUmmaMaxGroups) return false;
+    const int nGB = (G + GBL - 1) / GBL;
+    if (nGB > kUmmaMaxBlocks) return false;
+    *out = UmmaHost();
+    out->p = (int) p; out->q = (int) q; out->taps = taps; out->G = G; out->GBL = GBL; out->nGB = nGB;
+    std::vector<float> w((size_t) taps);
+    std::vector<float> wslot((size_t) 16 * taps);
+    for (int b = 0; b < nGB; ++b) {
+        UmmaBlockInfo& BI = out->blk[b];
+        const int g0 = b * GBL, g1 = std::min(G, g0 + GBL);
+        std::vector<GroupGeom> geo((size_t) (g1 - g0));
+        long long lo = (1LL << 60), hi = -(1LL << 60), wendMax = -(1LL << 60);
+        for (int g = g0; g < g1; ++g) {
+            group_geom(p, q, taps, g, &geo[(size_t) (g - g0)]);
+            lo = std::min(lo, geo[(size_t) (g - g0)].t0);
+            hi = std::max(hi, geo[(size_t) (g - g0)].t0 + 16LL * geo[(size_t) (g - g0)].ksteps);
+            wendMax = std::max(wendMax, geo[(size_t) (g - g0)].wend);
+        }
+        BI.U0 = (int) lo; BI.nK = (int) ((hi - lo) / 16); BI.nGroups = g1 - g0; BI.slot0 = g0 * 16;
+        BI.nStages = std::max((BI.nK + 1) / 2, (int) ((wendMax - lo + 3 + 31) / 32));
+        BI.entryOff = (int) out->sched.size(); BI.ksOff = (int) out->ksCount.size(); BI.wOff = (int) out->W.size();
+        // per-slot taps of every group of the block, then the tiles in schedule order (K step major, group minor)
+        std::vector<std::vector<float>> gw((size_t) (g1 - g0));
+        std::vector<std::vector<int>> gshift((size_t) (g1 - g0));
+        for (int g = g0; g < g1; ++g) {
+            auto& W = gw[(size_t) (g - g0)]; auto& S = gshift[(size_t) (g - g0)];
+            W.assign((size_t) 16 * taps, 0.0f); S.assign(16, -1);
+            for (int s = 0; s < 16; ++s) {
+                const long long k = 16LL * g + s;
+                if (k >= q) break;
+                const long long phi = (k * p) % q;
+                const float offset = (float) ((double) phi / (double) q);
+                tap_weights(kind, sinc_table, offset, w.data());
+                std::memcpy(&W[(size_t) s * taps], w.data(), sizeof(float) * (size_t) taps);
+                S[(size_t) s] = (int) ((k * p) / q - (taps - 1) - geo[(size_t) (g - g0)].t0);   // K offset of tap 0 inside the group window
+            }
+        }
+        int entries = 0;
+        for (int ks = 0; ks < BI.nK; ++ks) {
+            int cnt = 0;
+            for (int g = g0; g < g1; ++g) {
+                const GroupGeom& gg = geo[(size_t) (g - g0)];
+                const int first = (int) ((gg.t0 - lo) / 16);
+                if (ks < first || ks >= first + gg.ksteps) continue;
+                const int j = ks - first;
+                out->sched.push_back((uint16_t) ((g - g0) | (j == 0 ? 0x40 : 0) | (j == gg.ksteps - 1 ? 0x80 : 0)));
+                const size_t base = out->W.size();
+                out->W.resize(base + 1024, 0);
+                for (int s = 0; s < 16; ++s) {
+                    const int sh = gshift[(size_t) (g - g0)][(size_t) s];
+                    if (sh < 0) continue;
+                    for (int kk = 0; kk < 16; ++kk) {
+                        const int tap = 16 * j + kk - sh;
+                        if (tap < 0 || tap >= taps) continue;
+                        const float wv = gw[(size_t) (g - g0)][(size_t) s * taps + (size_t) tap];
+                        const uint16_t h0 = f32_to_f16_bits(wv);
+                        const uint16_t h1 = f32_to_f16_bits((wv - f16_bits_to_f32(h0)) * 2048.0f);
+                        const size_t off0 = base + (size_t) (kk / 8) * 512 + (size_t) s * 16 + (size_t) (kk % 8) * 2;
+                        const size_t off1 = off0 + 16 * 16;
+                        std::memcpy(&out->W[off0], &h0, 2); std::memcpy(&out->W[off1], &h1, 2);
+                    }
+                }
+                ++cnt; ++entries;
+            }
+            out->ksCount.push_back((uint8_t) cnt);
+        }
+        BI.nEntries = entries;
+        out->maxEntries = std::max(out->maxEntries, entries);
+        out->maxNK = std::max(out->maxNK, BI.nK);
+    }
+    return true;
+}
+
+}  // namespace f9
