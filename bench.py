@@ -175,7 +175,15 @@ def run_gpu(args, rank: int, local_rank: int, world: int):
     ctx.set_stream(stream.cuda_stream)
     L = f9.lib()
 
-    caps = W.fill_device(batch, first_file, dev)                          # [files, ch, cap] resident in HBM
+    caps0 = W.fill_device(batch, first_file, dev)                         # [files, ch, cap] resident in HBM
+    # Resident layout = the library's own upload layout (f9_batch.cu): each capture sits so that its TRIMMED start
+    # (capture + latency frames) is 16-byte aligned; --unaligned keeps the capture's first frame aligned instead.
+    pads = [0 if args.unaligned else (-lat) % 4 for lat in batch.latency_frames]
+    cap_stride = batch.cap_frames + 64
+    caps = torch.zeros((batch.files, batch.num_ch, cap_stride), dtype=torch.float32, device=dev)
+    for i in range(batch.files):
+        caps[i, :, pads[i]:pads[i] + batch.cap_frames] = caps0[i]
+    del caps0
     n_out = f9.resampled_length(batch.src_frames, batch.fs_in, batch.fs_out)
     out_stride = (n_out + 63) // 64 * 64
     outs = torch.empty((batch.files, batch.num_ch, out_stride), dtype=torch.float32, device=dev)
@@ -190,13 +198,13 @@ def run_gpu(args, rank: int, local_rank: int, world: int):
     tails = (f9.TailParams * batch.files)()
     segs = (f9.ResampleSeg * (batch.files * batch.num_ch))()
     for i in range(batch.files):
-        base = caps.data_ptr() + 4 * i * batch.num_ch * batch.cap_frames
-        bufs[i] = f9.DevBuffer(base, batch.cap_frames, batch.num_ch, batch.cap_frames)
+        base = caps.data_ptr() + 4 * (i * batch.num_ch * cap_stride + pads[i])
+        bufs[i] = f9.DevBuffer(base, cap_stride, batch.num_ch, batch.cap_frames)
         lat = batch.latency_frames[i]
         tails[i] = f9.TailParams(batch.src_frames + lat, win, hop, req, f9.TAIL_RMS, 1, -90.0, 0.0)
         copied = max(0, min(batch.src_frames, batch.cap_frames - lat))    # trimLatency arithmetic (MainComponent.cpp:833-845)
         for c in range(batch.num_ch):
-            segs[i * batch.num_ch + c] = f9.ResampleSeg(base + 4 * (c * batch.cap_frames + lat), 0, copied,
+            segs[i * batch.num_ch + c] = f9.ResampleSeg(base + 4 * (c * cap_stride + lat), 0, copied,
                                                         outs.data_ptr() + 4 * (i * batch.num_ch + c) * out_stride, 0, n_out)
     plans = {}
     for kind in (f9.WINDOWED_SINC, f9.LAGRANGE):
@@ -256,8 +264,9 @@ def run_gpu(args, rank: int, local_rank: int, world: int):
         return
 
     # ---- e2e: host buffers through f9_process_batch, H2D + D2H inside the timed region ----
-    caps_h = torch.empty(caps.shape, dtype=torch.float32, pin_memory=True)
-    caps_h.copy_(caps)
+    caps_h = torch.empty((batch.files, batch.num_ch, batch.cap_frames), dtype=torch.float32, pin_memory=True)
+    for i in range(batch.files):                                          # host buffers are plain juce::AudioBuffer-style planes
+        caps_h[i].copy_(caps[i, :, pads[i]:pads[i] + batch.cap_frames])
     outs_h = torch.empty((batch.files, batch.num_ch, n_out), dtype=torch.float32, pin_memory=True)
     torch.cuda.synchronize(dev)
     fp = C.POINTER(C.c_float)
@@ -365,6 +374,7 @@ def main():
     ap.add_argument("--ref-files", type=int, default=16, help="files in the CPU baseline sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--kernel-only", action="store_true", help="development: print kernel times only")
+    ap.add_argument("--unaligned", action="store_true", help="resident captures start (not their trimmed start) on 16 bytes")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -55,8 +55,12 @@ int run_chunk(f9_context* ctx, const f9_job* jobs, f9_result* results, const std
     for (int t = 0; t < n; ++t) {
         const f9_job& J = jobs[idx[(size_t) t]];
         JobPlan& P = plans[(size_t) t];
-        const long long cs = pad64(J.captured_frames);
-        float* d_cap = (float*) ctx->d_alloc(sizeof(float) * (size_t) cs * J.numCh);
+        // trimLatency is fused into the resampler as a pointer offset of `start` frames: place the capture so that this
+        // trimmed start (not the capture's first frame) falls on a 16-byte boundary, which lets the FIR's loader use
+        // aligned 128-bit loads for every row (f9_umma.cu, loader_role<true>).
+        const int padA = (P.convert && P.start > 0) ? ((4 - (P.start & 3)) & 3) : 0;
+        const long long cs = pad64(J.captured_frames + 4);
+        float* d_cap = (float*) ctx->d_alloc(sizeof(float) * (size_t) cs * J.numCh) + padA;
         for (int c = 0; c < J.numCh; ++c)
             if (J.captured_frames > 0)
                 F9_TRY_CUDA(ctx, cudaMemcpyAsync(d_cap + c * cs, J.captured[c], sizeof(float) * (size_t) J.captured_frames, cudaMemcpyHostToDevice, s));
@@ -232,7 +236,7 @@ extern "C" int f9_process_batch(f9_context* ctx, const f9_job* jobs, int n_jobs,
             const long long startFrame = (long long) J.original_length + std::max(P.latency_frames, 0);
             P.polls = (int) std::max<long long>(0, (J.captured_frames - startFrame) / J.tail_hop);
         }
-        P.bytes = sizeof(float) * (size_t) J.numCh * (size_t) (pad64(J.captured_frames) + pad64(P.out_frames) + pad64(J.original_length))
+        P.bytes = sizeof(float) * (size_t) J.numCh * (size_t) (pad64(J.captured_frames + 4) + pad64(P.out_frames) + pad64(J.original_length))
                   + (size_t) P.out_frames * J.numCh * 3 + 4096;
         R.latency_frames = P.latency_frames; R.trim_start = P.start; R.frames_copied = P.copied;
         R.out_frames = P.out_frames; R.tail_polls = P.polls;

@@ -125,6 +125,7 @@ void build_banded(int kind, const float* sinc_table, long long p, long long q, i
 // (x = x0 + x1/2048, w = w0 + w1/2048), three products are kept:  D0 += x0*w0,  D1 += x0*w1 + x1*w0,  out = D0 + D1/2048.
 constexpr int kUmmaMaxBlocks = 8;        // group blocks per ratio (passes over the same rows)
 constexpr int kUmmaMaxGroups = 14;       // groups per block: 32 TMEM columns each, 448 of 512
+constexpr int kUmmaMaxNK = 64;           // K steps per block (period + taps + alignment <= 1024 input samples)
 struct UmmaBlockInfo {
     int U0;            // K index 0 is input sample a*p + U0 (multiple of 16, <= every window start of the block)
     int nK;            // K steps (16 samples each) the block's windows span
@@ -132,23 +133,31 @@ struct UmmaBlockInfo {
     int nGroups;       // groups in this block
     int slot0;         // first slot of the block
     int nEntries;      // MMA schedule entries (one per active (K step, group)); weight tile e is 1 KB at wOff + 1024*e
-    int entryOff;      // offset into sched[]
-    int ksOff;         // offset into ksCount[]
     int wOff;          // byte offset into W
 };
 struct UmmaHost {
     int p = 0, q = 0, taps = 0, G = 0, GBL = 0, nGB = 0;
     int maxEntries = 0, maxNK = 0;
     UmmaBlockInfo blk[kUmmaMaxBlocks] = {};
+    // MMA schedule, one word per K step: the groups whose window contains the step are a contiguous range (windows move
+    // monotonically with the slot), the ones starting at this step are its top end, the ones finishing its bottom end.
+    // bits 0-3 first active group, 4-7 active count, 8-11 how many start here, 12-15 how many finish here,
+    // 16-19 how many (bottom end) are past their split step, 20-23 how many of those cross it at this step.
+    // (A per-entry operand list in kernel parameters was tried: its constant-cache misses made the issue 2x slower.)
+    uint32_t ksWord[kUmmaMaxBlocks][kUmmaMaxNK] = {};
+    // Accumulation split (poolN > 0): the tensor core truncates the fp32 accumulator after every MMA, so x0*w0 of the K
+    // steps after the window's centre (small partial sums) goes to a second accumulator D0B taken from a pool of poolN
+    // 16-column slots (group g uses slot g % poolN); the epilogue adds D0A + D0B.  split = first K step of the second part.
+    int poolN = 0, split = 0;
     std::vector<uint8_t> W;              // fp16 weight tiles [2 K chunks][32 rows: 16 x w0, 16 x w1*2048][8], schedule order
-    std::vector<uint16_t> sched;         // bits 0-5 local group, bit 6 first K step of the group, bit 7 last
-    std::vector<uint8_t> ksCount;        // entries per K step
 };
 struct UmmaDev {
     int p = 0, q = 0, taps = 0, G = 0, GBL = 0, nGB = 0;
     int maxEntries = 0, maxNK = 0;
     UmmaBlockInfo blk[kUmmaMaxBlocks] = {};
-    const uint8_t* W = nullptr; const uint16_t* sched = nullptr; const uint8_t* ksCount = nullptr;
+    uint32_t ksWord[kUmmaMaxBlocks][kUmmaMaxNK] = {};
+    int poolN = 0, split = 0;
+    const uint8_t* W = nullptr;
 };
 bool build_umma(int kind, const float* sinc_table, long long p, long long q, int GBL, UmmaHost* out);
 size_t umma_smem_bytes(int maxEntries, int maxNK, int stages);
@@ -160,6 +169,7 @@ struct ResampleLaunch {
     bool umma = false;
     UmmaDev um;
     int um_stages = 0; size_t um_smem = 0;
+    bool um_aligned = false;       // every row piece of every segment starts on 16 bytes (set by resample_build_tiles)
     unsigned* d_ovf = nullptr;     // device flag: an input sample was outside the fp16 split's range -> fp32 redo
     // banded (register-tiled) path
     bool banded = false;
@@ -184,7 +194,7 @@ cudaError_t launch_umma(const ResampleLaunch& L, cudaStream_t s, long long* laun
 // CTAs one segment needs under launch configuration L (tile_out outputs each, or period blocks x group blocks)
 long long   resample_ctas_for_segment(const ResampleLaunch& L, long long n0, long long numOut);
 // Fill tile_prefix (n+1 ints) for the segments; returns the CTA total or -1 on overflow.
-int         resample_build_tiles(const ResampleLaunch& L, const Seg* segs, int n, std::vector<int>* prefix);
+int         resample_build_tiles(ResampleLaunch& L, const Seg* segs, int n, std::vector<int>* prefix);
 
 }  // namespace f9
 

@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 #include "f9_internal.cuh"
 
@@ -408,9 +409,18 @@ long long resample_ctas_for_segment(const ResampleLaunch& L, long long n0, long 
     return ((aLast - aFirst + 1 + NPc - 1) / NPc) * L.nGB;
 }
 
-int resample_build_tiles(const ResampleLaunch& L, const Seg* segs, int n, std::vector<int>* prefix) {
+int resample_build_tiles(ResampleLaunch& L, const Seg* segs, int n, std::vector<int>* prefix) {
     prefix->assign((size_t) n + 1, 0);
     long long total = 0;
+    if (L.umma) {
+        // row pieces start at in + (n0/q + 128*pb + row)*p + U0 - inOffset floats: all on 16 bytes iff p % 4 == 0 (U0 is a
+        // multiple of 16) and every segment's (in - inOffset) is
+        bool aligned = (L.um.p & 3) == 0;
+        for (int i = 0; i < n && aligned; ++i)
+            if (segs[i].numOut > 0 && ((((long long) (reinterpret_cast<uintptr_t>(segs[i].in) >> 2) - segs[i].inOffset) & 3) != 0 ||
+                                       (reinterpret_cast<uintptr_t>(segs[i].in) & 3) != 0)) aligned = false;
+        L.um_aligned = aligned && getenv("F9_UMMA_UNALIGNED") == nullptr;
+    }
     for (int i = 0; i < n; ++i) {
         total += resample_ctas_for_segment(L, segs[i].n0, segs[i].numOut);
         if (total > 0x7fffffffLL) return -1;
@@ -473,14 +483,12 @@ int f9_context::get_umma(int kind, long long p, long long q, int GBL, UmmaDev* o
     if (!build_umma(kind, sinc_table.data(), p, q, GBL, &H)) return fail(F9_ERR_INVALID, "umma table build failed");
     UmmaDev D; D.p = H.p; D.q = H.q; D.taps = H.taps; D.G = H.G; D.GBL = H.GBL; D.nGB = H.nGB; D.maxEntries = H.maxEntries; D.maxNK = H.maxNK;
     for (int b = 0; b < kUmmaMaxBlocks; ++b) D.blk[b] = H.blk[b];
-    uint8_t* dW = nullptr; uint16_t* dS = nullptr; uint8_t* dK = nullptr;
+    std::memcpy(D.ksWord, H.ksWord, sizeof(D.ksWord));
+    D.poolN = H.poolN; D.split = H.split;
+    uint8_t* dW = nullptr;
     F9_TRY_CUDA(this, cudaMalloc((void**) &dW, H.W.size()));
-    F9_TRY_CUDA(this, cudaMalloc((void**) &dS, sizeof(uint16_t) * H.sched.size()));
-    F9_TRY_CUDA(this, cudaMalloc((void**) &dK, H.ksCount.size()));
     F9_TRY_CUDA(this, cudaMemcpy(dW, H.W.data(), H.W.size(), cudaMemcpyHostToDevice));
-    F9_TRY_CUDA(this, cudaMemcpy(dS, H.sched.data(), sizeof(uint16_t) * H.sched.size(), cudaMemcpyHostToDevice));
-    F9_TRY_CUDA(this, cudaMemcpy(dK, H.ksCount.data(), H.ksCount.size(), cudaMemcpyHostToDevice));
-    D.W = dW; D.sched = dS; D.ksCount = dK;
+    D.W = dW;
     umma_cache[key] = D;
     *out = D;
     return F9_OK;
@@ -521,7 +529,7 @@ int f9_context::prepare_resample(int kind, double ratio, double pos0, bool allow
             // lowest modelled cost whose tables fit shared memory with at least two staging buffers.
             const int taps = interp_memory(kind);
             double best = 1e30; long long bm = 0; int bGBL = 0;
-            for (long long m = 1; m * q <= 16LL * kUmmaMaxGroups * kUmmaMaxBlocks && m * p <= 8192; ++m) {
+            for (long long m = 1; m * q <= 16LL * kUmmaMaxGroups * kUmmaMaxBlocks && m * p + taps + 48 <= 16 * kUmmaMaxNK; ++m) {
                 const long long ps = p * m, qs = q * m;
                 if (qs < 48 && (m + 1) * q <= 224) continue;                       // too few slots per period: keep scaling
                 const int G = (int) ((qs + 15) / 16);
@@ -537,12 +545,15 @@ int f9_context::prepare_resample(int kind, double ratio, double pos0, bool allow
             }
             if (bm > 0) {
                 if (!d_ovf) F9_TRY_CUDA(this, cudaMalloc((void**) &d_ovf, sizeof(unsigned)));
-                rc = get_umma(kind, p * bm, q * bm, bGBL, &L->um); if (rc) return rc;
-                int stages = 2;
-                while (stages < 4 && umma_smem_bytes(L->um.maxEntries, L->um.maxNK, stages + 1) <= 227 * 1024) ++stages;
-                L->um_stages = stages; L->um_smem = umma_smem_bytes(L->um.maxEntries, L->um.maxNK, stages);
-                L->d_ovf = d_ovf; L->umma = true;
-                return F9_OK;
+                rc = get_umma(kind, p * bm, q * bm, bGBL, &L->um);
+                if (rc == F9_OK) {
+                    int stages = 2;
+                    while (stages < 4 && umma_smem_bytes(L->um.maxEntries, L->um.maxNK, stages + 1) <= 227 * 1024) ++stages;
+                    L->um_stages = stages; L->um_smem = umma_smem_bytes(L->um.maxEntries, L->um.maxNK, stages);
+                    L->d_ovf = d_ovf; L->umma = true;
+                    return F9_OK;
+                }
+                if (rc != F9_ERR_INVALID) return rc;                                // tables this kernel cannot express: CUDA-core paths
             }
         }
         if (kind == F9_WINDOWED_SINC && getenv("F9_NO_BANDED") == nullptr) {

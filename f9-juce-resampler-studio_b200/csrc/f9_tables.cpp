@@ -306,7 +306,7 @@ size_t umma_smem_bytes(int maxEntries, int maxNK, int stages) {
     const size_t w = (size_t) maxEntries * 1024;
     const size_t ring = (size_t) stages * 8 * (128 * 16 + 32);
     const size_t epi = 128 * 36 * 4;
-    const size_t sched = ((size_t) maxEntries * 2 + 15) / 16 * 16 + ((size_t) maxNK + 15) / 16 * 16;
+    const size_t sched = 0; (void) maxNK;
     const size_t bars = (size_t) (2 * stages + 2 * kUmmaMaxGroups) * 8 + 16;
     return w + ring + epi + sched + bars + 128;       // + alignment slack
 }
@@ -342,6 +342,28 @@ bool build_umma(int kind, const float* sinc_table, long long p, long long q, int
     if (nGB > kUmmaMaxBlocks) return false;
     *out = UmmaHost();
     out->p = (int) p; out->q = (int) q; out->taps = taps; out->G = G; out->GBL = GBL; out->nGB = nGB;
+    // accumulation split: only for long windows; the split step is the same for every group (first step past every slot's
+    // centre tap), which keeps "past the split" a bottom-end range of the active groups.
+    int poolN = GBL <= 10 ? 8 : (GBL <= 12 ? 4 : 0), split = 0;
+    if (taps >= 64 && poolN > 0) {
+        for (int g = 0; g < G; ++g) {
+            GroupGeom gg; group_geom(p, q, taps, g, &gg);
+            const long long k1 = std::min<long long>(q, 16LL * g + 16) - 1;
+            const long long centre = (k1 * p) / q - (taps - 1) - gg.t0 + taps / 2 + 2;     // K offset of the last slot's centre tap
+            split = std::max(split, (int) ((centre + 8 + 15) / 16));
+        }
+        for (int g = 0; g < G && poolN > 0; ++g) {
+            GroupGeom gg; group_geom(p, q, taps, g, &gg);
+            if (gg.ksteps <= split) poolN = 0;                                              // a group without a second part
+            const int gl = g % GBL;
+            if (gl >= poolN && poolN > 0) {                                                 // slot reuse inside a tile: the previous
+                GroupGeom gp; group_geom(p, q, taps, g - poolN, &gp);                       // user must have finished before
+                if (gg.t0 / 16 + split < gp.t0 / 16 + gp.ksteps) poolN = 0;                 // this group crosses its split
+            }
+        }
+    } else poolN = 0;
+    if (poolN == 0) split = 0;
+    out->poolN = poolN; out->split = split;
     std::vector<float> w((size_t) taps);
     std::vector<float> wslot((size_t) 16 * taps);
     for (int b = 0; b < nGB; ++b) {
@@ -357,7 +379,8 @@ bool build_umma(int kind, const float* sinc_table, long long p, long long q, int
         }
         BI.U0 = (int) lo; BI.nK = (int) ((hi - lo) / 16); BI.nGroups = g1 - g0; BI.slot0 = g0 * 16;
         BI.nStages = std::max((BI.nK + 1) / 2, (int) ((wendMax - lo + 3 + 31) / 32));
-        BI.entryOff = (int) out->sched.size(); BI.ksOff = (int) out->ksCount.size(); BI.wOff = (int) out->W.size();
+        BI.wOff = (int) out->W.size();
+        if (BI.nK > kUmmaMaxNK) return false;
         // per-slot taps of every group of the block, then the tiles in schedule order (K step major, group minor)
         std::vector<std::vector<float>> gw((size_t) (g1 - g0));
         std::vector<std::vector<int>> gshift((size_t) (g1 - g0));
@@ -376,13 +399,17 @@ bool build_umma(int kind, const float* sinc_table, long long p, long long q, int
         }
         int entries = 0;
         for (int ks = 0; ks < BI.nK; ++ks) {
-            int cnt = 0;
+            int cnt = 0, glFirst = -1, nFirst = 0, nLast = 0, nSecond = 0, nEnter = 0;
             for (int g = g0; g < g1; ++g) {
                 const GroupGeom& gg = geo[(size_t) (g - g0)];
                 const int first = (int) ((gg.t0 - lo) / 16);
                 if (ks < first || ks >= first + gg.ksteps) continue;
                 const int j = ks - first;
-                out->sched.push_back((uint16_t) ((g - g0) | (j == 0 ? 0x40 : 0) | (j == gg.ksteps - 1 ? 0x80 : 0)));
+                if (glFirst < 0) glFirst = g - g0;
+                if (g - g0 != glFirst + cnt) return false;                     // active groups must be contiguous
+                if (j == 0) ++nFirst; else if (nFirst) return false;           // starters are the top of the range
+                if (j == gg.ksteps - 1) { if (nLast != cnt) return false; ++nLast; }   // finishers are the bottom
+                if (poolN > 0 && j >= split) { if (nSecond != cnt) return false; ++nSecond; if (j == split) ++nEnter; }
                 const size_t base = out->W.size();
                 out->W.resize(base + 1024, 0);
                 for (int s = 0; s < 16; ++s) {
@@ -401,7 +428,8 @@ bool build_umma(int kind, const float* sinc_table, long long p, long long q, int
                 }
                 ++cnt; ++entries;
             }
-            out->ksCount.push_back((uint8_t) cnt);
+            if (cnt > 15 || nFirst > 15 || nLast > 15) return false;
+            out->ksWord[b][ks] = (uint32_t) ((glFirst < 0 ? 0 : glFirst) | (cnt << 4) | (nFirst << 8) | (nLast << 12) | (nSecond << 16) | (nEnter << 20));
         }
         BI.nEntries = entries;
         out->maxEntries = std::max(out->maxEntries, entries);

@@ -26,7 +26,9 @@
 // tcgen05.cp 128x256b = 64 clk.
 #include <algorithm>
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
+#include <vector>
 #include <cuda_fp16.h>
 
 #include "f9_internal.cuh"
@@ -57,7 +59,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    #pragma unroll 1
     for (int i = 0; i < kSpin; ++i) if (mbar_try_wait(bar, parity)) return;
+    __trap();
+}
+// Same, for waits that are expected to be long (epilogue): the hardware may park the thread for up to `ns` per attempt
+// instead of re-issuing the poll, which leaves the issue slots to the loader warps.
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity, uint32_t ns) {
+    #pragma unroll 1
+    for (int i = 0; i < kSpin; ++i) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(ns) : "memory");
+        if (ok) return;
+    }
     __trap();
 }
 __device__ __forceinline__ uint32_t elect_one() {
@@ -68,6 +83,15 @@ __device__ __forceinline__ uint32_t elect_one() {
 __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
                  :: "r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+// guarded forms (straight-line unrolled issue blocks: no branch between the MMAs of neighbouring schedule entries)
+__device__ __forceinline__ void umma_ts_if(uint32_t guard, uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                 :: "r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc), "r"(guard) : "memory");
+}
+__device__ __forceinline__ void umma_commit_if(uint32_t guard, uint64_t* bar) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+                 :: "r"(smem_u32(bar)), "r"(guard) : "memory");
 }
 __device__ __forceinline__ void umma_cp(uint32_t d_tmem, uint64_t sdesc) {
     asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" :: "r"(d_tmem), "l"(sdesc) : "memory");
@@ -98,17 +122,15 @@ __device__ __forceinline__ float load_in(const Seg& S, long long l) {          /
 }
 
 struct SmemMap {
-    uint8_t* W; uint8_t* ring; float* epi; uint16_t* sched; uint8_t* ksCount;
+    uint8_t* W; uint8_t* ring; float* epi;
     uint64_t *full, *empty, *accFull, *accEmpty; uint32_t* tmemSlot;
 };
-__device__ __forceinline__ SmemMap carve(uint8_t* smem, int maxEntries, int maxNK, int stages) {
+__device__ __forceinline__ SmemMap carve(uint8_t* smem, int maxEntries, int stages) {
     SmemMap m;
     m.W = smem;
     m.ring = m.W + (size_t) maxEntries * 1024;
     m.epi = reinterpret_cast<float*>(m.ring + (size_t) stages * kStageBytes);
-    m.sched = reinterpret_cast<uint16_t*>(m.epi + kRows * kEpiPitch);
-    m.ksCount = reinterpret_cast<uint8_t*>(m.sched) + ((size_t) maxEntries * 2 + 15) / 16 * 16;
-    m.full = reinterpret_cast<uint64_t*>(m.ksCount + ((size_t) maxNK + 15) / 16 * 16);
+    m.full = reinterpret_cast<uint64_t*>(m.epi + kRows * kEpiPitch);
     m.empty = m.full + stages;
     m.accFull = m.empty + stages;
     m.accEmpty = m.accFull + kUmmaMaxGroups;
@@ -116,24 +138,170 @@ __device__ __forceinline__ SmemMap carve(uint8_t* smem, int maxEntries, int maxN
     return m;
 }
 
+// fp16 head / scaled fp16 tail of four samples, written to the operand tile (8 bytes each)
+__device__ __forceinline__ void split_store(const float4 xv, uint8_t* dst, __half2& hmax) {
+    const __half2 h01 = __floats2half2_rn(xv.x, xv.y), h23 = __floats2half2_rn(xv.z, xv.w);
+    hmax = __hmax2_nan(hmax, __hmax2_nan(__habs2(h01), __habs2(h23)));
+    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+    const __half2 t01 = __floats2half2_rn((xv.x - f01.x) * 2048.0f, (xv.y - f01.y) * 2048.0f);
+    const __half2 t23 = __floats2half2_rn((xv.z - f23.x) * 2048.0f, (xv.w - f23.y) * 2048.0f);
+    uint2 hv, tv;
+    hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
+    tv.x = *reinterpret_cast<const uint32_t*>(&t01); tv.y = *reinterpret_cast<const uint32_t*>(&t23);
+    *reinterpret_cast<uint2*>(dst) = hv;
+    *reinterpret_cast<uint2*>(dst + 4 * kChunk) = tv;
+}
+
+// ------------------------------------------------------------------------------------------------- loader warps
+// Every lane owns, per stage, 4 row pieces of 4 samples (rows i*32 + lw*4 + lane/8, samples 4*(lane%8)..+3): one warp
+// instruction reads 4 rows x 128 contiguous bytes.  Loads run three stages ahead of the conversion (four register buffers,
+// 48 KB per SM in flight); the cursor walks (tile, stage) across tile boundaries.
+// ALIGNED: every row piece of every segment starts on a 16-byte boundary (the host checked), so the loaded vector is the
+// lane's four samples.  Otherwise a lane loads the aligned vector that starts m = (address mod 4) floats early and the four
+// samples are funnelled out of (own vector, next lane's vector); lane 7's "next" is lane 0's vector of the next stage.
+struct LoaderArgs {
+    const Seg* segs; const int* tilePrefix; int nSegs, nTiles, nGB, p, q, U0, nStages, stages, myTiles;
+    uint8_t* ring; uint64_t *full, *empty; unsigned* ovf; long long* prof;
+};
+template <bool ALIGNED>
+__device__ __forceinline__ void loader_role(const LoaderArgs& A, int lw, int lane) {
+    const int rsub = lane >> 3, j = lane & 7;
+    const uint32_t dstLane = (uint32_t) ((j >> 1) * kChunk + (j & 1) * 8 + (lw * 4 + rsub) * 16);
+    __half2 hmax = __floats2half2_rn(0.f, 0.f);                // running max |x0| (NaN-propagating)
+    const int total = A.myTiles * A.nStages;
+    long long pT0 = 0, pW0 = 0;
+    if (A.prof) pT0 = clock64();
+
+    // ---- prefetch cursor: state of the tile being loaded (three stages ahead of the one being converted)
+    int curTile = blockIdx.x, curSt = 0;
+    const float* rowPtr[4] = {nullptr, nullptr, nullptr, nullptr};            // aligned vector of (row i, stage 0) for this lane
+    long long lRow[4] = {0, 0, 0, 0}, lEnd = 0;                               // its window index; S.inAvail
+    uint32_t mrow = 0; bool interior = false;
+    auto open_tile = [&]() {
+        const int sidx = find_seg(A.tilePrefix, A.nSegs, curTile);
+        const Seg S = A.segs[sidx];
+        const int pb = (curTile - A.tilePrefix[sidx]) / A.nGB;
+        const long long A0 = S.n0 / A.q + (long long) pb * kRows;
+        const long long l00 = A0 * A.p + A.U0 - S.inOffset;                     // window index of (row 0, K 0)
+        const long long addr0 = (long long) (reinterpret_cast<uintptr_t>(S.in) >> 2) + l00;   // its address in floats
+        uint32_t mm = 0;
+        #pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = i * 32 + lw * 4 + rsub;
+            const int m = ALIGNED ? 0 : (int) ((addr0 + (long long) r * A.p) & 3);
+            mm |= (uint32_t) m << (2 * i);
+            lRow[i] = l00 + (long long) r * A.p + j * 4 - m;
+            rowPtr[i] = S.in + lRow[i];
+        }
+        mrow = mm; lEnd = S.inAvail;
+        // interior: every vector any lane loads for this tile lies inside the segment's window
+        interior = l00 - 3 >= 0 && l00 + (long long) (kRows - 1) * A.p + (long long) A.nStages * 32 + 3 < S.inAvail;
+    };
+    struct Buf { float4 v[4]; uint32_t mrow; };
+    auto issue = [&](Buf& b) {
+        if (curSt == 0) open_tile();
+        const int koff = curSt * 32;
+        if (interior) {
+            #pragma unroll
+            for (int i = 0; i < 4; ++i)
+                asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];"
+                             : "=f"(b.v[i].x), "=f"(b.v[i].y), "=f"(b.v[i].z), "=f"(b.v[i].w) : "l"(rowPtr[i] + koff));
+        } else {
+            // Predicated loads straight into the buffer registers (no branch, no select between a load and its use).
+            bool straddle = false;
+            #pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const long long l = lRow[i] + koff;
+                const bool inside = l >= 0 && l + 3 < lEnd;
+                straddle |= !inside && l + 3 >= 0 && l < lEnd;
+                b.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\t@p ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];\n\t}"
+                             : "+f"(b.v[i].x), "+f"(b.v[i].y), "+f"(b.v[i].z), "+f"(b.v[i].w) : "l"(rowPtr[i] + koff), "r"((int) inside));
+            }
+            if (__any_sync(0xffffffffu, straddle)) {           // a vector crosses the start or the end of the segment's window
+                #pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const long long l = lRow[i] + koff;
+                    if (!(l >= 0 && l + 3 < lEnd)) {
+                        const float* ptr = rowPtr[i] + koff;
+                        b.v[i].x = (l >= 0 && l < lEnd) ? __ldg(ptr) : 0.f;             b.v[i].y = (l + 1 >= 0 && l + 1 < lEnd) ? __ldg(ptr + 1) : 0.f;
+                        b.v[i].z = (l + 2 >= 0 && l + 2 < lEnd) ? __ldg(ptr + 2) : 0.f; b.v[i].w = (l + 3 >= 0 && l + 3 < lEnd) ? __ldg(ptr + 3) : 0.f;
+                    }
+                }
+            }
+        }
+        b.mrow = mrow;
+        if (++curSt == A.nStages) { curSt = 0; curTile += gridDim.x; }
+    };
+    int sIdx = 0; uint32_t sPh = 0;                            // ring slot / phase of the stage being produced
+    const int srcLane = (lane & ~7) | ((j + 1) & 7);           // the lane holding the next 16 bytes of this row
+    auto process = [&](const Buf& b, const Buf& nb) {
+        float4 x[4];
+        #pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (ALIGNED) { x[i] = b.v[i]; continue; }
+            const float4 pub = (j == 0) ? nb.v[i] : b.v[i];
+            const float4 v = b.v[i];
+            const float c4 = __shfl_sync(0xffffffffu, pub.x, srcLane);
+            const float c5 = __shfl_sync(0xffffffffu, pub.y, srcLane);
+            const float c6 = __shfl_sync(0xffffffffu, pub.z, srcLane);
+            const uint32_t m = (b.mrow >> (2 * i)) & 3u;
+            const bool m1 = m & 1u, m2 = m & 2u;
+            const float e0 = m1 ? v.y : v.x, e1 = m1 ? v.z : v.y, e2 = m1 ? v.w : v.z, e3 = m1 ? c4 : v.w, e4 = m1 ? c5 : c4, e5 = m1 ? c6 : c5;
+            x[i] = make_float4(m2 ? e2 : e0, m2 ? e3 : e1, m2 ? e4 : e2, m2 ? e5 : e3);
+        }
+        if (A.prof) { const long long w = clock64(); mbar_wait(A.empty + sIdx, sPh ^ 1); pW0 += clock64() - w; }
+        else mbar_wait(A.empty + sIdx, sPh ^ 1);
+        uint8_t* dst = A.ring + (size_t) sIdx * kStageBytes + dstLane;
+        #pragma unroll
+        for (int i = 0; i < 4; ++i) split_store(x[i], dst + i * 32 * 16, hmax);
+        // No proxy fence here: it compiles to MEMBAR.ALL.CTA, which would wait for the loads already in flight for the next
+        // stages.  The arrive below releases the stores; the tensor warp fences after it has acquired the barrier.
+        __syncwarp();
+        if (lane == 0) mbar_arrive(A.full + sIdx);
+        if (++sIdx == A.stages) { sIdx = 0; sPh ^= 1; }
+    };
+    Buf b0, b1, b2, b3;
+    #pragma unroll
+    for (int i = 0; i < 4; ++i) b0.v[i] = b1.v[i] = b2.v[i] = b3.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    b0.mrow = b1.mrow = b2.mrow = b3.mrow = 0;
+    int issued = 0, done = 0;
+    if (issued < total) { issue(b0); ++issued; }
+    if (issued < total) { issue(b1); ++issued; }
+    if (issued < total) { issue(b2); ++issued; }
+    while (done < total) {
+        if (issued < total) { issue(b3); ++issued; }
+        process(b0, b1); if (++done >= total) break;
+        if (issued < total) { issue(b0); ++issued; }
+        process(b1, b2); if (++done >= total) break;
+        if (issued < total) { issue(b1); ++issued; }
+        process(b2, b3); if (++done >= total) break;
+        if (issued < total) { issue(b2); ++issued; }
+        process(b3, b0); ++done;
+    }
+    const float2 hm = __half22float2(hmax);
+    if (!(hm.x < 32768.0f) || !(hm.y < 32768.0f)) atomicOr(A.ovf, 1u);         // |x| >= 32768, Inf or NaN in this CTA's input
+    if (A.prof && lw == 0 && lane == 0) { A.prof[blockIdx.x * 16 + 0] = clock64() - pT0; A.prof[blockIdx.x * 16 + 1] = pW0; }
+}
+
+template <bool MERGED>
 __global__ void __launch_bounds__(kThreads, 1)
-umma_fir_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix, int nSegs, int nTiles, const UmmaDev P,
-                int stages, unsigned* __restrict__ ovf) {
+umma_fir_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix, int nSegs, int nTiles,
+                const __grid_constant__ UmmaDev P, int stages, int alignedAll, unsigned* __restrict__ ovf, long long* __restrict__ prof) {
     extern __shared__ __align__(128) uint8_t smem[];
-    const SmemMap sm = carve(smem, P.maxEntries, P.maxNK, stages);
+    const SmemMap sm = carve(smem, P.maxEntries, stages);
     const int warp = __shfl_sync(0xffffffffu, (int) (threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int gb = blockIdx.x % P.nGB;
-    const UmmaBlockInfo BI = P.blk[gb];
+    const UmmaBlockInfo& BI = P.blk[gb];
     const int p = P.p, q = P.q;
     const int nStages = BI.nStages;                            // stages per tile (two K steps each)
+    const int myTiles = (int) blockIdx.x < nTiles ? (nTiles - 1 - (int) blockIdx.x) / (int) gridDim.x + 1 : 0;
 
-    // ---- one-time setup: weights + schedule into shared memory, barriers, TMEM
+    // ---- one-time setup: weights into shared memory, barriers, TMEM
     {
         const uint4* src = reinterpret_cast<const uint4*>(P.W + BI.wOff);
         uint4* dst = reinterpret_cast<uint4*>(sm.W);
         for (int i = threadIdx.x; i < BI.nEntries * 64; i += kThreads) dst[i] = __ldg(src + i);
-        for (int i = threadIdx.x; i < BI.nEntries; i += kThreads) sm.sched[i] = P.sched[BI.entryOff + i];
-        for (int i = threadIdx.x; i < BI.nK; i += kThreads) sm.ksCount[i] = P.ksCount[BI.ksOff + i];
         if (threadIdx.x == 0) {
             for (int s = 0; s < stages; ++s) { mbar_init(sm.full + s, kLoaderWarps); mbar_init(sm.empty + s, 1); }
             for (int g = 0; g < kUmmaMaxGroups; ++g) { mbar_init(sm.accFull + g, 1); mbar_init(sm.accEmpty + g, 4); }
@@ -149,176 +317,128 @@ umma_fir_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix
         tc_fence_after();
     }
     const uint32_t tmem = *sm.tmemSlot;
+    // optional cycle accounting (development): per CTA [0] loader-warp-0 total, [1] its wait on "stage free", [2] tensor warp
+    // total, [3] its wait on "stage full", [4] its wait on "accumulator drained", [5] epilogue-warp-0 total, [6] its wait on
+    // "group done", [7] its time in the store loops
+    long long pT0 = 0, pW0 = 0, pW1 = 0, pW2 = 0, pF = 0, pC = 0, pM = 0;
+    #define PROF_BEGIN(v) long long v = prof ? clock64() : 0
+    #define PROF_END(acc, v) if (prof) acc += clock64() - v
+    if (prof) pT0 = clock64();
 
     if (warp >= 5) {
         // =========================================================== loaders
-        // Every lane owns, per stage, 4 row pieces of 4 samples (rows i*32 + lw*4 + lane/8, samples 4*(lane%8)..+3): one
-        // warp instruction reads 4 rows x 128 contiguous bytes.  Loads run two stages ahead of the conversion (three
-        // register buffers) so ~32 KB per SM are in flight; the cursor walks (tile, stage) across tile boundaries.
-        const int lw = warp - 5;
-        const int rsub = lane >> 3, j = lane & 7;
-        const uint32_t dstLane = (uint32_t) ((j >> 1) * kChunk + (j & 1) * 8);
-        uint32_t amax = 0;                                     // running max of |x| bit patterns
-        const int myTiles = blockIdx.x < nTiles ? (nTiles - 1 - (int) blockIdx.x) / (int) gridDim.x + 1 : 0;
-        const int total = myTiles * nStages;
-
-        int curTile = blockIdx.x, curSt = 0;                   // prefetch cursor
-        Seg S = {}; long long l00 = 0, addr0 = 0; bool aligned = false;
-        auto open_tile = [&]() {
-            const int sidx = find_seg(tilePrefix, nSegs, curTile);
-            S = segs[sidx];
-            const int pb = (curTile - tilePrefix[sidx]) / P.nGB;
-            const long long A0 = S.n0 / q + (long long) pb * kRows;
-            l00 = A0 * p + BI.U0 - S.inOffset;                                  // window index of (row 0, K 0)
-            addr0 = (long long) (reinterpret_cast<uintptr_t>(S.in) >> 2) + l00; // its address in floats
-            aligned = ((p & 3) == 0) && ((addr0 & 3) == 0);                     // every row piece starts on 16 bytes
-        };
-        // A buffer holds, per row piece, the 16-byte ALIGNED vector that starts m = (address mod 4) floats before the
-        // lane's 4 samples; meta = m of the 4 rows (2 bits each) | bit 8: tile fully aligned (all m = 0).
-        struct Buf { float4 v[4]; uint32_t meta; };
-        auto issue = [&](Buf& b) {
-            if (curSt == 0) open_tile();
-            uint32_t meta = aligned ? 0x100u : 0u;
-            #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int r = i * 32 + lw * 4 + rsub;
-                const int m = (int) ((addr0 + (long long) r * p) & 3);
-                meta |= (uint32_t) m << (2 * i);
-                const long long l = l00 + (long long) r * p + curSt * 32 + j * 4 - m;
-                if (l >= 0 && l + 3 < S.inAvail) b.v[i] = __ldg(reinterpret_cast<const float4*>(S.in + l));
-                else { b.v[i].x = load_in(S, l); b.v[i].y = load_in(S, l + 1); b.v[i].z = load_in(S, l + 2); b.v[i].w = load_in(S, l + 3); }
-            }
-            b.meta = meta;
-            if (++curSt == nStages) { curSt = 0; curTile += gridDim.x; }
-        };
-        uint32_t it = 0;                                       // stages produced by this CTA so far
-        const int srcLane = (lane & ~7) | ((j + 1) & 7);       // the lane holding the next 16 bytes of this row
-        auto process = [&](const Buf& b, const Buf& nb) {
-            const int s = (int) (it % (uint32_t) stages);
-            const uint32_t ph = (it / (uint32_t) stages) & 1;
-            ++it;
-            float4 x[4];
-            if (b.meta & 0x100u) {
-                #pragma unroll
-                for (int i = 0; i < 4; ++i) x[i] = b.v[i];
-            } else {
-                // funnel shift: samples m..m+3 of (own vector, next vector); lane 7's next vector is lane 0's vector of the
-                // next stage (already in registers: the loads run two stages ahead)
-                #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float4 pub = (j == 0) ? nb.v[i] : b.v[i];
-                    const float c4 = __shfl_sync(0xffffffffu, pub.x, srcLane);
-                    const float c5 = __shfl_sync(0xffffffffu, pub.y, srcLane);
-                    const float c6 = __shfl_sync(0xffffffffu, pub.z, srcLane);
-                    const uint32_t m = (b.meta >> (2 * i)) & 3u;
-                    const float4 v = b.v[i];
-                    const bool m1 = m & 1u, m2 = m & 2u;
-                    const float e0 = m1 ? v.y : v.x, e1 = m1 ? v.z : v.y, e2 = m1 ? v.w : v.z, e3 = m1 ? c4 : v.w, e4 = m1 ? c5 : c4, e5 = m1 ? c6 : c5;
-                    x[i] = make_float4(m2 ? e2 : e0, m2 ? e3 : e1, m2 ? e4 : e2, m2 ? e5 : e3);
-                }
-            }
-            mbar_wait(sm.empty + s, ph ^ 1);
-            uint8_t* stage = sm.ring + (size_t) s * kStageBytes;
-            #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int r = i * 32 + lw * 4 + rsub;
-                const float4 xv = x[i];
-                amax = max(max(amax, __float_as_uint(xv.x) & 0x7fffffffu), max(__float_as_uint(xv.y) & 0x7fffffffu,
-                           max(__float_as_uint(xv.z) & 0x7fffffffu, __float_as_uint(xv.w) & 0x7fffffffu)));
-                const __half2 h01 = __floats2half2_rn(xv.x, xv.y), h23 = __floats2half2_rn(xv.z, xv.w);
-                const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-                const __half2 t01 = __floats2half2_rn((xv.x - f01.x) * 2048.0f, (xv.y - f01.y) * 2048.0f);
-                const __half2 t23 = __floats2half2_rn((xv.z - f23.x) * 2048.0f, (xv.w - f23.y) * 2048.0f);
-                uint8_t* dst = stage + dstLane + r * 16;
-                uint2 hv, tv;
-                hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
-                tv.x = *reinterpret_cast<const uint32_t*>(&t01); tv.y = *reinterpret_cast<const uint32_t*>(&t23);
-                *reinterpret_cast<uint2*>(dst) = hv;
-                *reinterpret_cast<uint2*>(dst + 4 * kChunk) = tv;
-            }
-            fence_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(sm.full + s);
-        };
-        Buf b0, b1, b2;
-        #pragma unroll
-        for (int i = 0; i < 4; ++i) b0.v[i] = b1.v[i] = b2.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        b0.meta = b1.meta = b2.meta = 0x100u;
-        int issued = 0, done = 0;
-        if (issued < total) { issue(b0); ++issued; }
-        if (issued < total) { issue(b1); ++issued; }
-        while (done < total) {
-            if (issued < total) { issue(b2); ++issued; }
-            process(b0, b1); if (++done >= total) break;
-            if (issued < total) { issue(b0); ++issued; }
-            process(b1, b2); if (++done >= total) break;
-            if (issued < total) { issue(b1); ++issued; }
-            process(b2, b0); ++done;
-        }
-        if (amax >= 0x47000000u) atomicOr(ovf, 1u);            // |x| >= 32768, Inf or NaN somewhere in this CTA's input
+        LoaderArgs LA;
+        LA.segs = segs; LA.tilePrefix = tilePrefix; LA.nSegs = nSegs; LA.nTiles = nTiles; LA.nGB = P.nGB; LA.p = p; LA.q = q;
+        LA.U0 = BI.U0; LA.nStages = nStages; LA.stages = stages; LA.myTiles = myTiles;
+        LA.ring = sm.ring; LA.full = sm.full; LA.empty = sm.empty; LA.ovf = ovf; LA.prof = prof;
+        if (alignedAll) loader_role<true>(LA, warp - 5, lane);
+        else loader_role<false>(LA, warp - 5, lane);
     } else if (warp == 4) {
         // =========================================================== tensor pipe
+        // Warp-uniform control flow in the uniform datapath; one elected lane issues.  tcgen05 operands are uniform
+        // registers, and what bounds this warp is the handful of uniform-datapath instructions per MMA, not the tensor pipe
+        // (measured: ~45 clk per issued MMA against 8 clk of pipe time), hence the straight-line 4-entry blocks below.
         const uint32_t el = elect_one();
-        const uint32_t idescHi = make_idesc(kRows, 32), idescLo = make_idesc(kRows, 16);
-        const uint32_t wBase = smem_u32(sm.W);
-        uint32_t it = 0, tcount = 0;
-        for (int tileId = blockIdx.x; tileId < nTiles; tileId += gridDim.x, ++tcount) {
-            int e = 0;
-            for (int st = 0; st < nStages; ++st, ++it) {
-                const int s = (int) (it % (uint32_t) stages);
-                const uint32_t ph = (it / (uint32_t) stages) & 1;
-                mbar_wait(sm.full + s, ph);
+        const uint32_t idesc16 = make_idesc(kRows, 16), idesc32 = make_idesc(kRows, 32);
+        const uint32_t poolCol = (uint32_t) (P.GBL * 32), poolMask = (uint32_t) (P.poolN > 0 ? P.poolN - 1 : 0);
+        const uint64_t wDesc0 = make_desc(smem_u32(sm.W), 512, 128);           // weight tile e: + 64*e (1 KB, 16-byte units)
+        const uint64_t aDesc0 = make_desc(smem_u32(sm.ring), kChunk, 128);
+        int sIdx = 0; uint32_t sPh = 0;
+        for (int t = 0; t < myTiles; ++t) {
+            uint32_t e = 0;
+            for (int st = 0; st < nStages; ++st) {
+                { PROF_BEGIN(w); mbar_wait(sm.full + sIdx, sPh); PROF_END(pW0, w); }
+                PROF_BEGIN(wf);
+                fence_async_smem();                            // generic-proxy stores of the loaders -> async-proxy reads of tcgen05.cp
                 tc_fence_after();
-                const uint32_t stageAddr = smem_u32(sm.ring + (size_t) s * kStageBytes);
+                PROF_END(pF, wf);
+                PROF_BEGIN(wc);
                 if (el) {
-                    #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const uint32_t slot = (uint32_t) (((2 * st + h) & 3) * 16);
-                        umma_cp(tmem + kACol + slot, make_desc(stageAddr + h * 2 * kChunk, kChunk, 128));
-                        umma_cp(tmem + kACol + slot + 8, make_desc(stageAddr + (4 + h * 2) * kChunk, kChunk, 128));
-                    }
-                    umma_commit(sm.empty + s);                 // the stage is free once the copies have read it
+                    const uint64_t ad = aDesc0 + (uint64_t) ((sIdx * kStageBytes) >> 4);
+                    const uint32_t slot0 = tmem + kACol + (uint32_t) ((st & 1) * 32);
+                    umma_cp(slot0, ad);                                         // K step 2*st   head
+                    umma_cp(slot0 + 8, ad + ((4 * kChunk) >> 4));               //               tail
+                    umma_cp(slot0 + 16, ad + ((2 * kChunk) >> 4));              // K step 2*st+1 head
+                    umma_cp(slot0 + 24, ad + ((6 * kChunk) >> 4));              //               tail
+                    umma_commit(sm.empty + sIdx);              // the stage is free once the copies have read it
                 }
                 __syncwarp();
+                PROF_END(pC, wc);
+                if (++sIdx == stages) { sIdx = 0; sPh ^= 1; }
+                PROF_BEGIN(wm);
+                #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const int ks = 2 * st + h;
                     if (ks >= BI.nK) break;
+                    const uint32_t word = P.ksWord[gb][ks];
+                    const uint32_t gl0 = word & 15u, cnt = (word >> 4) & 15u, nFirst = (word >> 8) & 15u, nLast = (word >> 12) & 15u;
+                    const uint32_t nSecond = (word >> 16) & 15u, nEnter = (word >> 20) & 15u;
                     const uint32_t aHi = tmem + kACol + (uint32_t) ((ks & 3) * 16);
-                    const int cnt = sm.ksCount[ks];
-                    for (int c = 0; c < cnt; ++c, ++e) {
-                        const uint32_t ent = sm.sched[e];
-                        const uint32_t gl = ent & 63u;
-                        if (ent & 0x40u) {                     // first K step of this group in this tile: accumulator drained?
-                            mbar_wait(sm.accEmpty + gl, (tcount & 1) ^ 1);
-                            tc_fence_after();
+                    // waits first (rare: once per group and tile), so that the issue block below is straight-line code
+                    if (nFirst | nEnter) {
+                        PROF_BEGIN(w);
+                        for (uint32_t c = cnt - nFirst; c < cnt; ++c)          // groups starting here: accumulators drained?
+                            mbar_wait(sm.accEmpty + gl0 + c, (t & 1) ^ 1);
+                        for (uint32_t c = nSecond - nEnter; c < nSecond; ++c) { // groups crossing their split: the pool slot's previous user read?
+                            const uint32_t gl = gl0 + c;
+                            if (gl > poolMask) mbar_wait(sm.accEmpty + (gl - poolMask - 1), t & 1);      // same tile
+                            else {                                                                       // previous tile
+                                uint32_t lu = gl; while (lu + poolMask + 1 < (uint32_t) BI.nGroups) lu += poolMask + 1;
+                                mbar_wait(sm.accEmpty + lu, (t & 1) ^ 1);
+                            }
                         }
-                        if (el) {
-                            const uint64_t bd = make_desc(wBase + (uint32_t) e * 1024u, 512, 128);
-                            umma_ts(tmem + gl * 32, aHi, bd, idescHi, (ent & 0x40u) ? 0u : 1u);   // [D0 | D1] (+)= x0 * [w0 | w1]
-                            umma_ts(tmem + gl * 32 + 16, aHi + 8, bd, idescLo, 1u);               //  D1       +=  x1 * w0
-                            if (ent & 0x80u) umma_commit(sm.accFull + gl);
-                        }
-                        __syncwarp();
+                        PROF_END(pW1, w);
+                        tc_fence_after();
                     }
+                    if (el) {
+                        for (uint32_t c0 = 0; c0 < cnt; c0 += 4) {
+                            #pragma unroll
+                            for (uint32_t u = 0; u < 4; ++u) {
+                                const uint32_t c = c0 + u, gl = gl0 + c;
+                                const uint32_t valid = c < cnt;
+                                const bool first = c + nFirst >= cnt;
+                                const uint32_t d1 = tmem + gl * 32 + 16;
+                                const uint64_t bd = wDesc0 + (uint64_t) ((e + c) * 64u);
+                                if (MERGED) {                  // no accumulator split: [D0 | D1] (+)= x0 * [w0 | w1] as one N = 32 MMA
+                                    umma_ts_if(valid, d1 - 16, aHi, bd, idesc32, first ? 0u : 1u);
+                                } else {                       // three MMAs of identical shape
+                                    const bool second = c < nSecond, enter = second && c + nEnter >= nSecond;
+                                    const uint32_t d0 = second ? tmem + poolCol + (gl & poolMask) * 16 : d1 - 16;
+                                    umma_ts_if(valid, d0, aHi, bd, idesc16, (first || enter) ? 0u : 1u);   // D0 (+)= x0 * w0
+                                    umma_ts_if(valid, d1, aHi, bd + 16, idesc16, first ? 0u : 1u);         // D1 (+)= x0 * w1
+                                }
+                                umma_ts_if(valid, d1, aHi + 8, bd, idesc16, 1u);                           // D1  += x1 * w0
+                                umma_commit_if(valid && c < nLast, sm.accFull + gl);
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    e += cnt;
                 }
+                PROF_END(pM, wm);
             }
         }
+        if (prof && lane == 0) { prof[blockIdx.x * 16 + 8] = pF; prof[blockIdx.x * 16 + 9] = pC; prof[blockIdx.x * 16 + 10] = pM; }
+        if (prof && lane == 0) { prof[blockIdx.x * 16 + 2] = clock64() - pT0; prof[blockIdx.x * 16 + 3] = pW0; prof[blockIdx.x * 16 + 4] = pW1; }
     } else {
         // =========================================================== epilogue
         const int row0 = warp * 32 + lane;                     // TMEM lane = period row of this thread
-        uint32_t tcount = 0;
-        for (int tileId = blockIdx.x; tileId < nTiles; tileId += gridDim.x, ++tcount) {
+        int tileId = blockIdx.x;
+        for (int t = 0; t < myTiles; ++t, tileId += gridDim.x) {
             const int sidx = find_seg(tilePrefix, nSegs, tileId);
             const Seg S = segs[sidx];
             const int pb = (tileId - tilePrefix[sidx]) / P.nGB;
             const long long A0 = S.n0 / q + (long long) pb * kRows;
+            const long long oBase = A0 * q + BI.slot0 - S.n0;                  // output index of (row 0, slot 0 of the block)
+            const int blockSlots = min(BI.nGroups * 16, q - BI.slot0);          // real (non-padding) slots of this block
+            const bool rowsInside = oBase >= 0 && oBase + (long long) (kRows - 1) * q + blockSlots <= S.numOut;
             for (int gp = 0; gp * 2 < BI.nGroups; ++gp) {
                 #pragma unroll
                 for (int gg = 0; gg < 2; ++gg) {
                     const int gl = gp * 2 + gg;
                     float o[16];
                     if (gl < BI.nGroups) {
-                        mbar_wait(sm.accFull + gl, tcount & 1);
+                        { PROF_BEGIN(w); mbar_wait_parked(sm.accFull + gl, t & 1, 2000); PROF_END(pW0, w); }
                         tc_fence_after();
                         uint32_t v[32];
                         const uint32_t taddr = tmem + (uint32_t) (gl * 32) + ((uint32_t) (warp * 32) << 16);
@@ -328,12 +448,24 @@ umma_fir_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix
                                        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
                                        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                                      : "r"(taddr));
+                        uint32_t vb[16];
+                        if (P.poolN > 0) {
+                            const uint32_t tb = tmem + (uint32_t) (P.GBL * 32 + (gl & (P.poolN - 1)) * 16) + ((uint32_t) (warp * 32) << 16);
+                            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                                         : "=r"(vb[0]), "=r"(vb[1]), "=r"(vb[2]), "=r"(vb[3]), "=r"(vb[4]), "=r"(vb[5]), "=r"(vb[6]), "=r"(vb[7]),
+                                           "=r"(vb[8]), "=r"(vb[9]), "=r"(vb[10]), "=r"(vb[11]), "=r"(vb[12]), "=r"(vb[13]), "=r"(vb[14]), "=r"(vb[15])
+                                         : "r"(tb));
+                        } else {
+                            #pragma unroll
+                            for (int c = 0; c < 16; ++c) vb[c] = 0u;
+                        }
                         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(sm.accEmpty + gl);      // the next tile may overwrite this accumulator
+                        if (lane == 0) mbar_arrive(sm.accEmpty + gl);      // the next tile may overwrite these accumulators
                         #pragma unroll
-                        for (int c = 0; c < 16; ++c) o[c] = fmaf(__uint_as_float(v[16 + c]), 1.0f / 2048.0f, __uint_as_float(v[c]));
+                        for (int c = 0; c < 16; ++c)
+                            o[c] = fmaf(__uint_as_float(v[16 + c]), 1.0f / 2048.0f, __uint_as_float(v[c]) + __uint_as_float(vb[c]));
                     } else {
                         #pragma unroll
                         for (int c = 0; c < 16; ++c) o[c] = 0.0f;
@@ -342,16 +474,30 @@ umma_fir_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix
                     dst[0] = make_float4(o[0], o[1], o[2], o[3]);   dst[1] = make_float4(o[4], o[5], o[6], o[7]);
                     dst[2] = make_float4(o[8], o[9], o[10], o[11]); dst[3] = make_float4(o[12], o[13], o[14], o[15]);
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                // rows of 32 slots are contiguous in the output: one coalesced 128-byte store per row
-                const int slot = BI.slot0 + gp * 32 + lane;
-                for (int r = warp; r < kRows; r += 4) {
-                    const long long o = (A0 + r) * q + slot - S.n0;
-                    if (slot < q && o >= 0 && o < S.numOut) S.out[o] = sm.epi[r * kEpiPitch + lane];
+                // Each warp transposes its own 32 rows (its TMEM lanes) through its own slice of the staging buffer: only a
+                // warp-level sync, then one coalesced 128-byte store per row (32 slots are contiguous in the output).
+                __syncwarp();
+                PROF_BEGIN(wst);
+                const float* src = sm.epi + (warp * 32) * kEpiPitch + lane;
+                const long long o0 = oBase + (long long) (warp * 32) * q + gp * 32 + lane;
+                float* dstp = reinterpret_cast<float*>(__cvta_generic_to_global(S.out)) + o0;
+                if (rowsInside && gp * 32 + 32 <= blockSlots) {
+                    #pragma unroll 8
+                    for (int r = 0; r < 32; ++r, dstp += q)
+                        asm volatile("st.global.cs.f32 [%0], %1;" :: "l"(dstp), "f"(src[r * kEpiPitch]) : "memory");
+                } else {
+                    const int slot = BI.slot0 + gp * 32 + lane;
+                    const bool slotOk = slot < q && gp * 32 + lane < blockSlots;
+                    for (int r = 0; r < 32; ++r, dstp += q) {
+                        const long long o = o0 + (long long) r * q;
+                        if (slotOk && o >= 0 && o < S.numOut) *dstp = src[r * kEpiPitch];
+                    }
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                __syncwarp();
+                PROF_END(pW2, wst);
             }
         }
+        if (prof && warp == 0 && lane == 0) { prof[blockIdx.x * 16 + 5] = clock64() - pT0; prof[blockIdx.x * 16 + 6] = pW0; prof[blockIdx.x * 16 + 7] = pW2; }
     }
 
     tc_fence_before();
@@ -390,7 +536,8 @@ umma_redo_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefi
 cudaError_t launch_umma(const ResampleLaunch& L, cudaStream_t s, long long* launches) {
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(umma_fir_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(umma_fir_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(umma_fir_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
@@ -399,7 +546,22 @@ cudaError_t launch_umma(const ResampleLaunch& L, cudaStream_t s, long long* laun
     if (grid <= 0) return cudaErrorInvalidValue;
     cudaError_t e = cudaMemsetAsync(L.d_ovf, 0, sizeof(unsigned), s);
     if (e != cudaSuccess) return e;
-    umma_fir_kernel<<<grid, kThreads, L.um_smem, s>>>(L.d_segs, L.d_tile_prefix, L.n_segs, L.n_tiles, L.um, L.um_stages, L.d_ovf);
+    // F9_UMMA_PROF=1 (development): per-role cycle accounting of the first launch, printed to stderr
+    static long long* d_prof = nullptr; static int prof_calls = 0;
+    const char* profEnv = getenv("F9_UMMA_PROF");
+    const bool doProf = profEnv != nullptr && prof_calls++ == atoi(profEnv);
+    if (doProf) { cudaMalloc((void**) &d_prof, sizeof(long long) * 16 * grid); cudaMemsetAsync(d_prof, 0, sizeof(long long) * 16 * grid, s); }
+    if (L.um.poolN == 0)
+        umma_fir_kernel<true><<<grid, kThreads, L.um_smem, s>>>(L.d_segs, L.d_tile_prefix, L.n_segs, L.n_tiles, L.um, L.um_stages, L.um_aligned ? 1 : 0, L.d_ovf, doProf ? d_prof : nullptr);
+    else
+        umma_fir_kernel<false><<<grid, kThreads, L.um_smem, s>>>(L.d_segs, L.d_tile_prefix, L.n_segs, L.n_tiles, L.um, L.um_stages, L.um_aligned ? 1 : 0, L.d_ovf, doProf ? d_prof : nullptr);
+    if (doProf) {
+        std::vector<long long> h((size_t) 16 * grid);
+        cudaStreamSynchronize(s); cudaMemcpy(h.data(), d_prof, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost);
+        double a[16] = {0}; for (int i = 0; i < grid; ++i) for (int k = 0; k < 16; ++k) a[k] += (double) h[(size_t) i * 16 + k] / grid;
+        fprintf(stderr, "[umma prof] tiles/CTA %.1f stages/tile %d | loader total %.0f wait-free %.0f | tensor total %.0f wait-full %.0f wait-drained %.0f | epilogue total %.0f wait-done %.0f stores %.0f | tensor: fence %.0f cp-issue %.0f mma-issue %.0f\n",
+                (double) L.n_tiles / grid, L.um.blk[0].nStages, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10]);
+    }
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     ++*launches;
     umma_redo_kernel<<<std::min(L.n_tiles, 8 * L.sm_count), 256, 0, s>>>(L.d_segs, L.d_tile_prefix, L.n_segs, L.n_tiles, L.um.nGB, L.um.q,

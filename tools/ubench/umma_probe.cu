@@ -64,7 +64,7 @@ constexpr int KCH  = 8;                 // K chunks held (K = 64)
 
 struct Params { int swap_lbo_sbo; int nrep; };
 
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(384, 1)
 probe_kernel(const uint8_t* __restrict__ a_img, const uint8_t* __restrict__ b_img, const __half* __restrict__ a_rm, float* __restrict__ d_out,
              long long* __restrict__ cyc, int* __restrict__ err, Params P) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -79,8 +79,8 @@ probe_kernel(const uint8_t* __restrict__ a_img, const uint8_t* __restrict__ b_im
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_s)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    for (int i = threadIdx.x; i < KCH * A_CH / 16; i += 128) reinterpret_cast<uint4*>(As)[i] = reinterpret_cast<const uint4*>(a_img)[i];
-    for (int i = threadIdx.x; i < KCH * B_CH / 16; i += 128) reinterpret_cast<uint4*>(Bs)[i] = reinterpret_cast<const uint4*>(b_img)[i];
+    for (int i = threadIdx.x; i < KCH * A_CH / 16; i += blockDim.x) reinterpret_cast<uint4*>(As)[i] = reinterpret_cast<const uint4*>(a_img)[i];
+    for (int i = threadIdx.x; i < KCH * B_CH / 16; i += blockDim.x) reinterpret_cast<uint4*>(Bs)[i] = reinterpret_cast<const uint4*>(b_img)[i];
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
