@@ -120,11 +120,11 @@ struct BandedHost {
 void build_banded(int kind, const float* sinc_table, long long p, long long q, int TK, int Gpad, BandedHost* out);
 
 // Tensor-core polyphase FIR (umma_fir_kernel, f9_umma.cu).  Outputs are indexed (period a, slot k) as above; a tile is
-// 128 periods (the M rows of a tcgen05.mma) x one block of <= 14 groups of 16 slots (N).  K runs over the input window of a
+// 128 periods (the M rows of a tcgen05.mma) x one block of groups of NB = 16 or 32 slots (N).  K runs over the input window of a
 // period in steps of 16 samples.  Samples and weights are split into an fp16 head and an fp16 tail scaled by 2^11
 // (x = x0 + x1/2048, w = w0 + w1/2048), three products are kept:  D0 += x0*w0,  D1 += x0*w1 + x1*w0,  out = D0 + D1/2048.
 constexpr int kUmmaMaxBlocks = 8;        // group blocks per ratio (passes over the same rows)
-constexpr int kUmmaMaxGroups = 14;       // groups per block: 32 TMEM columns each, 448 of 512
+constexpr int kUmmaMaxGroups = 14;       // groups per block: 2*NB TMEM columns each, 448 of 512
 constexpr int kUmmaMaxNK = 64;           // K steps per block (period + taps + alignment <= 1024 input samples)
 struct UmmaBlockInfo {
     int U0;            // K index 0 is input sample a*p + U0 (multiple of 16, <= every window start of the block)
@@ -136,7 +136,7 @@ struct UmmaBlockInfo {
     int wOff;          // byte offset into W
 };
 struct UmmaHost {
-    int p = 0, q = 0, taps = 0, G = 0, GBL = 0, nGB = 0;
+    int p = 0, q = 0, taps = 0, NB = 16, G = 0, GBL = 0, nGB = 0;
     int maxEntries = 0, maxNK = 0;
     UmmaBlockInfo blk[kUmmaMaxBlocks] = {};
     // MMA schedule, one word per K step: the groups whose window contains the step are a contiguous range (windows move
@@ -152,16 +152,16 @@ struct UmmaHost {
     std::vector<uint8_t> W;              // fp16 weight tiles [2 K chunks][32 rows: 16 x w0, 16 x w1*2048][8], schedule order
 };
 struct UmmaDev {
-    int p = 0, q = 0, taps = 0, G = 0, GBL = 0, nGB = 0;
+    int p = 0, q = 0, taps = 0, NB = 16, G = 0, GBL = 0, nGB = 0;
     int maxEntries = 0, maxNK = 0;
     UmmaBlockInfo blk[kUmmaMaxBlocks] = {};
     uint32_t ksWord[kUmmaMaxBlocks][kUmmaMaxNK] = {};
     int poolN = 0, split = 0;
     const uint8_t* W = nullptr;
 };
-bool build_umma(int kind, const float* sinc_table, long long p, long long q, int GBL, UmmaHost* out);
-size_t umma_smem_bytes(int maxEntries, int maxNK, int stages);
-double umma_cost_per_output(int taps, long long p, long long q, int GBL, size_t* smem2);   // model used to pick the scaling
+bool build_umma(int kind, const float* sinc_table, long long p, long long q, int NB, int GBL, UmmaHost* out);
+size_t umma_smem_bytes(int maxEntries, int NB, int stages);
+double umma_cost_per_output(int taps, long long p, long long q, int NB, int GBL, size_t* smem2);   // model used to pick the plan
 
 struct ResampleLaunch {
     int kind = 0;
@@ -222,10 +222,10 @@ struct f9_context {
         return std::tie(kind, p, q, TK, Gpad, epoch) < std::tie(o.kind, o.p, o.q, o.TK, o.Gpad, o.epoch); } };
     std::map<BandKey, f9::BandedDev> band_cache;
     int   get_banded(int kind, long long p, long long q, int TK, int Gpad, f9::BandedDev* out);
-    struct UmmaKey { int kind; long long p, q; int GBL; unsigned epoch; bool operator<(const UmmaKey& o) const {
-        return std::tie(kind, p, q, GBL, epoch) < std::tie(o.kind, o.p, o.q, o.GBL, o.epoch); } };
+    struct UmmaKey { int kind; long long p, q; int NB, GBL; unsigned epoch; bool operator<(const UmmaKey& o) const {
+        return std::tie(kind, p, q, NB, GBL, epoch) < std::tie(o.kind, o.p, o.q, o.NB, o.GBL, o.epoch); } };
     std::map<UmmaKey, f9::UmmaDev> umma_cache;
-    int   get_umma(int kind, long long p, long long q, int GBL, f9::UmmaDev* out);
+    int   get_umma(int kind, long long p, long long q, int NB, int GBL, f9::UmmaDev* out);
     unsigned* d_ovf = nullptr;          // see ResampleLaunch::d_ovf
     // Choose kernel + tables for (kind, ratio, pos0); fills everything in L except the segment table.
     int   prepare_resample(int kind, double ratio, double pos0, bool allow_rational, f9::ResampleLaunch* L);

@@ -475,13 +475,13 @@ cudaError_t launch_resample(const ResampleLaunch& L, cudaStream_t s, long long* 
 // ------------------------------------------------------------------------------------------------ planning (host)
 using namespace f9;
 
-int f9_context::get_umma(int kind, long long p, long long q, int GBL, UmmaDev* out) {
-    UmmaKey key{kind, p, q, GBL, sinc_epoch};
+int f9_context::get_umma(int kind, long long p, long long q, int NB, int GBL, UmmaDev* out) {
+    UmmaKey key{kind, p, q, NB, GBL, sinc_epoch};
     auto it = umma_cache.find(key);
     if (it != umma_cache.end()) { *out = it->second; return F9_OK; }
     UmmaHost H;
-    if (!build_umma(kind, sinc_table.data(), p, q, GBL, &H)) return fail(F9_ERR_INVALID, "umma table build failed");
-    UmmaDev D; D.p = H.p; D.q = H.q; D.taps = H.taps; D.G = H.G; D.GBL = H.GBL; D.nGB = H.nGB; D.maxEntries = H.maxEntries; D.maxNK = H.maxNK;
+    if (!build_umma(kind, sinc_table.data(), p, q, NB, GBL, &H)) return fail(F9_ERR_INVALID, "umma table build failed");
+    UmmaDev D; D.p = H.p; D.q = H.q; D.taps = H.taps; D.NB = H.NB; D.G = H.G; D.GBL = H.GBL; D.nGB = H.nGB; D.maxEntries = H.maxEntries; D.maxNK = H.maxNK;
     for (int b = 0; b < kUmmaMaxBlocks; ++b) D.blk[b] = H.blk[b];
     std::memcpy(D.ksWord, H.ksWord, sizeof(D.ksWord));
     D.poolN = H.poolN; D.split = H.split;
@@ -525,31 +525,34 @@ int f9_context::prepare_resample(int kind, double ratio, double pos0, bool allow
         L->rational = true;
         L->sm_count = sm_count;
         if (getenv("F9_NO_UMMA") == nullptr && interp_memory(kind) >= 2) {
-            // Tensor-core path: scale p/q by m so that a period has 64..224 slots, choose the scaling / block size with the
-            // lowest modelled cost whose tables fit shared memory with at least two staging buffers.
+            // Tensor-core path: scale p/q by m so that a period has 64..224 slots; choose the scaling, the group width (16 or
+            // 32 slots) and the block size with the lowest modelled cost whose tables fit shared memory with two staging buffers.
             const int taps = interp_memory(kind);
-            double best = 1e30; long long bm = 0; int bGBL = 0;
+            double best = 1e30; long long bm = 0; int bGBL = 0, bNB = 0;
             for (long long m = 1; m * q <= 16LL * kUmmaMaxGroups * kUmmaMaxBlocks && m * p + taps + 48 <= 16 * kUmmaMaxNK; ++m) {
                 const long long ps = p * m, qs = q * m;
                 if (qs < 48 && (m + 1) * q <= 224) continue;                       // too few slots per period: keep scaling
-                const int G = (int) ((qs + 15) / 16);
-                for (int nGB = (G + kUmmaMaxGroups - 1) / kUmmaMaxGroups; nGB <= kUmmaMaxBlocks && nGB <= G; ++nGB) {
-                    const int GBL = (G + nGB - 1) / nGB;
-                    size_t smem2 = 0;
-                    const double c = umma_cost_per_output(taps, ps, qs, GBL, &smem2);
-                    if (smem2 > 227 * 1024) continue;
-                    if (c < best) { best = c; bm = m; bGBL = GBL; }
-                    break;                                                          // more blocks only cost more
+                for (int NB : {32, 16}) {
+                    if (getenv("F9_UMMA_NB") && atoi(getenv("F9_UMMA_NB")) != NB) continue;
+                    const int G = (int) ((qs + NB - 1) / NB), maxG = std::min(kUmmaMaxGroups, 448 / (2 * NB));
+                    for (int nGB = (G + maxG - 1) / maxG; nGB <= kUmmaMaxBlocks && nGB <= G; ++nGB) {
+                        const int GBL = (G + nGB - 1) / nGB;
+                        size_t smem2 = 0;
+                        const double c = umma_cost_per_output(taps, ps, qs, NB, GBL, &smem2);
+                        if (smem2 > 227 * 1024) continue;
+                        if (c < best) { best = c; bm = m; bGBL = GBL; bNB = NB; }
+                        break;                                                      // more blocks only cost more
+                    }
                 }
                 if (qs >= 224) break;
             }
             if (bm > 0) {
                 if (!d_ovf) F9_TRY_CUDA(this, cudaMalloc((void**) &d_ovf, sizeof(unsigned)));
-                rc = get_umma(kind, p * bm, q * bm, bGBL, &L->um);
+                rc = get_umma(kind, p * bm, q * bm, bNB, bGBL, &L->um);
                 if (rc == F9_OK) {
                     int stages = 2;
-                    while (stages < 4 && umma_smem_bytes(L->um.maxEntries, L->um.maxNK, stages + 1) <= 227 * 1024) ++stages;
-                    L->um_stages = stages; L->um_smem = umma_smem_bytes(L->um.maxEntries, L->um.maxNK, stages);
+                    while (stages < 4 && umma_smem_bytes(L->um.maxEntries, L->um.NB, stages + 1) <= 227 * 1024) ++stages;
+                    L->um_stages = stages; L->um_smem = umma_smem_bytes(L->um.maxEntries, L->um.NB, stages);
                     L->d_ovf = d_ovf; L->umma = true;
                     return F9_OK;
                 }

@@ -292,72 +292,81 @@ float f16_bits_to_f32(uint16_t h) {
 inline long long floor16(long long x) { return x >= 0 ? (x / 16) * 16 : -(((-x) + 15) / 16) * 16; }
 
 struct GroupGeom { long long t0; int ksteps; long long wend; };   // K origin of the group's first step (multiple of 16), steps, window end
-void group_geom(long long p, long long q, int taps, int g, GroupGeom* out) {
-    const long long k0 = 16LL * g, k1 = std::min<long long>(q, k0 + 16) - 1;
+void group_geom(long long p, long long q, int taps, int NB, int g, GroupGeom* out) {
+    const long long k0 = (long long) NB * g, k1 = std::min<long long>(q, k0 + NB) - 1;
     const long long wmin = (k0 * p) / q - (taps - 1), wend = (k1 * p) / q + 1;
     out->t0 = floor16(wmin);
     out->ksteps = (int) ((wend - out->t0 + 15) / 16);
     out->wend = wend;
 }
+int umma_pool_slots(int NB, int GBL) {                     // accumulator-split pool: power of two, NB columns per slot
+    const int spare = 448 - GBL * 2 * NB;                  // TMEM columns 448..511 hold the operand ring
+    int n = 0;
+    for (int c = 8; c >= 2; c /= 2) if (c * NB <= spare) { n = c; break; }
+    return n;
+}
 
 }  // namespace
 
-size_t umma_smem_bytes(int maxEntries, int maxNK, int stages) {
-    const size_t w = (size_t) maxEntries * 1024;
+size_t umma_smem_bytes(int maxEntries, int NB, int stages) {
+    const size_t w = (size_t) maxEntries * NB * 64;        // tile: 2 K chunks x 2*NB rows x 16 B
     const size_t ring = (size_t) stages * 8 * (128 * 16 + 32);
-    const size_t epi = 128 * 36 * 4;
-    const size_t sched = 0; (void) maxNK;
+    const size_t epi = 128 * 20 * 4;
     const size_t bars = (size_t) (2 * stages + 2 * kUmmaMaxGroups) * 8 + 16;
-    return w + ring + epi + sched + bars + 128;       // + alignment slack
+    return w + ring + epi + bars + 128;                    // + alignment slack
 }
 
-// Relative cost (SM cycles per output) of running ratio p/q with GBL groups per block: the tensor pipe
-// (tcgen05.cp 64 clk per 4 KB operand tile, 24 clk of MMAs per active (K step, group)) against the load/store unit
-// (one wavefront per 128 bytes loaded, stored to shared memory, and three per 128 bytes of output).
-double umma_cost_per_output(int taps, long long p, long long q, int GBL, size_t* smem2) {
-    const int G = (int) ((q + 15) / 16);
+// Relative cost (SM cycles per output) of running ratio p/q with groups of NB slots, GBL groups per block.  Tensor pipe:
+// tcgen05.cp 64 clk per 4 KB operand tile (4 per stage of 32 samples), three MMAs per active (K step, group) at
+// max(16, NB/2) clk each (measured: an MMA that fetches a fresh B tile costs >= 16 clk).  Issue: ~45 clk per MMA.
+// Load/store unit: one wavefront per 128 bytes loaded, stored to shared memory, and three per 128 bytes of output.
+double umma_cost_per_output(int taps, long long p, long long q, int NB, int GBL, size_t* smem2) {
+    const int G = (int) ((q + NB - 1) / NB);
     const int nGB = (G + GBL - 1) / GBL;
-    double tensor = 0.0, lsu = 0.0; int maxEntries = 0, maxNK = 0;
+    double tensor = 0.0, issue = 0.0, lsu = 0.0; int maxEntries = 0;
     for (int b = 0; b < nGB; ++b) {
         long long lo = (1LL << 60), hi = -(1LL << 60); int entries = 0;
         for (int g = b * GBL; g < std::min(G, (b + 1) * GBL); ++g) {
-            GroupGeom gg; group_geom(p, q, taps, g, &gg);
+            GroupGeom gg; group_geom(p, q, taps, NB, g, &gg);
             lo = std::min(lo, gg.t0); hi = std::max(hi, gg.t0 + 16LL * gg.ksteps); entries += gg.ksteps;
         }
         const int nK = (int) ((hi - lo) / 16);
-        tensor += 128.0 * nK + 24.0 * entries;
+        tensor += 128.0 * nK + 3.0 * std::max(16, NB / 2) * entries;
+        issue += 135.0 * entries + 150.0 * nK;
         lsu += 2.0 * nK * 16 * 128 * 4 / 128.0;
-        maxEntries = std::max(maxEntries, entries); maxNK = std::max(maxNK, nK);
+        maxEntries = std::max(maxEntries, entries);
     }
     lsu += 3.0 * (double) q * 128 * 4 / 128.0;
-    if (smem2) *smem2 = umma_smem_bytes(maxEntries, maxNK + 1, 2);
-    return std::max(tensor, lsu) / (128.0 * (double) q);
+    if (smem2) *smem2 = umma_smem_bytes(maxEntries, NB, 2);
+    return std::max(std::max(tensor, issue), lsu) / (128.0 * (double) q);
 }
 
-bool build_umma(int kind, const float* sinc_table, long long p, long long q, int GBL, UmmaHost* out) {
+bool build_umma(int kind, const float* sinc_table, long long p, long long q, int NB, int GBL, UmmaHost* out) {
     const int taps = interp_memory(kind);
-    const int G = (int) ((q + 15) / 16);
-    if (GBL < 1 || GBL > kUmmaMaxGroups) return false;
+    if (NB != 16 && NB != 32) return false;
+    const int G = (int) ((q + NB - 1) / NB);
+    if (GBL < 1 || GBL * 2 * NB > 448) return false;
     const int nGB = (G + GBL - 1) / GBL;
     if (nGB > kUmmaMaxBlocks) return false;
     *out = UmmaHost();
-    out->p = (int) p; out->q = (int) q; out->taps = taps; out->G = G; out->GBL = GBL; out->nGB = nGB;
+    out->p = (int) p; out->q = (int) q; out->taps = taps; out->NB = NB; out->G = G; out->GBL = GBL; out->nGB = nGB;
+    const int tileBytes = NB * 64, chunkBytes = NB * 32;
     // accumulation split: only for long windows; the split step is the same for every group (first step past every slot's
     // centre tap), which keeps "past the split" a bottom-end range of the active groups.
-    int poolN = GBL <= 10 ? 8 : (GBL <= 12 ? 4 : 0), split = 0;
+    int poolN = umma_pool_slots(NB, GBL), split = 0;
     if (taps >= 64 && poolN > 0) {
         for (int g = 0; g < G; ++g) {
-            GroupGeom gg; group_geom(p, q, taps, g, &gg);
-            const long long k1 = std::min<long long>(q, 16LL * g + 16) - 1;
+            GroupGeom gg; group_geom(p, q, taps, NB, g, &gg);
+            const long long k1 = std::min<long long>(q, (long long) NB * g + NB) - 1;
             const long long centre = (k1 * p) / q - (taps - 1) - gg.t0 + taps / 2 + 2;     // K offset of the last slot's centre tap
             split = std::max(split, (int) ((centre + 8 + 15) / 16));
         }
         for (int g = 0; g < G && poolN > 0; ++g) {
-            GroupGeom gg; group_geom(p, q, taps, g, &gg);
+            GroupGeom gg; group_geom(p, q, taps, NB, g, &gg);
             if (gg.ksteps <= split) poolN = 0;                                              // a group without a second part
             const int gl = g % GBL;
             if (gl >= poolN && poolN > 0) {                                                 // slot reuse inside a tile: the previous
-                GroupGeom gp; group_geom(p, q, taps, g - poolN, &gp);                       // user must have finished before
+                GroupGeom gp; group_geom(p, q, taps, NB, g - poolN, &gp);                   // user must have finished before
                 if (gg.t0 / 16 + split < gp.t0 / 16 + gp.ksteps) poolN = 0;                 // this group crosses its split
             }
         }
@@ -365,19 +374,18 @@ bool build_umma(int kind, const float* sinc_table, long long p, long long q, int
     if (poolN == 0) split = 0;
     out->poolN = poolN; out->split = split;
     std::vector<float> w((size_t) taps);
-    std::vector<float> wslot((size_t) 16 * taps);
     for (int b = 0; b < nGB; ++b) {
         UmmaBlockInfo& BI = out->blk[b];
         const int g0 = b * GBL, g1 = std::min(G, g0 + GBL);
         std::vector<GroupGeom> geo((size_t) (g1 - g0));
         long long lo = (1LL << 60), hi = -(1LL << 60), wendMax = -(1LL << 60);
         for (int g = g0; g < g1; ++g) {
-            group_geom(p, q, taps, g, &geo[(size_t) (g - g0)]);
+            group_geom(p, q, taps, NB, g, &geo[(size_t) (g - g0)]);
             lo = std::min(lo, geo[(size_t) (g - g0)].t0);
             hi = std::max(hi, geo[(size_t) (g - g0)].t0 + 16LL * geo[(size_t) (g - g0)].ksteps);
             wendMax = std::max(wendMax, geo[(size_t) (g - g0)].wend);
         }
-        BI.U0 = (int) lo; BI.nK = (int) ((hi - lo) / 16); BI.nGroups = g1 - g0; BI.slot0 = g0 * 16;
+        BI.U0 = (int) lo; BI.nK = (int) ((hi - lo) / 16); BI.nGroups = g1 - g0; BI.slot0 = g0 * NB;
         BI.nStages = std::max((BI.nK + 1) / 2, (int) ((wendMax - lo + 3 + 31) / 32));
         BI.wOff = (int) out->W.size();
         if (BI.nK > kUmmaMaxNK) return false;
@@ -386,9 +394,9 @@ bool build_umma(int kind, const float* sinc_table, long long p, long long q, int
         std::vector<std::vector<int>> gshift((size_t) (g1 - g0));
         for (int g = g0; g < g1; ++g) {
             auto& W = gw[(size_t) (g - g0)]; auto& S = gshift[(size_t) (g - g0)];
-            W.assign((size_t) 16 * taps, 0.0f); S.assign(16, -1);
-            for (int s = 0; s < 16; ++s) {
-                const long long k = 16LL * g + s;
+            W.assign((size_t) NB * taps, 0.0f); S.assign((size_t) NB, -1);
+            for (int s = 0; s < NB; ++s) {
+                const long long k = (long long) NB * g + s;
                 if (k >= q) break;
                 const long long phi = (k * p) % q;
                 const float offset = (float) ((double) phi / (double) q);
@@ -411,8 +419,8 @@ bool build_umma(int kind, const float* sinc_table, long long p, long long q, int
                 if (j == gg.ksteps - 1) { if (nLast != cnt) return false; ++nLast; }   // finishers are the bottom
                 if (poolN > 0 && j >= split) { if (nSecond != cnt) return false; ++nSecond; if (j == split) ++nEnter; }
                 const size_t base = out->W.size();
-                out->W.resize(base + 1024, 0);
-                for (int s = 0; s < 16; ++s) {
+                out->W.resize(base + (size_t) tileBytes, 0);
+                for (int s = 0; s < NB; ++s) {
                     const int sh = gshift[(size_t) (g - g0)][(size_t) s];
                     if (sh < 0) continue;
                     for (int kk = 0; kk < 16; ++kk) {
@@ -421,8 +429,8 @@ bool build_umma(int kind, const float* sinc_table, long long p, long long q, int
                         const float wv = gw[(size_t) (g - g0)][(size_t) s * taps + (size_t) tap];
                         const uint16_t h0 = f32_to_f16_bits(wv);
                         const uint16_t h1 = f32_to_f16_bits((wv - f16_bits_to_f32(h0)) * 2048.0f);
-                        const size_t off0 = base + (size_t) (kk / 8) * 512 + (size_t) s * 16 + (size_t) (kk % 8) * 2;
-                        const size_t off1 = off0 + 16 * 16;
+                        const size_t off0 = base + (size_t) (kk / 8) * chunkBytes + (size_t) s * 16 + (size_t) (kk % 8) * 2;
+                        const size_t off1 = off0 + (size_t) NB * 16;
                         std::memcpy(&out->W[off0], &h0, 2); std::memcpy(&out->W[off1], &h1, 2);
                     }
                 }

@@ -39,7 +39,7 @@ namespace {
 constexpr int kRows = 128;                       // periods per tile = MMA M
 constexpr int kChunk = kRows * 16 + 32;          // bytes between K chunks (8 samples) of the X operand: 128 rows x 16 B + pad
 constexpr int kStageBytes = 8 * kChunk;          // one stage = 32 samples: chunks 0-3 head (x0), 4-7 tail (x1)
-constexpr int kEpiPitch = 36;                    // floats per row of the epilogue transpose buffer (32 + 4)
+constexpr int kEpiPitch = 20;                    // floats per row of the epilogue transpose buffer (16 + 4)
 constexpr int kACol = 448;                       // TMEM columns 448..511: ring of 4 K steps x (8 head + 8 tail)
 constexpr int kLoaderWarps = 8;
 constexpr int kThreads = (4 + 1 + kLoaderWarps) * 32;
@@ -125,10 +125,10 @@ struct SmemMap {
     uint8_t* W; uint8_t* ring; float* epi;
     uint64_t *full, *empty, *accFull, *accEmpty; uint32_t* tmemSlot;
 };
-__device__ __forceinline__ SmemMap carve(uint8_t* smem, int maxEntries, int stages) {
+__device__ __forceinline__ SmemMap carve(uint8_t* smem, int maxEntries, int NB, int stages) {
     SmemMap m;
     m.W = smem;
-    m.ring = m.W + (size_t) maxEntries * 1024;
+    m.ring = m.W + (size_t) maxEntries * NB * 64;
     m.epi = reinterpret_cast<float*>(m.ring + (size_t) stages * kStageBytes);
     m.full = reinterpret_cast<uint64_t*>(m.epi + kRows * kEpiPitch);
     m.empty = m.full + stages;
@@ -287,9 +287,10 @@ __device__ __forceinline__ void loader_role(const LoaderArgs& A, int lw, int lan
 template <bool MERGED>
 __global__ void __launch_bounds__(kThreads, 1)
 umma_fir_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix, int nSegs, int nTiles,
-                const __grid_constant__ UmmaDev P, int stages, int alignedAll, unsigned* __restrict__ ovf, long long* __restrict__ prof) {
+                const __grid_constant__ UmmaDev P, int stages, int alignedAll, unsigned* __restrict__ ovf, long long* __restrict__ prof, int dbg) {
     extern __shared__ __align__(128) uint8_t smem[];
-    const SmemMap sm = carve(smem, P.maxEntries, stages);
+    const SmemMap sm = carve(smem, P.maxEntries, P.NB, stages);
+    const int NB = P.NB;                                       // slots per group: MMA N
     const int warp = __shfl_sync(0xffffffffu, (int) (threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int gb = blockIdx.x % P.nGB;
     const UmmaBlockInfo& BI = P.blk[gb];
@@ -301,7 +302,7 @@ umma_fir_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix
     {
         const uint4* src = reinterpret_cast<const uint4*>(P.W + BI.wOff);
         uint4* dst = reinterpret_cast<uint4*>(sm.W);
-        for (int i = threadIdx.x; i < BI.nEntries * 64; i += kThreads) dst[i] = __ldg(src + i);
+        for (int i = threadIdx.x; i < BI.nEntries * NB * 4; i += kThreads) dst[i] = __ldg(src + i);
         if (threadIdx.x == 0) {
             for (int s = 0; s < stages; ++s) { mbar_init(sm.full + s, kLoaderWarps); mbar_init(sm.empty + s, 1); }
             for (int g = 0; g < kUmmaMaxGroups; ++g) { mbar_init(sm.accFull + g, 1); mbar_init(sm.accEmpty + g, 4); }
@@ -320,7 +321,7 @@ umma_fir_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix
     // optional cycle accounting (development): per CTA [0] loader-warp-0 total, [1] its wait on "stage free", [2] tensor warp
     // total, [3] its wait on "stage full", [4] its wait on "accumulator drained", [5] epilogue-warp-0 total, [6] its wait on
     // "group done", [7] its time in the store loops
-    long long pT0 = 0, pW0 = 0, pW1 = 0, pW2 = 0, pF = 0, pC = 0, pM = 0;
+    long long pT0 = 0, pW0 = 0, pW1 = 0, pW2 = 0, pF = 0, pC = 0, pM = 0, pI = 0;
     #define PROF_BEGIN(v) long long v = prof ? clock64() : 0
     #define PROF_END(acc, v) if (prof) acc += clock64() - v
     if (prof) pT0 = clock64();
@@ -339,32 +340,43 @@ umma_fir_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix
         // registers, and what bounds this warp is the handful of uniform-datapath instructions per MMA, not the tensor pipe
         // (measured: ~45 clk per issued MMA against 8 clk of pipe time), hence the straight-line 4-entry blocks below.
         const uint32_t el = elect_one();
-        const uint32_t idesc16 = make_idesc(kRows, 16), idesc32 = make_idesc(kRows, 32);
-        const uint32_t poolCol = (uint32_t) (P.GBL * 32), poolMask = (uint32_t) (P.poolN > 0 ? P.poolN - 1 : 0);
-        const uint64_t wDesc0 = make_desc(smem_u32(sm.W), 512, 128);           // weight tile e: + 64*e (1 KB, 16-byte units)
+        const uint32_t idescN = make_idesc(kRows, NB), idesc2N = make_idesc(kRows, 2 * NB);
+        const uint32_t nb = (uint32_t) NB, poolCol = (uint32_t) (P.GBL * 2 * NB), poolMask = (uint32_t) (P.poolN > 0 ? P.poolN - 1 : 0);
+        const uint64_t wDesc0 = make_desc(smem_u32(sm.W), 32 * NB, 128);       // weight tile e: + 4*NB*e (16-byte units); w1 rows at + NB
         const uint64_t aDesc0 = make_desc(smem_u32(sm.ring), kChunk, 128);
+        // The copies of stage g+1 are issued BEFORE the MMAs of stage g: an MMA then never waits on a copy that was issued
+        // just ahead of it (the pipe executes in order, and a dependent MMA stalls the issuing thread for the copy's whole
+        // latency).  TMEM operand slots alternate with the global stage count, so consecutive stages never share a slot.
         int sIdx = 0; uint32_t sPh = 0;
+        const int totalStages = myTiles * nStages;
+        auto stage_in = [&](int gs) {                          // wait for stage gs in shared memory, copy it into TMEM slot gs & 1
+            { PROF_BEGIN(w); mbar_wait(sm.full + sIdx, sPh); PROF_END(pW0, w); }
+            PROF_BEGIN(wf);
+            fence_async_smem();                                // generic-proxy stores of the loaders -> async-proxy reads of tcgen05.cp
+            tc_fence_after();
+            PROF_END(pF, wf);
+            PROF_BEGIN(wc);
+            if (el) {
+                const uint64_t ad = aDesc0 + (uint64_t) ((sIdx * kStageBytes) >> 4);
+                const uint32_t slot0 = tmem + kACol + (uint32_t) ((gs & 1) * 32);
+                if (!(dbg & 2)) {
+                umma_cp(slot0, ad);                                             // first K step  head
+                umma_cp(slot0 + 8, ad + ((4 * kChunk) >> 4));                   //               tail
+                umma_cp(slot0 + 16, ad + ((2 * kChunk) >> 4));                  // second K step head
+                umma_cp(slot0 + 24, ad + ((6 * kChunk) >> 4));                  //               tail
+                }
+                umma_commit(sm.empty + sIdx);                  // the stage is free once the copies have read it
+            }
+            __syncwarp();
+            PROF_END(pC, wc);
+            if (++sIdx == stages) { sIdx = 0; sPh ^= 1; }
+        };
+        if (totalStages > 0) stage_in(0);
+        int gs = 0;
         for (int t = 0; t < myTiles; ++t) {
             uint32_t e = 0;
-            for (int st = 0; st < nStages; ++st) {
-                { PROF_BEGIN(w); mbar_wait(sm.full + sIdx, sPh); PROF_END(pW0, w); }
-                PROF_BEGIN(wf);
-                fence_async_smem();                            // generic-proxy stores of the loaders -> async-proxy reads of tcgen05.cp
-                tc_fence_after();
-                PROF_END(pF, wf);
-                PROF_BEGIN(wc);
-                if (el) {
-                    const uint64_t ad = aDesc0 + (uint64_t) ((sIdx * kStageBytes) >> 4);
-                    const uint32_t slot0 = tmem + kACol + (uint32_t) ((st & 1) * 32);
-                    umma_cp(slot0, ad);                                         // K step 2*st   head
-                    umma_cp(slot0 + 8, ad + ((4 * kChunk) >> 4));               //               tail
-                    umma_cp(slot0 + 16, ad + ((2 * kChunk) >> 4));              // K step 2*st+1 head
-                    umma_cp(slot0 + 24, ad + ((6 * kChunk) >> 4));              //               tail
-                    umma_commit(sm.empty + sIdx);              // the stage is free once the copies have read it
-                }
-                __syncwarp();
-                PROF_END(pC, wc);
-                if (++sIdx == stages) { sIdx = 0; sPh ^= 1; }
+            for (int st = 0; st < nStages; ++st, ++gs) {
+                if (gs + 1 < totalStages) stage_in(gs + 1);
                 PROF_BEGIN(wm);
                 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
@@ -373,7 +385,7 @@ umma_fir_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix
                     const uint32_t word = P.ksWord[gb][ks];
                     const uint32_t gl0 = word & 15u, cnt = (word >> 4) & 15u, nFirst = (word >> 8) & 15u, nLast = (word >> 12) & 15u;
                     const uint32_t nSecond = (word >> 16) & 15u, nEnter = (word >> 20) & 15u;
-                    const uint32_t aHi = tmem + kACol + (uint32_t) ((ks & 3) * 16);
+                    const uint32_t aHi = tmem + kACol + (uint32_t) ((gs & 1) * 32 + h * 16);
                     // waits first (rare: once per group and tile), so that the issue block below is straight-line code
                     if (nFirst | nEnter) {
                         PROF_BEGIN(w);
@@ -390,39 +402,44 @@ umma_fir_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix
                         PROF_END(pW1, w);
                         tc_fence_after();
                     }
+                    PROF_BEGIN(wi);
                     if (el) {
-                        for (uint32_t c0 = 0; c0 < cnt; c0 += 4) {
-                            #pragma unroll
-                            for (uint32_t u = 0; u < 4; ++u) {
-                                const uint32_t c = c0 + u, gl = gl0 + c;
-                                const uint32_t valid = c < cnt;
-                                const bool first = c + nFirst >= cnt;
-                                const uint32_t d1 = tmem + gl * 32 + 16;
-                                const uint64_t bd = wDesc0 + (uint64_t) ((e + c) * 64u);
-                                if (MERGED) {                  // no accumulator split: [D0 | D1] (+)= x0 * [w0 | w1] as one N = 32 MMA
-                                    umma_ts_if(valid, d1 - 16, aHi, bd, idesc32, first ? 0u : 1u);
-                                } else {                       // three MMAs of identical shape
-                                    const bool second = c < nSecond, enter = second && c + nEnter >= nSecond;
-                                    const uint32_t d0 = second ? tmem + poolCol + (gl & poolMask) * 16 : d1 - 16;
-                                    umma_ts_if(valid, d0, aHi, bd, idesc16, (first || enter) ? 0u : 1u);   // D0 (+)= x0 * w0
-                                    umma_ts_if(valid, d1, aHi, bd + 16, idesc16, first ? 0u : 1u);         // D1 (+)= x0 * w1
-                                }
-                                umma_ts_if(valid, d1, aHi + 8, bd, idesc16, 1u);                           // D1  += x1 * w0
-                                umma_commit_if(valid && c < nLast, sm.accFull + gl);
+                        // rolled loop, strength-reduced operands: the cost of this block is its uniform-datapath instruction
+                        // count (~4 clk each), so it must be proportional to the number of entries
+                        uint32_t d1 = tmem + (2 * gl0 + 1) * nb;
+                        uint64_t bd = wDesc0 + (uint64_t) (e * 4u * nb);
+                        uint64_t* fullBar = sm.accFull + gl0;
+                        const uint32_t cFirst = cnt - nFirst, cEnter = nSecond - nEnter;
+                        #pragma unroll 1
+                        for (uint32_t c = 0; c < cnt; ++c, d1 += 2 * nb, bd += 4 * nb, ++fullBar) {
+                            const uint32_t accD1 = c < cFirst ? 1u : 0u;
+                            if (dbg & 1) { if (c < nLast) umma_commit(fullBar); continue; }
+                            if (MERGED || c >= nSecond) {      // D0 and D1 adjacent: [D0 | D1] (+)= x0 * [w0 | w1] as one N = 2*NB MMA
+                                umma_ts(d1 - nb, aHi, bd, idesc2N, accD1);
+                            } else {                           // past the split: D0 lives in the pool
+                                umma_ts(tmem + poolCol + ((gl0 + c) & poolMask) * nb, aHi, bd, idescN, c >= cEnter ? 0u : 1u);   // D0B (+)= x0 * w0
+                                umma_ts(d1, aHi, bd + nb, idescN, 1u);                                                        // D1    += x0 * w1
                             }
+                            umma_ts(d1, aHi + 8, bd, idescN, 1u);                                                             // D1    += x1 * w0
+                            if (c < nLast) umma_commit(fullBar);
                         }
                     }
                     __syncwarp();
+                    PROF_END(pI, wi);
                     e += cnt;
                 }
                 PROF_END(pM, wm);
             }
         }
-        if (prof && lane == 0) { prof[blockIdx.x * 16 + 8] = pF; prof[blockIdx.x * 16 + 9] = pC; prof[blockIdx.x * 16 + 10] = pM; }
+        if (prof && lane == 0) { prof[blockIdx.x * 16 + 8] = pF; prof[blockIdx.x * 16 + 9] = pC; prof[blockIdx.x * 16 + 10] = pM; prof[blockIdx.x * 16 + 11] = pI; }
         if (prof && lane == 0) { prof[blockIdx.x * 16 + 2] = clock64() - pT0; prof[blockIdx.x * 16 + 3] = pW0; prof[blockIdx.x * 16 + 4] = pW1; }
     } else {
         // =========================================================== epilogue
-        const int row0 = warp * 32 + lane;                     // TMEM lane = period row of this thread
+        // Thread = TMEM lane = period row.  Per group and 16-slot chunk: read D0 (+ its pool half) and D1, combine, transpose
+        // through the warp's own slice of the staging buffer, store two rows per instruction (16 slots = 64 contiguous bytes).
+        const int row0 = warp * 32 + lane;
+        const uint32_t laneBase = (uint32_t) (warp * 32) << 16;
+        const int chunks = NB / 16;
         int tileId = blockIdx.x;
         for (int t = 0; t < myTiles; ++t, tileId += gridDim.x) {
             const int sidx = find_seg(tilePrefix, nSegs, tileId);
@@ -430,71 +447,60 @@ umma_fir_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix
             const int pb = (tileId - tilePrefix[sidx]) / P.nGB;
             const long long A0 = S.n0 / q + (long long) pb * kRows;
             const long long oBase = A0 * q + BI.slot0 - S.n0;                  // output index of (row 0, slot 0 of the block)
-            const int blockSlots = min(BI.nGroups * 16, q - BI.slot0);          // real (non-padding) slots of this block
+            const int blockSlots = min(BI.nGroups * NB, q - BI.slot0);          // real (non-padding) slots of this block
             const bool rowsInside = oBase >= 0 && oBase + (long long) (kRows - 1) * q + blockSlots <= S.numOut;
-            for (int gp = 0; gp * 2 < BI.nGroups; ++gp) {
-                #pragma unroll
-                for (int gg = 0; gg < 2; ++gg) {
-                    const int gl = gp * 2 + gg;
-                    float o[16];
-                    if (gl < BI.nGroups) {
-                        { PROF_BEGIN(w); mbar_wait_parked(sm.accFull + gl, t & 1, 2000); PROF_END(pW0, w); }
-                        tc_fence_after();
-                        uint32_t v[32];
-                        const uint32_t taddr = tmem + (uint32_t) (gl * 32) + ((uint32_t) (warp * 32) << 16);
-                        asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-                                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                                       "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-                                       "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-                                       "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                                     : "r"(taddr));
-                        uint32_t vb[16];
-                        if (P.poolN > 0) {
-                            const uint32_t tb = tmem + (uint32_t) (P.GBL * 32 + (gl & (P.poolN - 1)) * 16) + ((uint32_t) (warp * 32) << 16);
-                            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                                         : "=r"(vb[0]), "=r"(vb[1]), "=r"(vb[2]), "=r"(vb[3]), "=r"(vb[4]), "=r"(vb[5]), "=r"(vb[6]), "=r"(vb[7]),
-                                           "=r"(vb[8]), "=r"(vb[9]), "=r"(vb[10]), "=r"(vb[11]), "=r"(vb[12]), "=r"(vb[13]), "=r"(vb[14]), "=r"(vb[15])
-                                         : "r"(tb));
-                        } else {
-                            #pragma unroll
-                            for (int c = 0; c < 16; ++c) vb[c] = 0u;
-                        }
-                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            float* outG = reinterpret_cast<float*>(__cvta_generic_to_global(S.out));
+            for (int gl = 0; gl < BI.nGroups; ++gl) {
+                { PROF_BEGIN(w); mbar_wait_parked(sm.accFull + gl, t & 1, 2000); PROF_END(pW0, w); }
+                tc_fence_after();
+                for (int h = 0; h < chunks; ++h) {
+                    uint32_t v0[16], v1[16], vb[16];
+                    const uint32_t c0 = tmem + laneBase + (uint32_t) (gl * 2 * NB + h * 16);
+                    #define LD16(arr, addr) asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];" \
+                        : "=r"(arr[0]), "=r"(arr[1]), "=r"(arr[2]), "=r"(arr[3]), "=r"(arr[4]), "=r"(arr[5]), "=r"(arr[6]), "=r"(arr[7]), \
+                          "=r"(arr[8]), "=r"(arr[9]), "=r"(arr[10]), "=r"(arr[11]), "=r"(arr[12]), "=r"(arr[13]), "=r"(arr[14]), "=r"(arr[15]) : "r"(addr))
+                    LD16(v0, c0);
+                    LD16(v1, c0 + (uint32_t) NB);
+                    if (P.poolN > 0) { LD16(vb, tmem + laneBase + (uint32_t) (P.GBL * 2 * NB + (gl & (P.poolN - 1)) * NB + h * 16)); }
+                    else {
+                        #pragma unroll
+                        for (int c = 0; c < 16; ++c) vb[c] = 0u;
+                    }
+                    #undef LD16
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (h == chunks - 1) {                     // the whole group has been read: the next tile may overwrite it
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(sm.accEmpty + gl);      // the next tile may overwrite these accumulators
-                        #pragma unroll
-                        for (int c = 0; c < 16; ++c)
-                            o[c] = fmaf(__uint_as_float(v[16 + c]), 1.0f / 2048.0f, __uint_as_float(v[c]) + __uint_as_float(vb[c]));
+                        if (lane == 0) mbar_arrive(sm.accEmpty + gl);
+                    }
+                    float4* dst = reinterpret_cast<float4*>(sm.epi + row0 * kEpiPitch);
+                    #pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        dst[c] = make_float4(fmaf(__uint_as_float(v1[4 * c]), 1.0f / 2048.0f, __uint_as_float(v0[4 * c]) + __uint_as_float(vb[4 * c])),
+                                             fmaf(__uint_as_float(v1[4 * c + 1]), 1.0f / 2048.0f, __uint_as_float(v0[4 * c + 1]) + __uint_as_float(vb[4 * c + 1])),
+                                             fmaf(__uint_as_float(v1[4 * c + 2]), 1.0f / 2048.0f, __uint_as_float(v0[4 * c + 2]) + __uint_as_float(vb[4 * c + 2])),
+                                             fmaf(__uint_as_float(v1[4 * c + 3]), 1.0f / 2048.0f, __uint_as_float(v0[4 * c + 3]) + __uint_as_float(vb[4 * c + 3])));
+                    __syncwarp();
+                    PROF_BEGIN(wst);
+                    const int col = gl * NB + h * 16 + (lane & 15);           // slot inside the block
+                    const int rsel = lane >> 4;
+                    const float* src = sm.epi + (warp * 32 + rsel) * kEpiPitch + (lane & 15);
+                    const long long o0 = oBase + (long long) (warp * 32 + rsel) * q + col;
+                    float* dstp = outG + o0;
+                    if (dbg & 4) {} else if (rowsInside && gl * NB + h * 16 + 16 <= blockSlots) {
+                        #pragma unroll 8
+                        for (int r = 0; r < 16; ++r, dstp += 2 * q)
+                            asm volatile("st.global.cs.f32 [%0], %1;" :: "l"(dstp), "f"(src[r * 2 * kEpiPitch]) : "memory");
                     } else {
-                        #pragma unroll
-                        for (int c = 0; c < 16; ++c) o[c] = 0.0f;
+                        const bool slotOk = col < blockSlots;
+                        for (int r = 0; r < 16; ++r, dstp += 2 * q) {
+                            const long long o = o0 + (long long) r * 2 * q;
+                            if (slotOk && o >= 0 && o < S.numOut) *dstp = src[r * 2 * kEpiPitch];
+                        }
                     }
-                    float4* dst = reinterpret_cast<float4*>(sm.epi + row0 * kEpiPitch + gg * 16);
-                    dst[0] = make_float4(o[0], o[1], o[2], o[3]);   dst[1] = make_float4(o[4], o[5], o[6], o[7]);
-                    dst[2] = make_float4(o[8], o[9], o[10], o[11]); dst[3] = make_float4(o[12], o[13], o[14], o[15]);
+                    __syncwarp();
+                    PROF_END(pW2, wst);
                 }
-                // Each warp transposes its own 32 rows (its TMEM lanes) through its own slice of the staging buffer: only a
-                // warp-level sync, then one coalesced 128-byte store per row (32 slots are contiguous in the output).
-                __syncwarp();
-                PROF_BEGIN(wst);
-                const float* src = sm.epi + (warp * 32) * kEpiPitch + lane;
-                const long long o0 = oBase + (long long) (warp * 32) * q + gp * 32 + lane;
-                float* dstp = reinterpret_cast<float*>(__cvta_generic_to_global(S.out)) + o0;
-                if (rowsInside && gp * 32 + 32 <= blockSlots) {
-                    #pragma unroll 8
-                    for (int r = 0; r < 32; ++r, dstp += q)
-                        asm volatile("st.global.cs.f32 [%0], %1;" :: "l"(dstp), "f"(src[r * kEpiPitch]) : "memory");
-                } else {
-                    const int slot = BI.slot0 + gp * 32 + lane;
-                    const bool slotOk = slot < q && gp * 32 + lane < blockSlots;
-                    for (int r = 0; r < 32; ++r, dstp += q) {
-                        const long long o = o0 + (long long) r * q;
-                        if (slotOk && o >= 0 && o < S.numOut) *dstp = src[r * kEpiPitch];
-                    }
-                }
-                __syncwarp();
-                PROF_END(pW2, wst);
             }
         }
         if (prof && warp == 0 && lane == 0) { prof[blockIdx.x * 16 + 5] = clock64() - pT0; prof[blockIdx.x * 16 + 6] = pW0; prof[blockIdx.x * 16 + 7] = pW2; }
@@ -551,16 +557,17 @@ cudaError_t launch_umma(const ResampleLaunch& L, cudaStream_t s, long long* laun
     const char* profEnv = getenv("F9_UMMA_PROF");
     const bool doProf = profEnv != nullptr && prof_calls++ == atoi(profEnv);
     if (doProf) { cudaMalloc((void**) &d_prof, sizeof(long long) * 16 * grid); cudaMemsetAsync(d_prof, 0, sizeof(long long) * 16 * grid, s); }
+    const int dbg = getenv("F9_UMMA_DBG") ? atoi(getenv("F9_UMMA_DBG")) : 0;     // development: 1 skip MMAs, 2 skip copies, 4 skip stores
     if (L.um.poolN == 0)
-        umma_fir_kernel<true><<<grid, kThreads, L.um_smem, s>>>(L.d_segs, L.d_tile_prefix, L.n_segs, L.n_tiles, L.um, L.um_stages, L.um_aligned ? 1 : 0, L.d_ovf, doProf ? d_prof : nullptr);
+        umma_fir_kernel<true><<<grid, kThreads, L.um_smem, s>>>(L.d_segs, L.d_tile_prefix, L.n_segs, L.n_tiles, L.um, L.um_stages, L.um_aligned ? 1 : 0, L.d_ovf, doProf ? d_prof : nullptr, dbg);
     else
-        umma_fir_kernel<false><<<grid, kThreads, L.um_smem, s>>>(L.d_segs, L.d_tile_prefix, L.n_segs, L.n_tiles, L.um, L.um_stages, L.um_aligned ? 1 : 0, L.d_ovf, doProf ? d_prof : nullptr);
+        umma_fir_kernel<false><<<grid, kThreads, L.um_smem, s>>>(L.d_segs, L.d_tile_prefix, L.n_segs, L.n_tiles, L.um, L.um_stages, L.um_aligned ? 1 : 0, L.d_ovf, doProf ? d_prof : nullptr, dbg);
     if (doProf) {
         std::vector<long long> h((size_t) 16 * grid);
         cudaStreamSynchronize(s); cudaMemcpy(h.data(), d_prof, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost);
         double a[16] = {0}; for (int i = 0; i < grid; ++i) for (int k = 0; k < 16; ++k) a[k] += (double) h[(size_t) i * 16 + k] / grid;
-        fprintf(stderr, "[umma prof] tiles/CTA %.1f stages/tile %d | loader total %.0f wait-free %.0f | tensor total %.0f wait-full %.0f wait-drained %.0f | epilogue total %.0f wait-done %.0f stores %.0f | tensor: fence %.0f cp-issue %.0f mma-issue %.0f\n",
-                (double) L.n_tiles / grid, L.um.blk[0].nStages, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10]);
+        fprintf(stderr, "[umma prof] tiles/CTA %.1f stages/tile %d | loader total %.0f wait-free %.0f | tensor total %.0f wait-full %.0f wait-drained %.0f | epilogue total %.0f wait-done %.0f stores %.0f | tensor: fence %.0f cp-issue %.0f mma-issue %.0f (issue blocks %.0f)\n",
+                (double) L.n_tiles / grid, L.um.blk[0].nStages, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[11]);
     }
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     ++*launches;
