@@ -132,19 +132,17 @@ struct UmmaBlockInfo {
     int nStages;       // 32-sample stages staged per tile: covers the last window sample + 3 (loader funnel shift)
     int nGroups;       // groups in this block
     int slot0;         // first slot of the block
-    int nEntries;      // MMA schedule entries (one per active (K step, group)); weight tile e is 1 KB at wOff + 1024*e
+    int nEntries;      // weight tiles of the block (one per (group, K step of its window)), NB*64 bytes each from wOff
     int wOff;          // byte offset into W
 };
 struct UmmaHost {
     int p = 0, q = 0, taps = 0, NB = 16, G = 0, GBL = 0, nGB = 0;
     int maxEntries = 0, maxNK = 0;
     UmmaBlockInfo blk[kUmmaMaxBlocks] = {};
-    // MMA schedule, one word per K step: the groups whose window contains the step are a contiguous range (windows move
-    // monotonically with the slot), the ones starting at this step are its top end, the ones finishing its bottom end.
-    // bits 0-3 first active group, 4-7 active count, 8-11 how many start here, 12-15 how many finish here,
-    // 16-19 how many (bottom end) are past their split step, 20-23 how many of those cross it at this step.
-    // (A per-entry operand list in kernel parameters was tried: its constant-cache misses made the issue 2x slower.)
-    uint32_t ksWord[kUmmaMaxBlocks][kUmmaMaxNK] = {};
+    // MMA schedule, per group of a block: first K step, number of K steps, index of its first weight tile (tiles are stored
+    // group-major so an issuing warp walks a group with constant operand increments).
+    uint8_t gStart[kUmmaMaxBlocks][kUmmaMaxGroups] = {}, gSteps[kUmmaMaxBlocks][kUmmaMaxGroups] = {};
+    uint16_t gTile[kUmmaMaxBlocks][kUmmaMaxGroups] = {};
     // Accumulation split (poolN > 0): the tensor core truncates the fp32 accumulator after every MMA, so x0*w0 of the K
     // steps after the window's centre (small partial sums) goes to a second accumulator D0B taken from a pool of poolN
     // 16-column slots (group g uses slot g % poolN); the epilogue adds D0A + D0B.  split = first K step of the second part.
@@ -155,7 +153,8 @@ struct UmmaDev {
     int p = 0, q = 0, taps = 0, NB = 16, G = 0, GBL = 0, nGB = 0;
     int maxEntries = 0, maxNK = 0;
     UmmaBlockInfo blk[kUmmaMaxBlocks] = {};
-    uint32_t ksWord[kUmmaMaxBlocks][kUmmaMaxNK] = {};
+    uint8_t gStart[kUmmaMaxBlocks][kUmmaMaxGroups] = {}, gSteps[kUmmaMaxBlocks][kUmmaMaxGroups] = {};
+    uint16_t gTile[kUmmaMaxBlocks][kUmmaMaxGroups] = {};
     int poolN = 0, split = 0;
     const uint8_t* W = nullptr;
 };

@@ -312,7 +312,7 @@ size_t umma_smem_bytes(int maxEntries, int NB, int stages) {
     const size_t w = (size_t) maxEntries * NB * 64;        // tile: 2 K chunks x 2*NB rows x 16 B
     const size_t ring = (size_t) stages * 8 * (128 * 16 + 32);
     const size_t epi = 128 * 20 * 4;
-    const size_t bars = (size_t) (2 * stages + 2 * kUmmaMaxGroups) * 8 + 16;
+    const size_t bars = (size_t) (2 * stages + 2 * kUmmaMaxGroups + 4) * 8 + 16;
     return w + ring + epi + bars + 128;                    // + alignment slack
 }
 
@@ -406,27 +406,24 @@ bool build_umma(int kind, const float* sinc_table, long long p, long long q, int
             }
         }
         int entries = 0;
-        for (int ks = 0; ks < BI.nK; ++ks) {
-            int cnt = 0, glFirst = -1, nFirst = 0, nLast = 0, nSecond = 0, nEnter = 0;
-            for (int g = g0; g < g1; ++g) {
-                const GroupGeom& gg = geo[(size_t) (g - g0)];
-                const int first = (int) ((gg.t0 - lo) / 16);
-                if (ks < first || ks >= first + gg.ksteps) continue;
-                const int j = ks - first;
-                if (glFirst < 0) glFirst = g - g0;
-                if (g - g0 != glFirst + cnt) return false;                     // active groups must be contiguous
-                if (j == 0) ++nFirst; else if (nFirst) return false;           // starters are the top of the range
-                if (j == gg.ksteps - 1) { if (nLast != cnt) return false; ++nLast; }   // finishers are the bottom
-                if (poolN > 0 && j >= split) { if (nSecond != cnt) return false; ++nSecond; if (j == split) ++nEnter; }
+        for (int g = g0; g < g1; ++g) {                                        // tiles group-major, K step minor
+            const GroupGeom& gg = geo[(size_t) (g - g0)];
+            const int gl = g - g0;
+            out->gStart[b][gl] = (uint8_t) ((gg.t0 - lo) / 16);
+            out->gSteps[b][gl] = (uint8_t) gg.ksteps;
+            out->gTile[b][gl] = (uint16_t) entries;
+            if (gl > 0 && (out->gStart[b][gl] < out->gStart[b][gl - 1] ||
+                           out->gStart[b][gl] + gg.ksteps < out->gStart[b][gl - 1] + out->gSteps[b][gl - 1])) return false;   // windows move monotonically
+            for (int j = 0; j < gg.ksteps; ++j) {
                 const size_t base = out->W.size();
                 out->W.resize(base + (size_t) tileBytes, 0);
                 for (int s = 0; s < NB; ++s) {
-                    const int sh = gshift[(size_t) (g - g0)][(size_t) s];
+                    const int sh = gshift[(size_t) gl][(size_t) s];
                     if (sh < 0) continue;
                     for (int kk = 0; kk < 16; ++kk) {
                         const int tap = 16 * j + kk - sh;
                         if (tap < 0 || tap >= taps) continue;
-                        const float wv = gw[(size_t) (g - g0)][(size_t) s * taps + (size_t) tap];
+                        const float wv = gw[(size_t) gl][(size_t) s * taps + (size_t) tap];
                         const uint16_t h0 = f32_to_f16_bits(wv);
                         const uint16_t h1 = f32_to_f16_bits((wv - f16_bits_to_f32(h0)) * 2048.0f);
                         const size_t off0 = base + (size_t) (kk / 8) * chunkBytes + (size_t) s * 16 + (size_t) (kk % 8) * 2;
@@ -434,10 +431,8 @@ bool build_umma(int kind, const float* sinc_table, long long p, long long q, int
                         std::memcpy(&out->W[off0], &h0, 2); std::memcpy(&out->W[off1], &h1, 2);
                     }
                 }
-                ++cnt; ++entries;
+                ++entries;
             }
-            if (cnt > 15 || nFirst > 15 || nLast > 15) return false;
-            out->ksWord[b][ks] = (uint32_t) ((glFirst < 0 ? 0 : glFirst) | (cnt << 4) | (nFirst << 8) | (nLast << 12) | (nSecond << 16) | (nEnter << 20));
         }
         BI.nEntries = entries;
         out->maxEntries = std::max(out->maxEntries, entries);

@@ -42,7 +42,9 @@ constexpr int kStageBytes = 8 * kChunk;          // one stage = 32 samples: chun
 constexpr int kEpiPitch = 20;                    // floats per row of the epilogue transpose buffer (16 + 4)
 constexpr int kACol = 448;                       // TMEM columns 448..511: ring of 4 K steps x (8 head + 8 tail)
 constexpr int kLoaderWarps = 8;
-constexpr int kThreads = (4 + 1 + kLoaderWarps) * 32;
+constexpr int kIssuers = 3;                      // MMA-issuing warps (groups are dealt round-robin)
+constexpr int kFirstLoader = 4 + 1 + kIssuers;   // warps 0-3 epilogue, 4 copy, 5..7 issue, 8..15 load
+constexpr int kThreads = (kFirstLoader + kLoaderWarps) * 32;
 constexpr int kSpin = 1 << 26;                   // bounded waits: a protocol bug must not hang the GPU
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
@@ -123,7 +125,7 @@ __device__ __forceinline__ float load_in(const Seg& S, long long l) {          /
 
 struct SmemMap {
     uint8_t* W; uint8_t* ring; float* epi;
-    uint64_t *full, *empty, *accFull, *accEmpty; uint32_t* tmemSlot;
+    uint64_t *full, *empty, *accFull, *accEmpty, *cpDone, *slotFree; uint32_t* tmemSlot;
 };
 __device__ __forceinline__ SmemMap carve(uint8_t* smem, int maxEntries, int NB, int stages) {
     SmemMap m;
@@ -134,7 +136,9 @@ __device__ __forceinline__ SmemMap carve(uint8_t* smem, int maxEntries, int NB, 
     m.empty = m.full + stages;
     m.accFull = m.empty + stages;
     m.accEmpty = m.accFull + kUmmaMaxGroups;
-    m.tmemSlot = reinterpret_cast<uint32_t*>(m.accEmpty + kUmmaMaxGroups);
+    m.cpDone = m.accEmpty + kUmmaMaxGroups;
+    m.slotFree = m.cpDone + 2;
+    m.tmemSlot = reinterpret_cast<uint32_t*>(m.slotFree + 2);
     return m;
 }
 
@@ -306,6 +310,7 @@ umma_fir_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix
         if (threadIdx.x == 0) {
             for (int s = 0; s < stages; ++s) { mbar_init(sm.full + s, kLoaderWarps); mbar_init(sm.empty + s, 1); }
             for (int g = 0; g < kUmmaMaxGroups; ++g) { mbar_init(sm.accFull + g, 1); mbar_init(sm.accEmpty + g, 4); }
+            for (int i = 0; i < 2; ++i) { mbar_init(sm.cpDone + i, 1); mbar_init(sm.slotFree + i, kIssuers); }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         if (warp == 4) {
@@ -326,35 +331,31 @@ umma_fir_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix
     #define PROF_END(acc, v) if (prof) acc += clock64() - v
     if (prof) pT0 = clock64();
 
-    if (warp >= 5) {
+    if (warp >= kFirstLoader) {
         // =========================================================== loaders
         LoaderArgs LA;
         LA.segs = segs; LA.tilePrefix = tilePrefix; LA.nSegs = nSegs; LA.nTiles = nTiles; LA.nGB = P.nGB; LA.p = p; LA.q = q;
         LA.U0 = BI.U0; LA.nStages = nStages; LA.stages = stages; LA.myTiles = myTiles;
         LA.ring = sm.ring; LA.full = sm.full; LA.empty = sm.empty; LA.ovf = ovf; LA.prof = prof;
-        if (alignedAll) loader_role<true>(LA, warp - 5, lane);
-        else loader_role<false>(LA, warp - 5, lane);
+        if (alignedAll) loader_role<true>(LA, warp - kFirstLoader, lane);
+        else loader_role<false>(LA, warp - kFirstLoader, lane);
     } else if (warp == 4) {
-        // =========================================================== tensor pipe
-        // Warp-uniform control flow in the uniform datapath; one elected lane issues.  tcgen05 operands are uniform
-        // registers, and what bounds this warp is the handful of uniform-datapath instructions per MMA, not the tensor pipe
-        // (measured: ~45 clk per issued MMA against 8 clk of pipe time), hence the straight-line 4-entry blocks below.
+        // =========================================================== copy warp
+        // Stage gs (32 samples of all 128 rows, head + tail) goes from shared memory into TMEM operand slot gs & 1 with four
+        // tcgen05.cp.  A single warp issuing copies AND MMAs was bound by its own instruction latency (the uniform datapath
+        // runs ~4 clk per instruction: ~300 clk per K step before the first MMA), so the MMAs are issued by other warps:
+        // cpDone[slot] tells them the operand is in TMEM, slotFree[slot] tells this warp they have finished reading it.
         const uint32_t el = elect_one();
-        const uint32_t idescN = make_idesc(kRows, NB), idesc2N = make_idesc(kRows, 2 * NB);
-        const uint32_t nb = (uint32_t) NB, poolCol = (uint32_t) (P.GBL * 2 * NB), poolMask = (uint32_t) (P.poolN > 0 ? P.poolN - 1 : 0);
-        const uint64_t wDesc0 = make_desc(smem_u32(sm.W), 32 * NB, 128);       // weight tile e: + 4*NB*e (16-byte units); w1 rows at + NB
         const uint64_t aDesc0 = make_desc(smem_u32(sm.ring), kChunk, 128);
-        // The copies of stage g+1 are issued BEFORE the MMAs of stage g: an MMA then never waits on a copy that was issued
-        // just ahead of it (the pipe executes in order, and a dependent MMA stalls the issuing thread for the copy's whole
-        // latency).  TMEM operand slots alternate with the global stage count, so consecutive stages never share a slot.
-        int sIdx = 0; uint32_t sPh = 0;
         const int totalStages = myTiles * nStages;
-        auto stage_in = [&](int gs) {                          // wait for stage gs in shared memory, copy it into TMEM slot gs & 1
+        int sIdx = 0; uint32_t sPh = 0;
+        for (int gs = 0; gs < totalStages; ++gs) {
             { PROF_BEGIN(w); mbar_wait(sm.full + sIdx, sPh); PROF_END(pW0, w); }
             PROF_BEGIN(wf);
             fence_async_smem();                                // generic-proxy stores of the loaders -> async-proxy reads of tcgen05.cp
-            tc_fence_after();
             PROF_END(pF, wf);
+            if (gs >= 2) { PROF_BEGIN(w); mbar_wait(sm.slotFree + (gs & 1), (uint32_t) (((gs >> 1) - 1) & 1)); PROF_END(pW1, w); }
+            tc_fence_after();
             PROF_BEGIN(wc);
             if (el) {
                 const uint64_t ad = aDesc0 + (uint64_t) ((sIdx * kStageBytes) >> 4);
@@ -366,73 +367,72 @@ umma_fir_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix
                 umma_cp(slot0 + 24, ad + ((6 * kChunk) >> 4));                  //               tail
                 }
                 umma_commit(sm.empty + sIdx);                  // the stage is free once the copies have read it
+                umma_commit(sm.cpDone + (gs & 1));
             }
             __syncwarp();
             PROF_END(pC, wc);
             if (++sIdx == stages) { sIdx = 0; sPh ^= 1; }
-        };
-        if (totalStages > 0) stage_in(0);
+        }
+        if (prof && lane == 0) { prof[blockIdx.x * 16 + 8] = pF; prof[blockIdx.x * 16 + 9] = pC; }
+        if (prof && lane == 0) { prof[blockIdx.x * 16 + 2] = clock64() - pT0; prof[blockIdx.x * 16 + 3] = pW0; prof[blockIdx.x * 16 + 4] = pW1; }
+    } else if (warp > 4) {
+        // =========================================================== MMA issuers
+        // Warp w owns the groups gl = w, w + kIssuers, ...: per group the operands advance by constants from K step to K step
+        // (weight tiles are stored group-major), so the issue loop is a few uniform adds around three tcgen05.mma.
+        const int w = warp - 5;
+        const uint32_t el = elect_one();
+        const uint32_t nb = (uint32_t) NB;
+        const uint32_t idescN = make_idesc(kRows, NB), idesc2N = make_idesc(kRows, 2 * NB);
+        const uint32_t poolCol = (uint32_t) (P.GBL * 2 * NB), poolMask = (uint32_t) (P.poolN > 0 ? P.poolN - 1 : 0);
+        const uint64_t wDesc0 = make_desc(smem_u32(sm.W), 32 * NB, 128);       // weight tile i: + 4*NB*i (16-byte units); w1 rows at + NB
+        const int split = P.poolN > 0 ? P.split : 0x7fffffff;
         int gs = 0;
         for (int t = 0; t < myTiles; ++t) {
-            uint32_t e = 0;
             for (int st = 0; st < nStages; ++st, ++gs) {
-                if (gs + 1 < totalStages) stage_in(gs + 1);
-                PROF_BEGIN(wm);
-                #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int ks = 2 * st + h;
-                    if (ks >= BI.nK) break;
-                    const uint32_t word = P.ksWord[gb][ks];
-                    const uint32_t gl0 = word & 15u, cnt = (word >> 4) & 15u, nFirst = (word >> 8) & 15u, nLast = (word >> 12) & 15u;
-                    const uint32_t nSecond = (word >> 16) & 15u, nEnter = (word >> 20) & 15u;
-                    const uint32_t aHi = tmem + kACol + (uint32_t) ((gs & 1) * 32 + h * 16);
-                    // waits first (rare: once per group and tile), so that the issue block below is straight-line code
-                    if (nFirst | nEnter) {
-                        PROF_BEGIN(w);
-                        for (uint32_t c = cnt - nFirst; c < cnt; ++c)          // groups starting here: accumulators drained?
-                            mbar_wait(sm.accEmpty + gl0 + c, (t & 1) ^ 1);
-                        for (uint32_t c = nSecond - nEnter; c < nSecond; ++c) { // groups crossing their split: the pool slot's previous user read?
-                            const uint32_t gl = gl0 + c;
-                            if (gl > poolMask) mbar_wait(sm.accEmpty + (gl - poolMask - 1), t & 1);      // same tile
-                            else {                                                                       // previous tile
-                                uint32_t lu = gl; while (lu + poolMask + 1 < (uint32_t) BI.nGroups) lu += poolMask + 1;
+                { PROF_BEGIN(wq); mbar_wait(sm.cpDone + (gs & 1), (uint32_t) ((gs >> 1) & 1)); PROF_END(pW0, wq); }
+                tc_fence_after();
+                PROF_BEGIN(wi);
+                for (int gl = w; gl < BI.nGroups; gl += kIssuers) {
+                    const int g0 = P.gStart[gb][gl], gn = P.gSteps[gb][gl];
+                    #pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int j = 2 * st + h - g0;                         // K step inside the group's window
+                        if (j < 0 || j >= gn) continue;
+                        if (j == 0) {                                           // accumulators drained by the epilogue (previous tile)?
+                            PROF_BEGIN(wd); mbar_wait(sm.accEmpty + gl, (t & 1) ^ 1); PROF_END(pW1, wd);
+                            tc_fence_after();
+                        } else if (j == split) {                                // the pool slot's previous user read?
+                            PROF_BEGIN(wd);
+                            if ((uint32_t) gl > poolMask) mbar_wait(sm.accEmpty + (gl - (int) poolMask - 1), t & 1);       // same tile
+                            else {                                                                                  // previous tile
+                                int lu = gl; while (lu + (int) poolMask + 1 < BI.nGroups) lu += (int) poolMask + 1;
                                 mbar_wait(sm.accEmpty + lu, (t & 1) ^ 1);
                             }
+                            PROF_END(pW1, wd);
+                            tc_fence_after();
                         }
-                        PROF_END(pW1, w);
-                        tc_fence_after();
-                    }
-                    PROF_BEGIN(wi);
-                    if (el) {
-                        // rolled loop, strength-reduced operands: the cost of this block is its uniform-datapath instruction
-                        // count (~4 clk each), so it must be proportional to the number of entries
-                        uint32_t d1 = tmem + (2 * gl0 + 1) * nb;
-                        uint64_t bd = wDesc0 + (uint64_t) (e * 4u * nb);
-                        uint64_t* fullBar = sm.accFull + gl0;
-                        const uint32_t cFirst = cnt - nFirst, cEnter = nSecond - nEnter;
-                        #pragma unroll 1
-                        for (uint32_t c = 0; c < cnt; ++c, d1 += 2 * nb, bd += 4 * nb, ++fullBar) {
-                            const uint32_t accD1 = c < cFirst ? 1u : 0u;
-                            if (dbg & 1) { if (c < nLast) umma_commit(fullBar); continue; }
-                            if (MERGED || c >= nSecond) {      // D0 and D1 adjacent: [D0 | D1] (+)= x0 * [w0 | w1] as one N = 2*NB MMA
-                                umma_ts(d1 - nb, aHi, bd, idesc2N, accD1);
+                        if (el && !(dbg & 1)) {
+                            const uint32_t aHi = tmem + kACol + (uint32_t) ((gs & 1) * 32 + h * 16);
+                            const uint32_t d1 = tmem + (uint32_t) (2 * gl + 1) * nb;
+                            const uint64_t bd = wDesc0 + (uint64_t) ((uint32_t) (P.gTile[gb][gl] + j) * 4u * nb);
+                            const uint32_t acc = j > 0 ? 1u : 0u;
+                            if (MERGED || j < split) {         // D0 and D1 adjacent: [D0 | D1] (+)= x0 * [w0 | w1] as one N = 2*NB MMA
+                                umma_ts(d1 - nb, aHi, bd, idesc2N, acc);
                             } else {                           // past the split: D0 lives in the pool
-                                umma_ts(tmem + poolCol + ((gl0 + c) & poolMask) * nb, aHi, bd, idescN, c >= cEnter ? 0u : 1u);   // D0B (+)= x0 * w0
-                                umma_ts(d1, aHi, bd + nb, idescN, 1u);                                                        // D1    += x0 * w1
+                                umma_ts(tmem + poolCol + ((uint32_t) gl & poolMask) * nb, aHi, bd, idescN, j > split ? 1u : 0u);   // D0B (+)= x0 * w0
+                                umma_ts(d1, aHi, bd + nb, idescN, 1u);                                                          // D1    += x0 * w1
                             }
-                            umma_ts(d1, aHi + 8, bd, idescN, 1u);                                                             // D1    += x1 * w0
-                            if (c < nLast) umma_commit(fullBar);
+                            umma_ts(d1, aHi + 8, bd, idescN, 1u);                                                               // D1    += x1 * w0
                         }
+                        if (el && j == gn - 1) umma_commit(sm.accFull + gl);
                     }
-                    __syncwarp();
-                    PROF_END(pI, wi);
-                    e += cnt;
                 }
-                PROF_END(pM, wm);
+                if (el) umma_commit(sm.slotFree + (gs & 1));   // arrives once this warp's MMAs on the slot have completed
+                __syncwarp();
+                PROF_END(pI, wi);
             }
         }
-        if (prof && lane == 0) { prof[blockIdx.x * 16 + 8] = pF; prof[blockIdx.x * 16 + 9] = pC; prof[blockIdx.x * 16 + 10] = pM; prof[blockIdx.x * 16 + 11] = pI; }
-        if (prof && lane == 0) { prof[blockIdx.x * 16 + 2] = clock64() - pT0; prof[blockIdx.x * 16 + 3] = pW0; prof[blockIdx.x * 16 + 4] = pW1; }
+        if (prof && w == 0 && lane == 0) { prof[blockIdx.x * 16 + 10] = pW0; prof[blockIdx.x * 16 + 11] = pI; prof[blockIdx.x * 16 + 12] = pW1; }
     } else {
         // =========================================================== epilogue
         // Thread = TMEM lane = period row.  Per group and 16-slot chunk: read D0 (+ its pool half) and D1, combine, transpose
@@ -566,8 +566,8 @@ cudaError_t launch_umma(const ResampleLaunch& L, cudaStream_t s, long long* laun
         std::vector<long long> h((size_t) 16 * grid);
         cudaStreamSynchronize(s); cudaMemcpy(h.data(), d_prof, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost);
         double a[16] = {0}; for (int i = 0; i < grid; ++i) for (int k = 0; k < 16; ++k) a[k] += (double) h[(size_t) i * 16 + k] / grid;
-        fprintf(stderr, "[umma prof] tiles/CTA %.1f stages/tile %d | loader total %.0f wait-free %.0f | tensor total %.0f wait-full %.0f wait-drained %.0f | epilogue total %.0f wait-done %.0f stores %.0f | tensor: fence %.0f cp-issue %.0f mma-issue %.0f (issue blocks %.0f)\n",
-                (double) L.n_tiles / grid, L.um.blk[0].nStages, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[11]);
+        fprintf(stderr, "[umma prof] tiles/CTA %.1f stages/tile %d | loader total %.0f wait-free %.0f | copy total %.0f wait-full %.0f wait-slot %.0f | epilogue total %.0f wait-done %.0f stores %.0f | copy: fence %.0f cp-issue %.0f | issuer0: wait-cp %.0f issue %.0f (wait-drained %.0f)\n",
+                (double) L.n_tiles / grid, L.um.blk[0].nStages, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[11], a[12]);
     }
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     ++*launches;
