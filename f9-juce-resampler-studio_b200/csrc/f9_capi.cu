@@ -118,6 +118,10 @@ void f9_context_destroy(f9_context* ctx) {
     for (auto& kv : ctx->umma_cache) cudaFree((void*) kv.second.W);
     if (ctx->d_ovf) cudaFree(ctx->d_ovf);
     if (ctx->d_sinc_table) cudaFree(ctx->d_sinc_table);
+    if (ctx->cur_slot) ctx->swap_slot();
+    if (ctx->alt_stream) { cudaStreamSynchronize(ctx->alt_stream); cudaStreamDestroy(ctx->alt_stream); }
+    if (ctx->parked.d_arena) cudaFree(ctx->parked.d_arena);
+    if (ctx->parked.h_arena) cudaFreeHost(ctx->parked.h_arena);
     if (ctx->d_arena) cudaFree(ctx->d_arena);
     if (ctx->h_arena) cudaFreeHost(ctx->h_arena);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);

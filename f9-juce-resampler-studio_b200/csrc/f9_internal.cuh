@@ -8,6 +8,7 @@
 #include <map>
 #include <string>
 #include <tuple>
+#include <utility>
 #include <vector>
 
 #include "f9dsp.h"
@@ -160,6 +161,7 @@ struct UmmaDev {
 };
 bool build_umma(int kind, const float* sinc_table, long long p, long long q, int NB, int GBL, UmmaHost* out);
 size_t umma_smem_bytes(int maxEntries, int NB, int stages);
+void umma_choose_plan(int taps, long long p, long long q, long long* m_out, int* NB_out, int* GBL_out);
 double umma_cost_per_output(int taps, long long p, long long q, int NB, int GBL, size_t* smem2);   // model used to pick the plan
 
 struct ResampleLaunch {
@@ -225,7 +227,7 @@ struct f9_context {
         return std::tie(kind, p, q, NB, GBL, epoch) < std::tie(o.kind, o.p, o.q, o.NB, o.GBL, o.epoch); } };
     std::map<UmmaKey, f9::UmmaDev> umma_cache;
     int   get_umma(int kind, long long p, long long q, int NB, int GBL, f9::UmmaDev* out);
-    unsigned* d_ovf = nullptr;          // see ResampleLaunch::d_ovf
+    unsigned* d_ovf = nullptr;          // see ResampleLaunch::d_ovf (two flags: one per pipeline slot)
     // Choose kernel + tables for (kind, ratio, pos0); fills everything in L except the segment table.
     int   prepare_resample(int kind, double ratio, double pos0, bool allow_rational, f9::ResampleLaunch* L);
 
@@ -234,6 +236,17 @@ struct f9_context {
         err = std::string(what) + ": " + cudaGetErrorString(e); return F9_ERR_CUDA;
     }
     bool  quiescent = true;             // nothing enqueued by this context can still touch the arenas
+    // f9_process_batch pipelines chunks over two slots (arena + stream each) so that the upload of chunk k+1 overlaps the
+    // kernels and the download of chunk k; swap_slot() exchanges the current arena / stream with the parked one.
+    struct ParkedSlot { char* d_arena = nullptr; size_t d_cap = 0, d_used = 0; char* h_arena = nullptr; size_t h_cap = 0, h_used = 0;
+                        cudaStream_t stream = nullptr; bool quiescent = true; } parked;
+    cudaStream_t alt_stream = nullptr;  // owned; the parked slot's stream
+    int   cur_slot = 0;
+    void  swap_slot() {
+        std::swap(d_arena, parked.d_arena); std::swap(d_cap, parked.d_cap); std::swap(d_used, parked.d_used);
+        std::swap(h_arena, parked.h_arena); std::swap(h_cap, parked.h_cap); std::swap(h_used, parked.h_used);
+        std::swap(stream, parked.stream); std::swap(quiescent, parked.quiescent); cur_slot ^= 1;
+    }
     void  arena_reset() { d_used = 0; h_used = 0; }
     int   arena_reserve(size_t d_bytes, size_t h_bytes, bool async_call = false);
     void* d_alloc(size_t bytes) { size_t o = (d_used + 255) & ~size_t(255); d_used = o + bytes; return d_arena + o; }

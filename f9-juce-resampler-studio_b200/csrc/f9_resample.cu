@@ -525,35 +525,16 @@ int f9_context::prepare_resample(int kind, double ratio, double pos0, bool allow
         L->rational = true;
         L->sm_count = sm_count;
         if (getenv("F9_NO_UMMA") == nullptr && interp_memory(kind) >= 2) {
-            // Tensor-core path: scale p/q by m so that a period has 64..224 slots; choose the scaling, the group width (16 or
-            // 32 slots) and the block size with the lowest modelled cost whose tables fit shared memory with two staging buffers.
-            const int taps = interp_memory(kind);
-            double best = 1e30; long long bm = 0; int bGBL = 0, bNB = 0;
-            for (long long m = 1; m * q <= 16LL * kUmmaMaxGroups * kUmmaMaxBlocks && m * p + taps + 48 <= 16 * kUmmaMaxNK; ++m) {
-                const long long ps = p * m, qs = q * m;
-                if (qs < 48 && (m + 1) * q <= 224) continue;                       // too few slots per period: keep scaling
-                for (int NB : {32, 16}) {
-                    if (getenv("F9_UMMA_NB") && atoi(getenv("F9_UMMA_NB")) != NB) continue;
-                    const int G = (int) ((qs + NB - 1) / NB), maxG = std::min(kUmmaMaxGroups, 448 / (2 * NB));
-                    for (int nGB = (G + maxG - 1) / maxG; nGB <= kUmmaMaxBlocks && nGB <= G; ++nGB) {
-                        const int GBL = (G + nGB - 1) / nGB;
-                        size_t smem2 = 0;
-                        const double c = umma_cost_per_output(taps, ps, qs, NB, GBL, &smem2);
-                        if (smem2 > 227 * 1024) continue;
-                        if (c < best) { best = c; bm = m; bGBL = GBL; bNB = NB; }
-                        break;                                                      // more blocks only cost more
-                    }
-                }
-                if (qs >= 224) break;
-            }
+            long long bm = 0; int bGBL = 0, bNB = 0;
+            umma_choose_plan(interp_memory(kind), p, q, &bm, &bNB, &bGBL);
             if (bm > 0) {
-                if (!d_ovf) F9_TRY_CUDA(this, cudaMalloc((void**) &d_ovf, sizeof(unsigned)));
+                if (!d_ovf) F9_TRY_CUDA(this, cudaMalloc((void**) &d_ovf, 2 * sizeof(unsigned)));
                 rc = get_umma(kind, p * bm, q * bm, bNB, bGBL, &L->um);
                 if (rc == F9_OK) {
                     int stages = 2;
                     while (stages < 4 && umma_smem_bytes(L->um.maxEntries, L->um.NB, stages + 1) <= 227 * 1024) ++stages;
                     L->um_stages = stages; L->um_smem = umma_smem_bytes(L->um.maxEntries, L->um.NB, stages);
-                    L->d_ovf = d_ovf; L->umma = true;
+                    L->d_ovf = d_ovf + cur_slot; L->umma = true;
                     return F9_OK;
                 }
                 if (rc != F9_ERR_INVALID) return rc;                                // tables this kernel cannot express: CUDA-core paths

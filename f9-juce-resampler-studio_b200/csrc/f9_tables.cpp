@@ -7,6 +7,7 @@
 //  algorithm as recorded in SURVEY.md Appendix A.]
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "f9_internal.cuh"
@@ -341,6 +342,31 @@ double umma_cost_per_output(int taps, long long p, long long q, int NB, int GBL,
     return std::max(std::max(tensor, issue), lsu) / (128.0 * (double) q);
 }
 
+// Tensor-core plan for ratio p/q: scale p/q by m so that a period has 64..224 slots; choose the scaling, the group width
+// (16 or 32 slots) and the block size with the lowest modelled cost whose tables fit shared memory with two staging buffers.
+// *m = 0 when no plan fits.
+void umma_choose_plan(int taps, long long p, long long q, long long* m_out, int* NB_out, int* GBL_out) {
+    double best = 1e30; *m_out = 0; *NB_out = 0; *GBL_out = 0;
+    for (long long m = 1; m * q <= 16LL * kUmmaMaxGroups * kUmmaMaxBlocks && m * p + taps + 48 <= 16 * kUmmaMaxNK; ++m) {
+        const long long ps = p * m, qs = q * m;
+        if (qs < 48 && (m + 1) * q <= 224) continue;                           // too few slots per period: keep scaling
+        for (int NB : {32, 16}) {
+            if (getenv("F9_UMMA_NB") && atoi(getenv("F9_UMMA_NB")) != NB) continue;
+            const int G = (int) ((qs + NB - 1) / NB), maxG = std::min(kUmmaMaxGroups, 448 / (2 * NB));
+            for (int nGB = (G + maxG - 1) / maxG; nGB <= kUmmaMaxBlocks && nGB <= G; ++nGB) {
+                const int GBL = (G + nGB - 1) / nGB;
+                size_t smem2 = 0;
+                double c = umma_cost_per_output(taps, ps, qs, NB, GBL, &smem2);
+                if (smem2 > 227 * 1024) continue;
+                if (ps & 3) c *= 1.25;                                          // rows not 16-byte aligned: the loader funnels
+                if (c < 0.97 * best) { best = c; *m_out = m; *GBL_out = GBL; *NB_out = NB; }    // ties go to the smaller plan
+                break;                                                          // more blocks only cost more
+            }
+        }
+        if (qs >= 224) break;
+    }
+}
+
 bool build_umma(int kind, const float* sinc_table, long long p, long long q, int NB, int GBL, UmmaHost* out) {
     const int taps = interp_memory(kind);
     if (NB != 16 && NB != 32) return false;
@@ -442,3 +468,57 @@ bool build_umma(int kind, const float* sinc_table, long long p, long long q, int
 }
 
 }  // namespace f9
+
+// ---- diagnostics (host only) -------------------------------------------------------------------------------
+// Builds the tensor-core plan of ratio p/q and checks its tables against the fp32 polyphase weights: every (slot, tap)
+// appears in exactly one weight tile position, everything else is zero, and head + tail/2048 reproduces the weight.
+extern "C" double f9_umma_selfcheck(int kind, long long p, long long q, int* info /* 8 ints or NULL */) {
+    using namespace f9;
+    const int taps = interp_memory(kind);
+    if (taps == 0 || p <= 0 || q <= 0) return -1.0;
+    std::vector<float> table((size_t) kSincTableSize + 1, 0.0f);
+    make_default_sinc_table(table.data());
+    long long m = 0; int NB = 0, GBL = 0;
+    umma_choose_plan(taps, p, q, &m, &NB, &GBL);
+    if (m == 0) return -2.0;
+    UmmaHost H;
+    if (!build_umma(kind, table.data(), p * m, q * m, NB, GBL, &H)) return -3.0;
+    const long long ps = p * m, qs = q * m;
+    double maxErr = 0.0;
+    std::vector<float> w((size_t) taps);
+    for (int b = 0; b < H.nGB; ++b) {
+        const UmmaBlockInfo& BI = H.blk[b];
+        for (int gl = 0; gl < BI.nGroups; ++gl) {
+            const int g = b * H.GBL + gl;
+            for (int s = 0; s < NB; ++s) {
+                const long long k = (long long) NB * g + s;
+                std::vector<double> rec((size_t) taps, 0.0); std::vector<int> seen((size_t) taps, 0);
+                const long long tap0 = k < qs ? (k * ps) / qs - (taps - 1) : 0;             // input offset of tap 0 (period relative)
+                for (int j = 0; j < H.gSteps[b][gl]; ++j) {
+                    const uint8_t* tile = H.W.data() + BI.wOff + (size_t) (H.gTile[b][gl] + j) * NB * 64;
+                    for (int kk = 0; kk < 16; ++kk) {
+                        uint16_t h0, h1;
+                        std::memcpy(&h0, tile + (size_t) (kk / 8) * NB * 32 + (size_t) s * 16 + (size_t) (kk % 8) * 2, 2);
+                        std::memcpy(&h1, tile + (size_t) (kk / 8) * NB * 32 + (size_t) (NB + s) * 16 + (size_t) (kk % 8) * 2, 2);
+                        const double v = (double) f16_bits_to_f32(h0) + (double) f16_bits_to_f32(h1) / 2048.0;
+                        const long long in = BI.U0 + 16LL * (H.gStart[b][gl] + j) + kk;     // input offset this K index reads
+                        const long long tap = in - tap0;
+                        if (k < qs && tap >= 0 && tap < taps) { rec[(size_t) tap] += v; ++seen[(size_t) tap]; }
+                        else if (v != 0.0) return -4.0;                                     // weight outside the slot's window
+                    }
+                }
+                if (k >= qs) continue;
+                tap_weights(kind, table.data(), (float) ((double) ((k * ps) % qs) / (double) qs), w.data());
+                for (int t = 0; t < taps; ++t) {
+                    if (seen[(size_t) t] != 1) return -5.0;                                 // a tap is missing or duplicated
+                    maxErr = std::max(maxErr, std::fabs(rec[(size_t) t] - (double) w[(size_t) t]));
+                }
+            }
+        }
+    }
+    if (info) {
+        info[0] = (int) m; info[1] = NB; info[2] = H.G; info[3] = H.GBL; info[4] = H.nGB; info[5] = H.poolN; info[6] = H.split;
+        info[7] = (int) umma_smem_bytes(H.maxEntries, NB, 2);
+    }
+    return maxErr;
+}

@@ -12,8 +12,8 @@
 //     outside: every 16-sample step of X is staged once and used by all groups whose window contains it.
 //   * precision: x = x0 + x1/2048, w = w0 + w1/2048 with fp16 parts (x1, w1 stored pre-multiplied by 2048 so they
 //     stay normal numbers).  D0 += x0*w0 and D1 += x0*w1 + x1*w0 accumulate in fp32 in TMEM; the dropped x1*w1 term
-//     is < 2^-24 relative.  out = D0 + D1/2048.  Samples with |x| >= 2^15 (or NaN/Inf) do not fit the split: the
-//     loader raises a flag and umma_redo_kernel recomputes the launch in fp32.
+//     is < 2^-24 relative.  out = D0 + D1/2048.  Samples are pre-scaled by 2^7 (see split_store); |x| >= 256 (or NaN/Inf)
+//     does not fit the split: the loader raises a flag and umma_redo_kernel recomputes the launch in fp32.
 //
 // Warp roles (416 threads, one CTA per SM, persistent over tiles):
 //   warps 0-3   epilogue: tcgen05.ld the finished accumulators (lane = period), combine D0/D1, transpose through
@@ -142,8 +142,12 @@ __device__ __forceinline__ SmemMap carve(uint8_t* smem, int maxEntries, int NB, 
     return m;
 }
 
-// fp16 head / scaled fp16 tail of four samples, written to the operand tile (8 bytes each)
-__device__ __forceinline__ void split_store(const float4 xv, uint8_t* dst, __half2& hmax) {
+// fp16 head / scaled fp16 tail of four samples, written to the operand tile (8 bytes each).  Samples are pre-scaled by
+// kPreScale = 2^7 (exact) so that the fp16 head stays a normal number down to |x| = 2^-21 (-126 dBFS): without it signals
+// below -84 dBFS would lose head bits to fp16 subnormals.  The price is the range: |x| >= 256 (+48 dBFS) takes the fp32 redo.
+constexpr float kPreScale = 128.0f;
+__device__ __forceinline__ void split_store(float4 xv, uint8_t* dst, __half2& hmax) {
+    xv.x *= kPreScale; xv.y *= kPreScale; xv.z *= kPreScale; xv.w *= kPreScale;
     const __half2 h01 = __floats2half2_rn(xv.x, xv.y), h23 = __floats2half2_rn(xv.z, xv.w);
     hmax = __hmax2_nan(hmax, __hmax2_nan(__habs2(h01), __habs2(h23)));
     const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
@@ -284,8 +288,13 @@ __device__ __forceinline__ void loader_role(const LoaderArgs& A, int lw, int lan
         process(b3, b0); ++done;
     }
     const float2 hm = __half22float2(hmax);
-    if (!(hm.x < 32768.0f) || !(hm.y < 32768.0f)) atomicOr(A.ovf, 1u);         // |x| >= 32768, Inf or NaN in this CTA's input
+    if (!(hm.x < 32768.0f) || !(hm.y < 32768.0f)) atomicOr(A.ovf, 1u);         // |128 x| >= 32768, Inf or NaN in this CTA's input
     if (A.prof && lw == 0 && lane == 0) { A.prof[blockIdx.x * 16 + 0] = clock64() - pT0; A.prof[blockIdx.x * 16 + 1] = pW0; }
+}
+
+// out = (D0A + D0B + D1 / 2048) / kPreScale: the scalings are powers of two, the only roundings are the two additions
+__device__ __forceinline__ float combine(uint32_t d0a, uint32_t d0b, uint32_t d1) {
+    return fmaf(__uint_as_float(d1), 1.0f / (2048.0f * kPreScale), (__uint_as_float(d0a) + __uint_as_float(d0b)) * (1.0f / kPreScale));
 }
 
 template <bool MERGED>
@@ -476,10 +485,8 @@ umma_fir_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix
                     float4* dst = reinterpret_cast<float4*>(sm.epi + row0 * kEpiPitch);
                     #pragma unroll
                     for (int c = 0; c < 4; ++c)
-                        dst[c] = make_float4(fmaf(__uint_as_float(v1[4 * c]), 1.0f / 2048.0f, __uint_as_float(v0[4 * c]) + __uint_as_float(vb[4 * c])),
-                                             fmaf(__uint_as_float(v1[4 * c + 1]), 1.0f / 2048.0f, __uint_as_float(v0[4 * c + 1]) + __uint_as_float(vb[4 * c + 1])),
-                                             fmaf(__uint_as_float(v1[4 * c + 2]), 1.0f / 2048.0f, __uint_as_float(v0[4 * c + 2]) + __uint_as_float(vb[4 * c + 2])),
-                                             fmaf(__uint_as_float(v1[4 * c + 3]), 1.0f / 2048.0f, __uint_as_float(v0[4 * c + 3]) + __uint_as_float(vb[4 * c + 3])));
+                        dst[c] = make_float4(combine(v0[4 * c], vb[4 * c], v1[4 * c]), combine(v0[4 * c + 1], vb[4 * c + 1], v1[4 * c + 1]),
+                                             combine(v0[4 * c + 2], vb[4 * c + 2], v1[4 * c + 2]), combine(v0[4 * c + 3], vb[4 * c + 3], v1[4 * c + 3]));
                     __syncwarp();
                     PROF_BEGIN(wst);
                     const int col = gl * NB + h * 16 + (lane & 15);           // slot inside the block

@@ -81,6 +81,12 @@ F9_API int  f9_host_alloc(f9_context* ctx, void** out, size_t bytes);
 F9_API int  f9_host_free(f9_context* ctx, void* p);
 F9_API int  f9_version(void);                 /* major*100 + minor */
 F9_API int  f9_device_count(void);            /* 0 when there is no usable device; never fails */
+/* Host-only diagnostic of the tensor-core FIR tables (no GPU needed): plans the rational ratio p/q for `kind` and checks
+ * that every (output slot, tap) sits in exactly one position of the fp16 weight tiles and that head + tail/2048
+ * reproduces the fp32 polyphase weight.  Returns the largest reconstruction error, or < 0: -1 bad arguments, -2 no
+ * tensor-core plan fits (the CUDA-core kernels serve the ratio), -3..-5 table defects.  info (8 ints, may be NULL):
+ * scale m, slots per group, groups, groups per block, blocks, accumulator pool slots, split step, shared-memory bytes. */
+F9_API double f9_umma_selfcheck(int kind, long long p, long long q, int* info);
 
 /* ============================ B. settings math =============================== */
 /* Host scalars; mirror ProcessingSettings (Source/AppState.h:183-259). */

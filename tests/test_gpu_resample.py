@@ -255,3 +255,95 @@ def test_full_size_properties_config1(ctx, O, f9):
             ref, _ = O.resample_channel(0, fs_in / fs_out, a[1][shift_in:], cnt + 320)
             ref = ref[320:]
         assert np.max(np.abs(ref - ya[1][n0:n0 + cnt])) <= TOL, n0
+
+
+# ---------------------------------------------------------------- tensor-core FIR (f9_umma.cu): its own edge cases
+def _plan_resample(ctx, f9, x_dev, n_in, kind, fs_in, fs_out, offset=0):
+    """Device-pointer plan API on a channel that starts `offset` floats into an aligned allocation."""
+    torch = pytest.importorskip("torch")
+    import ctypes as C
+    n_out = f9.resampled_length(n_in, fs_in, fs_out)
+    out = torch.zeros(n_out, dtype=torch.float32, device="cuda")
+    seg = (f9.ResampleSeg * 1)(f9.ResampleSeg(x_dev.data_ptr() + 4 * offset, 0, n_in, out.data_ptr(), 0, n_out))
+    plan = C.c_void_p(None)
+    torch.cuda.synchronize()
+    assert f9.lib().f9_resample_plan_create(ctx.handle, kind, fs_in / fs_out, seg, 1, C.byref(plan)) == 0
+    assert f9.lib().f9_resample_plan_run(plan) == 0
+    ctx.synchronize()
+    f9.lib().f9_plan_destroy(plan)
+    return out.cpu().numpy()
+
+
+@pytest.mark.parametrize("offset", [0, 1, 2, 3])
+@pytest.mark.parametrize("fs", [(96000, 44100), (44100, 48000)])
+def test_umma_any_input_alignment(ctx, O, f9, offset, fs):
+    """The loader has an aligned fast path and a funnel-shift path: every misalignment of the channel start (which is
+    what trimLatency's pointer offset produces) must give the same samples."""
+    torch = pytest.importorskip("torch")
+    n_in = 70001
+    x = signal(n_in + 8, 31)
+    d = torch.from_numpy(x).cuda()
+    for kind in (0, 1):
+        got = _plan_resample(ctx, f9, d, n_in, kind, fs[0], fs[1], offset)
+        ref, _ = O.resample_channel(kind, fs[0] / fs[1], x[offset:offset + n_in], got.shape[0])
+        assert np.max(np.abs(got - ref)) <= TOL, (offset, fs, kind)
+
+
+def test_umma_headroom(ctx, O):
+    """Float audio may exceed full scale: up to |x| < 256 (+48 dBFS) stays on the tensor-core path, error relative to the peak."""
+    x = (signal(40000, 37) * 400.0)[None, :]                 # peaks at 200
+    y = ctx.resample(x, 96000, 44100, 0)
+    ref, _ = O.resample_channel(0, 96000 / 44100, x[0], y.shape[1])
+    assert np.max(np.abs(y[0] - ref)) <= TOL * 400.0 and snr_db(ref, y[0]) >= 120.0
+
+
+def test_umma_out_of_range_input_is_recomputed_in_fp32(ctx, O):
+    """Samples with |x| >= 256 (or Inf/NaN) do not fit the fp16 head/tail split: the launch is redone in fp32."""
+    x = signal(40000, 32)[None, :].copy()
+    x[0, 12345] = 50000.0
+    x[0, 30000] = -1.0e6
+    y = ctx.resample(x, 96000, 44100, 0)
+    ref, _ = O.resample_channel(0, 96000 / 44100, x[0], y.shape[1])
+    assert np.all(np.isfinite(y))
+    assert np.max(np.abs(y[0] - ref) / np.maximum(1.0, np.abs(ref))) <= 4 * TOL      # relative to the huge samples' scale
+    quiet = np.abs(ref) < 2.0
+    assert np.max(np.abs(y[0][quiet] - ref[quiet])) <= 64 * TOL                      # fp32 sums next to 1e6-sized terms
+
+
+def test_umma_small_and_ragged_segments(ctx, O, f9):
+    """Segments much shorter than a tile (128 periods), single-sample outputs, and a batch of unequal lengths."""
+    for n_in in (1, 7, 199, 200, 321, 5000):
+        x = signal(n_in, 33 + n_in)[None, :]
+        for kind in (0, 1):
+            y = ctx.resample(x, 96000, 44100, kind)
+            ref, _ = O.resample_channel(kind, 96000 / 44100, x[0], y.shape[1])
+            assert y.shape[1] == f9.resampled_length(n_in, 96000, 44100)
+            assert np.max(np.abs(y[0] - ref)) <= TOL, (n_in, kind)
+
+
+def test_umma_quiet_signal_keeps_relative_accuracy(ctx, O):
+    """Samples are pre-scaled by 2^7 and the fp16 tail by another 2^11, so signals down to -120 dBFS keep the SNR of a
+    full-scale one (below about -126 dBFS the fp16 head goes subnormal and the error floor, ~1e-13, takes over)."""
+    for amp in (1e-2, 1e-4, 1e-5, 2e-6):
+        x = (signal(50000, 34) * amp)[None, :]
+        y = ctx.resample(x, 96000, 44100, 0)
+        ref, _ = O.resample_channel(0, 96000 / 44100, x[0], y.shape[1])
+        assert snr_db(ref, y[0]) >= 120.0, amp
+
+
+def test_umma_group_widths_agree(ctx, O, f9, monkeypatch):
+    """Plans with 16- and 32-slot groups (F9_UMMA_NB) and the CUDA-core kernels (F9_NO_UMMA) agree with the oracle."""
+    x = np.stack([signal(60000, 35), signal(60000, 36, "sweep")])
+    refs = [O.resample_channel(0, 96000 / 44100, x[c], f9.resampled_length(60000, 96000, 44100))[0] for c in range(2)]
+    for env in ({"F9_UMMA_NB": "16"}, {"F9_UMMA_NB": "32"}, {"F9_NO_UMMA": "1"}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        c2 = f9.Context(0)                       # plans are cached per context
+        try:
+            y = c2.resample(x, 96000, 44100, 0)
+        finally:
+            c2.close()
+        for k in env:
+            monkeypatch.delenv(k)
+        for c in range(2):
+            assert np.max(np.abs(y[c] - refs[c])) <= TOL, env

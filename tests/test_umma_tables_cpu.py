@@ -1,0 +1,39 @@
+"""CPU: the host-built tables of the tensor-core FIR (f9_umma.cu).  f9_umma_selfcheck plans a ratio exactly as the
+library does at run time and verifies the fp16 head/tail weight tiles against the fp32 polyphase weights tap by tap
+(every tap exactly once, zeros elsewhere), so a table defect is caught here without a GPU."""
+import ctypes as C
+
+import pytest
+
+RATIOS = [(320, 147), (147, 160), (1, 4), (2, 1), (4, 1), (147, 80), (147, 320), (160, 147), (1, 1), (3, 2), (2, 3), (441, 160)]
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2, 3])
+@pytest.mark.parametrize("pq", RATIOS)
+def test_tables_reproduce_polyphase_weights(f9, kind, pq):
+    info = (C.c_int * 8)()
+    err = f9.lib().f9_umma_selfcheck(kind, pq[0], pq[1], info)
+    if err == -2.0:
+        pytest.skip("no tensor-core plan for this ratio: served by the CUDA-core kernels")
+    assert err >= 0.0, f"table defect {err} for kind {kind} ratio {pq}"
+    # x = x0 + x1/2048 with fp16 parts: |w - (w0 + w1/2048)| <= 2^-11 * 2^-11 * |w| / 2 (+ fp16 rounding of the tail)
+    assert err <= 2.0 ** -22, (kind, pq, err)
+    m, nb, groups, gbl, blocks, pool, split, smem = list(info)
+    assert nb in (16, 32) and m >= 1 and blocks >= 1 and groups == -(-(pq[1] * m) // nb)
+    assert gbl * 2 * nb + pool * nb <= 448                 # TMEM: accumulators + pool below the operand ring
+    assert smem <= 227 * 1024
+    if pool:
+        assert kind == 0 and split > 0                      # the accumulator split is for long windows only
+
+
+def test_bench_ratio_plan(f9):
+    """config 2 (96 kHz -> 44.1 kHz, WindowedSinc): 32-slot groups, one block, accumulator split on."""
+    info = (C.c_int * 8)()
+    assert f9.lib().f9_umma_selfcheck(0, 320, 147, info) >= 0
+    m, nb, groups, gbl, blocks, pool, split, smem = list(info)
+    assert (m, nb, groups, blocks) == (1, 32, 5, 1) and pool >= 4 and split >= 8
+
+
+def test_bad_arguments(f9):
+    assert f9.lib().f9_umma_selfcheck(99, 1, 1, None) == -1.0
+    assert f9.lib().f9_umma_selfcheck(0, 0, 1, None) == -1.0
