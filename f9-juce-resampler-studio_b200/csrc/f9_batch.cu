@@ -60,6 +60,7 @@ int run_chunk(f9_context* ctx, const f9_job* jobs, f9_result* results, const std
     size_t totalCh = 0;
     for (int t = 0; t < n; ++t) totalCh += (size_t) jobs[idx[(size_t) t]].numCh;
     d_bytes += (size_t) nTail * ((size_t) maxPolls * sizeof(int) + 64) + (size_t) n * 2048 + totalCh * 256;
+    d_bytes += totalCh * 1024 + d_bytes / 64;                  // per-tile records of the tensor-core resampler (64 B per >= 24 KB of output)
     h_bytes += (size_t) n * 2048 + (size_t) nTail * 16 + totalCh * 256;
     int rc = ctx->arena_reserve(d_bytes, h_bytes); if (rc) return rc;
     cudaStream_t s = ctx->stream;
@@ -187,6 +188,7 @@ int run_chunk(f9_context* ctx, const f9_job* jobs, f9_result* results, const std
             F9_TRY_CUDA(ctx, cudaMemcpyAsync(d_s, h_s, sizeof(Seg) * segs.size(), cudaMemcpyHostToDevice, s));
             F9_TRY_CUDA(ctx, cudaMemcpyAsync(d_p, h_p, sizeof(int) * prefix.size(), cudaMemcpyHostToDevice, s));
             L.d_segs = d_s; L.d_tile_prefix = d_p; L.n_segs = (int) segs.size(); L.n_tiles = prefix.back();
+            if (const size_t sb = resample_scratch_bytes(L, L.n_tiles)) L.d_tile_recs = (UmmaTileRec*) ctx->d_alloc(sb);
             F9_TRY_CUDA(ctx, launch_resample(L, s, &ctx->launches));
         }
     }

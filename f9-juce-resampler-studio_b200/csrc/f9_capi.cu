@@ -482,6 +482,7 @@ struct f9_plan {
     ResampleLaunch L;
     Seg* d_segs = nullptr;
     int* d_prefix = nullptr;
+    void* d_scratch = nullptr;
 };
 
 namespace {
@@ -746,6 +747,10 @@ int f9_resample_plan_create(f9_context* ctx, int kind, double speed_ratio, const
         return ctx->fail_cuda(e, "plan upload");
     }
     P->L.d_segs = P->d_segs; P->L.d_tile_prefix = P->d_prefix; P->L.n_segs = n_segs; P->L.n_tiles = tiles;
+    if (const size_t sb = resample_scratch_bytes(P->L, tiles)) {
+        if ((e = cudaMalloc(&P->d_scratch, sb)) != cudaSuccess) { f9_plan_destroy(P); return ctx->fail_cuda(e, "plan scratch"); }
+        P->L.d_tile_recs = (UmmaTileRec*) P->d_scratch;
+    }
     *out = P;
     return F9_OK;
 }
@@ -762,6 +767,7 @@ void f9_plan_destroy(f9_plan* plan) {
     cudaStreamSynchronize(plan->ctx->stream);
     if (plan->d_segs) cudaFree(plan->d_segs);
     if (plan->d_prefix) cudaFree(plan->d_prefix);
+    if (plan->d_scratch) cudaFree(plan->d_scratch);
     delete plan;
 }
 

@@ -2,6 +2,7 @@
 // Product code: nothing here may include or link anything under oracle/.
 #pragma once
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
@@ -160,7 +161,28 @@ struct UmmaDev {
     const uint8_t* W = nullptr;
 };
 bool build_umma(int kind, const float* sinc_table, long long p, long long q, int NB, int GBL, UmmaHost* out);
-size_t umma_smem_bytes(int maxEntries, int NB, int stages);
+size_t umma_smem_bytes(int maxEntries, int NB, int stages, bool tma = false);
+// TMA feed of the tensor-core FIR: the input rows of a tile (128 periods, p floats apart, 32 samples per stage) are one box of a
+// rank-2 tensor map whose row stride is p floats, i.e. the rows overlap in memory.  One map covers 4 GiB from its base (box
+// coordinates are 32-bit element indices); a launch carries up to kUmmaMaxMaps maps, 4 GiB apart, from the lowest input address.
+constexpr int kUmmaMaxMaps = 8;
+struct alignas(64) UmmaTma {
+    CUtensorMap maps[kUmmaMaxMaps];
+    unsigned long long base0 = 0;      // device address of maps[0]'s origin (16-byte aligned)
+    int nMaps = 0;
+};
+// Encodes the maps for rows p floats apart that start at or after `lo` and end before `hi` (device addresses).  False when the
+// driver entry point is missing or refuses the map (the register loader is used instead).
+// Per-tile record of the TMA-fed kernel, written by umma_tile_table_kernel before the FIR launch so that no role searches the
+// segment table on its critical path (a role loads the record of its next tile one tile ahead).
+struct alignas(16) UmmaTileRec {
+    const float* in; float* out;       // segment window origin, segment output
+    long long l00, inAvail;            // window index of (row 0, K 0); window length
+    long long oBase, numOut;           // output index of (row 0, slot 0 of the block), relative to the segment; segment outputs
+    int x0, mapIdx;                    // box coordinate / tensor map of stage 0; mapIdx < 0: the tile does not go through TMA
+    int pad[2];
+};
+bool umma_encode_maps(unsigned long long lo, unsigned long long hi, int p, UmmaTma* out);
 void umma_choose_plan(int taps, long long p, long long q, long long* m_out, int* NB_out, int* GBL_out);
 double umma_cost_per_output(int taps, long long p, long long q, int NB, int GBL, size_t* smem2);   // model used to pick the plan
 
@@ -171,6 +193,9 @@ struct ResampleLaunch {
     UmmaDev um;
     int um_stages = 0; size_t um_smem = 0;
     bool um_aligned = false;       // every row piece of every segment starts on 16 bytes (set by resample_build_tiles)
+    bool um_tma = false;           // aligned and the tensor maps were encoded: TMA feed (set by resample_build_tiles)
+    UmmaTma um_maps;
+    UmmaTileRec* d_tile_recs = nullptr;    // n_tiles records, caller-provided scratch when um_tma (see resample_scratch_bytes)
     unsigned* d_ovf = nullptr;     // device flag: an input sample was outside the fp16 split's range -> fp32 redo
     // banded (register-tiled) path
     bool banded = false;
@@ -196,6 +221,8 @@ cudaError_t launch_umma(const ResampleLaunch& L, cudaStream_t s, long long* laun
 long long   resample_ctas_for_segment(const ResampleLaunch& L, long long n0, long long numOut);
 // Fill tile_prefix (n+1 ints) for the segments; returns the CTA total or -1 on overflow.
 int         resample_build_tiles(ResampleLaunch& L, const Seg* segs, int n, std::vector<int>* prefix);
+// Device scratch the launch needs next to the segment table (set L.d_tile_recs to a buffer of this size; 0 = none)
+inline size_t resample_scratch_bytes(const ResampleLaunch& L, int n_tiles) { return L.umma && L.um_tma ? sizeof(UmmaTileRec) * (size_t) n_tiles : 0; }
 
 }  // namespace f9
 

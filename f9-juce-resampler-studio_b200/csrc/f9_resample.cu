@@ -420,6 +420,24 @@ int resample_build_tiles(ResampleLaunch& L, const Seg* segs, int n, std::vector<
             if (segs[i].numOut > 0 && ((((long long) (reinterpret_cast<uintptr_t>(segs[i].in) >> 2) - segs[i].inOffset) & 3) != 0 ||
                                        (reinterpret_cast<uintptr_t>(segs[i].in) & 3) != 0)) aligned = false;
         L.um_aligned = aligned && getenv("F9_UMMA_UNALIGNED") == nullptr;
+        // TMA feed (aligned rows only): tensor maps over the address range the segments read, ring of raw fp32 boxes
+        L.um_tma = false;
+        if (L.um_aligned && getenv("F9_UMMA_NOTMA") == nullptr) {
+            unsigned long long lo = ~0ull, hi = 0;
+            for (int i = 0; i < n; ++i) {
+                if (segs[i].numOut <= 0 || segs[i].inAvail <= 0) continue;
+                const unsigned long long a = (unsigned long long) reinterpret_cast<uintptr_t>(segs[i].in);
+                lo = std::min(lo, a); hi = std::max(hi, a + 4ull * (unsigned long long) segs[i].inAvail);
+            }
+            if (hi > lo && umma_encode_maps(lo, hi, L.um.p, &L.um_maps)) {
+                int stages = 2;
+                const int maxStages = getenv("F9_UMMA_STAGES") ? atoi(getenv("F9_UMMA_STAGES")) : 8;
+                while (stages < maxStages && umma_smem_bytes(L.um.maxEntries, L.um.NB, stages + 1, true) <= 227 * 1024) ++stages;
+                if (umma_smem_bytes(L.um.maxEntries, L.um.NB, stages, true) <= 227 * 1024) {
+                    L.um_tma = true; L.um_stages = stages; L.um_smem = umma_smem_bytes(L.um.maxEntries, L.um.NB, stages, true);
+                }
+            }
+        }
     }
     for (int i = 0; i < n; ++i) {
         total += resample_ctas_for_segment(L, segs[i].n0, segs[i].numOut);

@@ -309,9 +309,11 @@ int umma_pool_slots(int NB, int GBL) {                     // accumulator-split 
 
 }  // namespace
 
-size_t umma_smem_bytes(int maxEntries, int NB, int stages) {
+size_t umma_smem_bytes(int maxEntries, int NB, int stages, bool tma) {
     const size_t w = (size_t) maxEntries * NB * 64;        // tile: 2 K chunks x 2*NB rows x 16 B
-    const size_t ring = (size_t) stages * 8 * (128 * 16 + 32);
+    // register loader: converted stages (fp16 head + tail, padded K chunks); TMA feed: raw fp32 boxes of 128 rows x 128 B,
+    // 1024-byte aligned for the 128-byte swizzle
+    const size_t ring = tma ? (size_t) stages * 16384 + 1024 : (size_t) stages * 8 * (128 * 16 + 32);
     const size_t epi = 128 * 20 * 4;
     const size_t bars = (size_t) (2 * stages + 2 * kUmmaMaxGroups + 4) * 8 + 16;
     return w + ring + epi + bars + 128;                    // + alignment slack

@@ -101,6 +101,16 @@ __device__ __forceinline__ void umma_cp(uint32_t d_tmem, uint64_t sdesc) {
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 :: "r"(dst), "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void l2_prefetch(const void* p, uint32_t bytes) {       // p and bytes multiples of 16
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(p), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -127,11 +137,13 @@ struct SmemMap {
     uint8_t* W; uint8_t* ring; float* epi;
     uint64_t *full, *empty, *accFull, *accEmpty, *cpDone, *slotFree; uint32_t* tmemSlot;
 };
-__device__ __forceinline__ SmemMap carve(uint8_t* smem, int maxEntries, int NB, int stages) {
+constexpr int kTmaStageBytes = kRows * 128;         // TMA feed: one stage = a box of 128 rows x 32 floats, 128-byte swizzle
+__device__ __forceinline__ SmemMap carve(uint8_t* smem, int maxEntries, int NB, int stages, bool tma) {
     SmemMap m;
     m.W = smem;
     m.ring = m.W + (size_t) maxEntries * NB * 64;
-    m.epi = reinterpret_cast<float*>(m.ring + (size_t) stages * kStageBytes);
+    if (tma) m.ring += (1024u - (smem_u32(m.ring) & 1023u)) & 1023u;          // swizzle atoms are 1024 bytes
+    m.epi = reinterpret_cast<float*>(m.ring + (size_t) stages * (tma ? kTmaStageBytes : kStageBytes));
     m.full = reinterpret_cast<uint64_t*>(m.epi + kRows * kEpiPitch);
     m.empty = m.full + stages;
     m.accFull = m.empty + stages;
@@ -292,17 +304,153 @@ __device__ __forceinline__ void loader_role(const LoaderArgs& A, int lw, int lan
     if (A.prof && lw == 0 && lane == 0) { A.prof[blockIdx.x * 16 + 0] = clock64() - pT0; A.prof[blockIdx.x * 16 + 1] = pW0; }
 }
 
+
+// ------------------------------------------------------------------------------------------------- TMA feed
+// With 16-byte aligned rows (p % 4 == 0, aligned segments) the loader warps above are replaced by:
+//   warp 4, one lane: per stage one cp.async.bulk.tensor of the box [128 rows (p floats apart: the rows overlap in memory) x
+//                     32 floats] into a ring of raw fp32 stages (128-byte swizzle), plus a bulk L2 prefetch of the CTA's next tile;
+//   warps 8-15:       thread = period row = TMEM lane.  Each warp converts one 16-sample K step of its 32 rows (4 conflict-free
+//                     LDS.128, fp16 head / tail split in registers) and writes it straight into the TMEM operand slot with one
+//                     tcgen05.st.32x32b.x16: no converted copy in shared memory, no tcgen05.cp, no proxy fence.
+// A tile whose boxes would leave its segment's window [0, inAvail) does not go through the ring: the converters read its
+// rows from global memory with guards (both sides derive this from the same tile geometry).
+// The geometry of a tile comes from its record (UmmaTileRec, written by umma_tile_table_kernel just before this launch).
+template <typename T> __device__ __forceinline__ T* ldg_ptr(T* const* p) {
+    return reinterpret_cast<T*>(__ldg(reinterpret_cast<const unsigned long long*>(p)));
+}
+__device__ __forceinline__ int4 ld_rec_tail(const UmmaTileRec* r) { return __ldg(reinterpret_cast<const int4*>(&r->x0)); }   // x0, mapIdx
+
+struct FeedArgs {
+    const UmmaTileRec* recs; int p, nStages, stages, myTiles;
+    uint8_t* ring; uint64_t *full, *empty, *aReady, *slotFree; unsigned* ovf; long long* prof;
+};
+__device__ __forceinline__ void producer_role(const FeedArgs& A, const UmmaTma& TM) {
+    int sIdx = 0; uint32_t sPh = 0;
+    long long pW = 0; const long long pT0 = A.prof ? clock64() : 0;
+    const uint32_t ring0 = smem_u32(A.ring);
+    const uint32_t tileBytes = (uint32_t) (((kRows - 1) * A.p + A.nStages * 32) * 4);
+    const uint32_t pfChunk = (tileBytes / (uint32_t) A.nStages + 15u) & ~15u;
+    const UmmaTileRec* rec = A.recs + blockIdx.x;
+    int4 cur = A.myTiles > 0 ? ld_rec_tail(rec) : make_int4(0, -1, 0, 0);
+    for (int t = 0; t < A.myTiles; ++t, rec += gridDim.x) {
+        // the next tile: its record (x0, mapIdx) for the next iteration and its input range for the L2 prefetch
+        int4 nxt = make_int4(0, -1, 0, 0); const char* pf = nullptr;
+        if (t + 1 < A.myTiles) {
+            const UmmaTileRec* nr = rec + gridDim.x;
+            nxt = ld_rec_tail(nr);
+            if (nxt.y >= 0) pf = reinterpret_cast<const char*>(ldg_ptr(&nr->in) + __ldg(&nr->l00));
+        }
+        if (cur.y < 0) {
+            if (pf) for (int st = 0; st < A.nStages; ++st) l2_prefetch(pf + (size_t) st * pfChunk, pfChunk);
+        } else {
+            const CUtensorMap* map = &TM.maps[cur.y];
+            for (int st = 0; st < A.nStages; ++st) {
+                if (A.prof) { const long long w = clock64(); mbar_wait(A.empty + sIdx, sPh ^ 1); pW += clock64() - w; }
+                else mbar_wait(A.empty + sIdx, sPh ^ 1);
+                mbar_expect_tx(A.full + sIdx, (uint32_t) kTmaStageBytes);
+                tma_load_2d(ring0 + (uint32_t) (sIdx * kTmaStageBytes), map, cur.x + st * 32, 0, A.full + sIdx);
+                if (pf) l2_prefetch(pf + (size_t) st * pfChunk, pfChunk);
+                if (++sIdx == A.stages) { sIdx = 0; sPh ^= 1; }
+            }
+        }
+        cur = nxt;
+    }
+    if (A.prof) { A.prof[blockIdx.x * 16 + 2] = clock64() - pT0; A.prof[blockIdx.x * 16 + 3] = pW; }
+}
+
+__device__ __forceinline__ void converter_role(const FeedArgs& A, uint32_t tmem, int cw, int lane) {
+    const int quarter = cw & 3, h = cw >> 2;                   // TMEM lane quarter (= warp id % 4), K step of the stage
+    const int rho = quarter * 32 + lane;                       // period row = TMEM lane = row of the box
+    const uint32_t tdst = tmem + ((uint32_t) (quarter * 32) << 16) + (uint32_t) (kACol + h * 16);
+    const uint32_t ringRow = smem_u32(A.ring) + (uint32_t) (rho * 128);
+    const uint32_t sw = (uint32_t) (rho & 7);
+    __half2 hmax = __floats2half2_rn(0.f, 0.f);
+    int sIdx = 0; uint32_t sPh = 0; int gs = 0;
+    long long pW0 = 0, pW1 = 0, pS = 0; const long long pT0 = A.prof ? clock64() : 0;
+    struct TileIn { const float* in; long long l00, inAvail; bool viaTma; };
+    auto load_rec = [&](const UmmaTileRec* r) {
+        TileIn T; T.in = ldg_ptr(&r->in); T.l00 = __ldg(&r->l00); T.inAvail = __ldg(&r->inAvail); T.viaTma = __ldg(&r->mapIdx) >= 0; return T;
+    };
+    const UmmaTileRec* rec = A.recs + blockIdx.x;
+    TileIn T = {nullptr, 0, 0, false}, N = T;
+    if (A.myTiles > 0) N = load_rec(rec);
+    for (int t = 0; t < A.myTiles; ++t, rec += gridDim.x) {
+        T = N;
+        if (t + 1 < A.myTiles) N = load_rec(rec + gridDim.x);                  // consumed one tile later
+        const long long lrow = T.l00 + (long long) rho * A.p + h * 16;
+        for (int st = 0; st < A.nStages; ++st, ++gs) {
+            float4 v[4];
+            if (T.viaTma) {
+                if (A.prof) { const long long w = clock64(); mbar_wait(A.full + sIdx, sPh); pW0 += clock64() - w; }
+                else mbar_wait(A.full + sIdx, sPh);
+                const uint32_t a = ringRow + (uint32_t) (sIdx * kTmaStageBytes);
+                #pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[c].x), "=f"(v[c].y), "=f"(v[c].z), "=f"(v[c].w)
+                                 : "r"(a + ((((uint32_t) (4 * h + c)) ^ sw) << 4)) : "memory");
+            } else {
+                #pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const long long l = lrow + st * 32 + 4 * c;
+                    const float* ptr = T.in + l;
+                    if (l >= 0 && l + 3 < T.inAvail) v[c] = __ldg(reinterpret_cast<const float4*>(ptr));
+                    else {
+                        v[c].x = (l >= 0 && l < T.inAvail) ? __ldg(ptr) : 0.f;             v[c].y = (l + 1 >= 0 && l + 1 < T.inAvail) ? __ldg(ptr + 1) : 0.f;
+                        v[c].z = (l + 2 >= 0 && l + 2 < T.inAvail) ? __ldg(ptr + 2) : 0.f; v[c].w = (l + 3 >= 0 && l + 3 < T.inAvail) ? __ldg(ptr + 3) : 0.f;
+                    }
+                }
+            }
+            uint32_t hd[8], tl[8];
+            #pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float4 xv = v[c];
+                xv.x *= kPreScale; xv.y *= kPreScale; xv.z *= kPreScale; xv.w *= kPreScale;
+                const __half2 h01 = __floats2half2_rn(xv.x, xv.y), h23 = __floats2half2_rn(xv.z, xv.w);
+                hmax = __hmax2_nan(hmax, __hmax2_nan(__habs2(h01), __habs2(h23)));
+                const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                const __half2 t01 = __floats2half2_rn((xv.x - f01.x) * 2048.0f, (xv.y - f01.y) * 2048.0f);
+                const __half2 t23 = __floats2half2_rn((xv.z - f23.x) * 2048.0f, (xv.w - f23.y) * 2048.0f);
+                hd[2 * c] = *reinterpret_cast<const uint32_t*>(&h01); hd[2 * c + 1] = *reinterpret_cast<const uint32_t*>(&h23);
+                tl[2 * c] = *reinterpret_cast<const uint32_t*>(&t01); tl[2 * c + 1] = *reinterpret_cast<const uint32_t*>(&t23);
+            }
+            if (T.viaTma) {                                    // the stage's rows are in registers: the box may be refilled
+                __syncwarp();
+                if (lane == 0) mbar_arrive(A.empty + sIdx);
+                if (++sIdx == A.stages) { sIdx = 0; sPh ^= 1; }
+            }
+            if (gs >= 2) {                                     // MMAs of stage gs - 2 have read the slot
+                if (A.prof) { const long long w = clock64(); mbar_wait(A.slotFree + (gs & 1), (uint32_t) (((gs >> 1) - 1) & 1)); pW1 += clock64() - w; }
+                else mbar_wait(A.slotFree + (gs & 1), (uint32_t) (((gs >> 1) - 1) & 1));
+            }
+            tc_fence_after();
+            const long long pS0 = A.prof ? clock64() : 0;
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                         :: "r"(tdst + (uint32_t) ((gs & 1) * 32)), "r"(hd[0]), "r"(hd[1]), "r"(hd[2]), "r"(hd[3]), "r"(hd[4]), "r"(hd[5]), "r"(hd[6]), "r"(hd[7]),
+                            "r"(tl[0]), "r"(tl[1]), "r"(tl[2]), "r"(tl[3]), "r"(tl[4]), "r"(tl[5]), "r"(tl[6]), "r"(tl[7]) : "memory");
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(A.aReady + (gs & 1));
+            if (A.prof) pS += clock64() - pS0;
+        }
+    }
+    const float2 hm = __half22float2(hmax);
+    if (!(hm.x < 32768.0f) || !(hm.y < 32768.0f)) atomicOr(A.ovf, 1u);
+    if (A.prof && cw == 0 && lane == 0) { A.prof[blockIdx.x * 16 + 0] = clock64() - pT0; A.prof[blockIdx.x * 16 + 1] = pW0; A.prof[blockIdx.x * 16 + 8] = pW1; A.prof[blockIdx.x * 16 + 9] = pS; }
+}
+
 // out = (D0A + D0B + D1 / 2048) / kPreScale: the scalings are powers of two, the only roundings are the two additions
 __device__ __forceinline__ float combine(uint32_t d0a, uint32_t d0b, uint32_t d1) {
     return fmaf(__uint_as_float(d1), 1.0f / (2048.0f * kPreScale), (__uint_as_float(d0a) + __uint_as_float(d0b)) * (1.0f / kPreScale));
 }
 
-template <bool MERGED>
+template <bool MERGED, bool TMA>
 __global__ void __launch_bounds__(kThreads, 1)
 umma_fir_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix, int nSegs, int nTiles,
-                const __grid_constant__ UmmaDev P, int stages, int alignedAll, unsigned* __restrict__ ovf, long long* __restrict__ prof, int dbg) {
+                const __grid_constant__ UmmaDev P, const __grid_constant__ UmmaTma TM, const UmmaTileRec* __restrict__ recs, int stages, int alignedAll,
+                unsigned* __restrict__ ovf, long long* __restrict__ prof, int dbg) {
     extern __shared__ __align__(128) uint8_t smem[];
-    const SmemMap sm = carve(smem, P.maxEntries, P.NB, stages);
+    const SmemMap sm = carve(smem, P.maxEntries, P.NB, stages, TMA);
     const int NB = P.NB;                                       // slots per group: MMA N
     const int warp = __shfl_sync(0xffffffffu, (int) (threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int gb = blockIdx.x % P.nGB;
@@ -317,9 +465,11 @@ umma_fir_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix
         uint4* dst = reinterpret_cast<uint4*>(sm.W);
         for (int i = threadIdx.x; i < BI.nEntries * NB * 4; i += kThreads) dst[i] = __ldg(src + i);
         if (threadIdx.x == 0) {
-            for (int s = 0; s < stages; ++s) { mbar_init(sm.full + s, kLoaderWarps); mbar_init(sm.empty + s, 1); }
+            // register loader: full <- 8 loader warps, empty <- the copy warp's commit, cpDone <- its commit
+            // TMA feed:        full <- the producer's expect_tx, empty <- 8 converter warps, cpDone ("operand ready") <- 8 converter warps
+            for (int s = 0; s < stages; ++s) { mbar_init(sm.full + s, TMA ? 1 : kLoaderWarps); mbar_init(sm.empty + s, TMA ? kLoaderWarps : 1); }
             for (int g = 0; g < kUmmaMaxGroups; ++g) { mbar_init(sm.accFull + g, 1); mbar_init(sm.accEmpty + g, 4); }
-            for (int i = 0; i < 2; ++i) { mbar_init(sm.cpDone + i, 1); mbar_init(sm.slotFree + i, kIssuers); }
+            for (int i = 0; i < 2; ++i) { mbar_init(sm.cpDone + i, TMA ? kLoaderWarps : 1); mbar_init(sm.slotFree + i, kIssuers); }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         if (warp == 4) {
@@ -340,7 +490,15 @@ umma_fir_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix
     #define PROF_END(acc, v) if (prof) acc += clock64() - v
     if (prof) pT0 = clock64();
 
-    if (warp >= kFirstLoader) {
+    if (TMA && (warp >= kFirstLoader || warp == 4)) {
+        // =========================================================== TMA producer / converters
+        FeedArgs FA;
+        FA.recs = recs; FA.p = p;
+        FA.nStages = nStages; FA.stages = stages; FA.myTiles = myTiles;
+        FA.ring = sm.ring; FA.full = sm.full; FA.empty = sm.empty; FA.aReady = sm.cpDone; FA.slotFree = sm.slotFree; FA.ovf = ovf; FA.prof = prof;
+        if (warp == 4) { if (lane == 0) producer_role(FA, TM); }
+        else converter_role(FA, tmem, warp - kFirstLoader, lane);
+    } else if (warp >= kFirstLoader) {
         // =========================================================== loaders
         LoaderArgs LA;
         LA.segs = segs; LA.tilePrefix = tilePrefix; LA.nSegs = nSegs; LA.nTiles = nTiles; LA.nGB = P.nGB; LA.p = p; LA.q = q;
@@ -395,14 +553,30 @@ umma_fir_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix
         const uint32_t poolCol = (uint32_t) (P.GBL * 2 * NB), poolMask = (uint32_t) (P.poolN > 0 ? P.poolN - 1 : 0);
         const uint64_t wDesc0 = make_desc(smem_u32(sm.W), 32 * NB, 128);       // weight tile i: + 4*NB*i (16-byte units); w1 rows at + NB
         const int split = P.poolN > 0 ? P.split : 0x7fffffff;
+        // schedule of the groups this warp owns, read once (the kernel parameters are constant-bank loads: in the issue loop
+        // they sat on the dependency chain in front of every MMA)
+        constexpr int kMaxOwn = (kUmmaMaxGroups + kIssuers - 1) / kIssuers;
+        int gG0[kMaxOwn], gGn[kMaxOwn]; uint32_t gBd[kMaxOwn];
+        #pragma unroll
+        for (int i = 0; i < kMaxOwn; ++i) {
+            const int gl = w + i * kIssuers;
+            const bool own = gl < BI.nGroups;
+            gG0[i] = own ? (int) P.gStart[gb][gl] : 0; gGn[i] = own ? (int) P.gSteps[gb][gl] : 0;
+            gBd[i] = own ? (uint32_t) P.gTile[gb][gl] * 4u * nb : 0u;
+        }
+        const int nGroups = BI.nGroups;
         int gs = 0;
         for (int t = 0; t < myTiles; ++t) {
             for (int st = 0; st < nStages; ++st, ++gs) {
                 { PROF_BEGIN(wq); mbar_wait(sm.cpDone + (gs & 1), (uint32_t) ((gs >> 1) & 1)); PROF_END(pW0, wq); }
                 tc_fence_after();
                 PROF_BEGIN(wi);
-                for (int gl = w; gl < BI.nGroups; gl += kIssuers) {
-                    const int g0 = P.gStart[gb][gl], gn = P.gSteps[gb][gl];
+                const uint32_t aSlot = tmem + kACol + (uint32_t) ((gs & 1) * 32);
+                #pragma unroll
+                for (int i = 0; i < kMaxOwn; ++i) {
+                    const int gl = w + i * kIssuers;
+                    const int g0 = gG0[i], gn = gGn[i];
+                    if (2 * st + 1 < g0 || 2 * st >= g0 + gn) continue;           // no K step of this stage inside the group's window (gn = 0: not owned)
                     #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         const int j = 2 * st + h - g0;                         // K step inside the group's window
@@ -414,16 +588,16 @@ umma_fir_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix
                             PROF_BEGIN(wd);
                             if ((uint32_t) gl > poolMask) mbar_wait(sm.accEmpty + (gl - (int) poolMask - 1), t & 1);       // same tile
                             else {                                                                                  // previous tile
-                                int lu = gl; while (lu + (int) poolMask + 1 < BI.nGroups) lu += (int) poolMask + 1;
+                                int lu = gl; while (lu + (int) poolMask + 1 < nGroups) lu += (int) poolMask + 1;
                                 mbar_wait(sm.accEmpty + lu, (t & 1) ^ 1);
                             }
                             PROF_END(pW1, wd);
                             tc_fence_after();
                         }
                         if (el && !(dbg & 1)) {
-                            const uint32_t aHi = tmem + kACol + (uint32_t) ((gs & 1) * 32 + h * 16);
+                            const uint32_t aHi = aSlot + (uint32_t) (h * 16);
                             const uint32_t d1 = tmem + (uint32_t) (2 * gl + 1) * nb;
-                            const uint64_t bd = wDesc0 + (uint64_t) ((uint32_t) (P.gTile[gb][gl] + j) * 4u * nb);
+                            const uint64_t bd = wDesc0 + (uint64_t) (gBd[i] + (uint32_t) j * 4u * nb);
                             const uint32_t acc = j > 0 ? 1u : 0u;
                             if (MERGED || j < split) {         // D0 and D1 adjacent: [D0 | D1] (+)= x0 * [w0 | w1] as one N = 2*NB MMA
                                 umma_ts(d1 - nb, aHi, bd, idesc2N, acc);
@@ -450,12 +624,25 @@ umma_fir_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix
         const uint32_t laneBase = (uint32_t) (warp * 32) << 16;
         const int chunks = NB / 16;
         int tileId = blockIdx.x;
+        struct TileOut { float* out; long long oBase, numOut; };
+        auto load_out = [&](int id) {
+            TileOut O;
+            if (TMA) { const UmmaTileRec* r = recs + id; O.out = ldg_ptr(&r->out); O.oBase = __ldg(&r->oBase); O.numOut = __ldg(&r->numOut); }
+            else {
+                const int sidx = find_seg(tilePrefix, nSegs, id);
+                const Seg S = segs[sidx];
+                const int pb = (id - tilePrefix[sidx]) / P.nGB;
+                const long long A0 = S.n0 / q + (long long) pb * kRows;
+                O.out = S.out; O.oBase = A0 * q + BI.slot0 - S.n0; O.numOut = S.numOut;
+            }
+            return O;
+        };
+        TileOut ON = {nullptr, 0, 0};
+        if (myTiles > 0) ON = load_out(tileId);
         for (int t = 0; t < myTiles; ++t, tileId += gridDim.x) {
-            const int sidx = find_seg(tilePrefix, nSegs, tileId);
-            const Seg S = segs[sidx];
-            const int pb = (tileId - tilePrefix[sidx]) / P.nGB;
-            const long long A0 = S.n0 / q + (long long) pb * kRows;
-            const long long oBase = A0 * q + BI.slot0 - S.n0;                  // output index of (row 0, slot 0 of the block)
+            const TileOut S = ON;
+            if (t + 1 < myTiles) ON = load_out(tileId + (int) gridDim.x);     // consumed one tile later
+            const long long oBase = S.oBase;                                    // output index of (row 0, slot 0 of the block)
             const int blockSlots = min(BI.nGroups * NB, q - BI.slot0);          // real (non-padding) slots of this block
             const bool rowsInside = oBase >= 0 && oBase + (long long) (kRows - 1) * q + blockSlots <= S.numOut;
             float* outG = reinterpret_cast<float*>(__cvta_generic_to_global(S.out));
@@ -519,6 +706,31 @@ umma_fir_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix
     if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512) : "memory");
 }
 
+// One thread per tile: the record the TMA-fed kernel's roles read instead of searching the segment table.
+__global__ void __launch_bounds__(256)
+umma_tile_table_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix, int nSegs, int nTiles,
+                       const __grid_constant__ UmmaDev P, const __grid_constant__ UmmaTma TM, UmmaTileRec* __restrict__ recs) {
+    const int tileId = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tileId >= nTiles) return;
+    const UmmaBlockInfo& BI = P.blk[tileId % P.nGB];            // every segment owns a multiple of nGB tiles
+    const int sidx = find_seg(tilePrefix, nSegs, tileId);
+    const Seg S = segs[sidx];
+    const int pb = (tileId - tilePrefix[sidx]) / P.nGB;
+    const long long A0 = S.n0 / P.q + (long long) pb * kRows;
+    UmmaTileRec R;
+    R.in = S.in; R.out = S.out; R.inAvail = S.inAvail; R.numOut = S.numOut;
+    R.l00 = A0 * P.p + BI.U0 - S.inOffset;
+    R.oBase = A0 * P.q + BI.slot0 - S.n0;
+    // through TMA only if every box of the tile lies inside the segment's window (no reliance on out-of-bounds fill, no reads
+    // outside the caller's buffer) and inside the address range the maps cover
+    const bool interior = R.l00 >= 0 && R.l00 + (long long) (kRows - 1) * P.p + (long long) BI.nStages * 32 <= S.inAvail;
+    const unsigned long long rel = (unsigned long long) reinterpret_cast<uintptr_t>(S.in + R.l00) - TM.base0;
+    R.x0 = (int) ((rel & 0xffffffffull) >> 2);
+    R.mapIdx = interior && (rel >> 32) < (unsigned long long) TM.nMaps ? (int) (rel >> 32) : -1;
+    R.pad[0] = R.pad[1] = 0;
+    recs[tileId] = R;
+}
+
 // fp32 recomputation of a launch whose input did not fit the fp16 split (same tiles, CUDA cores, no staging):
 // exits at once unless the flag is set.
 __global__ void __launch_bounds__(256)
@@ -546,11 +758,46 @@ umma_redo_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefi
 
 }  // namespace
 
+// ---- tensor maps (host) ---------------------------------------------------------------------------------------
+// The driver entry point is fetched through the runtime (no link against libcuda).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+bool umma_encode_maps(unsigned long long lo, unsigned long long hi, int p, UmmaTma* out) {
+    static EncodeTiledFn encode = nullptr; static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* fn = nullptr; cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            encode = reinterpret_cast<EncodeTiledFn>(fn);
+        else (void) cudaGetLastError();
+    }
+    if (!encode || (p & 3) != 0 || p <= 0 || hi <= lo) return false;
+    const unsigned long long base0 = lo & ~15ull;
+    const int n = (int) (((hi - base0) >> 32) + 1);
+    if (n > kUmmaMaxMaps) return false;
+    // Rows p floats apart, 32 floats per box row: the rows overlap in memory, which the descriptor does not mind.  The extents
+    // are only bounds for the coordinates the kernel uses (x < 2^30 + a tile's K span, y < 128): tiles that would leave their
+    // segment's window never go through TMA, so out-of-bounds fill is never relied on.
+    const cuuint64_t dims[2] = {(cuuint64_t) ((1ull << 30) + 65536), 1024};
+    const cuuint64_t strides[1] = {(cuuint64_t) p * 4};
+    const cuuint32_t box[2] = {32, (cuuint32_t) kRows}, es[2] = {1, 1};
+    for (int k = 0; k < n; ++k) {
+        const CUresult r = encode(&out->maps[k], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, reinterpret_cast<void*>(base0 + ((unsigned long long) k << 32)), dims, strides,
+                                  box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return false;
+    }
+    out->base0 = base0; out->nMaps = n;
+    return true;
+}
+
 cudaError_t launch_umma(const ResampleLaunch& L, cudaStream_t s, long long* launches) {
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(umma_fir_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(umma_fir_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(umma_fir_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(umma_fir_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(umma_fir_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(umma_fir_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
@@ -565,14 +812,25 @@ cudaError_t launch_umma(const ResampleLaunch& L, cudaStream_t s, long long* laun
     const bool doProf = profEnv != nullptr && prof_calls++ == atoi(profEnv);
     if (doProf) { cudaMalloc((void**) &d_prof, sizeof(long long) * 16 * grid); cudaMemsetAsync(d_prof, 0, sizeof(long long) * 16 * grid, s); }
     const int dbg = getenv("F9_UMMA_DBG") ? atoi(getenv("F9_UMMA_DBG")) : 0;     // development: 1 skip MMAs, 2 skip copies, 4 skip stores
-    if (L.um.poolN == 0)
-        umma_fir_kernel<true><<<grid, kThreads, L.um_smem, s>>>(L.d_segs, L.d_tile_prefix, L.n_segs, L.n_tiles, L.um, L.um_stages, L.um_aligned ? 1 : 0, L.d_ovf, doProf ? d_prof : nullptr, dbg);
-    else
-        umma_fir_kernel<false><<<grid, kThreads, L.um_smem, s>>>(L.d_segs, L.d_tile_prefix, L.n_segs, L.n_tiles, L.um, L.um_stages, L.um_aligned ? 1 : 0, L.d_ovf, doProf ? d_prof : nullptr, dbg);
+    #define F9_UMMA_LAUNCH(MERGED, TMA) umma_fir_kernel<MERGED, TMA><<<grid, kThreads, L.um_smem, s>>>(L.d_segs, L.d_tile_prefix, L.n_segs, L.n_tiles, \
+        L.um, L.um_maps, L.d_tile_recs, L.um_stages, L.um_aligned ? 1 : 0, L.d_ovf, doProf ? d_prof : nullptr, dbg)
+    if (L.um_tma) {
+        if (!L.d_tile_recs) return cudaErrorInvalidValue;
+        umma_tile_table_kernel<<<(L.n_tiles + 255) / 256, 256, 0, s>>>(L.d_segs, L.d_tile_prefix, L.n_segs, L.n_tiles, L.um, L.um_maps, L.d_tile_recs);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        ++*launches;
+        if (L.um.poolN == 0) F9_UMMA_LAUNCH(true, true); else F9_UMMA_LAUNCH(false, true);
+    }
+    else          { if (L.um.poolN == 0) F9_UMMA_LAUNCH(true, false); else F9_UMMA_LAUNCH(false, false); }
+    #undef F9_UMMA_LAUNCH
     if (doProf) {
         std::vector<long long> h((size_t) 16 * grid);
         cudaStreamSynchronize(s); cudaMemcpy(h.data(), d_prof, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost);
         double a[16] = {0}; for (int i = 0; i < grid; ++i) for (int k = 0; k < 16; ++k) a[k] += (double) h[(size_t) i * 16 + k] / grid;
+        if (L.um_tma)
+            fprintf(stderr, "[umma prof tma] tiles/CTA %.1f stages/tile %d ring %d | converter0 total %.0f wait-full %.0f wait-slot %.0f st+arrive %.0f | producer total %.0f wait-empty %.0f | epilogue total %.0f wait-done %.0f stores %.0f | issuer0: wait-ready %.0f issue %.0f (wait-drained %.0f)\n",
+                    (double) L.n_tiles / grid, L.um.blk[0].nStages, L.um_stages, a[0], a[1], a[8], a[9], a[2], a[3], a[5], a[6], a[7], a[10], a[11], a[12]);
+        else
         fprintf(stderr, "[umma prof] tiles/CTA %.1f stages/tile %d | loader total %.0f wait-free %.0f | copy total %.0f wait-full %.0f wait-slot %.0f | epilogue total %.0f wait-done %.0f stores %.0f | copy: fence %.0f cp-issue %.0f | issuer0: wait-cp %.0f issue %.0f (wait-drained %.0f)\n",
                 (double) L.n_tiles / grid, L.um.blk[0].nStages, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[11], a[12]);
     }
