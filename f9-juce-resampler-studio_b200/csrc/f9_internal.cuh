@@ -126,8 +126,29 @@ void build_banded(int kind, const float* sinc_table, long long p, long long q, i
 // period in steps of 16 samples.  Samples and weights are split into an fp16 head and an fp16 tail scaled by 2^11
 // (x = x0 + x1/2048, w = w0 + w1/2048), three products are kept:  D0 += x0*w0,  D1 += x0*w1 + x1*w0,  out = D0 + D1/2048.
 constexpr int kUmmaMaxBlocks = 8;        // group blocks per ratio (passes over the same rows)
-constexpr int kUmmaMaxGroups = 14;       // groups per block: 2*NB TMEM columns each, 448 of 512
+constexpr int kUmmaMaxGroups = 12;       // groups per block: 2*NB TMEM columns each
 constexpr int kUmmaMaxNK = 64;           // K steps per block (period + taps + alignment <= 1024 input samples)
+constexpr int kUmmaIssuers = 3;          // MMA-issuing warps: group gl of a block belongs to warp gl % kUmmaIssuers
+// One (group, K step) of a tile as the issuing warp sees it: 16 bytes, listed per warp in issue order (stage, group, K step).
+// The lists are built on the host (build_umma), live behind the weight tiles and are copied to shared memory with them.
+struct UmmaOp {
+    uint16_t d1Col;        // TMEM column of the group's D1 accumulator ((2 gl + 1) NB); D0 is NB columns below
+    uint16_t poolCol;      // TMEM column of the group's D0B pool slot (split plans)
+    uint32_t bOff;         // weight tile offset from the first tile, in 16-byte units (shared-memory descriptor address field)
+    uint8_t  stage, h;     // stage of the tile, K step of the stage (0 / 1)
+    uint8_t  gl;           // group inside the block
+    uint8_t  flags;        // kOp* below
+    uint8_t  waitGl;       // kOpWaitPool: the group whose drained accumulators free the pool slot
+    uint8_t  pad[3];
+};
+static_assert(sizeof(UmmaOp) == 16, "UmmaOp is loaded as one 128-bit word");
+enum : uint8_t { kOpAcc = 1,          // accumulate into D0/D1 (not the group's first K step)
+                 kOpMerged = 2,       // [D0 | D1] (+)= x0 [w0 | w1] as one N = 2 NB MMA (before the split, or no split)
+                 kOpPoolAcc = 4,      // past the split: accumulate into the pool slot (not its first step there)
+                 kOpWaitDrain = 8,    // first K step: the epilogue must have drained the group's accumulators (previous tile)
+                 kOpWaitPool = 16,    // first step past the split: the pool slot's previous user must have been drained
+                 kOpPoolPrevTile = 32,// ... and that user belongs to the previous tile
+                 kOpLast = 64 };      // last K step: commit "group done"
 struct UmmaBlockInfo {
     int U0;            // K index 0 is input sample a*p + U0 (multiple of 16, <= every window start of the block)
     int nK;            // K steps (16 samples each) the block's windows span
@@ -136,6 +157,8 @@ struct UmmaBlockInfo {
     int slot0;         // first slot of the block
     int nEntries;      // weight tiles of the block (one per (group, K step of its window)), NB*64 bytes each from wOff
     int wOff;          // byte offset into W
+    int opOff;         // byte offset into W of the block's UmmaOp lists (nEntries records, warp 0's first)
+    int opStart[kUmmaIssuers + 1];   // record range of each issuing warp
 };
 struct UmmaHost {
     int p = 0, q = 0, taps = 0, NB = 16, G = 0, GBL = 0, nGB = 0;
@@ -149,6 +172,7 @@ struct UmmaHost {
     // steps after the window's centre (small partial sums) goes to a second accumulator D0B taken from a pool of poolN
     // 16-column slots (group g uses slot g % poolN); the epilogue adds D0A + D0B.  split = first K step of the second part.
     int poolN = 0, split = 0;
+    int aSlots = 2;                      // stages of the TMEM operand ring (2 or 4): columns 512 - 32*aSlots .. 511
     std::vector<uint8_t> W;              // fp16 weight tiles [2 K chunks][32 rows: 16 x w0, 16 x w1*2048][8], schedule order
 };
 struct UmmaDev {
@@ -158,6 +182,7 @@ struct UmmaDev {
     uint8_t gStart[kUmmaMaxBlocks][kUmmaMaxGroups] = {}, gSteps[kUmmaMaxBlocks][kUmmaMaxGroups] = {};
     uint16_t gTile[kUmmaMaxBlocks][kUmmaMaxGroups] = {};
     int poolN = 0, split = 0;
+    int aSlots = 2;
     const uint8_t* W = nullptr;
 };
 bool build_umma(int kind, const float* sinc_table, long long p, long long q, int NB, int GBL, UmmaHost* out);

@@ -502,7 +502,7 @@ int f9_context::get_umma(int kind, long long p, long long q, int NB, int GBL, Um
     UmmaDev D; D.p = H.p; D.q = H.q; D.taps = H.taps; D.NB = H.NB; D.G = H.G; D.GBL = H.GBL; D.nGB = H.nGB; D.maxEntries = H.maxEntries; D.maxNK = H.maxNK;
     for (int b = 0; b < kUmmaMaxBlocks; ++b) D.blk[b] = H.blk[b];
     std::memcpy(D.gStart, H.gStart, sizeof(D.gStart)); std::memcpy(D.gSteps, H.gSteps, sizeof(D.gSteps)); std::memcpy(D.gTile, H.gTile, sizeof(D.gTile));
-    D.poolN = H.poolN; D.split = H.split;
+    D.poolN = H.poolN; D.split = H.split; D.aSlots = H.aSlots;
     uint8_t* dW = nullptr;
     F9_TRY_CUDA(this, cudaMalloc((void**) &dW, H.W.size()));
     F9_TRY_CUDA(this, cudaMemcpy(dW, H.W.data(), H.W.size(), cudaMemcpyHostToDevice));

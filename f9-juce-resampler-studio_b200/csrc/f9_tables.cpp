@@ -300,8 +300,8 @@ void group_geom(long long p, long long q, int taps, int NB, int g, GroupGeom* ou
     out->ksteps = (int) ((wend - out->t0 + 15) / 16);
     out->wend = wend;
 }
-int umma_pool_slots(int NB, int GBL) {                     // accumulator-split pool: power of two, NB columns per slot
-    const int spare = 448 - GBL * 2 * NB;                  // TMEM columns 448..511 hold the operand ring
+int umma_pool_slots(int NB, int GBL, int accCols) {        // accumulator-split pool: power of two, NB columns per slot
+    const int spare = accCols - GBL * 2 * NB;              // the columns above accCols hold the operand ring
     int n = 0;
     for (int c = 8; c >= 2; c /= 2) if (c * NB <= spare) { n = c; break; }
     return n;
@@ -314,8 +314,8 @@ size_t umma_smem_bytes(int maxEntries, int NB, int stages, bool tma) {
     // register loader: converted stages (fp16 head + tail, padded K chunks); TMA feed: raw fp32 boxes of 128 rows x 128 B,
     // 1024-byte aligned for the 128-byte swizzle
     const size_t ring = tma ? (size_t) stages * 16384 + 1024 : (size_t) stages * 8 * (128 * 16 + 32);
-    const size_t epi = 128 * 20 * 4;
-    const size_t bars = (size_t) (2 * stages + 2 * kUmmaMaxGroups + 4) * 8 + 16;
+    const size_t epi = 128 * 20 * 4 + (size_t) maxEntries * 16;                // transpose buffer + the issue lists (UmmaOp)
+    const size_t bars = (size_t) (2 * stages + 2 * kUmmaMaxGroups + 8) * 8 + 16;
     return w + ring + epi + bars + 128;                    // + alignment slack
 }
 
@@ -373,7 +373,7 @@ bool build_umma(int kind, const float* sinc_table, long long p, long long q, int
     const int taps = interp_memory(kind);
     if (NB != 16 && NB != 32) return false;
     const int G = (int) ((q + NB - 1) / NB);
-    if (GBL < 1 || GBL * 2 * NB > 448) return false;
+    if (GBL < 1 || GBL > kUmmaMaxGroups || GBL * 2 * NB > 448) return false;
     const int nGB = (G + GBL - 1) / GBL;
     if (nGB > kUmmaMaxBlocks) return false;
     *out = UmmaHost();
@@ -381,8 +381,13 @@ bool build_umma(int kind, const float* sinc_table, long long p, long long q, int
     const int tileBytes = NB * 64, chunkBytes = NB * 32;
     // accumulation split: only for long windows; the split step is the same for every group (first step past every slot's
     // centre tap), which keeps "past the split" a bottom-end range of the active groups.
-    int poolN = umma_pool_slots(NB, GBL), split = 0;
-    if (taps >= 64 && poolN > 0) {
+    // TMEM budget: 512 columns = accumulators (2*NB per group) + pool + operand ring (32 columns per stage).  A ring of four
+    // stages (accumulators + pool <= 384 columns) decouples the converters from the MMAs; plans whose pool needs the room
+    // (groups that overlap a lot in time, e.g. upsampling) keep the two-stage ring.
+    int split = 0;
+    auto pool_for = [&](int accCols) {
+        int poolN = umma_pool_slots(NB, GBL, accCols); split = 0;
+        if (taps < 64 || poolN == 0) return 0;
         for (int g = 0; g < G; ++g) {
             GroupGeom gg; group_geom(p, q, taps, NB, g, &gg);
             const long long k1 = std::min<long long>(q, (long long) NB * g + NB) - 1;
@@ -398,8 +403,16 @@ bool build_umma(int kind, const float* sinc_table, long long p, long long q, int
                 if (gg.t0 / 16 + split < gp.t0 / 16 + gp.ksteps) poolN = 0;                 // this group crosses its split
             }
         }
-    } else poolN = 0;
+        return poolN;
+    };
+    int aSlots = 2, poolN = pool_for(448);
+    if (GBL * 2 * NB <= 384) {
+        const int splitWide = split, poolNarrow = pool_for(384);
+        if ((poolN == 0) == (poolNarrow == 0)) { aSlots = 4; poolN = poolNarrow; }
+        else split = splitWide;
+    }
     if (poolN == 0) split = 0;
+    out->aSlots = aSlots;
     out->poolN = poolN; out->split = split;
     std::vector<float> w((size_t) taps);
     for (int b = 0; b < nGB; ++b) {
@@ -466,6 +479,47 @@ bool build_umma(int kind, const float* sinc_table, long long p, long long q, int
         out->maxEntries = std::max(out->maxEntries, entries);
         out->maxNK = std::max(out->maxNK, BI.nK);
     }
+    // issue lists: per block, per issuing warp, the (stage, group, K step) entries in the order the warp walks them
+    for (int b = 0; b < nGB; ++b) {
+        UmmaBlockInfo& BI = out->blk[b];
+        BI.opOff = (int) out->W.size();
+        int count = 0;
+        for (int w = 0; w < kUmmaIssuers; ++w) {
+            BI.opStart[w] = count;
+            for (int st = 0; st < BI.nStages; ++st)
+                for (int gl = w; gl < BI.nGroups; gl += kUmmaIssuers)
+                    for (int h = 0; h < 2; ++h) {
+                        const int g0 = out->gStart[b][gl], gn = out->gSteps[b][gl];
+                        const int j = 2 * st + h - g0;
+                        if (j < 0 || j >= gn) continue;
+                        UmmaOp op; std::memset(&op, 0, sizeof op);
+                        op.d1Col = (uint16_t) ((2 * gl + 1) * NB);
+                        op.bOff = (uint32_t) (out->gTile[b][gl] + j) * 4u * (uint32_t) NB;
+                        op.stage = (uint8_t) st; op.h = (uint8_t) h; op.gl = (uint8_t) gl;
+                        uint8_t f = 0;
+                        if (j > 0) f |= kOpAcc;
+                        if (j == 0) f |= kOpWaitDrain;
+                        if (j == gn - 1) f |= kOpLast;
+                        if (poolN == 0 || j < split) f |= kOpMerged;
+                        else {
+                            op.poolCol = (uint16_t) (GBL * 2 * NB + (gl & (poolN - 1)) * NB);
+                            if (j > split) f |= kOpPoolAcc;
+                            if (j == split) {
+                                f |= kOpWaitPool;
+                                if (gl >= poolN) op.waitGl = (uint8_t) (gl - poolN);                  // same tile
+                                else { int lu = gl; while (lu + poolN < BI.nGroups) lu += poolN; op.waitGl = (uint8_t) lu; f |= kOpPoolPrevTile; }
+                            }
+                        }
+                        op.flags = f;
+                        const size_t at = out->W.size();
+                        out->W.resize(at + sizeof op);
+                        std::memcpy(&out->W[at], &op, sizeof op);
+                        ++count;
+                    }
+        }
+        BI.opStart[kUmmaIssuers] = count;
+        if (count != BI.nEntries) return false;
+    }
     return true;
 }
 
@@ -521,6 +575,7 @@ extern "C" double f9_umma_selfcheck(int kind, long long p, long long q, int* inf
     if (info) {
         info[0] = (int) m; info[1] = NB; info[2] = H.G; info[3] = H.GBL; info[4] = H.nGB; info[5] = H.poolN; info[6] = H.split;
         info[7] = (int) umma_smem_bytes(H.maxEntries, NB, 2);
+        info[0] |= H.aSlots << 16;                          // operand ring depth in the high half of info[0]
     }
     return maxErr;
 }

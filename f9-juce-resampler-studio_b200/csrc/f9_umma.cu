@@ -40,11 +40,15 @@ constexpr int kRows = 128;                       // periods per tile = MMA M
 constexpr int kChunk = kRows * 16 + 32;          // bytes between K chunks (8 samples) of the X operand: 128 rows x 16 B + pad
 constexpr int kStageBytes = 8 * kChunk;          // one stage = 32 samples: chunks 0-3 head (x0), 4-7 tail (x1)
 constexpr int kEpiPitch = 20;                    // floats per row of the epilogue transpose buffer (16 + 4)
-constexpr int kACol = 448;                       // TMEM columns 448..511: ring of 4 K steps x (8 head + 8 tail)
+constexpr int kASlotsMax = 4;                    // TMEM operand ring: up to 4 slots of one stage (2 K steps x (8 head + 8 tail) columns)
+                                                 // in the top columns (UmmaDev::aSlots: 2 or 4, chosen with the plan)
 constexpr int kLoaderWarps = 8;
-constexpr int kIssuers = 3;                      // MMA-issuing warps (groups are dealt round-robin)
+constexpr int kIssuers = kUmmaIssuers;            // MMA-issuing warps (groups are dealt round-robin)
 constexpr int kFirstLoader = 4 + 1 + kIssuers;   // warps 0-3 epilogue, 4 copy, 5..7 issue, 8..15 load
+constexpr int kConvWarps = 16;                   // TMA feed: converter warps (a quarter of the rows x half a K step each)
 constexpr int kThreads = (kFirstLoader + kLoaderWarps) * 32;
+constexpr int kThreadsTma = (kFirstLoader + kConvWarps) * 32;
+constexpr uint32_t kParkNs = 1000;                // suspend-time hint of the TMA roles' barrier waits (a hot poll loop cost 40 % of the issue slots)
 constexpr int kSpin = 1 << 26;                   // bounded waits: a protocol bug must not hang the GPU
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
@@ -134,7 +138,7 @@ __device__ __forceinline__ float load_in(const Seg& S, long long l) {          /
 }
 
 struct SmemMap {
-    uint8_t* W; uint8_t* ring; float* epi;
+    uint8_t* W; uint8_t* ring; float* epi; uint4* ops;
     uint64_t *full, *empty, *accFull, *accEmpty, *cpDone, *slotFree; uint32_t* tmemSlot;
 };
 constexpr int kTmaStageBytes = kRows * 128;         // TMA feed: one stage = a box of 128 rows x 32 floats, 128-byte swizzle
@@ -144,13 +148,14 @@ __device__ __forceinline__ SmemMap carve(uint8_t* smem, int maxEntries, int NB, 
     m.ring = m.W + (size_t) maxEntries * NB * 64;
     if (tma) m.ring += (1024u - (smem_u32(m.ring) & 1023u)) & 1023u;          // swizzle atoms are 1024 bytes
     m.epi = reinterpret_cast<float*>(m.ring + (size_t) stages * (tma ? kTmaStageBytes : kStageBytes));
-    m.full = reinterpret_cast<uint64_t*>(m.epi + kRows * kEpiPitch);
+    m.ops = reinterpret_cast<uint4*>(m.epi + kRows * kEpiPitch);
+    m.full = reinterpret_cast<uint64_t*>(m.ops + maxEntries);
     m.empty = m.full + stages;
     m.accFull = m.empty + stages;
     m.accEmpty = m.accFull + kUmmaMaxGroups;
     m.cpDone = m.accEmpty + kUmmaMaxGroups;
-    m.slotFree = m.cpDone + 2;
-    m.tmemSlot = reinterpret_cast<uint32_t*>(m.slotFree + 2);
+    m.slotFree = m.cpDone + kASlotsMax;
+    m.tmemSlot = reinterpret_cast<uint32_t*>(m.slotFree + kASlotsMax);
     return m;
 }
 
@@ -321,12 +326,11 @@ template <typename T> __device__ __forceinline__ T* ldg_ptr(T* const* p) {
 __device__ __forceinline__ int4 ld_rec_tail(const UmmaTileRec* r) { return __ldg(reinterpret_cast<const int4*>(&r->x0)); }   // x0, mapIdx
 
 struct FeedArgs {
-    const UmmaTileRec* recs; int p, nStages, stages, myTiles;
-    uint8_t* ring; uint64_t *full, *empty, *aReady, *slotFree; unsigned* ovf; long long* prof;
+    const UmmaTileRec* recs; int p, nStages, stages, myTiles, aCol, aMask, aShift;
+    uint8_t* ring; uint64_t *full, *empty, *aReady, *slotFree; unsigned* ovf;
 };
 __device__ __forceinline__ void producer_role(const FeedArgs& A, const UmmaTma& TM) {
     int sIdx = 0; uint32_t sPh = 0;
-    long long pW = 0; const long long pT0 = A.prof ? clock64() : 0;
     const uint32_t ring0 = smem_u32(A.ring);
     const uint32_t tileBytes = (uint32_t) (((kRows - 1) * A.p + A.nStages * 32) * 4);
     const uint32_t pfChunk = (tileBytes / (uint32_t) A.nStages + 15u) & ~15u;
@@ -345,8 +349,7 @@ __device__ __forceinline__ void producer_role(const FeedArgs& A, const UmmaTma& 
         } else {
             const CUtensorMap* map = &TM.maps[cur.y];
             for (int st = 0; st < A.nStages; ++st) {
-                if (A.prof) { const long long w = clock64(); mbar_wait(A.empty + sIdx, sPh ^ 1); pW += clock64() - w; }
-                else mbar_wait(A.empty + sIdx, sPh ^ 1);
+                mbar_wait_parked(A.empty + sIdx, sPh ^ 1, kParkNs);
                 mbar_expect_tx(A.full + sIdx, (uint32_t) kTmaStageBytes);
                 tma_load_2d(ring0 + (uint32_t) (sIdx * kTmaStageBytes), map, cur.x + st * 32, 0, A.full + sIdx);
                 if (pf) l2_prefetch(pf + (size_t) st * pfChunk, pfChunk);
@@ -355,18 +358,17 @@ __device__ __forceinline__ void producer_role(const FeedArgs& A, const UmmaTma& 
         }
         cur = nxt;
     }
-    if (A.prof) { A.prof[blockIdx.x * 16 + 2] = clock64() - pT0; A.prof[blockIdx.x * 16 + 3] = pW; }
 }
 
 __device__ __forceinline__ void converter_role(const FeedArgs& A, uint32_t tmem, int cw, int lane) {
-    const int quarter = cw & 3, h = cw >> 2;                   // TMEM lane quarter (= warp id % 4), K step of the stage
+    const int quarter = cw & 3, h = cw >> 3, half = (cw >> 2) & 1;   // TMEM lane quarter (= warp id % 4), K step of the stage, its 8-sample half
     const int rho = quarter * 32 + lane;                       // period row = TMEM lane = row of the box
-    const uint32_t tdst = tmem + ((uint32_t) (quarter * 32) << 16) + (uint32_t) (kACol + h * 16);
+    const uint32_t tdst = tmem + ((uint32_t) (quarter * 32) << 16) + (uint32_t) (A.aCol + h * 16 + half * 4);
     const uint32_t ringRow = smem_u32(A.ring) + (uint32_t) (rho * 128);
     const uint32_t sw = (uint32_t) (rho & 7);
     __half2 hmax = __floats2half2_rn(0.f, 0.f);
+    const int aMask = A.aMask, aShift = A.aShift;
     int sIdx = 0; uint32_t sPh = 0; int gs = 0;
-    long long pW0 = 0, pW1 = 0, pS = 0; const long long pT0 = A.prof ? clock64() : 0;
     struct TileIn { const float* in; long long l00, inAvail; bool viaTma; };
     auto load_rec = [&](const UmmaTileRec* r) {
         TileIn T; T.in = ldg_ptr(&r->in); T.l00 = __ldg(&r->l00); T.inAvail = __ldg(&r->inAvail); T.viaTma = __ldg(&r->mapIdx) >= 0; return T;
@@ -377,20 +379,19 @@ __device__ __forceinline__ void converter_role(const FeedArgs& A, uint32_t tmem,
     for (int t = 0; t < A.myTiles; ++t, rec += gridDim.x) {
         T = N;
         if (t + 1 < A.myTiles) N = load_rec(rec + gridDim.x);                  // consumed one tile later
-        const long long lrow = T.l00 + (long long) rho * A.p + h * 16;
+        const long long lrow = T.l00 + (long long) rho * A.p + h * 16 + half * 8;
         for (int st = 0; st < A.nStages; ++st, ++gs) {
-            float4 v[4];
+            float4 v[2];
             if (T.viaTma) {
-                if (A.prof) { const long long w = clock64(); mbar_wait(A.full + sIdx, sPh); pW0 += clock64() - w; }
-                else mbar_wait(A.full + sIdx, sPh);
+                mbar_wait_parked(A.full + sIdx, sPh, kParkNs);
                 const uint32_t a = ringRow + (uint32_t) (sIdx * kTmaStageBytes);
                 #pragma unroll
-                for (int c = 0; c < 4; ++c)
+                for (int c = 0; c < 2; ++c)
                     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[c].x), "=f"(v[c].y), "=f"(v[c].z), "=f"(v[c].w)
-                                 : "r"(a + ((((uint32_t) (4 * h + c)) ^ sw) << 4)) : "memory");
+                                 : "r"(a + ((((uint32_t) (4 * h + 2 * half + c)) ^ sw) << 4)) : "memory");
             } else {
                 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
+                for (int c = 0; c < 2; ++c) {
                     const long long l = lrow + st * 32 + 4 * c;
                     const float* ptr = T.in + l;
                     if (l >= 0 && l + 3 < T.inAvail) v[c] = __ldg(reinterpret_cast<const float4*>(ptr));
@@ -400,9 +401,9 @@ __device__ __forceinline__ void converter_role(const FeedArgs& A, uint32_t tmem,
                     }
                 }
             }
-            uint32_t hd[8], tl[8];
+            uint32_t hd[4], tl[4];
             #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < 2; ++c) {
                 float4 xv = v[c];
                 xv.x *= kPreScale; xv.y *= kPreScale; xv.z *= kPreScale; xv.w *= kPreScale;
                 const __half2 h01 = __floats2half2_rn(xv.x, xv.y), h23 = __floats2half2_rn(xv.z, xv.w);
@@ -418,25 +419,19 @@ __device__ __forceinline__ void converter_role(const FeedArgs& A, uint32_t tmem,
                 if (lane == 0) mbar_arrive(A.empty + sIdx);
                 if (++sIdx == A.stages) { sIdx = 0; sPh ^= 1; }
             }
-            if (gs >= 2) {                                     // MMAs of stage gs - 2 have read the slot
-                if (A.prof) { const long long w = clock64(); mbar_wait(A.slotFree + (gs & 1), (uint32_t) (((gs >> 1) - 1) & 1)); pW1 += clock64() - w; }
-                else mbar_wait(A.slotFree + (gs & 1), (uint32_t) (((gs >> 1) - 1) & 1));
-            }
+            if (gs > aMask) mbar_wait_parked(A.slotFree + (gs & aMask), (uint32_t) (((gs >> aShift) - 1) & 1), kParkNs);   // the MMAs of the slot's previous stage are done
             tc_fence_after();
-            const long long pS0 = A.prof ? clock64() : 0;
-            asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
-                         :: "r"(tdst + (uint32_t) ((gs & 1) * 32)), "r"(hd[0]), "r"(hd[1]), "r"(hd[2]), "r"(hd[3]), "r"(hd[4]), "r"(hd[5]), "r"(hd[6]), "r"(hd[7]),
-                            "r"(tl[0]), "r"(tl[1]), "r"(tl[2]), "r"(tl[3]), "r"(tl[4]), "r"(tl[5]), "r"(tl[6]), "r"(tl[7]) : "memory");
+            const uint32_t td = tdst + (uint32_t) ((gs & aMask) * 32);          // head columns; the tail sits 8 columns up
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" :: "r"(td), "r"(hd[0]), "r"(hd[1]), "r"(hd[2]), "r"(hd[3]) : "memory");
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" :: "r"(td + 8), "r"(tl[0]), "r"(tl[1]), "r"(tl[2]), "r"(tl[3]) : "memory");
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(A.aReady + (gs & 1));
-            if (A.prof) pS += clock64() - pS0;
+            if (lane == 0) mbar_arrive(A.aReady + (gs & aMask));
         }
     }
     const float2 hm = __half22float2(hmax);
     if (!(hm.x < 32768.0f) || !(hm.y < 32768.0f)) atomicOr(A.ovf, 1u);
-    if (A.prof && cw == 0 && lane == 0) { A.prof[blockIdx.x * 16 + 0] = clock64() - pT0; A.prof[blockIdx.x * 16 + 1] = pW0; A.prof[blockIdx.x * 16 + 8] = pW1; A.prof[blockIdx.x * 16 + 9] = pS; }
 }
 
 // out = (D0A + D0B + D1 / 2048) / kPreScale: the scalings are powers of two, the only roundings are the two additions
@@ -445,13 +440,14 @@ __device__ __forceinline__ float combine(uint32_t d0a, uint32_t d0b, uint32_t d1
 }
 
 template <bool MERGED, bool TMA>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(TMA ? kThreadsTma : kThreads, 1)
 umma_fir_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix, int nSegs, int nTiles,
                 const __grid_constant__ UmmaDev P, const __grid_constant__ UmmaTma TM, const UmmaTileRec* __restrict__ recs, int stages, int alignedAll,
                 unsigned* __restrict__ ovf, long long* __restrict__ prof, int dbg) {
     extern __shared__ __align__(128) uint8_t smem[];
     const SmemMap sm = carve(smem, P.maxEntries, P.NB, stages, TMA);
     const int NB = P.NB;                                       // slots per group: MMA N
+    const int aMask = P.aSlots - 1, aShift = P.aSlots == 4 ? 2 : 1, aCol = 512 - 32 * P.aSlots;   // TMEM operand ring
     const int warp = __shfl_sync(0xffffffffu, (int) (threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int gb = blockIdx.x % P.nGB;
     const UmmaBlockInfo& BI = P.blk[gb];
@@ -463,13 +459,15 @@ umma_fir_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix
     {
         const uint4* src = reinterpret_cast<const uint4*>(P.W + BI.wOff);
         uint4* dst = reinterpret_cast<uint4*>(sm.W);
-        for (int i = threadIdx.x; i < BI.nEntries * NB * 4; i += kThreads) dst[i] = __ldg(src + i);
+        for (int i = threadIdx.x; i < BI.nEntries * NB * 4; i += blockDim.x) dst[i] = __ldg(src + i);
+        const uint4* osrc = reinterpret_cast<const uint4*>(P.W + BI.opOff);
+        for (int i = threadIdx.x; i < BI.nEntries; i += blockDim.x) sm.ops[i] = __ldg(osrc + i);
         if (threadIdx.x == 0) {
             // register loader: full <- 8 loader warps, empty <- the copy warp's commit, cpDone <- its commit
             // TMA feed:        full <- the producer's expect_tx, empty <- 8 converter warps, cpDone ("operand ready") <- 8 converter warps
-            for (int s = 0; s < stages; ++s) { mbar_init(sm.full + s, TMA ? 1 : kLoaderWarps); mbar_init(sm.empty + s, TMA ? kLoaderWarps : 1); }
+            for (int s = 0; s < stages; ++s) { mbar_init(sm.full + s, TMA ? 1 : kLoaderWarps); mbar_init(sm.empty + s, TMA ? kConvWarps : 1); }
             for (int g = 0; g < kUmmaMaxGroups; ++g) { mbar_init(sm.accFull + g, 1); mbar_init(sm.accEmpty + g, 4); }
-            for (int i = 0; i < 2; ++i) { mbar_init(sm.cpDone + i, TMA ? kLoaderWarps : 1); mbar_init(sm.slotFree + i, kIssuers); }
+            for (int i = 0; i < kASlotsMax; ++i) { mbar_init(sm.cpDone + i, TMA ? kConvWarps : 1); mbar_init(sm.slotFree + i, kIssuers); }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         if (warp == 4) {
@@ -486,16 +484,16 @@ umma_fir_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix
     // total, [3] its wait on "stage full", [4] its wait on "accumulator drained", [5] epilogue-warp-0 total, [6] its wait on
     // "group done", [7] its time in the store loops
     long long pT0 = 0, pW0 = 0, pW1 = 0, pW2 = 0, pF = 0, pC = 0, pM = 0, pI = 0;
-    #define PROF_BEGIN(v) long long v = prof ? clock64() : 0
-    #define PROF_END(acc, v) if (prof) acc += clock64() - v
-    if (prof) pT0 = clock64();
+    #define PROF_BEGIN(v) long long v = (!TMA && prof) ? clock64() : 0
+    #define PROF_END(acc, v) if (!TMA && prof) acc += clock64() - v
+    if (!TMA && prof) pT0 = clock64();
 
     if (TMA && (warp >= kFirstLoader || warp == 4)) {
         // =========================================================== TMA producer / converters
         FeedArgs FA;
-        FA.recs = recs; FA.p = p;
+        FA.recs = recs; FA.p = p; FA.aCol = aCol; FA.aMask = aMask; FA.aShift = aShift;
         FA.nStages = nStages; FA.stages = stages; FA.myTiles = myTiles;
-        FA.ring = sm.ring; FA.full = sm.full; FA.empty = sm.empty; FA.aReady = sm.cpDone; FA.slotFree = sm.slotFree; FA.ovf = ovf; FA.prof = prof;
+        FA.ring = sm.ring; FA.full = sm.full; FA.empty = sm.empty; FA.aReady = sm.cpDone; FA.slotFree = sm.slotFree; FA.ovf = ovf;
         if (warp == 4) { if (lane == 0) producer_role(FA, TM); }
         else converter_role(FA, tmem, warp - kFirstLoader, lane);
     } else if (warp >= kFirstLoader) {
@@ -521,12 +519,12 @@ umma_fir_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix
             PROF_BEGIN(wf);
             fence_async_smem();                                // generic-proxy stores of the loaders -> async-proxy reads of tcgen05.cp
             PROF_END(pF, wf);
-            if (gs >= 2) { PROF_BEGIN(w); mbar_wait(sm.slotFree + (gs & 1), (uint32_t) (((gs >> 1) - 1) & 1)); PROF_END(pW1, w); }
+            if (gs > aMask) { PROF_BEGIN(w); mbar_wait(sm.slotFree + (gs & aMask), (uint32_t) (((gs >> aShift) - 1) & 1)); PROF_END(pW1, w); }
             tc_fence_after();
             PROF_BEGIN(wc);
             if (el) {
                 const uint64_t ad = aDesc0 + (uint64_t) ((sIdx * kStageBytes) >> 4);
-                const uint32_t slot0 = tmem + kACol + (uint32_t) ((gs & 1) * 32);
+                const uint32_t slot0 = tmem + (uint32_t) aCol + (uint32_t) ((gs & aMask) * 32);
                 if (!(dbg & 2)) {
                 umma_cp(slot0, ad);                                             // first K step  head
                 umma_cp(slot0 + 8, ad + ((4 * kChunk) >> 4));                   //               tail
@@ -534,7 +532,7 @@ umma_fir_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix
                 umma_cp(slot0 + 24, ad + ((6 * kChunk) >> 4));                  //               tail
                 }
                 umma_commit(sm.empty + sIdx);                  // the stage is free once the copies have read it
-                umma_commit(sm.cpDone + (gs & 1));
+                umma_commit(sm.cpDone + (gs & aMask));
             }
             __syncwarp();
             PROF_END(pC, wc);
@@ -550,67 +548,49 @@ umma_fir_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix
         const uint32_t el = elect_one();
         const uint32_t nb = (uint32_t) NB;
         const uint32_t idescN = make_idesc(kRows, NB), idesc2N = make_idesc(kRows, 2 * NB);
-        const uint32_t poolCol = (uint32_t) (P.GBL * 2 * NB), poolMask = (uint32_t) (P.poolN > 0 ? P.poolN - 1 : 0);
         const uint64_t wDesc0 = make_desc(smem_u32(sm.W), 32 * NB, 128);       // weight tile i: + 4*NB*i (16-byte units); w1 rows at + NB
-        const int split = P.poolN > 0 ? P.split : 0x7fffffff;
-        // schedule of the groups this warp owns, read once (the kernel parameters are constant-bank loads: in the issue loop
-        // they sat on the dependency chain in front of every MMA)
-        constexpr int kMaxOwn = (kUmmaMaxGroups + kIssuers - 1) / kIssuers;
-        int gG0[kMaxOwn], gGn[kMaxOwn]; uint32_t gBd[kMaxOwn];
-        #pragma unroll
-        for (int i = 0; i < kMaxOwn; ++i) {
-            const int gl = w + i * kIssuers;
-            const bool own = gl < BI.nGroups;
-            gG0[i] = own ? (int) P.gStart[gb][gl] : 0; gGn[i] = own ? (int) P.gSteps[gb][gl] : 0;
-            gBd[i] = own ? (uint32_t) P.gTile[gb][gl] * 4u * nb : 0u;
-        }
-        const int nGroups = BI.nGroups;
+        // The warp walks its host-built list (UmmaOp, shared memory) once per tile: one 128-bit load per (group, K step), fetched
+        // an entry ahead, decoded with a handful of bit operations.  (Decoding the schedule from the kernel parameters put
+        // constant-bank loads and a long branchy chain in front of every MMA: ~175 clk per entry.)
+        const uint4* ops = sm.ops + BI.opStart[w];
+        const int nOps = BI.opStart[w + 1] - BI.opStart[w];
+        const uint32_t wLo = (uint32_t) (wDesc0 & 0xffffffffull), wHi = (uint32_t) (wDesc0 >> 32);
         int gs = 0;
         for (int t = 0; t < myTiles; ++t) {
+            int k = 0;
+            uint4 nx = nOps > 0 ? ops[0] : make_uint4(0, 0, 0xff, 0);
             for (int st = 0; st < nStages; ++st, ++gs) {
-                { PROF_BEGIN(wq); mbar_wait(sm.cpDone + (gs & 1), (uint32_t) ((gs >> 1) & 1)); PROF_END(pW0, wq); }
+                { PROF_BEGIN(wq); if (TMA) mbar_wait_parked(sm.cpDone + (gs & aMask), (uint32_t) ((gs >> aShift) & 1), kParkNs); else mbar_wait(sm.cpDone + (gs & aMask), (uint32_t) ((gs >> aShift) & 1)); PROF_END(pW0, wq); }
                 tc_fence_after();
                 PROF_BEGIN(wi);
-                const uint32_t aSlot = tmem + kACol + (uint32_t) ((gs & 1) * 32);
-                #pragma unroll
-                for (int i = 0; i < kMaxOwn; ++i) {
-                    const int gl = w + i * kIssuers;
-                    const int g0 = gG0[i], gn = gGn[i];
-                    if (2 * st + 1 < g0 || 2 * st >= g0 + gn) continue;           // no K step of this stage inside the group's window (gn = 0: not owned)
-                    #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int j = 2 * st + h - g0;                         // K step inside the group's window
-                        if (j < 0 || j >= gn) continue;
-                        if (j == 0) {                                           // accumulators drained by the epilogue (previous tile)?
-                            PROF_BEGIN(wd); mbar_wait(sm.accEmpty + gl, (t & 1) ^ 1); PROF_END(pW1, wd);
-                            tc_fence_after();
-                        } else if (j == split) {                                // the pool slot's previous user read?
-                            PROF_BEGIN(wd);
-                            if ((uint32_t) gl > poolMask) mbar_wait(sm.accEmpty + (gl - (int) poolMask - 1), t & 1);       // same tile
-                            else {                                                                                  // previous tile
-                                int lu = gl; while (lu + (int) poolMask + 1 < nGroups) lu += (int) poolMask + 1;
-                                mbar_wait(sm.accEmpty + lu, (t & 1) ^ 1);
-                            }
-                            PROF_END(pW1, wd);
-                            tc_fence_after();
+                const uint32_t aSlot = tmem + (uint32_t) aCol + (uint32_t) ((gs & aMask) * 32);
+                while (k < nOps && (int) (nx.z & 0xffu) == st) {
+                    const uint4 o = nx;
+                    ++k;
+                    nx = ops[k < nOps ? k : 0];
+                    const uint32_t d1 = tmem + (o.x & 0xffffu), pool = tmem + (o.x >> 16);
+                    const uint32_t h = (o.z >> 8) & 0xffu, gl = (o.z >> 16) & 0xffu, fl = o.z >> 24, waitGl = o.w & 0xffu;
+                    if (fl & kOpWaitDrain) {                                    // accumulators drained by the epilogue (previous tile)?
+                        PROF_BEGIN(wd); mbar_wait(sm.accEmpty + gl, (t & 1) ^ 1); PROF_END(pW1, wd);
+                        tc_fence_after();
+                    } else if (fl & kOpWaitPool) {                              // the pool slot's previous user read?
+                        PROF_BEGIN(wd); mbar_wait(sm.accEmpty + waitGl, (fl & kOpPoolPrevTile) ? (t & 1) ^ 1 : (t & 1)); PROF_END(pW1, wd);
+                        tc_fence_after();
+                    }
+                    if (el && !(dbg & 1)) {
+                        const uint32_t aHi = aSlot + h * 16u;
+                        const uint64_t bd = ((uint64_t) wHi << 32) | (uint64_t) (wLo + o.y);
+                        if (MERGED || (fl & kOpMerged)) {      // D0 and D1 adjacent: [D0 | D1] (+)= x0 * [w0 | w1] as one N = 2*NB MMA
+                            umma_ts(d1 - nb, aHi, bd, idesc2N, fl & kOpAcc);
+                        } else {                               // past the split: D0 lives in the pool
+                            umma_ts(pool, aHi, bd, idescN, fl & kOpPoolAcc);    // D0B (+)= x0 * w0
+                            umma_ts(d1, aHi, bd + nb, idescN, 1u);              // D1    += x0 * w1
                         }
-                        if (el && !(dbg & 1)) {
-                            const uint32_t aHi = aSlot + (uint32_t) (h * 16);
-                            const uint32_t d1 = tmem + (uint32_t) (2 * gl + 1) * nb;
-                            const uint64_t bd = wDesc0 + (uint64_t) (gBd[i] + (uint32_t) j * 4u * nb);
-                            const uint32_t acc = j > 0 ? 1u : 0u;
-                            if (MERGED || j < split) {         // D0 and D1 adjacent: [D0 | D1] (+)= x0 * [w0 | w1] as one N = 2*NB MMA
-                                umma_ts(d1 - nb, aHi, bd, idesc2N, acc);
-                            } else {                           // past the split: D0 lives in the pool
-                                umma_ts(tmem + poolCol + ((uint32_t) gl & poolMask) * nb, aHi, bd, idescN, j > split ? 1u : 0u);   // D0B (+)= x0 * w0
-                                umma_ts(d1, aHi, bd + nb, idescN, 1u);                                                          // D1    += x0 * w1
-                            }
-                            umma_ts(d1, aHi + 8, bd, idescN, 1u);                                                               // D1    += x1 * w0
-                        }
-                        if (el && j == gn - 1) umma_commit(sm.accFull + gl);
+                        umma_ts(d1, aHi + 8, bd, idescN, 1u);                   // D1    += x1 * w0
+                        if (fl & kOpLast) umma_commit(sm.accFull + gl);
                     }
                 }
-                if (el) umma_commit(sm.slotFree + (gs & 1));   // arrives once this warp's MMAs on the slot have completed
+                if (el) umma_commit(sm.slotFree + (gs & aMask));   // arrives once this warp's MMAs on the slot have completed
                 __syncwarp();
                 PROF_END(pI, wi);
             }
@@ -682,9 +662,12 @@ umma_fir_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix
                     const long long o0 = oBase + (long long) (warp * 32 + rsel) * q + col;
                     float* dstp = outG + o0;
                     if (dbg & 4) {} else if (rowsInside && gl * NB + h * 16 + 16 <= blockSlots) {
-                        #pragma unroll 8
+                        float ov[16];                          // all loads first: a volatile store after each load serialised them
+                        #pragma unroll
+                        for (int r = 0; r < 16; ++r) ov[r] = src[r * 2 * kEpiPitch];
+                        #pragma unroll
                         for (int r = 0; r < 16; ++r, dstp += 2 * q)
-                            asm volatile("st.global.cs.f32 [%0], %1;" :: "l"(dstp), "f"(src[r * 2 * kEpiPitch]) : "memory");
+                            asm volatile("st.global.cs.f32 [%0], %1;" :: "l"(dstp), "f"(ov[r]));
                     } else {
                         const bool slotOk = col < blockSlots;
                         for (int r = 0; r < 16; ++r, dstp += 2 * q) {
@@ -812,7 +795,7 @@ cudaError_t launch_umma(const ResampleLaunch& L, cudaStream_t s, long long* laun
     const bool doProf = profEnv != nullptr && prof_calls++ == atoi(profEnv);
     if (doProf) { cudaMalloc((void**) &d_prof, sizeof(long long) * 16 * grid); cudaMemsetAsync(d_prof, 0, sizeof(long long) * 16 * grid, s); }
     const int dbg = getenv("F9_UMMA_DBG") ? atoi(getenv("F9_UMMA_DBG")) : 0;     // development: 1 skip MMAs, 2 skip copies, 4 skip stores
-    #define F9_UMMA_LAUNCH(MERGED, TMA) umma_fir_kernel<MERGED, TMA><<<grid, kThreads, L.um_smem, s>>>(L.d_segs, L.d_tile_prefix, L.n_segs, L.n_tiles, \
+    #define F9_UMMA_LAUNCH(MERGED, TMA) umma_fir_kernel<MERGED, TMA><<<grid, TMA ? kThreadsTma : kThreads, L.um_smem, s>>>(L.d_segs, L.d_tile_prefix, L.n_segs, L.n_tiles, \
         L.um, L.um_maps, L.d_tile_recs, L.um_stages, L.um_aligned ? 1 : 0, L.d_ovf, doProf ? d_prof : nullptr, dbg)
     if (L.um_tma) {
         if (!L.d_tile_recs) return cudaErrorInvalidValue;
