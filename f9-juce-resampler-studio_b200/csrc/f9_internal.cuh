@@ -159,6 +159,8 @@ struct UmmaBlockInfo {
     int wOff;          // byte offset into W
     int opOff;         // byte offset into W of the block's UmmaOp lists (nEntries records, warp 0's first)
     int opStart[kUmmaIssuers + 1];   // record range of each issuing warp
+    int w2Off[2];      // CTA-pair kernel (NB = 32, one block): byte offset into W of the weight halves of cluster rank 0 / 1:
+                       // per tile [2 K chunks][16 x w0, 16 x w1*2048 of slots 16*rank ..][8] = 1 KB; -1: not built
 };
 struct UmmaHost {
     int p = 0, q = 0, taps = 0, NB = 16, G = 0, GBL = 0, nGB = 0;
@@ -186,7 +188,7 @@ struct UmmaDev {
     const uint8_t* W = nullptr;
 };
 bool build_umma(int kind, const float* sinc_table, long long p, long long q, int NB, int GBL, UmmaHost* out);
-size_t umma_smem_bytes(int maxEntries, int NB, int stages, bool tma = false);
+size_t umma_smem_bytes(int maxEntries, int NB, int stages, bool tma = false, bool cta2 = false);
 // TMA feed of the tensor-core FIR: the input rows of a tile (128 periods, p floats apart, 32 samples per stage) are one box of a
 // rank-2 tensor map whose row stride is p floats, i.e. the rows overlap in memory.  One map covers 4 GiB from its base (box
 // coordinates are 32-bit element indices); a launch carries up to kUmmaMaxMaps maps, 4 GiB apart, from the lowest input address.
@@ -219,6 +221,7 @@ struct ResampleLaunch {
     int um_stages = 0; size_t um_smem = 0;
     bool um_aligned = false;       // every row piece of every segment starts on 16 bytes (set by resample_build_tiles)
     bool um_tma = false;           // aligned and the tensor maps were encoded: TMA feed (set by resample_build_tiles)
+    bool um_cta2 = false;          // ... and the plan suits CTA pairs (tcgen05.mma.cta_group::2: each CTA holds half of every weight tile)
     UmmaTma um_maps;
     UmmaTileRec* d_tile_recs = nullptr;    // n_tiles records, caller-provided scratch when um_tma (see resample_scratch_bytes)
     unsigned* d_ovf = nullptr;     // device flag: an input sample was outside the fp16 split's range -> fp32 redo
@@ -247,7 +250,7 @@ long long   resample_ctas_for_segment(const ResampleLaunch& L, long long n0, lon
 // Fill tile_prefix (n+1 ints) for the segments; returns the CTA total or -1 on overflow.
 int         resample_build_tiles(ResampleLaunch& L, const Seg* segs, int n, std::vector<int>* prefix);
 // Device scratch the launch needs next to the segment table (set L.d_tile_recs to a buffer of this size; 0 = none)
-inline size_t resample_scratch_bytes(const ResampleLaunch& L, int n_tiles) { return L.umma && L.um_tma ? sizeof(UmmaTileRec) * (size_t) n_tiles : 0; }
+inline size_t resample_scratch_bytes(const ResampleLaunch& L, int n_tiles) { return L.umma && L.um_tma ? sizeof(UmmaTileRec) * ((size_t) n_tiles + 1) : 0; }
 
 }  // namespace f9
 

@@ -430,11 +430,14 @@ int resample_build_tiles(ResampleLaunch& L, const Seg* segs, int n, std::vector<
                 lo = std::min(lo, a); hi = std::max(hi, a + 4ull * (unsigned long long) segs[i].inAvail);
             }
             if (hi > lo && umma_encode_maps(lo, hi, L.um.p, &L.um_maps)) {
+                // CTA pairs halve the weights per SM: worth it when the weights leave a single CTA only a shallow input ring
+                const bool cta2 = L.um.blk[0].w2Off[0] >= 0 && L.sm_count >= 2 && getenv("F9_UMMA_NOCTA2") == nullptr &&
+                                  (umma_smem_bytes(L.um.maxEntries, L.um.NB, 4, true) > 227 * 1024 || getenv("F9_UMMA_CTA2") != nullptr);
                 int stages = 2;
                 const int maxStages = getenv("F9_UMMA_STAGES") ? atoi(getenv("F9_UMMA_STAGES")) : 8;
-                while (stages < maxStages && umma_smem_bytes(L.um.maxEntries, L.um.NB, stages + 1, true) <= 227 * 1024) ++stages;
-                if (umma_smem_bytes(L.um.maxEntries, L.um.NB, stages, true) <= 227 * 1024) {
-                    L.um_tma = true; L.um_stages = stages; L.um_smem = umma_smem_bytes(L.um.maxEntries, L.um.NB, stages, true);
+                while (stages < maxStages && umma_smem_bytes(L.um.maxEntries, L.um.NB, stages + 1, true, cta2) <= 227 * 1024) ++stages;
+                if (umma_smem_bytes(L.um.maxEntries, L.um.NB, stages, true, cta2) <= 227 * 1024) {
+                    L.um_tma = true; L.um_cta2 = cta2; L.um_stages = stages; L.um_smem = umma_smem_bytes(L.um.maxEntries, L.um.NB, stages, true, cta2);
                 }
             }
         }

@@ -309,8 +309,8 @@ int umma_pool_slots(int NB, int GBL, int accCols) {        // accumulator-split 
 
 }  // namespace
 
-size_t umma_smem_bytes(int maxEntries, int NB, int stages, bool tma) {
-    const size_t w = (size_t) maxEntries * NB * 64;        // tile: 2 K chunks x 2*NB rows x 16 B
+size_t umma_smem_bytes(int maxEntries, int NB, int stages, bool tma, bool cta2) {
+    const size_t w = (size_t) maxEntries * NB * (cta2 ? 32 : 64);   // tile: 2 K chunks x 2*NB rows x 16 B (half of the rows per CTA of a pair)
     // register loader: converted stages (fp16 head + tail, padded K chunks); TMA feed: raw fp32 boxes of 128 rows x 128 B,
     // 1024-byte aligned for the 128-byte swizzle
     const size_t ring = tma ? (size_t) stages * 16384 + 1024 : (size_t) stages * 8 * (128 * 16 + 32);
@@ -519,6 +519,24 @@ bool build_umma(int kind, const float* sinc_table, long long p, long long q, int
         }
         BI.opStart[kUmmaIssuers] = count;
         if (count != BI.nEntries) return false;
+    }
+    // CTA-pair kernel: the weight tiles again, split by slot halves (cluster rank r holds slots 16 r .. 16 r + 15 of every group)
+    for (int b = 0; b < nGB; ++b) out->blk[b].w2Off[0] = out->blk[b].w2Off[1] = -1;
+    if (nGB == 1 && NB == 32) {
+        UmmaBlockInfo& BI = out->blk[0];
+        for (int r = 0; r < 2; ++r) {
+            BI.w2Off[r] = (int) out->W.size();
+            out->W.resize(out->W.size() + (size_t) BI.nEntries * 1024, 0);
+            for (int e = 0; e < BI.nEntries; ++e) {
+                const uint8_t* src = out->W.data() + BI.wOff + (size_t) e * tileBytes;
+                uint8_t* dst = out->W.data() + BI.w2Off[r] + (size_t) e * 1024;
+                for (int c = 0; c < 2; ++c)
+                    for (int i = 0; i < 16; ++i) {
+                        std::memcpy(dst + c * 512 + i * 16, src + (size_t) c * chunkBytes + (size_t) (16 * r + i) * 16, 16);
+                        std::memcpy(dst + c * 512 + 256 + i * 16, src + (size_t) c * chunkBytes + (size_t) NB * 16 + (size_t) (16 * r + i) * 16, 16);
+                    }
+            }
+        }
     }
     return true;
 }

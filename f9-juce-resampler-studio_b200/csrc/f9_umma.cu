@@ -115,6 +115,36 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
 __device__ __forceinline__ void l2_prefetch(const void* p, uint32_t bytes) {       // p and bytes multiples of 16
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(p), "r"(bytes) : "memory");
 }
+// ---- CTA pairs (cluster of two): barriers that collect arrivals from both CTAs live in the leader (cluster rank 0)
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// What crosses between the CTAs is TMEM traffic ordered by the tcgen05 fences, not generic memory: the arrive keeps the default
+// (CTA-scope) release.  A cluster-scope release compiled to MEMBAR.ALL.GPU + ERRBAR in front of every arrive: 40 % of all stalls.
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {                 // same offset in the leader's shared memory
+    asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, 0;\n\tmbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+                 :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity, uint32_t ns) {     // acquires the peer CTA's arrivals too
+    #pragma unroll 1
+    for (int i = 0; i < kSpin; ++i) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(ns) : "memory");
+        if (ok) return;
+    }
+    __trap();
+}
+__device__ __forceinline__ void umma2_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                 :: "r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma2_commit_both(uint64_t* bar) {                  // arrives on the barrier at this offset in both CTAs
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 :: "r"(smem_u32(bar)), "h"((uint16_t) 3) : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -142,10 +172,10 @@ struct SmemMap {
     uint64_t *full, *empty, *accFull, *accEmpty, *cpDone, *slotFree; uint32_t* tmemSlot;
 };
 constexpr int kTmaStageBytes = kRows * 128;         // TMA feed: one stage = a box of 128 rows x 32 floats, 128-byte swizzle
-__device__ __forceinline__ SmemMap carve(uint8_t* smem, int maxEntries, int NB, int stages, bool tma) {
+__device__ __forceinline__ SmemMap carve(uint8_t* smem, int maxEntries, int NB, int stages, bool tma, bool cta2) {
     SmemMap m;
     m.W = smem;
-    m.ring = m.W + (size_t) maxEntries * NB * 64;
+    m.ring = m.W + (size_t) maxEntries * NB * (cta2 ? 32 : 64);
     if (tma) m.ring += (1024u - (smem_u32(m.ring) & 1023u)) & 1023u;          // swizzle atoms are 1024 bytes
     m.epi = reinterpret_cast<float*>(m.ring + (size_t) stages * (tma ? kTmaStageBytes : kStageBytes));
     m.ops = reinterpret_cast<uint4*>(m.epi + kRows * kEpiPitch);
@@ -326,7 +356,7 @@ template <typename T> __device__ __forceinline__ T* ldg_ptr(T* const* p) {
 __device__ __forceinline__ int4 ld_rec_tail(const UmmaTileRec* r) { return __ldg(reinterpret_cast<const int4*>(&r->x0)); }   // x0, mapIdx
 
 struct FeedArgs {
-    const UmmaTileRec* recs; int p, nStages, stages, myTiles, aCol, aMask, aShift;
+    const UmmaTileRec* recs; int p, nStages, stages, myTiles, aCol, aMask, aShift; bool pair;
     uint8_t* ring; uint64_t *full, *empty, *aReady, *slotFree; unsigned* ovf;
 };
 __device__ __forceinline__ void producer_role(const FeedArgs& A, const UmmaTma& TM) {
@@ -427,7 +457,7 @@ __device__ __forceinline__ void converter_role(const FeedArgs& A, uint32_t tmem,
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(A.aReady + (gs & aMask));
+            if (lane == 0) { if (A.pair) mbar_arrive_leader(A.aReady + (gs & aMask)); else mbar_arrive(A.aReady + (gs & aMask)); }
         }
     }
     const float2 hm = __half22float2(hmax);
@@ -439,13 +469,18 @@ __device__ __forceinline__ float combine(uint32_t d0a, uint32_t d0b, uint32_t d1
     return fmaf(__uint_as_float(d1), 1.0f / (2048.0f * kPreScale), (__uint_as_float(d0a) + __uint_as_float(d0b)) * (1.0f / kPreScale));
 }
 
-template <bool MERGED, bool TMA>
+// CTA2: two CTAs of a cluster work as a pair (tcgen05.mma.cta_group::2, M = 256): each converts and stores its own tile of 128
+// periods, each holds the weights of half the slots of every group (half the shared memory: the input ring gets 7 stages
+// instead of 2), the leader issues every MMA for both.  Tile t of the pair is recs[blockIdx.x + i * gridDim.x] as before; the
+// table is padded so that the odd CTA's last tile exists (a record without input or output).
+template <bool MERGED, bool TMA, bool CTA2>
 __global__ void __launch_bounds__(TMA ? kThreadsTma : kThreads, 1)
 umma_fir_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix, int nSegs, int nTiles,
                 const __grid_constant__ UmmaDev P, const __grid_constant__ UmmaTma TM, const UmmaTileRec* __restrict__ recs, int stages, int alignedAll,
                 unsigned* __restrict__ ovf, long long* __restrict__ prof, int dbg) {
     extern __shared__ __align__(128) uint8_t smem[];
-    const SmemMap sm = carve(smem, P.maxEntries, P.NB, stages, TMA);
+    const SmemMap sm = carve(smem, P.maxEntries, P.NB, stages, TMA, CTA2);
+    const uint32_t rank = CTA2 ? cluster_rank() : 0u;        // 0: leader (issues the MMAs)
     const int NB = P.NB;                                       // slots per group: MMA N
     const int aMask = P.aSlots - 1, aShift = P.aSlots == 4 ? 2 : 1, aCol = 512 - 32 * P.aSlots;   // TMEM operand ring
     const int warp = __shfl_sync(0xffffffffu, (int) (threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
@@ -453,30 +488,38 @@ umma_fir_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix
     const UmmaBlockInfo& BI = P.blk[gb];
     const int p = P.p, q = P.q;
     const int nStages = BI.nStages;                            // stages per tile (two K steps each)
-    const int myTiles = (int) blockIdx.x < nTiles ? (nTiles - 1 - (int) blockIdx.x) / (int) gridDim.x + 1 : 0;
+    const int firstTile = CTA2 ? (int) (blockIdx.x & ~1u) : (int) blockIdx.x;     // both CTAs of a pair walk the same number of tiles
+    const int myTiles = firstTile < nTiles ? (nTiles - 1 - firstTile) / (int) gridDim.x + 1 : 0;
 
     // ---- one-time setup: weights into shared memory, barriers, TMEM
     {
-        const uint4* src = reinterpret_cast<const uint4*>(P.W + BI.wOff);
+        const uint4* src = reinterpret_cast<const uint4*>(P.W + (CTA2 ? BI.w2Off[rank] : BI.wOff));
         uint4* dst = reinterpret_cast<uint4*>(sm.W);
-        for (int i = threadIdx.x; i < BI.nEntries * NB * 4; i += blockDim.x) dst[i] = __ldg(src + i);
+        for (int i = threadIdx.x; i < BI.nEntries * NB * (CTA2 ? 2 : 4); i += blockDim.x) dst[i] = __ldg(src + i);
         const uint4* osrc = reinterpret_cast<const uint4*>(P.W + BI.opOff);
         for (int i = threadIdx.x; i < BI.nEntries; i += blockDim.x) sm.ops[i] = __ldg(osrc + i);
         if (threadIdx.x == 0) {
             // register loader: full <- 8 loader warps, empty <- the copy warp's commit, cpDone <- its commit
             // TMA feed:        full <- the producer's expect_tx, empty <- 8 converter warps, cpDone ("operand ready") <- 8 converter warps
             for (int s = 0; s < stages; ++s) { mbar_init(sm.full + s, TMA ? 1 : kLoaderWarps); mbar_init(sm.empty + s, TMA ? kConvWarps : 1); }
-            for (int g = 0; g < kUmmaMaxGroups; ++g) { mbar_init(sm.accFull + g, 1); mbar_init(sm.accEmpty + g, 4); }
-            for (int i = 0; i < kASlotsMax; ++i) { mbar_init(sm.cpDone + i, TMA ? kConvWarps : 1); mbar_init(sm.slotFree + i, kIssuers); }
+            // CTA pairs: "operand ready" and "accumulator drained" collect both CTAs' arrivals in the leader
+            for (int g = 0; g < kUmmaMaxGroups; ++g) { mbar_init(sm.accFull + g, 1); mbar_init(sm.accEmpty + g, CTA2 ? 8 : 4); }
+            for (int i = 0; i < kASlotsMax; ++i) { mbar_init(sm.cpDone + i, TMA ? (CTA2 ? 2 : 1) * kConvWarps : 1); mbar_init(sm.slotFree + i, kIssuers); }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         if (warp == 4) {
-            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(sm.tmemSlot)), "r"(512) : "memory");
-            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+            if (CTA2) {
+                asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(sm.tmemSlot)), "r"(512) : "memory");
+                asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+            } else {
+                asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(sm.tmemSlot)), "r"(512) : "memory");
+                asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+            }
         }
         fence_async_smem();                                    // the weights are read by the tensor pipe (async proxy)
         tc_fence_before();
         __syncthreads();
+        if (CTA2) cluster_sync_all();                          // the peer's barriers and weights are ready before anything crosses over
         tc_fence_after();
     }
     const uint32_t tmem = *sm.tmemSlot;
@@ -491,7 +534,7 @@ umma_fir_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix
     if (TMA && (warp >= kFirstLoader || warp == 4)) {
         // =========================================================== TMA producer / converters
         FeedArgs FA;
-        FA.recs = recs; FA.p = p; FA.aCol = aCol; FA.aMask = aMask; FA.aShift = aShift;
+        FA.recs = recs; FA.p = p; FA.aCol = aCol; FA.aMask = aMask; FA.aShift = aShift; FA.pair = CTA2;
         FA.nStages = nStages; FA.stages = stages; FA.myTiles = myTiles;
         FA.ring = sm.ring; FA.full = sm.full; FA.empty = sm.empty; FA.aReady = sm.cpDone; FA.slotFree = sm.slotFree; FA.ovf = ovf;
         if (warp == 4) { if (lane == 0) producer_role(FA, TM); }
@@ -540,15 +583,15 @@ umma_fir_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix
         }
         if (prof && lane == 0) { prof[blockIdx.x * 16 + 8] = pF; prof[blockIdx.x * 16 + 9] = pC; }
         if (prof && lane == 0) { prof[blockIdx.x * 16 + 2] = clock64() - pT0; prof[blockIdx.x * 16 + 3] = pW0; prof[blockIdx.x * 16 + 4] = pW1; }
-    } else if (warp > 4) {
-        // =========================================================== MMA issuers
+    } else if (warp > 4 && (!CTA2 || rank == 0)) {
+        // =========================================================== MMA issuers (CTA pairs: the leader's only)
         // Warp w owns the groups gl = w, w + kIssuers, ...: per group the operands advance by constants from K step to K step
         // (weight tiles are stored group-major), so the issue loop is a few uniform adds around three tcgen05.mma.
         const int w = warp - 5;
         const uint32_t el = elect_one();
         const uint32_t nb = (uint32_t) NB;
-        const uint32_t idescN = make_idesc(kRows, NB), idesc2N = make_idesc(kRows, 2 * NB);
-        const uint64_t wDesc0 = make_desc(smem_u32(sm.W), 32 * NB, 128);       // weight tile i: + 4*NB*i (16-byte units); w1 rows at + NB
+        const uint32_t idescN = make_idesc(CTA2 ? 2 * kRows : kRows, NB), idesc2N = make_idesc(kRows, 2 * NB);
+        const uint64_t wDesc0 = make_desc(smem_u32(sm.W), CTA2 ? 16 * NB : 32 * NB, 128);   // weight tile i: + 4*NB*i (16-byte units; half for pairs); w1 rows at + NB (+ NB/2)
         // The warp walks its host-built list (UmmaOp, shared memory) once per tile: one 128-bit load per (group, K step), fetched
         // an entry ahead, decoded with a handful of bit operations.  (Decoding the schedule from the kernel parameters put
         // constant-bank loads and a long branchy chain in front of every MMA: ~175 clk per entry.)
@@ -560,7 +603,7 @@ umma_fir_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix
             int k = 0;
             uint4 nx = nOps > 0 ? ops[0] : make_uint4(0, 0, 0xff, 0);
             for (int st = 0; st < nStages; ++st, ++gs) {
-                { PROF_BEGIN(wq); if (TMA) mbar_wait_parked(sm.cpDone + (gs & aMask), (uint32_t) ((gs >> aShift) & 1), kParkNs); else mbar_wait(sm.cpDone + (gs & aMask), (uint32_t) ((gs >> aShift) & 1)); PROF_END(pW0, wq); }
+                { PROF_BEGIN(wq); if (CTA2) mbar_wait_cluster(sm.cpDone + (gs & aMask), (uint32_t) ((gs >> aShift) & 1), kParkNs); else if (TMA) mbar_wait_parked(sm.cpDone + (gs & aMask), (uint32_t) ((gs >> aShift) & 1), kParkNs); else mbar_wait(sm.cpDone + (gs & aMask), (uint32_t) ((gs >> aShift) & 1)); PROF_END(pW0, wq); }
                 tc_fence_after();
                 PROF_BEGIN(wi);
                 const uint32_t aSlot = tmem + (uint32_t) aCol + (uint32_t) ((gs & aMask) * 32);
@@ -571,12 +614,26 @@ umma_fir_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix
                     const uint32_t d1 = tmem + (o.x & 0xffffu), pool = tmem + (o.x >> 16);
                     const uint32_t h = (o.z >> 8) & 0xffu, gl = (o.z >> 16) & 0xffu, fl = o.z >> 24, waitGl = o.w & 0xffu;
                     if (fl & kOpWaitDrain) {                                    // accumulators drained by the epilogue (previous tile)?
-                        PROF_BEGIN(wd); mbar_wait(sm.accEmpty + gl, (t & 1) ^ 1); PROF_END(pW1, wd);
+                        PROF_BEGIN(wd); if (CTA2) mbar_wait_cluster(sm.accEmpty + gl, (t & 1) ^ 1, 200); else mbar_wait(sm.accEmpty + gl, (t & 1) ^ 1); PROF_END(pW1, wd);
                         tc_fence_after();
                     } else if (fl & kOpWaitPool) {                              // the pool slot's previous user read?
-                        PROF_BEGIN(wd); mbar_wait(sm.accEmpty + waitGl, (fl & kOpPoolPrevTile) ? (t & 1) ^ 1 : (t & 1)); PROF_END(pW1, wd);
+                        PROF_BEGIN(wd);
+                        if (CTA2) mbar_wait_cluster(sm.accEmpty + waitGl, (fl & kOpPoolPrevTile) ? (t & 1) ^ 1 : (t & 1), 200);
+                        else mbar_wait(sm.accEmpty + waitGl, (fl & kOpPoolPrevTile) ? (t & 1) ^ 1 : (t & 1));
+                        PROF_END(pW1, wd);
                         tc_fence_after();
                     }
+                    if (CTA2) {
+                        if (el) {                              // three N = NB MMAs over both CTAs (M = 256); each CTA supplies its 16 slots of the weight tile
+                            const uint32_t aHi = aSlot + h * 16u;
+                            const uint64_t bd = ((uint64_t) wHi << 32) | (uint64_t) (wLo + (o.y >> 1));
+                            const bool toPool = !(fl & kOpMerged);                                  // past the split: D0 lives in the pool
+                            umma2_ts(toPool ? pool : d1 - nb, aHi, bd, idescN, toPool ? (fl & kOpPoolAcc) : (fl & kOpAcc));   // D0 (+)= x0 * w0
+                            umma2_ts(d1, aHi, bd + 16, idescN, fl & kOpAcc);                        // D1 (+)= x0 * w1 (the w1 rows sit 256 bytes up)
+                            umma2_ts(d1, aHi + 8, bd, idescN, 1u);                                  // D1  += x1 * w0
+                            if (fl & kOpLast) umma2_commit_both(sm.accFull + gl);
+                        }
+                    } else
                     if (el && !(dbg & 1)) {
                         const uint32_t aHi = aSlot + h * 16u;
                         const uint64_t bd = ((uint64_t) wHi << 32) | (uint64_t) (wLo + o.y);
@@ -590,13 +647,13 @@ umma_fir_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix
                         if (fl & kOpLast) umma_commit(sm.accFull + gl);
                     }
                 }
-                if (el) umma_commit(sm.slotFree + (gs & aMask));   // arrives once this warp's MMAs on the slot have completed
+                if (el) { if (CTA2) umma2_commit_both(sm.slotFree + (gs & aMask)); else umma_commit(sm.slotFree + (gs & aMask)); }   // arrives once this warp's MMAs on the slot have completed
                 __syncwarp();
                 PROF_END(pI, wi);
             }
         }
         if (prof && w == 0 && lane == 0) { prof[blockIdx.x * 16 + 10] = pW0; prof[blockIdx.x * 16 + 11] = pI; prof[blockIdx.x * 16 + 12] = pW1; }
-    } else {
+    } else if (warp < 4) {
         // =========================================================== epilogue
         // Thread = TMEM lane = period row.  Per group and 16-slot chunk: read D0 (+ its pool half) and D1, combine, transpose
         // through the warp's own slice of the staging buffer, store two rows per instruction (16 slots = 64 contiguous bytes).
@@ -647,7 +704,7 @@ umma_fir_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix
                     if (h == chunks - 1) {                     // the whole group has been read: the next tile may overwrite it
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(sm.accEmpty + gl);
+                        if (lane == 0) { if (CTA2) mbar_arrive_leader(sm.accEmpty + gl); else mbar_arrive(sm.accEmpty + gl); }
                     }
                     float4* dst = reinterpret_cast<float4*>(sm.epi + row0 * kEpiPitch);
                     #pragma unroll
@@ -685,8 +742,12 @@ umma_fir_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix
 
     tc_fence_before();
     __syncthreads();
+    if (CTA2) cluster_sync_all();                              // the peer may still read this CTA's weights / signal its barriers
     tc_fence_after();
-    if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512) : "memory");
+    if (warp == 4) {
+        if (CTA2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512) : "memory");
+    }
 }
 
 // One thread per tile: the record the TMA-fed kernel's roles read instead of searching the segment table.
@@ -694,7 +755,12 @@ __global__ void __launch_bounds__(256)
 umma_tile_table_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix, int nSegs, int nTiles,
                        const __grid_constant__ UmmaDev P, const __grid_constant__ UmmaTma TM, UmmaTileRec* __restrict__ recs) {
     const int tileId = blockIdx.x * blockDim.x + threadIdx.x;
-    if (tileId >= nTiles) return;
+    if (tileId > nTiles) return;
+    if (tileId == nTiles) {                                     // padding for CTA pairs: a tile without input or output
+        UmmaTileRec R; R.in = nullptr; R.out = nullptr; R.l00 = 0; R.inAvail = 0; R.oBase = 0; R.numOut = 0; R.x0 = 0; R.mapIdx = -1; R.pad[0] = R.pad[1] = 0;
+        recs[tileId] = R;
+        return;
+    }
     const UmmaBlockInfo& BI = P.blk[tileId % P.nGB];            // every segment owns a multiple of nGB tiles
     const int sidx = find_seg(tilePrefix, nSegs, tileId);
     const Seg S = segs[sidx];
@@ -777,16 +843,19 @@ bool umma_encode_maps(unsigned long long lo, unsigned long long hi, int p, UmmaT
 cudaError_t launch_umma(const ResampleLaunch& L, cudaStream_t s, long long* launches) {
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(umma_fir_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(umma_fir_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(umma_fir_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(umma_fir_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(umma_fir_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(umma_fir_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(umma_fir_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(umma_fir_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(umma_fir_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
     int grid = std::min(L.n_tiles, std::max(L.sm_count, L.um.nGB));
     grid -= grid % L.um.nGB;
     if (grid <= 0) return cudaErrorInvalidValue;
+    const bool pairs = L.um_tma && L.um_cta2;
+    if (pairs) grid = std::min((grid + 1) & ~1, L.sm_count & ~1);   // whole pairs; the table has a padding record for an odd last tile
     cudaError_t e = cudaMemsetAsync(L.d_ovf, 0, sizeof(unsigned), s);
     if (e != cudaSuccess) return e;
     // F9_UMMA_PROF=1 (development): per-role cycle accounting of the first launch, printed to stderr
@@ -795,14 +864,28 @@ cudaError_t launch_umma(const ResampleLaunch& L, cudaStream_t s, long long* laun
     const bool doProf = profEnv != nullptr && prof_calls++ == atoi(profEnv);
     if (doProf) { cudaMalloc((void**) &d_prof, sizeof(long long) * 16 * grid); cudaMemsetAsync(d_prof, 0, sizeof(long long) * 16 * grid, s); }
     const int dbg = getenv("F9_UMMA_DBG") ? atoi(getenv("F9_UMMA_DBG")) : 0;     // development: 1 skip MMAs, 2 skip copies, 4 skip stores
-    #define F9_UMMA_LAUNCH(MERGED, TMA) umma_fir_kernel<MERGED, TMA><<<grid, TMA ? kThreadsTma : kThreads, L.um_smem, s>>>(L.d_segs, L.d_tile_prefix, L.n_segs, L.n_tiles, \
+    #define F9_UMMA_LAUNCH(MERGED, TMA) umma_fir_kernel<MERGED, TMA, false><<<grid, TMA ? kThreadsTma : kThreads, L.um_smem, s>>>(L.d_segs, L.d_tile_prefix, L.n_segs, L.n_tiles, \
         L.um, L.um_maps, L.d_tile_recs, L.um_stages, L.um_aligned ? 1 : 0, L.d_ovf, doProf ? d_prof : nullptr, dbg)
     if (L.um_tma) {
         if (!L.d_tile_recs) return cudaErrorInvalidValue;
-        umma_tile_table_kernel<<<(L.n_tiles + 255) / 256, 256, 0, s>>>(L.d_segs, L.d_tile_prefix, L.n_segs, L.n_tiles, L.um, L.um_maps, L.d_tile_recs);
+        umma_tile_table_kernel<<<(L.n_tiles + 256) / 256, 256, 0, s>>>(L.d_segs, L.d_tile_prefix, L.n_segs, L.n_tiles, L.um, L.um_maps, L.d_tile_recs);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         ++*launches;
-        if (L.um.poolN == 0) F9_UMMA_LAUNCH(true, true); else F9_UMMA_LAUNCH(false, true);
+        if (pairs) {                                             // clusters of two CTAs
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned) grid); cfg.blockDim = dim3(kThreadsTma); cfg.dynamicSmemBytes = L.um_smem; cfg.stream = s;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension; attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+            if (getenv("F9_UMMA_PROF")) {
+                int nc = -1; cudaError_t qe = cudaOccupancyMaxActiveClusters(&nc, umma_fir_kernel<false, true, true>, &cfg);
+                fprintf(stderr, "[umma pairs] grid %d smem %zu stages %d max active clusters %d (%s)\n", grid, L.um_smem, L.um_stages, nc, cudaGetErrorString(qe));
+            }
+            e = cudaLaunchKernelEx(&cfg, umma_fir_kernel<false, true, true>, L.d_segs, L.d_tile_prefix, L.n_segs, L.n_tiles, L.um, L.um_maps,
+                                   (const UmmaTileRec*) L.d_tile_recs, L.um_stages, L.um_aligned ? 1 : 0, L.d_ovf, (long long*) nullptr, dbg);
+            if (e != cudaSuccess) return e;
+        }
+        else if (L.um.poolN == 0) F9_UMMA_LAUNCH(true, true); else F9_UMMA_LAUNCH(false, true);
     }
     else          { if (L.um.poolN == 0) F9_UMMA_LAUNCH(true, false); else F9_UMMA_LAUNCH(false, false); }
     #undef F9_UMMA_LAUNCH
