@@ -592,60 +592,85 @@ umma_fir_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix
         const uint32_t nb = (uint32_t) NB;
         const uint32_t idescN = make_idesc(CTA2 ? 2 * kRows : kRows, NB), idesc2N = make_idesc(kRows, 2 * NB);
         const uint64_t wDesc0 = make_desc(smem_u32(sm.W), CTA2 ? 16 * NB : 32 * NB, 128);   // weight tile i: + 4*NB*i (16-byte units; half for pairs); w1 rows at + NB (+ NB/2)
-        // The warp walks its host-built list (UmmaOp, shared memory) once per tile: one 128-bit load per (group, K step), fetched
-        // an entry ahead, decoded with a handful of bit operations.  (Decoding the schedule from the kernel parameters put
-        // constant-bank loads and a long branchy chain in front of every MMA: ~175 clk per entry.)
-        const uint4* ops = sm.ops + BI.opStart[w];
+        // The warp walks its host-built list (UmmaOp, shared memory) once per tile.  The list is first rewritten in place into
+        // what the issue needs verbatim: {TMEM address of D0 (or its pool slot), TMEM address of D1, low word of the weight
+        // tile's descriptor, flags | h << 7 | gl << 8 | waitGl << 16 | stage << 24}, so that an entry costs one 128-bit load
+        // (fetched an entry ahead) and one block of predicated tcgen05 instructions.  A single thread's instruction latency is
+        // what bounds this role: ~100 instructions per entry (flag decoding, 64-bit descriptor arithmetic) cost ~360 clk.
+        uint4* ops = sm.ops + BI.opStart[w];
         const int nOps = BI.opStart[w + 1] - BI.opStart[w];
         const uint32_t wLo = (uint32_t) (wDesc0 & 0xffffffffull), wHi = (uint32_t) (wDesc0 >> 32);
+        enum : uint32_t { fA0 = 1, fA1 = 2, fM = 4, fDrain = 8, fPool = 16, fPrev = 32, fLast = 64, fH = 128 };
+        for (int i = lane; i < nOps; i += 32) {
+            const uint4 o = ops[i];
+            const uint32_t d1c = o.x & 0xffffu, poolc = o.x >> 16, hh = (o.z >> 8) & 0xffu, gl = (o.z >> 16) & 0xffu, fl = o.z >> 24;
+            const bool merged = !CTA2 && (MERGED || (fl & kOpMerged)), toPool = !(MERGED || (fl & kOpMerged));
+            uint32_t f = 0;
+            if (toPool ? (fl & kOpPoolAcc) : (fl & kOpAcc)) f |= fA0;
+            if (fl & kOpAcc) f |= fA1;
+            if (merged) f |= fM;
+            if (fl & kOpWaitDrain) f |= fDrain; else if (fl & kOpWaitPool) f |= fPool;
+            if (fl & kOpPoolPrevTile) f |= fPrev;
+            if (fl & kOpLast) f |= fLast;
+            if (hh) f |= fH;
+            ops[i] = make_uint4(tmem + (toPool ? poolc : d1c - nb), tmem + d1c, wLo + (CTA2 ? o.y >> 1 : o.y),
+                                f | (gl << 8) | ((o.w & 0xffu) << 16) | ((o.z & 0xffu) << 24));
+        }
+        __syncwarp();
+        const uint32_t w1Off = CTA2 ? nb / 2 : nb;             // the w1 rows of a tile, in 16-byte units
+        const uint32_t accFull0 = smem_u32(sm.accFull);
         int gs = 0;
         for (int t = 0; t < myTiles; ++t) {
             int k = 0;
-            uint4 nx = nOps > 0 ? ops[0] : make_uint4(0, 0, 0xff, 0);
+            uint4 nx = nOps > 0 ? ops[0] : make_uint4(0, 0, 0, 0xff000000u);
             for (int st = 0; st < nStages; ++st, ++gs) {
                 { PROF_BEGIN(wq); if (CTA2) mbar_wait_cluster(sm.cpDone + (gs & aMask), (uint32_t) ((gs >> aShift) & 1), kParkNs); else if (TMA) mbar_wait_parked(sm.cpDone + (gs & aMask), (uint32_t) ((gs >> aShift) & 1), kParkNs); else mbar_wait(sm.cpDone + (gs & aMask), (uint32_t) ((gs >> aShift) & 1)); PROF_END(pW0, wq); }
                 tc_fence_after();
                 PROF_BEGIN(wi);
                 const uint32_t aSlot = tmem + (uint32_t) aCol + (uint32_t) ((gs & aMask) * 32);
-                while (k < nOps && (int) (nx.z & 0xffu) == st) {
+                while (k < nOps && (int) (nx.w >> 24) == st) {
                     const uint4 o = nx;
                     ++k;
                     nx = ops[k < nOps ? k : 0];
-                    const uint32_t d1 = tmem + (o.x & 0xffffu), pool = tmem + (o.x >> 16);
-                    const uint32_t h = (o.z >> 8) & 0xffu, gl = (o.z >> 16) & 0xffu, fl = o.z >> 24, waitGl = o.w & 0xffu;
-                    if (fl & kOpWaitDrain) {                                    // accumulators drained by the epilogue (previous tile)?
-                        PROF_BEGIN(wd); if (CTA2) mbar_wait_cluster(sm.accEmpty + gl, (t & 1) ^ 1, 200); else mbar_wait(sm.accEmpty + gl, (t & 1) ^ 1); PROF_END(pW1, wd);
-                        tc_fence_after();
-                    } else if (fl & kOpWaitPool) {                              // the pool slot's previous user read?
-                        PROF_BEGIN(wd);
-                        if (CTA2) mbar_wait_cluster(sm.accEmpty + waitGl, (fl & kOpPoolPrevTile) ? (t & 1) ^ 1 : (t & 1), 200);
-                        else mbar_wait(sm.accEmpty + waitGl, (fl & kOpPoolPrevTile) ? (t & 1) ^ 1 : (t & 1));
-                        PROF_END(pW1, wd);
+                    if (o.w & (fDrain | fPool)) {                               // rare: first K step of a group / first step past the split
+                        const uint32_t gl = (o.w >> 8) & 0xffu, waitGl = (o.w >> 16) & 0xffu;
+                        uint64_t* bar = sm.accEmpty + ((o.w & fDrain) ? gl : waitGl);
+                        const uint32_t par = ((o.w & fDrain) || (o.w & fPrev)) ? (uint32_t) ((t & 1) ^ 1) : (uint32_t) (t & 1);
+                        PROF_BEGIN(wd); if (CTA2) mbar_wait_cluster(bar, par, 200); else mbar_wait(bar, par); PROF_END(pW1, wd);
                         tc_fence_after();
                     }
-                    if (CTA2) {
-                        if (el) {                              // three N = NB MMAs over both CTAs (M = 256); each CTA supplies its 16 slots of the weight tile
-                            const uint32_t aHi = aSlot + h * 16u;
-                            const uint64_t bd = ((uint64_t) wHi << 32) | (uint64_t) (wLo + (o.y >> 1));
-                            const bool toPool = !(fl & kOpMerged);                                  // past the split: D0 lives in the pool
-                            umma2_ts(toPool ? pool : d1 - nb, aHi, bd, idescN, toPool ? (fl & kOpPoolAcc) : (fl & kOpAcc));   // D0 (+)= x0 * w0
-                            umma2_ts(d1, aHi, bd + 16, idescN, fl & kOpAcc);                        // D1 (+)= x0 * w1 (the w1 rows sit 256 bytes up)
-                            umma2_ts(d1, aHi + 8, bd, idescN, 1u);                                  // D1  += x1 * w0
-                            if (fl & kOpLast) umma2_commit_both(sm.accFull + gl);
-                        }
-                    } else
-                    if (el && !(dbg & 1)) {
-                        const uint32_t aHi = aSlot + h * 16u;
-                        const uint64_t bd = ((uint64_t) wHi << 32) | (uint64_t) (wLo + o.y);
-                        if (MERGED || (fl & kOpMerged)) {      // D0 and D1 adjacent: [D0 | D1] (+)= x0 * [w0 | w1] as one N = 2*NB MMA
-                            umma_ts(d1 - nb, aHi, bd, idesc2N, fl & kOpAcc);
-                        } else {                               // past the split: D0 lives in the pool
-                            umma_ts(pool, aHi, bd, idescN, fl & kOpPoolAcc);    // D0B (+)= x0 * w0
-                            umma_ts(d1, aHi, bd + nb, idescN, 1u);              // D1    += x0 * w1
-                        }
-                        umma_ts(d1, aHi + 8, bd, idescN, 1u);                   // D1    += x1 * w0
-                        if (fl & kOpLast) umma_commit(sm.accFull + gl);
-                    }
+                    // x0 * w0 -> D0 (N = 2 NB over [D0 | D1] when merged), x0 * w1 -> D1 (unless merged), x1 * w0 -> D1, "group done"
+                    // (issued under the elected lane's branch: a per-lane predicate on these warp-uniform instructions makes the
+                    // compiler serialise them with an election loop)
+                    const uint32_t go = (dbg & 1) ? 0u : 1u;
+                    const uint32_t aHi = aSlot + ((o.w & fH) ? 16u : 0u);
+                    const uint32_t lastBar = accFull0 + ((o.w >> 8) & 0xffu) * 8u;
+                    if (!el) continue;
+                    if (CTA2)
+                        asm volatile("{\n\t.reg .pred pe, pa0, pa1, pl;\n\t.reg .b32 t;\n\t.reg .b64 b0, b1;\n\t"
+                                     "setp.ne.b32 pe, %0, 0;\n\t"
+                                     "and.b32 t, %1, 1;\n\tsetp.ne.b32 pa0, t, 0;\n\tand.b32 t, %1, 2;\n\tsetp.ne.b32 pa1, t, 0;\n\t"
+                                     "setp.ne.b32 pl, %10, 0;\n\tand.b32 t, %1, 64;\n\tsetp.ne.and.b32 pl, t, 0, pl;\n\t"
+                                     "mov.b64 b0, {%2, %3};\n\tadd.u32 t, %2, %4;\n\tmov.b64 b1, {t, %3};\n\t"
+                                     "@pe tcgen05.mma.cta_group::2.kind::f16 [%5], [%7], b0, %9, pa0;\n\t"
+                                     "@pe tcgen05.mma.cta_group::2.kind::f16 [%6], [%7], b1, %9, pa1;\n\t"
+                                     "@pe tcgen05.mma.cta_group::2.kind::f16 [%6], [%8], b0, %9, 1;\n\t"
+                                     "@pl tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%11], %12;\n\t}"
+                                     :: "r"(go), "r"(o.w), "r"(o.z), "r"(wHi), "r"(w1Off), "r"(o.x), "r"(o.y), "r"(aHi), "r"(aHi + 8u), "r"(idescN),
+                                        "r"(1u), "r"(lastBar), "h"((uint16_t) 3) : "memory");
+                    else
+                        asm volatile("{\n\t.reg .pred pe, pn, pa0, pa1, pm, pl;\n\t.reg .b32 t, id;\n\t.reg .b64 b0, b1;\n\t"
+                                     "setp.ne.b32 pe, %0, 0;\n\t"
+                                     "and.b32 t, %1, 1;\n\tsetp.ne.b32 pa0, t, 0;\n\tand.b32 t, %1, 2;\n\tsetp.ne.b32 pa1, t, 0;\n\t"
+                                     "and.b32 t, %1, 4;\n\tsetp.ne.b32 pm, t, 0;\n\tselp.b32 id, %12, %9, pm;\n\tand.pred pn, pe, !pm;\n\t"
+                                     "setp.ne.b32 pl, %10, 0;\n\tand.b32 t, %1, 64;\n\tsetp.ne.and.b32 pl, t, 0, pl;\n\t"
+                                     "mov.b64 b0, {%2, %3};\n\tadd.u32 t, %2, %4;\n\tmov.b64 b1, {t, %3};\n\t"
+                                     "@pe tcgen05.mma.cta_group::1.kind::f16 [%5], [%7], b0, id, pa0;\n\t"
+                                     "@pn tcgen05.mma.cta_group::1.kind::f16 [%6], [%7], b1, %9, pa1;\n\t"
+                                     "@pe tcgen05.mma.cta_group::1.kind::f16 [%6], [%8], b0, %9, 1;\n\t"
+                                     "@pl tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%11];\n\t}"
+                                     :: "r"(go), "r"(o.w), "r"(o.z), "r"(wHi), "r"(w1Off), "r"(o.x), "r"(o.y), "r"(aHi), "r"(aHi + 8u), "r"(idescN),
+                                        "r"(1u), "r"(lastBar), "r"(idesc2N) : "memory");
                 }
                 if (el) { if (CTA2) umma2_commit_both(sm.slotFree + (gs & aMask)); else umma_commit(sm.slotFree + (gs & aMask)); }   // arrives once this warp's MMAs on the slot have completed
                 __syncwarp();
