@@ -128,7 +128,8 @@ void build_banded(int kind, const float* sinc_table, long long p, long long q, i
 constexpr int kUmmaMaxBlocks = 8;        // group blocks per ratio (passes over the same rows)
 constexpr int kUmmaMaxGroups = 12;       // groups per block: 2*NB TMEM columns each
 constexpr int kUmmaMaxNK = 64;           // K steps per block (period + taps + alignment <= 1024 input samples)
-constexpr int kUmmaIssuers = 3;          // MMA-issuing warps: group gl of a block belongs to warp gl % kUmmaIssuers
+constexpr int kUmmaIssuers = 3;          // MMA-issuing warps of the register-loader kernel: group gl of a block belongs to warp gl % 3
+constexpr int kUmmaIssuersTma = 5;       // ... of the TMA-fed kernels (a single thread's issue latency bounds the role: fewer groups per warp)
 // One (group, K step) of a tile as the issuing warp sees it: 16 bytes, listed per warp in issue order (stage, group, K step).
 // The lists are built on the host (build_umma), live behind the weight tiles and are copied to shared memory with them.
 struct UmmaOp {
@@ -157,8 +158,10 @@ struct UmmaBlockInfo {
     int slot0;         // first slot of the block
     int nEntries;      // weight tiles of the block (one per (group, K step of its window)), NB*64 bytes each from wOff
     int wOff;          // byte offset into W
-    int opOff;         // byte offset into W of the block's UmmaOp lists (nEntries records, warp 0's first)
+    int opOff;         // byte offset into W of the block's UmmaOp lists (nEntries records, warp 0's first), 3 issuing warps
     int opStart[kUmmaIssuers + 1];   // record range of each issuing warp
+    int opOffT;        // the same for the TMA-fed kernels' 5 issuing warps
+    int opStartT[kUmmaIssuersTma + 1];
     int w2Off[2];      // CTA-pair kernel (NB = 32, one block): byte offset into W of the weight halves of cluster rank 0 / 1:
                        // per tile [2 K chunks][16 x w0, 16 x w1*2048 of slots 16*rank ..][8] = 1 KB; -1: not built
 };

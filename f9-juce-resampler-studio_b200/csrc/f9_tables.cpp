@@ -480,14 +480,14 @@ bool build_umma(int kind, const float* sinc_table, long long p, long long q, int
         out->maxNK = std::max(out->maxNK, BI.nK);
     }
     // issue lists: per block, per issuing warp, the (stage, group, K step) entries in the order the warp walks them
-    for (int b = 0; b < nGB; ++b) {
+    auto build_ops = [&](int b, int nIss, int* opOff, int* opStart) {
         UmmaBlockInfo& BI = out->blk[b];
-        BI.opOff = (int) out->W.size();
+        *opOff = (int) out->W.size();
         int count = 0;
-        for (int w = 0; w < kUmmaIssuers; ++w) {
-            BI.opStart[w] = count;
+        for (int w = 0; w < nIss; ++w) {
+            opStart[w] = count;
             for (int st = 0; st < BI.nStages; ++st)
-                for (int gl = w; gl < BI.nGroups; gl += kUmmaIssuers)
+                for (int gl = w; gl < BI.nGroups; gl += nIss)
                     for (int h = 0; h < 2; ++h) {
                         const int g0 = out->gStart[b][gl], gn = out->gSteps[b][gl];
                         const int j = 2 * st + h - g0;
@@ -517,8 +517,12 @@ bool build_umma(int kind, const float* sinc_table, long long p, long long q, int
                         ++count;
                     }
         }
-        BI.opStart[kUmmaIssuers] = count;
-        if (count != BI.nEntries) return false;
+        opStart[nIss] = count;
+        return count == BI.nEntries;
+    };
+    for (int b = 0; b < nGB; ++b) {
+        UmmaBlockInfo& BI = out->blk[b];
+        if (!build_ops(b, kUmmaIssuers, &BI.opOff, BI.opStart) || !build_ops(b, kUmmaIssuersTma, &BI.opOffT, BI.opStartT)) return false;
     }
     // CTA-pair kernel: the weight tiles again, split by slot halves (cluster rank r holds slots 16 r .. 16 r + 15 of every group)
     for (int b = 0; b < nGB; ++b) out->blk[b].w2Off[0] = out->blk[b].w2Off[1] = -1;

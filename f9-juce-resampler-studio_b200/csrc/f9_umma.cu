@@ -45,9 +45,12 @@ constexpr int kASlotsMax = 4;                    // TMEM operand ring: up to 4 s
 constexpr int kLoaderWarps = 8;
 constexpr int kIssuers = kUmmaIssuers;            // MMA-issuing warps (groups are dealt round-robin)
 constexpr int kFirstLoader = 4 + 1 + kIssuers;   // warps 0-3 epilogue, 4 copy, 5..7 issue, 8..15 load
-constexpr int kConvWarps = 16;                   // TMA feed: converter warps (a quarter of the rows x half a K step each)
 constexpr int kThreads = (kFirstLoader + kLoaderWarps) * 32;
-constexpr int kThreadsTma = (kFirstLoader + kConvWarps) * 32;
+// TMA-fed kernels: warps 0-3 epilogue, 4 producer, 5..9 issue, 10..17 convert (a quarter of the rows x one K step each)
+constexpr int kIssuersTma = kUmmaIssuersTma;
+constexpr int kFirstConv = 4 + 1 + kIssuersTma;
+constexpr int kConvWarps = 8;
+constexpr int kThreadsTma = (kFirstConv + kConvWarps) * 32;
 constexpr uint32_t kParkNs = 1000;                // suspend-time hint of the TMA roles' barrier waits (a hot poll loop cost 40 % of the issue slots)
 constexpr int kSpin = 1 << 26;                   // bounded waits: a protocol bug must not hang the GPU
 
@@ -390,10 +393,10 @@ __device__ __forceinline__ void producer_role(const FeedArgs& A, const UmmaTma& 
     }
 }
 
-__device__ __forceinline__ void converter_role(const FeedArgs& A, uint32_t tmem, int cw, int lane) {
-    const int quarter = cw & 3, h = cw >> 3, half = (cw >> 2) & 1;   // TMEM lane quarter (= warp id % 4), K step of the stage, its 8-sample half
+__device__ __forceinline__ void converter_role(const FeedArgs& A, uint32_t tmem, int warp, int lane) {
+    const int quarter = warp & 3, h = (warp - kFirstConv) >> 2;    // TMEM lane quarter (fixed by the warp id), K step of the stage
     const int rho = quarter * 32 + lane;                       // period row = TMEM lane = row of the box
-    const uint32_t tdst = tmem + ((uint32_t) (quarter * 32) << 16) + (uint32_t) (A.aCol + h * 16 + half * 4);
+    const uint32_t tdst = tmem + ((uint32_t) (quarter * 32) << 16) + (uint32_t) (A.aCol + h * 16);
     const uint32_t ringRow = smem_u32(A.ring) + (uint32_t) (rho * 128);
     const uint32_t sw = (uint32_t) (rho & 7);
     __half2 hmax = __floats2half2_rn(0.f, 0.f);
@@ -409,19 +412,19 @@ __device__ __forceinline__ void converter_role(const FeedArgs& A, uint32_t tmem,
     for (int t = 0; t < A.myTiles; ++t, rec += gridDim.x) {
         T = N;
         if (t + 1 < A.myTiles) N = load_rec(rec + gridDim.x);                  // consumed one tile later
-        const long long lrow = T.l00 + (long long) rho * A.p + h * 16 + half * 8;
+        const long long lrow = T.l00 + (long long) rho * A.p + h * 16;
         for (int st = 0; st < A.nStages; ++st, ++gs) {
-            float4 v[2];
+            float4 v[4];
             if (T.viaTma) {
                 mbar_wait_parked(A.full + sIdx, sPh, kParkNs);
                 const uint32_t a = ringRow + (uint32_t) (sIdx * kTmaStageBytes);
                 #pragma unroll
-                for (int c = 0; c < 2; ++c)
+                for (int c = 0; c < 4; ++c)
                     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[c].x), "=f"(v[c].y), "=f"(v[c].z), "=f"(v[c].w)
-                                 : "r"(a + ((((uint32_t) (4 * h + 2 * half + c)) ^ sw) << 4)) : "memory");
+                                 : "r"(a + ((((uint32_t) (4 * h + c)) ^ sw) << 4)) : "memory");
             } else {
                 #pragma unroll
-                for (int c = 0; c < 2; ++c) {
+                for (int c = 0; c < 4; ++c) {
                     const long long l = lrow + st * 32 + 4 * c;
                     const float* ptr = T.in + l;
                     if (l >= 0 && l + 3 < T.inAvail) v[c] = __ldg(reinterpret_cast<const float4*>(ptr));
@@ -431,9 +434,9 @@ __device__ __forceinline__ void converter_role(const FeedArgs& A, uint32_t tmem,
                     }
                 }
             }
-            uint32_t hd[4], tl[4];
+            uint32_t hd[8], tl[8];
             #pragma unroll
-            for (int c = 0; c < 2; ++c) {
+            for (int c = 0; c < 4; ++c) {
                 float4 xv = v[c];
                 xv.x *= kPreScale; xv.y *= kPreScale; xv.z *= kPreScale; xv.w *= kPreScale;
                 const __half2 h01 = __floats2half2_rn(xv.x, xv.y), h23 = __floats2half2_rn(xv.z, xv.w);
@@ -451,9 +454,9 @@ __device__ __forceinline__ void converter_role(const FeedArgs& A, uint32_t tmem,
             }
             if (gs > aMask) mbar_wait_parked(A.slotFree + (gs & aMask), (uint32_t) (((gs >> aShift) - 1) & 1), kParkNs);   // the MMAs of the slot's previous stage are done
             tc_fence_after();
-            const uint32_t td = tdst + (uint32_t) ((gs & aMask) * 32);          // head columns; the tail sits 8 columns up
-            asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" :: "r"(td), "r"(hd[0]), "r"(hd[1]), "r"(hd[2]), "r"(hd[3]) : "memory");
-            asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" :: "r"(td + 8), "r"(tl[0]), "r"(tl[1]), "r"(tl[2]), "r"(tl[3]) : "memory");
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                         :: "r"(tdst + (uint32_t) ((gs & aMask) * 32)), "r"(hd[0]), "r"(hd[1]), "r"(hd[2]), "r"(hd[3]), "r"(hd[4]), "r"(hd[5]), "r"(hd[6]), "r"(hd[7]),
+                            "r"(tl[0]), "r"(tl[1]), "r"(tl[2]), "r"(tl[3]), "r"(tl[4]), "r"(tl[5]), "r"(tl[6]), "r"(tl[7]) : "memory");
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
             __syncwarp();
@@ -496,7 +499,7 @@ umma_fir_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix
         const uint4* src = reinterpret_cast<const uint4*>(P.W + (CTA2 ? BI.w2Off[rank] : BI.wOff));
         uint4* dst = reinterpret_cast<uint4*>(sm.W);
         for (int i = threadIdx.x; i < BI.nEntries * NB * (CTA2 ? 2 : 4); i += blockDim.x) dst[i] = __ldg(src + i);
-        const uint4* osrc = reinterpret_cast<const uint4*>(P.W + BI.opOff);
+        const uint4* osrc = reinterpret_cast<const uint4*>(P.W + (TMA ? BI.opOffT : BI.opOff));
         for (int i = threadIdx.x; i < BI.nEntries; i += blockDim.x) sm.ops[i] = __ldg(osrc + i);
         if (threadIdx.x == 0) {
             // register loader: full <- 8 loader warps, empty <- the copy warp's commit, cpDone <- its commit
@@ -504,7 +507,7 @@ umma_fir_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix
             for (int s = 0; s < stages; ++s) { mbar_init(sm.full + s, TMA ? 1 : kLoaderWarps); mbar_init(sm.empty + s, TMA ? kConvWarps : 1); }
             // CTA pairs: "operand ready" and "accumulator drained" collect both CTAs' arrivals in the leader
             for (int g = 0; g < kUmmaMaxGroups; ++g) { mbar_init(sm.accFull + g, 1); mbar_init(sm.accEmpty + g, CTA2 ? 8 : 4); }
-            for (int i = 0; i < kASlotsMax; ++i) { mbar_init(sm.cpDone + i, TMA ? (CTA2 ? 2 : 1) * kConvWarps : 1); mbar_init(sm.slotFree + i, kIssuers); }
+            for (int i = 0; i < kASlotsMax; ++i) { mbar_init(sm.cpDone + i, TMA ? (CTA2 ? 2 : 1) * kConvWarps : 1); mbar_init(sm.slotFree + i, TMA ? kIssuersTma : kIssuers); }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         if (warp == 4) {
@@ -531,15 +534,15 @@ umma_fir_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix
     #define PROF_END(acc, v) if (!TMA && prof) acc += clock64() - v
     if (!TMA && prof) pT0 = clock64();
 
-    if (TMA && (warp >= kFirstLoader || warp == 4)) {
+    if (TMA && (warp >= kFirstConv || warp == 4)) {
         // =========================================================== TMA producer / converters
         FeedArgs FA;
         FA.recs = recs; FA.p = p; FA.aCol = aCol; FA.aMask = aMask; FA.aShift = aShift; FA.pair = CTA2;
         FA.nStages = nStages; FA.stages = stages; FA.myTiles = myTiles;
         FA.ring = sm.ring; FA.full = sm.full; FA.empty = sm.empty; FA.aReady = sm.cpDone; FA.slotFree = sm.slotFree; FA.ovf = ovf;
         if (warp == 4) { if (lane == 0) producer_role(FA, TM); }
-        else converter_role(FA, tmem, warp - kFirstLoader, lane);
-    } else if (warp >= kFirstLoader) {
+        else converter_role(FA, tmem, warp, lane);
+    } else if (!TMA && warp >= kFirstLoader) {
         // =========================================================== loaders
         LoaderArgs LA;
         LA.segs = segs; LA.tilePrefix = tilePrefix; LA.nSegs = nSegs; LA.nTiles = nTiles; LA.nGB = P.nGB; LA.p = p; LA.q = q;
@@ -597,8 +600,8 @@ umma_fir_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix
         // tile's descriptor, flags | h << 7 | gl << 8 | waitGl << 16 | stage << 24}, so that an entry costs one 128-bit load
         // (fetched an entry ahead) and one block of predicated tcgen05 instructions.  A single thread's instruction latency is
         // what bounds this role: ~100 instructions per entry (flag decoding, 64-bit descriptor arithmetic) cost ~360 clk.
-        uint4* ops = sm.ops + BI.opStart[w];
-        const int nOps = BI.opStart[w + 1] - BI.opStart[w];
+        uint4* ops = sm.ops + (TMA ? BI.opStartT[w] : BI.opStart[w]);
+        const int nOps = TMA ? BI.opStartT[w + 1] - BI.opStartT[w] : BI.opStart[w + 1] - BI.opStart[w];
         const uint32_t wLo = (uint32_t) (wDesc0 & 0xffffffffull), wHi = (uint32_t) (wDesc0 >> 32);
         enum : uint32_t { fA0 = 1, fA1 = 2, fM = 4, fDrain = 8, fPool = 16, fPrev = 32, fLast = 64, fH = 128 };
         for (int i = lane; i < nOps; i += 32) {
