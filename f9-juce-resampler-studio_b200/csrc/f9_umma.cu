@@ -441,10 +441,17 @@ __device__ __forceinline__ void converter_role(const FeedArgs& A, uint32_t tmem,
                 xv.x *= kPreScale; xv.y *= kPreScale; xv.z *= kPreScale; xv.w *= kPreScale;
                 const __half2 h01 = __floats2half2_rn(xv.x, xv.y), h23 = __floats2half2_rn(xv.z, xv.w);
                 hmax = __hmax2_nan(hmax, __hmax2_nan(__habs2(h01), __habs2(h23)));
-                const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-                const __half2 t01 = __floats2half2_rn((xv.x - f01.x) * 2048.0f, (xv.y - f01.y) * 2048.0f);
-                const __half2 t23 = __floats2half2_rn((xv.z - f23.x) * 2048.0f, (xv.w - f23.y) * 2048.0f);
                 hd[2 * c] = *reinterpret_cast<const uint32_t*>(&h01); hd[2 * c + 1] = *reinterpret_cast<const uint32_t*>(&h23);
+                // tail = (x' - head) * 2048, exact: one mixed-precision FMA, head * (-2048) + x' * 2048.  x' * 2048 is an exponent
+                // add on the integer pipe (x' = 0 becomes 2^-116, which the fp16 tail rounds to 0; non-finite x' takes the redo).
+                float t0, t1, t2, t3;
+                asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tfma.rn.f32.f16 %0, lo, %5, %3;\n\tfma.rn.f32.f16 %1, hi, %5, %4;\n\t}"
+                    : "=f"(t0), "=f"(t1) : "r"(hd[2 * c]), "f"(__int_as_float(__float_as_int(xv.x) + (11 << 23))),
+                      "f"(__int_as_float(__float_as_int(xv.y) + (11 << 23))), "h"((unsigned short) 0xE800));
+                asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tfma.rn.f32.f16 %0, lo, %5, %3;\n\tfma.rn.f32.f16 %1, hi, %5, %4;\n\t}"
+                    : "=f"(t2), "=f"(t3) : "r"(hd[2 * c + 1]), "f"(__int_as_float(__float_as_int(xv.z) + (11 << 23))),
+                      "f"(__int_as_float(__float_as_int(xv.w) + (11 << 23))), "h"((unsigned short) 0xE800));
+                const __half2 t01 = __floats2half2_rn(t0, t1), t23 = __floats2half2_rn(t2, t3);
                 tl[2 * c] = *reinterpret_cast<const uint32_t*>(&t01); tl[2 * c + 1] = *reinterpret_cast<const uint32_t*>(&t23);
             }
             if (T.viaTma) {                                    // the stage's rows are in registers: the box may be refilled
