@@ -200,9 +200,14 @@ struct alignas(64) UmmaTma {
     CUtensorMap maps[kUmmaMaxMaps];
     unsigned long long base0 = 0;      // device address of maps[0]'s origin (16-byte aligned)
     int nMaps = 0;
+    // Device allocations the segments live in (cuPointerGetAttribute): a tile at the start or the end of a segment, whose boxes
+    // leave the segment's window, still goes through TMA when the boxes stay inside one of these (the converters zero what lies
+    // outside the window); otherwise its rows are read with guarded loads.
+    int nRanges = 0;
+    unsigned long long rangeLo[kUmmaMaxMaps] = {}, rangeHi[kUmmaMaxMaps] = {};
 };
-// Encodes the maps for rows p floats apart that start at or after `lo` and end before `hi` (device addresses).  False when the
-// driver entry point is missing or refuses the map (the register loader is used instead).
+// Encodes the maps for rows p floats apart over the address range the segments read and finds the allocations around them.
+// False when the driver entry point is missing or refuses the map (the register loader is used instead).
 // Per-tile record of the TMA-fed kernel, written by umma_tile_table_kernel before the FIR launch so that no role searches the
 // segment table on its critical path (a role loads the record of its next tile one tile ahead).
 struct alignas(16) UmmaTileRec {
@@ -210,9 +215,9 @@ struct alignas(16) UmmaTileRec {
     long long l00, inAvail;            // window index of (row 0, K 0); window length
     long long oBase, numOut;           // output index of (row 0, slot 0 of the block), relative to the segment; segment outputs
     int x0, mapIdx;                    // box coordinate / tensor map of stage 0; mapIdx < 0: the tile does not go through TMA
-    int pad[2];
+    int mask, pad;                     // mask: the boxes leave the window [0, inAvail): zero what lies outside after the load
 };
-bool umma_encode_maps(unsigned long long lo, unsigned long long hi, int p, UmmaTma* out);
+bool umma_encode_maps(const Seg* segs, int n, int p, UmmaTma* out);
 void umma_choose_plan(int taps, long long p, long long q, long long* m_out, int* NB_out, int* GBL_out);
 double umma_cost_per_output(int taps, long long p, long long q, int NB, int GBL, size_t* smem2);   // model used to pick the plan
 

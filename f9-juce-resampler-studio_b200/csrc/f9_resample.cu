@@ -423,13 +423,7 @@ int resample_build_tiles(ResampleLaunch& L, const Seg* segs, int n, std::vector<
         // TMA feed (aligned rows only): tensor maps over the address range the segments read, ring of raw fp32 boxes
         L.um_tma = false;
         if (L.um_aligned && getenv("F9_UMMA_NOTMA") == nullptr) {
-            unsigned long long lo = ~0ull, hi = 0;
-            for (int i = 0; i < n; ++i) {
-                if (segs[i].numOut <= 0 || segs[i].inAvail <= 0) continue;
-                const unsigned long long a = (unsigned long long) reinterpret_cast<uintptr_t>(segs[i].in);
-                lo = std::min(lo, a); hi = std::max(hi, a + 4ull * (unsigned long long) segs[i].inAvail);
-            }
-            if (hi > lo && umma_encode_maps(lo, hi, L.um.p, &L.um_maps)) {
+            if (umma_encode_maps(segs, n, L.um.p, &L.um_maps)) {
                 // CTA pairs halve the weights per SM: worth it when the weights leave a single CTA only a shallow input ring
                 const bool cta2 = L.um.blk[0].w2Off[0] >= 0 && L.sm_count >= 2 && getenv("F9_UMMA_NOCTA2") == nullptr &&
                                   (umma_smem_bytes(L.um.maxEntries, L.um.NB, 4, true) > 227 * 1024 || getenv("F9_UMMA_CTA2") != nullptr);

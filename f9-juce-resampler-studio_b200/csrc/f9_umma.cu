@@ -402,12 +402,13 @@ __device__ __forceinline__ void converter_role(const FeedArgs& A, uint32_t tmem,
     __half2 hmax = __floats2half2_rn(0.f, 0.f);
     const int aMask = A.aMask, aShift = A.aShift;
     int sIdx = 0; uint32_t sPh = 0; int gs = 0;
-    struct TileIn { const float* in; long long l00, inAvail; bool viaTma; };
+    struct TileIn { const float* in; long long l00, inAvail; bool viaTma, mask; };
     auto load_rec = [&](const UmmaTileRec* r) {
-        TileIn T; T.in = ldg_ptr(&r->in); T.l00 = __ldg(&r->l00); T.inAvail = __ldg(&r->inAvail); T.viaTma = __ldg(&r->mapIdx) >= 0; return T;
+        TileIn T; T.in = ldg_ptr(&r->in); T.l00 = __ldg(&r->l00); T.inAvail = __ldg(&r->inAvail);
+        const int4 tail = ld_rec_tail(r); T.viaTma = tail.y >= 0; T.mask = tail.z != 0; return T;
     };
     const UmmaTileRec* rec = A.recs + blockIdx.x;
-    TileIn T = {nullptr, 0, 0, false}, N = T;
+    TileIn T = {nullptr, 0, 0, false, false}, N = T;
     if (A.myTiles > 0) N = load_rec(rec);
     for (int t = 0; t < A.myTiles; ++t, rec += gridDim.x) {
         T = N;
@@ -422,6 +423,17 @@ __device__ __forceinline__ void converter_role(const FeedArgs& A, uint32_t tmem,
                 for (int c = 0; c < 4; ++c)
                     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[c].x), "=f"(v[c].y), "=f"(v[c].z), "=f"(v[c].w)
                                  : "r"(a + ((((uint32_t) (4 * h + c)) ^ sw) << 4)) : "memory");
+                if (T.mask) {                                  // the box left the window [0, inAvail): zero what lies outside
+                    const long long l0 = lrow + st * 32;
+                    const long long lo = -l0, hi = T.inAvail - l0;              // valid element indices e of this thread's 16: lo <= e < hi
+                    #pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        if (4 * c < lo || 4 * c >= hi) v[c].x = 0.f;
+                        if (4 * c + 1 < lo || 4 * c + 1 >= hi) v[c].y = 0.f;
+                        if (4 * c + 2 < lo || 4 * c + 2 >= hi) v[c].z = 0.f;
+                        if (4 * c + 3 < lo || 4 * c + 3 >= hi) v[c].w = 0.f;
+                    }
+                }
             } else {
                 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
@@ -792,7 +804,7 @@ umma_tile_table_kernel(const Seg* __restrict__ segs, const int* __restrict__ til
     const int tileId = blockIdx.x * blockDim.x + threadIdx.x;
     if (tileId > nTiles) return;
     if (tileId == nTiles) {                                     // padding for CTA pairs: a tile without input or output
-        UmmaTileRec R; R.in = nullptr; R.out = nullptr; R.l00 = 0; R.inAvail = 0; R.oBase = 0; R.numOut = 0; R.x0 = 0; R.mapIdx = -1; R.pad[0] = R.pad[1] = 0;
+        UmmaTileRec R; R.in = nullptr; R.out = nullptr; R.l00 = 0; R.inAvail = 0; R.oBase = 0; R.numOut = 0; R.x0 = 0; R.mapIdx = -1; R.mask = 0; R.pad = 0;
         recs[tileId] = R;
         return;
     }
@@ -805,13 +817,18 @@ umma_tile_table_kernel(const Seg* __restrict__ segs, const int* __restrict__ til
     R.in = S.in; R.out = S.out; R.inAvail = S.inAvail; R.numOut = S.numOut;
     R.l00 = A0 * P.p + BI.U0 - S.inOffset;
     R.oBase = A0 * P.q + BI.slot0 - S.n0;
-    // through TMA only if every box of the tile lies inside the segment's window (no reliance on out-of-bounds fill, no reads
-    // outside the caller's buffer) and inside the address range the maps cover
+    // Through TMA if every box of the tile lies inside the segment's window, or at least inside the allocation around it (then
+    // the converters zero what lies outside the window); never a read outside memory the caller owns, never reliance on
+    // out-of-bounds fill.
     const bool interior = R.l00 >= 0 && R.l00 + (long long) (kRows - 1) * P.p + (long long) BI.nStages * 32 <= S.inAvail;
-    const unsigned long long rel = (unsigned long long) reinterpret_cast<uintptr_t>(S.in + R.l00) - TM.base0;
+    const unsigned long long aLo = (unsigned long long) reinterpret_cast<uintptr_t>(S.in + R.l00);
+    const unsigned long long aHi = aLo + 4ull * (unsigned long long) ((kRows - 1) * P.p + BI.nStages * 32);
+    bool contained = false;
+    for (int r = 0; r < TM.nRanges; ++r) contained |= aLo >= TM.rangeLo[r] && aHi <= TM.rangeHi[r];
+    const unsigned long long rel = aLo - TM.base0;
     R.x0 = (int) ((rel & 0xffffffffull) >> 2);
-    R.mapIdx = interior && (rel >> 32) < (unsigned long long) TM.nMaps ? (int) (rel >> 32) : -1;
-    R.pad[0] = R.pad[1] = 0;
+    R.mapIdx = (interior || contained) && aLo >= TM.base0 && (rel >> 32) < (unsigned long long) TM.nMaps ? (int) (rel >> 32) : -1;
+    R.mask = interior ? 0 : 1; R.pad = 0;
     recs[tileId] = R;
 }
 
@@ -846,32 +863,61 @@ umma_redo_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefi
 // The driver entry point is fetched through the runtime (no link against libcuda).
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-bool umma_encode_maps(unsigned long long lo, unsigned long long hi, int p, UmmaTma* out) {
-    static EncodeTiledFn encode = nullptr; static bool tried = false;
+typedef CUresult (*PointerAttrFn)(void*, CUpointer_attribute, CUdeviceptr);
+bool umma_encode_maps(const Seg* segs, int n, int p, UmmaTma* out) {
+    static EncodeTiledFn encode = nullptr; static PointerAttrFn pattr = nullptr; static bool tried = false;
     if (!tried) {
         tried = true;
         void* fn = nullptr; cudaDriverEntryPointQueryResult qres;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
             encode = reinterpret_cast<EncodeTiledFn>(fn);
         else (void) cudaGetLastError();
+        fn = nullptr;
+        if (cudaGetDriverEntryPoint("cuPointerGetAttribute", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            pattr = reinterpret_cast<PointerAttrFn>(fn);
+        else (void) cudaGetLastError();
     }
-    if (!encode || (p & 3) != 0 || p <= 0 || hi <= lo) return false;
-    const unsigned long long base0 = lo & ~15ull;
-    const int n = (int) (((hi - base0) >> 32) + 1);
-    if (n > kUmmaMaxMaps) return false;
+    if (!encode || (p & 3) != 0 || p <= 0) return false;
+    std::vector<std::pair<unsigned long long, unsigned long long>> wins;
+    for (int i = 0; i < n; ++i) {
+        if (segs[i].numOut <= 0 || segs[i].inAvail <= 0) continue;
+        const unsigned long long a = (unsigned long long) reinterpret_cast<uintptr_t>(segs[i].in);
+        wins.emplace_back(a, a + 4ull * (unsigned long long) segs[i].inAvail);
+    }
+    if (wins.empty()) return false;
+    std::sort(wins.begin(), wins.end());
+    unsigned long long lo = wins.front().first, hi = 0;
+    for (const auto& w : wins) hi = std::max(hi, w.second);
+    // allocations around the windows (usually one: an arena or a framework's pool block)
+    out->nRanges = 0;
+    if (pattr && getenv("F9_UMMA_NORANGES") == nullptr)
+        for (const auto& w : wins) {
+            bool known = false;
+            for (int r = 0; r < out->nRanges && !known; ++r) known = w.first >= out->rangeLo[r] && w.second <= out->rangeHi[r];
+            if (known || out->nRanges == kUmmaMaxMaps) continue;
+            CUdeviceptr rs = 0; size_t sz = 0;
+            if (pattr(&rs, CU_POINTER_ATTRIBUTE_RANGE_START_ADDR, (CUdeviceptr) w.first) != CUDA_SUCCESS ||
+                pattr(&sz, CU_POINTER_ATTRIBUTE_RANGE_SIZE, (CUdeviceptr) w.first) != CUDA_SUCCESS || sz == 0) continue;
+            out->rangeLo[out->nRanges] = (unsigned long long) rs; out->rangeHi[out->nRanges] = (unsigned long long) rs + sz; ++out->nRanges;
+        }
+    // the first tile of a segment starts a window's worth of taps before it, the last one ends up to a tile after it
+    unsigned long long base0 = lo > (1ull << 16) ? lo - (1ull << 16) : 0, top = hi + (1ull << 22);
+    base0 &= ~15ull;
+    const int nm = (int) (((top - base0) >> 32) + 1);
+    if (nm > kUmmaMaxMaps) return false;
     // Rows p floats apart, 32 floats per box row: the rows overlap in memory, which the descriptor does not mind.  The extents
-    // are only bounds for the coordinates the kernel uses (x < 2^30 + a tile's K span, y < 128): tiles that would leave their
-    // segment's window never go through TMA, so out-of-bounds fill is never relied on.
+    // are only bounds for the coordinates the kernel uses (x < 2^30 + a tile's K span, y < 128); out-of-bounds fill is never
+    // relied on: what a box reads outside its segment's window is real memory of the same allocation, zeroed by the converters.
     const cuuint64_t dims[2] = {(cuuint64_t) ((1ull << 30) + 65536), 1024};
     const cuuint64_t strides[1] = {(cuuint64_t) p * 4};
     const cuuint32_t box[2] = {32, (cuuint32_t) kRows}, es[2] = {1, 1};
-    for (int k = 0; k < n; ++k) {
+    for (int k = 0; k < nm; ++k) {
         const CUresult r = encode(&out->maps[k], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, reinterpret_cast<void*>(base0 + ((unsigned long long) k << 32)), dims, strides,
                                   box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return false;
     }
-    out->base0 = base0; out->nMaps = n;
+    out->base0 = base0; out->nMaps = nm;
     return true;
 }
 
