@@ -46,10 +46,11 @@ constexpr int kLoaderWarps = 8;
 constexpr int kIssuers = kUmmaIssuers;            // MMA-issuing warps (groups are dealt round-robin)
 constexpr int kFirstLoader = 4 + 1 + kIssuers;   // warps 0-3 epilogue, 4 copy, 5..7 issue, 8..15 load
 constexpr int kThreads = (kFirstLoader + kLoaderWarps) * 32;
-// TMA-fed kernels: warps 0-3 epilogue, 4 producer, 5..9 issue, 10..17 convert (a quarter of the rows x one K step each)
+// TMA-fed kernels: warps 0-3 epilogue, 4 producer, 5..9 issue, 10.. convert (a quarter of the rows x (part of) one K step each)
 constexpr int kIssuersTma = kUmmaIssuersTma;
 constexpr int kFirstConv = 4 + 1 + kIssuersTma;
-constexpr int kConvWarps = 8;
+constexpr int kConvSplit = 1;                    // converter warps per (row quarter, K step): 1 or 2 (8 or 16 samples per thread)
+constexpr int kConvWarps = 8 * kConvSplit;
 constexpr int kThreadsTma = (kFirstConv + kConvWarps) * 32;
 constexpr uint32_t kParkNs = 1000;                // suspend-time hint of the TMA roles' barrier waits (a hot poll loop cost 40 % of the issue slots)
 constexpr int kSpin = 1 << 26;                   // bounded waits: a protocol bug must not hang the GPU
@@ -394,9 +395,11 @@ __device__ __forceinline__ void producer_role(const FeedArgs& A, const UmmaTma& 
 }
 
 __device__ __forceinline__ void converter_role(const FeedArgs& A, uint32_t tmem, int warp, int lane) {
-    const int quarter = warp & 3, h = (warp - kFirstConv) >> 2;    // TMEM lane quarter (fixed by the warp id), K step of the stage
+    constexpr int C = 4 / kConvSplit;                          // 16-byte chunks (4 samples) per thread and stage
+    const int quarter = warp & 3, part = (warp - kFirstConv) >> 2; // TMEM lane quarter (fixed by the warp id); K step of the stage and its part
+    const int h = part / kConvSplit, sub = part % kConvSplit;
     const int rho = quarter * 32 + lane;                       // period row = TMEM lane = row of the box
-    const uint32_t tdst = tmem + ((uint32_t) (quarter * 32) << 16) + (uint32_t) (A.aCol + h * 16);
+    const uint32_t tdst = tmem + ((uint32_t) (quarter * 32) << 16) + (uint32_t) (A.aCol + h * 16 + sub * 2 * C);
     const uint32_t ringRow = smem_u32(A.ring) + (uint32_t) (rho * 128);
     const uint32_t sw = (uint32_t) (rho & 7);
     __half2 hmax = __floats2half2_rn(0.f, 0.f);
@@ -413,21 +416,21 @@ __device__ __forceinline__ void converter_role(const FeedArgs& A, uint32_t tmem,
     for (int t = 0; t < A.myTiles; ++t, rec += gridDim.x) {
         T = N;
         if (t + 1 < A.myTiles) N = load_rec(rec + gridDim.x);                  // consumed one tile later
-        const long long lrow = T.l00 + (long long) rho * A.p + h * 16;
+        const long long lrow = T.l00 + (long long) rho * A.p + h * 16 + sub * 4 * C;
         for (int st = 0; st < A.nStages; ++st, ++gs) {
-            float4 v[4];
+            float4 v[C];
             if (T.viaTma) {
                 mbar_wait_parked(A.full + sIdx, sPh, kParkNs);
                 const uint32_t a = ringRow + (uint32_t) (sIdx * kTmaStageBytes);
                 #pragma unroll
-                for (int c = 0; c < 4; ++c)
+                for (int c = 0; c < C; ++c)
                     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[c].x), "=f"(v[c].y), "=f"(v[c].z), "=f"(v[c].w)
-                                 : "r"(a + ((((uint32_t) (4 * h + c)) ^ sw) << 4)) : "memory");
+                                 : "r"(a + ((((uint32_t) (4 * h + C * sub + c)) ^ sw) << 4)) : "memory");
                 if (T.mask) {                                  // the box left the window [0, inAvail): zero what lies outside
                     const long long l0 = lrow + st * 32;
-                    const long long lo = -l0, hi = T.inAvail - l0;              // valid element indices e of this thread's 16: lo <= e < hi
+                    const long long lo = -l0, hi = T.inAvail - l0;              // valid element indices e of this thread's samples: lo <= e < hi
                     #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
+                    for (int c = 0; c < C; ++c) {
                         if (4 * c < lo || 4 * c >= hi) v[c].x = 0.f;
                         if (4 * c + 1 < lo || 4 * c + 1 >= hi) v[c].y = 0.f;
                         if (4 * c + 2 < lo || 4 * c + 2 >= hi) v[c].z = 0.f;
@@ -436,7 +439,7 @@ __device__ __forceinline__ void converter_role(const FeedArgs& A, uint32_t tmem,
                 }
             } else {
                 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
+                for (int c = 0; c < C; ++c) {
                     const long long l = lrow + st * 32 + 4 * c;
                     const float* ptr = T.in + l;
                     if (l >= 0 && l + 3 < T.inAvail) v[c] = __ldg(reinterpret_cast<const float4*>(ptr));
@@ -446,9 +449,9 @@ __device__ __forceinline__ void converter_role(const FeedArgs& A, uint32_t tmem,
                     }
                 }
             }
-            uint32_t hd[8], tl[8];
+            uint32_t hd[2 * C], tl[2 * C];
             #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < C; ++c) {
                 float4 xv = v[c];
                 xv.x *= kPreScale; xv.y *= kPreScale; xv.z *= kPreScale; xv.w *= kPreScale;
                 const __half2 h01 = __floats2half2_rn(xv.x, xv.y), h23 = __floats2half2_rn(xv.z, xv.w);
@@ -473,9 +476,15 @@ __device__ __forceinline__ void converter_role(const FeedArgs& A, uint32_t tmem,
             }
             if (gs > aMask) mbar_wait_parked(A.slotFree + (gs & aMask), (uint32_t) (((gs >> aShift) - 1) & 1), kParkNs);   // the MMAs of the slot's previous stage are done
             tc_fence_after();
-            asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
-                         :: "r"(tdst + (uint32_t) ((gs & aMask) * 32)), "r"(hd[0]), "r"(hd[1]), "r"(hd[2]), "r"(hd[3]), "r"(hd[4]), "r"(hd[5]), "r"(hd[6]), "r"(hd[7]),
-                            "r"(tl[0]), "r"(tl[1]), "r"(tl[2]), "r"(tl[3]), "r"(tl[4]), "r"(tl[5]), "r"(tl[6]), "r"(tl[7]) : "memory");
+            const uint32_t td = tdst + (uint32_t) ((gs & aMask) * 32);           // head columns; the tail sits 8 columns up
+            if constexpr (kConvSplit == 1) {
+                asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                             :: "r"(td), "r"(hd[0]), "r"(hd[1]), "r"(hd[2]), "r"(hd[3]), "r"(hd[4 % (2 * C)]), "r"(hd[5 % (2 * C)]), "r"(hd[6 % (2 * C)]), "r"(hd[7 % (2 * C)]),
+                                "r"(tl[0]), "r"(tl[1]), "r"(tl[2]), "r"(tl[3]), "r"(tl[4 % (2 * C)]), "r"(tl[5 % (2 * C)]), "r"(tl[6 % (2 * C)]), "r"(tl[7 % (2 * C)]) : "memory");
+            } else {
+                asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" :: "r"(td), "r"(hd[0]), "r"(hd[1]), "r"(hd[2]), "r"(hd[3]) : "memory");
+                asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" :: "r"(td + 8), "r"(tl[0]), "r"(tl[1]), "r"(tl[2]), "r"(tl[3]) : "memory");
+            }
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
             __syncwarp();
