@@ -347,3 +347,76 @@ def test_umma_group_widths_agree(ctx, O, f9, monkeypatch):
             monkeypatch.delenv(k)
         for c in range(2):
             assert np.max(np.abs(y[c] - refs[c])) <= TOL, env
+
+
+# ---------------------------------------------------------------- TMA-fed / CTA-pair variants of the tensor-core FIR
+def _plan_resample_many(ctx, f9, x_dev, windows, kind, fs_in, fs_out):
+    """Plan API over several windows (offset, n_in) of one device buffer; returns the list of outputs."""
+    torch = pytest.importorskip("torch")
+    import ctypes as C
+    outs = [torch.full((f9.resampled_length(n, fs_in, fs_out),), float("nan"), dtype=torch.float32, device="cuda") for _, n in windows]
+    segs = (f9.ResampleSeg * len(windows))(*[f9.ResampleSeg(x_dev.data_ptr() + 4 * off, 0, n, o.data_ptr(), 0, o.numel())
+                                             for (off, n), o in zip(windows, outs)])
+    plan = C.c_void_p(None)
+    torch.cuda.synchronize()
+    assert f9.lib().f9_resample_plan_create(ctx.handle, kind, fs_in / fs_out, segs, len(windows), C.byref(plan)) == 0
+    assert f9.lib().f9_resample_plan_run(plan) == 0
+    ctx.synchronize()
+    f9.lib().f9_plan_destroy(plan)
+    return [o.cpu().numpy() for o in outs]
+
+
+FEEDS = [{}, {"F9_UMMA_NOCTA2": "1"}, {"F9_UMMA_CTA2": "1"}, {"F9_UMMA_NORANGES": "1"}, {"F9_UMMA_NOTMA": "1"}]
+
+
+@pytest.mark.parametrize("kind", [0, 1])
+def test_umma_feed_variants_are_bit_identical(ctx, O, f9, monkeypatch, kind):
+    """The same plan through CTA pairs, single CTAs, TMA without the allocation lookup (boundary tiles read with guarded
+    loads) and the register loader: identical arithmetic, so identical bits; and all within tolerance of the oracle.
+    Windows are 16-byte aligned (TMA feed), of ragged lengths (odd tile counts exercise the pair padding record)."""
+    torch = pytest.importorskip("torch")
+    x = signal(400000, 41)
+    d = torch.from_numpy(x).cuda()
+    windows = [(0, 70001), (70004, 1), (70008, 26000), (96008, 131000), (227008, 19), (227028, 150000)]
+    got = {}
+    for i, env in enumerate(FEEDS):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        got[i] = _plan_resample_many(ctx, f9, d, windows, kind, 96000, 44100)
+        for k in env:
+            monkeypatch.delenv(k)
+    for (off, n), y in zip(windows, got[0]):
+        ref, _ = O.resample_channel(kind, 96000 / 44100, x[off:off + n], y.shape[0])
+        assert np.max(np.abs(y - ref)) <= TOL, (off, n)
+    for i in range(1, len(FEEDS)):
+        for a, b in zip(got[0], got[i]):
+            assert np.array_equal(a, b), FEEDS[i]
+
+
+def test_umma_memory_outside_the_window_never_leaks(ctx, O, f9):
+    """Boundary tiles read whole boxes through TMA, i.e. real memory before and after the segment's window; the converters
+    must zero it.  The neighbourhood is poisoned with NaN, Inf and huge values: any leak shows up in the output."""
+    torch = pytest.importorskip("torch")
+    n_in, pad = 90000, 4096
+    x = signal(n_in, 42)
+    buf = np.empty(n_in + 2 * pad, dtype=np.float32)
+    buf[:pad] = np.nan; buf[pad:pad + n_in] = x; buf[pad + n_in:] = np.inf
+    buf[pad - 3] = 1e30; buf[pad + n_in + 2] = -1e30
+    d = torch.from_numpy(buf).cuda()
+    for kind in (0, 1):
+        for fs in ((96000, 44100), (48000, 192000), (192000, 48000)):
+            y = _plan_resample_many(ctx, f9, d, [(pad, n_in)], kind, fs[0], fs[1])[0]
+            ref, _ = O.resample_channel(kind, fs[0] / fs[1], x, y.shape[0])
+            assert np.all(np.isfinite(y)), (kind, fs)
+            assert np.max(np.abs(y - ref)) <= 1.5 * TOL, (kind, fs)
+
+
+def test_umma_many_segments_small_grid(ctx, O, f9):
+    """A single tile, two tiles and an odd number of tiles: whole CTA pairs are launched, the odd CTA gets the padding record."""
+    torch = pytest.importorskip("torch")
+    x = signal(300000, 43)
+    d = torch.from_numpy(x).cuda()
+    for n_in in (100, 128 * 320, 128 * 320 + 4, 3 * 128 * 320 - 8):
+        y = _plan_resample_many(ctx, f9, d, [(1024, n_in)], 0, 96000, 44100)[0]
+        ref, _ = O.resample_channel(0, 96000 / 44100, x[1024:1024 + n_in], y.shape[0])
+        assert np.max(np.abs(y - ref)) <= TOL, n_in
