@@ -152,7 +152,7 @@ def run_reference(args, rank: int, world: int):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one umma_fir_kernel launch (ncu --set full, profiles/), by files per GPU
-TRAFFIC_BYTES_PER_LAUNCH = {256: 1.969825e9 + 875.5136e6}      # profiles/r01_v2_umma_fir_full.txt
+TRAFFIC_BYTES_PER_LAUNCH = {256: 2.059729e9 + 874.370048e6}    # profiles/r01_v3_umma_fir_full.txt (dram read + write of one launch)
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -344,7 +344,8 @@ def run_gpu(args, rank: int, local_rank: int, world: int):
                        "seconds_per_file": batch.src_frames / batch.fs_in, "tail_scan": "RMS, 100 ms window / 50 ms hop / 3 consecutive",
                        "trim": "fused into the resampler", "l2": "inputs (%.2f GB per GPU) larger than L2" % (h2d / 1e9),
                        "parallelism": f"files x{world} (weak, no collective)"},
-            "roofline": {"kernel": "umma_fir_kernel (WindowedSinc polyphase FIR on tcgen05: fp16 2-split, fp32 TMEM accumulators)",
+            "roofline": {"kernel": "umma_fir_kernel (WindowedSinc polyphase FIR on tcgen05: TMA-fed CTA pairs, fp16 2-split, fp32 TMEM accumulators; "
+                                   "timed with its tile-table and redo-check launches)",
                          "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
                          "peak_source": peak_src, "traffic": TRAFFIC_BYTES_PER_LAUNCH.get(batch.files),
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kavg,
