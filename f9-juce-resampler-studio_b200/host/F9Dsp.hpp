@@ -7,6 +7,7 @@
 // No JUCE types are needed: AudioBufferView is the read/write-pointer subset of juce::AudioBuffer<float>.
 #pragma once
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <string>
@@ -123,6 +124,60 @@ struct Interpolators {
     using CatmullRom    = GenericInterpolator<F9_CATMULL_ROM>;
     using Linear        = GenericInterpolator<F9_LINEAR>;
     using ZeroOrderHold = GenericInterpolator<F9_ZERO_ORDER_HOLD>;
+};
+
+// ---- juce::AudioSource / juce::ResamplingAudioSource (JUCE 8.0.10 juce_audio_basics/sources), GPU backed -----------------
+struct AudioSourceChannelInfo {
+    AudioBufferView* buffer = nullptr;
+    int startSample = 0, numSamples = 0;
+};
+class AudioSource {
+public:
+    virtual ~AudioSource() = default;
+    virtual void prepareToPlay(int samplesPerBlockExpected, double sampleRate) = 0;
+    virtual void releaseResources() = 0;
+    virtual void getNextAudioBlock(const AudioSourceChannelInfo& bufferToFill) = 0;
+};
+/** Same calls as juce::ResamplingAudioSource.  The input source is pulled on the host exactly as JUCE pulls it
+    (round(numSamples * ratio) + 3 samples minus what is still buffered, in one request); filters and interpolation run on
+    the GPU behind f9_ras_get_next_audio_block. */
+class ResamplingAudioSource : public AudioSource {
+public:
+    ResamplingAudioSource(Context& c, AudioSource* inputSource, bool deleteInputWhenDeleted, int numChannels = 2)
+        : input_(inputSource), own_(deleteInputWhenDeleted), numChannels_(numChannels) { f9_ras_create(c.get(), numChannels, &h_); }
+    ~ResamplingAudioSource() override { f9_ras_destroy(h_); if (own_) delete input_; }
+    ResamplingAudioSource(const ResamplingAudioSource&) = delete;
+    ResamplingAudioSource& operator=(const ResamplingAudioSource&) = delete;
+    void setResamplingRatio(double samplesInPerOutputSample) { f9_ras_set_resampling_ratio(h_, samplesInPerOutputSample); }
+    double getResamplingRatio() const noexcept { return f9_ras_get_resampling_ratio(h_); }
+    void prepareToPlay(int samplesPerBlockExpected, double sampleRate) override {
+        const double ratio = getResamplingRatio();
+        input_->prepareToPlay((int) std::lrint(samplesPerBlockExpected * ratio), sampleRate * ratio);
+        f9_ras_prepare_to_play(h_, samplesPerBlockExpected, sampleRate);
+    }
+    void flushBuffers() { f9_ras_flush_buffers(h_); }
+    void releaseResources() override { input_->releaseResources(); f9_ras_release_resources(h_); }
+    void getNextAudioBlock(const AudioSourceChannelInfo& info) override {
+        const int channels = std::min(numChannels_, info.buffer->numChannels);
+        const int pull = std::max(0, f9_ras_num_samples_to_pull(h_, info.numSamples));
+        pulled_.setSize(numChannels_, std::max(pull, 1));
+        if (pull > 0) {
+            AudioBufferView v = pulled_.view();
+            AudioSourceChannelInfo readInfo; readInfo.buffer = &v; readInfo.startSample = 0; readInfo.numSamples = pull;
+            input_->getNextAudioBlock(readInfo);
+        }
+        std::vector<float*> out((size_t) numChannels_, nullptr);
+        scratch_.setSize(numChannels_, std::max(info.numSamples, 1));
+        for (int c = 0; c < numChannels_; ++c)
+            out[(size_t) c] = c < channels ? info.buffer->channels[c] + info.startSample : scratch_.view().channels[c];
+        f9_ras_get_next_audio_block(h_, pulled_.view().channels, pull, out.data(), info.numSamples);
+    }
+private:
+    AudioSource* input_ = nullptr;
+    bool own_ = false;
+    int numChannels_ = 2;
+    f9_resampling_source* h_ = nullptr;
+    AudioBuffer pulled_, scratch_;
 };
 
 // ---- the MainComponent helper set (Source/MainComponent.h:186-237), GPU backed ---------------------------

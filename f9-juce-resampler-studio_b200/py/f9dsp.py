@@ -97,6 +97,19 @@ SYMBOLS = [
     ("f9_interp_process", _i, [_vp, _d, _fp, _fp, _i]),
     ("f9_interp_process_adding", _i, [_vp, _d, _fp, _fp, _i, _f]),
     ("f9_interp_process_wrap", _i, [_vp, _d, _fp, _fp, _i, _i, _i]),
+    ("f9_ras_create", _i, [_vp, _i, C.POINTER(_vp)]),
+    ("f9_ras_destroy", None, [_vp]),
+    ("f9_ras_set_resampling_ratio", _i, [_vp, _d]),
+    ("f9_ras_get_resampling_ratio", _d, [_vp]),
+    ("f9_ras_prepare_to_play", _i, [_vp, _i, _d]),
+    ("f9_ras_flush_buffers", _i, [_vp]),
+    ("f9_ras_release_resources", _i, [_vp]),
+    ("f9_ras_set_intel_denormal_flush", _i, [_vp, _i]),
+    ("f9_ras_num_samples_to_pull", _i, [_vp, _i]),
+    ("f9_ras_get_next_audio_block", _i, [_vp, _fpp, _i, _fpp, _i]),
+    ("f9_ras_convert", _i, [_vp, _fpp, _i, _ll, _d, _fpp, _ll]),
+    ("f9_ras_scratch_frames", _ll, [_d, _ll]),
+    ("f9_dev_ras_convert", _i, [_vp, _vp, _ll, _i, _ll, _d, _vp, _ll, _ll, _vp, _ll]),
     ("f9_sinc_table_set", _i, [_vp, _fp]),
     ("f9_sinc_table_get", _i, [_vp, _fp]),
     ("f9_resampled_length", _ll, [_ll, _d, _d]),
@@ -425,6 +438,13 @@ class Context:
         self._check(lib().f9_deinterleave(self._h, _p(a), num_ch, frames, _chan_ptrs(out)))
         return out
 
+    # ---- juce::ResamplingAudioSource over whole channels from reset state
+    def ras_convert(self, buf, ratio: float, num_out: int) -> np.ndarray:
+        a = _planar(buf)
+        out = np.empty((a.shape[0], num_out), dtype=np.float32)
+        self._check(lib().f9_ras_convert(self._h, _chan_ptrs(a), a.shape[0], a.shape[1], ratio, _chan_ptrs(out), num_out))
+        return out
+
     # ---- whole-channel conversion through a one-segment job (host buffers)
     def resample(self, buf, fs_in: float, fs_out: float, kind: int, num_out: int | None = None) -> np.ndarray:
         a = _planar(buf)
@@ -433,6 +453,40 @@ class Context:
         if res[0]["status"]:
             raise F9Error(res[0]["status"], "resample failed")
         return outs[0] if num_out is None else outs[0][:, :num_out]
+
+
+class ResamplingAudioSource:
+    """juce::ResamplingAudioSource-shaped object over planar numpy input (the input AudioSource is `source`, read in order)."""
+
+    def __init__(self, ctx: Context, source, num_channels: int | None = None):
+        self._ctx = ctx
+        self._src = _planar(source)
+        self._cursor = 0
+        self._nch = num_channels or self._src.shape[0]
+        self._h = C.c_void_p(None)
+        ctx._check(lib().f9_ras_create(ctx.handle, self._nch, C.byref(self._h)))
+
+    def __del__(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().f9_ras_destroy(self._h)
+            self._h = C.c_void_p(None)
+
+    def set_resampling_ratio(self, ratio: float):
+        self._ctx._check(lib().f9_ras_set_resampling_ratio(self._h, ratio))
+
+    def prepare_to_play(self, samples_per_block: int, sample_rate: float = 44100.0):
+        self._ctx._check(lib().f9_ras_prepare_to_play(self._h, samples_per_block, sample_rate))
+
+    def flush_buffers(self):
+        self._ctx._check(lib().f9_ras_flush_buffers(self._h))
+
+    def get_next_audio_block(self, num_samples: int) -> np.ndarray:
+        out = np.empty((self._nch, num_samples), dtype=np.float32)
+        rest = np.ascontiguousarray(self._src[:, self._cursor:])
+        pulled = self._ctx._check(lib().f9_ras_get_next_audio_block(self._h, _chan_ptrs(rest), rest.shape[1], _chan_ptrs(out), num_samples))
+        self._cursor += min(pulled, rest.shape[1])
+        self.pulled = pulled
+        return out
 
 
 class Interpolator:

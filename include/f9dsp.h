@@ -63,6 +63,7 @@ enum { F9_TAIL_RMS = 0, F9_TAIL_PEAK = 1 };
 typedef struct f9_context f9_context;
 typedef struct f9_interp  f9_interp;
 typedef struct f9_plan    f9_plan;
+typedef struct f9_resampling_source f9_resampling_source;
 
 /* =============================== A. context ================================== */
 /* device: CUDA ordinal.  Fails with F9_ERR_NO_DEVICE when there is no GPU. */
@@ -169,6 +170,39 @@ F9_API int   f9_interp_process_wrap(f9_interp* h, double speed_ratio, const floa
  * default is sinc*Hann.  A host that has JUCE can install the real table here. */
 F9_API int   f9_sinc_table_set(f9_context* ctx, const float* table10001);
 F9_API int   f9_sinc_table_get(const f9_context* ctx, float* table10001);
+
+/* ============ D2. juce::ResamplingAudioSource-shaped object ============ */
+/* [JUCE 8.0.10 juce_audio_basics/sources/juce_ResamplingAudioSource.{h,cpp}; named by north_star next to the
+ * Interpolators, no call site in the reference]  Linear interpolation with a double sub-sample position plus a 2nd-order
+ * Butterworth low-pass (double state): on the pulled input when ratio > 1.0001, on the output when ratio < 0.9999.
+ * One object carries numChannels channels, as JUCE.  The caller plays the role of the input AudioSource: `in` holds the
+ * next samples that source would deliver; past num_in_available it delivers zeros (AudioFormatReaderSource past the end
+ * of a file).  Control flow on the host as in JUCE, filters and interpolation on the GPU in JUCE's operation order. */
+F9_API int    f9_ras_create(f9_context* ctx, int num_channels, f9_resampling_source** out);
+F9_API void   f9_ras_destroy(f9_resampling_source* h);
+F9_API int    f9_ras_set_resampling_ratio(f9_resampling_source* h, double samples_in_per_output_sample); /* setResamplingRatio */
+F9_API double f9_ras_get_resampling_ratio(const f9_resampling_source* h);                                 /* getResamplingRatio */
+F9_API int    f9_ras_prepare_to_play(f9_resampling_source* h, int samples_per_block_expected, double sample_rate);
+F9_API int    f9_ras_flush_buffers(f9_resampling_source* h);                                              /* flushBuffers      */
+F9_API int    f9_ras_release_resources(f9_resampling_source* h);                                          /* releaseResources  */
+/* applyFilter's JUCE_INTEL branch (filter outputs within +-1e-8 are flushed to 0): on by default (x86 build of the reference) */
+F9_API int    f9_ras_set_intel_denormal_flush(f9_resampling_source* h, int on);
+/* getNextAudioBlock(info): fills out[c][0 .. num_samples).  Returns the number of samples pulled from the input source
+ * (round(num_samples * ratio) + 3 - samples still buffered; the caller advances its read position by min(that,
+ * num_in_available)), or a negative status. */
+/* how many samples the next getNextAudioBlock(num_samples) will pull from the input source */
+F9_API int    f9_ras_num_samples_to_pull(const f9_resampling_source* h, int num_samples);
+F9_API int    f9_ras_get_next_audio_block(f9_resampling_source* h, const float* const* in, int num_in_available,
+                                          float* const* out, int num_samples);
+/* Whole channels from reset state (prepareToPlay + getNextAudioBlock until num_out), all channels in one pass; the IIR is
+ * evaluated chunk-parallel (tolerance parity).  Host buffers / device buffers (planar, strides in floats;
+ * d_scratch: num_streams x scratch_stride floats with scratch_stride >= f9_ras_scratch_frames(ratio, num_out)). */
+F9_API int    f9_ras_convert(f9_context* ctx, const float* const* in, int numCh, long long num_in, double ratio,
+                             float* const* out, long long num_out);
+F9_API long long f9_ras_scratch_frames(double ratio, long long num_out);
+F9_API int    f9_dev_ras_convert(f9_context* ctx, const float* d_in, long long in_stride, int num_streams, long long num_in,
+                                 double ratio, float* d_out, long long out_stride, long long num_out,
+                                 float* d_scratch, long long scratch_stride);
 
 /* ======================= E. batch job flow (host buffers) =================== */
 /* One job = one file of the MainComponent/AppState batch flow (Source/MainComponent.cpp:705-805;

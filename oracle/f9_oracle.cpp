@@ -647,3 +647,132 @@ ORC_API void orc_resampling_source_coeffs(double ratio, double* c6) {
     c6[0] = c1; c6[1] = c1 * 2.0; c6[2] = c1; c6[3] = 1.0;
     c6[4] = c1 * 2.0 * (1.0 - nSquared); c6[5] = c1 * (1.0 - std::sqrt(2.0) * n + nSquared);
 }
+
+// ---- the whole class [JUCE-recall: JUCE 8.0.10 juce_audio_basics/sources/juce_ResamplingAudioSource.cpp] ---------------
+// State and control flow of getNextAudioBlock restated member for member: ring buffer of pulled input (pre-filtered when
+// ratio > 1.0001), double subSampleOffset, float lerp `src[pos] + alpha * (src[next] - src[pos])`, post-filter when
+// ratio < 0.9999, filter states "stoked" with the last outputs when no filter runs.  The input AudioSource is the caller's
+// planar arrays with a read cursor; past their end it delivers zeros (what AudioFormatReaderSource does past the end of a
+// file).  applyFilter's JUCE_INTEL branch (outputs within +-1e-8 are flushed to 0) is kept: north_star runs the
+// reference on x86 Linux.  PARITY UNPINNED (no JUCE here, no call site in the reference).
+namespace {
+struct RasFilterState { double x1 = 0, x2 = 0, y1 = 0, y2 = 0; };
+struct Ras {
+    int numChannels = 0;
+    double ratio = 1.0, lastRatio = 1.0;
+    double coefficients[6] = {0, 0, 0, 0, 0, 0};
+    double subSampleOffset = 0.0;
+    int bufferPos = 0, sampsInBuffer = 0, bufferSize = 0;
+    std::vector<std::vector<float>> buffer;
+    std::vector<RasFilterState> filterStates;
+    bool intel = true;
+
+    void setSize(int n, bool keep) {
+        for (auto& b : buffer) { if (!keep) b.assign((size_t) n, 0.0f); else b.resize((size_t) n, 0.0f); }
+        bufferSize = n;
+    }
+    void createLowPass(double frequencyRatio) {
+        double c[6]; orc_resampling_source_coeffs(frequencyRatio, c);
+        const double a = 1.0 / c[3];                                    // setFilterCoefficients
+        coefficients[0] = c[0] * a; coefficients[1] = c[1] * a; coefficients[2] = c[2] * a; coefficients[3] = c[3];
+        coefficients[4] = c[4] * a; coefficients[5] = c[5] * a;
+    }
+    void resetFilters() { for (auto& f : filterStates) f = RasFilterState(); }
+    void flushBuffers() { for (auto& b : buffer) std::fill(b.begin(), b.end(), 0.0f); bufferPos = 0; sampsInBuffer = 0; subSampleOffset = 0.0; resetFilters(); }
+    void prepareToPlay(int samplesPerBlockExpected) {
+        const int scaledBlockSize = (int) std::lrint(samplesPerBlockExpected * ratio);        // roundToInt
+        buffer.assign((size_t) numChannels, std::vector<float>());
+        setSize(scaledBlockSize + 32, false);
+        filterStates.assign((size_t) numChannels, RasFilterState());
+        createLowPass(ratio);
+        flushBuffers();
+    }
+    void applyFilter(float* samples, int num, RasFilterState& fs) const {
+        while (--num >= 0) {
+            const double in = *samples;
+            double out = coefficients[0] * in + coefficients[1] * fs.x1 + coefficients[2] * fs.x2
+                         - coefficients[4] * fs.y1 - coefficients[5] * fs.y2;
+            if (intel && !(out < -1.0e-8 || out > 1.0e-8)) out = 0;
+            fs.x2 = fs.x1; fs.x1 = in; fs.y2 = fs.y1; fs.y1 = out;
+            *samples++ = (float) out;
+        }
+    }
+    // returns the number of samples pulled from the input source
+    long long getNextAudioBlock(const float* const* in, long long inTotal, long long cursor, float* const* out, int numSamples) {
+        const long long cursor0 = cursor;
+        const double localRatio = ratio;
+        if (lastRatio != localRatio) { createLowPass(localRatio); lastRatio = localRatio; }
+        const int sampsNeeded = (int) std::lrint(numSamples * localRatio) + 3;
+        if (bufferSize < sampsNeeded + 8) {
+            bufferPos %= bufferSize;
+            setSize(sampsNeeded + 32, true);
+        }
+        bufferPos %= bufferSize;
+        int endOfBufferPos = bufferPos + sampsInBuffer;
+        const int channelsToProcess = numChannels;
+        while (sampsNeeded > sampsInBuffer) {
+            endOfBufferPos %= bufferSize;
+            const int numToDo = std::min(sampsNeeded - sampsInBuffer, bufferSize - endOfBufferPos);
+            for (int c = 0; c < channelsToProcess; ++c)                                       // input->getNextAudioBlock(readInfo)
+                for (int i = 0; i < numToDo; ++i) {
+                    const long long s = cursor + i;
+                    buffer[(size_t) c][(size_t) (endOfBufferPos + i)] = s < inTotal ? in[c][s] : 0.0f;
+                }
+            cursor += numToDo;
+            if (localRatio > 1.0001)
+                for (int i = channelsToProcess; --i >= 0;) applyFilter(buffer[(size_t) i].data() + endOfBufferPos, numToDo, filterStates[(size_t) i]);
+            sampsInBuffer += numToDo;
+            endOfBufferPos += numToDo;
+        }
+        int nextPos = (bufferPos + 1) % bufferSize;
+        for (int m = 0; m < numSamples; ++m) {
+            const float alpha = (float) subSampleOffset;
+            for (int c = 0; c < channelsToProcess; ++c) {
+                const float* src = buffer[(size_t) c].data();
+                out[c][m] = src[bufferPos] + alpha * (src[nextPos] - src[bufferPos]);
+            }
+            subSampleOffset += localRatio;
+            while (subSampleOffset >= 1.0) {
+                if (++bufferPos >= bufferSize) bufferPos = 0;
+                --sampsInBuffer;
+                nextPos = (bufferPos + 1) % bufferSize;
+                subSampleOffset -= 1.0;
+            }
+        }
+        if (localRatio < 0.9999) {
+            for (int i = channelsToProcess; --i >= 0;) applyFilter(out[i], numSamples, filterStates[(size_t) i]);
+        } else if (localRatio <= 1.0001 && numSamples > 0) {
+            for (int i = channelsToProcess; --i >= 0;) {
+                const float* endOfBuffer = out[i] + numSamples - 1;
+                RasFilterState& fs = filterStates[(size_t) i];
+                if (numSamples > 1) fs.y2 = fs.x2 = *(endOfBuffer - 1);
+                else { fs.y2 = fs.y1; fs.x2 = fs.x1; }
+                fs.y1 = fs.x1 = *endOfBuffer;
+            }
+        }
+        return cursor - cursor0;
+    }
+};
+}  // namespace
+
+ORC_API void* orc_ras_create(int numChannels, int intelFlush) { Ras* r = new Ras(); r->numChannels = numChannels; r->intel = intelFlush != 0; return r; }
+ORC_API void orc_ras_destroy(void* p) { delete (Ras*) p; }
+ORC_API void orc_ras_set_ratio(void* p, double samplesInPerOutputSample) { ((Ras*) p)->ratio = std::max(0.0, samplesInPerOutputSample); }
+ORC_API void orc_ras_prepare(void* p, int samplesPerBlockExpected) { ((Ras*) p)->prepareToPlay(samplesPerBlockExpected); }
+ORC_API void orc_ras_flush(void* p) { ((Ras*) p)->flushBuffers(); }
+ORC_API long long orc_ras_get_next_block(void* p, const float* const* in, long long inTotal, long long cursor, float* const* out, int numSamples) {
+    return ((Ras*) p)->getNextAudioBlock(in, inTotal, cursor, out, numSamples);
+}
+// Whole file from reset state in blocks of `block` output samples (the result does not depend on the block size: every input
+// sample is pulled and filtered exactly once, in order).
+ORC_API void orc_ras_convert(int numCh, const float* const* in, long long nIn, double ratio, float* const* out, long long numOut, int block, int intelFlush) {
+    Ras r; r.numChannels = numCh; r.intel = intelFlush != 0; r.ratio = std::max(0.0, ratio); r.lastRatio = r.ratio;
+    r.prepareToPlay(block);
+    std::vector<float*> o((size_t) numCh);
+    long long cursor = 0;
+    for (long long done = 0; done < numOut; done += block) {
+        const int n = (int) std::min<long long>(block, numOut - done);
+        for (int c = 0; c < numCh; ++c) o[(size_t) c] = out[c] + done;
+        cursor += r.getNextAudioBlock(in, nIn, cursor, o.data(), n);
+    }
+}

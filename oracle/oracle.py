@@ -112,6 +112,20 @@ def lib():
         L.orc_deinterleave.argtypes = [_fp, C.c_int, C.c_longlong, _fpp]
         L.orc_resampling_source_coeffs.restype = None
         L.orc_resampling_source_coeffs.argtypes = [C.c_double, C.POINTER(C.c_double)]
+        L.orc_ras_create.restype = C.c_void_p
+        L.orc_ras_create.argtypes = [C.c_int, C.c_int]
+        L.orc_ras_destroy.restype = None
+        L.orc_ras_destroy.argtypes = [C.c_void_p]
+        L.orc_ras_set_ratio.restype = None
+        L.orc_ras_set_ratio.argtypes = [C.c_void_p, C.c_double]
+        L.orc_ras_prepare.restype = None
+        L.orc_ras_prepare.argtypes = [C.c_void_p, C.c_int]
+        L.orc_ras_flush.restype = None
+        L.orc_ras_flush.argtypes = [C.c_void_p]
+        L.orc_ras_get_next_block.restype = C.c_longlong
+        L.orc_ras_get_next_block.argtypes = [C.c_void_p, _fpp, C.c_longlong, C.c_longlong, _fpp, C.c_int]
+        L.orc_ras_convert.restype = None
+        L.orc_ras_convert.argtypes = [C.c_int, _fpp, C.c_longlong, C.c_double, _fpp, C.c_longlong, C.c_int, C.c_int]
         _lib = L
     return _lib
 
@@ -379,3 +393,39 @@ def resampling_source_coeffs(ratio: float) -> np.ndarray:
     c = (C.c_double * 6)()
     lib().orc_resampling_source_coeffs(ratio, c)
     return np.array(list(c))
+
+
+class ResamplingAudioSource:
+    """juce::ResamplingAudioSource restated (f9_oracle.cpp): the input source is a planar array read in order."""
+
+    def __init__(self, source, intel_flush: bool = True):
+        self._src = _planar(source)
+        self._cursor = 0
+        self._h = lib().orc_ras_create(self._src.shape[0], int(intel_flush))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_ras_destroy(self._h)
+            self._h = None
+
+    def set_resampling_ratio(self, ratio: float):
+        lib().orc_ras_set_ratio(self._h, ratio)
+
+    def prepare_to_play(self, samples_per_block: int):
+        lib().orc_ras_prepare(self._h, samples_per_block)
+
+    def flush_buffers(self):
+        lib().orc_ras_flush(self._h)
+
+    def get_next_audio_block(self, num_samples: int) -> np.ndarray:
+        out = np.empty((self._src.shape[0], num_samples), dtype=np.float32)
+        self.pulled = lib().orc_ras_get_next_block(self._h, _chan_ptrs(self._src), self._src.shape[1], self._cursor, _chan_ptrs(out), num_samples)
+        self._cursor += self.pulled
+        return out
+
+
+def ras_convert(buf, ratio: float, num_out: int, block: int = 512, intel_flush: bool = True) -> np.ndarray:
+    a = _planar(buf)
+    out = np.empty((a.shape[0], num_out), dtype=np.float32)
+    lib().orc_ras_convert(a.shape[0], _chan_ptrs(a), a.shape[1], ratio, _chan_ptrs(out), num_out, block, int(intel_flush))
+    return out

@@ -38,6 +38,34 @@ int main(int argc, char** argv) {
     const int used1 = sinc.process(0.91875, cap.getReadPointer(0), o1.data(), numOut);
     const int used2 = lag.process(0.91875, cap.getReadPointer(1), o2.data(), numOut);
 
+    // juce::ResamplingAudioSource over an AudioSource that reads the capture (zeros past its end), three uneven blocks
+    struct MemorySource : f9::AudioSource {
+        const f9::AudioBuffer& src; int pos = 0;
+        explicit MemorySource(const f9::AudioBuffer& s) : src(s) {}
+        void prepareToPlay(int, double) override {}
+        void releaseResources() override {}
+        void getNextAudioBlock(const f9::AudioSourceChannelInfo& info) override {
+            for (int c = 0; c < info.buffer->numChannels; ++c)
+                for (int i = 0; i < info.numSamples; ++i)
+                    info.buffer->channels[c][info.startSample + i] = pos + i < src.getNumSamples() ? src.getReadPointer(c)[pos + i] : 0.0f;
+            pos += info.numSamples;
+        }
+    };
+    const int rasBlocks[3] = {512, 333, 1155};
+    f9::AudioBuffer rasOut(2, 2000);
+    {
+        f9::ResamplingAudioSource ras(ctx, new MemorySource(cap), true, 2);
+        ras.setResamplingRatio(96000.0 / 44100.0);
+        ras.prepareToPlay(512, 44100.0);
+        f9::AudioBufferView v = rasOut.view();
+        int at = 0;
+        for (int b = 0; b < 3; ++b) {
+            f9::AudioSourceChannelInfo info; info.buffer = &v; info.startSample = at; info.numSamples = rasBlocks[b];
+            ras.getNextAudioBlock(info);
+            at += rasBlocks[b];
+        }
+    }
+
     FILE* g = std::fopen(argv[2], "wb");
     if (!g) return 5;
     int32_t hdr[8] = {measured ? 1 : 0, settings.measuredLatencySamples, below ? 1 : 0, used1, used2, numOut,
@@ -49,6 +77,7 @@ int main(int argc, char** argv) {
     for (int c = 0; c < 2; ++c) std::fwrite(trimmedOnly.getReadPointer(c), 4, (size_t) playback, g);
     std::fwrite(o1.data(), 4, (size_t) numOut, g);
     std::fwrite(o2.data(), 4, (size_t) numOut, g);
+    for (int c = 0; c < 2; ++c) std::fwrite(rasOut.getReadPointer(c), 4, 2000, g);
     std::fclose(g);
     return 0;
 }

@@ -41,7 +41,8 @@ def test_host_mirror_matches_oracle(O, tmp_path):
     body = np.frombuffer(raw[40:], np.float32)
     trimmed = body[: 2 * playback].reshape(2, playback)
     trimmed_only = body[2 * playback: 4 * playback].reshape(2, playback)
-    o1, o2 = body[4 * playback: 4 * playback + 4000], body[4 * playback + 4000:]
+    o1, o2 = body[4 * playback: 4 * playback + 4000], body[4 * playback + 4000: 4 * playback + 8000]
+    ras = body[4 * playback + 8000:].reshape(2, 2000)
     assert hdr[0] == 1 and hdr[1] == 2 * O.find_peak_position(cap, 0.1) == 2 * lat
     assert abs(nf - float(O.noise_floor_db(cap))) <= 1e-5 and abs(rms - float(O.calculate_rms(cap))) <= 1e-9
     t, _ = O.trim_latency(cap, 2 * lat, playback)
@@ -53,3 +54,9 @@ def test_host_mirror_matches_oracle(O, tmp_path):
     assert (hdr[3], hdr[4], hdr[5], hdr[6]) == (u1, u2, 4000, playback)
     assert hdr[7] == O.recording_length(playback, lat)
     assert np.max(np.abs(o1 - y1)) <= 2.0 ** -20 and np.max(np.abs(o2 - y2)) <= 2.0 ** -20
+    # juce::ResamplingAudioSource through the AudioSource-shaped mirror: bit-exact against the oracle's object
+    src = O.ResamplingAudioSource(cap)
+    src.set_resampling_ratio(96000.0 / 44100.0)
+    src.prepare_to_play(512)
+    ref = np.concatenate([src.get_next_audio_block(n) for n in (512, 333, 1155)], axis=1)
+    assert np.array_equal(ras, ref)
