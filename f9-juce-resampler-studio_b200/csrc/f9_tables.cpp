@@ -360,12 +360,14 @@ void umma_choose_plan(int taps, long long p, long long q, long long* m_out, int*
                 size_t smem2 = 0;
                 double c = umma_cost_per_output(taps, ps, qs, NB, GBL, &smem2);
                 if (smem2 > 227 * 1024) continue;
-                if (ps & 3) c *= 1.25;                                          // rows not 16-byte aligned: the loader funnels
+                if (ps & 3) c *= taps >= 64 ? 1.4 : 1.25;                       // rows not 16-byte aligned: register loader instead of the TMA feed
                 if (c < 0.97 * best) { best = c; *m_out = m; *GBL_out = GBL; *NB_out = NB; }    // ties go to the smaller plan
                 break;                                                          // more blocks only cost more
             }
         }
-        if (qs >= 224) break;
+        // rows not yet 16-byte aligned: a multiple of the period may be, which buys the TMA feed (measured 1.6x for the 200-tap
+        // kernel at 147/160; the short kinds are faster on the register loader than on a plan with more blocks)
+        if (qs >= 224 && ((ps & 3) == 0 || m >= 4 || taps < 64)) break;
     }
 }
 
