@@ -931,7 +931,11 @@ bool umma_encode_maps(const Seg* segs, int n, int p, UmmaTma* out) {
 }
 
 cudaError_t launch_umma(const ResampleLaunch& L, cudaStream_t s, long long* launches) {
-    static bool attr_done = false;
+    // the opt-in shared-memory size is a per-device function attribute (one context per GPU may share this process)
+    static unsigned long long attr_done_mask = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    const bool attr_done = dev < 64 && ((attr_done_mask >> dev) & 1ull);
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(umma_fir_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(umma_fir_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -939,7 +943,7 @@ cudaError_t launch_umma(const ResampleLaunch& L, cudaStream_t s, long long* laun
         if (e == cudaSuccess) e = cudaFuncSetAttribute(umma_fir_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(umma_fir_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
-        attr_done = true;
+        if (dev < 64) attr_done_mask |= 1ull << dev;
     }
     int grid = std::min(L.n_tiles, std::max(L.sm_count, L.um.nGB));
     grid -= grid % L.um.nGB;
