@@ -274,17 +274,23 @@ __global__ void fill_int_kernel(int* p, size_t n, int v) {
 // double and fma(x, y, acc) rounds once, so a thread that walks i in order reproduces the sequential CPU
 // sum bit for bit; the argmax below then needs no guard band.  One thread per lag, one CTA per
 // (buffer, channel, tile of kXcLags lags); y staged through shared memory in stimulus-sized chunks.
-constexpr int kXcLags = 256;
-constexpr int kXcChunk = 512;
+constexpr int kXcThreads = 256;
+constexpr int kXcR = 8;                          // consecutive lags per thread (register tile)
+constexpr int kXcLags = kXcThreads * kXcR;       // lags per CTA
+constexpr int kXcChunk = 512;                    // stimulus samples per shared-memory chunk
+constexpr int kXcPlane = (kXcChunk + kXcLags) / kXcR + 1;
 
 __device__ __forceinline__ bool xc_better(double v, int ch, int lag, double bv, int bch, int blag) {
-    if (v > bv) return true;
-    if (v < bv) return false;
-    if (ch != bch) return ch < bch;
-    return lag < blag;
+    return v > bv || (v == bv && (ch < bch || (ch == bch && lag < blag)));
 }
 
-__global__ void __launch_bounds__(kXcLags)
+// Register-tiled direct form.  A thread owns kXcR consecutive lags and walks the stimulus in order (every sum is the same fma
+// chain as the scalar code: bit-exact doubles, hence an exact argmax).  Per stimulus sample it needs one new recording
+// sample: x and y are converted to double once when a chunk is staged, and y is stored in kXcR interleaved planes
+// (element e in plane e % R at offset e / R) so that the "new sample" loads of a warp are consecutive doubles.  Per tap:
+// one broadcast load, one conflict-free load, kXcR DFMAs (the one-lag-per-thread version spent two loads and two
+// float->double conversions per DFMA: 4.5 TFLOP/s).
+__global__ void __launch_bounds__(kXcThreads)
 xcorr_partial_kernel(const DevBuf* __restrict__ bufs, const int* __restrict__ prefix, int n,
                      const float* __restrict__ stim, int stimLen, int lagMin, int lagMax, XcPartial* __restrict__ partials) {
     int lo = 0, hi = n;
@@ -296,38 +302,67 @@ xcorr_partial_kernel(const DevBuf* __restrict__ bufs, const int* __restrict__ pr
     const int tiles = (nLags + kXcLags - 1) / kXcLags;
     const int ch = local / tiles, tile = local - ch * tiles;
     const int lag0 = lagMin + tile * kXcLags;
-    const int lag = lag0 + threadIdx.x;
+    const int t = threadIdx.x;
     const float* __restrict__ y = B.base + (long long) ch * B.chStride;
 
-    __shared__ float xs[kXcChunk];
-    __shared__ float ys[kXcChunk + kXcLags];
-    double acc = 0.0;
+    __shared__ double xs[kXcChunk];
+    __shared__ double ys[kXcR][kXcPlane];
+    double acc[kXcR];
+    #pragma unroll
+    for (int r = 0; r < kXcR; ++r) acc[r] = 0.0;
     for (int c0 = 0; c0 < stimLen; c0 += kXcChunk) {
         const int clen = min(kXcChunk, stimLen - c0);
-        for (int i = threadIdx.x; i < clen; i += kXcLags) xs[i] = stim[c0 + i];
-        for (int i = threadIdx.x; i < clen + kXcLags; i += kXcLags) {
-            const long long g = (long long) c0 + lag0 + i;
-            ys[i] = (g >= 0 && g < B.numFrames) ? y[g] : 0.0f;
+        for (int i = t; i < clen; i += kXcThreads) xs[i] = (double) stim[c0 + i];
+        for (int e = t; e < clen + kXcLags; e += kXcThreads) {              // element e = recording sample c0 + lag0 + e
+            const long long g = (long long) c0 + lag0 + e;
+            ys[e % kXcR][e / kXcR] = (g >= 0 && g < B.numFrames) ? (double) y[g] : 0.0;
         }
         __syncthreads();
-        #pragma unroll 4
-        for (int i = 0; i < clen; ++i) acc = fma((double) xs[i], (double) ys[i + threadIdx.x], acc);
+        // window w[r] = element i + kXcR * t + r; tap i multiplies w[0 .. R-1], then the window slides by one element
+        double w[kXcR];
+        #pragma unroll
+        for (int r = 0; r < kXcR; ++r) w[r] = ys[r][t];                       // elements kXcR * t + r
+        int i = 0;
+        for (; i + kXcR <= clen; i += kXcR) {                                  // i stays a multiple of kXcR: static plane indices
+            const int q = i / kXcR + t;
+            #pragma unroll
+            for (int u = 0; u < kXcR; ++u) {
+                const double x = xs[i + u];
+                #pragma unroll
+                for (int r = 0; r < kXcR; ++r) acc[r] = fma(x, w[(u + r) % kXcR], acc[r]);
+                w[u] = ys[u][q + 1];                                          // element i + u + kXcR * (t + 1): the window's next sample
+            }
+        }
+        for (; i < clen; ++i) {                                                // chunk tail (clen not a multiple of kXcR)
+            const double x = xs[i];
+            #pragma unroll
+            for (int r = 0; r < kXcR; ++r) {
+                const int e = i + kXcR * t + r;
+                acc[r] = fma(x, ys[e % kXcR][e / kXcR], acc[r]);
+            }
+        }
         __syncthreads();
     }
-    double v = (lag <= lagMax) ? fabs(acc) : -1.0;
-    int blag = lag;
+    // best of this thread's lags (ascending lag, strict >: ties keep the lower lag), then warp, then block
+    double v = -1.0; int blag = 0x7fffffff;
+    #pragma unroll
+    for (int r = 0; r < kXcR; ++r) {
+        const int lag = lag0 + kXcR * t + r;
+        const double a = fabs(acc[r]);
+        if (lag <= lagMax && a > v) { v = a; blag = lag; }
+    }
     #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
         const double ov = __shfl_xor_sync(0xffffffffu, v, off);
         const int ol = __shfl_xor_sync(0xffffffffu, blag, off);
         if (ov > v || (ov == v && ol < blag)) { v = ov; blag = ol; }
     }
-    __shared__ double sv[kXcLags / 32]; __shared__ int sl[kXcLags / 32];
+    __shared__ double sv[kXcThreads / 32]; __shared__ int sl[kXcThreads / 32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (lane == 0) { sv[warp] = v; sl[warp] = blag; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int w = 1; w < kXcLags / 32; ++w) if (sv[w] > v || (sv[w] == v && sl[w] < blag)) { v = sv[w]; blag = sl[w]; }
+        for (int wi = 1; wi < kXcThreads / 32; ++wi) if (sv[wi] > v || (sv[wi] == v && sl[wi] < blag)) { v = sv[wi]; blag = sl[wi]; }
         XcPartial r; r.v = v; r.ch = ch; r.lag = blag; r.pad = 0;
         partials[bid] = r;
     }
@@ -407,7 +442,7 @@ cudaError_t launch_xcorr(const DevBuf* d_bufs, int n, int total_ctas, const int*
                          int lagMin, int lagMax, XcPartial* d_partials, XcPartial* d_best, cudaStream_t s, long long* launches) {
     if (n <= 0) return cudaSuccess;
     if (total_ctas > 0) {
-        xcorr_partial_kernel<<<total_ctas, kXcLags, 0, s>>>(d_bufs, d_prefix, n, d_stim, stimLen, lagMin, lagMax, d_partials);
+        xcorr_partial_kernel<<<total_ctas, kXcThreads, 0, s>>>(d_bufs, d_prefix, n, d_stim, stimLen, lagMin, lagMax, d_partials);
         ++*launches;
     }
     xcorr_final_kernel<<<(n + 127) / 128, 128, 0, s>>>(d_partials, d_prefix, n, d_best);
