@@ -355,19 +355,25 @@ void umma_choose_plan(int taps, long long p, long long q, long long* m_out, int*
         for (int NB : {32, 16}) {
             if (getenv("F9_UMMA_NB") && atoi(getenv("F9_UMMA_NB")) != NB) continue;
             const int G = (int) ((qs + NB - 1) / NB), maxG = std::min(kUmmaMaxGroups, 448 / (2 * NB));
-            for (int nGB = (G + maxG - 1) / maxG; nGB <= kUmmaMaxBlocks && nGB <= G; ++nGB) {
+            // a period scaled for alignment (m > 1 of an unaligned p) splits best into blocks of whole original periods: every
+            // block then has the window of one period, as the unscaled plan's tiles have
+            int nGB0 = (G + maxG - 1) / maxG;
+            if (m > 1 && (p & 3) != 0)
+                for (int d = (int) m; d > nGB0; --d)
+                    if (m % d == 0 && G % d == 0 && G / d <= maxG) { nGB0 = d; break; }
+            for (int nGB = nGB0; nGB <= kUmmaMaxBlocks && nGB <= G; ++nGB) {
                 const int GBL = (G + nGB - 1) / nGB;
                 size_t smem2 = 0;
                 double c = umma_cost_per_output(taps, ps, qs, NB, GBL, &smem2);
                 if (smem2 > 227 * 1024) continue;
-                if (ps & 3) c *= taps >= 64 ? 1.4 : 1.25;                       // rows not 16-byte aligned: register loader instead of the TMA feed
+                if (ps & 3) c *= 1.4;                           // rows not 16-byte aligned: register loader instead of the TMA feed
                 if (c < 0.97 * best) { best = c; *m_out = m; *GBL_out = GBL; *NB_out = NB; }    // ties go to the smaller plan
                 break;                                                          // more blocks only cost more
             }
         }
-        // rows not yet 16-byte aligned: a multiple of the period may be, which buys the TMA feed (measured 1.6x for the 200-tap
-        // kernel at 147/160; the short kinds are faster on the register loader than on a plan with more blocks)
-        if (qs >= 224 && ((ps & 3) == 0 || m >= 4 || taps < 64)) break;
+        // rows not yet 16-byte aligned: a multiple of the period may be, which buys the TMA feed (measured at 147/160: 1.6x for
+        // the 200-tap kernel, 1.33x for Lagrange once the blocks are whole original periods)
+        if (qs >= 224 && ((ps & 3) == 0 || m >= 4)) break;
     }
 }
 
