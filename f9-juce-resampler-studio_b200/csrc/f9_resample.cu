@@ -400,7 +400,9 @@ long long resample_ctas_for_segment(const ResampleLaunch& L, long long n0, long 
     if (L.umma) {
         const long long q = L.um.q;
         const long long aFirst = n0 / q, aLast = (n0 + numOut - 1) / q;
-        return ((aLast - aFirst + 1 + 127) / 128) * L.um.nGB;
+        long long blocks = (aLast - aFirst + 1 + 127) / 128;
+        if (L.um_tma && L.um_cta2 && L.um.nGB > 1) blocks += blocks & 1;       // CTA pairs walk two period blocks of the same slot block
+        return blocks * L.um.nGB;
     }
     if (!L.banded) return (numOut + L.tile_out - 1) / L.tile_out;
     const long long q = L.band.q;
@@ -425,7 +427,9 @@ int resample_build_tiles(ResampleLaunch& L, const Seg* segs, int n, std::vector<
         if (L.um_aligned && getenv("F9_UMMA_NOTMA") == nullptr) {
             if (umma_encode_maps(segs, n, L.um.p, &L.um_maps)) {
                 // CTA pairs halve the weights per SM: worth it when the weights leave a single CTA only a shallow input ring
-                const bool cta2 = L.um.blk[0].w2Off[0] >= 0 && L.sm_count >= 2 && getenv("F9_UMMA_NOCTA2") == nullptr &&
+                // (with several slot blocks only when the TMEM operand ring has four stages: measured slower otherwise, 147/160)
+                const bool cta2 = L.um.blk[0].w2Off[0] >= 0 && L.sm_count >= 2 * L.um.nGB && getenv("F9_UMMA_NOCTA2") == nullptr &&
+                                  (L.um.nGB == 1 || L.um.aSlots == 4) &&
                                   (umma_smem_bytes(L.um.maxEntries, L.um.NB, 4, true) > 227 * 1024 || getenv("F9_UMMA_CTA2") != nullptr);
                 int stages = 2;
                 const int maxStages = getenv("F9_UMMA_STAGES") ? atoi(getenv("F9_UMMA_STAGES")) : 8;

@@ -534,19 +534,21 @@ bool build_umma(int kind, const float* sinc_table, long long p, long long q, int
     }
     // CTA-pair kernel: the weight tiles again, split by slot halves (cluster rank r holds slots 16 r .. 16 r + 15 of every group)
     for (int b = 0; b < nGB; ++b) out->blk[b].w2Off[0] = out->blk[b].w2Off[1] = -1;
-    if (nGB == 1 && NB == 32) {
-        UmmaBlockInfo& BI = out->blk[0];
-        for (int r = 0; r < 2; ++r) {
-            BI.w2Off[r] = (int) out->W.size();
-            out->W.resize(out->W.size() + (size_t) BI.nEntries * 1024, 0);
-            for (int e = 0; e < BI.nEntries; ++e) {
-                const uint8_t* src = out->W.data() + BI.wOff + (size_t) e * tileBytes;
-                uint8_t* dst = out->W.data() + BI.w2Off[r] + (size_t) e * 1024;
-                for (int c = 0; c < 2; ++c)
-                    for (int i = 0; i < 16; ++i) {
-                        std::memcpy(dst + c * 512 + i * 16, src + (size_t) c * chunkBytes + (size_t) (16 * r + i) * 16, 16);
-                        std::memcpy(dst + c * 512 + 256 + i * 16, src + (size_t) c * chunkBytes + (size_t) NB * 16 + (size_t) (16 * r + i) * 16, 16);
-                    }
+    if (NB == 32) {
+        for (int b = 0; b < nGB; ++b) {
+            UmmaBlockInfo& BI = out->blk[b];
+            for (int r = 0; r < 2; ++r) {
+                BI.w2Off[r] = (int) out->W.size();
+                out->W.resize(out->W.size() + (size_t) BI.nEntries * 1024, 0);
+                for (int e = 0; e < BI.nEntries; ++e) {
+                    const uint8_t* src = out->W.data() + BI.wOff + (size_t) e * tileBytes;
+                    uint8_t* dst = out->W.data() + BI.w2Off[r] + (size_t) e * 1024;
+                    for (int c = 0; c < 2; ++c)
+                        for (int i = 0; i < 16; ++i) {
+                            std::memcpy(dst + c * 512 + i * 16, src + (size_t) c * chunkBytes + (size_t) (16 * r + i) * 16, 16);
+                            std::memcpy(dst + c * 512 + 256 + i * 16, src + (size_t) c * chunkBytes + (size_t) NB * 16 + (size_t) (16 * r + i) * 16, 16);
+                        }
+                }
             }
         }
     }

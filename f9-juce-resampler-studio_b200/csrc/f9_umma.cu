@@ -515,7 +515,9 @@ umma_fir_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix
     const int NB = P.NB;                                       // slots per group: MMA N
     const int aMask = P.aSlots - 1, aShift = P.aSlots == 4 ? 2 : 1, aCol = 512 - 32 * P.aSlots;   // TMEM operand ring
     const int warp = __shfl_sync(0xffffffffu, (int) (threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-    const int gb = blockIdx.x % P.nGB;
+    // slot block of this CTA: tile t belongs to block t % nGB; with CTA pairs tiles are dealt two at a time, (t / 2) % nGB, so
+    // that both CTAs of a pair hold the same weights (the grid is a multiple of 2 * nGB: the block never changes)
+    const int gb = CTA2 ? (int) (blockIdx.x >> 1) % P.nGB : (int) blockIdx.x % P.nGB;
     const UmmaBlockInfo& BI = P.blk[gb];
     const int p = P.p, q = P.q;
     const int nStages = BI.nStages;                            // stages per tile (two K steps each)
@@ -809,7 +811,7 @@ umma_fir_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix
 // One thread per tile: the record the TMA-fed kernel's roles read instead of searching the segment table.
 __global__ void __launch_bounds__(256)
 umma_tile_table_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix, int nSegs, int nTiles,
-                       const __grid_constant__ UmmaDev P, const __grid_constant__ UmmaTma TM, UmmaTileRec* __restrict__ recs) {
+                       const __grid_constant__ UmmaDev P, const __grid_constant__ UmmaTma TM, UmmaTileRec* __restrict__ recs, int pairs) {
     const int tileId = blockIdx.x * blockDim.x + threadIdx.x;
     if (tileId > nTiles) return;
     if (tileId == nTiles) {                                     // padding for CTA pairs: a tile without input or output
@@ -817,10 +819,13 @@ umma_tile_table_kernel(const Seg* __restrict__ segs, const int* __restrict__ til
         recs[tileId] = R;
         return;
     }
-    const UmmaBlockInfo& BI = P.blk[tileId % P.nGB];            // every segment owns a multiple of nGB tiles
+    // every segment owns a multiple of nGB tiles (of 2 * nGB with CTA pairs, which take two period blocks of one slot block)
     const int sidx = find_seg(tilePrefix, nSegs, tileId);
     const Seg S = segs[sidx];
-    const int pb = (tileId - tilePrefix[sidx]) / P.nGB;
+    const int local = tileId - tilePrefix[sidx];
+    const int gbT = pairs ? (local >> 1) % P.nGB : local % P.nGB;
+    const int pb = pairs ? 2 * ((local >> 1) / P.nGB) + (local & 1) : local / P.nGB;
+    const UmmaBlockInfo& BI = P.blk[gbT];
     const long long A0 = S.n0 / P.q + (long long) pb * kRows;
     UmmaTileRec R;
     R.in = S.in; R.out = S.out; R.inAvail = S.inAvail; R.numOut = S.numOut;
@@ -847,8 +852,8 @@ __global__ void __launch_bounds__(256)
 umma_redo_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix, int nSegs, int nTiles, int nGB, int q16,
                  PolyDev W, const unsigned* __restrict__ ovf) {
     if (*ovf == 0u) return;
-    for (int tileId = blockIdx.x; tileId < nTiles; tileId += gridDim.x) {
-        if (tileId % nGB != 0) continue;                       // one pass per period block covers all slots
+    for (int blk = blockIdx.x; blk < nTiles / nGB; blk += gridDim.x) {       // one pass per period block covers all slots
+        const int tileId = blk * nGB;                          // a segment owns a multiple of nGB tiles: block index -> segment
         const int sidx = find_seg(tilePrefix, nSegs, tileId);
         const Seg S = segs[sidx];
         const int pb = (tileId - tilePrefix[sidx]) / nGB;
@@ -949,7 +954,11 @@ cudaError_t launch_umma(const ResampleLaunch& L, cudaStream_t s, long long* laun
     grid -= grid % L.um.nGB;
     if (grid <= 0) return cudaErrorInvalidValue;
     const bool pairs = L.um_tma && L.um_cta2;
-    if (pairs) grid = std::min((grid + 1) & ~1, L.sm_count & ~1);   // whole pairs; the table has a padding record for an odd last tile
+    if (pairs) {                                               // whole pairs, a multiple of 2 * nGB; the table has a padding record for an odd last tile
+        const int unit = 2 * L.um.nGB;
+        grid = std::min((grid + unit - 1) / unit * unit, L.sm_count / unit * unit);
+        if (grid <= 0) return cudaErrorInvalidValue;
+    }
     cudaError_t e = cudaMemsetAsync(L.d_ovf, 0, sizeof(unsigned), s);
     if (e != cudaSuccess) return e;
     // F9_UMMA_PROF=1 (development): per-role cycle accounting of the first launch, printed to stderr
@@ -962,7 +971,8 @@ cudaError_t launch_umma(const ResampleLaunch& L, cudaStream_t s, long long* laun
         L.um, L.um_maps, L.d_tile_recs, L.um_stages, L.um_aligned ? 1 : 0, L.d_ovf, doProf ? d_prof : nullptr, dbg)
     if (L.um_tma) {
         if (!L.d_tile_recs) return cudaErrorInvalidValue;
-        umma_tile_table_kernel<<<(L.n_tiles + 256) / 256, 256, 0, s>>>(L.d_segs, L.d_tile_prefix, L.n_segs, L.n_tiles, L.um, L.um_maps, L.d_tile_recs);
+        umma_tile_table_kernel<<<(L.n_tiles + 256) / 256, 256, 0, s>>>(L.d_segs, L.d_tile_prefix, L.n_segs, L.n_tiles, L.um, L.um_maps, L.d_tile_recs,
+                                                                           pairs && L.um.nGB > 1 ? 1 : 0);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         ++*launches;
         if (pairs) {                                             // clusters of two CTAs
