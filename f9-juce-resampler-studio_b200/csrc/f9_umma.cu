@@ -15,15 +15,15 @@
 //     is < 2^-24 relative.  out = D0 + D1/2048.  Samples are pre-scaled by 2^7 (see split_store); |x| >= 256 (or NaN/Inf)
 //     does not fit the split: the loader raises a flag and umma_redo_kernel recomputes the launch in fp32.
 //
-// Warp roles (416 threads, one CTA per SM, persistent over tiles):
-//   warps 0-3   epilogue: tcgen05.ld the finished accumulators (lane = period), combine D0/D1, transpose through
-//               shared memory, coalesced stores
-//   warp  4     tensor pipe: tcgen05.cp the staged X steps into TMEM (the A operand is read from TMEM, so an MMA
-//               costs N/2 cycles instead of the ~36 an SS-mode MMA spends fetching 4 KB of A), then the MMAs of
-//               the host-built schedule; tcgen05.commit signals "stage free" / "group done"
-//   warps 5-12  loaders: global -> fp16 split -> shared memory in the canonical K-major (no swizzle) operand layout
-// Measured building blocks (tools/ubench/umma_probe.cu, B200): SS MMA M=128 = 32 + N/4 clk, TS MMA = N/2 clk,
-// tcgen05.cp 128x256b = 64 clk.
+// Variants (template <MERGED, TMA, CTA2>):
+//   * TMA-fed (rows 16-byte aligned): warp 4 streams boxes of 128 overlapping rows x 32 floats (tensor map with a row stride of
+//     p floats) into a ring of raw fp32 stages, warps 10-17 convert (thread = row) and write the TMEM operand with tcgen05.st,
+//     warps 5-9 issue the MMAs from host-built lists, warps 0-3 drain the accumulators.
+//   * CTA pairs on top of that (tcgen05.mma.cta_group::2): half the weights per CTA, the leader issues for both.
+//   * register loader (any alignment): warps 8-15 load, split and stage canonical K-major tiles in shared memory, warp 4 copies
+//     them into TMEM with tcgen05.cp, warps 5-7 issue.
+// Measured building blocks (tools/ubench/umma_probe.cu, tma_probe.cu, B200): SS MMA M=128 = 32 + N/4 clk, TS MMA = N/2 clk,
+// tcgen05.cp 128x256b = 64 clk, box stream 2.7 / 4.6 TB/s of unique input with a ring of 2 / 8 stages.
 #include <algorithm>
 #include <cstdint>
 #include <cstdio>
@@ -90,19 +90,6 @@ __device__ __forceinline__ uint32_t elect_one() {
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(el));
     return el;
 }
-__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-                 :: "r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
-}
-// guarded forms (straight-line unrolled issue blocks: no branch between the MMAs of neighbouring schedule entries)
-__device__ __forceinline__ void umma_ts_if(uint32_t guard, uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-                 :: "r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc), "r"(guard) : "memory");
-}
-__device__ __forceinline__ void umma_commit_if(uint32_t guard, uint64_t* bar) {
-    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
-                 :: "r"(smem_u32(bar)), "r"(guard) : "memory");
-}
 __device__ __forceinline__ void umma_cp(uint32_t d_tmem, uint64_t sdesc) {
     asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" :: "r"(d_tmem), "l"(sdesc) : "memory");
 }
@@ -140,10 +127,6 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
         if (ok) return;
     }
     __trap();
-}
-__device__ __forceinline__ void umma2_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-                 :: "r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
 __device__ __forceinline__ void umma2_commit_both(uint64_t* bar) {                  // arrives on the barrier at this offset in both CTAs
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
@@ -559,7 +542,7 @@ umma_fir_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix
     // optional cycle accounting (development): per CTA [0] loader-warp-0 total, [1] its wait on "stage free", [2] tensor warp
     // total, [3] its wait on "stage full", [4] its wait on "accumulator drained", [5] epilogue-warp-0 total, [6] its wait on
     // "group done", [7] its time in the store loops
-    long long pT0 = 0, pW0 = 0, pW1 = 0, pW2 = 0, pF = 0, pC = 0, pM = 0, pI = 0;
+    long long pT0 = 0, pW0 = 0, pW1 = 0, pW2 = 0, pF = 0, pC = 0, pI = 0;
     #define PROF_BEGIN(v) long long v = (!TMA && prof) ? clock64() : 0
     #define PROF_END(acc, v) if (!TMA && prof) acc += clock64() - v
     if (!TMA && prof) pT0 = clock64();
