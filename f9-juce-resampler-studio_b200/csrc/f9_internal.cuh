@@ -242,6 +242,9 @@ struct ResampleLaunch {
     double pos0 = 1.0;             // sub-sample position before output 0 (1.0 = reset state)
     bool rational = false;
     PolyDev poly;                  // valid when rational
+    // short kinds (<= 5 taps) at a rational ratio: CUDA-core kernel, slot weights in registers (short_kernel)
+    int short_S = 0;               // thread stride in outputs (a multiple of q); 0 = not this path
+    int short_threads = 0; size_t short_smem = 0; int short_stage_floats = 0, short_stages = 3;
     const float* d_sinc_table = nullptr;   // generic WindowedSinc path
     const Seg* d_segs = nullptr;
     const int* d_tile_prefix = nullptr;    // n_segs + 1
@@ -258,7 +261,11 @@ long long   resample_ctas_for_segment(const ResampleLaunch& L, long long n0, lon
 // Fill tile_prefix (n+1 ints) for the segments; returns the CTA total or -1 on overflow.
 int         resample_build_tiles(ResampleLaunch& L, const Seg* segs, int n, std::vector<int>* prefix);
 // Device scratch the launch needs next to the segment table (set L.d_tile_recs to a buffer of this size; 0 = none)
-inline size_t resample_scratch_bytes(const ResampleLaunch& L, int n_tiles) { return L.umma && L.um_tma ? sizeof(UmmaTileRec) * ((size_t) n_tiles + 1) : 0; }
+constexpr size_t kShortTileRecBytes = 48;   // sizeof(ShortTileRec), f9_resample.cu
+inline size_t resample_scratch_bytes(const ResampleLaunch& L, int n_tiles) {
+    if (L.short_S > 0) return kShortTileRecBytes * ((size_t) n_tiles + 1);
+    return L.umma && L.um_tma ? sizeof(UmmaTileRec) * ((size_t) n_tiles + 1) : 0;
+}
 
 }  // namespace f9
 

@@ -92,6 +92,137 @@ poly_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix, in
     }
 }
 
+// --------------------------------------------------------------------------------------------- short kinds (<= 5 taps)
+// Lagrange / CatmullRom / Linear / ZeroOrderHold at a rational ratio: 2-10 FLOP per output against 5-13 bytes, i.e.
+// HBM-bound on CUDA cores (north_star's design for the short kernels).  A tile is `tileOut` consecutive outputs of a segment;
+// persistent CTAs walk the tiles blockIdx.x, + gridDim.x, ... through a ring of kShortStages shared-memory stages:
+//   * the tile's input span (+ taps - 1 of halo), aligned down to 16 bytes, is brought in with cp.async (16 bytes per copy, no
+//     register staging) two tiles ahead of the arithmetic; a tile that touches the edge of its segment's window is staged with
+//     guarded loads instead (zeros outside the window);
+//   * thread t owns the outputs o = t, t + S, t + 2S, ... of a tile, S = c*q a multiple of the period, so its slot -- and with
+//     it the TAPS weights and the window offset -- is fixed per tile: an output costs TAPS shared loads, TAPS FFMA and one
+//     store, the window advances by c*p samples per step; consecutive lanes write consecutive outputs (coalesced stores);
+//   * the geometry of a tile comes from its record (short_tile_table_kernel, one thread per tile, just before this launch).
+struct ShortTileRec {
+    const float* in; float* out;   // the segment's window; the tile's first output
+    long long lA, inAvail;         // 16-byte aligned start of the tile's span as an index into the window; window length
+    int cnt, nvec, k0, mis;        // outputs; 16-byte vectors to stage; slot of output 0; the span proper starts at xs[mis]
+};
+
+template <int TAPS>
+__global__ void __launch_bounds__(256)
+short_tile_table_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix, int nSegs, int nTiles, PolyDev P, int tileOut,
+                        ShortTileRec* __restrict__ recs) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nTiles) return;
+    const int sidx = find_seg(tilePrefix, nSegs, t);
+    const Seg Sg = segs[sidx];
+    const int tile = t - tilePrefix[sidx];
+    const long long o0 = (long long) tile * tileOut;
+    const int cnt = (int) min((long long) tileOut, Sg.numOut - o0);
+    const long long nFirst = Sg.n0 + o0, nLast = nFirst + cnt - 1;
+    const long long a0 = nFirst / P.q;  const int k0 = (int) (nFirst - a0 * P.q);
+    const long long a1 = nLast / P.q;   const int k1 = (int) (nLast - a1 * P.q);
+    const long long lo = a0 * P.p + __ldg(P.B + k0) - (TAPS - 1);        // oldest sample of the tile (channel index)
+    const int span = (int) (a1 * P.p + __ldg(P.B + k1) - lo + 1);
+    const long long l0 = lo - Sg.inOffset;                               // the same as an index into the segment's window
+    const int mis = (int) (((long long) (reinterpret_cast<uintptr_t>(Sg.in) >> 2) + l0) & 3);
+    ShortTileRec R;
+    R.in = Sg.in; R.out = Sg.out + o0; R.lA = l0 - mis; R.inAvail = Sg.inAvail;
+    R.cnt = cnt; R.nvec = (span + mis + 3) >> 2; R.k0 = k0; R.mis = mis;
+    recs[t] = R;
+}
+
+template <int TAPS, int kShortStages>
+__global__ void __launch_bounds__(256)
+short_kernel(const ShortTileRec* __restrict__ recs, int nTiles, PolyDev P, int S, int stageFloats) {
+    extern __shared__ __align__(16) float smem[];
+    float* __restrict__ Ws = smem;                                       // [TAPS][qpad]
+    int* __restrict__ Bs = reinterpret_cast<int*>(Ws + TAPS * P.qpad);   // [qpad]
+    float* __restrict__ ring = reinterpret_cast<float*>(Bs + P.qpad);    // kShortStages x stageFloats
+    for (int i = threadIdx.x; i < TAPS * P.qpad; i += blockDim.x) Ws[i] = __ldg(P.W + i);
+    for (int i = threadIdx.x; i < P.q; i += blockDim.x) Bs[i] = __ldg(P.B + i);
+    const int tq = (int) threadIdx.x / P.q, tr = (int) threadIdx.x - tq * P.q;
+    const int step = (S / P.q) * P.p;
+    const int myTiles = ((int) blockIdx.x < nTiles) ? (nTiles - 1 - (int) blockIdx.x) / (int) gridDim.x + 1 : 0;
+
+    // Records are fetched a tile ahead of their use (registers), so their L2 latency overlaps the arithmetic of the tile before.
+    struct IssueRec { const float* in; long long lA, inAvail; int nvec; };
+    struct ComputeRec { float* out; int4 g; };                          // g = cnt, nvec, k0, mis
+    auto load_issue = [&](int i) {
+        IssueRec R; R.in = nullptr; R.lA = 0; R.inAvail = 0; R.nvec = -1;
+        if (i < myTiles) {
+            const ShortTileRec* r = recs + blockIdx.x + (size_t) i * gridDim.x;
+            R.in = reinterpret_cast<const float*>(__ldg(reinterpret_cast<const unsigned long long*>(&r->in)));
+            R.lA = __ldg(&r->lA); R.inAvail = __ldg(&r->inAvail); R.nvec = __ldg(&r->nvec);
+        }
+        return R;
+    };
+    auto load_compute = [&](int i) {
+        ComputeRec R; R.out = nullptr; R.g = make_int4(0, 0, 0, 0);
+        if (i < myTiles) {
+            const ShortTileRec* r = recs + blockIdx.x + (size_t) i * gridDim.x;
+            R.out = reinterpret_cast<float*>(__ldg(reinterpret_cast<const unsigned long long*>(&r->out)));
+            R.g = __ldg(reinterpret_cast<const int4*>(&r->cnt));
+        }
+        return R;
+    };
+    auto issue = [&](int i, const IssueRec& R) {
+        if (R.nvec >= 0) {
+            float* xs = ring + (i % kShortStages) * stageFloats;
+            if (R.lA >= 0 && R.lA + 4LL * R.nvec <= R.inAvail) {
+                const float* __restrict__ src = R.in + R.lA;
+                const uint32_t dst = (uint32_t) __cvta_generic_to_shared(xs);
+                for (int v = threadIdx.x; v < R.nvec; v += blockDim.x)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst + 16u * (uint32_t) v), "l"(src + 4 * v) : "memory");
+            } else {
+                float4* __restrict__ xs4 = reinterpret_cast<float4*>(xs);
+                for (int v = threadIdx.x; v < R.nvec; v += blockDim.x) {
+                    const long long l = R.lA + 4 * (long long) v;
+                    float4 x4;
+                    if (l >= 0 && l + 3 < R.inAvail) x4 = __ldg(reinterpret_cast<const float4*>(R.in + l));
+                    else {
+                        x4.x = (l >= 0 && l < R.inAvail) ? __ldg(R.in + l) : 0.f;             x4.y = (l + 1 >= 0 && l + 1 < R.inAvail) ? __ldg(R.in + l + 1) : 0.f;
+                        x4.z = (l + 2 >= 0 && l + 2 < R.inAvail) ? __ldg(R.in + l + 2) : 0.f; x4.w = (l + 3 >= 0 && l + 3 < R.inAvail) ? __ldg(R.in + l + 3) : 0.f;
+                    }
+                    xs4[v] = x4;
+                }
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");            // one group per tile, empty or not: uniform counting
+    };
+
+    #pragma unroll
+    for (int i = 0; i < kShortStages - 1; ++i) issue(i, load_issue(i));
+    IssueRec In = load_issue(kShortStages - 1);
+    ComputeRec Cn = load_compute(0);
+    for (int i = 0; i < myTiles; ++i) {
+        asm volatile("cp.async.wait_group %0;" :: "n"(kShortStages - 2) : "memory");   // this thread's copies of tile i have landed
+        __syncthreads();                                                 // ... everyone's; and everyone is done with tile i - 1
+        const IssueRec Ic = In;     In = load_issue(i + kShortStages);
+        const ComputeRec Cc = Cn;   Cn = load_compute(i + 1);
+        issue(i + kShortStages - 1, Ic);                                 // into the stage tile i - 1 just left
+        if ((int) threadIdx.x < S) {
+            float* __restrict__ out = Cc.out;
+            const int kk = Cc.g.z + tr;
+            const int wrap = kk >= P.q ? 1 : 0;
+            const int k = kk - wrap * P.q;
+            float w[TAPS];
+            #pragma unroll
+            for (int j = 0; j < TAPS; ++j) w[j] = Ws[j * P.qpad + k];
+            const float* __restrict__ x = ring + (i % kShortStages) * stageFloats + Cc.g.w + (tq + wrap) * P.p + Bs[k] - Bs[Cc.g.z];
+            #pragma unroll 4
+            for (int o = threadIdx.x; o < Cc.g.x; o += S, x += step) {
+                float acc = 0.0f;
+                #pragma unroll
+                for (int j = 0; j < TAPS; ++j) acc = fmaf(x[j], w[j], acc);
+                out[o] = acc;
+            }
+        }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
 // --------------------------------------------------------------------------------------------- generic ratio
 // Any double ratio (and any pos0: the stateful process() calls land here).  Weights are evaluated per output in
 // the scalar interpolator's own operation order with explicit _rn intrinsics (no FMA contraction).
@@ -356,6 +487,32 @@ cudaError_t run_poly(const ResampleLaunch& L, size_t smem, cudaStream_t s) {
     poly_kernel<TAPS><<<L.n_tiles, kRsThreads, smem, s>>>(L.d_segs, L.d_tile_prefix, L.n_segs, L.poly, L.tile_out, L.adding, L.gain);
     return cudaGetLastError();
 }
+template <int TAPS, int NST>
+cudaError_t run_short_st(const ResampleLaunch& L, ShortTileRec* recs, int grid, cudaStream_t s) {
+    cudaError_t e = set_smem(short_kernel<TAPS, NST>, L.short_smem);
+    if (e != cudaSuccess) return e;
+    short_kernel<TAPS, NST><<<grid, L.short_threads, L.short_smem, s>>>(recs, L.n_tiles, L.poly, L.short_S, L.short_stage_floats);
+    return cudaGetLastError();
+}
+template <int TAPS>
+cudaError_t run_short(const ResampleLaunch& L, cudaStream_t s, long long* launches) {
+    if (!L.d_tile_recs) return cudaErrorInvalidValue;
+    ShortTileRec* recs = reinterpret_cast<ShortTileRec*>(L.d_tile_recs);
+    short_tile_table_kernel<TAPS><<<(L.n_tiles + 255) / 256, 256, 0, s>>>(L.d_segs, L.d_tile_prefix, L.n_segs, L.n_tiles, L.poly, L.tile_out, recs);
+    ++*launches;
+    const int perSm = std::max(1, std::min(2048 / L.short_threads, (int) ((227 * 1024) / (L.short_smem + 1024))));
+    const int grid = std::min(L.n_tiles, L.sm_count * perSm);
+    cudaError_t e;
+    switch (L.short_stages) {
+        case 2: e = run_short_st<TAPS, 2>(L, recs, grid, s); break;
+        case 3: e = run_short_st<TAPS, 3>(L, recs, grid, s); break;
+        case 4: e = run_short_st<TAPS, 4>(L, recs, grid, s); break;
+        default: return cudaErrorInvalidValue;
+    }
+    if (e == cudaSuccess) ++*launches;
+    return e;
+}
+static_assert(sizeof(ShortTileRec) == kShortTileRecBytes, "ShortTileRec layout");
 template <int KIND>
 cudaError_t run_generic(const ResampleLaunch& L, size_t smem, cudaStream_t s) {
     cudaError_t e = set_smem(generic_kernel<KIND>, smem);
@@ -466,6 +623,16 @@ cudaError_t launch_resample(const ResampleLaunch& L, cudaStream_t s, long long* 
     const int taps = interp_memory(L.kind);
     const size_t smem = sizeof(float) * ((size_t) ((double) L.tile_out * L.ratio) + (size_t) taps + 8);
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
+    if (L.rational && L.short_S > 0 && !L.adding) {
+        switch (L.kind) {
+            case F9_LAGRANGE: e = run_short<5>(L, s, launches); break;
+            case F9_CATMULL_ROM: e = run_short<4>(L, s, launches); break;
+            case F9_LINEAR: e = run_short<2>(L, s, launches); break;
+            case F9_ZERO_ORDER_HOLD: e = run_short<1>(L, s, launches); break;
+            default: return cudaErrorInvalidValue;
+        }
+        return e;
+    }
     if (L.rational) {
         switch (L.kind) {
             case F9_WINDOWED_SINC: e = run_poly<200>(L, smem, s); break;
@@ -543,6 +710,27 @@ int f9_context::prepare_resample(int kind, double ratio, double pos0, bool allow
         int rc = get_poly(kind, p, q, &L->poly); if (rc) return rc;
         L->rational = true;
         L->sm_count = sm_count;
+        // short kinds: bandwidth-bound on CUDA cores with the slot's weights in registers (F9_SHORT_UMMA=1: tensor-core kernel instead)
+        // Integer decimation (q == 1, p >= 2) stays on the tensor-core kernel when it is enabled: the short kernel's stride-p shared
+        // loads conflict p ways there (measured 82 % / 76 % against 93 % / 95 % of the HBM roofline at 2:1 / 4:1); everywhere else
+        // the short kernel is as fast or faster (44.1 -> 48 k: 86 % against 66 %; 48 -> 192 k: 84 % against 65 %) and exact fp32.
+        const bool decim = q == 1 && p >= 2 && getenv("F9_NO_UMMA") == nullptr && getenv("F9_SHORT_ALL") == nullptr;
+        if (interp_memory(kind) <= 5 && q <= 256 && p <= 8192 && !decim && getenv("F9_SHORT_UMMA") == nullptr && getenv("F9_NO_SHORT") == nullptr) {
+            const int c = (int) std::max(1LL, 256 / q);
+            const int S = (int) q * c;
+            long long I = (4096 * q + (long long) S * p / 2) / ((long long) S * p);
+            I = std::max(2LL, std::min(64LL, I));
+            if (const char* e = getenv("F9_SHORT_I")) I = std::max(1, atoi(e));          // experiments: steps per thread
+            const long long stageFloats = (((S * I * p + q - 1) / q + interp_memory(kind) + 8) + 3) / 4 * 4;
+            const int nst = getenv("F9_SHORT_STAGES") ? std::max(2, std::min(4, atoi(getenv("F9_SHORT_STAGES")))) : 3;
+            const size_t smem = sizeof(float) * (size_t) (nst * stageFloats + (interp_memory(kind) + 1) * L->poly.qpad);
+            L->short_stages = nst;
+            if (smem <= 200 * 1024) {
+                L->short_S = S; L->short_threads = (S + 31) / 32 * 32;
+                L->tile_out = (int) (S * I); L->short_smem = smem; L->short_stage_floats = (int) stageFloats;
+                return F9_OK;
+            }
+        }
         if (getenv("F9_NO_UMMA") == nullptr && interp_memory(kind) >= 2) {
             long long bm = 0; int bGBL = 0, bNB = 0;
             umma_choose_plan(interp_memory(kind), p, q, &bm, &bNB, &bGBL);

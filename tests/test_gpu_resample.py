@@ -366,7 +366,9 @@ def _plan_resample_many(ctx, f9, x_dev, windows, kind, fs_in, fs_out):
     return [o.cpu().numpy() for o in outs]
 
 
-FEEDS = [{}, {"F9_UMMA_NOCTA2": "1"}, {"F9_UMMA_CTA2": "1"}, {"F9_UMMA_NORANGES": "1"}, {"F9_UMMA_NOTMA": "1"}]
+# F9_SHORT_UMMA keeps Lagrange on the tensor-core kernel (by default the short kinds take short_kernel)
+FEEDS = [{"F9_SHORT_UMMA": "1"}, {"F9_SHORT_UMMA": "1", "F9_UMMA_NOCTA2": "1"}, {"F9_SHORT_UMMA": "1", "F9_UMMA_CTA2": "1"},
+         {"F9_SHORT_UMMA": "1", "F9_UMMA_NORANGES": "1"}, {"F9_SHORT_UMMA": "1", "F9_UMMA_NOTMA": "1"}]
 
 
 @pytest.mark.parametrize("kind", [0, 1])
@@ -391,6 +393,42 @@ def test_umma_feed_variants_are_bit_identical(ctx, O, f9, monkeypatch, kind):
     for i in range(1, len(FEEDS)):
         for a, b in zip(got[0], got[i]):
             assert np.array_equal(a, b), FEEDS[i]
+
+
+@pytest.mark.parametrize("kind", [1, 2, 3, 4])
+@pytest.mark.parametrize("fs", RATIONAL + [(48000, 48000), (44100, 88200), (32000, 48000)])
+def test_short_kernel_windows(ctx, O, f9, monkeypatch, kind, fs):
+    """Short kinds (Lagrange, CatmullRom, Linear, ZeroOrderHold) at rational ratios run short_kernel: windows at every 16-byte
+    misalignment, ragged lengths (1 sample, less than a period, several tiles), poisoned neighbourhood (nothing outside the
+    window may leak in); the tensor-core kernel and the v1 polyphase kernel agree with it within the tolerance."""
+    torch = pytest.importorskip("torch")
+    fs_in, fs_out = fs
+    x = signal(300000, 43 + kind)
+    windows = [(5, 70001), (70011, 1), (70018, 3), (70031, 611), (96009, 131000), (227012, 19), (227033, 50000)]
+    xp = x.copy()
+    mask = np.ones(x.size, bool)
+    for off, n in windows:
+        mask[off:off + n] = False
+    xp[mask] = np.nan
+    xp[mask & (np.arange(x.size) % 3 == 0)] = np.inf
+    d = torch.from_numpy(xp).cuda()
+    got = _plan_resample_many(ctx, f9, d, windows, kind, fs_in, fs_out)
+    for (off, n), y in zip(windows, got):
+        assert np.all(np.isfinite(y)), (off, n)
+        if kind == 4:
+            continue        # ZeroOrderHold is discontinuous: the oracle's rounded recurrence may pick the other sample on exact integers
+        ref, _ = O.resample_channel(kind, fs_in / fs_out, x[off:off + n], y.shape[0])
+        assert np.max(np.abs(y - ref)) <= TOL, (off, n)
+        if n > 1000:
+            assert snr_db(ref, y) >= 120.0
+    for env in ({"F9_SHORT_UMMA": "1"}, {"F9_NO_SHORT": "1", "F9_NO_UMMA": "1"}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        other = _plan_resample_many(ctx, f9, torch.from_numpy(x).cuda(), windows, kind, fs_in, fs_out)
+        for k in env:
+            monkeypatch.delenv(k)
+        for a, b in zip(got, other):
+            assert np.max(np.abs(a - b)) <= TOL, env
 
 
 def test_umma_memory_outside_the_window_never_leaks(ctx, O, f9):

@@ -22,6 +22,9 @@ def plan_time(kind, fs_in, fs_out, nch, n_in):
     L.f9_plan_destroy(plan)
     ts.sort(); ms = ts[3]
     print(kind, fs_in, fs_out, round(ms, 4), "ms", round(4.0 * nch * (n_in + no) / ms / 1e6 / 6551.4 * 100, 1), "%", flush=True)
-for kind in (0, 1):
-    for fs in (44100, 88200):
-        plan_time(kind, fs, 48000, 512, 10 * fs)
+# usage: rate_bench.py [kinds, e.g. 0,1] [fs_in:fs_out, ...]   (512 channels of 10 s each)
+kinds = [int(k) for k in sys.argv[1].split(",")] if len(sys.argv) > 1 else [0, 1]
+rates = [tuple(int(v) for v in a.split(":")) for a in sys.argv[2:]] or [(44100, 48000), (88200, 48000)]
+for kind in kinds:
+    for fs_in, fs_out in rates:
+        plan_time(kind, fs_in, fs_out, 512, 10 * fs_in)
