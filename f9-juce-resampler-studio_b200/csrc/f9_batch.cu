@@ -194,13 +194,27 @@ int run_chunk(f9_context* ctx, const f9_job* jobs, f9_result* results, const std
     }
 
     // ---- 24-bit payload + downloads ----
+    {   // one launch packs every file that asked for the WAV payload
+        std::vector<DevBuf> pb; std::vector<unsigned char*> pd;
+        for (int t = 0; t < n; ++t) {
+            const f9_job& J = jobs[idx[(size_t) t]];
+            const JobPlan& P = plans[(size_t) t];
+            if ((J.flags & F9_JOB_PCM24) && P.out_frames > 0) { DevBuf b = P.out; b.numCh = J.numCh; b.numFrames = P.out_frames; pb.push_back(b); pd.push_back(P.d_pcm); }
+        }
+        if (!pb.empty()) {
+            DevBuf* d_b = (DevBuf*) ctx->d_alloc(sizeof(DevBuf) * pb.size()); unsigned char** d_p = (unsigned char**) ctx->d_alloc(sizeof(void*) * pd.size());
+            DevBuf* h_b = (DevBuf*) ctx->h_alloc(sizeof(DevBuf) * pb.size()); unsigned char** h_p = (unsigned char**) ctx->h_alloc(sizeof(void*) * pd.size());
+            std::memcpy(h_b, pb.data(), sizeof(DevBuf) * pb.size()); std::memcpy(h_p, pd.data(), sizeof(void*) * pd.size());
+            F9_TRY_CUDA(ctx, cudaMemcpyAsync(d_b, h_b, sizeof(DevBuf) * pb.size(), cudaMemcpyHostToDevice, s));
+            F9_TRY_CUDA(ctx, cudaMemcpyAsync(d_p, h_p, sizeof(void*) * pd.size(), cudaMemcpyHostToDevice, s));
+            F9_TRY_CUDA(ctx, launch_planar_to_pcm24_batch(pb.data(), d_b, d_p, (int) pb.size(), s, &ctx->launches));
+        }
+    }
     for (int t = 0; t < n; ++t) {
         const f9_job& J = jobs[idx[(size_t) t]];
         const JobPlan& P = plans[(size_t) t];
-        if ((J.flags & F9_JOB_PCM24) && P.out_frames > 0) {
-            F9_TRY_CUDA(ctx, launch_planar_to_pcm24(P.out.base, P.out.chStride, J.numCh, P.out_frames, P.d_pcm, s, &ctx->launches));
+        if ((J.flags & F9_JOB_PCM24) && P.out_frames > 0)
             F9_TRY_CUDA(ctx, cudaMemcpyAsync(J.out_pcm24, P.d_pcm, (size_t) P.out_frames * J.numCh * 3, cudaMemcpyDeviceToHost, s));
-        }
         if (J.out && P.out_frames > 0)
             for (int c = 0; c < J.numCh; ++c)
                 F9_TRY_CUDA(ctx, cudaMemcpyAsync(J.out[c], P.out.base + c * P.out.chStride, sizeof(float) * (size_t) P.out_frames, cudaMemcpyDeviceToHost, s));

@@ -812,6 +812,37 @@ int f9_dev_planar_to_pcm24(f9_context* ctx, const float* d_src, long long src_ch
     return F9_OK;
 }
 
+int f9_dev_pcm_to_planar_batch(f9_context* ctx, const void* const* d_srcs, int fmt, int src_ch, const f9_dev_buffer* dst, int n) {
+    if (!ctx || fmt < F9_PCM_U8 || fmt > F9_PCM_F32LE || src_ch <= 0 || n < 0 || (n > 0 && (!d_srcs || !dst))) return F9_ERR_INVALID;
+    if (n == 0) return F9_OK;
+    for (int i = 0; i < n; ++i)
+        if (dst[i].numCh <= 0 || dst[i].numFrames < 0 || (dst[i].numFrames > 0 && (!d_srcs[i] || !dst[i].base))) return ctx->fail(F9_ERR_INVALID, "bad file descriptor in the batch");
+    F9_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    const DevBuf* hb = reinterpret_cast<const DevBuf*>(dst);
+    int rc = ctx->arena_reserve((sizeof(DevBuf) + sizeof(void*)) * (size_t) n + 16384, (sizeof(DevBuf) + sizeof(void*)) * (size_t) n + 8192, true);
+    if (rc) return rc;
+    DevBuf* d_b; const unsigned char** d_p;
+    rc = upload_array(ctx, hb, (size_t) n, &d_b); if (rc) return rc;
+    rc = upload_array(ctx, reinterpret_cast<const unsigned char* const*>(d_srcs), (size_t) n, &d_p); if (rc) return rc;
+    F9_TRY_CUDA(ctx, launch_pcm_to_planar_batch(d_p, fmt, src_ch, hb, d_b, n, ctx->stream, &ctx->launches));
+    return F9_OK;
+}
+int f9_dev_planar_to_pcm24_batch(f9_context* ctx, const f9_dev_buffer* src, unsigned char* const* d_dsts, int n) {
+    if (!ctx || n < 0 || (n > 0 && (!src || !d_dsts))) return F9_ERR_INVALID;
+    if (n == 0) return F9_OK;
+    for (int i = 0; i < n; ++i)
+        if (src[i].numCh <= 0 || src[i].numFrames < 0 || (src[i].numFrames > 0 && (!d_dsts[i] || !src[i].base))) return ctx->fail(F9_ERR_INVALID, "bad file descriptor in the batch");
+    F9_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    const DevBuf* hb = reinterpret_cast<const DevBuf*>(src);
+    int rc = ctx->arena_reserve((sizeof(DevBuf) + sizeof(void*)) * (size_t) n + 16384, (sizeof(DevBuf) + sizeof(void*)) * (size_t) n + 8192, true);
+    if (rc) return rc;
+    DevBuf* d_b; unsigned char** d_p;
+    rc = upload_array(ctx, hb, (size_t) n, &d_b); if (rc) return rc;
+    rc = upload_array(ctx, const_cast<unsigned char**>(d_dsts), (size_t) n, &d_p); if (rc) return rc;
+    F9_TRY_CUDA(ctx, launch_planar_to_pcm24_batch(hb, d_b, d_p, n, ctx->stream, &ctx->launches));
+    return F9_OK;
+}
+
 int f9_pcm_to_planar(f9_context* ctx, const void* src, int fmt, int src_ch, long long num_frames, float* const* dst, int dst_ch) {
     if (!ctx) return F9_ERR_INVALID;
     if (fmt < F9_PCM_U8 || fmt > F9_PCM_F32LE || src_ch <= 0 || dst_ch <= 0 || num_frames < 0 || (num_frames > 0 && (!src || !dst)))

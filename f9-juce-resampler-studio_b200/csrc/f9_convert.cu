@@ -76,12 +76,11 @@ __device__ __forceinline__ float pcm_load(const unsigned char* __restrict__ src,
 // planar writes are coalesced.
 // frames per CTA: sized by the launcher so the staging tile stays under ~40 KB for any channel count
 __host__ __device__ inline int cvt_frames(int bytesPerFrame) { int f = 40960 / (bytesPerFrame > 0 ? bytesPerFrame : 1); f = f > 1024 ? 1024 : f; f &= ~31; return f < 32 ? 32 : f; }
-__global__ void __launch_bounds__(kThreads)
-pcm_to_planar_kernel(const unsigned char* __restrict__ src, int fmt, int srcCh, long long frames,
-                     float* __restrict__ dst, long long dstStride, int dstCh, int kCvtFrames) {
-    extern __shared__ unsigned char raw[];
+__device__ __forceinline__ void pcm_to_planar_tile(unsigned char* raw, const unsigned char* __restrict__ src, int fmt, int srcCh, long long frames,
+                                                   float* __restrict__ dst, long long dstStride, int dstCh, int kCvtFrames) {
     const int bps = (fmt == F9_PCM_U8) ? 1 : (fmt == F9_PCM_S16LE) ? 2 : (fmt == F9_PCM_S24LE) ? 3 : 4;
     const long long f0 = (long long) blockIdx.x * kCvtFrames;
+    if (f0 >= frames) return;
     const int nf = (int) min((long long) kCvtFrames, frames - f0);
     const long long byte0 = f0 * srcCh * bps;
     const int nbytes = nf * srcCh * bps;
@@ -102,6 +101,20 @@ pcm_to_planar_kernel(const unsigned char* __restrict__ src, int fmt, int srcCh, 
         for (int f = threadIdx.x; f < nf; f += kThreads) d[f] = pcm_load(raw, fmt, (long long) f * srcCh + sc);
     }
 }
+__global__ void __launch_bounds__(kThreads)
+pcm_to_planar_kernel(const unsigned char* __restrict__ src, int fmt, int srcCh, long long frames,
+                     float* __restrict__ dst, long long dstStride, int dstCh, int kCvtFrames) {
+    extern __shared__ unsigned char raw[];
+    pcm_to_planar_tile(raw, src, fmt, srcCh, frames, dst, dstStride, dstCh, kCvtFrames);
+}
+// Batched form: blockIdx.y = file; file i reads srcs[i] (srcCh interleaved channels of its destination's frame count) into
+// the planar buffer dsts[i].  One launch for a whole batch instead of one per file (6 us each: the per-file form is launch-bound).
+__global__ void __launch_bounds__(kThreads)
+pcm_to_planar_batch_kernel(const unsigned char* const* __restrict__ srcs, int fmt, int srcCh, const DevBuf* __restrict__ dsts, int kCvtFrames) {
+    extern __shared__ unsigned char raw[];
+    const DevBuf D = dsts[blockIdx.y];
+    pcm_to_planar_tile(raw, srcs[blockIdx.y], fmt, srcCh, D.numFrames, const_cast<float*>(D.base), D.chStride, D.numCh, kCvtFrames);
+}
 
 // ---- planar float -> interleaved 24-bit LE (JUCE writer: clip, roundToInt(INT_MAX * (double) x), top 24 bits) ---
 __device__ __forceinline__ int float_to_i32(float x) {
@@ -110,10 +123,10 @@ __device__ __forceinline__ int float_to_i32(float x) {
     if (samp >= 1.0) return 0x7fffffff;
     return __double2int_rn(__dmul_rn(2147483647.0, samp));
 }
-__global__ void __launch_bounds__(kThreads)
-planar_to_pcm24_kernel(const float* __restrict__ src, long long srcStride, int numCh, long long frames, unsigned char* __restrict__ dst, int kCvtFrames) {
-    extern __shared__ unsigned char raw[];
+__device__ __forceinline__ void planar_to_pcm24_tile(unsigned char* raw, const float* __restrict__ src, long long srcStride, int numCh, long long frames,
+                                                     unsigned char* __restrict__ dst, int kCvtFrames) {
     const long long f0 = (long long) blockIdx.x * kCvtFrames;
+    if (f0 >= frames) return;
     const int nf = (int) min((long long) kCvtFrames, frames - f0);
     for (int c = 0; c < numCh; ++c) {
         const float* __restrict__ s = src + (long long) c * srcStride + f0;
@@ -135,6 +148,18 @@ planar_to_pcm24_kernel(const float* __restrict__ src, long long srcStride, int n
     } else {
         for (int i = threadIdx.x; i < nbytes; i += kThreads) dst[byte0 + i] = raw[i];
     }
+}
+__global__ void __launch_bounds__(kThreads)
+planar_to_pcm24_kernel(const float* __restrict__ src, long long srcStride, int numCh, long long frames, unsigned char* __restrict__ dst, int kCvtFrames) {
+    extern __shared__ unsigned char raw[];
+    planar_to_pcm24_tile(raw, src, srcStride, numCh, frames, dst, kCvtFrames);
+}
+// Batched form: blockIdx.y = file (its own channel count and length); tiles of kCvtFrames frames, sized for the widest file.
+__global__ void __launch_bounds__(kThreads)
+planar_to_pcm24_batch_kernel(const DevBuf* __restrict__ srcs, unsigned char* const* __restrict__ dsts, int kCvtFrames) {
+    extern __shared__ unsigned char raw[];
+    const DevBuf B = srcs[blockIdx.y];
+    planar_to_pcm24_tile(raw, B.base, B.chStride, B.numCh, B.numFrames, dsts[blockIdx.y], kCvtFrames);
 }
 
 // ---- planar <-> interleaved float (AudioProcessingService.swift:361-365, :524-531) ----------------------
@@ -221,6 +246,41 @@ cudaError_t launch_planar_to_pcm24(const float* d_src, long long srcStride, int 
     const long long ctas = (frames + kCvtFrames - 1) / kCvtFrames;
     planar_to_pcm24_kernel<<<(unsigned) ctas, kThreads, smem, s>>>(d_src, srcStride, numCh, frames, d_dst, kCvtFrames);
     ++*launches;
+    return cudaGetLastError();
+}
+
+// h_bufs: host copy of the descriptors (for sizing the grid); d_bufs / d_ptrs: the same on the device
+cudaError_t launch_planar_to_pcm24_batch(const DevBuf* h_srcs, const DevBuf* d_srcs, unsigned char* const* d_dsts, int n,
+                                         cudaStream_t s, long long* launches) {
+    int maxCh = 0, maxFrames = 0;
+    for (int i = 0; i < n; ++i) { maxCh = std::max(maxCh, h_srcs[i].numCh); maxFrames = std::max(maxFrames, h_srcs[i].numFrames); }
+    if (n <= 0 || maxCh <= 0 || maxFrames <= 0) return cudaSuccess;
+    const int kCvtFrames = cvt_frames(maxCh * 3);
+    const size_t smem = (size_t) kCvtFrames * maxCh * 3 + 16;
+    cudaError_t e = allow_smem(planar_to_pcm24_batch_kernel, smem);
+    if (e != cudaSuccess) return e;
+    const unsigned ctas = (unsigned) ((maxFrames + kCvtFrames - 1) / kCvtFrames);
+    for (int b0 = 0; b0 < n; b0 += 65535) {
+        planar_to_pcm24_batch_kernel<<<dim3(ctas, (unsigned) std::min(65535, n - b0)), kThreads, smem, s>>>(d_srcs + b0, d_dsts + b0, kCvtFrames);
+        ++*launches;
+    }
+    return cudaGetLastError();
+}
+cudaError_t launch_pcm_to_planar_batch(const unsigned char* const* d_srcs, int fmt, int srcCh, const DevBuf* h_dsts, const DevBuf* d_dsts, int n,
+                                       cudaStream_t s, long long* launches) {
+    int maxFrames = 0;
+    for (int i = 0; i < n; ++i) maxFrames = std::max(maxFrames, h_dsts[i].numFrames);
+    if (n <= 0 || maxFrames <= 0) return cudaSuccess;
+    const int bps = (fmt == F9_PCM_U8) ? 1 : (fmt == F9_PCM_S16LE) ? 2 : (fmt == F9_PCM_S24LE) ? 3 : 4;
+    const int kCvtFrames = cvt_frames(srcCh * bps);
+    const size_t smem = (size_t) kCvtFrames * srcCh * bps + 16;
+    cudaError_t e = allow_smem(pcm_to_planar_batch_kernel, smem);
+    if (e != cudaSuccess) return e;
+    const unsigned ctas = (unsigned) ((maxFrames + kCvtFrames - 1) / kCvtFrames);
+    for (int b0 = 0; b0 < n; b0 += 65535) {
+        pcm_to_planar_batch_kernel<<<dim3(ctas, (unsigned) std::min(65535, n - b0)), kThreads, smem, s>>>(d_srcs + b0, fmt, srcCh, d_dsts + b0, kCvtFrames);
+        ++*launches;
+    }
     return cudaGetLastError();
 }
 

@@ -92,6 +92,10 @@ cudaError_t launch_remove_dc(const DevBuf* d_bufs /* writable */, int n, int max
 
 cudaError_t launch_pcm_to_planar(const void* d_src, int fmt, int srcCh, long long frames, float* d_dst,
                                  long long dstStride, int dstCh, cudaStream_t s, long long* launches);
+cudaError_t launch_planar_to_pcm24_batch(const DevBuf* h_srcs, const DevBuf* d_srcs, unsigned char* const* d_dsts, int n,
+                                         cudaStream_t s, long long* launches);
+cudaError_t launch_pcm_to_planar_batch(const unsigned char* const* d_srcs, int fmt, int srcCh, const DevBuf* h_dsts, const DevBuf* d_dsts, int n,
+                                       cudaStream_t s, long long* launches);
 cudaError_t launch_planar_to_pcm24(const float* d_src, long long srcStride, int numCh, long long frames,
                                    unsigned char* d_dst, cudaStream_t s, long long* launches);
 cudaError_t launch_interleave(const float* d_src, long long srcStride, int numCh, long long frames, float* d_dst,

@@ -129,6 +129,8 @@ SYMBOLS = [
     ("f9_deinterleave", _i, [_vp, _fp, _i, _ll, _fpp]),
     ("f9_dev_pcm_to_planar", _i, [_vp, _vp, _i, _i, _ll, _vp, _ll, _i]),
     ("f9_dev_planar_to_pcm24", _i, [_vp, _vp, _ll, _i, _ll, _vp]),
+    ("f9_dev_pcm_to_planar_batch", _i, [_vp, C.POINTER(C.c_void_p), _i, _i, C.POINTER(DevBuffer), _i]),
+    ("f9_dev_planar_to_pcm24_batch", _i, [_vp, C.POINTER(DevBuffer), C.POINTER(C.c_void_p), _i]),
 ]
 
 _lib = None

@@ -317,6 +317,14 @@ F9_API int f9_dev_pcm_to_planar(f9_context* ctx, const void* d_src, int fmt, int
                                 float* d_dst, long long dst_ch_stride, int dst_ch);
 F9_API int f9_dev_planar_to_pcm24(f9_context* ctx, const float* d_src, long long src_ch_stride, int numCh,
                                   long long num_frames, unsigned char* d_dst);
+/* batched device forms: one launch for a whole batch of files (the per-file calls above are launch-bound on short files).
+ * Replaces the per-file reader->read / 24-bit writer passes of the save loop (Source/MainComponent.cpp:734-739, :785-801).
+ * pcm_to_planar_batch: file i reads d_srcs[i] (src_ch interleaved channels, dst[i].numFrames frames of format fmt) into the
+ * planar buffer dst[i] (dst[i].base is written).  planar_to_pcm24_batch: file i writes src[i] to d_dsts[i]
+ * (src[i].numCh * src[i].numFrames * 3 bytes).  d_srcs / d_dsts are host arrays of device pointers. */
+F9_API int f9_dev_pcm_to_planar_batch(f9_context* ctx, const void* const* d_srcs, int fmt, int src_ch,
+                                      const f9_dev_buffer* dst, int n);
+F9_API int f9_dev_planar_to_pcm24_batch(f9_context* ctx, const f9_dev_buffer* src, unsigned char* const* d_dsts, int n);
 
 #ifdef __cplusplus
 }

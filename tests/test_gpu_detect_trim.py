@@ -206,6 +206,46 @@ def test_planar_to_pcm24(ctx, O, ch, frames):
     assert np.array_equal(ctx.planar_to_pcm24(x), O.planar_to_pcm24(x))
 
 
+def test_pcm_batch_forms(ctx, O, f9):
+    """One launch for a ragged batch of files (different lengths and channel counts, an empty file, odd byte offsets):
+    both directions bit-identical to the oracle's per-file conversion."""
+    torch = pytest.importorskip("torch")
+    import ctypes as C
+    shapes = [(2, 4099), (1, 7), (2, 0), (6, 1001), (2, 44100), (3, 1), (2, 1023), (2, 1024), (2, 1025)]
+    xs = [rnd(s, 900 + i, 1.2) for i, s in enumerate(shapes)]
+    n = len(xs)
+    # planar float -> 24-bit payload
+    d_x = [torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in xs]
+    d_p = [torch.full((max(1, x.size * 3) + 1,), 0xAB, dtype=torch.uint8, device="cuda") for x in xs]
+    bufs = (f9.DevBuffer * n)(*[f9.DevBuffer(t.data_ptr(), x.shape[1], x.shape[0], x.shape[1]) for t, x in zip(d_x, xs)])
+    ptrs = (C.c_void_p * n)(*[t.data_ptr() for t in d_p])
+    torch.cuda.synchronize()
+    ctx._check(f9.lib().f9_dev_planar_to_pcm24_batch(ctx.handle, bufs, ptrs, n))
+    ctx.synchronize()
+    for x, t in zip(xs, d_p):
+        got = t.cpu().numpy()
+        assert np.array_equal(got[:x.size * 3], O.planar_to_pcm24(x)) if x.size else True
+        assert np.all(got[x.size * 3:] == 0xAB)                       # nothing written past the payload
+    # 24-bit payload -> planar float (mono -> stereo duplication through the destination's channel count)
+    rng = np.random.default_rng(77)
+    frames = [4099, 7, 0, 1001, 44100, 1]
+    src_ch = 2
+    raws = [rng.integers(0, 256, 3 * src_ch * f, dtype=np.uint8) for f in frames]
+    d_raw = [torch.from_numpy(np.concatenate([r, np.zeros(1, np.uint8)])).cuda() for r in raws]
+    dst_ch = [2, 1, 2, 3, 2, 2]
+    d_out = [torch.full((c, max(f, 1) + 5), float("nan"), dtype=torch.float32, device="cuda") for c, f in zip(dst_ch, frames)]
+    bufs = (f9.DevBuffer * len(frames))(*[f9.DevBuffer(t.data_ptr(), t.shape[1], c, f) for t, c, f in zip(d_out, dst_ch, frames)])
+    ptrs = (C.c_void_p * len(frames))(*[t.data_ptr() for t in d_raw])
+    torch.cuda.synchronize()
+    ctx._check(f9.lib().f9_dev_pcm_to_planar_batch(ctx.handle, ptrs, 3, src_ch, bufs, len(frames)))
+    ctx.synchronize()
+    for r, t, c, f in zip(raws, d_out, dst_ch, frames):
+        got = t.cpu().numpy()
+        if f:
+            assert np.array_equal(got[:, :f], O.pcm_to_planar(r, 3, src_ch, c))
+        assert np.all(np.isnan(got[:, f:]))
+
+
 @pytest.mark.parametrize("ch,frames", [(1, 5), (2, 4099), (3, 70000), (64, 300)])
 def test_interleave_round_trip(ctx, O, ch, frames):
     x = rnd((ch, frames), 10 + ch)
