@@ -116,6 +116,7 @@ void f9_context_destroy(f9_context* ctx) {
     for (auto& kv : ctx->poly_cache) { cudaFree(kv.second.B); cudaFree(kv.second.W); }
     for (auto& kv : ctx->band_cache) { cudaFree(kv.second.C); cudaFree(kv.second.wmin); }
     for (auto& kv : ctx->umma_cache) cudaFree((void*) kv.second.W);
+    for (auto& kv : ctx->hankel_cache) cudaFree((void*) kv.second.W);
     if (ctx->d_ovf) cudaFree(ctx->d_ovf);
     if (ctx->d_sinc_table) cudaFree(ctx->d_sinc_table);
     if (ctx->cur_slot) ctx->swap_slot();

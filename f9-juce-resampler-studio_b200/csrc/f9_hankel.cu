@@ -1,0 +1,376 @@
+// WindowedSinc (and any other kind) at integer upsampling ratios 1:L, L in {2, 4, 8, 16} -- config 3's 48 -> 192 kHz -- on
+// tcgen05 with a *Hankel* operand.
+//
+// Output n = L*a + k reads x[a - (taps-1) .. a] with the weights of phase k.  Take a column of 128 consecutive outputs,
+// n = 128*r + l, l = i*L + k (R = 128/L inputs per column).  Then
+//     D[l, r] = sum_t  A[l, t] * X[r, t],     X[r, t] = x[R*r - 208 + t],     A[(i,k), t] = w_k[t - 9 - i]  (0 elsewhere),
+// a GEMM with M = 128 (the lane IS the output's offset inside its column: no transpose in the epilogue, a warp stores 128
+// contiguous bytes per column), N = columns, K = R + 208 rounded up to 16.  A is a constant weight image.  X is a Hankel
+// matrix: row r is the input itself shifted by R samples, i.e. 2R bytes of fp16 = 16 / 32 / 64 / 128 bytes -- exactly the row
+// pitch of a K-major shared-memory operand with no / 32 / 64 / 128-byte swizzle.  So the operand is the converted input
+// stored ONCE, linearly (element m at swz(2m)), and K step s is the same buffer read from a start address 32*s bytes further
+// on (tools/ubench/hankel_probe.cu: the swizzle is a function of the absolute address bits, base_offset 0 is right for every
+// start).  Every input sample is fetched from HBM once, converted once and stored once; the polyphase kernel in f9_umma.cu
+// stages and converts each sample (taps + p)/p = 6 times at this ratio.
+//
+// Precision as in f9_umma.cu: x' = 128 x = x0 + x1/2048, w = w0 + w1/2048 (fp16 parts), D0 += w0 x0 split over two accumulators
+// (first / second half of K: the tensor core truncates the fp32 accumulator after every MMA), D1 += w1 x0 + w0 x1,
+// out = (D0A + D0B + D1/2048) / 128.  |x| >= 256, Inf or NaN raise the flag and hankel_redo_kernel recomputes in fp32.
+//
+// Roles (416 threads, one persistent CTA per SM; tile = 64 columns = 8192 outputs):
+//   warps 5-12  converters: coalesced 128-bit loads of the tile's input span (zeros outside the segment's window), fp16 head /
+//               tail split, one 16-byte shared store each into the swizzled head and tail buffers of a 3-stage ring
+//   warp 4      issues 3 * K/16 MMAs (M = 128, N = 64, SS mode) per tile into one of two accumulator sets in TMEM
+//   warps 0-3   epilogue: tcgen05.ld (thread = lane = output offset), combine, st.global (128 contiguous bytes per warp and column)
+#include <algorithm>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cuda_fp16.h>
+
+#include "f9_internal.cuh"
+
+namespace f9 {
+namespace {
+
+constexpr int kHkCols = 64;                 // columns (of 128 outputs) per tile = MMA N
+constexpr int kHkStages = 3;                // input ring
+constexpr int kHkThreads = 13 * 32;
+constexpr int kHkConvWarps = 8, kHkFirstConv = 5;
+constexpr float kHkPre = 128.0f;            // 2^7 pre-scale, as f9_umma.cu
+constexpr uint32_t kHkPark = 2000;
+
+struct HankelTileRec {
+    const float* in; float* out;   // the segment's window and output
+    long long x0, inAvail;         // window index of operand element 0 (may be negative); window length
+    long long oBase, numOut;       // output index (relative to out) of column 0 / lane 0; outputs of the segment
+};
+static_assert(sizeof(HankelTileRec) == kHankelTileRecBytes, "HankelTileRec layout");
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+// Bounded: the hardware may park the thread up to kHkPark ns per attempt; a barrier that never completes traps instead of hanging.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    #pragma unroll 1
+    for (int i = 0; i < (1 << 22); ++i) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(kHkPark) : "memory");
+        if (ok) return;
+    }
+    __trap();
+}
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t el;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(el));
+    return el;
+}
+__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// K-major operand descriptor.  layout 0: no swizzle, element (row r, k) at (k/8)*lbo + (r/8)*sbo + (r%8)*16 + (k%8)*2;
+// layout 2 / 4 / 6: 128 / 64 / 32-byte swizzle, rows one swizzle width apart, sbo = 8 rows.  base_offset stays 0 (see the probe).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+    uint64_t d = 0;
+    d |= (uint64_t) ((saddr >> 4) & 0x3fff);
+    d |= (uint64_t) ((lbo_bytes >> 4) & 0x3fff) << 16;
+    d |= (uint64_t) ((sbo_bytes >> 4) & 0x3fff) << 32;
+    d |= (uint64_t) 1 << 46;
+    d |= (uint64_t) (layout & 7) << 61;
+    return d;
+}
+__device__ __forceinline__ constexpr uint32_t make_idesc(int M, int N) {        // fp16 x fp16 -> fp32, both K-major
+    return (1u << 4) | ((uint32_t) (N >> 3) << 17) | ((uint32_t) (M >> 4) << 24);
+}
+__device__ __forceinline__ int find_seg(const int* __restrict__ prefix, int n, int bid) {
+    int lo = 0, hi = n;
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (prefix[mid] <= bid) lo = mid; else hi = mid; }
+    return lo;
+}
+template <typename T> __device__ __forceinline__ T* ldg_ptr(T* const* p) {
+    return reinterpret_cast<T*>(__ldg(reinterpret_cast<const unsigned long long*>(p)));
+}
+__device__ __forceinline__ float combine(uint32_t d0a, uint32_t d0b, uint32_t d1) {
+    return fmaf(__uint_as_float(d1), 1.0f / (2048.0f * kHkPre), (__uint_as_float(d0a) + __uint_as_float(d0b)) * (1.0f / kHkPre));
+}
+
+// One thread per tile.  Columns are absolute: column c holds outputs 128c .. 128c+127 of the channel, so a segment that starts
+// at n0 owns columns n0/128 .. (n0+numOut-1)/128 and its tiles are runs of kHkCols of them.
+__global__ void __launch_bounds__(256)
+hankel_tile_table_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix, int nSegs, int nTiles, int R,
+                         HankelTileRec* __restrict__ recs) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nTiles) return;
+    const int sidx = find_seg(tilePrefix, nSegs, t);
+    const Seg S = segs[sidx];
+    const long long r0 = S.n0 / 128 + (long long) (t - tilePrefix[sidx]) * kHkCols;
+    HankelTileRec Rr;
+    Rr.in = S.in; Rr.out = S.out;
+    Rr.x0 = (long long) R * r0 - 208 - S.inOffset; Rr.inAvail = S.inAvail;
+    Rr.oBase = 128 * r0 - S.n0; Rr.numOut = S.numOut;
+    recs[t] = Rr;
+}
+
+__global__ void __launch_bounds__(kHkThreads, 1)
+hankel_fir_kernel(const HankelTileRec* __restrict__ recs, int nTiles, const __grid_constant__ HankelDev P, unsigned* __restrict__ ovf) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // the swizzle patterns repeat on 1024 bytes
+    const int KS = P.KS;
+    const uint32_t wBytes = (uint32_t) KS * 4096u;                  // one weight part: per K step 2 chunks x 128 rows x 16 B
+    uint8_t* Wsm = smem;                                            // head image, tail image
+    uint8_t* ring = smem + 2 * wBytes;                              // kHkStages x (head buffer, tail buffer), bufBytes each (1024-aligned)
+    const uint32_t bufBytes = (uint32_t) P.bufBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + kHkStages * 2 * bufBytes);
+    uint64_t *bFull = bars, *bEmpty = bars + kHkStages, *accFull = bars + 2 * kHkStages, *accEmpty = accFull + 2;
+    uint32_t* tmemSlot = reinterpret_cast<uint32_t*>(accEmpty + 2);
+    const int warp = __shfl_sync(0xffffffffu, (int) (threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    const int myTiles = (int) blockIdx.x < nTiles ? (nTiles - 1 - (int) blockIdx.x) / (int) gridDim.x + 1 : 0;
+
+    {   // ---- one-time setup
+        const uint4* src = reinterpret_cast<const uint4*>(P.W);
+        uint4* dst = reinterpret_cast<uint4*>(Wsm);
+        for (int i = threadIdx.x; i < (int) (2 * wBytes / 16); i += blockDim.x) dst[i] = __ldg(src + i);
+        if (threadIdx.x == 0) {
+            for (int s = 0; s < kHkStages; ++s) { mbar_init(bFull + s, kHkConvWarps); mbar_init(bEmpty + s, 1); }
+            for (int a = 0; a < 2; ++a) { mbar_init(accFull + a, 1); mbar_init(accEmpty + a, 4); }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        if (warp == 4) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmemSlot)), "r"(512) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+        fence_async_smem();                                          // the weights are read by the tensor pipe (async proxy)
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+    }
+    const uint32_t tmem = *tmemSlot;
+
+    if (warp >= kHkFirstConv) {
+        // =========================================================== converters
+        // The loads of tile i + 1 are issued (into registers) before tile i is converted, so their latency overlaps the
+        // conversion, the stores and the wait for the ring; every sample is loaded exactly once.
+        const int ctid = (warp - kHkFirstConv) * 32 + lane;
+        const int groups = P.elems >> 3;                             // 8 samples = 16 bytes of fp16 per group
+        constexpr int kG = 3;                                        // groups per thread and tile (elems <= 3 * 256 * 8)
+        const uint32_t swzMask = P.rowBytes == 128 ? 7u : P.rowBytes == 64 ? 3u : P.rowBytes == 32 ? 1u : 0u;
+        __half2 hmax = __floats2half2_rn(0.f, 0.f);
+        const HankelTileRec* rec = recs + blockIdx.x;
+        struct TileIn { const float* in; long long x0, inAvail; };
+        auto load_rec = [&](const HankelTileRec* r) { TileIn T; T.in = ldg_ptr(&r->in); T.x0 = __ldg(&r->x0); T.inAvail = __ldg(&r->inAvail); return T; };
+        auto load_tile = [&](const TileIn& T, float (&v)[kG][8]) {
+            const bool vec = (((long long) (reinterpret_cast<uintptr_t>(T.in) >> 2) + T.x0) & 3) == 0;
+            #pragma unroll
+            for (int u = 0; u < kG; ++u) {
+                const int g = ctid + u * kHkConvWarps * 32;
+                if (g < groups) {
+                    const long long l = T.x0 + 8LL * g;
+                    if (vec && l >= 0 && l + 7 < T.inAvail) {
+                        const float4 a = __ldg(reinterpret_cast<const float4*>(T.in + l)), b = __ldg(reinterpret_cast<const float4*>(T.in + l + 4));
+                        v[u][0] = a.x; v[u][1] = a.y; v[u][2] = a.z; v[u][3] = a.w; v[u][4] = b.x; v[u][5] = b.y; v[u][6] = b.z; v[u][7] = b.w;
+                    } else {
+                        #pragma unroll
+                        for (int e = 0; e < 8; ++e) v[u][e] = (l + e >= 0 && l + e < T.inAvail) ? __ldg(T.in + l + e) : 0.f;
+                    }
+                }
+            }
+        };
+        float nxt[kG][8], cur[kG][8];
+        TileIn T1 = {nullptr, 0, 0}, T2 = T1;
+        if (myTiles > 0) { T1 = load_rec(rec); load_tile(T1, nxt); }
+        if (myTiles > 1) T2 = load_rec(rec + gridDim.x);
+        for (int i = 0; i < myTiles; ++i, rec += gridDim.x) {
+            #pragma unroll
+            for (int u = 0; u < kG; ++u)
+                #pragma unroll
+                for (int e = 0; e < 8; ++e) cur[u][e] = nxt[u][e];
+            if (i + 1 < myTiles) {
+                T1 = T2;
+                load_tile(T1, nxt);
+                if (i + 2 < myTiles) T2 = load_rec(rec + 2 * (size_t) gridDim.x);
+            }
+            const int st = i % kHkStages;
+            if (i >= kHkStages) mbar_wait(bEmpty + st, (uint32_t) ((i / kHkStages - 1) & 1));       // the MMAs that read this stage are done
+            const uint32_t hb = smem_u32(ring + (size_t) st * 2 * bufBytes), tb = hb + bufBytes;
+            #pragma unroll
+            for (int u = 0; u < kG; ++u) {
+                const int g = ctid + u * kHkConvWarps * 32;
+                if (g < groups) {
+                    uint32_t hd[4], tl[4];
+                    #pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float x0 = cur[u][2 * e] * kHkPre, x1 = cur[u][2 * e + 1] * kHkPre;
+                        const __half2 h = __floats2half2_rn(x0, x1);
+                        hmax = __hmax2_nan(hmax, __habs2(h));
+                        const float2 hf = __half22float2(h);
+                        const __half2 t = __floats2half2_rn((x0 - hf.x) * 2048.0f, (x1 - hf.y) * 2048.0f);      // exact differences
+                        hd[e] = *reinterpret_cast<const uint32_t*>(&h); tl[e] = *reinterpret_cast<const uint32_t*>(&t);
+                    }
+                    const uint32_t a0 = hb + 16u * (uint32_t) g, a1 = tb + 16u * (uint32_t) g;
+                    const uint32_t s0 = a0 ^ (((a0 >> 7) & swzMask) << 4), s1 = a1 ^ (((a1 >> 7) & swzMask) << 4);
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" :: "r"(s0), "r"(hd[0]), "r"(hd[1]), "r"(hd[2]), "r"(hd[3]) : "memory");
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" :: "r"(s1), "r"(tl[0]), "r"(tl[1]), "r"(tl[2]), "r"(tl[3]) : "memory");
+                }
+            }
+            fence_async_smem();                                      // generic-proxy stores -> async-proxy reads of the MMAs
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bFull + st);
+        }
+        const float2 hm = __half22float2(hmax);
+        if (!(hm.x < 32768.0f) || !(hm.y < 32768.0f)) atomicOr(ovf, 1u);
+    } else if (warp == 4) {
+        // =========================================================== MMA issue
+        const uint32_t el = elect_one();
+        const uint32_t idesc = make_idesc(128, kHkCols);
+        const uint32_t wh = smem_u32(Wsm), wt = wh + wBytes;
+        const uint32_t sbo = 8u * (uint32_t) P.rowBytes, lay = (uint32_t) P.layout;
+        // x0*w0 of the K steps that hold the filters' main lobe (|w| up to 1: steps cLo..cHi) accumulate in D0A, the sinc tails
+        // (|w| < 0.05) in D0B: the tensor core truncates the accumulator after every MMA, by an ulp of its magnitude, so the
+        // error comes from the few centre steps only; D0B stays small and its truncations are negligible.
+        const uint64_t aH0 = make_desc(wh, 2048, 128, 0), aT0 = make_desc(wt, 2048, 128, 0);
+        for (int i = 0; i < myTiles; ++i) {
+            const int st = i % kHkStages, ac = i & 1;
+            if (i >= 2) mbar_wait(accEmpty + ac, (uint32_t) ((i / 2 - 1) & 1));                    // the epilogue has drained this accumulator set
+            mbar_wait(bFull + st, (uint32_t) ((i / kHkStages) & 1));
+            tc_fence_after();
+            if (el) {
+                const uint32_t hb = smem_u32(ring + (size_t) st * 2 * bufBytes), tb = hb + bufBytes;
+                const uint32_t d0a = tmem + (uint32_t) (ac * 3 * kHkCols), d0b = d0a + kHkCols, d1 = d0a + 2 * kHkCols;
+                const uint64_t bH0 = make_desc(hb, 16, sbo, lay), bT0 = make_desc(tb, 16, sbo, lay);
+                bool firstB = true;
+                for (int s = 0; s < KS; ++s) {
+                    const uint64_t aH = aH0 + (uint64_t) (s * 256), aT = aT0 + (uint64_t) (s * 256);     // + 4096 bytes per K step (address field is >> 4)
+                    const uint64_t bH = bH0 + (uint64_t) (2 * s), bT = bT0 + (uint64_t) (2 * s);         // + 32 bytes per K step: the Hankel shift
+                    const bool centre = s >= P.cLo && s <= P.cHi;
+                    if (centre) umma_ss(d0a, aH, bH, idesc, s != P.cLo ? 1u : 0u);                        // w0 x0, main lobe
+                    else { umma_ss(d0b, aH, bH, idesc, firstB ? 0u : 1u); firstB = false; }               // w0 x0, tails
+                    umma_ss(d1, aT, bH, idesc, s != 0 ? 1u : 0u);                                     // w1 x0
+                    umma_ss(d1, aH, bT, idesc, 1u);                                                   // w0 x1
+                }
+                umma_commit(bEmpty + st);                            // the stage may be refilled once these MMAs have read it
+                umma_commit(accFull + ac);
+            }
+            __syncwarp();
+        }
+    } else {
+        // =========================================================== epilogue
+        const uint32_t laneBase = (uint32_t) (warp * 32) << 16;
+        const int l = warp * 32 + lane;                              // TMEM lane = offset of the output inside its column
+        const HankelTileRec* rec = recs + blockIdx.x;
+        struct TileOut { float* out; long long oBase, numOut; };
+        auto load_rec = [&](const HankelTileRec* r) { TileOut T; T.out = ldg_ptr(&r->out); T.oBase = __ldg(&r->oBase); T.numOut = __ldg(&r->numOut); return T; };
+        TileOut N = {nullptr, 0, 0};
+        if (myTiles > 0) N = load_rec(rec);
+        for (int i = 0; i < myTiles; ++i, rec += gridDim.x) {
+            const TileOut T = N;
+            if (i + 1 < myTiles) N = load_rec(rec + gridDim.x);
+            const int ac = i & 1;
+            mbar_wait(accFull + ac, (uint32_t) ((i / 2) & 1));
+            tc_fence_after();
+            const bool inside = T.oBase >= 0 && T.oBase + 128LL * kHkCols <= T.numOut;
+            float* outG = reinterpret_cast<float*>(__cvta_generic_to_global(T.out));
+            #pragma unroll 1
+            for (int c = 0; c < kHkCols / 16; ++c) {
+                uint32_t va[16], vb[16], v1[16];
+                const uint32_t c0 = tmem + laneBase + (uint32_t) (ac * 3 * kHkCols + c * 16);
+                #define LD16(arr, addr) asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];" \
+                    : "=r"(arr[0]), "=r"(arr[1]), "=r"(arr[2]), "=r"(arr[3]), "=r"(arr[4]), "=r"(arr[5]), "=r"(arr[6]), "=r"(arr[7]), \
+                      "=r"(arr[8]), "=r"(arr[9]), "=r"(arr[10]), "=r"(arr[11]), "=r"(arr[12]), "=r"(arr[13]), "=r"(arr[14]), "=r"(arr[15]) : "r"(addr))
+                LD16(va, c0);
+                LD16(vb, c0 + (uint32_t) kHkCols);
+                LD16(v1, c0 + (uint32_t) (2 * kHkCols));
+                #undef LD16
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (c == kHkCols / 16 - 1) {                         // everything has been read: the set may be overwritten
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(accEmpty + ac);
+                }
+                const long long o0 = T.oBase + 128LL * (c * 16) + l;
+                if (inside) {
+                    #pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        asm volatile("st.global.cs.f32 [%0], %1;" :: "l"(outG + o0 + 128 * j), "f"(combine(va[j], vb[j], v1[j])));
+                } else {
+                    #pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const long long o = o0 + 128 * j;
+                        if (o >= 0 && o < T.numOut) outG[o] = combine(va[j], vb[j], v1[j]);
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512) : "memory");
+}
+
+// fp32 recomputation of a launch whose input did not fit the fp16 split: exits at once unless the flag is set.
+__global__ void __launch_bounds__(256)
+hankel_redo_kernel(const HankelTileRec* __restrict__ recs, int nTiles, int L, PolyDev W, const unsigned* __restrict__ ovf) {
+    if (*ovf == 0u) return;
+    const int R = 128 / L;
+    for (int t = blockIdx.x; t < nTiles; t += gridDim.x) {
+        const HankelTileRec T = recs[t];
+        for (int i = threadIdx.x; i < 128 * kHkCols; i += blockDim.x) {
+            const long long o = T.oBase + i;
+            if (o < 0 || o >= T.numOut) continue;
+            const int col = i >> 7, l = i & 127, ii = l / L, k = l - ii * L;
+            const long long m = T.x0 + 208 + (long long) R * col + ii;          // window index of the newest input of this output
+            float acc = 0.0f;
+            for (int j = 0; j < W.taps; ++j) {
+                const long long li = m - (W.taps - 1) + j;
+                const float x = (li >= 0 && li < T.inAvail) ? __ldg(T.in + li) : 0.0f;
+                acc = fmaf(x, __ldg(W.W + (size_t) j * W.qpad + k), acc);
+            }
+            T.out[o] = acc;
+        }
+    }
+}
+
+}  // namespace
+
+size_t hankel_smem_bytes(const HankelDev& P) {
+    return 1024 + (size_t) 2 * P.KS * 4096 + (size_t) kHkStages * 2 * P.bufBytes + 256;
+}
+long long hankel_tiles_for_segment(long long n0, long long numOut) {
+    if (numOut <= 0) return 0;
+    const long long c0 = n0 / 128, c1 = (n0 + numOut - 1) / 128;
+    return (c1 - c0 + 1 + kHkCols - 1) / kHkCols;
+}
+int hankel_tile_elems(int L, int KS) { return (128 / L) * kHkCols + 16 * KS; }
+
+cudaError_t launch_hankel(const ResampleLaunch& L, cudaStream_t s, long long* launches) {
+    if (!L.d_tile_recs || !L.d_ovf) return cudaErrorInvalidValue;
+    HankelTileRec* recs = reinterpret_cast<HankelTileRec*>(L.d_tile_recs);
+    const size_t smem = hankel_smem_bytes(L.hk);
+    cudaError_t e = cudaFuncSetAttribute(hankel_fir_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    if (e != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(L.d_ovf, 0, sizeof(unsigned), s)) != cudaSuccess) return e;
+    hankel_tile_table_kernel<<<(L.n_tiles + 255) / 256, 256, 0, s>>>(L.d_segs, L.d_tile_prefix, L.n_segs, L.n_tiles, 128 / L.hk.L, recs);
+    ++*launches;
+    const int grid = std::min(L.n_tiles, L.sm_count);
+    hankel_fir_kernel<<<grid, kHkThreads, smem, s>>>(recs, L.n_tiles, L.hk, L.d_ovf);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    ++*launches;
+    hankel_redo_kernel<<<std::min(L.n_tiles, 8 * L.sm_count), 256, 0, s>>>(recs, L.n_tiles, L.hk.L, L.poly, L.d_ovf);
+    ++*launches;
+    return cudaGetLastError();
+}
+
+}  // namespace f9

@@ -225,8 +225,25 @@ bool umma_encode_maps(const Seg* segs, int n, int p, UmmaTma* out);
 void umma_choose_plan(int taps, long long p, long long q, long long* m_out, int* NB_out, int* GBL_out);
 double umma_cost_per_output(int taps, long long p, long long q, int NB, int GBL, size_t* smem2);   // model used to pick the plan
 
+// Hankel-operand FIR for integer upsampling 1:L (f9_hankel.cu): device weight image + geometry
+struct HankelDev {
+    int L = 0;                     // upsampling factor (2, 4, 8, 16); R = 128 / L inputs per column of 128 outputs
+    int KS = 0;                    // K steps of 16 samples: K = R + 208 rounded up
+    int rowBytes = 0, layout = 0;  // operand row pitch 2R bytes = swizzle width; descriptor layout code (0 none, 6 / 4 / 2 = 32 / 64 / 128-byte swizzle)
+    int elems = 0, bufBytes = 0;   // fp16 elements per tile buffer (R * 64 + 16 * KS); buffer size rounded up to 1024 bytes
+    int cLo = 0, cHi = 0;          // K steps that hold the main lobe of some lane's filter (|w| up to 1): separate accumulator
+    const uint8_t* W = nullptr;    // [head, tail][KS][2 chunks][128 rows][8 fp16]: A[(i,k), t] = w_k[t - (209 - taps) - i]
+};
+constexpr size_t kHankelTileRecBytes = 48;  // sizeof(HankelTileRec), f9_hankel.cu
+bool build_hankel(int kind, const float* sinc_table, int L, std::vector<uint8_t>* image, int* KS_out);
+size_t hankel_smem_bytes(const HankelDev& P);
+long long hankel_tiles_for_segment(long long n0, long long numOut);
+int hankel_tile_elems(int L, int KS);
+
 struct ResampleLaunch {
     int kind = 0;
+    bool hankel = false;           // integer upsampling on the Hankel-operand kernel (takes priority)
+    HankelDev hk;
     // tensor-core path (takes priority over banded when set; never used with adding)
     bool umma = false;
     UmmaDev um;
@@ -260,6 +277,7 @@ struct ResampleLaunch {
 int         choose_tile_out(double ratio);
 cudaError_t launch_resample(const ResampleLaunch& L, cudaStream_t s, long long* launches);
 cudaError_t launch_umma(const ResampleLaunch& L, cudaStream_t s, long long* launches);     // f9_umma.cu
+cudaError_t launch_hankel(const ResampleLaunch& L, cudaStream_t s, long long* launches);   // f9_hankel.cu
 // CTAs one segment needs under launch configuration L (tile_out outputs each, or period blocks x group blocks)
 long long   resample_ctas_for_segment(const ResampleLaunch& L, long long n0, long long numOut);
 // Fill tile_prefix (n+1 ints) for the segments; returns the CTA total or -1 on overflow.
@@ -267,6 +285,7 @@ int         resample_build_tiles(ResampleLaunch& L, const Seg* segs, int n, std:
 // Device scratch the launch needs next to the segment table (set L.d_tile_recs to a buffer of this size; 0 = none)
 constexpr size_t kShortTileRecBytes = 48;   // sizeof(ShortTileRec), f9_resample.cu
 inline size_t resample_scratch_bytes(const ResampleLaunch& L, int n_tiles) {
+    if (L.hankel) return kHankelTileRecBytes * ((size_t) n_tiles + 1);
     if (L.short_S > 0) return kShortTileRecBytes * ((size_t) n_tiles + 1);
     return L.umma && L.um_tma ? sizeof(UmmaTileRec) * ((size_t) n_tiles + 1) : 0;
 }
@@ -300,6 +319,8 @@ struct f9_context {
     struct UmmaKey { int kind; long long p, q; int NB, GBL; unsigned epoch; bool operator<(const UmmaKey& o) const {
         return std::tie(kind, p, q, NB, GBL, epoch) < std::tie(o.kind, o.p, o.q, o.NB, o.GBL, o.epoch); } };
     std::map<UmmaKey, f9::UmmaDev> umma_cache;
+    std::map<std::tuple<int, int, unsigned>, f9::HankelDev> hankel_cache;      // (kind, L, sinc epoch)
+    int   get_hankel(int kind, int L, f9::HankelDev* out);
     int   get_umma(int kind, long long p, long long q, int NB, int GBL, f9::UmmaDev* out);
     unsigned* d_ovf = nullptr;          // see ResampleLaunch::d_ovf (two flags: one per pipeline slot)
     // Choose kernel + tables for (kind, ratio, pos0); fills everything in L except the segment table.

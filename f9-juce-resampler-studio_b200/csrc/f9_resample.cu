@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <tuple>
 
 #include "f9_internal.cuh"
 
@@ -554,6 +555,7 @@ int choose_tile_out(double ratio) {
 
 long long resample_ctas_for_segment(const ResampleLaunch& L, long long n0, long long numOut) {
     if (numOut <= 0) return 0;
+    if (L.hankel) return hankel_tiles_for_segment(n0, numOut);
     if (L.umma) {
         const long long q = L.um.q;
         const long long aFirst = n0 / q, aLast = (n0 + numOut - 1) / q;
@@ -608,6 +610,7 @@ int resample_build_tiles(ResampleLaunch& L, const Seg* segs, int n, std::vector<
 cudaError_t launch_resample(const ResampleLaunch& L, cudaStream_t s, long long* launches) {
     if (L.n_tiles <= 0) return cudaSuccess;
     cudaError_t e;
+    if (L.hankel) return launch_hankel(L, s, launches);
     if (L.umma) return launch_umma(L, s, launches);
     if (L.banded) {
         switch (L.band.TK) {
@@ -680,6 +683,26 @@ int f9_context::get_umma(int kind, long long p, long long q, int NB, int GBL, Um
     return F9_OK;
 }
 
+int f9_context::get_hankel(int kind, int L, HankelDev* out) {
+    const auto key = std::make_tuple(kind, L, sinc_epoch);
+    auto it = hankel_cache.find(key);
+    if (it != hankel_cache.end()) { *out = it->second; return F9_OK; }
+    std::vector<uint8_t> image; int KS = 0;
+    if (!build_hankel(kind, sinc_table.data(), L, &image, &KS)) return fail(F9_ERR_INVALID, "hankel table build failed");
+    HankelDev D; D.L = L; D.KS = KS; D.rowBytes = 2 * (128 / L);
+    D.layout = D.rowBytes == 128 ? 2 : D.rowBytes == 64 ? 4 : D.rowBytes == 32 ? 6 : 0;
+    { const int taps = interp_memory(kind), shift = 209 - taps, R = 128 / L;      // lane i's filter is centred on t = shift + i + taps/2
+      D.cLo = std::max(0, (shift + taps / 2 - 3) / 16); D.cHi = std::min(KS - 1, (shift + taps / 2 + 3 + R - 1) / 16); }
+    D.elems = hankel_tile_elems(L, KS); D.bufBytes = (D.elems * 2 + 1023) / 1024 * 1024;
+    uint8_t* dW = nullptr;
+    F9_TRY_CUDA(this, cudaMalloc((void**) &dW, image.size()));
+    F9_TRY_CUDA(this, cudaMemcpy(dW, image.data(), image.size(), cudaMemcpyHostToDevice));
+    D.W = dW;
+    hankel_cache[key] = D;
+    *out = D;
+    return F9_OK;
+}
+
 int f9_context::get_banded(int kind, long long p, long long q, int TK, int Gpad, BandedDev* out) {
     BandKey key{kind, p, q, TK, Gpad, sinc_epoch};
     auto it = band_cache.find(key);
@@ -711,6 +734,12 @@ int f9_context::prepare_resample(int kind, double ratio, double pos0, bool allow
         L->rational = true;
         L->sm_count = sm_count;
         // short kinds: bandwidth-bound on CUDA cores with the slot's weights in registers (F9_SHORT_UMMA=1: tensor-core kernel instead)
+        // Integer upsampling of the long kinds: Hankel-operand kernel (every input sample staged and converted once)
+        if (p == 1 && (q == 2 || q == 4 || q == 8 || q == 16) && interp_memory(kind) > 5 && getenv("F9_NO_UMMA") == nullptr && getenv("F9_NO_HANKEL") == nullptr) {
+            if (!d_ovf) F9_TRY_CUDA(this, cudaMalloc((void**) &d_ovf, 2 * sizeof(unsigned)));
+            rc = get_hankel(kind, (int) q, &L->hk); if (rc) return rc;
+            if (hankel_smem_bytes(L->hk) <= 227 * 1024) { L->hankel = true; L->d_ovf = d_ovf + cur_slot; return F9_OK; }
+        }
         // Integer decimation (q == 1, p >= 2) stays on the tensor-core kernel when it is enabled: the short kernel's stride-p shared
         // loads conflict p ways there (measured 82 % / 76 % against 93 % / 95 % of the HBM roofline at 2:1 / 4:1); everywhere else
         // the short kernel is as fast or faster (44.1 -> 48 k: 86 % against 66 %; 48 -> 192 k: 84 % against 65 %) and exact fp32.

@@ -309,6 +309,33 @@ int umma_pool_slots(int NB, int GBL, int accCols) {        // accumulator-split 
 
 }  // namespace
 
+// Weight image of the Hankel-operand FIR (f9_hankel.cu): A[l = i*L + k, t] = w_k[t - shift - i], shift = 209 - taps, as two
+// K-major no-swizzle operands (fp16 head, fp16 tail * 2048): per K step two chunks of 8 k, each 128 rows x 16 bytes.
+bool build_hankel(int kind, const float* sinc_table, int L, std::vector<uint8_t>* image, int* KS_out) {
+    const int taps = interp_memory(kind);
+    if (taps < 1 || taps > 200 || (L != 2 && L != 4 && L != 8 && L != 16)) return false;
+    const int R = 128 / L, KS = (R + 208 + 15) / 16, shift = 209 - taps;
+    image->assign((size_t) 2 * KS * 4096, 0);
+    std::vector<float> w((size_t) taps);
+    for (int k = 0; k < L; ++k) {
+        tap_weights(kind, sinc_table, (float) ((double) k / (double) L), w.data());      // phase (k*p) mod q / q with p = 1, q = L
+        for (int i = 0; i < R; ++i) {
+            const int l = i * L + k;
+            for (int j = 0; j < taps; ++j) {
+                const int t = i + j + shift;
+                const float wv = w[(size_t) j];
+                const uint16_t h0 = f32_to_f16_bits(wv);
+                const uint16_t h1 = f32_to_f16_bits((wv - f16_bits_to_f32(h0)) * 2048.0f);
+                const size_t off = (size_t) (t / 16) * 4096 + (size_t) ((t % 16) / 8) * 2048 + (size_t) (l / 8) * 128 + (size_t) (l % 8) * 16 + (size_t) (t % 8) * 2;
+                std::memcpy(image->data() + off, &h0, 2);
+                std::memcpy(image->data() + (size_t) KS * 4096 + off, &h1, 2);
+            }
+        }
+    }
+    *KS_out = KS;
+    return true;
+}
+
 size_t umma_smem_bytes(int maxEntries, int NB, int stages, bool tma, bool cta2) {
     const size_t w = (size_t) maxEntries * NB * (cta2 ? 32 : 64);   // tile: 2 K chunks x 2*NB rows x 16 B (half of the rows per CTA of a pair)
     // register loader: converted stages (fp16 head + tail, padded K chunks); TMA feed: raw fp32 boxes of 128 rows x 128 B,

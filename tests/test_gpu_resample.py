@@ -431,6 +431,69 @@ def test_short_kernel_windows(ctx, O, f9, monkeypatch, kind, fs):
             assert np.max(np.abs(a - b)) <= TOL, env
 
 
+@pytest.mark.parametrize("up", [2, 4, 8, 16])
+def test_hankel_upsampling(ctx, O, f9, monkeypatch, up):
+    """WindowedSinc at integer upsampling ratios runs the Hankel-operand tensor-core kernel (f9_hankel.cu): windows at every
+    16-byte misalignment, ragged lengths (1 sample, less than a column, several tiles), a poisoned neighbourhood (nothing
+    outside the window may leak in), time segments (n0 > 0, not a multiple of the column) equal to the whole, and agreement
+    with the polyphase tensor-core kernel (F9_NO_HANKEL) within the tolerance."""
+    torch = pytest.importorskip("torch")
+    fs_in, fs_out = 48000, 48000 * up
+    x = signal(120000, 60 + up)
+    windows = [(4, 30001), (30011, 1), (30018, 3), (30040, 611), (30700, 40000), (70800, 19), (70900, 9000)]
+    xp = x.copy()
+    mask = np.ones(x.size, bool)
+    for off, n in windows:
+        mask[off:off + n] = False
+    xp[mask] = np.nan
+    xp[mask & (np.arange(x.size) % 3 == 0)] = np.inf
+    got = _plan_resample_many(ctx, f9, torch.from_numpy(xp).cuda(), windows, 0, fs_in, fs_out)
+    for (off, n), y in zip(windows, got):
+        ref, _ = O.resample_channel(0, fs_in / fs_out, x[off:off + n], y.shape[0])
+        assert np.all(np.isfinite(y)), (off, n)
+        assert np.max(np.abs(y - ref)) <= TOL, (off, n, float(np.max(np.abs(y - ref))) / TOL)
+        if n > 1000:
+            assert snr_db(ref, y) >= 120.0
+    monkeypatch.setenv("F9_NO_HANKEL", "1")
+    other = _plan_resample_many(ctx, f9, torch.from_numpy(x).cuda(), windows, 0, fs_in, fs_out)
+    monkeypatch.delenv("F9_NO_HANKEL")
+    for a, b in zip(got, other):
+        assert np.max(np.abs(a - b)) <= TOL
+    # time segments: outputs [n0, n0 + m) of the conversion of one channel, each from its own input window with halo
+    import ctypes as C
+    n_in = 50000
+    xs = signal(n_in, 70 + up)
+    n_out = f9.resampled_length(n_in, fs_in, fs_out)
+    whole, _ = O.resample_channel(0, fs_in / fs_out, xs, n_out)
+    d = torch.from_numpy(xs).cuda()
+    cuts = [0, 1, 129, 5000 * up + 77, 31000 * up + 5, n_out]
+    outs, segs = [], []
+    for n0, n1 in zip(cuts[:-1], cuts[1:]):
+        first, last = C.c_longlong(0), C.c_longlong(0)
+        assert f9.lib().f9_resample_segment_input_range(0, fs_in / fs_out, n0, n1 - n0, C.byref(first), C.byref(last)) == 0
+        lo, hi = max(0, first.value), min(n_in, last.value)
+        o = torch.full((n1 - n0,), float("nan"), dtype=torch.float32, device="cuda")
+        outs.append(o)
+        segs.append(f9.ResampleSeg(d.data_ptr() + 4 * lo, lo, hi - lo, o.data_ptr(), n0, n1 - n0))
+    arr = (f9.ResampleSeg * len(segs))(*segs)
+    plan = C.c_void_p(None)
+    torch.cuda.synchronize()
+    assert f9.lib().f9_resample_plan_create(ctx.handle, 0, fs_in / fs_out, arr, len(segs), C.byref(plan)) == 0
+    assert f9.lib().f9_resample_plan_run(plan) == 0
+    ctx.synchronize()
+    f9.lib().f9_plan_destroy(plan)
+    y = np.concatenate([o.cpu().numpy() for o in outs])
+    assert np.max(np.abs(y - whole)) <= TOL
+
+
+def test_hankel_out_of_range_input_takes_the_fp32_redo(ctx, O, f9):
+    """|x| >= 256 does not fit the fp16 split: the flag is raised and the launch is recomputed in fp32."""
+    x = (signal(20000, 81) * 2000.0)[None, :]
+    y = ctx.resample(x, 48000, 192000, 0)
+    ref, _ = O.resample_channel(0, 0.25, x[0], y.shape[1])
+    assert np.max(np.abs(y[0] - ref)) <= 2000.0 * TOL
+
+
 def test_umma_memory_outside_the_window_never_leaks(ctx, O, f9):
     """Boundary tiles read whole boxes through TMA, i.e. real memory before and after the segment's window; the converters
     must zero it.  The neighbourhood is poisoned with NaN, Inf and huge values: any leak shows up in the output."""
