@@ -34,8 +34,11 @@ namespace f9 {
 namespace {
 
 constexpr int kHkCols = 64;                 // columns (of 128 outputs) per tile = MMA N
-constexpr int kHkStages = 3;                // input ring
-constexpr int kHkThreads = 13 * 32;
+constexpr int kHkStages = 4;                // input ring
+constexpr int kHkThreads = 14 * 32;         // warps 0-3 epilogue, 4 and 13 MMA issue (one half of the tile's columns each), 5-12 converters
+constexpr int kHkHalf = kHkCols / 2;        // columns per MMA (N) and accumulator set
+constexpr int kHkATail = 136;               // TMEM columns: weight heads at 0, tails at 136 (8 per K step, K <= 272)
+constexpr int kHkD = 272;                   // accumulator sets at 272 + 96 h: D0A, D0B, D1 of kHkHalf columns each
 constexpr int kHkConvWarps = 8, kHkFirstConv = 5;
 constexpr float kHkPre = 128.0f;            // 2^7 pre-scale, as f9_umma.cu
 constexpr uint32_t kHkPark = 2000;
@@ -73,6 +76,10 @@ __device__ __forceinline__ uint32_t elect_one() {
 __device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                  :: "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                 :: "r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
@@ -124,42 +131,52 @@ hankel_tile_table_kernel(const Seg* __restrict__ segs, const int* __restrict__ t
     recs[t] = Rr;
 }
 
+template <int KS>
 __global__ void __launch_bounds__(kHkThreads, 1)
-hankel_fir_kernel(const HankelTileRec* __restrict__ recs, int nTiles, const __grid_constant__ HankelDev P, unsigned* __restrict__ ovf) {
+hankel_fir_kernel(const HankelTileRec* __restrict__ recs, int nTiles, const __grid_constant__ HankelDev P, unsigned* __restrict__ ovf, int dbg) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // the swizzle patterns repeat on 1024 bytes
-    const int KS = P.KS;
-    const uint32_t wBytes = (uint32_t) KS * 4096u;                  // one weight part: per K step 2 chunks x 128 rows x 16 B
-    uint8_t* Wsm = smem;                                            // head image, tail image
-    uint8_t* ring = smem + 2 * wBytes;                              // kHkStages x (head buffer, tail buffer), bufBytes each (1024-aligned)
-    const uint32_t bufBytes = (uint32_t) P.bufBytes;
+    uint8_t* ring = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // the swizzle patterns repeat on 1024 bytes
+    const uint32_t bufBytes = (uint32_t) P.bufBytes;                // kHkStages x (head buffer, tail buffer), 1024-aligned
     uint64_t* bars = reinterpret_cast<uint64_t*>(ring + kHkStages * 2 * bufBytes);
     uint64_t *bFull = bars, *bEmpty = bars + kHkStages, *accFull = bars + 2 * kHkStages, *accEmpty = accFull + 2;
     uint32_t* tmemSlot = reinterpret_cast<uint32_t*>(accEmpty + 2);
     const int warp = __shfl_sync(0xffffffffu, (int) (threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int myTiles = (int) blockIdx.x < nTiles ? (nTiles - 1 - (int) blockIdx.x) / (int) gridDim.x + 1 : 0;
 
-    {   // ---- one-time setup
-        const uint4* src = reinterpret_cast<const uint4*>(P.W);
-        uint4* dst = reinterpret_cast<uint4*>(Wsm);
-        for (int i = threadIdx.x; i < (int) (2 * wBytes / 16); i += blockDim.x) dst[i] = __ldg(src + i);
-        if (threadIdx.x == 0) {
-            for (int s = 0; s < kHkStages; ++s) { mbar_init(bFull + s, kHkConvWarps); mbar_init(bEmpty + s, 1); }
-            for (int a = 0; a < 2; ++a) { mbar_init(accFull + a, 1); mbar_init(accEmpty + a, 4); }
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        if (warp == 4) {
-            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmemSlot)), "r"(512) : "memory");
-            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-        }
-        fence_async_smem();                                          // the weights are read by the tensor pipe (async proxy)
-        tc_fence_before();
-        __syncthreads();
-        tc_fence_after();
+    // ---- one-time setup: barriers, TMEM, the weights into TMEM (the M-side operand of every MMA: lane = output offset)
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kHkStages; ++s) { mbar_init(bFull + s, kHkConvWarps); mbar_init(bEmpty + s, 2); }
+        for (int a = 0; a < 2; ++a) { mbar_init(accFull + a, 1); mbar_init(accEmpty + a, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmemSlot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
     const uint32_t tmem = *tmemSlot;
+    if (warp < 4) {
+        const int l = warp * 32 + lane;
+        const uint32_t laneBase = (uint32_t) (warp * 32) << 16;
+        #pragma unroll 1
+        for (int part = 0; part < 2; ++part) {
+            const uint4* row = reinterpret_cast<const uint4*>(P.W + ((size_t) part * 128 + l) * (size_t) (KS * 32));   // KS * 16 fp16 per lane
+            #pragma unroll 1
+            for (int s = 0; s < KS; ++s) {
+                const uint4 a = __ldg(row + 2 * s), b = __ldg(row + 2 * s + 1);
+                asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                             :: "r"(tmem + laneBase + (uint32_t) (part * kHkATail + 8 * s)), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
+            }
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
 
-    if (warp >= kHkFirstConv) {
+    if (warp >= kHkFirstConv && warp < kHkFirstConv + kHkConvWarps) {
         // =========================================================== converters
         // The loads of tile i + 1 are issued (into registers) before tile i is converted, so their latency overlaps the
         // conversion, the stores and the wait for the ring; every sample is loaded exactly once.
@@ -190,7 +207,7 @@ hankel_fir_kernel(const HankelTileRec* __restrict__ recs, int nTiles, const __gr
         };
         float nxt[kG][8], cur[kG][8];
         TileIn T1 = {nullptr, 0, 0}, T2 = T1;
-        if (myTiles > 0) { T1 = load_rec(rec); load_tile(T1, nxt); }
+        if (myTiles > 0) { T1 = load_rec(rec); if (!(dbg & 2)) load_tile(T1, nxt); }
         if (myTiles > 1) T2 = load_rec(rec + gridDim.x);
         for (int i = 0; i < myTiles; ++i, rec += gridDim.x) {
             #pragma unroll
@@ -199,7 +216,7 @@ hankel_fir_kernel(const HankelTileRec* __restrict__ recs, int nTiles, const __gr
                 for (int e = 0; e < 8; ++e) cur[u][e] = nxt[u][e];
             if (i + 1 < myTiles) {
                 T1 = T2;
-                load_tile(T1, nxt);
+                if (!(dbg & 2)) load_tile(T1, nxt);
                 if (i + 2 < myTiles) T2 = load_rec(rec + 2 * (size_t) gridDim.x);
             }
             const int st = i % kHkStages;
@@ -208,7 +225,7 @@ hankel_fir_kernel(const HankelTileRec* __restrict__ recs, int nTiles, const __gr
             #pragma unroll
             for (int u = 0; u < kG; ++u) {
                 const int g = ctid + u * kHkConvWarps * 32;
-                if (g < groups) {
+                if (g < groups && !(dbg & 2)) {
                     uint32_t hd[4], tl[4];
                     #pragma unroll
                     for (int e = 0; e < 4; ++e) {
@@ -231,37 +248,38 @@ hankel_fir_kernel(const HankelTileRec* __restrict__ recs, int nTiles, const __gr
         }
         const float2 hm = __half22float2(hmax);
         if (!(hm.x < 32768.0f) || !(hm.y < 32768.0f)) atomicOr(ovf, 1u);
-    } else if (warp == 4) {
-        // =========================================================== MMA issue
-        const uint32_t el = elect_one();
-        const uint32_t idesc = make_idesc(128, kHkCols);
-        const uint32_t wh = smem_u32(Wsm), wt = wh + wBytes;
-        const uint32_t sbo = 8u * (uint32_t) P.rowBytes, lay = (uint32_t) P.layout;
+    } else if (warp == 4 || warp == 13) {
+        // =========================================================== MMA issue (TS mode: weights from TMEM, input from shared memory)
+        // Warp 4 owns columns 0-31 of every tile and accumulator set 0, warp 13 columns 32-63 and set 1: 3 * KS MMAs of N = 32 each.
         // x0*w0 of the K steps that hold the filters' main lobe (|w| up to 1: steps cLo..cHi) accumulate in D0A, the sinc tails
         // (|w| < 0.05) in D0B: the tensor core truncates the accumulator after every MMA, by an ulp of its magnitude, so the
         // error comes from the few centre steps only; D0B stays small and its truncations are negligible.
-        const uint64_t aH0 = make_desc(wh, 2048, 128, 0), aT0 = make_desc(wt, 2048, 128, 0);
+        const int h = warp == 4 ? 0 : 1;
+        const uint32_t el = elect_one();
+        const uint32_t idesc = make_idesc(128, kHkHalf);
+        const uint32_t sbo = 8u * (uint32_t) P.rowBytes, lay = (uint32_t) P.layout;
+        const uint32_t d0a = tmem + (uint32_t) (kHkD + 96 * h), d0b = d0a + kHkHalf, d1 = d0a + 2 * kHkHalf;
+        const int cLo = P.cLo, cHi = P.cHi;
         for (int i = 0; i < myTiles; ++i) {
-            const int st = i % kHkStages, ac = i & 1;
-            if (i >= 2) mbar_wait(accEmpty + ac, (uint32_t) ((i / 2 - 1) & 1));                    // the epilogue has drained this accumulator set
+            const int st = i % kHkStages;
+            if (i >= 1) mbar_wait(accEmpty + h, (uint32_t) ((i - 1) & 1));                         // the epilogue has drained this accumulator set
             mbar_wait(bFull + st, (uint32_t) ((i / kHkStages) & 1));
             tc_fence_after();
             if (el) {
-                const uint32_t hb = smem_u32(ring + (size_t) st * 2 * bufBytes), tb = hb + bufBytes;
-                const uint32_t d0a = tmem + (uint32_t) (ac * 3 * kHkCols), d0b = d0a + kHkCols, d1 = d0a + 2 * kHkCols;
+                const uint32_t hb = smem_u32(ring + (size_t) st * 2 * bufBytes) + (uint32_t) (h * kHkHalf * P.rowBytes), tb = hb + bufBytes;
                 const uint64_t bH0 = make_desc(hb, 16, sbo, lay), bT0 = make_desc(tb, 16, sbo, lay);
-                bool firstB = true;
-                for (int s = 0; s < KS; ++s) {
-                    const uint64_t aH = aH0 + (uint64_t) (s * 256), aT = aT0 + (uint64_t) (s * 256);     // + 4096 bytes per K step (address field is >> 4)
-                    const uint64_t bH = bH0 + (uint64_t) (2 * s), bT = bT0 + (uint64_t) (2 * s);         // + 32 bytes per K step: the Hankel shift
-                    const bool centre = s >= P.cLo && s <= P.cHi;
-                    if (centre) umma_ss(d0a, aH, bH, idesc, s != P.cLo ? 1u : 0u);                        // w0 x0, main lobe
-                    else { umma_ss(d0b, aH, bH, idesc, firstB ? 0u : 1u); firstB = false; }               // w0 x0, tails
-                    umma_ss(d1, aT, bH, idesc, s != 0 ? 1u : 0u);                                     // w1 x0
-                    umma_ss(d1, aH, bT, idesc, 1u);                                                   // w0 x1
+                if (!(dbg & 1)) {
+                    #pragma unroll
+                    for (int s = 0; s < KS; ++s) {
+                        const uint64_t bH = bH0 + (uint64_t) (2 * s), bT = bT0 + (uint64_t) (2 * s);         // + 32 bytes per K step: the Hankel shift
+                        const bool centre = s >= cLo && s <= cHi;
+                        umma_ts(centre ? d0a : d0b, tmem + (uint32_t) (8 * s), bH, idesc, (s == cLo || s == (cLo == 0 ? cHi + 1 : 0)) ? 0u : 1u);   // w0 x0
+                        umma_ts(d1, tmem + (uint32_t) (kHkATail + 8 * s), bH, idesc, s != 0 ? 1u : 0u);     // w1 x0
+                        umma_ts(d1, tmem + (uint32_t) (8 * s), bT, idesc, 1u);                                // w0 x1
+                    }
                 }
-                umma_commit(bEmpty + st);                            // the stage may be refilled once these MMAs have read it
-                umma_commit(accFull + ac);
+                umma_commit(bEmpty + st);                            // the stage may be refilled once both halves' MMAs have read it
+                umma_commit(accFull + h);
             }
             __syncwarp();
         }
@@ -277,38 +295,40 @@ hankel_fir_kernel(const HankelTileRec* __restrict__ recs, int nTiles, const __gr
         for (int i = 0; i < myTiles; ++i, rec += gridDim.x) {
             const TileOut T = N;
             if (i + 1 < myTiles) N = load_rec(rec + gridDim.x);
-            const int ac = i & 1;
-            mbar_wait(accFull + ac, (uint32_t) ((i / 2) & 1));
-            tc_fence_after();
             const bool inside = T.oBase >= 0 && T.oBase + 128LL * kHkCols <= T.numOut;
             float* outG = reinterpret_cast<float*>(__cvta_generic_to_global(T.out));
             #pragma unroll 1
-            for (int c = 0; c < kHkCols / 16; ++c) {
-                uint32_t va[16], vb[16], v1[16];
-                const uint32_t c0 = tmem + laneBase + (uint32_t) (ac * 3 * kHkCols + c * 16);
-                #define LD16(arr, addr) asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];" \
-                    : "=r"(arr[0]), "=r"(arr[1]), "=r"(arr[2]), "=r"(arr[3]), "=r"(arr[4]), "=r"(arr[5]), "=r"(arr[6]), "=r"(arr[7]), \
-                      "=r"(arr[8]), "=r"(arr[9]), "=r"(arr[10]), "=r"(arr[11]), "=r"(arr[12]), "=r"(arr[13]), "=r"(arr[14]), "=r"(arr[15]) : "r"(addr))
-                LD16(va, c0);
-                LD16(vb, c0 + (uint32_t) kHkCols);
-                LD16(v1, c0 + (uint32_t) (2 * kHkCols));
-                #undef LD16
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (c == kHkCols / 16 - 1) {                         // everything has been read: the set may be overwritten
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(accEmpty + ac);
-                }
-                const long long o0 = T.oBase + 128LL * (c * 16) + l;
-                if (inside) {
-                    #pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        asm volatile("st.global.cs.f32 [%0], %1;" :: "l"(outG + o0 + 128 * j), "f"(combine(va[j], vb[j], v1[j])));
-                } else {
-                    #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const long long o = o0 + 128 * j;
-                        if (o >= 0 && o < T.numOut) outG[o] = combine(va[j], vb[j], v1[j]);
+            for (int h = 0; h < 2; ++h) {
+                mbar_wait(accFull + h, (uint32_t) (i & 1));
+                tc_fence_after();
+                #pragma unroll 1
+                for (int c = 0; c < kHkHalf / 16; ++c) {
+                    uint32_t va[16], vb[16], v1[16];
+                    const uint32_t c0 = tmem + laneBase + (uint32_t) (kHkD + 96 * h + c * 16);
+                    #define LD16(arr, addr) asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];" \
+                        : "=r"(arr[0]), "=r"(arr[1]), "=r"(arr[2]), "=r"(arr[3]), "=r"(arr[4]), "=r"(arr[5]), "=r"(arr[6]), "=r"(arr[7]), \
+                          "=r"(arr[8]), "=r"(arr[9]), "=r"(arr[10]), "=r"(arr[11]), "=r"(arr[12]), "=r"(arr[13]), "=r"(arr[14]), "=r"(arr[15]) : "r"(addr))
+                    LD16(va, c0);
+                    LD16(vb, c0 + (uint32_t) kHkHalf);
+                    LD16(v1, c0 + (uint32_t) (2 * kHkHalf));
+                    #undef LD16
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (c == kHkHalf / 16 - 1) {                     // everything has been read: the set may be overwritten
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(accEmpty + h);
+                    }
+                    const long long o0 = T.oBase + 128LL * (h * kHkHalf + c * 16) + l;
+                    if (dbg & 4) {} else if (inside) {
+                        #pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            asm volatile("st.global.cs.f32 [%0], %1;" :: "l"(outG + o0 + 128 * j), "f"(combine(va[j], vb[j], v1[j])));
+                    } else {
+                        #pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const long long o = o0 + 128 * j;
+                            if (o >= 0 && o < T.numOut) outG[o] = combine(va[j], vb[j], v1[j]);
+                        }
                     }
                 }
             }
@@ -346,7 +366,7 @@ hankel_redo_kernel(const HankelTileRec* __restrict__ recs, int nTiles, int L, Po
 }  // namespace
 
 size_t hankel_smem_bytes(const HankelDev& P) {
-    return 1024 + (size_t) 2 * P.KS * 4096 + (size_t) kHkStages * 2 * P.bufBytes + 256;
+    return 1024 + (size_t) kHkStages * 2 * P.bufBytes + 256;
 }
 long long hankel_tiles_for_segment(long long n0, long long numOut) {
     if (numOut <= 0) return 0;
@@ -359,13 +379,22 @@ cudaError_t launch_hankel(const ResampleLaunch& L, cudaStream_t s, long long* la
     if (!L.d_tile_recs || !L.d_ovf) return cudaErrorInvalidValue;
     HankelTileRec* recs = reinterpret_cast<HankelTileRec*>(L.d_tile_recs);
     const size_t smem = hankel_smem_bytes(L.hk);
-    cudaError_t e = cudaFuncSetAttribute(hankel_fir_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-    if (e != cudaSuccess) return e;
+    cudaError_t e;
     if ((e = cudaMemsetAsync(L.d_ovf, 0, sizeof(unsigned), s)) != cudaSuccess) return e;
     hankel_tile_table_kernel<<<(L.n_tiles + 255) / 256, 256, 0, s>>>(L.d_segs, L.d_tile_prefix, L.n_segs, L.n_tiles, 128 / L.hk.L, recs);
     ++*launches;
     const int grid = std::min(L.n_tiles, L.sm_count);
-    hankel_fir_kernel<<<grid, kHkThreads, smem, s>>>(recs, L.n_tiles, L.hk, L.d_ovf);
+    const int dbg = getenv("F9_HK_DBG") ? atoi(getenv("F9_HK_DBG")) : 0;      // development: 1 skip MMAs, 2 skip loads + conversion, 4 skip stores
+    #define F9_HK_LAUNCH(KS) do { \
+        if ((e = cudaFuncSetAttribute(hankel_fir_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)) != cudaSuccess) return e; \
+        hankel_fir_kernel<KS><<<grid, kHkThreads, smem, s>>>(recs, L.n_tiles, L.hk, L.d_ovf, dbg); } while (0)
+    switch (L.hk.KS) {
+        case 14: F9_HK_LAUNCH(14); break;
+        case 15: F9_HK_LAUNCH(15); break;
+        case 17: F9_HK_LAUNCH(17); break;
+        default: return cudaErrorInvalidValue;
+    }
+    #undef F9_HK_LAUNCH
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     ++*launches;
     hankel_redo_kernel<<<std::min(L.n_tiles, 8 * L.sm_count), 256, 0, s>>>(recs, L.n_tiles, L.hk.L, L.poly, L.d_ovf);

@@ -310,7 +310,7 @@ int umma_pool_slots(int NB, int GBL, int accCols) {        // accumulator-split 
 }  // namespace
 
 // Weight image of the Hankel-operand FIR (f9_hankel.cu): A[l = i*L + k, t] = w_k[t - shift - i], shift = 209 - taps, as two
-// K-major no-swizzle operands (fp16 head, fp16 tail * 2048): per K step two chunks of 8 k, each 128 rows x 16 bytes.
+// row-major matrices [128 lanes][16 KS] of fp16 (heads, then tails * 2048): each lane's row goes into TMEM as the MMAs' M-side operand.
 bool build_hankel(int kind, const float* sinc_table, int L, std::vector<uint8_t>* image, int* KS_out) {
     const int taps = interp_memory(kind);
     if (taps < 1 || taps > 200 || (L != 2 && L != 4 && L != 8 && L != 16)) return false;
@@ -326,7 +326,7 @@ bool build_hankel(int kind, const float* sinc_table, int L, std::vector<uint8_t>
                 const float wv = w[(size_t) j];
                 const uint16_t h0 = f32_to_f16_bits(wv);
                 const uint16_t h1 = f32_to_f16_bits((wv - f16_bits_to_f32(h0)) * 2048.0f);
-                const size_t off = (size_t) (t / 16) * 4096 + (size_t) ((t % 16) / 8) * 2048 + (size_t) (l / 8) * 128 + (size_t) (l % 8) * 16 + (size_t) (t % 8) * 2;
+                const size_t off = ((size_t) l * (size_t) (KS * 16) + (size_t) t) * 2;
                 std::memcpy(image->data() + off, &h0, 2);
                 std::memcpy(image->data() + (size_t) KS * 4096 + off, &h1, 2);
             }
