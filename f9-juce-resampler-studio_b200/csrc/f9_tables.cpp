@@ -587,6 +587,41 @@ bool build_umma(int kind, const float* sinc_table, long long p, long long q, int
 // ---- diagnostics (host only) -------------------------------------------------------------------------------
 // Builds the tensor-core plan of ratio p/q and checks its tables against the fp32 polyphase weights: every (slot, tap)
 // appears in exactly one weight tile position, everything else is zero, and head + tail/2048 reproduces the weight.
+// Diagnostic for the Hankel-operand FIR's weight image (CPU only): rebuilds it for (kind, 1:L) and checks that lane l = i*L + k
+// holds w_k[j] at t = i + j + shift and zeros elsewhere.  Returns the largest |w - (w0 + w1/2048)|, -1 bad arguments, -3 defect.
+extern "C" double f9_hankel_selfcheck(int kind, int L, int* info /* 4 ints or NULL: KS, elements per tile, buffer bytes, shared-memory bytes */) {
+    using namespace f9;
+    const int taps = interp_memory(kind);
+    if (taps == 0) return -1.0;
+    std::vector<float> table((size_t) kSincTableSize + 1, 0.0f);
+    make_default_sinc_table(table.data());
+    std::vector<uint8_t> image; int KS = 0;
+    if (!build_hankel(kind, table.data(), L, &image, &KS)) return -1.0;
+    const int R = 128 / L, shift = 209 - taps, K = KS * 16;
+    if (R + 208 > K || image.size() != (size_t) 2 * KS * 4096) return -3.0;
+    std::vector<float> w((size_t) taps);
+    double maxErr = 0.0;
+    for (int l = 0; l < 128; ++l) {
+        const int i = l / L, k = l % L;
+        tap_weights(kind, table.data(), (float) ((double) k / (double) L), w.data());
+        for (int t = 0; t < K; ++t) {
+            uint16_t h0, h1;
+            std::memcpy(&h0, image.data() + ((size_t) l * K + t) * 2, 2);
+            std::memcpy(&h1, image.data() + (size_t) KS * 4096 + ((size_t) l * K + t) * 2, 2);
+            const int j = t - shift - i;
+            const double want = (j >= 0 && j < taps) ? (double) w[(size_t) j] : 0.0;
+            const double got = (double) f16_bits_to_f32(h0) + (double) f16_bits_to_f32(h1) / 2048.0;
+            if (want == 0.0 && (h0 & 0x7fff || h1 & 0x7fff)) return -3.0;
+            maxErr = std::max(maxErr, std::fabs(want - got));
+        }
+    }
+    if (info) {
+        HankelDev D; D.L = L; D.KS = KS; D.elems = hankel_tile_elems(L, KS); D.bufBytes = (D.elems * 2 + 1023) / 1024 * 1024;
+        info[0] = KS; info[1] = D.elems; info[2] = D.bufBytes; info[3] = (int) hankel_smem_bytes(D);
+    }
+    return maxErr;
+}
+
 extern "C" double f9_umma_selfcheck(int kind, long long p, long long q, int* info /* 8 ints or NULL */) {
     using namespace f9;
     const int taps = interp_memory(kind);

@@ -74,6 +74,7 @@ SYMBOLS = [
     ("f9_version", _i, []),
     ("f9_device_count", _i, []),
     ("f9_umma_selfcheck", _d, [_i, _ll, _ll, _ip]),
+    ("f9_hankel_selfcheck", _d, [_i, _i, _ip]),
     ("f9_recording_length", _i, [_i, _i]),
     ("f9_noise_floor_threshold_db", _f, [_i, _f, _f]),
     ("f9_threshold_linear", _f, [_f]),

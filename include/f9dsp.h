@@ -88,6 +88,10 @@ F9_API int  f9_device_count(void);            /* 0 when there is no usable devic
  * tensor-core plan fits (the CUDA-core kernels serve the ratio), -3..-5 table defects.  info (8 ints, may be NULL):
  * scale m, slots per group, groups, groups per block, blocks, accumulator pool slots, split step, shared-memory bytes. */
 F9_API double f9_umma_selfcheck(int kind, long long p, long long q, int* info);
+/* Same for the Hankel-operand FIR that serves integer upsampling 1:L (L = 2, 4, 8, 16): largest reconstruction error of the
+ * weight image, -1 bad arguments, -3 table defect.  info (4 ints, may be NULL): K steps, fp16 elements per tile buffer, buffer
+ * bytes, shared-memory bytes of the kernel. */
+F9_API double f9_hankel_selfcheck(int kind, int L, int* info);
 
 /* ============================ B. settings math =============================== */
 /* Host scalars; mirror ProcessingSettings (Source/AppState.h:183-259). */

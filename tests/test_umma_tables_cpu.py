@@ -37,6 +37,28 @@ def test_bench_ratio_plan(f9):
     assert m >> 16 == 4                                     # four-stage operand ring: the pool of two slots still fits
 
 
+@pytest.mark.parametrize("kind", [0, 1, 2, 3])
+@pytest.mark.parametrize("up", [2, 4, 8, 16])
+def test_hankel_weight_image(f9, kind, up):
+    """Weight image of the Hankel-operand FIR (integer upsampling): lane i*L + k holds phase k's taps shifted by i, zeros elsewhere;
+    the tile buffer holds every K step of every column; the kernel's shared memory and TMEM budgets hold."""
+    info = (C.c_int * 4)()
+    err = f9.lib().f9_hankel_selfcheck(kind, up, info)
+    assert 0.0 <= err <= 2.0 ** -22, (kind, up, err)
+    ks, elems, buf_bytes, smem = list(info)
+    r = 128 // up
+    assert ks * 16 >= r + 208 and ks in (14, 15, 17)
+    assert elems == r * 64 + 16 * ks and elems % 8 == 0 and elems <= 3 * 256 * 8      # three groups of 8 per converter thread
+    assert 32 * (ks - 1) + 63 * 2 * r + 32 <= 2 * elems                                 # last K step of the last column stays inside
+    assert buf_bytes % 1024 == 0 and buf_bytes >= 2 * elems and smem <= 227 * 1024
+    assert 8 * ks <= 136 and 272 + 2 * 96 <= 512                                        # TMEM: weight heads, tails, two accumulator sets
+
+
+def test_hankel_bad_arguments(f9):
+    assert f9.lib().f9_hankel_selfcheck(0, 3, None) == -1.0
+    assert f9.lib().f9_hankel_selfcheck(99, 4, None) == -1.0
+
+
 def test_bad_arguments(f9):
     assert f9.lib().f9_umma_selfcheck(99, 1, 1, None) == -1.0
     assert f9.lib().f9_umma_selfcheck(0, 0, 1, None) == -1.0
