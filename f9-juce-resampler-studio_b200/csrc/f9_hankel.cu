@@ -13,20 +13,22 @@
 // start).  Every input sample is fetched from HBM once, converted once and stored once; the polyphase kernel in f9_umma.cu
 // stages and converts each sample (taps + p)/p = 6 times at this ratio.
 //
-// Precision as in f9_umma.cu: x' = 128 x = x0 + x1/2048, w = w0 + w1/2048 (fp16 parts), D1 += w1 x0 + w0 x1, and D0 += w0 x0
-// split over two accumulators -- here by magnitude: the K steps that hold the main lobe of some lane's filter (|w| up to 1) go to
-// D0A, the sinc tails (|w| < 0.05) to D0B.  The tensor core truncates the fp32 accumulator after every MMA by an ulp of its
-// magnitude, so the error comes from the 2-5 centre steps only (measured: inside the 2^-20 tolerance for 1:2 .. 1:16, where the
-// polyphase kernel sits on it).  out = (D0A + D0B + D1/2048) / 128.  |x| >= 256, Inf or NaN raise the flag and
-// hankel_redo_kernel recomputes the launch in fp32.
+// Precision as in f9_umma.cu: x' = 128 x = x0 + x1/2048, w = w0 + w1/2048 (fp16 parts); two accumulators per output, D0 += w0 x0
+// and D1 += w1 x0 + w0 x1 (units of 1/2048), out = (D0 + D1/2048) / 128.  The tensor core truncates the fp32 accumulator after every
+// MMA by an ulp of its magnitude, so the K steps are issued *tails first* (|w| < 0.11, the accumulator is still small) and the 2-5
+// steps that hold the main lobe of some lane's filter (|w| up to 1) last: only those truncate at full scale (measured: inside the
+// 2^-20 tolerance for 1:2 .. 1:16 with margin; window order gave 1.06 x 2^-20, and the polyphase kernel sits on the tolerance at
+// upsampling ratios).  |x| >= 256, Inf or NaN raise the flag and hankel_redo_kernel recomputes the launch in fp32.
 //
 // Roles (448 threads, one persistent CTA per SM; tile = 64 columns = 8192 outputs):
 //   setup        the weights (M-side operand, constant) go into TMEM once: 8 columns per K step and part (tcgen05.st), so the
 //                MMAs run in TS mode and shared memory holds nothing but the input ring
-//   warps 5-12   converters: the loads of tile i+1 (128-bit, coalesced, zeros outside the segment's window) are in flight while
-//                tile i is split into fp16 head / tail and stored (16 bytes each) into the swizzled buffers of a 4-stage ring
-//   warps 4, 13  issue 3 * K/16 MMAs (M = 128, N = 32) per tile each: warp 4 for columns 0-31 into accumulator set 0, warp 13
-//                for columns 32-63 into set 1; the epilogue of one half overlaps the MMAs of the other
+//   warps 5-12   converters: thread-private cp.async copies of the tile's input span into a raw fp32 ring three tiles ahead (zeros
+//                outside the segment's window), then fp16 head / tail split and 16-byte stores into the swizzled buffers of a
+//                4-stage operand ring
+//   warps 4, 13  issue 3 * K/16 MMAs (M = 128, N = 32) per tile each: warp 4 for columns 0-31, warp 13 for columns 32-63, each into
+//                its own accumulator sets -- two per half when the weights leave room (K <= 256: 1:4, 1:8, 1:16), so that the
+//                epilogue of tile i overlaps the MMAs of tile i+1; one per half at 1:2
 //   warps 0-3    epilogue: tcgen05.ld (thread = lane = output offset), combine, st.global (128 contiguous bytes per warp and column)
 // Measured (B200, 512 channels of 10 s): 48 -> 192 k 1.14 ms = 65.6 % of the HBM roofline (polyphase kernel: 1.93 ms, 38.9 %),
 // 48 -> 96 k 70.2 % (48.4 %); with the MMAs switched off the load / convert / store path alone runs at 78 %, the MMAs alone at 94 %.
@@ -42,11 +44,20 @@ namespace f9 {
 namespace {
 
 constexpr int kHkCols = 64;                 // columns (of 128 outputs) per tile = MMA N
-constexpr int kHkStages = 4;                // input ring
+constexpr int kHkStages = 4;                // converted-input ring (operand buffers)
+constexpr int kHkRaw = 4;                   // raw fp32 ring: cp.async prefetch distance of the converters, in tiles
 constexpr int kHkThreads = 14 * 32;         // warps 0-3 epilogue, 4 and 13 MMA issue (one half of the tile's columns each), 5-12 converters
 constexpr int kHkHalf = kHkCols / 2;        // columns per MMA (N) and accumulator set
-constexpr int kHkATail = 136;               // TMEM columns: weight heads at 0, tails at 136 (8 per K step, K <= 272)
-constexpr int kHkD = 272;                   // accumulator sets at 272 + 96 h: D0A, D0B, D1 of kHkHalf columns each
+// TMEM columns: weight heads at 0, tails at 8 KS (8 columns per K step and image); accumulator sets (D0, D1 of kHkHalf columns
+// each) from column 256 (KS <= 16: two sets per column half, the epilogue of one tile overlaps the MMAs of the next) or 272
+// (KS = 17, 1:2: one set per half).
+template <int KS> struct HkTmem {
+    static constexpr int aTail = 8 * KS;
+    static constexpr int nBuf = 16 * KS <= 256 ? 2 : 1;
+    static constexpr int dBase = 16 * KS <= 256 ? 256 : 272;
+    static_assert(dBase + 2 * nBuf * 2 * kHkHalf <= 512 && 16 * KS <= dBase, "TMEM layout");
+    static __device__ __forceinline__ int set(int h, int b) { return dBase + 2 * kHkHalf * (h * nBuf + b); }
+};
 constexpr int kHkConvWarps = 8, kHkFirstConv = 5;
 constexpr float kHkPre = 128.0f;            // 2^7 pre-scale, as f9_umma.cu
 constexpr uint32_t kHkPark = 2000;
@@ -118,8 +129,8 @@ __device__ __forceinline__ int find_seg(const int* __restrict__ prefix, int n, i
 template <typename T> __device__ __forceinline__ T* ldg_ptr(T* const* p) {
     return reinterpret_cast<T*>(__ldg(reinterpret_cast<const unsigned long long*>(p)));
 }
-__device__ __forceinline__ float combine(uint32_t d0a, uint32_t d0b, uint32_t d1) {
-    return fmaf(__uint_as_float(d1), 1.0f / (2048.0f * kHkPre), (__uint_as_float(d0a) + __uint_as_float(d0b)) * (1.0f / kHkPre));
+__device__ __forceinline__ float combine(uint32_t d0, uint32_t d1) {                  // (D0 + D1 / 2048) / 128: one rounding
+    return fmaf(__uint_as_float(d1), 1.0f / (2048.0f * kHkPre), __uint_as_float(d0) * (1.0f / kHkPre));
 }
 
 // One thread per tile.  Columns are absolute: column c holds outputs 128c .. 128c+127 of the channel, so a segment that starts
@@ -139,22 +150,25 @@ hankel_tile_table_kernel(const Seg* __restrict__ segs, const int* __restrict__ t
     recs[t] = Rr;
 }
 
-template <int KS>
+template <int KS, int CLO, int CHI>
 __global__ void __launch_bounds__(kHkThreads, 1)
 hankel_fir_kernel(const HankelTileRec* __restrict__ recs, int nTiles, const __grid_constant__ HankelDev P, unsigned* __restrict__ ovf, int dbg) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* ring = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // the swizzle patterns repeat on 1024 bytes
     const uint32_t bufBytes = (uint32_t) P.bufBytes;                // kHkStages x (head buffer, tail buffer), 1024-aligned
-    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + kHkStages * 2 * bufBytes);
-    uint64_t *bFull = bars, *bEmpty = bars + kHkStages, *accFull = bars + 2 * kHkStages, *accEmpty = accFull + 2;
-    uint32_t* tmemSlot = reinterpret_cast<uint32_t*>(accEmpty + 2);
+    const uint32_t rawBytes = ((uint32_t) P.elems * 4u + 127u) & ~127u;
+    uint8_t* raw = ring + kHkStages * 2 * bufBytes;                 // kHkRaw x rawBytes: the tiles' input spans as they come from HBM
+    uint64_t* bars = reinterpret_cast<uint64_t*>(raw + kHkRaw * rawBytes);
+    uint64_t *bFull = bars, *bEmpty = bars + kHkStages, *accFull = bars + 2 * kHkStages, *accEmpty = accFull + 4;     // [half][buffer]
+    uint32_t* tmemSlot = reinterpret_cast<uint32_t*>(accEmpty + 4);
+    using TM = HkTmem<KS>;
     const int warp = __shfl_sync(0xffffffffu, (int) (threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int myTiles = (int) blockIdx.x < nTiles ? (nTiles - 1 - (int) blockIdx.x) / (int) gridDim.x + 1 : 0;
 
     // ---- one-time setup: barriers, TMEM, the weights into TMEM (the M-side operand of every MMA: lane = output offset)
     if (threadIdx.x == 0) {
         for (int s = 0; s < kHkStages; ++s) { mbar_init(bFull + s, kHkConvWarps); mbar_init(bEmpty + s, 2); }
-        for (int a = 0; a < 2; ++a) { mbar_init(accFull + a, 1); mbar_init(accEmpty + a, 4); }
+        for (int a = 0; a < 4; ++a) { mbar_init(accFull + a, 1); mbar_init(accEmpty + a, 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 4) {
@@ -175,7 +189,7 @@ hankel_fir_kernel(const HankelTileRec* __restrict__ recs, int nTiles, const __gr
             for (int s = 0; s < KS; ++s) {
                 const uint4 a = __ldg(row + 2 * s), b = __ldg(row + 2 * s + 1);
                 asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
-                             :: "r"(tmem + laneBase + (uint32_t) (part * kHkATail + 8 * s)), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
+                             :: "r"(tmem + laneBase + (uint32_t) (part * TM::aTail + 8 * s)), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
             }
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -186,58 +200,70 @@ hankel_fir_kernel(const HankelTileRec* __restrict__ recs, int nTiles, const __gr
 
     if (warp >= kHkFirstConv && warp < kHkFirstConv + kHkConvWarps) {
         // =========================================================== converters
-        // The loads of tile i + 1 are issued (into registers) before tile i is converted, so their latency overlaps the
-        // conversion, the stores and the wait for the ring; every sample is loaded exactly once.
+        // Every sample is loaded exactly once: thread c owns the groups c, c + 256, ... (8 samples = 32 bytes) of every tile, copies
+        // them with cp.async into its private places of a raw fp32 ring kHkRaw - 1 tiles ahead of the conversion (HBM latency under
+        // load is longer than a tile), then splits them into fp16 head / tail and stores 16 bytes each into the swizzled operand
+        // buffers.  16-byte copies when the span is aligned and inside the segment's window, 4-byte copies with zero fill otherwise.
         const int ctid = (warp - kHkFirstConv) * 32 + lane;
-        const int groups = P.elems >> 3;                             // 8 samples = 16 bytes of fp16 per group
+        const int groups = P.elems >> 3;
         constexpr int kG = 3;                                        // groups per thread and tile (elems <= 3 * 256 * 8)
         const uint32_t swzMask = P.rowBytes == 128 ? 7u : P.rowBytes == 64 ? 3u : P.rowBytes == 32 ? 1u : 0u;
+        const uint32_t raw0 = smem_u32(raw);
         __half2 hmax = __floats2half2_rn(0.f, 0.f);
-        const HankelTileRec* rec = recs + blockIdx.x;
         struct TileIn { const float* in; long long x0, inAvail; };
-        auto load_rec = [&](const HankelTileRec* r) { TileIn T; T.in = ldg_ptr(&r->in); T.x0 = __ldg(&r->x0); T.inAvail = __ldg(&r->inAvail); return T; };
-        auto load_tile = [&](const TileIn& T, float (&v)[kG][8]) {
-            const bool vec = (((long long) (reinterpret_cast<uintptr_t>(T.in) >> 2) + T.x0) & 3) == 0;
-            #pragma unroll
-            for (int u = 0; u < kG; ++u) {
-                const int g = ctid + u * kHkConvWarps * 32;
-                if (g < groups) {
-                    const long long l = T.x0 + 8LL * g;
-                    if (vec && l >= 0 && l + 7 < T.inAvail) {
-                        const float4 a = __ldg(reinterpret_cast<const float4*>(T.in + l)), b = __ldg(reinterpret_cast<const float4*>(T.in + l + 4));
-                        v[u][0] = a.x; v[u][1] = a.y; v[u][2] = a.z; v[u][3] = a.w; v[u][4] = b.x; v[u][5] = b.y; v[u][6] = b.z; v[u][7] = b.w;
-                    } else {
-                        #pragma unroll
-                        for (int e = 0; e < 8; ++e) v[u][e] = (l + e >= 0 && l + e < T.inAvail) ? __ldg(T.in + l + e) : 0.f;
+        auto load_rec = [&](int j) {
+            TileIn T = {nullptr, 0, 0};
+            if (j < myTiles) { const HankelTileRec* r = recs + blockIdx.x + (size_t) j * gridDim.x; T.in = ldg_ptr(&r->in); T.x0 = __ldg(&r->x0); T.inAvail = __ldg(&r->inAvail); }
+            return T;
+        };
+        auto issue = [&](int j, const TileIn& T) {
+            if (j < myTiles && !(dbg & 2)) {
+                const bool vec = (((long long) (reinterpret_cast<uintptr_t>(T.in) >> 2) + T.x0) & 3) == 0;
+                const uint32_t slot = raw0 + (uint32_t) (j % kHkRaw) * rawBytes;
+                #pragma unroll
+                for (int u = 0; u < kG; ++u) {
+                    const int g = ctid + u * kHkConvWarps * 32;
+                    if (g < groups) {
+                        const long long l = T.x0 + 8LL * g;
+                        const uint32_t dst = slot + 32u * (uint32_t) g;
+                        if (vec && l >= 0 && l + 7 < T.inAvail) {
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(T.in + l) : "memory");
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst + 16u), "l"(T.in + l + 4) : "memory");
+                        } else {
+                            #pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                const bool ok = l + e >= 0 && l + e < T.inAvail;
+                                asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" :: "r"(dst + 4u * e), "l"(ok ? T.in + l + e : T.in), "r"(ok ? 4 : 0) : "memory");
+                            }
+                        }
                     }
                 }
             }
+            asm volatile("cp.async.commit_group;" ::: "memory");            // one group per tile, empty or not: uniform counting
         };
-        float nxt[kG][8], cur[kG][8];
-        TileIn T1 = {nullptr, 0, 0}, T2 = T1;
-        if (myTiles > 0) { T1 = load_rec(rec); if (!(dbg & 2)) load_tile(T1, nxt); }
-        if (myTiles > 1) T2 = load_rec(rec + gridDim.x);
-        for (int i = 0; i < myTiles; ++i, rec += gridDim.x) {
-            #pragma unroll
-            for (int u = 0; u < kG; ++u)
-                #pragma unroll
-                for (int e = 0; e < 8; ++e) cur[u][e] = nxt[u][e];
-            if (i + 1 < myTiles) {
-                T1 = T2;
-                if (!(dbg & 2)) load_tile(T1, nxt);
-                if (i + 2 < myTiles) T2 = load_rec(rec + 2 * (size_t) gridDim.x);
-            }
+        #pragma unroll
+        for (int j = 0; j < kHkRaw - 1; ++j) issue(j, load_rec(j));
+        TileIn Tn = load_rec(kHkRaw - 1);
+        for (int i = 0; i < myTiles; ++i) {
+            const TileIn Tc = Tn;
+            Tn = load_rec(i + kHkRaw);                                       // consumed one iteration later
+            issue(i + kHkRaw - 1, Tc);
+            asm volatile("cp.async.wait_group %0;" :: "n"(kHkRaw - 1) : "memory");     // this thread's copies of tile i have landed
             const int st = i % kHkStages;
             if (i >= kHkStages) mbar_wait(bEmpty + st, (uint32_t) ((i / kHkStages - 1) & 1));       // the MMAs that read this stage are done
             const uint32_t hb = smem_u32(ring + (size_t) st * 2 * bufBytes), tb = hb + bufBytes;
+            const uint32_t slot = raw0 + (uint32_t) (i % kHkRaw) * rawBytes;
             #pragma unroll
             for (int u = 0; u < kG; ++u) {
                 const int g = ctid + u * kHkConvWarps * 32;
                 if (g < groups && !(dbg & 2)) {
+                    float v[8];
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(slot + 32u * (uint32_t) g) : "memory");
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "r"(slot + 32u * (uint32_t) g + 16u) : "memory");
                     uint32_t hd[4], tl[4];
                     #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        const float x0 = cur[u][2 * e] * kHkPre, x1 = cur[u][2 * e + 1] * kHkPre;
+                        const float x0 = v[2 * e] * kHkPre, x1 = v[2 * e + 1] * kHkPre;
                         const __half2 h = __floats2half2_rn(x0, x1);
                         hmax = __hmax2_nan(hmax, __habs2(h));
                         const float2 hf = __half22float2(h);
@@ -254,40 +280,47 @@ hankel_fir_kernel(const HankelTileRec* __restrict__ recs, int nTiles, const __gr
             __syncwarp();
             if (lane == 0) mbar_arrive(bFull + st);
         }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         const float2 hm = __half22float2(hmax);
         if (!(hm.x < 32768.0f) || !(hm.y < 32768.0f)) atomicOr(ovf, 1u);
     } else if (warp == 4 || warp == 13) {
         // =========================================================== MMA issue (TS mode: weights from TMEM, input from shared memory)
         // Warp 4 owns columns 0-31 of every tile and accumulator set 0, warp 13 columns 32-63 and set 1: 3 * KS MMAs of N = 32 each.
-        // x0*w0 of the K steps that hold the filters' main lobe (|w| up to 1: steps cLo..cHi) accumulate in D0A, the sinc tails
-        // (|w| < 0.05) in D0B: the tensor core truncates the accumulator after every MMA, by an ulp of its magnitude, so the
-        // error comes from the few centre steps only; D0B stays small and its truncations are negligible.
+        // Two accumulators per output: D0 += w0 x0, D1 += w1 x0 + w0 x1 (units of 1/2048).  The tensor core truncates the fp32
+        // accumulator after every MMA by an ulp of its magnitude, so the K steps are issued tails first (|w| < 0.11: the accumulator is
+        // still small) and the steps cLo..cHi that hold the main lobe of some lane's filter (|w| up to 1) last: only those 2-5 MMAs
+        // truncate at full scale.  (Window order measured 1.06 x 2^-20 on noise at amplitude 0.5; this order passes with margin.)
         const int h = warp == 4 ? 0 : 1;
         const uint32_t el = elect_one();
         const uint32_t idesc = make_idesc(128, kHkHalf);
         const uint32_t sbo = 8u * (uint32_t) P.rowBytes, lay = (uint32_t) P.layout;
-        const uint32_t d0a = tmem + (uint32_t) (kHkD + 96 * h), d0b = d0a + kHkHalf, d1 = d0a + 2 * kHkHalf;
-        const int cLo = P.cLo, cHi = P.cHi;
+        constexpr int cLo = CLO, cHi = CHI;                          // compile-time: the issue loop is straight-line code
         for (int i = 0; i < myTiles; ++i) {
             const int st = i % kHkStages;
-            if (i >= 1) mbar_wait(accEmpty + h, (uint32_t) ((i - 1) & 1));                         // the epilogue has drained this accumulator set
+            const int b = TM::nBuf == 2 ? (i & 1) : 0, u = TM::nBuf == 2 ? (i >> 1) : i;             // accumulator set of this tile, its use count
+            if (u >= 1) mbar_wait(accEmpty + 2 * h + b, (uint32_t) ((u - 1) & 1));                     // the epilogue has drained this set
             mbar_wait(bFull + st, (uint32_t) ((i / kHkStages) & 1));
             tc_fence_after();
             if (el) {
                 const uint32_t hb = smem_u32(ring + (size_t) st * 2 * bufBytes) + (uint32_t) (h * kHkHalf * P.rowBytes), tb = hb + bufBytes;
                 const uint64_t bH0 = make_desc(hb, 16, sbo, lay), bT0 = make_desc(tb, 16, sbo, lay);
+                const uint32_t d0 = tmem + (uint32_t) TM::set(h, b), d1 = d0 + kHkHalf;
                 if (!(dbg & 1)) {
                     #pragma unroll
-                    for (int s = 0; s < KS; ++s) {
-                        const uint64_t bH = bH0 + (uint64_t) (2 * s), bT = bT0 + (uint64_t) (2 * s);         // + 32 bytes per K step: the Hankel shift
-                        const bool centre = s >= cLo && s <= cHi;
-                        umma_ts(centre ? d0a : d0b, tmem + (uint32_t) (8 * s), bH, idesc, (s == cLo || s == (cLo == 0 ? cHi + 1 : 0)) ? 0u : 1u);   // w0 x0
-                        umma_ts(d1, tmem + (uint32_t) (kHkATail + 8 * s), bH, idesc, s != 0 ? 1u : 0u);     // w1 x0
-                        umma_ts(d1, tmem + (uint32_t) (8 * s), bT, idesc, 1u);                                // w0 x1
+                    for (int pass = 0; pass < 2; ++pass) {
+                        #pragma unroll
+                        for (int s = 0; s < KS; ++s) {
+                            if ((s >= cLo && s <= cHi) != (pass == 1)) continue;
+                            const uint64_t bH = bH0 + (uint64_t) (2 * s), bT = bT0 + (uint64_t) (2 * s);     // + 32 bytes per K step: the Hankel shift
+                            const uint32_t first = (pass == 0 && s == 0) ? 0u : 1u;                          // step 0 is a tail step (cLo >= 1)
+                            umma_ts(d0, tmem + (uint32_t) (8 * s), bH, idesc, first);                        // w0 x0
+                            umma_ts(d1, tmem + (uint32_t) (TM::aTail + 8 * s), bH, idesc, first);            // w1 x0
+                            umma_ts(d1, tmem + (uint32_t) (8 * s), bT, idesc, 1u);                           // w0 x1
+                        }
                     }
                 }
                 umma_commit(bEmpty + st);                            // the stage may be refilled once both halves' MMAs have read it
-                umma_commit(accFull + h);
+                umma_commit(accFull + 2 * h + b);
             }
             __syncwarp();
         }
@@ -305,37 +338,37 @@ hankel_fir_kernel(const HankelTileRec* __restrict__ recs, int nTiles, const __gr
             if (i + 1 < myTiles) N = load_rec(rec + gridDim.x);
             const bool inside = T.oBase >= 0 && T.oBase + 128LL * kHkCols <= T.numOut;
             float* outG = reinterpret_cast<float*>(__cvta_generic_to_global(T.out));
+            const int b = TM::nBuf == 2 ? (i & 1) : 0, u = TM::nBuf == 2 ? (i >> 1) : i;
             #pragma unroll 1
             for (int h = 0; h < 2; ++h) {
-                mbar_wait(accFull + h, (uint32_t) (i & 1));
+                mbar_wait(accFull + 2 * h + b, (uint32_t) (u & 1));
                 tc_fence_after();
                 #pragma unroll 1
                 for (int c = 0; c < kHkHalf / 16; ++c) {
-                    uint32_t va[16], vb[16], v1[16];
-                    const uint32_t c0 = tmem + laneBase + (uint32_t) (kHkD + 96 * h + c * 16);
+                    uint32_t v0[16], v1[16];
+                    const uint32_t c0 = tmem + laneBase + (uint32_t) (TM::set(h, b) + c * 16);
                     #define LD16(arr, addr) asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];" \
                         : "=r"(arr[0]), "=r"(arr[1]), "=r"(arr[2]), "=r"(arr[3]), "=r"(arr[4]), "=r"(arr[5]), "=r"(arr[6]), "=r"(arr[7]), \
                           "=r"(arr[8]), "=r"(arr[9]), "=r"(arr[10]), "=r"(arr[11]), "=r"(arr[12]), "=r"(arr[13]), "=r"(arr[14]), "=r"(arr[15]) : "r"(addr))
-                    LD16(va, c0);
-                    LD16(vb, c0 + (uint32_t) kHkHalf);
-                    LD16(v1, c0 + (uint32_t) (2 * kHkHalf));
+                    LD16(v0, c0);
+                    LD16(v1, c0 + (uint32_t) kHkHalf);
                     #undef LD16
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                     if (c == kHkHalf / 16 - 1) {                     // everything has been read: the set may be overwritten
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(accEmpty + h);
+                        if (lane == 0) mbar_arrive(accEmpty + 2 * h + b);
                     }
                     const long long o0 = T.oBase + 128LL * (h * kHkHalf + c * 16) + l;
                     if (dbg & 4) {} else if (inside) {
+                        float* __restrict__ dst = outG + o0;
                         #pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            asm volatile("st.global.cs.f32 [%0], %1;" :: "l"(outG + o0 + 128 * j), "f"(combine(va[j], vb[j], v1[j])));
+                        for (int j = 0; j < 16; ++j) __stcs(dst + 128 * j, combine(v0[j], v1[j]));
                     } else {
                         #pragma unroll
                         for (int j = 0; j < 16; ++j) {
                             const long long o = o0 + 128 * j;
-                            if (o >= 0 && o < T.numOut) outG[o] = combine(va[j], vb[j], v1[j]);
+                            if (o >= 0 && o < T.numOut) outG[o] = combine(v0[j], v1[j]);
                         }
                     }
                 }
@@ -374,7 +407,7 @@ hankel_redo_kernel(const HankelTileRec* __restrict__ recs, int nTiles, int L, Po
 }  // namespace
 
 size_t hankel_smem_bytes(const HankelDev& P) {
-    return 1024 + (size_t) kHkStages * 2 * P.bufBytes + 256;
+    return 1024 + (size_t) kHkStages * 2 * P.bufBytes + (size_t) kHkRaw * (((size_t) P.elems * 4 + 127) & ~(size_t) 127) + 256;
 }
 long long hankel_tiles_for_segment(long long n0, long long numOut) {
     if (numOut <= 0) return 0;
@@ -393,13 +426,15 @@ cudaError_t launch_hankel(const ResampleLaunch& L, cudaStream_t s, long long* la
     ++*launches;
     const int grid = std::min(L.n_tiles, L.sm_count);
     const int dbg = getenv("F9_HK_DBG") ? atoi(getenv("F9_HK_DBG")) : 0;      // development: 1 skip MMAs, 2 skip loads + conversion, 4 skip stores
-    #define F9_HK_LAUNCH(KS) do { \
-        if ((e = cudaFuncSetAttribute(hankel_fir_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)) != cudaSuccess) return e; \
-        hankel_fir_kernel<KS><<<grid, kHkThreads, smem, s>>>(recs, L.n_tiles, L.hk, L.d_ovf, dbg); } while (0)
-    switch (L.hk.KS) {
-        case 14: F9_HK_LAUNCH(14); break;
-        case 15: F9_HK_LAUNCH(15); break;
-        case 17: F9_HK_LAUNCH(17); break;
+    #define F9_HK_LAUNCH(ks_, lo_, hi_) do { \
+        if (L.hk.KS != ks_ || L.hk.cLo != lo_ || L.hk.cHi != hi_) return cudaErrorInvalidValue; \
+        if ((e = cudaFuncSetAttribute(hankel_fir_kernel<ks_, lo_, hi_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)) != cudaSuccess) return e; \
+        hankel_fir_kernel<ks_, lo_, hi_><<<grid, kHkThreads, smem, s>>>(recs, L.n_tiles, L.hk, L.d_ovf, dbg); } while (0)
+    switch (L.hk.L) {                                   // (K steps, first / last main-lobe step) of the 200-tap kinds
+        case 2:  F9_HK_LAUNCH(17, 6, 10); break;
+        case 4:  F9_HK_LAUNCH(15, 6, 8); break;
+        case 8:  F9_HK_LAUNCH(14, 6, 7); break;
+        case 16: F9_HK_LAUNCH(14, 6, 7); break;
         default: return cudaErrorInvalidValue;
     }
     #undef F9_HK_LAUNCH
