@@ -129,7 +129,9 @@ def main():
         ctx._check(L.f9_resample_plan_create(ctx.handle, kind, fs_in / fs_out, segs, nch, C.byref(plan)))
         ms = timed(lambda: ctx._check(L.f9_resample_plan_run(plan)), reps=5, do_flush=nch * n_in * 4 < (256 << 20))
         L.f9_plan_destroy(plan)
-        report(("umma_fir_kernel WindowedSinc " if kind == 0 else "short_kernel / umma_fir_kernel Lagrange ") + "%d -> %d" % (fs_in, fs_out), label, ms,
+        name = ("hankel_fir_kernel WindowedSinc " if fs_out % fs_in == 0 and fs_out > fs_in else "umma_fir_kernel WindowedSinc ") if kind == 0 else \
+               ("umma_fir_kernel Lagrange " if fs_in % fs_out == 0 and fs_in > fs_out else "short_kernel Lagrange ")
+        report(name + "%d -> %d" % (fs_in, fs_out), label, ms,
                4.0 * nch * (n_in + no), nch * no, "samples")
         return x, y, no
     for kind in (0, 1):
@@ -138,6 +140,7 @@ def main():
         plan_time(kind, 44100, 48000, 2, 60 * 44100, "config1: one 60 s stereo file (launch-latency bound)")
     for kind in (0, 1):
         plan_time(kind, 48000, 192000, 64, 120 * 48000, "config3 shape: 64 channels, 2 of the 10 minutes")
+    plan_time(0, 48000, 96000, 512, 10 * 48000, "1:2 upsampling, 256 stereo files of 10 s")
     for fs_in, fs_out in ((96000, 44100), (48000, 192000)):
         nch, n_in = 512, 10 * fs_in
         ratio = fs_in / fs_out
