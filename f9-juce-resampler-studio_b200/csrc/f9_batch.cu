@@ -57,9 +57,10 @@ int run_chunk(f9_context* ctx, const f9_job* jobs, f9_result* results, const std
         d_bytes += plans[(size_t) t].bytes;
         if (jobs[idx[(size_t) t]].flags & F9_JOB_TAIL_SCAN) { ++nTail; maxPolls = std::max(maxPolls, plans[(size_t) t].polls); }
     }
-    size_t totalCh = 0;
-    for (int t = 0; t < n; ++t) totalCh += (size_t) jobs[idx[(size_t) t]].numCh;
+    size_t totalCh = 0, widest = 0;
+    for (int t = 0; t < n; ++t) { totalCh += (size_t) jobs[idx[(size_t) t]].numCh; widest = std::max(widest, (size_t) jobs[idx[(size_t) t]].numCh); }
     d_bytes += (size_t) nTail * ((size_t) maxPolls * sizeof(int) + 64) + (size_t) n * 2048 + totalCh * 256;
+    d_bytes += (size_t) n * widest * sizeof(double) * kDcPartials;       // DC partial sums: files x widest channel count
     d_bytes += totalCh * 1024 + d_bytes / 64;                  // per-tile records of the tensor-core resampler (64 B per >= 24 KB of output)
     h_bytes += (size_t) n * 2048 + (size_t) nTail * 16 + totalCh * 256;
     int rc = ctx->arena_reserve(d_bytes, h_bytes); if (rc) return rc;
@@ -144,18 +145,18 @@ int run_chunk(f9_context* ctx, const f9_job* jobs, f9_result* results, const std
             F9_TRY_CUDA(ctx, cudaMemcpyAsync(d_c, h_c, sizeof(DevBuf) * m, cudaMemcpyHostToDevice, s));
             F9_TRY_CUDA(ctx, cudaMemcpyAsync(d_o, h_o, sizeof(DevBuf) * m, cudaMemcpyHostToDevice, s));
             F9_TRY_CUDA(ctx, cudaMemcpyAsync(d_l, h_l, sizeof(int) * m, cudaMemcpyHostToDevice, s));
-            F9_TRY_CUDA(ctx, launch_trim(d_c, d_l, d_o, (int) m, maxFrames, maxCh, s, &ctx->launches));
-            // DC removal on the subset that asked for it (contiguous copy of their descriptors)
-            std::vector<DevBuf> dcb;
-            for (size_t i = 0; i < m; ++i) if (dcMask[i]) dcb.push_back(to[i]);
-            if (!dcb.empty()) {
-                DevBuf* d_d = (DevBuf*) ctx->d_alloc(sizeof(DevBuf) * dcb.size());
-                DevBuf* h_d = (DevBuf*) ctx->h_alloc(sizeof(DevBuf) * dcb.size());
-                std::memcpy(h_d, dcb.data(), sizeof(DevBuf) * dcb.size());
-                F9_TRY_CUDA(ctx, cudaMemcpyAsync(d_d, h_d, sizeof(DevBuf) * dcb.size(), cudaMemcpyHostToDevice, s));
-                double* d_sums = (double*) ctx->d_alloc(sizeof(double) * dcb.size() * (size_t) maxCh);
-                F9_TRY_CUDA(ctx, launch_remove_dc(d_d, (int) dcb.size(), maxCh, maxFrames, d_sums, s, &ctx->launches));
+            // removeDCOffset is fused into the trim for the files that asked for it (mask), so their trimmed buffer is written once
+            bool anyDc = false;
+            for (size_t i = 0; i < m; ++i) anyDc = anyDc || dcMask[i] != 0;
+            double* d_part = nullptr; int* d_mask = nullptr;
+            if (anyDc) {
+                d_part = (double*) ctx->d_alloc(sizeof(double) * m * (size_t) maxCh * kDcPartials);
+                d_mask = (int*) ctx->d_alloc(sizeof(int) * m);
+                int* h_mask = (int*) ctx->h_alloc(sizeof(int) * m);
+                std::memcpy(h_mask, dcMask.data(), sizeof(int) * m);
+                F9_TRY_CUDA(ctx, cudaMemcpyAsync(d_mask, h_mask, sizeof(int) * m, cudaMemcpyHostToDevice, s));
             }
+            F9_TRY_CUDA(ctx, launch_trim(d_c, d_l, d_o, (int) m, maxFrames, maxCh, s, &ctx->launches, d_part, d_mask));
         }
     }
 

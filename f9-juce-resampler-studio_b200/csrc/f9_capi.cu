@@ -419,12 +419,12 @@ int f9_trim_latency_swift(f9_context* ctx, const float* captured, long long coun
 int f9_remove_dc_offset(f9_context* ctx, float* const* ch, int numCh, int numFrames) {
     int rc = check_planar(ctx, ch, numCh, numFrames); if (rc) return rc;
     if (numCh == 0 || numFrames == 0) return F9_OK;
-    rc = ctx->arena_reserve(planar_bytes(numCh, numFrames) + sizeof(double) * (size_t) numCh + 16384, 4096); if (rc) return rc;
+    rc = ctx->arena_reserve(planar_bytes(numCh, numFrames) + sizeof(double) * (size_t) numCh * kDcPartials + 16384, 4096); if (rc) return rc;
     DevBuf hb{};
     rc = upload_planar(ctx, ch, numCh, numFrames, &hb); if (rc) return rc;
     DevBuf* d_b;
     rc = upload_array(ctx, &hb, 1, &d_b); if (rc) return rc;
-    double* d_sums = (double*) ctx->d_alloc(sizeof(double) * (size_t) numCh);
+    double* d_sums = (double*) ctx->d_alloc(sizeof(double) * (size_t) numCh * kDcPartials);
     F9_TRY_CUDA(ctx, launch_remove_dc(d_b, 1, numCh, numFrames, d_sums, ctx->stream, &ctx->launches));
     for (int c = 0; c < numCh; ++c)
         F9_TRY_CUDA(ctx, cudaMemcpyAsync(ch[c], hb.base + c * hb.chStride, sizeof(float) * (size_t) numFrames, cudaMemcpyDeviceToHost, ctx->stream));
@@ -707,17 +707,14 @@ int f9_dev_trim_batch(f9_context* ctx, const f9_dev_buffer* captured, const int*
         if (hc[i].numCh <= 0 || ho[i].numCh != hc[i].numCh) return ctx->fail(F9_ERR_INVALID, "trim: channel counts differ");
         maxCh = std::max(maxCh, ho[i].numCh); maxFrames = std::max(maxFrames, ho[i].numFrames);
     }
-    const size_t bytes = (2 * sizeof(DevBuf) + sizeof(int)) * (size_t) n + sizeof(double) * (size_t) n * maxCh + 16384;
+    const size_t bytes = (2 * sizeof(DevBuf) + sizeof(int)) * (size_t) n + sizeof(double) * (size_t) n * maxCh * kDcPartials + 16384;
     int rc = ctx->arena_reserve(bytes, bytes, true); if (rc) return rc;
     DevBuf *d_c, *d_o; int* d_lat;
     rc = upload_array(ctx, hc, (size_t) n, &d_c); if (rc) return rc;
     rc = upload_array(ctx, ho, (size_t) n, &d_o); if (rc) return rc;
     rc = upload_array(ctx, latency_samples, (size_t) n, &d_lat); if (rc) return rc;
-    F9_TRY_CUDA(ctx, launch_trim(d_c, d_lat, d_o, n, maxFrames, maxCh, ctx->stream, &ctx->launches));
-    if (remove_dc) {
-        double* d_sums = (double*) ctx->d_alloc(sizeof(double) * (size_t) n * maxCh);
-        F9_TRY_CUDA(ctx, launch_remove_dc(d_o, n, maxCh, maxFrames, d_sums, ctx->stream, &ctx->launches));
-    }
+    double* d_part = remove_dc ? (double*) ctx->d_alloc(sizeof(double) * (size_t) n * maxCh * kDcPartials) : nullptr;      // fused removeDCOffset
+    F9_TRY_CUDA(ctx, launch_trim(d_c, d_lat, d_o, n, maxFrames, maxCh, ctx->stream, &ctx->launches, d_part, nullptr));
     return F9_OK;
 }
 

@@ -7,35 +7,80 @@ namespace {
 
 constexpr int kThreads = 256;
 
-// ---- trimLatency (Source/MainComponent.cpp:824-861), batched ------------------------------------------
-// grid: (tiles over frames, channel, buffer).  out = zeros, then captured[start .. start+n) when n > 0 && start >= 0.
+// ---- trimLatency (Source/MainComponent.cpp:824-861) and removeDCOffset (:884-902), batched ---------------
+// grid: (tiles over frames, channel, buffer).  out = zeros, then captured[start .. start+n) when n > 0 && start >= 0; with SUB the
+// channel's mean is subtracted on the way (removeDCOffset runs right after trimLatency in the save path, :766-769: fused, the
+// trimmed buffer is written once instead of written, read and rewritten).  A thread moves 4 consecutive frames per step: 128-bit
+// stores when the destination is aligned, 128-bit loads when the source is too (the latency decides), scalar loads otherwise.
+struct TrimGeom { const float* src; float* dst; int n, frames; };
+__device__ __forceinline__ TrimGeom trim_geom(const DevBuf& C, const DevBuf& O, int latency, int ch) {
+    TrimGeom G;
+    const int start = latency / C.numCh;                     // truncating division (:835)
+    G.frames = O.numFrames;                                  // originalLength
+    G.n = G.frames;
+    if (start + G.n > C.numFrames) G.n = max(0, C.numFrames - start);
+    if (start < 0) G.n = 0;
+    G.src = C.base + (long long) ch * C.chStride + start;
+    G.dst = const_cast<float*>(O.base) + (long long) ch * O.chStride;
+    return G;
+}
+// Sum of a channel's partial sums in index order (deterministic); kDcPartials doubles per (buffer, channel).
+__device__ __forceinline__ double dc_total(const double* __restrict__ partials, size_t slot) {
+    double t = 0.0;
+    #pragma unroll 4
+    for (int c = 0; c < kDcPartials; ++c) t += partials[slot * kDcPartials + c];
+    return t;
+}
+template <bool SUB>
 __global__ void __launch_bounds__(kThreads)
-trim_kernel(const DevBuf* __restrict__ cap, const int* __restrict__ latency, const DevBuf* __restrict__ out) {
+trim_kernel(const DevBuf* __restrict__ cap, const int* __restrict__ latency, const DevBuf* __restrict__ out,
+            const double* __restrict__ partials, const int* __restrict__ dcMask, int maxCh) {
     const int b = blockIdx.z, ch = blockIdx.y;
     const DevBuf C = cap[b];
     const DevBuf O = out[b];
     if (ch >= O.numCh) return;
-    const int start = latency[b] / C.numCh;                  // truncating division (:835)
-    int n = O.numFrames;                                     // originalLength
-    if (start + n > C.numFrames) n = max(0, C.numFrames - start);
-    if (start < 0) n = 0;
-    const float* __restrict__ src = C.base + (long long) ch * C.chStride + start;
-    float* __restrict__ dst = const_cast<float*>(O.base) + (long long) ch * O.chStride;
-    for (int i = blockIdx.x * kThreads + threadIdx.x; i < O.numFrames; i += gridDim.x * kThreads)
-        dst[i] = (i < n) ? __ldg(src + i) : 0.0f;
+    const TrimGeom G = trim_geom(C, O, latency[b], ch);
+    float dc = 0.0f;
+    if (SUB && G.frames > 0 && (dcMask == nullptr || dcMask[b] != 0)) dc = (float) dc_total(partials, (size_t) b * maxCh + ch) / (float) G.frames;
+    const bool dstVec = (reinterpret_cast<uintptr_t>(G.dst) & 15) == 0, srcVec = (reinterpret_cast<uintptr_t>(G.src) & 15) == 0;
+    #pragma unroll 2
+    for (int i = (blockIdx.x * kThreads + threadIdx.x) * 4; i < G.frames; i += gridDim.x * kThreads * 4) {
+        float4 v;
+        if (srcVec && i + 3 < G.n) v = __ldg(reinterpret_cast<const float4*>(G.src + i));
+        else {
+            v.x = (i < G.n) ? __ldg(G.src + i) : 0.0f;         v.y = (i + 1 < G.n) ? __ldg(G.src + i + 1) : 0.0f;
+            v.z = (i + 2 < G.n) ? __ldg(G.src + i + 2) : 0.0f; v.w = (i + 3 < G.n) ? __ldg(G.src + i + 3) : 0.0f;
+        }
+        if (SUB) { v.x = __fsub_rn(v.x, dc); v.y = __fsub_rn(v.y, dc); v.z = __fsub_rn(v.z, dc); v.w = __fsub_rn(v.w, dc); }
+        if (dstVec && i + 3 < G.frames) __stcs(reinterpret_cast<float4*>(G.dst + i), v);
+        else {
+            G.dst[i] = v.x;
+            if (i + 1 < G.frames) G.dst[i + 1] = v.y;
+            if (i + 2 < G.frames) G.dst[i + 2] = v.z;
+            if (i + 3 < G.frames) G.dst[i + 3] = v.w;
+        }
+    }
 }
 
 // ---- removeDCOffset (Source/MainComponent.cpp:884-902) -------------------------------------------------
 // The reference sums sequentially in float; a parallel sum can only match to tolerance.
-// Pass 1: per (buffer, channel) sum in double, deterministic tree.  Pass 2: subtract (float)(sum) / numFrames.
-__global__ void __launch_bounds__(kThreads)
-dc_sum_kernel(const DevBuf* __restrict__ bufs, int maxCh, double* __restrict__ sums) {
-    const int b = blockIdx.y, ch = blockIdx.x;
-    const DevBuf B = bufs[b];
-    if (ch >= B.numCh) return;
-    const float* __restrict__ x = B.base + (long long) ch * B.chStride;
+// Pass 1: kDcPartials CTAs per (buffer, channel), each a deterministic tree sum in double over its slice of the frames.
+// Pass 2: fold the partials in index order, subtract (float)(sum) / numFrames.
+__device__ __forceinline__ void dc_partial(const float* __restrict__ x, int frames, double* __restrict__ dstPartial) {
+    // slice blockIdx.x of kDcPartials, boundaries on multiples of 4 frames
+    const int per = ((frames + kDcPartials - 1) / kDcPartials + 3) & ~3;
+    const int lo = min(frames, (int) blockIdx.x * per), hi = min(frames, lo + per);
     double s = 0.0;
-    for (int i = threadIdx.x; i < B.numFrames; i += kThreads) s += (double) __ldg(x + i);
+    if ((reinterpret_cast<uintptr_t>(x + lo) & 15) == 0) {
+        const int nv = (hi - lo) >> 2;
+        const float4* __restrict__ xv = reinterpret_cast<const float4*>(x + lo);
+        #pragma unroll 4
+        for (int i = threadIdx.x; i < nv; i += kThreads) { const float4 v = __ldg(xv + i); s += ((double) v.x + (double) v.y) + ((double) v.z + (double) v.w); }
+        for (int i = lo + 4 * nv + threadIdx.x; i < hi; i += kThreads) s += (double) __ldg(x + i);
+    } else {
+        #pragma unroll 4
+        for (int i = lo + threadIdx.x; i < hi; i += kThreads) s += (double) __ldg(x + i);
+    }
     #pragma unroll
     for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
     __shared__ double sh[kThreads / 32];
@@ -44,17 +89,49 @@ dc_sum_kernel(const DevBuf* __restrict__ bufs, int maxCh, double* __restrict__ s
     if (threadIdx.x == 0) {
         double t = 0.0;
         for (int w = 0; w < kThreads / 32; ++w) t += sh[w];
-        sums[(size_t) b * maxCh + ch] = t;
+        *dstPartial = t;
     }
 }
+// grid: (kDcPartials, channel, buffer)
 __global__ void __launch_bounds__(kThreads)
-dc_sub_kernel(const DevBuf* __restrict__ bufs, int maxCh, const double* __restrict__ sums) {
+dc_sum_kernel(const DevBuf* __restrict__ bufs, int maxCh, double* __restrict__ partials) {
+    const int b = blockIdx.z, ch = blockIdx.y;
+    const DevBuf B = bufs[b];
+    if (ch >= B.numCh) return;
+    dc_partial(B.base + (long long) ch * B.chStride, B.numFrames, partials + ((size_t) b * maxCh + ch) * kDcPartials + blockIdx.x);
+}
+// The same over the region trimLatency copies (the zero padding adds nothing to the sum): the mean of the trimmed buffer
+// without materialising it first.
+__global__ void __launch_bounds__(kThreads)
+dc_sum_src_kernel(const DevBuf* __restrict__ cap, const int* __restrict__ latency, const DevBuf* __restrict__ out, int maxCh,
+                  double* __restrict__ partials) {
+    const int b = blockIdx.z, ch = blockIdx.y;
+    const DevBuf C = cap[b];
+    const DevBuf O = out[b];
+    if (ch >= O.numCh) return;
+    const TrimGeom G = trim_geom(C, O, latency[b], ch);
+    dc_partial(G.src, G.n, partials + ((size_t) b * maxCh + ch) * kDcPartials + blockIdx.x);
+}
+__global__ void __launch_bounds__(kThreads)
+dc_sub_kernel(const DevBuf* __restrict__ bufs, int maxCh, const double* __restrict__ partials) {
     const int b = blockIdx.z, ch = blockIdx.y;
     const DevBuf B = bufs[b];
     if (ch >= B.numCh || B.numFrames <= 0) return;
-    const float dc = (float) sums[(size_t) b * maxCh + ch] / (float) B.numFrames;
+    const float dc = (float) dc_total(partials, (size_t) b * maxCh + ch) / (float) B.numFrames;
     float* __restrict__ x = const_cast<float*>(B.base) + (long long) ch * B.chStride;
-    for (int i = blockIdx.x * kThreads + threadIdx.x; i < B.numFrames; i += gridDim.x * kThreads) x[i] = __fsub_rn(x[i], dc);
+    if ((reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+        const int nv = B.numFrames >> 2;
+        float4* __restrict__ xv = reinterpret_cast<float4*>(x);
+        #pragma unroll 2
+        for (int i = blockIdx.x * kThreads + threadIdx.x; i < nv; i += gridDim.x * kThreads) {
+            float4 v = xv[i];
+            v.x = __fsub_rn(v.x, dc); v.y = __fsub_rn(v.y, dc); v.z = __fsub_rn(v.z, dc); v.w = __fsub_rn(v.w, dc);
+            xv[i] = v;
+        }
+        for (int i = 4 * nv + blockIdx.x * kThreads + threadIdx.x; i < B.numFrames; i += gridDim.x * kThreads) x[i] = __fsub_rn(x[i], dc);
+    } else {
+        for (int i = blockIdx.x * kThreads + threadIdx.x; i < B.numFrames; i += gridDim.x * kThreads) x[i] = __fsub_rn(x[i], dc);
+    }
 }
 
 // ---- PCM -> planar float (JUCE reader: left-justify to int32, * 1/0x7fffffff) ---------------------------
@@ -197,26 +274,34 @@ cudaError_t allow_smem(K kernel, size_t bytes) {
 }  // namespace
 
 cudaError_t launch_trim(const DevBuf* d_captured, const int* d_latency, const DevBuf* d_out, int n, int maxOutFrames,
-                        int maxCh, cudaStream_t s, long long* launches) {
+                        int maxCh, cudaStream_t s, long long* launches, double* d_dc_partials, const int* d_dc_mask) {
     if (n <= 0 || maxCh <= 0) return cudaSuccess;
-    const int tiles = std::max(1, std::min((maxOutFrames + kThreads * 8 - 1) / (kThreads * 8), 4096));
+    const int tiles = std::max(1, std::min((maxOutFrames + kThreads * 16 - 1) / (kThreads * 16), 4096));
     for (int b0 = 0; b0 < n; b0 += 65535) {
         const int nb = std::min(65535, n - b0);
         dim3 grid(tiles, maxCh, nb);
-        trim_kernel<<<grid, kThreads, 0, s>>>(d_captured + b0, d_latency + b0, d_out + b0);
+        if (d_dc_partials) {                                   // fused removeDCOffset: mean of the copied region first
+            double* part = d_dc_partials + (size_t) b0 * maxCh * kDcPartials;
+            dc_sum_src_kernel<<<dim3(kDcPartials, maxCh, nb), kThreads, 0, s>>>(d_captured + b0, d_latency + b0, d_out + b0, maxCh, part);
+            ++*launches;
+            trim_kernel<true><<<grid, kThreads, 0, s>>>(d_captured + b0, d_latency + b0, d_out + b0, part, d_dc_mask ? d_dc_mask + b0 : nullptr, maxCh);
+        } else {
+            trim_kernel<false><<<grid, kThreads, 0, s>>>(d_captured + b0, d_latency + b0, d_out + b0, nullptr, nullptr, maxCh);
+        }
         ++*launches;
     }
     return cudaGetLastError();
 }
 
-cudaError_t launch_remove_dc(const DevBuf* d_bufs, int n, int maxCh, int maxFrames, double* d_sums, cudaStream_t s, long long* launches) {
+cudaError_t launch_remove_dc(const DevBuf* d_bufs, int n, int maxCh, int maxFrames, double* d_partials, cudaStream_t s, long long* launches) {
     if (n <= 0 || maxCh <= 0) return cudaSuccess;
     for (int b0 = 0; b0 < n; b0 += 65535) {
         const int nb = std::min(65535, n - b0);
-        dc_sum_kernel<<<dim3(maxCh, nb), kThreads, 0, s>>>(d_bufs + b0, maxCh, d_sums + (size_t) b0 * maxCh);
+        double* part = d_partials + (size_t) b0 * maxCh * kDcPartials;
+        dc_sum_kernel<<<dim3(kDcPartials, maxCh, nb), kThreads, 0, s>>>(d_bufs + b0, maxCh, part);
         ++*launches;
-        const int tiles = std::max(1, std::min((maxFrames + kThreads * 8 - 1) / (kThreads * 8), 4096));
-        dc_sub_kernel<<<dim3(tiles, maxCh, nb), kThreads, 0, s>>>(d_bufs + b0, maxCh, d_sums + (size_t) b0 * maxCh);
+        const int tiles = std::max(1, std::min((maxFrames + kThreads * 16 - 1) / (kThreads * 16), 4096));
+        dc_sub_kernel<<<dim3(tiles, maxCh, nb), kThreads, 0, s>>>(d_bufs + b0, maxCh, part);
         ++*launches;
     }
     return cudaGetLastError();

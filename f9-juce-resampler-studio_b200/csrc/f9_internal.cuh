@@ -85,11 +85,12 @@ cudaError_t launch_xcorr(const DevBuf* d_bufs, int n, int total_ctas, const int*
                          int lagMin, int lagMax, XcPartial* d_partials /* total_ctas */, XcPartial* d_best /* n */,
                          cudaStream_t s, long long* launches);
 
+constexpr int kDcPartials = 32;             // partial sums per (buffer, channel) of the DC passes: d_partials holds n * maxCh * kDcPartials doubles
+// d_dc_partials != nullptr: removeDCOffset fused into the trim (buffers with d_dc_mask[i] == 0 are copied unchanged; nullptr = all)
 cudaError_t launch_trim(const DevBuf* d_captured, const int* d_latency, const DevBuf* d_out, int n, int maxOutFrames,
-                        int maxCh, cudaStream_t s, long long* launches);
-cudaError_t launch_remove_dc(const DevBuf* d_bufs /* writable */, int n, int maxCh, int maxFrames, double* d_sums /* n*maxCh */,
+                        int maxCh, cudaStream_t s, long long* launches, double* d_dc_partials = nullptr, const int* d_dc_mask = nullptr);
+cudaError_t launch_remove_dc(const DevBuf* d_bufs /* writable */, int n, int maxCh, int maxFrames, double* d_partials /* n*maxCh*kDcPartials */,
                              cudaStream_t s, long long* launches);
-
 cudaError_t launch_pcm_to_planar(const void* d_src, int fmt, int srcCh, long long frames, float* d_dst,
                                  long long dstStride, int dstCh, cudaStream_t s, long long* launches);
 cudaError_t launch_planar_to_pcm24_batch(const DevBuf* h_srcs, const DevBuf* d_srcs, unsigned char* const* d_dsts, int n,

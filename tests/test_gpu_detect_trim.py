@@ -187,6 +187,37 @@ def test_remove_dc_tolerance(ctx, O):
     assert np.max(np.abs(g - c)) <= 2.0 ** -20           # tolerance parity: float sequential mean vs parallel mean
 
 
+@pytest.mark.parametrize("remove_dc", [0, 1])
+def test_dev_trim_batch_ragged(ctx, O, f9, remove_dc):
+    """Device-resident trimLatency (+ fused removeDCOffset) over a ragged batch: latencies at every 16-byte misalignment,
+    captures shorter than the request (zero padding), latency past the end, mono / stereo / 5 channels, odd strides.  Trim is
+    a bit-exact copy; with DC removal the mean is the parallel double sum (tolerance parity, as test_remove_dc_tolerance)."""
+    torch = pytest.importorskip("torch")
+    import ctypes as C
+    cases = [(2, 50000, 2 * 1001, 40000), (2, 50000, 2 * 1002, 48999), (2, 50000, 2 * 1003, 60000), (1, 9000, 7, 9000),
+             (5, 3000, 5 * 13, 2500), (2, 4000, 2 * 5000, 1000), (2, 70001, 2 * 64, 70001), (2, 100, 0, 1)]
+    caps = [(rnd((ch, frames), 300 + i, 0.4) + np.float32(0.002 * (i + 1))).astype(np.float32) for i, (ch, frames, _, _) in enumerate(cases)]
+    d_caps = [torch.from_numpy(c).cuda() for c in caps]
+    d_outs = [torch.full((ch, orig + 3), float("nan"), dtype=torch.float32, device="cuda") for (ch, _, _, orig) in cases]
+    n = len(cases)
+    cb = (f9.DevBuffer * n)(*[f9.DevBuffer(t.data_ptr(), t.shape[1], t.shape[0], t.shape[1]) for t in d_caps])
+    ob = (f9.DevBuffer * n)(*[f9.DevBuffer(t.data_ptr(), t.shape[1], t.shape[0], orig) for t, (_, _, _, orig) in zip(d_outs, cases)])
+    lat = (C.c_int * n)(*[c[2] for c in cases])
+    torch.cuda.synchronize()
+    ctx._check(f9.lib().f9_dev_trim_batch(ctx.handle, cb, lat, ob, n, remove_dc))
+    ctx.synchronize()
+    for cap, t, (ch, frames, latency, orig) in zip(caps, d_outs, cases):
+        got = t.cpu().numpy()
+        want, _ = O.trim_latency(cap, latency, orig)
+        assert np.all(np.isnan(got[:, orig:]))                       # nothing written past the requested length
+        if remove_dc:
+            exact = want - (want.astype(np.float64).sum(axis=1, keepdims=True) / orig).astype(np.float32)      # the mean without the float accumulator's drift
+            assert np.max(np.abs(got[:, :orig] - exact)) <= 2.0 ** -23
+            assert np.max(np.abs(got[:, :orig] - O.remove_dc_offset(want))) <= 2.0 ** -20                     # the reference's sequential float sum
+        else:
+            assert np.array_equal(got[:, :orig], want)
+
+
 # ---------------------------------------------------------------- format conversion (bit exact)
 @pytest.mark.parametrize("fmt,dt", [(1, np.uint8), (2, np.int16), (3, None), (4, np.int32), (5, np.float32)])
 @pytest.mark.parametrize("src_ch,dst_ch,frames", [(1, 2, 1000), (2, 2, 4099), (6, 6, 333), (2, 1, 64)])

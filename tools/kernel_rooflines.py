@@ -92,8 +92,8 @@ def main():
     ms = timed(lambda: ctx._check(L.f9_dev_trim_batch(ctx.handle, cb, lat, ob, nf, 0)), do_flush=False)
     report("trim_kernel (trimLatency as a copy)", "config2: 256 x 2 x 960000", ms, 8.0 * nf * 2 * src, nf * 2 * src, "samples", "in the job flow the trim is a pointer offset fused into the resampler")
     ms = timed(lambda: ctx._check(L.f9_dev_trim_batch(ctx.handle, cb, lat, ob, nf, 1)), do_flush=False)
-    report("trim_kernel + dc_sum/dc_sub (removeDCOffset)", "config2: 256 x 2 x 960000", ms, (8.0 + 4.0 + 8.0) * nf * 2 * src, nf * 2 * src, "samples",
-           "float mean: one more read, then read + write")
+    report("dc_sum_src + trim_kernel<SUB> (trimLatency + removeDCOffset, fused)", "config2: 256 x 2 x 960000", ms, (4.0 + 8.0) * nf * 2 * src, nf * 2 * src, "samples",
+           "mean of the copied region (one read), then read + subtract + write; the unfused form moved 20 bytes per sample")
     win, hop = 9600, 4800
     polls = (cap - src) // hop
     tails = (f9.TailParams * nf)(*[f9.TailParams(src + 128 * i + 7, win, hop, 3, f9.TAIL_RMS, 1, -90.0, 0.0) for i in range(nf)])
