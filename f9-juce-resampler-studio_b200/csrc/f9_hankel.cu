@@ -26,7 +26,7 @@
 //   warps 5-12   converters: thread-private cp.async copies of the tile's input span into a raw fp32 ring three tiles ahead (zeros
 //                outside the segment's window), then fp16 head / tail split and 16-byte stores into the swizzled buffers of a
 //                4-stage operand ring
-//   warps 4, 13  issue 3 * K/16 MMAs (M = 128, N = 32) per tile each: warp 4 for columns 0-31, warp 13 for columns 32-63, each into
+//   warps 4, 13  issue 3 * K/16 MMAs (M = 128, N = 32) per tile each: warp 4 for columns 0-31, the last warp for columns 32-63, each into
 //                its own accumulator sets -- two per half when the weights leave room (K <= 256: 1:4, 1:8, 1:16), so that the
 //                epilogue of tile i overlaps the MMAs of tile i+1; one per half at 1:2
 //   warps 0-3    epilogue: tcgen05.ld (thread = lane = output offset), combine, st.global (128 contiguous bytes per warp and column)
@@ -44,9 +44,19 @@ namespace f9 {
 namespace {
 
 constexpr int kHkCols = 64;                 // columns (of 128 outputs) per tile = MMA N
-constexpr int kHkStages = 4;                // converted-input ring (operand buffers)
-constexpr int kHkRaw = 4;                   // raw fp32 ring: cp.async prefetch distance of the converters, in tiles
-constexpr int kHkThreads = 14 * 32;         // warps 0-3 epilogue, 4 and 13 MMA issue (one half of the tile's columns each), 5-12 converters
+// Compile-time knobs (A/B builds; measured flat for 3-6 raw / operand stages and 4-8 converter warps, worse with 12-16)
+#ifndef F9_HK_STAGES
+#define F9_HK_STAGES 4
+#endif
+#ifndef F9_HK_RAW
+#define F9_HK_RAW 4
+#endif
+#ifndef F9_HK_CONV_WARPS
+#define F9_HK_CONV_WARPS 8
+#endif
+constexpr int kHkStages = F9_HK_STAGES;     // converted-input ring (operand buffers)
+constexpr int kHkRaw = F9_HK_RAW;           // raw fp32 ring: cp.async prefetch distance of the converters, in tiles
+constexpr int kHkThreads = (6 + F9_HK_CONV_WARPS) * 32;   // warps 0-3 epilogue, 4 and the last one MMA issue (one half of the tile's columns each), 5.. converters
 constexpr int kHkHalf = kHkCols / 2;        // columns per MMA (N) and accumulator set
 // TMEM columns: weight heads at 0, tails at 8 KS (8 columns per K step and image); accumulator sets (D0, D1 of kHkHalf columns
 // each) from column 256 (KS <= 16: two sets per column half, the epilogue of one tile overlaps the MMAs of the next) or 272
@@ -58,7 +68,7 @@ template <int KS> struct HkTmem {
     static_assert(dBase + 2 * nBuf * 2 * kHkHalf <= 512 && 16 * KS <= dBase, "TMEM layout");
     static __device__ __forceinline__ int set(int h, int b) { return dBase + 2 * kHkHalf * (h * nBuf + b); }
 };
-constexpr int kHkConvWarps = 8, kHkFirstConv = 5;
+constexpr int kHkConvWarps = F9_HK_CONV_WARPS, kHkFirstConv = 5, kHkIssuer1 = 5 + F9_HK_CONV_WARPS;
 constexpr float kHkPre = 128.0f;            // 2^7 pre-scale, as f9_umma.cu
 constexpr uint32_t kHkPark = 2000;
 
@@ -283,9 +293,9 @@ hankel_fir_kernel(const HankelTileRec* __restrict__ recs, int nTiles, const __gr
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         const float2 hm = __half22float2(hmax);
         if (!(hm.x < 32768.0f) || !(hm.y < 32768.0f)) atomicOr(ovf, 1u);
-    } else if (warp == 4 || warp == 13) {
+    } else if (warp == 4 || warp == kHkIssuer1) {
         // =========================================================== MMA issue (TS mode: weights from TMEM, input from shared memory)
-        // Warp 4 owns columns 0-31 of every tile and accumulator set 0, warp 13 columns 32-63 and set 1: 3 * KS MMAs of N = 32 each.
+        // Warp 4 owns columns 0-31 of every tile, the last warp columns 32-63: 3 * KS MMAs of N = 32 each into their own accumulator sets.
         // Two accumulators per output: D0 += w0 x0, D1 += w1 x0 + w0 x1 (units of 1/2048).  The tensor core truncates the fp32
         // accumulator after every MMA by an ulp of its magnitude, so the K steps are issued tails first (|w| < 0.11: the accumulator is
         // still small) and the steps cLo..cHi that hold the main lobe of some lane's filter (|w| up to 1) last: only those 2-5 MMAs
