@@ -143,8 +143,11 @@ def test_custom_sinc_table(ctx, O, f9):
 
 
 # ---------------------------------------------------------------- batch job flow
-def test_batch_flow_trim_tail_convert(ctx, O, f9):
-    fs_in, fs_out = 96000, 44100
+@pytest.mark.parametrize("fs", [(96000, 44100), (48000, 192000), (44100, 48000), (48000, 96000)])
+def test_batch_flow_trim_tail_convert(ctx, O, f9, fs):
+    """The job flow on every resampler kernel: tensor-core polyphase (96 -> 44.1 k), Hankel operand (1:4, 1:2) and, for the
+    Lagrange jobs, the short kernel; odd latencies put the trimmed starts off 16-byte alignment."""
+    fs_in, fs_out = fs
     rng = np.random.default_rng(10)
     jobs, expect = [], []
     for i in range(6):
