@@ -30,8 +30,9 @@
 //                its own accumulator sets -- two per half when the weights leave room (K <= 256: 1:4, 1:8, 1:16), so that the
 //                epilogue of tile i overlaps the MMAs of tile i+1; one per half at 1:2
 //   warps 0-3    epilogue: tcgen05.ld (thread = lane = output offset), combine, st.global (128 contiguous bytes per warp and column)
-// Measured (B200, 512 channels of 10 s): 48 -> 192 k 1.14 ms = 65.6 % of the HBM roofline (polyphase kernel: 1.93 ms, 38.9 %),
-// 48 -> 96 k 70.2 % (48.4 %); with the MMAs switched off the load / convert / store path alone runs at 78 %, the MMAs alone at 94 %.
+// Measured (B200, 512 channels of 10 s): 48 -> 192 k 1.07 ms = 70 % of the HBM roofline (polyphase kernel: 1.93 ms, 38.9 %),
+// 48 -> 96 k 72 % (48.4 %); with the MMAs switched off the load / convert / store path alone runs at 94 %, the MMAs alone at 90 %
+// (F9_HK_DBG; DESIGN.md 4.2 lists what was tried on the gap between the two).
 #include <algorithm>
 #include <cstdint>
 #include <cstdio>
@@ -101,10 +102,6 @@ __device__ __forceinline__ uint32_t elect_one() {
     uint32_t el;
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(el));
     return el;
-}
-__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                 :: "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
 __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"

@@ -15,7 +15,7 @@ def snr_db(ref, got):
 
 ctx = f9.Context(0)
 rng = np.random.default_rng(0)
-cases = [(96000, 44100), (44100, 48000), (48000, 192000), (96000, 48000), (192000, 48000), (88200, 48000), (44100, 96000), (48000, 44100)]
+cases = [(96000, 44100), (44100, 48000), (48000, 192000), (48000, 96000), (24000, 192000), (12000, 192000), (96000, 48000), (192000, 48000), (88200, 48000), (44100, 96000), (48000, 44100)]
 n_in = int(sys.argv[1]) if len(sys.argv) > 1 else 60000
 bad = 0
 for kind in (0, 1, 2, 3):
