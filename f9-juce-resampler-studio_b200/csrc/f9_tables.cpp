@@ -374,51 +374,9 @@ double umma_cost_per_output(int taps, long long p, long long q, int NB, int GBL,
 // Tensor-core plan for ratio p/q: scale p/q by m so that a period has 64..224 slots; choose the scaling, the group width
 // (16 or 32 slots) and the block size with the lowest modelled cost whose tables fit shared memory with two staging buffers.
 // *m = 0 when no plan fits.
-void umma_choose_plan(int taps, long long p, long long q, long long* m_out, int* NB_out, int* GBL_out) {
-    double best = 1e30; *m_out = 0; *NB_out = 0; *GBL_out = 0;
-    for (long long m = 1; m * q <= 16LL * kUmmaMaxGroups * kUmmaMaxBlocks && m * p + taps + 48 <= 16 * kUmmaMaxNK; ++m) {
-        const long long ps = p * m, qs = q * m;
-        if (qs < 48 && (m + 1) * q <= 224) continue;                           // too few slots per period: keep scaling
-        for (int NB : {32, 16}) {
-            if (getenv("F9_UMMA_NB") && atoi(getenv("F9_UMMA_NB")) != NB) continue;
-            const int G = (int) ((qs + NB - 1) / NB), maxG = std::min(kUmmaMaxGroups, 448 / (2 * NB));
-            // a period scaled for alignment (m > 1 of an unaligned p) splits best into blocks of whole original periods: every
-            // block then has the window of one period, as the unscaled plan's tiles have
-            int nGB0 = (G + maxG - 1) / maxG;
-            if (m > 1 && (p & 3) != 0)
-                for (int d = (int) m; d > nGB0; --d)
-                    if (m % d == 0 && G % d == 0 && G / d <= maxG) { nGB0 = d; break; }
-            for (int nGB = nGB0; nGB <= kUmmaMaxBlocks && nGB <= G; ++nGB) {
-                const int GBL = (G + nGB - 1) / nGB;
-                size_t smem2 = 0;
-                double c = umma_cost_per_output(taps, ps, qs, NB, GBL, &smem2);
-                if (smem2 > 227 * 1024) continue;
-                if (ps & 3) c *= 1.4;                           // rows not 16-byte aligned: register loader instead of the TMA feed
-                if (c < 0.97 * best) { best = c; *m_out = m; *GBL_out = GBL; *NB_out = NB; }    // ties go to the smaller plan
-                break;                                                          // more blocks only cost more
-            }
-        }
-        // rows not yet 16-byte aligned: a multiple of the period may be, which buys the TMA feed (measured at 147/160: 1.6x for
-        // the 200-tap kernel, 1.33x for Lagrange once the blocks are whole original periods)
-        if (qs >= 224 && ((ps & 3) == 0 || m >= 4)) break;
-    }
-}
-
-bool build_umma(int kind, const float* sinc_table, long long p, long long q, int NB, int GBL, UmmaHost* out) {
-    const int taps = interp_memory(kind);
-    if (NB != 16 && NB != 32) return false;
+// Accumulator-split plan of (p, q, NB, GBL): pool slots (0 = no split), split step, operand-ring depth.  See build_umma.
+static int umma_pool_plan(long long p, long long q, int taps, int NB, int GBL, int* split_out, int* aSlots_out) {
     const int G = (int) ((q + NB - 1) / NB);
-    if (GBL < 1 || GBL > kUmmaMaxGroups || GBL * 2 * NB > 448) return false;
-    const int nGB = (G + GBL - 1) / GBL;
-    if (nGB > kUmmaMaxBlocks) return false;
-    *out = UmmaHost();
-    out->p = (int) p; out->q = (int) q; out->taps = taps; out->NB = NB; out->G = G; out->GBL = GBL; out->nGB = nGB;
-    const int tileBytes = NB * 64, chunkBytes = NB * 32;
-    // accumulation split: only for long windows; the split step is the same for every group (first step past every slot's
-    // centre tap), which keeps "past the split" a bottom-end range of the active groups.
-    // TMEM budget: 512 columns = accumulators (2*NB per group) + pool + operand ring (32 columns per stage).  A ring of four
-    // stages (accumulators + pool <= 384 columns) decouples the converters from the MMAs; plans whose pool needs the room
-    // (groups that overlap a lot in time, e.g. upsampling) keep the two-stage ring.
     int split = 0;
     auto pool_for = [&](int accCols) {
         int poolN = umma_pool_slots(NB, GBL, accCols); split = 0;
@@ -447,6 +405,67 @@ bool build_umma(int kind, const float* sinc_table, long long p, long long q, int
         else split = splitWide;
     }
     if (poolN == 0) split = 0;
+    *split_out = split; *aSlots_out = aSlots;
+    return poolN;
+}
+
+void umma_choose_plan(int taps, long long p, long long q, long long* m_out, int* NB_out, int* GBL_out) {
+    double best = 1e30; *m_out = 0; *NB_out = 0; *GBL_out = 0;
+    for (long long m = 1; m * q <= 16LL * kUmmaMaxGroups * kUmmaMaxBlocks && m * p + taps + 48 <= 16 * kUmmaMaxNK; ++m) {
+        const long long ps = p * m, qs = q * m;
+        if (qs < 48 && (m + 1) * q <= 224) continue;                           // too few slots per period: keep scaling
+        for (int NB : {32, 16}) {
+            if (getenv("F9_UMMA_NB") && atoi(getenv("F9_UMMA_NB")) != NB) continue;
+            const int G = (int) ((qs + NB - 1) / NB), maxG = std::min(kUmmaMaxGroups, 448 / (2 * NB));
+            // a period scaled for alignment (m > 1 of an unaligned p) splits best into blocks of whole original periods: every
+            // block then has the window of one period, as the unscaled plan's tiles have
+            int nGB0 = (G + maxG - 1) / maxG;
+            if (m > 1 && (p & 3) != 0)
+                for (int d = (int) m; d > nGB0; --d)
+                    if (m % d == 0 && G % d == 0 && G / d <= maxG) { nGB0 = d; break; }
+            for (int nGB = nGB0; nGB <= kUmmaMaxBlocks && nGB <= G; ++nGB) {
+                const int GBL = (G + nGB - 1) / nGB;
+                size_t smem2 = 0;
+                double c = umma_cost_per_output(taps, ps, qs, NB, GBL, &smem2);
+                if (smem2 > 227 * 1024) continue;
+                if (ps & 3) c *= 1.4;                           // rows not 16-byte aligned: register loader instead of the TMA feed
+                // Upsampling with a long window: the groups of a block all overlap in time, and without the accumulator split the
+                // truncation error reaches the tolerance (44.1 -> 96 k measured 1.125 x 2^-20 unsplit).  Take more, smaller blocks
+                // until every group of a block has its own pool slot; the extra staging is the price.
+                if (ps < qs && taps >= 64) {
+                    int sp = 0, as = 0;
+                    if (umma_pool_plan(ps, qs, taps, NB, GBL, &sp, &as) == 0) {
+                        if (nGB < kUmmaMaxBlocks && nGB < G) continue;
+                        c *= 8.0;                               // no block count gives the split at this scale: last resort only
+                    }
+                }
+                if (c < 0.97 * best) { best = c; *m_out = m; *GBL_out = GBL; *NB_out = NB; }    // ties go to the smaller plan
+                break;                                                          // more blocks only cost more
+            }
+        }
+        // rows not yet 16-byte aligned: a multiple of the period may be, which buys the TMA feed (measured at 147/160: 1.6x for
+        // the 200-tap kernel, 1.33x for Lagrange once the blocks are whole original periods)
+        if (qs >= 224 && ((ps & 3) == 0 || m >= 4)) break;
+    }
+}
+
+bool build_umma(int kind, const float* sinc_table, long long p, long long q, int NB, int GBL, UmmaHost* out) {
+    const int taps = interp_memory(kind);
+    if (NB != 16 && NB != 32) return false;
+    const int G = (int) ((q + NB - 1) / NB);
+    if (GBL < 1 || GBL > kUmmaMaxGroups || GBL * 2 * NB > 448) return false;
+    const int nGB = (G + GBL - 1) / GBL;
+    if (nGB > kUmmaMaxBlocks) return false;
+    *out = UmmaHost();
+    out->p = (int) p; out->q = (int) q; out->taps = taps; out->NB = NB; out->G = G; out->GBL = GBL; out->nGB = nGB;
+    const int tileBytes = NB * 64, chunkBytes = NB * 32;
+    // accumulation split: only for long windows; the split step is the same for every group (first step past every slot's
+    // centre tap), which keeps "past the split" a bottom-end range of the active groups.
+    // TMEM budget: 512 columns = accumulators (2*NB per group) + pool + operand ring (32 columns per stage).  A ring of four
+    // stages (accumulators + pool <= 384 columns) decouples the converters from the MMAs; plans whose pool needs the room
+    // (groups that overlap a lot in time, e.g. upsampling) keep the two-stage ring.
+    int split = 0, aSlots = 2;
+    const int poolN = umma_pool_plan(p, q, taps, NB, GBL, &split, &aSlots);
     out->aSlots = aSlots;
     out->poolN = poolN; out->split = split;
     std::vector<float> w((size_t) taps);

@@ -113,6 +113,21 @@ def test_file_conversion(ctx, O, f9, kind, fs, sig):
             assert snr_db(ref, y[c]) >= 120.0
 
 
+@pytest.mark.parametrize("fs", [(44100, 96000), (48000, 88200), (16000, 48000), (44100, 192000), (44100, 48000), (32000, 48000),
+                                (48000, 192000), (48000, 96000)])
+def test_upsampling_precision(ctx, O, f9, fs):
+    """WindowedSinc at upsampling ratios on long full-amplitude noise: the groups of a block all overlap in time there, and an
+    unsplit fp32 accumulator in the tensor core reaches the tolerance (44.1 -> 96 k measured 1.125 x 2^-20 before the planner
+    insisted on the accumulator split for these plans).  The bound is north_star's, with no allowance."""
+    fs_in, fs_out = fs
+    n_in = 120000
+    x = np.random.default_rng(fs_in + fs_out).uniform(-0.5, 0.5, (1, n_in)).astype(np.float32)
+    y = ctx.resample(x, fs_in, fs_out, 0)
+    ref, _ = O.resample_channel(0, fs_in / fs_out, x[0], y.shape[1])
+    assert np.max(np.abs(y[0] - ref)) <= TOL, float(np.max(np.abs(y[0] - ref))) / TOL
+    assert snr_db(ref, y[0]) >= 120.0
+
+
 def test_file_conversion_irrational(ctx, O):
     x = signal(20000, 8)[None, :]
     for kind in (0, 1):
