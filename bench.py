@@ -156,11 +156,31 @@ TRAFFIC_BYTES_PER_LAUNCH = {256: 2.059729e9 + 874.370048e6}    # profiles/r01_v3
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
+def bind_to_gpu_numa_node(local_rank: int):
+    """One process per GPU: run on the CPUs next to this rank's GPU, so that the pinned host buffers of the e2e leg are
+    allocated (first touch) on the NUMA node its PCIe link hangs off.  Returns the CPU count bound to, or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w in range(words) for b in range(64) if (mask[w] >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def run_gpu(args, rank: int, local_rank: int, world: int):
     import torch
     import torch.distributed as dist
 
     f9 = _load("f9dsp", os.path.join(PKG, "py", "f9dsp.py"))
+    numa_cpus = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -347,7 +367,8 @@ def run_gpu(args, rank: int, local_rank: int, world: int):
                        "files_per_gpu": batch.files, "channels": batch.num_ch, "fs_in": batch.fs_in, "fs_out": batch.fs_out,
                        "seconds_per_file": batch.src_frames / batch.fs_in, "tail_scan": "RMS, 100 ms window / 50 ms hop / 3 consecutive",
                        "trim": "fused into the resampler", "l2": "inputs (%.2f GB per GPU) larger than L2" % (h2d / 1e9),
-                       "parallelism": f"files x{world} (weak, no collective)"},
+                       "parallelism": f"files x{world} (weak, no collective)",
+                       "host_binding": (f"rank bound to the {numa_cpus} CPUs of its GPU's NUMA node" if numa_cpus else "none")},
             "roofline": {"kernel": "umma_fir_kernel (WindowedSinc polyphase FIR on tcgen05: TMA-fed CTA pairs, fp16 2-split, fp32 TMEM accumulators; "
                                    "timed with its tile-table and redo-check launches)",
                          "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
