@@ -152,7 +152,7 @@ def run_reference(args, rank: int, world: int):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one umma_fir_kernel launch (ncu --set full, profiles/), by files per GPU
-TRAFFIC_BYTES_PER_LAUNCH = {256: 2.059729e9 + 874.370048e6}    # profiles/r01_v3_umma_fir_full.txt (dram read + write of one launch)
+TRAFFIC_BYTES_PER_LAUNCH = {256: 2.054042e9 + 873.202944e6}    # profiles/r01_v6_umma_fir_full.txt (dram read + write of one launch)
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
