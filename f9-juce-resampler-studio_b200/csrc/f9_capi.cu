@@ -756,7 +756,10 @@ int f9_resample_plan_run(f9_plan* plan) {
     if (!plan) return F9_ERR_INVALID;
     f9_context* ctx = plan->ctx;
     F9_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (plan->L.recs_stream != ctx->stream) plan->L.recs_ready = false;
     F9_TRY_CUDA(ctx, launch_resample(plan->L, ctx->stream, &ctx->launches));
+    plan->L.recs_ready = plan->L.d_tile_recs != nullptr;       // the segments of a plan never change: its tile records are built once
+    plan->L.recs_stream = ctx->stream;
     return F9_OK;
 }
 void f9_plan_destroy(f9_plan* plan) {

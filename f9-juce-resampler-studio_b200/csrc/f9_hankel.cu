@@ -429,8 +429,10 @@ cudaError_t launch_hankel(const ResampleLaunch& L, cudaStream_t s, long long* la
     const size_t smem = hankel_smem_bytes(L.hk);
     cudaError_t e;
     if ((e = cudaMemsetAsync(L.d_ovf, 0, sizeof(unsigned), s)) != cudaSuccess) return e;
-    hankel_tile_table_kernel<<<(L.n_tiles + 255) / 256, 256, 0, s>>>(L.d_segs, L.d_tile_prefix, L.n_segs, L.n_tiles, 128 / L.hk.L, recs);
-    ++*launches;
+    if (!L.recs_ready) {
+        hankel_tile_table_kernel<<<(L.n_tiles + 255) / 256, 256, 0, s>>>(L.d_segs, L.d_tile_prefix, L.n_segs, L.n_tiles, 128 / L.hk.L, recs);
+        ++*launches;
+    }
     const int grid = std::min(L.n_tiles, L.sm_count);
     const int dbg = getenv("F9_HK_DBG") ? atoi(getenv("F9_HK_DBG")) : 0;      // development: 1 skip MMAs, 2 skip loads + conversion, 4 skip stores
     #define F9_HK_LAUNCH(ks_, lo_, hi_) do { \

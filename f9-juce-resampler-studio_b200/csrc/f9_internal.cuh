@@ -254,6 +254,8 @@ struct ResampleLaunch {
     bool um_cta2 = false;          // ... and the plan suits CTA pairs (tcgen05.mma.cta_group::2: each CTA holds half of every weight tile)
     UmmaTma um_maps;
     UmmaTileRec* d_tile_recs = nullptr;    // n_tiles records, caller-provided scratch when um_tma (see resample_scratch_bytes)
+    bool recs_ready = false;       // the tile records in d_tile_recs are those of this launch's segments already (a plan's second run): skip the table kernel
+    cudaStream_t recs_stream = nullptr;   // ... written on this stream (another stream rebuilds them: no ordering between the two)
     unsigned* d_ovf = nullptr;     // device flag: an input sample was outside the fp16 split's range -> fp32 redo
     // banded (register-tiled) path
     bool banded = false;

@@ -499,8 +499,10 @@ template <int TAPS>
 cudaError_t run_short(const ResampleLaunch& L, cudaStream_t s, long long* launches) {
     if (!L.d_tile_recs) return cudaErrorInvalidValue;
     ShortTileRec* recs = reinterpret_cast<ShortTileRec*>(L.d_tile_recs);
-    short_tile_table_kernel<TAPS><<<(L.n_tiles + 255) / 256, 256, 0, s>>>(L.d_segs, L.d_tile_prefix, L.n_segs, L.n_tiles, L.poly, L.tile_out, recs);
-    ++*launches;
+    if (!L.recs_ready) {
+        short_tile_table_kernel<TAPS><<<(L.n_tiles + 255) / 256, 256, 0, s>>>(L.d_segs, L.d_tile_prefix, L.n_segs, L.n_tiles, L.poly, L.tile_out, recs);
+        ++*launches;
+    }
     const int perSm = std::max(1, std::min(2048 / L.short_threads, (int) ((227 * 1024) / (L.short_smem + 1024))));
     const int grid = std::min(L.n_tiles, L.sm_count * perSm);
     cudaError_t e;

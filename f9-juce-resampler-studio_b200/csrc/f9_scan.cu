@@ -212,8 +212,8 @@ tail_window_kernel(const DevBuf* __restrict__ bufs, const TailParams* __restrict
     const DevBuf B = bufs[b];
     const TailParams P = params[b];
     const long long e = P.startFrame + (long long) (i + 1) * P.hop;
-    if (e > B.numFrames) return;                       // past the data: no such poll (flag stays -2)
     int* out = flags + (size_t) b * max_polls + i;
+    if (e > B.numFrames) { if (threadIdx.x == 0) *out = -2; return; }      // past the data: no such poll
     if (e < P.window) { if (threadIdx.x == 0) *out = -1; return; }
     double s = 0.0; float m = 0.0f;
     __shared__ double sh_s[kStatThreads / 32]; __shared__ float sh_m[kStatThreads / 32];
@@ -265,9 +265,6 @@ __global__ void tail_runs_kernel(const DevBuf* __restrict__ bufs, const TailPara
     stop[b] = st;
 }
 
-__global__ void fill_int_kernel(int* p, size_t n, int v) {
-    for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) p[i] = v;
-}
 
 // ---- bounded-lag cross-correlation -----------------------------------------------------------------
 // r_c[lag] = sum_i (double) x[i] * (double) y_c[i+lag], i ascending.  The float*float product is exact in
@@ -420,8 +417,6 @@ cudaError_t launch_tail_scan(const DevBuf* d_bufs, const TailParams* d_params, i
                              long long* d_stop, int* d_flags, cudaStream_t s, long long* launches) {
     if (n <= 0) return cudaSuccess;
     if (max_polls > 0) {
-        fill_int_kernel<<<256, 256, 0, s>>>(d_flags, (size_t) n * max_polls, -2);
-        ++*launches;
         dim3 grid(max_polls, n);
         tail_window_kernel<<<grid, kStatThreads, 0, s>>>(d_bufs, d_params, max_polls, d_flags);
         ++*launches;

@@ -954,10 +954,12 @@ cudaError_t launch_umma(const ResampleLaunch& L, cudaStream_t s, long long* laun
         L.um, L.um_maps, L.d_tile_recs, L.um_stages, L.um_aligned ? 1 : 0, L.d_ovf, doProf ? d_prof : nullptr, dbg)
     if (L.um_tma) {
         if (!L.d_tile_recs) return cudaErrorInvalidValue;
-        umma_tile_table_kernel<<<(L.n_tiles + 256) / 256, 256, 0, s>>>(L.d_segs, L.d_tile_prefix, L.n_segs, L.n_tiles, L.um, L.um_maps, L.d_tile_recs,
-                                                                           pairs && L.um.nGB > 1 ? 1 : 0);
-        if ((e = cudaGetLastError()) != cudaSuccess) return e;
-        ++*launches;
+        if (!L.recs_ready) {
+            umma_tile_table_kernel<<<(L.n_tiles + 256) / 256, 256, 0, s>>>(L.d_segs, L.d_tile_prefix, L.n_segs, L.n_tiles, L.um, L.um_maps, L.d_tile_recs,
+                                                                               pairs && L.um.nGB > 1 ? 1 : 0);
+            if ((e = cudaGetLastError()) != cudaSuccess) return e;
+            ++*launches;
+        }
         if (pairs) {                                             // clusters of two CTAs
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3((unsigned) grid); cfg.blockDim = dim3(kThreadsTma); cfg.dynamicSmemBytes = L.um_smem; cfg.stream = s;
