@@ -638,6 +638,25 @@ int f9_dev_find_peak_batch(f9_context* ctx, const f9_dev_buffer* bufs, int n, fl
     return F9_OK;
 }
 
+int f9_dev_latency_stats_batch(f9_context* ctx, const f9_dev_buffer* bufs, int n, float threshold, int* d_out_pos, double* d_sumsq, float* d_peak) {
+    if (!ctx || n < 0 || (n > 0 && (!bufs || !d_out_pos || !d_sumsq))) return F9_ERR_INVALID;
+    if (n == 0) return F9_OK;
+    F9_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    const DevBuf* hb = reinterpret_cast<const DevBuf*>(bufs);
+    std::vector<int> prefix;
+    const int total = peak_prefix(hb, n, &prefix);
+    int rc = ctx->arena_reserve(sizeof(DevBuf) * (size_t) n + sizeof(int) * (size_t) (n + 1) + (sizeof(PeakPartial) + sizeof(double)) * (size_t) total + 16384,
+                                sizeof(DevBuf) * (size_t) n + sizeof(int) * (size_t) (n + 1) + 8192, true);
+    if (rc) return rc;
+    DevBuf* d_b; int* d_prefix;
+    rc = upload_array(ctx, hb, (size_t) n, &d_b); if (rc) return rc;
+    rc = upload_array(ctx, prefix.data(), prefix.size(), &d_prefix); if (rc) return rc;
+    PeakPartial* d_part = (PeakPartial*) ctx->d_alloc(sizeof(PeakPartial) * (size_t) std::max(total, 1));
+    double* d_psum = (double*) ctx->d_alloc(sizeof(double) * (size_t) std::max(total, 1));
+    F9_TRY_CUDA(ctx, launch_find_peak(d_b, n, total, d_prefix, threshold, d_part, d_out_pos, ctx->stream, &ctx->launches, d_psum, d_sumsq, d_peak));
+    return F9_OK;
+}
+
 int f9_dev_stats_batch(f9_context* ctx, const f9_dev_buffer* bufs, int n, double* d_sumsq, float* d_peak) {
     if (!ctx || n < 0 || (n > 0 && (!bufs || !d_sumsq || !d_peak))) return F9_ERR_INVALID;
     if (n == 0) return F9_OK;

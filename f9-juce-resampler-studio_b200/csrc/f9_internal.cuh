@@ -72,7 +72,9 @@ constexpr int kStatPartialsPerBuf = 64;     // stage-1 CTAs per buffer of launch
 
 int         peak_prefix(const DevBuf* h_bufs, int n, std::vector<int>* prefix);          // returns total CTAs
 cudaError_t launch_find_peak(const DevBuf* d_bufs, int n, int total_ctas, const int* d_prefix, float threshold,
-                             PeakPartial* d_partials /* total_ctas */, int* d_out_pos, cudaStream_t s, long long* launches);
+                             PeakPartial* d_partials /* total_ctas */, int* d_out_pos, cudaStream_t s, long long* launches,
+                             double* d_psum = nullptr /* total_ctas: the same pass sums the squares */, double* d_sumsq = nullptr,
+                             float* d_peakv = nullptr);
 
 cudaError_t launch_stats(const DevBuf* d_bufs, int n, double* d_psum, float* d_pmax /* n*kStatPartialsPerBuf each */,
                          double* d_sumsq, float* d_peak, cudaStream_t s, long long* launches);

@@ -20,8 +20,13 @@ __device__ __forceinline__ bool peak_better(float v, int ch, int pos, float bv, 
 }
 
 // ---- stage 1: one CTA per (buffer, channel, chunk) ---------------------------------------------------
+// STATS: the same pass also sums the squares (float product rounded to float, widened, double sum: calculateRMS, Source/
+// MainComponent.cpp:983-1004) -- findPeakPosition and calculateNoiseFloorDb read the same capture right after each other in the
+// latency measurement (:270-279), so one read serves both.
+template <bool STATS>
 __global__ void __launch_bounds__(kPeakThreads)
-peak_partial_kernel(const DevBuf* __restrict__ bufs, const int* __restrict__ prefix, int n, PeakPartial* __restrict__ partials) {
+peak_partial_kernel(const DevBuf* __restrict__ bufs, const int* __restrict__ prefix, int n, PeakPartial* __restrict__ partials,
+                    double* __restrict__ psum) {
     // locate the buffer of this CTA: prefix[b] <= blockIdx.x < prefix[b+1]
     int lo = 0, hi = n;
     const int bid = blockIdx.x;
@@ -36,13 +41,16 @@ peak_partial_kernel(const DevBuf* __restrict__ bufs, const int* __restrict__ pre
     const float* __restrict__ x = B.base + (long long) ch * B.chStride + start;
 
     float bv = 0.0f; int bpos = -1;
+    double sq = 0.0;
     // head to 16-byte alignment, float4 body, scalar tail; each thread visits increasing indices so a strict
     // '>' keeps its earliest maximum.
     const int mis = (int) ((reinterpret_cast<uintptr_t>(x) >> 2) & 3);
     const int head = min(len, (4 - mis) & 3);
     if ((int) threadIdx.x < head) {
-        float a = fabsf(x[threadIdx.x]);
+        const float xv0 = x[threadIdx.x];
+        float a = fabsf(xv0);
         if (a > bv) { bv = a; bpos = threadIdx.x; }
+        if (STATS) sq += (double) __fmul_rn(xv0, xv0);
     }
     const int nvec = (len - head) >> 2;
     const float4* __restrict__ xv = reinterpret_cast<const float4*>(x + head);
@@ -55,12 +63,15 @@ peak_partial_kernel(const DevBuf* __restrict__ bufs, const int* __restrict__ pre
         a = fabsf(v.y); if (a > bv) { bv = a; bpos = p + 1; }
         a = fabsf(v.z); if (a > bv) { bv = a; bpos = p + 2; }
         a = fabsf(v.w); if (a > bv) { bv = a; bpos = p + 3; }
+        if (STATS) sq += ((double) __fmul_rn(v.x, v.x) + (double) __fmul_rn(v.y, v.y)) + ((double) __fmul_rn(v.z, v.z) + (double) __fmul_rn(v.w, v.w));
     }
     const int tail0 = head + 4 * nvec;
     if (tail0 + (int) threadIdx.x < len) {
         // tail indices are larger than everything in the body: strict '>' again keeps the earliest
-        float a = fabsf(x[tail0 + threadIdx.x]);
+        const float xt = x[tail0 + threadIdx.x];
+        float a = fabsf(xt);
         if (a > bv) { bv = a; bpos = tail0 + threadIdx.x; }
+        if (STATS) sq += (double) __fmul_rn(xt, xt);
     }
     // a thread's head index is smaller than its body indices only for threads < head; handled by ordering above.
 
@@ -74,9 +85,20 @@ peak_partial_kernel(const DevBuf* __restrict__ bufs, const int* __restrict__ pre
     }
     __shared__ float sv[kPeakThreads / 32];
     __shared__ unsigned sp[kPeakThreads / 32];
+    __shared__ double ss[kPeakThreads / 32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (STATS) {
+        #pragma unroll
+        for (int off = 16; off > 0; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);      // fixed tree: deterministic
+        if (lane == 0) ss[warp] = sq;
+    }
     if (lane == 0) { sv[warp] = bv; sp[warp] = bposu; }
     __syncthreads();
+    if (STATS && threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < kPeakThreads / 32; ++w) t += ss[w];
+        psum[bid] = t;
+    }
     if (warp == 0) {
         bv = (lane < kPeakThreads / 32) ? sv[lane] : 0.0f;
         bposu = (lane < kPeakThreads / 32) ? sp[lane] : 0x7fffffffu;
@@ -97,13 +119,22 @@ peak_partial_kernel(const DevBuf* __restrict__ bufs, const int* __restrict__ pre
 
 // ---- stage 2: one CTA per buffer folds its partials in scan order ----------------------------------
 __global__ void __launch_bounds__(128)
-peak_final_kernel(const PeakPartial* __restrict__ partials, const int* __restrict__ prefix, float threshold, int* __restrict__ out_pos) {
+peak_final_kernel(const PeakPartial* __restrict__ partials, const int* __restrict__ prefix, float threshold, int* __restrict__ out_pos,
+                  const double* __restrict__ psum, double* __restrict__ sumsq, float* __restrict__ peakv) {
     const int b = blockIdx.x;
     const int p0 = prefix[b], p1 = prefix[b + 1];
     float bv = 0.0f; int bch = 0x7fffffff, bpos = 0x7fffffff;
+    double sq = 0.0;
     for (int i = p0 + threadIdx.x; i < p1; i += blockDim.x) {
         const PeakPartial r = partials[i];
         if (r.pos >= 0 && peak_better(r.v, r.ch, r.pos, bv, bch, bpos)) { bv = r.v; bch = r.ch; bpos = r.pos; }
+        if (psum) sq += psum[i];
+    }
+    __shared__ double ssq[4];
+    if (psum) {
+        #pragma unroll
+        for (int off = 16; off > 0; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
+        if ((threadIdx.x & 31) == 0) ssq[threadIdx.x >> 5] = sq;
     }
     #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
@@ -120,6 +151,7 @@ peak_final_kernel(const PeakPartial* __restrict__ partials, const int* __restric
         for (int w = 1; w < (int) blockDim.x / 32; ++w)
             if (peak_better(sv[w], sc[w], sp[w], bv, bch, bpos)) { bv = sv[w]; bch = sc[w]; bpos = sp[w]; }
         out_pos[b] = (bv > threshold && bpos != 0x7fffffff) ? bpos : -1;
+        if (psum) { sumsq[b] = (ssq[0] + ssq[1]) + (ssq[2] + ssq[3]); if (peakv) peakv[b] = bv; }
     }
 }
 
@@ -391,13 +423,15 @@ int peak_prefix(const DevBuf* h_bufs, int n, std::vector<int>* prefix) {
 }
 
 cudaError_t launch_find_peak(const DevBuf* d_bufs, int n, int total_ctas, const int* d_prefix, float threshold,
-                             PeakPartial* d_partials, int* d_out_pos, cudaStream_t s, long long* launches) {
+                             PeakPartial* d_partials, int* d_out_pos, cudaStream_t s, long long* launches,
+                             double* d_psum, double* d_sumsq, float* d_peakv) {
     if (n <= 0) return cudaSuccess;
     if (total_ctas > 0) {
-        peak_partial_kernel<<<total_ctas, kPeakThreads, 0, s>>>(d_bufs, d_prefix, n, d_partials);
+        if (d_psum) peak_partial_kernel<true><<<total_ctas, kPeakThreads, 0, s>>>(d_bufs, d_prefix, n, d_partials, d_psum);
+        else peak_partial_kernel<false><<<total_ctas, kPeakThreads, 0, s>>>(d_bufs, d_prefix, n, d_partials, nullptr);
         ++*launches;
     }
-    peak_final_kernel<<<n, 128, 0, s>>>(d_partials, d_prefix, threshold, d_out_pos);
+    peak_final_kernel<<<n, 128, 0, s>>>(d_partials, d_prefix, threshold, d_out_pos, d_psum, d_sumsq, d_peakv);
     ++*launches;
     return cudaGetLastError();
 }

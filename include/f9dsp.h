@@ -260,6 +260,11 @@ typedef struct f9_dev_buffer {      /* planar float32 on the device             
 
 /* batched findPeakPosition: d_out_pos[i] (device int) for each buffer */
 F9_API int f9_dev_find_peak_batch(f9_context* ctx, const f9_dev_buffer* bufs, int n, float threshold, int* d_out_pos);
+/* The latency measurement reads each capture twice in the reference -- findPeakPosition, then calculateNoiseFloorDb over the
+ * same buffer (Source/MainComponent.cpp:270-279).  This form serves both from one read: d_out_pos[i] as above, d_sumsq[i] the sum
+ * of squares (double; rms = sqrt(sumsq / (numCh * numFrames)), noise floor = 20 log10f(max(rms, 1e-6f))), d_peak[i] (optional) max |x|. */
+F9_API int f9_dev_latency_stats_batch(f9_context* ctx, const f9_dev_buffer* bufs, int n, float threshold, int* d_out_pos,
+                                      double* d_sumsq, float* d_peak);
 /* batched sum of squares (double) and peak per buffer: d_sumsq[i], d_peak[i] (device) */
 F9_API int f9_dev_stats_batch(f9_context* ctx, const f9_dev_buffer* bufs, int n, double* d_sumsq, float* d_peak);
 

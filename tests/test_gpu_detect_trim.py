@@ -187,6 +187,46 @@ def test_remove_dc_tolerance(ctx, O):
     assert np.max(np.abs(g - c)) <= 2.0 ** -20           # tolerance parity: float sequential mean vs parallel mean
 
 
+def test_latency_stats_one_pass(ctx, O, f9):
+    """findPeakPosition + the sum of squares behind calculateNoiseFloorDb from one read of each capture: the position is the
+    reference's (ties, threshold, all-zero buffer), the RMS within one float ulp of the sequential double sum, the peak exact."""
+    torch = pytest.importorskip("torch")
+    import ctypes as C
+    rng = np.random.default_rng(5)
+    shapes = [(2, 240000), (1, 50001), (2, 7), (5, 33333), (2, 16384), (2, 16385), (2, 1000), (2, 4096)]
+    caps = []
+    for i, (ch, frames) in enumerate(shapes):
+        x = (rng.standard_normal((ch, frames)) * 10 ** (-80 / 20)).astype(np.float32)
+        if i == 6:
+            x[:] = 0.0                                                 # all zero: -1
+        elif i == 7:
+            x[:] *= 100.0                                              # peak below the 0.1 threshold: -1
+        else:
+            d = int(rng.integers(0, frames))
+            x[ch - 1, d] = 0.9
+            if i % 2 == 0 and d + 5 < frames:
+                x[0, d + 5] = 0.9                                      # equal peak in channel 0, later frame: channel order wins
+        caps.append(x)
+    d_caps = [torch.from_numpy(c).cuda() for c in caps]
+    n = len(caps)
+    bufs = (f9.DevBuffer * n)(*[f9.DevBuffer(t.data_ptr(), t.shape[1], t.shape[0], t.shape[1]) for t in d_caps])
+    pos = torch.full((n,), -7, dtype=torch.int32, device="cuda")
+    pos2 = torch.full((n,), -7, dtype=torch.int32, device="cuda")
+    sumsq = torch.zeros(n, dtype=torch.float64, device="cuda")
+    peak = torch.zeros(n, dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    ctx._check(f9.lib().f9_dev_latency_stats_batch(ctx.handle, bufs, n, 0.1, pos.data_ptr(), sumsq.data_ptr(), peak.data_ptr()))
+    ctx._check(f9.lib().f9_dev_find_peak_batch(ctx.handle, bufs, n, 0.1, pos2.data_ptr()))
+    ctx.synchronize()
+    pos, pos2, sumsq, peak = pos.cpu().numpy(), pos2.cpu().numpy(), sumsq.cpu().numpy(), peak.cpu().numpy()
+    for i, x in enumerate(caps):
+        assert pos[i] == pos2[i] == O.find_peak_position(x, 0.1), i
+        assert peak[i] == np.max(np.abs(x))
+        rms = np.float32(np.sqrt(sumsq[i] / x.size))
+        ref = np.float32(O.calculate_rms(x))
+        assert abs(int(rms.view(np.int32)) - int(ref.view(np.int32))) <= 1, (i, rms, ref)
+
+
 @pytest.mark.parametrize("remove_dc", [0, 1])
 def test_dev_trim_batch_ragged(ctx, O, f9, remove_dc):
     """Device-resident trimLatency (+ fused removeDCOffset) over a ragged batch: latencies at every 16-byte misalignment,

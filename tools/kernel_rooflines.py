@@ -68,6 +68,9 @@ def main():
     sumsq = torch.empty(n, dtype=torch.float64, device=dev); pk = torch.empty(n, dtype=torch.float32, device=dev)
     ms = timed(lambda: ctx._check(L.f9_dev_stats_batch(ctx.handle, bufs, n, sumsq.data_ptr(), pk.data_ptr())))
     report("stats_partial/final (calculateRMS / noise floor)", "config4: 512 x 2 x 240000", ms, 4.0 * n * ch * frames, n * ch * frames, "samples")
+    ms = timed(lambda: ctx._check(L.f9_dev_latency_stats_batch(ctx.handle, bufs, n, 0.1, pos.data_ptr(), sumsq.data_ptr(), pk.data_ptr())))
+    report("peak_partial<STATS>/final (findPeakPosition + calculateNoiseFloorDb, one read)", "config4: 512 x 2 x 240000", ms, 4.0 * n * ch * frames, n * ch * frames, "samples",
+           "the latency measurement's two passes over a capture (MainComponent.cpp:270-279) as one")
     stim = torch.zeros(256, dtype=torch.float32, device=dev); stim[0] = 0.9
     raw = torch.zeros(n * 24, dtype=torch.uint8, device=dev)
     ms = timed(lambda: ctx._check(L.f9_dev_xcorr_peak_batch(ctx.handle, bufs, n, stim.data_ptr(), 256, -65536, 65536, raw.data_ptr())), reps=5)
