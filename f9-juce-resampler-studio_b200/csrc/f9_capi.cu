@@ -249,6 +249,33 @@ int f9_find_peak_position(f9_context* ctx, const float* const* ch, int numCh, in
     return F9_OK;
 }
 
+// The latency measurement of timerCallback (Source/MainComponent.cpp:266-284) in one call: one upload and one read of the capture
+// give findPeakPosition(buffer, threshold) and calculateNoiseFloorDb(buffer).
+int f9_measure_latency(f9_context* ctx, const float* const* ch, int numCh, int numFrames, float threshold, int* out_pos, float* out_noise_floor_db) {
+    int rc = check_planar(ctx, ch, numCh, numFrames); if (rc) return rc;
+    if (!out_pos || !out_noise_floor_db) return ctx->fail(F9_ERR_INVALID, "null output");
+    if (numCh == 0 || numFrames == 0) { *out_pos = -1; *out_noise_floor_db = noise_floor_db_from_rms(0.0f); return F9_OK; }
+    DevBuf hb{}; std::vector<int> prefix;
+    hb.numCh = numCh; hb.numFrames = numFrames;
+    const int total = peak_prefix(&hb, 1, &prefix);
+    rc = ctx->arena_reserve(planar_bytes(numCh, numFrames) + (sizeof(PeakPartial) + sizeof(double)) * (size_t) total + 4096, 4096); if (rc) return rc;
+    rc = upload_planar(ctx, ch, numCh, numFrames, &hb); if (rc) return rc;
+    DevBuf* d_bufs; int* d_prefix;
+    rc = upload_array(ctx, &hb, 1, &d_bufs); if (rc) return rc;
+    rc = upload_array(ctx, prefix.data(), prefix.size(), &d_prefix); if (rc) return rc;
+    PeakPartial* d_part = (PeakPartial*) ctx->d_alloc(sizeof(PeakPartial) * (size_t) total);
+    double* d_psum = (double*) ctx->d_alloc(sizeof(double) * (size_t) total);
+    double* d_res = (double*) ctx->d_alloc(2 * sizeof(double));              // [0] sum of squares, [1] (as int) position
+    int* d_pos = reinterpret_cast<int*>(d_res + 1);
+    F9_TRY_CUDA(ctx, launch_find_peak(d_bufs, 1, total, d_prefix, threshold, d_part, d_pos, ctx->stream, &ctx->launches, d_psum, d_res, nullptr));
+    double* h_res = (double*) ctx->h_alloc(2 * sizeof(double));
+    F9_TRY_CUDA(ctx, cudaMemcpyAsync(h_res, d_res, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    F9_FINISH(ctx);
+    *out_pos = *reinterpret_cast<const int*>(h_res + 1);
+    *out_noise_floor_db = noise_floor_db_from_rms((float) std::sqrt(h_res[0] / (double) ((long long) numCh * numFrames)));
+    return F9_OK;
+}
+
 int f9_find_peak_interleaved(f9_context* ctx, const float* audio, long long n, float threshold, long long* out_index, int* out_found) {
     if (!ctx) return F9_ERR_INVALID;
     if (n < 0 || n > 0x7fffffffLL || (n > 0 && !audio) || !out_index) return ctx->fail(F9_ERR_INVALID, "bad interleaved buffer");

@@ -218,11 +218,13 @@ public:
     }
     /** The body of timerCallback's latency completion (Source/MainComponent.cpp:265-294). */
     bool completeLatencyMeasurement(const AudioBufferView& latencyCaptureBuffer) {
-        const int peak = findPeakPosition(latencyCaptureBuffer, 0.1f);
-        if (peak < 0) return false;
+        // findPeakPosition(buffer, 0.1f) and calculateNoiseFloorDb(buffer) from one upload and one read of the capture
+        int peak = -1; float noiseFloorDb = -120.0f;
+        if (f9_measure_latency(ctx_.get(), latencyCaptureBuffer.channels, latencyCaptureBuffer.numChannels, latencyCaptureBuffer.numSamples,
+                               0.1f, &peak, &noiseFloorDb) != F9_OK || peak < 0) return false;
         settings.measuredLatencySamples = peak * 2;              // "Assuming stereo" (:275)
         settings.lastBufferSizeWhenMeasured = settings.bufferSize;
-        settings.measuredNoiseFloorDb = calculateNoiseFloorDb(latencyCaptureBuffer);
+        settings.measuredNoiseFloorDb = noiseFloorDb;
         settings.hasNoiseFloorMeasurement = true;
         return true;
     }

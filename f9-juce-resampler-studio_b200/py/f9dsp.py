@@ -116,6 +116,7 @@ SYMBOLS = [
     ("f9_resampled_length", _ll, [_ll, _d, _d]),
     ("f9_process_batch", _i, [_vp, C.POINTER(Job), _i, C.POINTER(Result)]),
     ("f9_dev_find_peak_batch", _i, [_vp, C.POINTER(DevBuffer), _i, _f, _vp]),
+    ("f9_measure_latency", _i, [_vp, _fpp, _i, _i, C.c_float, _ip, _fp]),
     ("f9_dev_latency_stats_batch", _i, [_vp, C.POINTER(DevBuffer), _i, C.c_float, _vp, _vp, _vp]),
     ("f9_dev_stats_batch", _i, [_vp, C.POINTER(DevBuffer), _i, _vp, _vp]),
     ("f9_resample_plan_create", _i, [_vp, _i, _d, C.POINTER(ResampleSeg), _i, C.POINTER(_vp)]),

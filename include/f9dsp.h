@@ -111,6 +111,10 @@ F9_API int f9_find_peak_position(f9_context* ctx, const float* const* ch, int nu
                                  float threshold, int* out_pos);
 /* Swift analyzeCapturedAudio, LatencyMeasurementService.swift:147-171 (interleaved index, default 0;
  * *out_found = 0 where Swift throws noImpulseDetected). */
+/* The two calls of the latency measurement (Source/MainComponent.cpp:266-284) as one: findPeakPosition(buffer, threshold) and
+ * calculateNoiseFloorDb(buffer) from one upload and one read of the capture. */
+F9_API int f9_measure_latency(f9_context* ctx, const float* const* ch, int numCh, int numFrames, float threshold,
+                              int* out_pos, float* out_noise_floor_db);
 F9_API int f9_find_peak_interleaved(f9_context* ctx, const float* audio, long long n, float threshold,
                                     long long* out_index, int* out_found);
 /* MainComponent::calculateRMS, Source/MainComponent.cpp:983-1004. */

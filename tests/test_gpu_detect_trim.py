@@ -219,6 +219,14 @@ def test_latency_stats_one_pass(ctx, O, f9):
     ctx._check(f9.lib().f9_dev_find_peak_batch(ctx.handle, bufs, n, 0.1, pos2.data_ptr()))
     ctx.synchronize()
     pos, pos2, sumsq, peak = pos.cpu().numpy(), pos2.cpu().numpy(), sumsq.cpu().numpy(), peak.cpu().numpy()
+    fpp = C.POINTER(C.c_float)
+    for x in caps:                                                     # the host-level form: one upload, one read
+        rows = [np.ascontiguousarray(r) for r in x]
+        chans = (fpp * len(rows))(*[r.ctypes.data_as(fpp) for r in rows])
+        p1, nf = C.c_int(-7), C.c_float(0.0)
+        ctx._check(f9.lib().f9_measure_latency(ctx.handle, chans, x.shape[0], x.shape[1], 0.1, C.byref(p1), C.byref(nf)))
+        assert p1.value == O.find_peak_position(x, 0.1)
+        assert abs(nf.value - float(O.noise_floor_db(x))) <= 1e-4
     for i, x in enumerate(caps):
         assert pos[i] == pos2[i] == O.find_peak_position(x, 0.1), i
         assert peak[i] == np.max(np.abs(x))
