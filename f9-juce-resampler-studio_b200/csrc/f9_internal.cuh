@@ -315,7 +315,7 @@ struct f9_context {
     unsigned sinc_epoch = 0;            // bumped by f9_sinc_table_set
 
     struct PolyKey { int kind; long long p, q; unsigned epoch; bool operator<(const PolyKey& o) const {
-        if (kind != o.kind) return kind < o.kind; if (p != o.p) return p < o.p; if (q != o.q) return q < o.q; return epoch < o.epoch; } };
+        return std::tie(kind, p, q, epoch) < std::tie(o.kind, o.p, o.q, o.epoch); } };
     std::map<PolyKey, f9::PolyDev> poly_cache;
     struct BandKey { int kind; long long p, q; int TK, Gpad; unsigned epoch; bool operator<(const BandKey& o) const {
         return std::tie(kind, p, q, TK, Gpad, epoch) < std::tie(o.kind, o.p, o.q, o.TK, o.Gpad, o.epoch); } };

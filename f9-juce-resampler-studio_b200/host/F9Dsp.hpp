@@ -183,7 +183,7 @@ private:
 // ---- the MainComponent helper set (Source/MainComponent.h:186-237), GPU backed ---------------------------
 class BatchDsp {
 public:
-    BatchDsp(Context& c, ProcessingSettings& s) : ctx_(c), settings(s) {}
+    BatchDsp(Context& c, ProcessingSettings& s) : settings(s), ctx_(c) {}
 
     /** MainComponent::trimLatency: latencySamples interleaved, originalLength frames; zero padded. */
     AudioBuffer trimLatency(const AudioBufferView& captured, int latencySamples, int originalLength) {
