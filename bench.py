@@ -148,7 +148,29 @@ def run_reference(args, rank: int, world: int):
                              "sample": f"{files} of {batch.files} files per step (tail scan + trimLatency + WindowedSinc), oracle port, g++ -O2 -ffp-contract=off"},
             "e2e": {"value": v, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+# The driver reads ONE JSON line from stdout.  Libraries write there too (NCCL prints its version banner on stdout at
+# NCCL_DEBUG=VERSION and WARN alike), so file descriptor 1 is pointed at stderr for the life of the process and the line goes
+# out through a private duplicate of the original stdout.
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one umma_fir_kernel launch (ncu --set full, profiles/), by files per GPU
@@ -397,7 +419,7 @@ def run_gpu(args, rank: int, local_rank: int, world: int):
             n, dt = cpu_leg(batch, 0, args.ref_files, cores)
             line["cpu_baseline"] = {"value": n / dt / 1e6, "unit": "Msamples/s", "cores": cores, "kind": "port",
                                     "sample": f"{args.ref_files} of {batch.files} files (tail scan + trimLatency + WindowedSinc), oracle port, {dt:.1f} s"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     for p in plans.values():
         L.f9_plan_destroy(p)
     ctx.close()
@@ -424,6 +446,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    if not args.kernel_only:
+        claim_stdout()
     if args.impl == "reference":
         run_reference(args, rank, world)
     else:
