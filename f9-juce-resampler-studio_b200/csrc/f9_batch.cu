@@ -190,6 +190,7 @@ int run_chunk(f9_context* ctx, const f9_job* jobs, f9_result* results, const std
             F9_TRY_CUDA(ctx, cudaMemcpyAsync(d_p, h_p, sizeof(int) * prefix.size(), cudaMemcpyHostToDevice, s));
             L.d_segs = d_s; L.d_tile_prefix = d_p; L.n_segs = (int) segs.size(); L.n_tiles = prefix.back();
             if (const size_t sb = resample_scratch_bytes(L, L.n_tiles)) L.d_tile_recs = (UmmaTileRec*) ctx->d_alloc(sb);
+            if (resample_needs_ovf(L)) L.d_ovf = (unsigned*) ctx->d_alloc(sizeof(unsigned));
             F9_TRY_CUDA(ctx, launch_resample(L, s, &ctx->launches));
         }
     }
@@ -235,10 +236,9 @@ extern "C" int f9_process_batch(f9_context* ctx, const f9_job* jobs, int n_jobs,
     F9_TRY_CUDA(ctx, cudaMemGetInfo(&freeB, &totalB));
     // Chunks are pipelined over two slots: while chunk k's kernels and downloads run on one stream, chunk k+1 uploads on
     // the other (PCIe is full duplex and the copy engines are independent), so a large batch costs about
-    // max(upload, download) instead of their sum.  A chunk is ~F9_BATCH_CHUNK_MB of device memory (default 64: measured best on B200 / PCIe 5,
+    // max(upload, download) instead of their sum.  A chunk is ~64 MB of device memory (option F9_BATCH_CHUNK_MB; measured best on B200 / PCIe 5,
     // 48 ms against 60 ms unpipelined for 2.1 GB up + 0.9 GB down; smaller chunks pay the per-chunk synchronisation).
-    size_t chunkMB = 64;
-    if (const char* e = getenv("F9_BATCH_CHUNK_MB")) chunkMB = (size_t) std::max(1, atoi(e));
+    const size_t chunkMB = (size_t) std::max(1, ctx->diag.get("F9_BATCH_CHUNK_MB", 64));
     const size_t budget = std::min(std::max<size_t>((freeB + ctx->d_cap + ctx->parked.d_cap) / 4, 64u << 20), chunkMB << 20);
     if (!ctx->alt_stream) {
         F9_TRY_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->alt_stream, cudaStreamNonBlocking));

@@ -86,8 +86,9 @@ int f9_context_create(int device, f9_context** out) {
     cudaDeviceProp prop;
     e = cudaGetDeviceProperties(&prop, device);
     if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); return F9_ERR_CUDA; }
-    if (prop.major < 10) {
-        g_create_error = "device is not sm_100 class: this library carries sm_100a code only";
+    if (prop.major != 10 || prop.minor != 0) {
+        // sm_100a SASS is architecture-specific: it loads on compute capability 10.0 only (not on 10.3 or 12.x)
+        g_create_error = "device is not compute capability 10.0 (B200): this library carries sm_100a code only";
         return F9_ERR_NO_DEVICE;
     }
     f9_context* ctx = new (std::nothrow) f9_context();
@@ -117,10 +118,10 @@ void f9_context_destroy(f9_context* ctx) {
     for (auto& kv : ctx->band_cache) { cudaFree(kv.second.C); cudaFree(kv.second.wmin); }
     for (auto& kv : ctx->umma_cache) cudaFree((void*) kv.second.W);
     for (auto& kv : ctx->hankel_cache) cudaFree((void*) kv.second.W);
-    if (ctx->d_ovf) cudaFree(ctx->d_ovf);
     if (ctx->d_sinc_table) cudaFree(ctx->d_sinc_table);
     if (ctx->cur_slot) ctx->swap_slot();
     if (ctx->alt_stream) { cudaStreamSynchronize(ctx->alt_stream); cudaStreamDestroy(ctx->alt_stream); }
+    ctx->arena_reset(); ctx->swap_slot(); ctx->arena_reset(); ctx->swap_slot();      // frees both slots' spill allocations
     if (ctx->parked.d_arena) cudaFree(ctx->parked.d_arena);
     if (ctx->parked.h_arena) cudaFreeHost(ctx->parked.h_arena);
     if (ctx->d_arena) cudaFree(ctx->d_arena);
@@ -133,7 +134,23 @@ const char* f9_last_error(const f9_context* ctx) { return ctx ? ctx->err.c_str()
 
 int f9_set_stream(f9_context* ctx, void* cuda_stream) {
     if (!ctx) return F9_ERR_INVALID;
-    ctx->stream = cuda_stream ? (cudaStream_t) cuda_stream : ctx->own_stream;
+    cudaStream_t next = cuda_stream ? (cudaStream_t) cuda_stream : ctx->own_stream;
+    if (next == ctx->stream) return F9_OK;
+    // The arenas (descriptors, tile prefixes, partial sums) are ordered against the stream that was current when they were
+    // carved: work still in flight there must finish before a call on the new stream resets and overwrites them.
+    F9_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->quiescent) { F9_TRY_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); ctx->quiescent = true; }
+    ctx->stream = next;
+    return F9_OK;
+}
+int f9_context_set_option(f9_context* ctx, const char* name, int value) {
+    if (!ctx || !name) return F9_ERR_INVALID;
+    ctx->diag.m[name] = value;
+    return F9_OK;
+}
+int f9_context_clear_options(f9_context* ctx) {
+    if (!ctx) return F9_ERR_INVALID;
+    ctx->diag.m.clear();
     return F9_OK;
 }
 int f9_synchronize(f9_context* ctx) {
@@ -267,7 +284,7 @@ int f9_measure_latency(f9_context* ctx, const float* const* ch, int numCh, int n
     double* d_psum = (double*) ctx->d_alloc(sizeof(double) * (size_t) total);
     double* d_res = (double*) ctx->d_alloc(2 * sizeof(double));              // [0] sum of squares, [1] (as int) position
     int* d_pos = reinterpret_cast<int*>(d_res + 1);
-    F9_TRY_CUDA(ctx, launch_find_peak(d_bufs, 1, total, d_prefix, threshold, d_part, d_pos, ctx->stream, &ctx->launches, d_psum, d_res, nullptr));
+    F9_TRY_CUDA(ctx, launch_find_peak(d_bufs, 1, total, d_prefix, threshold, d_part, d_pos, ctx->stream, &ctx->launches, d_psum, d_res, nullptr, ctx->diag.get("F9_RMS_FORCE_ORDER")));
     double* h_res = (double*) ctx->h_alloc(2 * sizeof(double));
     F9_TRY_CUDA(ctx, cudaMemcpyAsync(h_res, d_res, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     F9_FINISH(ctx);
@@ -304,7 +321,7 @@ static int stats_one(f9_context* ctx, const float* const* ch, int numCh, int num
     float* d_pmax = (float*) ctx->d_alloc(sizeof(float) * kStatPartialsPerBuf);
     double* d_sum = (double*) ctx->d_alloc(sizeof(double));
     float* d_peak = (float*) ctx->d_alloc(sizeof(float));
-    F9_TRY_CUDA(ctx, launch_stats(d_bufs, 1, d_psum, d_pmax, d_sum, d_peak, ctx->stream, &ctx->launches));
+    F9_TRY_CUDA(ctx, launch_stats(d_bufs, 1, d_psum, d_pmax, d_sum, d_peak, ctx->stream, &ctx->launches, ctx->diag.get("F9_RMS_FORCE_ORDER")));
     double* h_sum = (double*) ctx->h_alloc(sizeof(double));
     float* h_peak = (float*) ctx->h_alloc(sizeof(float));
     F9_TRY_CUDA(ctx, cudaMemcpyAsync(h_sum, d_sum, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -459,6 +476,92 @@ int f9_remove_dc_offset(f9_context* ctx, float* const* ch, int numCh, int numFra
     return F9_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ stimuli
+// MainComponent::generateImpulse, Source/MainComponent.cpp:934-945: buffer.clear(), 0.9 on sample 0 of every channel.
+int f9_generate_impulse(f9_context* ctx, float* const* ch, int numCh, int numFrames) {
+    int rc = check_planar(ctx, ch, numCh, numFrames); if (rc) return rc;
+    if (numCh == 0 || numFrames == 0) return F9_OK;
+    rc = ctx->arena_reserve(planar_bytes(numCh, numFrames) + 16384, 4096); if (rc) return rc;
+    const long long stride = pad_stride(numFrames);
+    DevBuf hb{(float*) ctx->d_alloc(sizeof(float) * (size_t) stride * numCh), stride, numCh, numFrames};
+    DevBuf* d_b;
+    rc = upload_array(ctx, &hb, 1, &d_b); if (rc) return rc;
+    F9_TRY_CUDA(ctx, launch_impulse(d_b, 1, numCh, numFrames, 0.9f, ctx->stream, &ctx->launches));
+    for (int c = 0; c < numCh; ++c)
+        F9_TRY_CUDA(ctx, cudaMemcpyAsync(ch[c], hb.base + c * stride, sizeof(float) * (size_t) numFrames, cudaMemcpyDeviceToHost, ctx->stream));
+    F9_FINISH(ctx);
+    return F9_OK;
+}
+int f9_dev_generate_impulse(f9_context* ctx, const f9_dev_buffer* bufs, int n) {
+    if (!ctx || n < 0 || (n > 0 && !bufs)) return F9_ERR_INVALID;
+    if (n == 0) return F9_OK;
+    F9_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    const DevBuf* hb = reinterpret_cast<const DevBuf*>(bufs);
+    int maxCh = 0, maxFrames = 0;
+    for (int i = 0; i < n; ++i) {
+        if (hb[i].numCh < 0 || hb[i].numFrames < 0 || (hb[i].numCh > 0 && hb[i].numFrames > 0 && !hb[i].base)) return ctx->fail(F9_ERR_INVALID, "bad buffer");
+        maxCh = std::max(maxCh, hb[i].numCh); maxFrames = std::max(maxFrames, hb[i].numFrames);
+    }
+    int rc = ctx->arena_reserve(sizeof(DevBuf) * (size_t) n + 8192, sizeof(DevBuf) * (size_t) n + 8192, true); if (rc) return rc;
+    DevBuf* d_b;
+    rc = upload_array(ctx, hb, (size_t) n, &d_b); if (rc) return rc;
+    F9_TRY_CUDA(ctx, launch_impulse(d_b, n, maxCh, maxFrames, 0.9f, ctx->stream, &ctx->launches));
+    return F9_OK;
+}
+
+// MainComponent::generateSineWave, Source/MainComponent.cpp:907-932 (callback_form: the audio callback's variant :141-167, whose
+// sinePhase is the chain's own end value instead of the closed-form update of :929-931).
+int f9_generate_sine_wave(f9_context* ctx, float* const* ch, int numCh, int numSamples, float frequency, float sample_rate,
+                          float amplitude, float* phase_io, int callback_form) {
+    int rc = check_planar(ctx, ch, numCh, numSamples); if (rc) return rc;
+    if (!phase_io || !(sample_rate > 0.0f)) return ctx->fail(F9_ERR_INVALID, "bad sine arguments");
+    const float inc = sine_phase_increment(frequency, sample_rate);
+    if (numSamples == 0 || (numCh == 0 && !callback_form)) { if (!callback_form) *phase_io = sine_phase_after_block(*phase_io, inc, numSamples); return F9_OK; }
+    rc = ctx->arena_reserve(planar_bytes(numCh, numSamples) + sizeof(float) * ((size_t) numSamples + 1) + 16384, 4096); if (rc) return rc;
+    const long long stride = pad_stride(numSamples);
+    DevBuf hb{(float*) ctx->d_alloc(sizeof(float) * (size_t) stride * std::max(numCh, 1)), stride, numCh, numSamples};
+    float* d_ph = (float*) ctx->d_alloc(sizeof(float) * ((size_t) numSamples + 1));
+    F9_TRY_CUDA(ctx, launch_sine(hb, *phase_io, inc, amplitude, numSamples, d_ph, ctx->stream, &ctx->launches));
+    for (int c = 0; c < numCh; ++c)
+        F9_TRY_CUDA(ctx, cudaMemcpyAsync(ch[c], hb.base + c * stride, sizeof(float) * (size_t) numSamples, cudaMemcpyDeviceToHost, ctx->stream));
+    float* h_end = (float*) ctx->h_alloc(sizeof(float));
+    F9_TRY_CUDA(ctx, cudaMemcpyAsync(h_end, d_ph + numSamples, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    F9_FINISH(ctx);
+    *phase_io = callback_form ? *h_end : sine_phase_after_block(*phase_io, inc, numSamples);
+    return F9_OK;
+}
+int f9_dev_generate_sine_wave(f9_context* ctx, const f9_dev_buffer* buf, float frequency, float sample_rate, float amplitude, float phase0) {
+    if (!ctx || !buf || !(sample_rate > 0.0f) || buf->numCh < 0 || buf->numFrames < 0) return F9_ERR_INVALID;
+    if (buf->numCh == 0 || buf->numFrames == 0) return F9_OK;
+    F9_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = ctx->arena_reserve(sizeof(float) * ((size_t) buf->numFrames + 1) + 8192, 4096, true); if (rc) return rc;
+    float* d_ph = (float*) ctx->d_alloc(sizeof(float) * ((size_t) buf->numFrames + 1));
+    const DevBuf hb = *reinterpret_cast<const DevBuf*>(buf);
+    F9_TRY_CUDA(ctx, launch_sine(hb, phase0, sine_phase_increment(frequency, sample_rate), amplitude, buf->numFrames, d_ph, ctx->stream, &ctx->launches));
+    return F9_OK;
+}
+// Swift SineWaveGenerator.generateSineWave, SineWaveGenerator.swift:35-59: double phase, interleaved, one sample per frame on every channel.
+int f9_generate_sine_wave_swift(f9_context* ctx, float* buffer, int frame_count, int channel_count, double frequency, double sample_rate,
+                                float amplitude, double* phase_io) {
+    if (!ctx) return F9_ERR_INVALID;
+    if (frame_count < 0 || channel_count < 0 || !phase_io || !(sample_rate > 0.0) || (frame_count > 0 && channel_count > 0 && !buffer))
+        return ctx->fail(F9_ERR_INVALID, "bad sine arguments");
+    if (frame_count == 0) return F9_OK;
+    F9_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t outBytes = sizeof(float) * (size_t) frame_count * std::max(channel_count, 1);
+    int rc = ctx->arena_reserve(outBytes + sizeof(double) * ((size_t) frame_count + 1) + 16384, 4096); if (rc) return rc;
+    float* d_out = (float*) ctx->d_alloc(outBytes);
+    double* d_ph = (double*) ctx->d_alloc(sizeof(double) * ((size_t) frame_count + 1));
+    const double inc = 2.0 * 3.14159265358979323846 * frequency / sample_rate;
+    F9_TRY_CUDA(ctx, launch_sine_swift(d_out, channel_count, *phase_io, inc, amplitude, frame_count, d_ph, ctx->stream, &ctx->launches));
+    if (channel_count > 0) F9_TRY_CUDA(ctx, cudaMemcpyAsync(buffer, d_out, outBytes, cudaMemcpyDeviceToHost, ctx->stream));
+    double* h_end = (double*) ctx->h_alloc(sizeof(double));
+    F9_TRY_CUDA(ctx, cudaMemcpyAsync(h_end, d_ph + frame_count, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    F9_FINISH(ctx);
+    *phase_io = *h_end;
+    return F9_OK;
+}
+
 int f9_xcorr_peak(f9_context* ctx, const float* const* y, int numCh, int numFrames, const float* x, int stim_len,
                   int lag_min, int lag_max, float threshold, int* out_found, int* out_lag, int* out_ch, double* out_value) {
     int rc = check_planar(ctx, y, numCh, numFrames); if (rc) return rc;
@@ -509,7 +612,7 @@ struct f9_plan {
     f9_context* ctx = nullptr;
     ResampleLaunch L;
     Seg* d_segs = nullptr;
-    int* d_prefix = nullptr;
+    int* d_prefix = nullptr;           // n_segs + 1 tile counts, then the plan's own overflow flag
     void* d_scratch = nullptr;
 };
 
@@ -543,6 +646,7 @@ int interp_run(f9_interp* h, double ratio, const float* lin, int n_used, float* 
     rc = upload_array(ctx, &seg, 1, &d_seg); if (rc) return rc;
     rc = upload_array(ctx, prefix.data(), prefix.size(), &d_prefix); if (rc) return rc;
     L.d_segs = d_seg; L.d_tile_prefix = d_prefix; L.n_segs = 1; L.n_tiles = tiles;
+    if (resample_needs_ovf(L)) L.d_ovf = (unsigned*) ctx->d_alloc(sizeof(unsigned));
     L.adding = adding ? 1 : 0; L.gain = gain;
     F9_TRY_CUDA(ctx, launch_resample(L, ctx->stream, &ctx->launches));
     F9_TRY_CUDA(ctx, cudaMemcpyAsync(out, d_out, sizeof(float) * (size_t) num_out, cudaMemcpyDeviceToHost, ctx->stream));
@@ -680,7 +784,7 @@ int f9_dev_latency_stats_batch(f9_context* ctx, const f9_dev_buffer* bufs, int n
     rc = upload_array(ctx, prefix.data(), prefix.size(), &d_prefix); if (rc) return rc;
     PeakPartial* d_part = (PeakPartial*) ctx->d_alloc(sizeof(PeakPartial) * (size_t) std::max(total, 1));
     double* d_psum = (double*) ctx->d_alloc(sizeof(double) * (size_t) std::max(total, 1));
-    F9_TRY_CUDA(ctx, launch_find_peak(d_b, n, total, d_prefix, threshold, d_part, d_out_pos, ctx->stream, &ctx->launches, d_psum, d_sumsq, d_peak));
+    F9_TRY_CUDA(ctx, launch_find_peak(d_b, n, total, d_prefix, threshold, d_part, d_out_pos, ctx->stream, &ctx->launches, d_psum, d_sumsq, d_peak, ctx->diag.get("F9_RMS_FORCE_ORDER")));
     return F9_OK;
 }
 
@@ -695,7 +799,7 @@ int f9_dev_stats_batch(f9_context* ctx, const f9_dev_buffer* bufs, int n, double
     rc = upload_array(ctx, hb, (size_t) n, &d_b); if (rc) return rc;
     double* d_psum = (double*) ctx->d_alloc(sizeof(double) * kStatPartialsPerBuf * (size_t) n);
     float* d_pmax = (float*) ctx->d_alloc(sizeof(float) * kStatPartialsPerBuf * (size_t) n);
-    F9_TRY_CUDA(ctx, launch_stats(d_b, n, d_psum, d_pmax, d_sumsq, d_peak, ctx->stream, &ctx->launches));
+    F9_TRY_CUDA(ctx, launch_stats(d_b, n, d_psum, d_pmax, d_sumsq, d_peak, ctx->stream, &ctx->launches, ctx->diag.get("F9_RMS_FORCE_ORDER")));
     return F9_OK;
 }
 
@@ -784,13 +888,14 @@ int f9_resample_plan_create(f9_context* ctx, int kind, double speed_ratio, const
     if (tiles < 0) { delete P; return ctx->fail(F9_ERR_INVALID, "too many tiles"); }
     cudaError_t e;
     if ((e = cudaMalloc((void**) &P->d_segs, sizeof(Seg) * (size_t) std::max(n_segs, 1))) != cudaSuccess ||
-        (e = cudaMalloc((void**) &P->d_prefix, sizeof(int) * (size_t) (n_segs + 1))) != cudaSuccess ||
+        (e = cudaMalloc((void**) &P->d_prefix, sizeof(int) * (size_t) (n_segs + 2))) != cudaSuccess ||
         (n_segs > 0 && (e = cudaMemcpy(P->d_segs, hs, sizeof(Seg) * (size_t) n_segs, cudaMemcpyHostToDevice)) != cudaSuccess) ||
         (e = cudaMemcpy(P->d_prefix, prefix.data(), sizeof(int) * (size_t) (n_segs + 1), cudaMemcpyHostToDevice)) != cudaSuccess) {
         f9_plan_destroy(P);
         return ctx->fail_cuda(e, "plan upload");
     }
     P->L.d_segs = P->d_segs; P->L.d_tile_prefix = P->d_prefix; P->L.n_segs = n_segs; P->L.n_tiles = tiles;
+    P->L.d_ovf = reinterpret_cast<unsigned*>(P->d_prefix + (n_segs + 1));
     if (const size_t sb = resample_scratch_bytes(P->L, tiles)) {
         if ((e = cudaMalloc(&P->d_scratch, sb)) != cudaSuccess) { f9_plan_destroy(P); return ctx->fail_cuda(e, "plan scratch"); }
         P->L.d_tile_recs = (UmmaTileRec*) P->d_scratch;

@@ -434,7 +434,11 @@ cudaError_t launch_hankel(const ResampleLaunch& L, cudaStream_t s, long long* la
         ++*launches;
     }
     const int grid = std::min(L.n_tiles, L.sm_count);
-    const int dbg = getenv("F9_HK_DBG") ? atoi(getenv("F9_HK_DBG")) : 0;      // development: 1 skip MMAs, 2 skip loads + conversion, 4 skip stores
+#ifdef F9_DIAG
+    const int dbg = getenv("F9_HK_DBG") ? atoi(getenv("F9_HK_DBG")) : 0;      // -DF9_DIAG builds: 1 skip MMAs, 2 skip loads + conversion, 4 skip stores
+#else
+    const int dbg = 0;
+#endif
     #define F9_HK_LAUNCH(ks_, lo_, hi_) do { \
         if (L.hk.KS != ks_ || L.hk.cLo != lo_ || L.hk.cHi != hi_) return cudaErrorInvalidValue; \
         if ((e = cudaFuncSetAttribute(hankel_fir_kernel<ks_, lo_, hi_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)) != cudaSuccess) return e; \

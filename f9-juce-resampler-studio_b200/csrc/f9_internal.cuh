@@ -16,6 +16,15 @@
 
 namespace f9 {
 
+// Variant switches for tests and development (f9_context_set_option): which kernel generation / feed a plan takes.  They are
+// per-context values set through the API; the library never reads the environment (a -DF9_DIAG build adds the in-kernel
+// ablation / cycle-accounting switches, read from F9_UMMA_DBG, F9_UMMA_PROF, F9_HK_DBG).
+struct DiagOpts {
+    std::map<std::string, int> m;
+    bool has(const char* k) const { return m.find(k) != m.end(); }
+    int  get(const char* k, int dflt = 0) const { auto it = m.find(k); return it == m.end() ? dflt : it->second; }
+};
+
 // ----------------------------------------------------------------------------- tables (host, f9_tables.cpp)
 constexpr int kSincTableSize = 10001;
 constexpr int kSincTaps = 200;       // WindowedSinc memory (taps i = -100 .. 99 contribute)
@@ -45,6 +54,8 @@ float largest_peak_below(float thrDb, int* below0);
 float noise_floor_db_from_rms(float rms);
 float nf_threshold_db(int has_nf, float nf_db, float margin_pct);
 float threshold_linear(float db);
+float sine_phase_increment(float frequency, float sample_rate);
+float sine_phase_after_block(float phase, float inc, int num_samples);
 int   run_position_chain(double* pos_io, double ratio, int num_out);
 void  position_closed_form(double pos0, double ratio, long long n, long long* c, double* frac_out);
 
@@ -74,10 +85,10 @@ int         peak_prefix(const DevBuf* h_bufs, int n, std::vector<int>* prefix); 
 cudaError_t launch_find_peak(const DevBuf* d_bufs, int n, int total_ctas, const int* d_prefix, float threshold,
                              PeakPartial* d_partials /* total_ctas */, int* d_out_pos, cudaStream_t s, long long* launches,
                              double* d_psum = nullptr /* total_ctas: the same pass sums the squares */, double* d_sumsq = nullptr,
-                             float* d_peakv = nullptr);
+                             float* d_peakv = nullptr, int forceOrder = 0 /* always re-sum in the reference's order (tests) */);
 
 cudaError_t launch_stats(const DevBuf* d_bufs, int n, double* d_psum, float* d_pmax /* n*kStatPartialsPerBuf each */,
-                         double* d_sumsq, float* d_peak, cudaStream_t s, long long* launches);
+                         double* d_sumsq, float* d_peak, cudaStream_t s, long long* launches, int forceOrder = 0);
 
 cudaError_t launch_tail_scan(const DevBuf* d_bufs, const TailParams* d_params, int n, int max_polls,
                              long long* d_stop, int* d_flags /* n*max_polls, required */, cudaStream_t s, long long* launches);
@@ -105,6 +116,13 @@ cudaError_t launch_interleave(const float* d_src, long long srcStride, int numCh
                               cudaStream_t s, long long* launches);
 cudaError_t launch_deinterleave(const float* d_src, int numCh, long long frames, float* d_dst, long long dstStride,
                                 cudaStream_t s, long long* launches);
+
+// stimuli (f9_stimulus.cu): generateImpulse / generateSineWave
+cudaError_t launch_impulse(const DevBuf* d_bufs /* writable */, int n, int maxCh, int maxFrames, float amplitude, cudaStream_t s, long long* launches);
+cudaError_t launch_sine(const DevBuf& buf /* writable */, float phase0, float inc, float amplitude, int n, float* d_phases /* n + 1 */,
+                        cudaStream_t s, long long* launches);
+cudaError_t launch_sine_swift(float* d_out, int channels, double phase0, double inc, float amplitude, int frames, double* d_phases /* frames + 1 */,
+                              cudaStream_t s, long long* launches);
 
 // resampling ---------------------------------------------------------------
 struct PolyDev {                   // device copy of PolyHost
@@ -224,8 +242,8 @@ struct alignas(16) UmmaTileRec {
     int x0, mapIdx;                    // box coordinate / tensor map of stage 0; mapIdx < 0: the tile does not go through TMA
     int mask, pad;                     // mask: the boxes leave the window [0, inAvail): zero what lies outside after the load
 };
-bool umma_encode_maps(const Seg* segs, int n, int p, UmmaTma* out);
-void umma_choose_plan(int taps, long long p, long long q, long long* m_out, int* NB_out, int* GBL_out);
+bool umma_encode_maps(const Seg* segs, int n, int p, UmmaTma* out, bool noRanges = false);
+void umma_choose_plan(int taps, long long p, long long q, long long* m_out, int* NB_out, int* GBL_out, int forceNB = 0);
 double umma_cost_per_output(int taps, long long p, long long q, int NB, int GBL, size_t* smem2);   // model used to pick the plan
 
 // Hankel-operand FIR for integer upsampling 1:L (f9_hankel.cu): device weight image + geometry
@@ -245,6 +263,7 @@ int hankel_tile_elems(int L, int KS);
 
 struct ResampleLaunch {
     int kind = 0;
+    const DiagOpts* diag = nullptr;   // the context's variant switches (never null after prepare_resample)
     bool hankel = false;           // integer upsampling on the Hankel-operand kernel (takes priority)
     HankelDev hk;
     // tensor-core path (takes priority over banded when set; never used with adding)
@@ -258,7 +277,9 @@ struct ResampleLaunch {
     UmmaTileRec* d_tile_recs = nullptr;    // n_tiles records, caller-provided scratch when um_tma (see resample_scratch_bytes)
     bool recs_ready = false;       // the tile records in d_tile_recs are those of this launch's segments already (a plan's second run): skip the table kernel
     cudaStream_t recs_stream = nullptr;   // ... written on this stream (another stream rebuilds them: no ordering between the two)
-    unsigned* d_ovf = nullptr;     // device flag: an input sample was outside the fp16 split's range -> fp32 redo
+    unsigned* d_ovf = nullptr;     // device flag: an input sample was outside the fp16 split's range -> fp32 redo.  One per launch
+                                   // (the caller carves it next to the segment table: arena for transient launches, the plan's own
+                                   // allocation for plans), so launches on different streams never share a flag
     // banded (register-tiled) path
     bool banded = false;
     BandedDev band;
@@ -294,6 +315,7 @@ inline size_t resample_scratch_bytes(const ResampleLaunch& L, int n_tiles) {
     if (L.short_S > 0) return kShortTileRecBytes * ((size_t) n_tiles + 1);
     return L.umma && L.um_tma ? sizeof(UmmaTileRec) * ((size_t) n_tiles + 1) : 0;
 }
+inline bool resample_needs_ovf(const ResampleLaunch& L) { return L.hankel || L.umma; }
 
 }  // namespace f9
 
@@ -305,6 +327,7 @@ struct f9_context {
     cudaStream_t stream = nullptr;
     std::string err;
     long long launches = 0;
+    f9::DiagOpts diag;                  // f9_context_set_option
 
     // bump arenas, reset at the start of every blocking call
     char* d_arena = nullptr;  size_t d_cap = 0, d_used = 0;
@@ -327,7 +350,6 @@ struct f9_context {
     std::map<std::tuple<int, int, unsigned>, f9::HankelDev> hankel_cache;      // (kind, L, sinc epoch)
     int   get_hankel(int kind, int L, f9::HankelDev* out);
     int   get_umma(int kind, long long p, long long q, int NB, int GBL, f9::UmmaDev* out);
-    unsigned* d_ovf = nullptr;          // see ResampleLaunch::d_ovf (two flags: one per pipeline slot)
     // Choose kernel + tables for (kind, ratio, pos0); fills everything in L except the segment table.
     int   prepare_resample(int kind, double ratio, double pos0, bool allow_rational, f9::ResampleLaunch* L);
 
@@ -339,18 +361,39 @@ struct f9_context {
     // f9_process_batch pipelines chunks over two slots (arena + stream each) so that the upload of chunk k+1 overlaps the
     // kernels and the download of chunk k; swap_slot() exchanges the current arena / stream with the parked one.
     struct ParkedSlot { char* d_arena = nullptr; size_t d_cap = 0, d_used = 0; char* h_arena = nullptr; size_t h_cap = 0, h_used = 0;
-                        cudaStream_t stream = nullptr; bool quiescent = true; } parked;
+                        cudaStream_t stream = nullptr; bool quiescent = true; std::vector<void*> d_spill, h_spill; } parked;
     cudaStream_t alt_stream = nullptr;  // owned; the parked slot's stream
     int   cur_slot = 0;
     void  swap_slot() {
         std::swap(d_arena, parked.d_arena); std::swap(d_cap, parked.d_cap); std::swap(d_used, parked.d_used);
         std::swap(h_arena, parked.h_arena); std::swap(h_cap, parked.h_cap); std::swap(h_used, parked.h_used);
         std::swap(stream, parked.stream); std::swap(quiescent, parked.quiescent); cur_slot ^= 1;
+        d_spill.swap(parked.d_spill); h_spill.swap(parked.h_spill);
     }
-    void  arena_reset() { d_used = 0; h_used = 0; }
+    // A request the reserve estimate did not cover never writes past the arena: it is served by its own allocation (slow, counted
+    // in arena_spills for the tests) that lives until the arena is next reset, i.e. until the work that uses it has been waited for.
+    std::vector<void*> d_spill, h_spill; long long arena_spills = 0;
+    void  arena_reset() {
+        d_used = 0; h_used = 0;
+        for (void* p : d_spill) cudaFree(p);
+        for (void* p : h_spill) cudaFreeHost(p);
+        d_spill.clear(); h_spill.clear();
+    }
     int   arena_reserve(size_t d_bytes, size_t h_bytes, bool async_call = false);
-    void* d_alloc(size_t bytes) { size_t o = (d_used + 255) & ~size_t(255); d_used = o + bytes; return d_arena + o; }
-    void* h_alloc(size_t bytes) { size_t o = (h_used + 255) & ~size_t(255); h_used = o + bytes; return h_arena + o; }
+    void* d_alloc(size_t bytes) {
+        const size_t o = (d_used + 255) & ~size_t(255);
+        if (o + bytes <= d_cap) { d_used = o + bytes; return d_arena + o; }
+        void* p = nullptr; ++arena_spills;
+        if (cudaMalloc(&p, bytes > 0 ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        d_spill.push_back(p); return p;
+    }
+    void* h_alloc(size_t bytes) {
+        const size_t o = (h_used + 255) & ~size_t(255);
+        if (o + bytes <= h_cap) { h_used = o + bytes; return h_arena + o; }
+        void* p = nullptr; ++arena_spills;
+        if (cudaHostAlloc(&p, bytes > 0 ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        h_spill.push_back(p); return p;
+    }
     int   get_poly(int kind, long long p, long long q, f9::PolyDev* out);
 };
 

@@ -582,18 +582,20 @@ int resample_build_tiles(ResampleLaunch& L, const Seg* segs, int n, std::vector<
         for (int i = 0; i < n && aligned; ++i)
             if (segs[i].numOut > 0 && ((((long long) (reinterpret_cast<uintptr_t>(segs[i].in) >> 2) - segs[i].inOffset) & 3) != 0 ||
                                        (reinterpret_cast<uintptr_t>(segs[i].in) & 3) != 0)) aligned = false;
-        L.um_aligned = aligned && getenv("F9_UMMA_UNALIGNED") == nullptr;
+        static const DiagOpts kNoDiag;
+        const DiagOpts& D = L.diag ? *L.diag : kNoDiag;
+        L.um_aligned = aligned && !D.has("F9_UMMA_UNALIGNED");
         // TMA feed (aligned rows only): tensor maps over the address range the segments read, ring of raw fp32 boxes
         L.um_tma = false;
-        if (L.um_aligned && getenv("F9_UMMA_NOTMA") == nullptr) {
-            if (umma_encode_maps(segs, n, L.um.p, &L.um_maps)) {
+        if (L.um_aligned && !D.has("F9_UMMA_NOTMA")) {
+            if (umma_encode_maps(segs, n, L.um.p, &L.um_maps, D.has("F9_UMMA_NORANGES"))) {
                 // CTA pairs halve the weights per SM: worth it when the weights leave a single CTA only a shallow input ring
                 // (with several slot blocks only when the TMEM operand ring has four stages: measured slower otherwise, 147/160)
-                const bool cta2 = L.um.blk[0].w2Off[0] >= 0 && L.sm_count >= 2 * L.um.nGB && getenv("F9_UMMA_NOCTA2") == nullptr &&
+                const bool cta2 = L.um.blk[0].w2Off[0] >= 0 && L.sm_count >= 2 * L.um.nGB && !D.has("F9_UMMA_NOCTA2") &&
                                   (L.um.nGB == 1 || L.um.aSlots == 4) &&
-                                  (umma_smem_bytes(L.um.maxEntries, L.um.NB, 4, true) > 227 * 1024 || getenv("F9_UMMA_CTA2") != nullptr);
+                                  (umma_smem_bytes(L.um.maxEntries, L.um.NB, 4, true) > 227 * 1024 || D.has("F9_UMMA_CTA2"));
                 int stages = 2;
-                const int maxStages = getenv("F9_UMMA_STAGES") ? atoi(getenv("F9_UMMA_STAGES")) : 8;
+                const int maxStages = D.get("F9_UMMA_STAGES", 8);
                 while (stages < maxStages && umma_smem_bytes(L.um.maxEntries, L.um.NB, stages + 1, true, cta2) <= 227 * 1024) ++stages;
                 if (umma_smem_bytes(L.um.maxEntries, L.um.NB, stages, true, cta2) <= 227 * 1024) {
                     L.um_tma = true; L.um_cta2 = cta2; L.um_stages = stages; L.um_smem = umma_smem_bytes(L.um.maxEntries, L.um.NB, stages, true, cta2);
@@ -727,7 +729,8 @@ int f9_context::prepare_resample(int kind, double ratio, double pos0, bool allow
     if (interp_memory(kind) == 0) return fail(F9_ERR_INVALID, "unknown interpolator kind");
     if (!(ratio > 0.0) || !std::isfinite(ratio)) return fail(F9_ERR_INVALID, "speed ratio must be positive and finite");
     *L = ResampleLaunch();
-    L->kind = kind; L->ratio = ratio; L->pos0 = pos0;
+    L->kind = kind; L->ratio = ratio; L->pos0 = pos0; L->diag = &diag;
+    const DiagOpts& D = diag;
     L->d_sinc_table = d_sinc_table;
     L->tile_out = choose_tile_out(ratio);
     long long p = 0, q = 0;
@@ -737,23 +740,22 @@ int f9_context::prepare_resample(int kind, double ratio, double pos0, bool allow
         L->sm_count = sm_count;
         // short kinds: bandwidth-bound on CUDA cores with the slot's weights in registers (F9_SHORT_UMMA=1: tensor-core kernel instead)
         // Integer upsampling of the long kinds: Hankel-operand kernel (every input sample staged and converted once)
-        if (p == 1 && (q == 2 || q == 4 || q == 8 || q == 16) && interp_memory(kind) > 5 && getenv("F9_NO_UMMA") == nullptr && getenv("F9_NO_HANKEL") == nullptr) {
-            if (!d_ovf) F9_TRY_CUDA(this, cudaMalloc((void**) &d_ovf, 2 * sizeof(unsigned)));
+        if (p == 1 && (q == 2 || q == 4 || q == 8 || q == 16) && interp_memory(kind) > 5 && !D.has("F9_NO_UMMA") && !D.has("F9_NO_HANKEL")) {
             rc = get_hankel(kind, (int) q, &L->hk); if (rc) return rc;
-            if (hankel_smem_bytes(L->hk) <= 227 * 1024) { L->hankel = true; L->d_ovf = d_ovf + cur_slot; return F9_OK; }
+            if (hankel_smem_bytes(L->hk) <= 227 * 1024) { L->hankel = true; return F9_OK; }
         }
         // Integer decimation (q == 1, p >= 2) stays on the tensor-core kernel when it is enabled: the short kernel's stride-p shared
         // loads conflict p ways there (measured 82 % / 76 % against 93 % / 95 % of the HBM roofline at 2:1 / 4:1); everywhere else
         // the short kernel is as fast or faster (44.1 -> 48 k: 86 % against 66 %; 48 -> 192 k: 84 % against 65 %) and exact fp32.
-        const bool decim = q == 1 && p >= 2 && getenv("F9_NO_UMMA") == nullptr && getenv("F9_SHORT_ALL") == nullptr;
-        if (interp_memory(kind) <= 5 && q <= 256 && p <= 8192 && !decim && getenv("F9_SHORT_UMMA") == nullptr && getenv("F9_NO_SHORT") == nullptr) {
+        const bool decim = q == 1 && p >= 2 && !D.has("F9_NO_UMMA") && !D.has("F9_SHORT_ALL");
+        if (interp_memory(kind) <= 5 && q <= 256 && p <= 8192 && !decim && !D.has("F9_SHORT_UMMA") && !D.has("F9_NO_SHORT")) {
             const int c = (int) std::max(1LL, 256 / q);
             const int S = (int) q * c;
             long long I = (4096 * q + (long long) S * p / 2) / ((long long) S * p);
             I = std::max(2LL, std::min(64LL, I));
-            if (const char* e = getenv("F9_SHORT_I")) I = std::max(1, atoi(e));          // experiments: steps per thread
+            if (D.has("F9_SHORT_I")) I = std::max(1, D.get("F9_SHORT_I"));          // experiments: steps per thread
             const long long stageFloats = (((S * I * p + q - 1) / q + interp_memory(kind) + 8) + 3) / 4 * 4;
-            const int nst = getenv("F9_SHORT_STAGES") ? std::max(2, std::min(4, atoi(getenv("F9_SHORT_STAGES")))) : 3;
+            const int nst = std::max(2, std::min(4, D.get("F9_SHORT_STAGES", 3)));
             const size_t smem = sizeof(float) * (size_t) (nst * stageFloats + (interp_memory(kind) + 1) * L->poly.qpad);
             L->short_stages = nst;
             if (smem <= 200 * 1024) {
@@ -762,23 +764,22 @@ int f9_context::prepare_resample(int kind, double ratio, double pos0, bool allow
                 return F9_OK;
             }
         }
-        if (getenv("F9_NO_UMMA") == nullptr && interp_memory(kind) >= 2) {
+        if (!D.has("F9_NO_UMMA") && interp_memory(kind) >= 2) {
             long long bm = 0; int bGBL = 0, bNB = 0;
-            umma_choose_plan(interp_memory(kind), p, q, &bm, &bNB, &bGBL);
+            umma_choose_plan(interp_memory(kind), p, q, &bm, &bNB, &bGBL, D.get("F9_UMMA_NB", 0));
             if (bm > 0) {
-                if (!d_ovf) F9_TRY_CUDA(this, cudaMalloc((void**) &d_ovf, 2 * sizeof(unsigned)));
                 rc = get_umma(kind, p * bm, q * bm, bNB, bGBL, &L->um);
                 if (rc == F9_OK) {
                     int stages = 2;
                     while (stages < 4 && umma_smem_bytes(L->um.maxEntries, L->um.NB, stages + 1) <= 227 * 1024) ++stages;
                     L->um_stages = stages; L->um_smem = umma_smem_bytes(L->um.maxEntries, L->um.NB, stages);
-                    L->d_ovf = d_ovf + cur_slot; L->umma = true;
+                    L->umma = true;
                     return F9_OK;
                 }
                 if (rc != F9_ERR_INVALID) return rc;                                // tables this kernel cannot express: CUDA-core paths
             }
         }
-        if (kind == F9_WINDOWED_SINC && getenv("F9_NO_BANDED") == nullptr) {
+        if (kind == F9_WINDOWED_SINC && !D.has("F9_NO_BANDED")) {
             // scale p/q so a group of slots is at least 16 wide, then choose TK / TA / block shape for shared memory
             long long m = 1;
             while (q * m < 16) m *= 2;
@@ -787,7 +788,7 @@ int f9_context::prepare_resample(int kind, double ratio, double pos0, bool allow
             const size_t budget = 200 * 1024;
             double bestScore = -1.0; int bTK = 0, bTA = 0, bPB = 0, bGB = 0, bnGB = 0, bHalo = 0, bPs = 0; size_t bSmem = 0;
             int fTK = 0, fTA = 0, fnGB = 0;                      // F9_BANDED_CFG="TK,TA,nGB": force a configuration (experiments)
-            if (const char* cfg = getenv("F9_BANDED_CFG")) sscanf(cfg, "%d,%d,%d", &fTK, &fTA, &fnGB);
+            if (D.has("F9_BANDED_TK")) { fTK = D.get("F9_BANDED_TK"); fTA = D.get("F9_BANDED_TA"); fnGB = D.get("F9_BANDED_NGB"); }
             for (int TK : {20, 16, 12, 8}) {
                 if (fTK && TK != fTK) continue;
                 const int G = (int) ((qs + TK - 1) / TK);

@@ -117,10 +117,32 @@ peak_partial_kernel(const DevBuf* __restrict__ bufs, const int* __restrict__ pre
     }
 }
 
+// ---- calculateRMS bit for bit ------------------------------------------------------------------------
+// The reference sums the squares sequentially in double (Source/MainComponent.cpp:985-997); the kernels sum them as a tree.
+// All terms are >= 0, so either order is within (n - 1) 2^-53 relative of the exact sum, the two sums within twice that of each
+// other, and sqrt(sum / n) within about (n + 4) 2^-53.  (float) sqrt(sum / n) -- what calculateRMS returns -- therefore only
+// depends on the order when the double value lies that close to a float rounding boundary: then, and only then, the sum is
+// redone in the reference's order by one thread (a few times in a thousand buffers), and the returned sum of squares is the
+// reference's own double.
+__device__ __forceinline__ bool rms_order_dependent(double s, long long count) {
+    if (!(s != 0.0)) return false;                               // all samples zero: every order gives exactly 0
+    const double r = sqrt(s / (double) count);
+    const double d = (double) (count + 8) * 1.1102230246251565e-16;
+    return (float) (r * (1.0 - d)) != (float) (r * (1.0 + d));   // NaN compares unequal: redone in order, NaN again
+}
+__device__ __noinline__ double sum_squares_in_reference_order(const DevBuf& B) {
+    double ss = 0.0;
+    for (int c = 0; c < B.numCh; ++c) {
+        const float* __restrict__ x = B.base + (long long) c * B.chStride;
+        for (int k = 0; k < B.numFrames; ++k) { const float v = __ldg(x + k); ss = __dadd_rn(ss, (double) __fmul_rn(v, v)); }
+    }
+    return ss;
+}
+
 // ---- stage 2: one CTA per buffer folds its partials in scan order ----------------------------------
 __global__ void __launch_bounds__(128)
 peak_final_kernel(const PeakPartial* __restrict__ partials, const int* __restrict__ prefix, float threshold, int* __restrict__ out_pos,
-                  const double* __restrict__ psum, double* __restrict__ sumsq, float* __restrict__ peakv) {
+                  const double* __restrict__ psum, double* __restrict__ sumsq, float* __restrict__ peakv, const DevBuf* __restrict__ bufs, int forceOrder) {
     const int b = blockIdx.x;
     const int p0 = prefix[b], p1 = prefix[b + 1];
     float bv = 0.0f; int bch = 0x7fffffff, bpos = 0x7fffffff;
@@ -151,14 +173,19 @@ peak_final_kernel(const PeakPartial* __restrict__ partials, const int* __restric
         for (int w = 1; w < (int) blockDim.x / 32; ++w)
             if (peak_better(sv[w], sc[w], sp[w], bv, bch, bpos)) { bv = sv[w]; bch = sc[w]; bpos = sp[w]; }
         out_pos[b] = (bv > threshold && bpos != 0x7fffffff) ? bpos : -1;
-        if (psum) { sumsq[b] = (ssq[0] + ssq[1]) + (ssq[2] + ssq[3]); if (peakv) peakv[b] = bv; }
+        if (psum) {
+            double total = (ssq[0] + ssq[1]) + (ssq[2] + ssq[3]);
+            const DevBuf B = bufs[b];
+            if (forceOrder || rms_order_dependent(total, (long long) B.numCh * B.numFrames)) total = sum_squares_in_reference_order(B);
+            sumsq[b] = total; if (peakv) peakv[b] = bv;
+        }
     }
 }
 
 // ---- per-buffer sum of squares (double) + peak -----------------------------------------------------
 // calculateRMS (Source/MainComponent.cpp:983-1004): float product, widened, double sum.  The tree order here
-// differs from the sequential reference; callers that need the reference's decision bit for bit use the
-// guard band in tail_window_kernel.
+// differs from the sequential reference; the final kernels re-sum in the reference's order exactly when that could
+// change the float the reference returns (rms_order_dependent), so (float) sqrt(sumsq / n) is the reference's value bit for bit.
 constexpr int kStatThreads = 256;
 
 __device__ __forceinline__ void block_sum_max(double& s, float& m, double* sh_s, float* sh_m) {
@@ -227,11 +254,13 @@ stats_partial_kernel(const DevBuf* __restrict__ bufs, double* __restrict__ psum,
     }
 }
 __global__ void stats_final_kernel(const double* __restrict__ psum, const float* __restrict__ pmax, int maxChunks,
-                                   double* __restrict__ sumsq, float* __restrict__ peak, int n) {
+                                   double* __restrict__ sumsq, float* __restrict__ peak, int n, const DevBuf* __restrict__ bufs, int forceOrder) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= n) return;
     double s = 0.0; float m = 0.0f;
     for (int i = 0; i < maxChunks; ++i) { s += psum[(size_t) b * maxChunks + i]; m = fmaxf(m, pmax[(size_t) b * maxChunks + i]); }
+    const DevBuf B = bufs[b];
+    if (forceOrder || rms_order_dependent(s, (long long) B.numCh * B.numFrames)) s = sum_squares_in_reference_order(B);   // see rms_order_dependent
     sumsq[b] = s; peak[b] = m;
 }
 
@@ -424,25 +453,25 @@ int peak_prefix(const DevBuf* h_bufs, int n, std::vector<int>* prefix) {
 
 cudaError_t launch_find_peak(const DevBuf* d_bufs, int n, int total_ctas, const int* d_prefix, float threshold,
                              PeakPartial* d_partials, int* d_out_pos, cudaStream_t s, long long* launches,
-                             double* d_psum, double* d_sumsq, float* d_peakv) {
+                             double* d_psum, double* d_sumsq, float* d_peakv, int forceOrder) {
     if (n <= 0) return cudaSuccess;
     if (total_ctas > 0) {
         if (d_psum) peak_partial_kernel<true><<<total_ctas, kPeakThreads, 0, s>>>(d_bufs, d_prefix, n, d_partials, d_psum);
         else peak_partial_kernel<false><<<total_ctas, kPeakThreads, 0, s>>>(d_bufs, d_prefix, n, d_partials, nullptr);
         ++*launches;
     }
-    peak_final_kernel<<<n, 128, 0, s>>>(d_partials, d_prefix, threshold, d_out_pos, d_psum, d_sumsq, d_peakv);
+    peak_final_kernel<<<n, 128, 0, s>>>(d_partials, d_prefix, threshold, d_out_pos, d_psum, d_sumsq, d_peakv, d_bufs, forceOrder);
     ++*launches;
     return cudaGetLastError();
 }
 
 cudaError_t launch_stats(const DevBuf* d_bufs, int n, double* d_psum, float* d_pmax,
-                         double* d_sumsq, float* d_peak, cudaStream_t s, long long* launches) {
+                         double* d_sumsq, float* d_peak, cudaStream_t s, long long* launches, int forceOrder) {
     if (n <= 0) return cudaSuccess;
     dim3 grid(kStatPartials, n);
     stats_partial_kernel<<<grid, kStatThreads, 0, s>>>(d_bufs, d_psum, d_pmax, kStatPartials);
     ++*launches;
-    stats_final_kernel<<<(n + 127) / 128, 128, 0, s>>>(d_psum, d_pmax, kStatPartials, d_sumsq, d_peak, n);
+    stats_final_kernel<<<(n + 127) / 128, 128, 0, s>>>(d_psum, d_pmax, kStatPartials, d_sumsq, d_peak, n, d_bufs, forceOrder);
     ++*launches;
     return cudaGetLastError();
 }

@@ -188,6 +188,18 @@ float nf_threshold_db(int has_nf, float nf_db, float margin_pct) {              
 }
 float threshold_linear(float db) { return std::pow(10.0f, db / 20.0f); }                             // AppState.h:246-249
 
+// generateSineWave scalars (Source/MainComponent.cpp:910-911, :929-931), float arithmetic as written there
+float sine_phase_increment(float frequency, float sample_rate) {
+    const float pi = 3.14159265358979323846f;                 // juce::MathConstants<float>::pi
+    return (frequency * 2.0f * pi) / sample_rate;
+}
+float sine_phase_after_block(float phase, float inc, int num_samples) {
+    const float twoPi = 2.0f * 3.14159265358979323846f;
+    phase += inc * num_samples;
+    if (phase >= twoPi) phase -= twoPi;
+    return phase;
+}
+
 // GenericInterpolator position recurrence on the host (exact JUCE state): returns inputs consumed.
 int run_position_chain(double* pos_io, double ratio, int num_out) {
     double pos = *pos_io;
@@ -409,13 +421,13 @@ static int umma_pool_plan(long long p, long long q, int taps, int NB, int GBL, i
     return poolN;
 }
 
-void umma_choose_plan(int taps, long long p, long long q, long long* m_out, int* NB_out, int* GBL_out) {
+void umma_choose_plan(int taps, long long p, long long q, long long* m_out, int* NB_out, int* GBL_out, int forceNB) {
     double best = 1e30; *m_out = 0; *NB_out = 0; *GBL_out = 0;
     for (long long m = 1; m * q <= 16LL * kUmmaMaxGroups * kUmmaMaxBlocks && m * p + taps + 48 <= 16 * kUmmaMaxNK; ++m) {
         const long long ps = p * m, qs = q * m;
         if (qs < 48 && (m + 1) * q <= 224) continue;                           // too few slots per period: keep scaling
         for (int NB : {32, 16}) {
-            if (getenv("F9_UMMA_NB") && atoi(getenv("F9_UMMA_NB")) != NB) continue;
+            if (forceNB && forceNB != NB) continue;
             const int G = (int) ((qs + NB - 1) / NB), maxG = std::min(kUmmaMaxGroups, 448 / (2 * NB));
             // a period scaled for alignment (m > 1 of an unaligned p) splits best into blocks of whole original periods: every
             // block then has the window of one period, as the unscaled plan's tiles have

@@ -25,9 +25,11 @@
 // Measured building blocks (tools/ubench/umma_probe.cu, tma_probe.cu, B200): SS MMA M=128 = 32 + N/4 clk, TS MMA = N/2 clk,
 // tcgen05.cp 128x256b = 64 clk, box stream 2.7 / 4.6 TB/s of unique input with a ring of 2 / 8 stages.
 #include <algorithm>
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <mutex>
 #include <vector>
 #include <cuda_fp16.h>
 
@@ -861,10 +863,10 @@ umma_redo_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefi
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 typedef CUresult (*PointerAttrFn)(void*, CUpointer_attribute, CUdeviceptr);
-bool umma_encode_maps(const Seg* segs, int n, int p, UmmaTma* out) {
-    static EncodeTiledFn encode = nullptr; static PointerAttrFn pattr = nullptr; static bool tried = false;
-    if (!tried) {
-        tried = true;
+bool umma_encode_maps(const Seg* segs, int n, int p, UmmaTma* out, bool noRanges) {
+    // process-wide, resolved once (one host thread per GPU may plan concurrently: call_once orders the writes before every read)
+    static EncodeTiledFn encode = nullptr; static PointerAttrFn pattr = nullptr; static std::once_flag once;
+    std::call_once(once, [] {
         void* fn = nullptr; cudaDriverEntryPointQueryResult qres;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
             encode = reinterpret_cast<EncodeTiledFn>(fn);
@@ -873,7 +875,7 @@ bool umma_encode_maps(const Seg* segs, int n, int p, UmmaTma* out) {
         if (cudaGetDriverEntryPoint("cuPointerGetAttribute", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
             pattr = reinterpret_cast<PointerAttrFn>(fn);
         else (void) cudaGetLastError();
-    }
+    });
     if (!encode || (p & 3) != 0 || p <= 0) return false;
     std::vector<std::pair<unsigned long long, unsigned long long>> wins;
     for (int i = 0; i < n; ++i) {
@@ -887,7 +889,7 @@ bool umma_encode_maps(const Seg* segs, int n, int p, UmmaTma* out) {
     for (const auto& w : wins) hi = std::max(hi, w.second);
     // allocations around the windows (usually one: an arena or a framework's pool block)
     out->nRanges = 0;
-    if (pattr && getenv("F9_UMMA_NORANGES") == nullptr)
+    if (pattr && !noRanges)
         for (const auto& w : wins) {
             bool known = false;
             for (int r = 0; r < out->nRanges && !known; ++r) known = w.first >= out->rangeLo[r] && w.second <= out->rangeHi[r];
@@ -920,18 +922,18 @@ bool umma_encode_maps(const Seg* segs, int n, int p, UmmaTma* out) {
 
 cudaError_t launch_umma(const ResampleLaunch& L, cudaStream_t s, long long* launches) {
     // the opt-in shared-memory size is a per-device function attribute (one context per GPU may share this process)
-    static unsigned long long attr_done_mask = 0;
+    static std::atomic<unsigned long long> attr_done_mask{0};
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
-    const bool attr_done = dev < 64 && ((attr_done_mask >> dev) & 1ull);
-    if (!attr_done) {
+    const bool attr_done = dev < 64 && ((attr_done_mask.load(std::memory_order_acquire) >> dev) & 1ull);
+    if (!attr_done) {                                          // idempotent: two threads of one device may both set it
         cudaError_t e = cudaFuncSetAttribute(umma_fir_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(umma_fir_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(umma_fir_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(umma_fir_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(umma_fir_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
-        if (dev < 64) attr_done_mask |= 1ull << dev;
+        if (dev < 64) attr_done_mask.fetch_or(1ull << dev, std::memory_order_release);
     }
     int grid = std::min(L.n_tiles, std::max(L.sm_count, L.um.nGB));
     grid -= grid % L.um.nGB;
@@ -944,12 +946,17 @@ cudaError_t launch_umma(const ResampleLaunch& L, cudaStream_t s, long long* laun
     }
     cudaError_t e = cudaMemsetAsync(L.d_ovf, 0, sizeof(unsigned), s);
     if (e != cudaSuccess) return e;
-    // F9_UMMA_PROF=1 (development): per-role cycle accounting of the first launch, printed to stderr
+#ifdef F9_DIAG
+    // -DF9_DIAG builds only (single-threaded development runs): F9_UMMA_PROF=k: per-role cycle accounting of launch k, printed to
+    // stderr; F9_UMMA_DBG: 1 skip MMAs, 2 skip copies, 4 skip stores
     static long long* d_prof = nullptr; static int prof_calls = 0;
     const char* profEnv = getenv("F9_UMMA_PROF");
     const bool doProf = profEnv != nullptr && prof_calls++ == atoi(profEnv);
     if (doProf) { cudaMalloc((void**) &d_prof, sizeof(long long) * 16 * grid); cudaMemsetAsync(d_prof, 0, sizeof(long long) * 16 * grid, s); }
-    const int dbg = getenv("F9_UMMA_DBG") ? atoi(getenv("F9_UMMA_DBG")) : 0;     // development: 1 skip MMAs, 2 skip copies, 4 skip stores
+    const int dbg = getenv("F9_UMMA_DBG") ? atoi(getenv("F9_UMMA_DBG")) : 0;
+#else
+    long long* const d_prof = nullptr; const bool doProf = false; const int dbg = 0;
+#endif
     #define F9_UMMA_LAUNCH(MERGED, TMA) umma_fir_kernel<MERGED, TMA, false><<<grid, TMA ? kThreadsTma : kThreads, L.um_smem, s>>>(L.d_segs, L.d_tile_prefix, L.n_segs, L.n_tiles, \
         L.um, L.um_maps, L.d_tile_recs, L.um_stages, L.um_aligned ? 1 : 0, L.d_ovf, doProf ? d_prof : nullptr, dbg)
     if (L.um_tma) {
@@ -966,7 +973,7 @@ cudaError_t launch_umma(const ResampleLaunch& L, cudaStream_t s, long long* laun
             cudaLaunchAttribute attr[1];
             attr[0].id = cudaLaunchAttributeClusterDimension; attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
             cfg.attrs = attr; cfg.numAttrs = 1;
-            if (getenv("F9_UMMA_PROF")) {
+            if (doProf) {
                 int nc = -1; cudaError_t qe = cudaOccupancyMaxActiveClusters(&nc, umma_fir_kernel<false, true, true>, &cfg);
                 fprintf(stderr, "[umma pairs] grid %d smem %zu stages %d max active clusters %d (%s)\n", grid, L.um_smem, L.um_stages, nc, cudaGetErrorString(qe));
             }

@@ -53,12 +53,15 @@ private:
     int ch_ = 0, n_ = 0;
 };
 
-// ---- ProcessingSettings (Source/AppState.h:183-259): the fields the path reads, same defaults ----------
+// ---- BufferSize (Source/AppState.h:10-16) ---------------------------------------------------------------
+enum class BufferSize : int { samples128 = 128, samples256 = 256, samples512 = 512, samples1024 = 1024 };
+
+// ---- ProcessingSettings (Source/AppState.h:183-259): the fields the path reads, same types and defaults ---
 struct ProcessingSettings {
     double sampleRate = 44100.0;
-    int    bufferSize = 256;
+    BufferSize bufferSize = BufferSize::samples256;
     int    measuredLatencySamples = -1;        // -1 means not measured
-    int    lastBufferSizeWhenMeasured = 256;
+    BufferSize lastBufferSizeWhenMeasured = BufferSize::samples256;
     float  measuredNoiseFloorDb = 0.0f;
     bool   hasNoiseFloorMeasurement = false;
     bool   useReverbMode = false;
@@ -68,7 +71,7 @@ struct ProcessingSettings {
     bool   trimEnabled = true;
     bool   dcRemovalEnabled = true;
 
-    bool   needsLatencyRemeasurement() const { return f9_needs_latency_remeasurement(measuredLatencySamples, lastBufferSizeWhenMeasured, bufferSize) != 0; }
+    bool   needsLatencyRemeasurement() const { return f9_needs_latency_remeasurement(measuredLatencySamples, (int) lastBufferSizeWhenMeasured, (int) bufferSize) != 0; }
     double getLatencyInMs() const { return f9_latency_ms(measuredLatencySamples, sampleRate); }
     int    getRecordingLength(int sourceFileSamples, int latencySamples) const { return f9_recording_length(sourceFileSamples, latencySamples); }
     float  getThresholdLinear() const { return f9_threshold_linear(thresholdDb); }
@@ -216,6 +219,16 @@ public:
         f9_calculate_rms(ctx_.get(), buffer.channels, buffer.numChannels, buffer.numSamples, &rms);
         return rms;
     }
+    /** MainComponent::generateSineWave (Source/MainComponent.cpp:907-932): amplitude 0.5, float phase chain, sinePhase updated as there. */
+    void generateSineWave(const AudioBufferView& buffer, int numSamples) {
+        f9_generate_sine_wave(ctx_.get(), buffer.channels, buffer.numChannels, numSamples, sineFrequency, (float) settings.sampleRate,
+                              0.5f, &sinePhase, 0);
+    }
+    /** MainComponent::generateImpulse (Source/MainComponent.cpp:934-945): cleared buffer, 0.9 on sample 0 of every channel. */
+    void generateImpulse(const AudioBufferView& buffer) { f9_generate_impulse(ctx_.get(), buffer.channels, buffer.numChannels, buffer.numSamples); }
+    float sinePhase = 0.0f;                 // Source/MainComponent.h:153-154
+    float sineFrequency = 1000.0f;
+
     /** The body of timerCallback's latency completion (Source/MainComponent.cpp:265-294). */
     bool completeLatencyMeasurement(const AudioBufferView& latencyCaptureBuffer) {
         // findPeakPosition(buffer, 0.1f) and calculateNoiseFloorDb(buffer) from one upload and one read of the capture

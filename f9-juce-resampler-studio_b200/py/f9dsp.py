@@ -68,6 +68,8 @@ SYMBOLS = [
     ("f9_last_error", C.c_char_p, [_vp]),
     ("f9_set_stream", _i, [_vp, _vp]),
     ("f9_synchronize", _i, [_vp]),
+    ("f9_context_set_option", _i, [_vp, C.c_char_p, _i]),
+    ("f9_context_clear_options", _i, [_vp]),
     ("f9_launch_count", _ll, [_vp]),
     ("f9_host_alloc", _i, [_vp, C.POINTER(_vp), C.c_size_t]),
     ("f9_host_free", _i, [_vp, _vp]),
@@ -89,6 +91,11 @@ SYMBOLS = [
     ("f9_trim_latency", _i, [_vp, _fpp, _i, _i, _i, _i, _fpp, _ip]),
     ("f9_trim_latency_swift", _i, [_vp, _fp, _ll, _ll, _ll, _i, _fp, _llp]),
     ("f9_remove_dc_offset", _i, [_vp, _fpp, _i, _i]),
+    ("f9_generate_impulse", _i, [_vp, _fpp, _i, _i]),
+    ("f9_generate_sine_wave", _i, [_vp, _fpp, _i, _i, _f, _f, _f, _fp, _i]),
+    ("f9_generate_sine_wave_swift", _i, [_vp, _fp, _i, _i, _d, _d, _f, _dp]),
+    ("f9_dev_generate_impulse", _i, [_vp, C.POINTER(DevBuffer), _i]),
+    ("f9_dev_generate_sine_wave", _i, [_vp, C.POINTER(DevBuffer), _f, _f, _f, _f]),
     ("f9_tail_scan", _i, [_vp, _fpp, _i, _ll, _ll, _i, _i, _i, _i, _i, _f, _f, _llp, _ip, _i, _ip]),
     ("f9_xcorr_peak", _i, [_vp, _fpp, _i, _i, _fp, _i, _i, _i, _f, _ip, _ip, _ip, _dp]),
     ("f9_interp_create", _i, [_vp, _i, C.POINTER(_vp)]),
@@ -259,6 +266,13 @@ class Context:
     def set_stream(self, cuda_stream: int | None):
         self._check(lib().f9_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
 
+    def set_option(self, name: str, value: int = 1):
+        """Variant switch for plans created afterwards (f9_context_set_option)."""
+        self._check(lib().f9_context_set_option(self._h, name.encode(), int(value)))
+
+    def clear_options(self):
+        self._check(lib().f9_context_clear_options(self._h))
+
     def synchronize(self):
         self._check(lib().f9_synchronize(self._h))
 
@@ -335,6 +349,27 @@ class Context:
         a = _planar(buf).copy()
         self._check(lib().f9_remove_dc_offset(self._h, _chan_ptrs(a), a.shape[0], a.shape[1]))
         return a
+
+    def generate_impulse(self, num_ch: int, num_frames: int) -> np.ndarray:
+        out = np.full((num_ch, num_frames), np.nan, dtype=np.float32)
+        self._check(lib().f9_generate_impulse(self._h, _chan_ptrs(out), num_ch, num_frames))
+        return out
+
+    def generate_sine_wave(self, num_ch: int, num_samples: int, phase: float = 0.0, frequency: float = 1000.0,
+                           sample_rate: float = 44100.0, amplitude: float = 0.5, callback_form: bool = False):
+        """MainComponent::generateSineWave: returns (buffer, new sinePhase)."""
+        out = np.full((num_ch, num_samples), np.nan, dtype=np.float32)
+        ph = C.c_float(phase)
+        self._check(lib().f9_generate_sine_wave(self._h, _chan_ptrs(out), num_ch, num_samples, frequency, sample_rate, amplitude,
+                                                C.byref(ph), int(callback_form)))
+        return out, np.float32(ph.value)
+
+    def generate_sine_wave_swift(self, frames: int, channels: int, phase: float = 0.0, frequency: float = 1000.0,
+                                 sample_rate: float = 44100.0, amplitude: float = 0.5):
+        out = np.full(max(frames * channels, 1), np.nan, dtype=np.float32)
+        ph = C.c_double(phase)
+        self._check(lib().f9_generate_sine_wave_swift(self._h, _p(out), frames, channels, frequency, sample_rate, amplitude, C.byref(ph)))
+        return out[: frames * channels], ph.value
 
     def tail_scan(self, buf, start_frame: int, window: int, hop: int, required: int, mode: int,
                   has_nf: bool, nf_db: float, margin: float):

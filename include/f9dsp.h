@@ -8,7 +8,9 @@
  * reference interface it replaces (paths relative to the reference checkout).
  *
  * Threading: one f9_context per host thread / GPU.  A context is not thread-safe;
- * the library is re-entrant across contexts.  Calls block until the result is in
+ * the library is re-entrant across contexts (process-wide state is limited to driver entry points
+ * resolved under std::call_once and an atomic per-device attribute mask; tests/test_gpu_multi.py runs two
+ * contexts from two threads).  Calls block until the result is in
  * the caller's buffers unless the name ends in _async or takes device pointers
  * (section F), which only enqueue on the context's stream.
  *
@@ -75,6 +77,12 @@ F9_API const char* f9_last_error(const f9_context* ctx);
  * the context's own stream. */
 F9_API int  f9_set_stream(f9_context* ctx, void* cuda_stream);
 F9_API int  f9_synchronize(f9_context* ctx);
+/* Variant switches for tests and development: which kernel generation / feed a plan created afterwards takes (names as in
+ * "F9_NO_UMMA", "F9_UMMA_NB", "F9_SHORT_UMMA", "F9_UMMA_NOTMA", "F9_UMMA_NOCTA2", "F9_NO_HANKEL", "F9_BATCH_CHUNK_MB" ...).
+ * Every variant computes the same results within the stated tolerances; the defaults are the measured-fastest choices.  The
+ * library never reads the environment. */
+F9_API int  f9_context_set_option(f9_context* ctx, const char* name, int value);
+F9_API int  f9_context_clear_options(f9_context* ctx);
 /* Kernels launched by this context since creation (bench.py's gpu_launches claim). */
 F9_API long long f9_launch_count(const f9_context* ctx);
 /* Pinned host memory for full-speed H2D/D2H of caller buffers (optional; any host pointer works). */
@@ -140,6 +148,21 @@ F9_API int f9_trim_latency_swift(f9_context* ctx, const float* captured, long lo
 /* MainComponent::removeDCOffset, Source/MainComponent.cpp:884-902 (in place).  Tolerance parity only:
  * the reference accumulates the mean sequentially in float. */
 F9_API int f9_remove_dc_offset(f9_context* ctx, float* const* ch, int numCh, int numFrames);
+
+/* MainComponent::generateImpulse, Source/MainComponent.cpp:934-945 (Swift sendImpulse, LatencyMeasurementService.swift:130-145):
+ * clears the buffer and writes 0.9 to sample 0 of every channel -- the stimulus of the latency measurement. */
+F9_API int f9_generate_impulse(f9_context* ctx, float* const* ch, int numCh, int numFrames);
+/* MainComponent::generateSineWave, Source/MainComponent.cpp:907-932: data[i] = amplitude * sin(phase) with a FLOAT phase chain
+ * (phase += (frequency * 2 pi) / sample_rate, wrapped at 2 pi), the same chain on every channel.  *phase_io is sinePhase: read at
+ * entry, updated as :929-931 does (phase + inc * numSamples, one wrap).  callback_form != 0: the audio callback's variant
+ * (:141-167), where sinePhase is the chain itself.  The reference fixes amplitude 0.5 and frequency 1000 (MainComponent.h:153-154).
+ * The phase chain is bit-exact; samples are sin() correctly rounded (the host libm's sinf may differ by one ulp in rare cases). */
+F9_API int f9_generate_sine_wave(f9_context* ctx, float* const* ch, int numCh, int numSamples, float frequency, float sample_rate,
+                                 float amplitude, float* phase_io, int callback_form);
+/* Swift SineWaveGenerator.generateSineWave, SineWaveGenerator.swift:35-59: DOUBLE phase, interleaved output, every channel of a
+ * frame gets Float(sin(phase)) * amplitude; *phase_io is the generator's phase member. */
+F9_API int f9_generate_sine_wave_swift(f9_context* ctx, float* buffer, int frame_count, int channel_count, double frequency,
+                                       double sample_rate, float amplitude, double* phase_io);
 
 /* Offline form of the reverb-mode stop loop (Swift AudioProcessingService.swift:423-453; C++ intent
  * claude.md:346-367).  Poll i tests the last `window` frames before e_i = start_frame + (i+1)*hop;
@@ -312,6 +335,11 @@ F9_API int f9_dev_tail_scan_batch(f9_context* ctx, const f9_dev_buffer* bufs, co
  * original_length[i]); out numFrames must equal original_length[i]. */
 F9_API int f9_dev_trim_batch(f9_context* ctx, const f9_dev_buffer* captured, const int* latency_samples,
                              const f9_dev_buffer* out, int n, int remove_dc);
+
+/* stimuli on device buffers (bufs[i].base is written): generateImpulse for a batch, generateSineWave for one buffer */
+F9_API int f9_dev_generate_impulse(f9_context* ctx, const f9_dev_buffer* bufs, int n);
+F9_API int f9_dev_generate_sine_wave(f9_context* ctx, const f9_dev_buffer* buf, float frequency, float sample_rate, float amplitude,
+                                     float phase0);
 
 /* ======================= G. deinterleave / format convert =================== */
 /* interleaved PCM (host) -> planar float (host): JUCE reader semantics (left-justify to int32, scale by

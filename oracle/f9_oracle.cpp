@@ -288,6 +288,34 @@ ORC_API float orc_generate_sine(float* const* ch, int numCh, int numSamples, flo
     return p;
 }
 
+// Source/MainComponent.cpp:141-167  the audio callback's sine: same samples, sinePhase is the chain itself. Returns new phase.
+ORC_API float orc_generate_sine_callback(float* const* ch, int numCh, int numSamples, float freq, float sampleRate, float phase0) {
+    const float amplitude = 0.5f;
+    const float twoPi = 2.0f * 3.14159265358979323846f;
+    const float inc = (freq * 2.0f * 3.14159265358979323846f) / sampleRate;
+    float phase = phase0;
+    for (int i = 0; i < numSamples; ++i) {
+        const float sample = amplitude * std::sin(phase);
+        for (int c = 0; c < numCh; ++c) ch[c][i] = sample;
+        phase += inc;
+        if (phase >= twoPi) phase -= twoPi;
+    }
+    return phase;
+}
+// Swift SineWaveGenerator.swift:35-59: double phase, interleaved, Float(sin(phase)) * amplitude. Returns new phase.
+ORC_API double orc_generate_sine_swift(float* buffer, int frameCount, int channelCount, double freq, double sampleRate,
+                                       float amplitude, double phase) {
+    const double pi = 3.14159265358979323846;
+    const double inc = 2.0 * pi * freq / sampleRate;
+    for (int f = 0; f < frameCount; ++f) {
+        const float sample = (float) std::sin(phase) * amplitude;
+        for (int c = 0; c < channelCount; ++c) buffer[(size_t) f * channelCount + c] = sample;
+        phase += inc;
+        if (phase >= 2.0 * pi) phase -= 2.0 * pi;
+    }
+    return phase;
+}
+
 // =============================================================================
 // (1) sample-rate conversion -- juce::Interpolators  [JUCE-recall, JUCE 8.0.10
 // juce_audio_basics/utilities/juce_GenericInterpolator.h, juce_Interpolators.h,

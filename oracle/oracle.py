@@ -75,6 +75,10 @@ def lib():
         L.orc_generate_impulse.argtypes = [_fpp, C.c_int, C.c_int]
         L.orc_generate_sine.restype = C.c_float
         L.orc_generate_sine.argtypes = [_fpp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float]
+        L.orc_generate_sine_callback.restype = C.c_float
+        L.orc_generate_sine_callback.argtypes = [_fpp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float]
+        L.orc_generate_sine_swift.restype = C.c_double
+        L.orc_generate_sine_swift.argtypes = [_fp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_float, C.c_double]
         L.orc_sinc_table.restype = None
         L.orc_sinc_table.argtypes = [_fp]
         L.orc_interp_create.restype = C.c_void_p
@@ -255,6 +259,18 @@ def generate_sine(num_ch: int, n: int, freq: float = 1000.0, fs: float = 44100.0
     a = np.empty((num_ch, n), dtype=np.float32)
     ph = lib().orc_generate_sine(_chan_ptrs(a), num_ch, n, freq, fs, phase)
     return a, np.float32(ph)
+
+
+def generate_sine_callback(num_ch: int, n: int, freq: float = 1000.0, fs: float = 44100.0, phase: float = 0.0):
+    a = np.empty((num_ch, n), dtype=np.float32)
+    ph = lib().orc_generate_sine_callback(_chan_ptrs(a), num_ch, n, freq, fs, phase)
+    return a, np.float32(ph)
+
+
+def generate_sine_swift(frames: int, channels: int, freq: float = 1000.0, fs: float = 44100.0, amplitude: float = 0.5, phase: float = 0.0):
+    a = np.empty(max(frames * channels, 1), dtype=np.float32)
+    ph = lib().orc_generate_sine_swift(a.ctypes.data_as(_fp), frames, channels, freq, fs, amplitude, phase)
+    return a[: frames * channels], ph
 
 
 # ------------------------------------------------------------------ interpolators

@@ -66,6 +66,20 @@ int main(int argc, char** argv) {
         }
     }
 
+    // the stimuli: generateImpulse into a device block, generateSineWave over two consecutive blocks (sinePhase carried)
+    f9::AudioBuffer imp(2, 256), sine(2, 1024);
+    {
+        f9::AudioBufferView iv = imp.view();
+        for (int c = 0; c < 2; ++c) for (int i = 0; i < 256; ++i) iv.channels[c][i] = 7.0f;      // generateImpulse clears first
+        dsp.generateImpulse(iv);
+        float* half[2] = {sine.getWritePointer(0), sine.getWritePointer(1)};
+        f9::AudioBufferView s0{half, 2, 512};
+        dsp.generateSineWave(s0, 512);
+        float* half2[2] = {sine.getWritePointer(0) + 512, sine.getWritePointer(1) + 512};
+        f9::AudioBufferView s1{half2, 2, 512};
+        dsp.generateSineWave(s1, 512);
+    }
+
     FILE* g = std::fopen(argv[2], "wb");
     if (!g) return 5;
     int32_t hdr[8] = {measured ? 1 : 0, settings.measuredLatencySamples, below ? 1 : 0, used1, used2, numOut,
@@ -78,6 +92,9 @@ int main(int argc, char** argv) {
     std::fwrite(o1.data(), 4, (size_t) numOut, g);
     std::fwrite(o2.data(), 4, (size_t) numOut, g);
     for (int c = 0; c < 2; ++c) std::fwrite(rasOut.getReadPointer(c), 4, 2000, g);
+    for (int c = 0; c < 2; ++c) std::fwrite(imp.getReadPointer(c), 4, 256, g);
+    for (int c = 0; c < 2; ++c) std::fwrite(sine.getReadPointer(c), 4, 1024, g);
+    std::fwrite(&dsp.sinePhase, 4, 1, g);
     std::fclose(g);
     return 0;
 }

@@ -61,16 +61,40 @@ def test_latency_measurement_flow(ctx, O):
         pk = ctx.find_peak_position(cap, 0.1)
         assert pk == O.find_peak_position(cap, 0.1) == d
         nf_gpu, nf_cpu = ctx.calculate_noise_floor_db(cap), O.noise_floor_db(cap)
-        assert abs(float(nf_gpu) - float(nf_cpu)) <= 1e-5
+        assert nf_gpu.tobytes() == nf_cpu.tobytes()                              # calculateNoiseFloorDb bit for bit
 
 
 # ---------------------------------------------------------------- RMS
-@pytest.mark.parametrize("shape", SIZES)
-def test_rms_one_ulp(ctx, O, shape):
-    x = rnd(shape, 3 + sum(shape))
-    g, c = ctx.calculate_rms(x), O.calculate_rms(x)
-    assert abs(int(g.view(np.int32)) - int(c.view(np.int32))) <= 1
+@pytest.mark.parametrize("shape", SIZES + [(2, 240000), (2, 960000)])
+def test_rms_bit_exact(ctx, O, shape):
+    """calculateRMS (Source/MainComponent.cpp:983-1004) returns the reference's float bit for bit: the tree sum is redone in
+    the reference's sequential order whenever the order could change the rounded result (f9_scan.cu: rms_order_dependent)."""
+    for seed, scale in ((3, 0.5), (4, 1.0), (5, 1e-4)):
+        x = rnd(shape, seed + sum(shape), scale)
+        g, c = ctx.calculate_rms(x), O.calculate_rms(x)
+        assert g.tobytes() == c.tobytes(), (seed, scale)
+        assert ctx.calculate_noise_floor_db(x).tobytes() == O.noise_floor_db(x).tobytes()
     assert float(ctx.calculate_rms(np.zeros((2, 0), np.float32))) == 0.0
+    assert float(ctx.calculate_rms(np.zeros(shape, np.float32))) == 0.0
+
+
+def test_rms_reference_order_path(ctx, O, f9):
+    """The sequential re-sum itself (forced through the F9_RMS_FORCE_ORDER option) gives the reference's double sum, so the
+    float result equals the oracle's for any data; many small buffers also sweep the automatic trigger."""
+    c2 = f9.Context(0)
+    try:
+        c2.set_option("F9_RMS_FORCE_ORDER", 1)
+        for shape in [(1, 1), (2, 255), (3, 16385), (2, 220500)]:
+            x = rnd(shape, 11 + sum(shape), 0.7)
+            assert c2.calculate_rms(x).tobytes() == O.calculate_rms(x).tobytes()
+            assert c2.calculate_noise_floor_db(x).tobytes() == O.noise_floor_db(x).tobytes()
+    finally:
+        c2.close()
+    rng = np.random.default_rng(12)
+    for trial in range(300):
+        n = int(rng.integers(1, 700))
+        x = rng.uniform(-1, 1, (2, n)).astype(np.float32)
+        assert ctx.calculate_rms(x).tobytes() == O.calculate_rms(x).tobytes(), trial
 
 
 # ---------------------------------------------------------------- tail predicates and scan
@@ -189,7 +213,7 @@ def test_remove_dc_tolerance(ctx, O):
 
 def test_latency_stats_one_pass(ctx, O, f9):
     """findPeakPosition + the sum of squares behind calculateNoiseFloorDb from one read of each capture: the position is the
-    reference's (ties, threshold, all-zero buffer), the RMS within one float ulp of the sequential double sum, the peak exact."""
+    reference's (ties, threshold, all-zero buffer), the RMS and the noise floor the reference's floats bit for bit, the peak exact."""
     torch = pytest.importorskip("torch")
     import ctypes as C
     rng = np.random.default_rng(5)
@@ -226,13 +250,13 @@ def test_latency_stats_one_pass(ctx, O, f9):
         p1, nf = C.c_int(-7), C.c_float(0.0)
         ctx._check(f9.lib().f9_measure_latency(ctx.handle, chans, x.shape[0], x.shape[1], 0.1, C.byref(p1), C.byref(nf)))
         assert p1.value == O.find_peak_position(x, 0.1)
-        assert abs(nf.value - float(O.noise_floor_db(x))) <= 1e-4
+        assert np.float32(nf.value).tobytes() == O.noise_floor_db(x).tobytes()
     for i, x in enumerate(caps):
         assert pos[i] == pos2[i] == O.find_peak_position(x, 0.1), i
         assert peak[i] == np.max(np.abs(x))
         rms = np.float32(np.sqrt(sumsq[i] / x.size))
         ref = np.float32(O.calculate_rms(x))
-        assert abs(int(rms.view(np.int32)) - int(ref.view(np.int32))) <= 1, (i, rms, ref)
+        assert rms.tobytes() == ref.tobytes(), (i, rms, ref)
 
 
 @pytest.mark.parametrize("remove_dc", [0, 1])

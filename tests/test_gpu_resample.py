@@ -354,15 +354,13 @@ def test_umma_group_widths_agree(ctx, O, f9, monkeypatch):
     x = np.stack([signal(60000, 35), signal(60000, 36, "sweep")])
     refs = [O.resample_channel(0, 96000 / 44100, x[c], f9.resampled_length(60000, 96000, 44100))[0] for c in range(2)]
     for env in ({"F9_UMMA_NB": "16"}, {"F9_UMMA_NB": "32"}, {"F9_NO_UMMA": "1"}):
-        for k, v in env.items():
-            monkeypatch.setenv(k, v)
-        c2 = f9.Context(0)                       # plans are cached per context
+        c2 = f9.Context(0)                       # options are per context (f9_context_set_option)
         try:
+            for k, v in env.items():
+                c2.set_option(k, int(v))
             y = c2.resample(x, 96000, 44100, 0)
         finally:
             c2.close()
-        for k in env:
-            monkeypatch.delenv(k)
         for c in range(2):
             assert np.max(np.abs(y[c] - refs[c])) <= TOL, env
 
@@ -401,10 +399,11 @@ def test_umma_feed_variants_are_bit_identical(ctx, O, f9, monkeypatch, kind):
     got = {}
     for i, env in enumerate(FEEDS):
         for k, v in env.items():
-            monkeypatch.setenv(k, v)
-        got[i] = _plan_resample_many(ctx, f9, d, windows, kind, 96000, 44100)
-        for k in env:
-            monkeypatch.delenv(k)
+            ctx.set_option(k, int(v))
+        try:
+            got[i] = _plan_resample_many(ctx, f9, d, windows, kind, 96000, 44100)
+        finally:
+            ctx.clear_options()
     for (off, n), y in zip(windows, got[0]):
         ref, _ = O.resample_channel(kind, 96000 / 44100, x[off:off + n], y.shape[0])
         assert np.max(np.abs(y - ref)) <= TOL, (off, n)
@@ -441,10 +440,11 @@ def test_short_kernel_windows(ctx, O, f9, monkeypatch, kind, fs):
             assert snr_db(ref, y) >= 120.0
     for env in ({"F9_SHORT_UMMA": "1"}, {"F9_NO_SHORT": "1", "F9_NO_UMMA": "1"}):
         for k, v in env.items():
-            monkeypatch.setenv(k, v)
-        other = _plan_resample_many(ctx, f9, torch.from_numpy(x).cuda(), windows, kind, fs_in, fs_out)
-        for k in env:
-            monkeypatch.delenv(k)
+            ctx.set_option(k, int(v))
+        try:
+            other = _plan_resample_many(ctx, f9, torch.from_numpy(x).cuda(), windows, kind, fs_in, fs_out)
+        finally:
+            ctx.clear_options()
         for a, b in zip(got, other):
             assert np.max(np.abs(a - b)) <= TOL, env
 
@@ -472,9 +472,11 @@ def test_hankel_upsampling(ctx, O, f9, monkeypatch, up):
         assert np.max(np.abs(y - ref)) <= TOL, (off, n, float(np.max(np.abs(y - ref))) / TOL)
         if n > 1000:
             assert snr_db(ref, y) >= 120.0
-    monkeypatch.setenv("F9_NO_HANKEL", "1")
-    other = _plan_resample_many(ctx, f9, torch.from_numpy(x).cuda(), windows, 0, fs_in, fs_out)
-    monkeypatch.delenv("F9_NO_HANKEL")
+    ctx.set_option("F9_NO_HANKEL", 1)
+    try:
+        other = _plan_resample_many(ctx, f9, torch.from_numpy(x).cuda(), windows, 0, fs_in, fs_out)
+    finally:
+        ctx.clear_options()
     for a, b in zip(got, other):
         assert np.max(np.abs(a - b)) <= TOL
     # time segments: outputs [n0, n0 + m) of the conversion of one channel, each from its own input window with halo

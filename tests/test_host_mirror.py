@@ -42,9 +42,11 @@ def test_host_mirror_matches_oracle(O, tmp_path):
     trimmed = body[: 2 * playback].reshape(2, playback)
     trimmed_only = body[2 * playback: 4 * playback].reshape(2, playback)
     o1, o2 = body[4 * playback: 4 * playback + 4000], body[4 * playback + 4000: 4 * playback + 8000]
-    ras = body[4 * playback + 8000:].reshape(2, 2000)
+    ras = body[4 * playback + 8000: 4 * playback + 12000].reshape(2, 2000)
+    rest = body[4 * playback + 12000:]
+    imp, sine, phase = rest[:512].reshape(2, 256), rest[512: 512 + 2048].reshape(2, 1024), rest[512 + 2048]
     assert hdr[0] == 1 and hdr[1] == 2 * O.find_peak_position(cap, 0.1) == 2 * lat
-    assert abs(nf - float(O.noise_floor_db(cap))) <= 1e-5 and abs(rms - float(O.calculate_rms(cap))) <= 1e-9
+    assert np.float32(nf).tobytes() == O.noise_floor_db(cap).tobytes() and np.float32(rms).tobytes() == O.calculate_rms(cap).tobytes()
     t, _ = O.trim_latency(cap, 2 * lat, playback)
     assert np.array_equal(trimmed_only, t)
     assert np.max(np.abs(trimmed - O.remove_dc_offset(t))) <= 2.0 ** -20
@@ -60,3 +62,9 @@ def test_host_mirror_matches_oracle(O, tmp_path):
     src.prepare_to_play(512)
     ref = np.concatenate([src.get_next_audio_block(n) for n in (512, 333, 1155)], axis=1)
     assert np.array_equal(ras, ref)
+    # generateImpulse / generateSineWave through the MainComponent-shaped members
+    assert np.array_equal(imp, O.generate_impulse(2, 256))
+    a, ph = O.generate_sine(2, 512, 1000.0, 44100.0, 0.0)
+    b, ph = O.generate_sine(2, 512, 1000.0, 44100.0, float(ph))
+    assert phase.tobytes() == ph.tobytes()
+    assert np.max(np.abs(sine - np.concatenate([a, b], axis=1))) <= 2.0 ** -24
