@@ -26,9 +26,16 @@ struct JobPlan {
     int polls = 0;
 };
 
+inline int pcm_bps(int fmt) { return fmt == F9_PCM_U8 ? 1 : fmt == F9_PCM_S16LE ? 2 : fmt == F9_PCM_S24LE ? 3 : 4; }
+
 int validate(const f9_job& j) {
-    if (j.numCh <= 0 || j.captured_frames < 0 || j.original_length < 0 || !j.captured) return F9_ERR_INVALID;
-    for (int c = 0; c < j.numCh; ++c) if (j.captured_frames > 0 && !j.captured[c]) return F9_ERR_INVALID;
+    if (j.numCh <= 0 || j.captured_frames < 0 || j.original_length < 0) return F9_ERR_INVALID;
+    if (j.src_pcm) { if (j.src_fmt < F9_PCM_U8 || j.src_fmt > F9_PCM_F32LE || j.src_ch <= 0) return F9_ERR_INVALID; }
+    else {
+        if (!j.captured) return F9_ERR_INVALID;
+        for (int c = 0; c < j.numCh; ++c) if (j.captured_frames > 0 && !j.captured[c]) return F9_ERR_INVALID;
+    }
+    if (!j.out && !((j.flags & F9_JOB_PCM24) && j.out_pcm24)) return F9_ERR_INVALID;        // a job must deliver something
     if (!(j.fs_in > 0.0) || !(j.fs_out > 0.0)) return F9_ERR_INVALID;
     if (interp_memory(j.interp_kind) == 0) return F9_ERR_INVALID;
     if ((j.flags & F9_JOB_TAIL_SCAN) && (j.tail_window <= 0 || j.tail_hop <= 0 || j.tail_required <= 0 ||
@@ -67,6 +74,12 @@ int run_chunk(f9_context* ctx, const f9_job* jobs, f9_result* results, const std
     cudaStream_t s = ctx->stream;
 
     // ---- upload captures, carve outputs ----
+    // Captures given as file bytes (f9_job::src_pcm): the payload is uploaded as it is and deinterleaved / converted on the device,
+    // one launch per (format, channel count).  The planes start padA floats past a 16-byte boundary (see below); the payload is
+    // placed so that the first frame whose plane address IS aligned starts a 16-byte word of the payload too, which lets the
+    // 128-bit kernels serve everything but the `lead` <= 3 frames in front of it (those go through the byte-staged kernel).
+    struct PcmGroup { std::vector<const unsigned char*> src; std::vector<DevBuf> dst; };
+    std::map<std::pair<int, int>, PcmGroup> pcmMain, pcmHead;
     for (int t = 0; t < n; ++t) {
         const f9_job& J = jobs[idx[(size_t) t]];
         JobPlan& P = plans[(size_t) t];
@@ -76,6 +89,21 @@ int run_chunk(f9_context* ctx, const f9_job* jobs, f9_result* results, const std
         const int padA = (P.convert && P.start > 0) ? ((4 - (P.start & 3)) & 3) : 0;
         const long long cs = pad64(J.captured_frames + 4);
         float* d_cap = (float*) ctx->d_alloc(sizeof(float) * (size_t) cs * J.numCh) + padA;
+        if (J.src_pcm) {
+            if (J.captured_frames > 0) {
+                const size_t frameBytes = (size_t) J.src_ch * pcm_bps(J.src_fmt), bytes = frameBytes * (size_t) J.captured_frames;
+                const int lead = std::min(J.captured_frames, (4 - padA) & 3);
+                const size_t off = (16 - (lead * frameBytes) % 16) % 16;
+                unsigned char* d_src = (unsigned char*) ctx->d_alloc(bytes + 48) + off;
+                F9_TRY_CUDA(ctx, cudaMemcpyAsync(d_src, J.src_pcm, bytes, cudaMemcpyHostToDevice, s));
+                const auto key = std::make_pair(J.src_fmt, J.src_ch);
+                if (lead > 0) { pcmHead[key].src.push_back(d_src); pcmHead[key].dst.push_back(DevBuf{d_cap, cs, J.numCh, lead}); }
+                if (J.captured_frames > lead) {
+                    pcmMain[key].src.push_back(d_src + lead * frameBytes);
+                    pcmMain[key].dst.push_back(DevBuf{d_cap + lead, cs, J.numCh, J.captured_frames - lead});
+                }
+            }
+        } else
         for (int c = 0; c < J.numCh; ++c)
             if (J.captured_frames > 0)
                 F9_TRY_CUDA(ctx, cudaMemcpyAsync(d_cap + c * cs, J.captured[c], sizeof(float) * (size_t) J.captured_frames, cudaMemcpyHostToDevice, s));
@@ -90,6 +118,20 @@ int run_chunk(f9_context* ctx, const f9_job* jobs, f9_result* results, const std
         if (!P.convert) P.trimmed = P.out;
         if (J.flags & F9_JOB_PCM24) P.d_pcm = (unsigned char*) ctx->d_alloc((size_t) P.out_frames * J.numCh * 3 + 16);
     }
+
+    for (int pass = 0; pass < 2; ++pass)
+        for (auto& kv : (pass ? pcmHead : pcmMain)) {
+            PcmGroup& G = kv.second;
+            const size_t m = G.src.size();
+            const unsigned char** d_p = (const unsigned char**) ctx->d_alloc(sizeof(void*) * m); DevBuf* d_b = (DevBuf*) ctx->d_alloc(sizeof(DevBuf) * m);
+            const unsigned char** h_p = (const unsigned char**) ctx->h_alloc(sizeof(void*) * m); DevBuf* h_b = (DevBuf*) ctx->h_alloc(sizeof(DevBuf) * m);
+            if (!d_p || !d_b || !h_p || !h_b) return ctx->fail(F9_ERR_NOMEM, "arena");
+            std::memcpy(h_p, G.src.data(), sizeof(void*) * m); std::memcpy(h_b, G.dst.data(), sizeof(DevBuf) * m);
+            F9_TRY_CUDA(ctx, cudaMemcpyAsync(d_p, h_p, sizeof(void*) * m, cudaMemcpyHostToDevice, s));
+            F9_TRY_CUDA(ctx, cudaMemcpyAsync(d_b, h_b, sizeof(DevBuf) * m, cudaMemcpyHostToDevice, s));
+            F9_TRY_CUDA(ctx, launch_pcm_to_planar_batch(d_p, kv.first.first, kv.first.second, G.dst.data(), d_b, (int) m, s, &ctx->launches,
+                                                        pass ? nullptr : G.src.data()));
+        }
 
     // ---- reverb-tail scan (Swift :423-453): starts once source + latency frames are captured ----
     long long* h_stop = nullptr; std::vector<int> tailJobs;
@@ -209,7 +251,7 @@ int run_chunk(f9_context* ctx, const f9_job* jobs, f9_result* results, const std
             std::memcpy(h_b, pb.data(), sizeof(DevBuf) * pb.size()); std::memcpy(h_p, pd.data(), sizeof(void*) * pd.size());
             F9_TRY_CUDA(ctx, cudaMemcpyAsync(d_b, h_b, sizeof(DevBuf) * pb.size(), cudaMemcpyHostToDevice, s));
             F9_TRY_CUDA(ctx, cudaMemcpyAsync(d_p, h_p, sizeof(void*) * pd.size(), cudaMemcpyHostToDevice, s));
-            F9_TRY_CUDA(ctx, launch_planar_to_pcm24_batch(pb.data(), d_b, d_p, (int) pb.size(), s, &ctx->launches));
+            F9_TRY_CUDA(ctx, launch_planar_to_pcm24_batch(pb.data(), d_b, d_p, (int) pb.size(), s, &ctx->launches, pd.data()));
         }
     }
     for (int t = 0; t < n; ++t) {
@@ -288,7 +330,8 @@ extern "C" int f9_process_batch(f9_context* ctx, const f9_job* jobs, int n_jobs,
             P.polls = (int) std::max<long long>(0, (J.captured_frames - startFrame) / J.tail_hop);
         }
         P.bytes = sizeof(float) * (size_t) J.numCh * (size_t) (pad64(J.captured_frames + 4) + pad64(P.out_frames) + pad64(J.original_length))
-                  + (size_t) P.out_frames * J.numCh * 3 + 4096;
+                  + (size_t) P.out_frames * J.numCh * 3 + 4096
+                  + (J.src_pcm ? (size_t) J.captured_frames * J.src_ch * pcm_bps(J.src_fmt) + 512 : 0);
         R.latency_frames = P.latency_frames; R.trim_start = P.start; R.frames_copied = P.copied;
         R.out_frames = P.out_frames; R.tail_polls = P.polls;
         if (used + P.bytes > budget && !idx.empty()) { int rc = flush(); if (rc) worst = rc; }

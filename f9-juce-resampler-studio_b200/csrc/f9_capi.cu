@@ -976,7 +976,8 @@ int f9_dev_pcm_to_planar_batch(f9_context* ctx, const void* const* d_srcs, int f
     DevBuf* d_b; const unsigned char** d_p;
     rc = upload_array(ctx, hb, (size_t) n, &d_b); if (rc) return rc;
     rc = upload_array(ctx, reinterpret_cast<const unsigned char* const*>(d_srcs), (size_t) n, &d_p); if (rc) return rc;
-    F9_TRY_CUDA(ctx, launch_pcm_to_planar_batch(d_p, fmt, src_ch, hb, d_b, n, ctx->stream, &ctx->launches));
+    F9_TRY_CUDA(ctx, launch_pcm_to_planar_batch(d_p, fmt, src_ch, hb, d_b, n, ctx->stream, &ctx->launches,
+                                                ctx->diag.has("F9_PCM_BYTEWISE") ? nullptr : reinterpret_cast<const unsigned char* const*>(d_srcs)));
     return F9_OK;
 }
 int f9_dev_planar_to_pcm24_batch(f9_context* ctx, const f9_dev_buffer* src, unsigned char* const* d_dsts, int n) {
@@ -991,7 +992,7 @@ int f9_dev_planar_to_pcm24_batch(f9_context* ctx, const f9_dev_buffer* src, unsi
     DevBuf* d_b; unsigned char** d_p;
     rc = upload_array(ctx, hb, (size_t) n, &d_b); if (rc) return rc;
     rc = upload_array(ctx, const_cast<unsigned char**>(d_dsts), (size_t) n, &d_p); if (rc) return rc;
-    F9_TRY_CUDA(ctx, launch_planar_to_pcm24_batch(hb, d_b, d_p, n, ctx->stream, &ctx->launches));
+    F9_TRY_CUDA(ctx, launch_planar_to_pcm24_batch(hb, d_b, d_p, n, ctx->stream, &ctx->launches, ctx->diag.has("F9_PCM_BYTEWISE") ? nullptr : d_dsts));
     return F9_OK;
 }
 

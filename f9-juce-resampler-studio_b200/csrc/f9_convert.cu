@@ -239,6 +239,138 @@ planar_to_pcm24_batch_kernel(const DevBuf* __restrict__ srcs, unsigned char* con
     planar_to_pcm24_tile(raw, B.base, B.chStride, B.numCh, B.numFrames, dsts[blockIdx.y], kCvtFrames);
 }
 
+// ---- fast paths of the 24-bit / 16-bit payload (1 or 2 channels, 16-byte aligned planes and payloads) -------------------
+// The byte-staged kernels above reach 67 % of the HBM roofline: one-shot CTAs of 1024 frames behind a block barrier, scalar loads,
+// three byte stores per sample.  Here a thread owns 16 interleaved samples -- 48 bytes of 24-bit payload, three 16-byte words --
+// and everything moves as 128-bit accesses: planes with LDG.128 / STG.128 (a lane's 8 or 16 frames are contiguous), the payload
+// through a warp-private 1536-byte slice of shared memory (a lane's three words sit 48 bytes apart: conflict-free; the warp then
+// moves the slice as three fully coalesced 512-byte rows).  No block barrier, persistent grid-stride loop.
+constexpr int kFastWarps = kThreads / 32;
+__device__ __forceinline__ unsigned pk24(int v) { return (unsigned) (v >> 8) & 0xffffffu; }     // top 24 bits of the int32 sample
+
+template <int NCH>
+__global__ void __launch_bounds__(kThreads)
+pcm24_pack_fast_kernel(const DevBuf* __restrict__ srcs, unsigned char* const* __restrict__ dsts) {
+    __shared__ uint4 slice[kFastWarps][96];
+    const DevBuf B = srcs[blockIdx.y];
+    unsigned char* __restrict__ dst = dsts[blockIdx.y];
+    constexpr int FR = 16 / NCH;                                   // frames per thread
+    const long long groups = (long long) B.numFrames / FR;         // whole 16-sample groups
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (long long base = ((long long) blockIdx.x * kFastWarps + warp) * 32; base < groups; base += (long long) gridDim.x * kThreads) {
+        const long long g = base + lane;
+        unsigned w[12];
+        if (g < groups) {
+            int t[16];
+            if (NCH == 2) {
+                const float4* __restrict__ l4 = reinterpret_cast<const float4*>(B.base + g * FR);
+                const float4* __restrict__ r4 = reinterpret_cast<const float4*>(B.base + B.chStride + g * FR);
+                const float4 a0 = __ldg(l4), a1 = __ldg(l4 + 1), b0 = __ldg(r4), b1 = __ldg(r4 + 1);
+                const float L[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w}, R[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                #pragma unroll
+                for (int i = 0; i < 8; ++i) { t[2 * i] = float_to_i32(L[i]); t[2 * i + 1] = float_to_i32(R[i]); }
+            } else {
+                const float4* __restrict__ x4 = reinterpret_cast<const float4*>(B.base + g * FR);
+                #pragma unroll
+                for (int i = 0; i < 4; ++i) { const float4 v = __ldg(x4 + i); t[4 * i] = float_to_i32(v.x); t[4 * i + 1] = float_to_i32(v.y); t[4 * i + 2] = float_to_i32(v.z); t[4 * i + 3] = float_to_i32(v.w); }
+            }
+            #pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const unsigned a = pk24(t[4 * q]), b = pk24(t[4 * q + 1]), c = pk24(t[4 * q + 2]), d = pk24(t[4 * q + 3]);
+                w[3 * q] = a | (b << 24); w[3 * q + 1] = (b >> 8) | (c << 16); w[3 * q + 2] = (c >> 16) | (d << 8);
+            }
+            #pragma unroll
+            for (int k = 0; k < 3; ++k) slice[warp][3 * lane + k] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+        }
+        __syncwarp();
+        const int valid = (int) min((long long) 32, groups - base) * 3;           // 16-byte words of this warp's row
+        uint4* __restrict__ d4 = reinterpret_cast<uint4*>(dst + base * 48);
+        #pragma unroll
+        for (int k = 0; k < 3; ++k) if (lane + 32 * k < valid) __stcs(d4 + lane + 32 * k, slice[warp][lane + 32 * k]);
+        __syncwarp();
+    }
+    // the last frames (fewer than one group): bytes, by the first threads of the file's first CTA
+    if (blockIdx.x == 0) {
+        const long long f0 = groups * FR;
+        const int rem = (int) (B.numFrames - f0) * NCH;
+        if ((int) threadIdx.x < rem) {
+            const int f = threadIdx.x / NCH, c = threadIdx.x - f * NCH;
+            const int v = float_to_i32(__ldg(B.base + (long long) c * B.chStride + f0 + f)) >> 8;
+            unsigned char* r = dst + (f0 * NCH + threadIdx.x) * 3;
+            r[0] = (unsigned char) (v & 0xff); r[1] = (unsigned char) ((v >> 8) & 0xff); r[2] = (unsigned char) ((v >> 16) & 0xff);
+        }
+    }
+}
+
+// 24-bit (FMT24) or 16-bit interleaved payload of SRC channels -> DST planar channels (DST >= SRC: mono duplicated).
+template <int SRC, int DST, bool FMT24>
+__global__ void __launch_bounds__(kThreads)
+pcm_unpack_fast_kernel(const unsigned char* const* __restrict__ srcs, const DevBuf* __restrict__ dsts) {
+    __shared__ uint4 slice[kFastWarps][96];
+    const DevBuf D = dsts[blockIdx.y];
+    const unsigned char* __restrict__ src = srcs[blockIdx.y];
+    constexpr int FR = 16 / SRC;
+    const float scale = 1.0f / 0x7fffffff;
+    const long long groups = (long long) D.numFrames / FR;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* __restrict__ d0 = const_cast<float*>(D.base);
+    for (long long base = ((long long) blockIdx.x * kFastWarps + warp) * 32; base < groups; base += (long long) gridDim.x * kThreads) {
+        const long long g = base + lane;
+        int t[16];
+        if (FMT24) {
+            const int valid = (int) min((long long) 32, groups - base) * 3;
+            const uint4* __restrict__ s4 = reinterpret_cast<const uint4*>(src + base * 48);
+            #pragma unroll
+            for (int k = 0; k < 3; ++k) if (lane + 32 * k < valid) slice[warp][lane + 32 * k] = __ldg(s4 + lane + 32 * k);
+            __syncwarp();
+            if (g < groups) {
+                unsigned w[12];
+                #pragma unroll
+                for (int k = 0; k < 3; ++k) { const uint4 v = slice[warp][3 * lane + k]; w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w; }
+                #pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const unsigned w0 = w[3 * q], w1 = w[3 * q + 1], w2 = w[3 * q + 2];
+                    t[4 * q] = (int) (w0 << 8); t[4 * q + 1] = (int) (((w0 >> 24) | (w1 << 8)) << 8);
+                    t[4 * q + 2] = (int) (((w1 >> 16) | (w2 << 16)) << 8); t[4 * q + 3] = (int) (w2 & 0xffffff00u);
+                }
+            }
+            __syncwarp();
+        } else if (g < groups) {
+            const uint4* __restrict__ s4 = reinterpret_cast<const uint4*>(src + g * 32);
+            const uint4 a = __ldg(s4), b = __ldg(s4 + 1);
+            const unsigned w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+            #pragma unroll
+            for (int i = 0; i < 8; ++i) { t[2 * i] = (int) (w[i] << 16); t[2 * i + 1] = (int) (w[i] & 0xffff0000u); }
+        }
+        if (g < groups) {
+            float v[16];
+            #pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __fmul_rn((float) t[i], scale);
+            if (SRC == 2) {
+                float4* __restrict__ l4 = reinterpret_cast<float4*>(d0 + g * FR);
+                float4* __restrict__ r4 = reinterpret_cast<float4*>(d0 + D.chStride + g * FR);
+                l4[0] = make_float4(v[0], v[2], v[4], v[6]);  l4[1] = make_float4(v[8], v[10], v[12], v[14]);
+                r4[0] = make_float4(v[1], v[3], v[5], v[7]);  r4[1] = make_float4(v[9], v[11], v[13], v[15]);
+            } else {
+                #pragma unroll
+                for (int c = 0; c < DST; ++c) {
+                    float4* __restrict__ x4 = reinterpret_cast<float4*>(d0 + (long long) c * D.chStride + g * FR);
+                    #pragma unroll
+                    for (int i = 0; i < 4; ++i) x4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                }
+            }
+        }
+    }
+    if (blockIdx.x == 0) {                                         // the last frames (fewer than one group)
+        const long long f0 = groups * FR;
+        const int remFrames = (int) (D.numFrames - f0);
+        for (int i = threadIdx.x; i < remFrames * DST; i += kThreads) {
+            const int f = i / DST, c = i - f * DST;
+            d0[(long long) c * D.chStride + f0 + f] = pcm_load(src, FMT24 ? F9_PCM_S24LE : F9_PCM_S16LE, (f0 + f) * SRC + min(c, SRC - 1));
+        }
+    }
+}
+
 // ---- planar <-> interleaved float (AudioProcessingService.swift:361-365, :524-531) ----------------------
 __global__ void __launch_bounds__(kThreads)
 interleave_kernel(const float* __restrict__ src, long long srcStride, int numCh, long long frames, float* __restrict__ dst, int kCvtFrames) {
@@ -336,10 +468,23 @@ cudaError_t launch_planar_to_pcm24(const float* d_src, long long srcStride, int 
 
 // h_bufs: host copy of the descriptors (for sizing the grid); d_bufs / d_ptrs: the same on the device
 cudaError_t launch_planar_to_pcm24_batch(const DevBuf* h_srcs, const DevBuf* d_srcs, unsigned char* const* d_dsts, int n,
-                                         cudaStream_t s, long long* launches) {
+                                         cudaStream_t s, long long* launches, unsigned char* const* h_dsts) {
     int maxCh = 0, maxFrames = 0;
     for (int i = 0; i < n; ++i) { maxCh = std::max(maxCh, h_srcs[i].numCh); maxFrames = std::max(maxFrames, h_srcs[i].numFrames); }
     if (n <= 0 || maxCh <= 0 || maxFrames <= 0) return cudaSuccess;
+    // fast path: every file mono or every file stereo, planes and payloads on 16 bytes (h_dsts: host copy of the payload pointers)
+    bool fast = h_dsts != nullptr && maxCh <= 2 && n <= 65535;
+    for (int i = 0; i < n && fast; ++i)
+        fast = h_srcs[i].numCh == maxCh && (reinterpret_cast<uintptr_t>(h_srcs[i].base) & 15) == 0 && (h_srcs[i].chStride & 3) == 0 &&
+               (reinterpret_cast<uintptr_t>(h_dsts[i]) & 15) == 0;
+    if (fast) {
+        const long long groups = (long long) maxFrames * maxCh / 16;
+        const unsigned ctas = (unsigned) std::max<long long>(1, std::min<long long>((groups + kThreads - 1) / kThreads, std::max(1, 148 * 8 / std::min(n, 148 * 8))));
+        if (maxCh == 2) pcm24_pack_fast_kernel<2><<<dim3(ctas, (unsigned) n), kThreads, 0, s>>>(d_srcs, d_dsts);
+        else pcm24_pack_fast_kernel<1><<<dim3(ctas, (unsigned) n), kThreads, 0, s>>>(d_srcs, d_dsts);
+        ++*launches;
+        return cudaGetLastError();
+    }
     const int kCvtFrames = cvt_frames(maxCh * 3);
     const size_t smem = (size_t) kCvtFrames * maxCh * 3 + 16;
     cudaError_t e = allow_smem(planar_to_pcm24_batch_kernel, smem);
@@ -352,10 +497,27 @@ cudaError_t launch_planar_to_pcm24_batch(const DevBuf* h_srcs, const DevBuf* d_s
     return cudaGetLastError();
 }
 cudaError_t launch_pcm_to_planar_batch(const unsigned char* const* d_srcs, int fmt, int srcCh, const DevBuf* h_dsts, const DevBuf* d_dsts, int n,
-                                       cudaStream_t s, long long* launches) {
+                                       cudaStream_t s, long long* launches, const unsigned char* const* h_srcs) {
     int maxFrames = 0;
     for (int i = 0; i < n; ++i) maxFrames = std::max(maxFrames, h_dsts[i].numFrames);
     if (n <= 0 || maxFrames <= 0) return cudaSuccess;
+    // fast path: 24- or 16-bit payload of 1 or 2 channels into 1 or 2 planes (mono duplicated), everything on 16 bytes
+    const int dstCh = h_dsts[0].numCh;
+    bool fast = h_srcs != nullptr && (fmt == F9_PCM_S24LE || fmt == F9_PCM_S16LE) && srcCh <= 2 && dstCh >= srcCh && dstCh <= 2 && n <= 65535;
+    for (int i = 0; i < n && fast; ++i)
+        fast = h_dsts[i].numCh == dstCh && (reinterpret_cast<uintptr_t>(h_dsts[i].base) & 15) == 0 && (h_dsts[i].chStride & 3) == 0 &&
+               (reinterpret_cast<uintptr_t>(h_srcs[i]) & 15) == 0;
+    if (fast) {
+        const long long groups = (long long) maxFrames * srcCh / 16;
+        const unsigned ctas = (unsigned) std::max<long long>(1, std::min<long long>((groups + kThreads - 1) / kThreads, std::max(1, 148 * 8 / std::min(n, 148 * 8))));
+        const dim3 grid(ctas, (unsigned) n);
+        const bool f24 = fmt == F9_PCM_S24LE;
+        if (srcCh == 2)      { if (f24) pcm_unpack_fast_kernel<2, 2, true><<<grid, kThreads, 0, s>>>(d_srcs, d_dsts); else pcm_unpack_fast_kernel<2, 2, false><<<grid, kThreads, 0, s>>>(d_srcs, d_dsts); }
+        else if (dstCh == 2) { if (f24) pcm_unpack_fast_kernel<1, 2, true><<<grid, kThreads, 0, s>>>(d_srcs, d_dsts); else pcm_unpack_fast_kernel<1, 2, false><<<grid, kThreads, 0, s>>>(d_srcs, d_dsts); }
+        else                 { if (f24) pcm_unpack_fast_kernel<1, 1, true><<<grid, kThreads, 0, s>>>(d_srcs, d_dsts); else pcm_unpack_fast_kernel<1, 1, false><<<grid, kThreads, 0, s>>>(d_srcs, d_dsts); }
+        ++*launches;
+        return cudaGetLastError();
+    }
     const int bps = (fmt == F9_PCM_U8) ? 1 : (fmt == F9_PCM_S16LE) ? 2 : (fmt == F9_PCM_S24LE) ? 3 : 4;
     const int kCvtFrames = cvt_frames(srcCh * bps);
     const size_t smem = (size_t) kCvtFrames * srcCh * bps + 16;

@@ -17,7 +17,7 @@
 // and D1 += w1 x0 + w0 x1 (units of 1/2048), out = (D0 + D1/2048) / 128.  The tensor core truncates the fp32 accumulator after every
 // MMA by an ulp of its magnitude, so the K steps are issued *tails first* (|w| < 0.11, the accumulator is still small) and the 2-5
 // steps that hold the main lobe of some lane's filter (|w| up to 1) last: only those truncate at full scale (measured: inside the
-// 2^-20 tolerance for 1:2 .. 1:16: 0.81-0.88 x 2^-20 on full-amplitude noise; window order gave 1.06 x 2^-20).  |x| >= 256,
+// 2^-20 tolerance for 1:2 .. 1:16: 0.81-0.88 x 2^-20 against the oracle on noise of amplitude 0.5 (at 0 dBFS: <= 0.78 x 2^-20 against the exact value); window order gave 1.06 x 2^-20).  |x| >= 256,
 // Inf or NaN raise the flag and hankel_redo_kernel recomputes the launch in fp32.
 //
 // Roles (448 threads, one persistent CTA per SM; tile = 64 columns = 8192 outputs):

@@ -106,10 +106,11 @@ cudaError_t launch_remove_dc(const DevBuf* d_bufs /* writable */, int n, int max
                              cudaStream_t s, long long* launches);
 cudaError_t launch_pcm_to_planar(const void* d_src, int fmt, int srcCh, long long frames, float* d_dst,
                                  long long dstStride, int dstCh, cudaStream_t s, long long* launches);
+// h_dsts / h_srcs: host copies of the payload pointer arrays (alignment check for the 128-bit fast paths; nullptr = byte-staged kernels)
 cudaError_t launch_planar_to_pcm24_batch(const DevBuf* h_srcs, const DevBuf* d_srcs, unsigned char* const* d_dsts, int n,
-                                         cudaStream_t s, long long* launches);
+                                         cudaStream_t s, long long* launches, unsigned char* const* h_dsts = nullptr);
 cudaError_t launch_pcm_to_planar_batch(const unsigned char* const* d_srcs, int fmt, int srcCh, const DevBuf* h_dsts, const DevBuf* d_dsts, int n,
-                                       cudaStream_t s, long long* launches);
+                                       cudaStream_t s, long long* launches, const unsigned char* const* h_srcs = nullptr);
 cudaError_t launch_planar_to_pcm24(const float* d_src, long long srcStride, int numCh, long long frames,
                                    unsigned char* d_dst, cudaStream_t s, long long* launches);
 cudaError_t launch_interleave(const float* d_src, long long srcStride, int numCh, long long frames, float* d_dst,

@@ -51,7 +51,8 @@ class Job(C.Structure):
                 ("original_length", C.c_int), ("fs_in", C.c_double), ("fs_out", C.c_double), ("interp_kind", C.c_int),
                 ("flags", C.c_int), ("tail_window", C.c_int), ("tail_hop", C.c_int), ("tail_required", C.c_int),
                 ("tail_mode", C.c_int), ("has_nf", C.c_int), ("nf_db", C.c_float), ("margin_pct", C.c_float),
-                ("out", _fpp), ("out_capacity", C.c_int), ("out_pcm24", C.c_void_p)]
+                ("out", _fpp), ("out_capacity", C.c_int), ("out_pcm24", C.c_void_p),
+                ("src_pcm", C.c_void_p), ("src_fmt", C.c_int), ("src_ch", C.c_int)]
 
 
 class Result(C.Structure):
@@ -413,14 +414,30 @@ class Context:
         keep = []
         outs, pcms = [], []
         for i, j in enumerate(jobs):
-            cap = _planar(j["captured"])
             fs_in, fs_out = float(j.get("fs_in", 44100.0)), float(j.get("fs_out", 44100.0))
             out_frames = resampled_length(j["original_length"], fs_in, fs_out) if fs_in != fs_out else j["original_length"]
-            out = np.full((cap.shape[0], max(out_frames, 1)), np.nan, dtype=np.float32)
-            cp, op = _chan_ptrs(cap), _chan_ptrs(out)
-            keep += [cap, out, cp, op]
+            if "src_pcm" in j:          # the capture as file bytes: (raw uint8 array, fmt, src_ch[, numCh])
+                raw, fmt, src_ch = j["src_pcm"][:3]
+                raw = np.ascontiguousarray(raw).view(np.uint8).ravel()
+                num_ch = j["src_pcm"][3] if len(j["src_pcm"]) > 3 else src_ch
+                frames = raw.size // (_BYTES[fmt] * src_ch)
+                J[i].src_pcm, J[i].src_fmt, J[i].src_ch = raw.ctypes.data, fmt, src_ch
+                J[i].numCh, J[i].captured_frames = num_ch, frames
+                keep.append(raw)
+            else:
+                cap = _planar(j["captured"])
+                cp = _chan_ptrs(cap)
+                keep += [cap, cp]
+                num_ch = cap.shape[0]
+                J[i].captured, J[i].numCh, J[i].captured_frames = cp, cap.shape[0], cap.shape[1]
             flags = 0
-            J[i].captured, J[i].numCh, J[i].captured_frames = cp, cap.shape[0], cap.shape[1]
+            if j.get("no_float_out"):
+                out = np.zeros((num_ch, 0), dtype=np.float32)
+            else:
+                out = np.full((num_ch, max(out_frames, 1)), np.nan, dtype=np.float32)
+                op = _chan_ptrs(out)
+                keep += [out, op]
+                J[i].out, J[i].out_capacity = op, out.shape[1]
             J[i].latency_samples, J[i].original_length = j["latency_samples"], j["original_length"]
             J[i].fs_in, J[i].fs_out, J[i].interp_kind = fs_in, fs_out, j.get("kind", WINDOWED_SINC)
             if "tail" in j:
@@ -433,12 +450,11 @@ class Context:
             pcm = None
             if j.get("pcm24"):
                 flags |= JOB_PCM24
-                pcm = np.zeros(max(out_frames, 1) * cap.shape[0] * 3, dtype=np.uint8)
+                pcm = np.zeros(max(out_frames, 1) * num_ch * 3, dtype=np.uint8)
                 J[i].out_pcm24 = pcm.ctypes.data
                 keep.append(pcm)
             J[i].flags = flags
-            J[i].out, J[i].out_capacity = op, out.shape[1]
-            outs.append((out, out_frames))
+            outs.append((out, out_frames if not j.get("no_float_out") else 0))
             pcms.append(pcm)
         rc = lib().f9_process_batch(self._h, J, n, R)
         res = [dict(status=R[i].status, latency_frames=R[i].latency_frames, trim_start=R[i].trim_start,
@@ -447,7 +463,7 @@ class Context:
         if rc < 0 and all(r["status"] == 0 for r in res):
             self._check(rc)
         outputs = [o[:, :f] for (o, f) in outs]
-        pcm_out = [None if p is None else p[: outs[i][1] * outputs[i].shape[0] * 3] for i, p in enumerate(pcms)]
+        pcm_out = [None if p is None else p[: res[i]["out_frames"] * outputs[i].shape[0] * 3] for i, p in enumerate(pcms)]
         return outputs, pcm_out, res
 
     # ---- G. format convert

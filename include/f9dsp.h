@@ -36,7 +36,7 @@ extern "C" {
 #endif
 
 #define F9_VERSION_MAJOR 0
-#define F9_VERSION_MINOR 1
+#define F9_VERSION_MINOR 2
 
 /* ---- status codes (reference: sentinels + log lines, Source/MainComponent.cpp:974, :777-782;
  *      Swift typed errors AudioProcessingService.swift:16-52) ---------------------------- */
@@ -253,9 +253,16 @@ typedef struct f9_job {
     int   tail_window, tail_hop, tail_required, tail_mode;
     int   has_nf; float nf_db; float margin_pct;
     /* outputs (caller-allocated): */
-    float* const* out;              /* numCh channels, out_capacity frames each                     */
+    float* const* out;              /* numCh channels, out_capacity frames each; NULL: no float download (F9_JOB_PCM24 only) */
     int   out_capacity;
     unsigned char* out_pcm24;       /* optional: numCh*out_frames*3 bytes interleaved, or NULL      */
+    /* The capture as the file / device holds it (optional; when src_pcm != NULL it replaces `captured`, which may then be NULL):
+     * captured_frames frames of src_ch interleaved channels in format src_fmt (F9_PCM_*), i.e. what reader->read consumes at
+     * Source/MainComponent.cpp:734-739.  The deinterleave / int->float stage then runs on the device and the upload is the file's
+     * own 2 or 3 bytes per sample instead of 4.  Plane c of the job reads source channel min(c, src_ch - 1). */
+    const void* src_pcm;
+    int   src_fmt;
+    int   src_ch;
 } f9_job;
 
 enum { F9_JOB_TAIL_SCAN = 1, F9_JOB_REMOVE_DC = 2, F9_JOB_PCM24 = 4 };

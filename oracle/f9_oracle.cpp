@@ -553,6 +553,46 @@ ORC_API int orc_resample_channel(int kind, const float* table10001, double ratio
     return used;
 }
 
+// The same conversion with every product and the sum in double (WindowedSinc only): the float weights, the float inputs and the
+// position chain are the interpolator's own, only the 200-term accumulation is exact to ~1e-16.  This is NOT what the reference
+// computes; it is the yardstick that shows how far the reference's own sequential float sum is from the exact value (at 0 dBFS
+// noise: up to ~1.5 x 2^-20) and how far the tensor-core kernel is (tests/test_gpu_resample.py).
+ORC_API int orc_resample_channel_exact(const float* table10001, double ratio, const float* in, int numIn, double* out, int numOut) {
+    std::vector<float> table(kSincTableSize + 1, 0.0f);
+    if (table10001) std::memcpy(table.data(), table10001, sizeof(float) * kSincTableSize); else make_sinc_table(table.data());
+    const int M = 200;
+    float last[M]; for (int i = 0; i < M; ++i) last[i] = 0.0f;
+    int indexBuffer = 0, used = 0;
+    double pos = 1.0;
+    for (int n = 0; n < numOut; ++n) {
+        while (pos >= 1.0) { last[indexBuffer] = used < numIn ? in[used] : 0.0f; ++used; if (++indexBuffer == M) indexBuffer = 0; pos -= 1.0; }
+        const float offset = (float) pos;
+        // SincTraits::value with a double accumulator
+        double result = 0.0;
+        int samplePosition = indexBuffer; float firstFrac = 0.0f, lastSincPosition = -1.0f; int index = 0, sign = -1;
+        for (int i = -100; i <= 100; ++i) {
+            const float sincPosition = (1.0f - offset) + (float) i;
+            if (i == -100 || (sincPosition >= 0 && lastSincPosition < 0)) {
+                const float indexFloat = (sincPosition >= 0.f ? sincPosition : -sincPosition) * 100.0f;
+                const float indexFloored = std::floor(indexFloat);
+                index = (int) indexFloored; firstFrac = indexFloat - indexFloored; sign = (sincPosition < 0 ? -1 : 1);
+            }
+            if (sincPosition == 0.0f) result += (double) last[samplePosition];
+            else if (sincPosition < 100.0f && sincPosition > -100.0f) {
+                const float v1 = table[index], v2 = table[index + 1];
+                const float w = v1 + (firstFrac * (v2 - v1));
+                result += (double) last[samplePosition] * (double) w;
+            }
+            if (++samplePosition == M) samplePosition = 0;
+            lastSincPosition = sincPosition;
+            index += 100 * sign;
+        }
+        out[n] = result;
+        pos += ratio;
+    }
+    return used;
+}
+
 // Multi-threaded whole-file conversion used as the CPU baseline: one interpolator
 // object per channel, channels statically partitioned over `threads` host threads
 // (bench.py launches the threads; this entry converts channels [c0, c1)).

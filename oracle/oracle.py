@@ -79,6 +79,8 @@ def lib():
         L.orc_generate_sine_callback.argtypes = [_fpp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float]
         L.orc_generate_sine_swift.restype = C.c_double
         L.orc_generate_sine_swift.argtypes = [_fp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_float, C.c_double]
+        L.orc_resample_channel_exact.restype = C.c_int
+        L.orc_resample_channel_exact.argtypes = [_fp, C.c_double, _fp, C.c_int, C.POINTER(C.c_double), C.c_int]
         L.orc_sinc_table.restype = None
         L.orc_sinc_table.argtypes = [_fp]
         L.orc_interp_create.restype = C.c_void_p
@@ -330,6 +332,16 @@ def resample_channel(kind: int, ratio: float, inp, num_out: int, table=None):
     t = None if table is None else np.ascontiguousarray(table, dtype=np.float32)
     used = lib().orc_resample_channel(kind, None if t is None else _p(t), ratio, _p(a), a.size, _p(out), num_out)
     return out, used
+
+
+def resample_channel_exact(ratio: float, inp, num_out: int, table=None) -> np.ndarray:
+    """WindowedSinc with the 200-term sum in double (the interpolator's own float weights and positions): the exact value the
+    float paths approximate -- a yardstick, not the reference's output."""
+    a = np.ascontiguousarray(inp, dtype=np.float32)
+    out = np.empty(max(num_out, 0), dtype=np.float64)
+    t = None if table is None else np.ascontiguousarray(table, dtype=np.float32)
+    lib().orc_resample_channel_exact(None if t is None else _p(t), ratio, _p(a), a.size, out.ctypes.data_as(C.POINTER(C.c_double)), num_out)
+    return out
 
 
 def resample_channels(kind: int, ratio: float, buf, num_out: int, threads: int = 1, table=None) -> np.ndarray:

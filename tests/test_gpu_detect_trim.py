@@ -349,6 +349,62 @@ def test_pcm_batch_forms(ctx, O, f9):
         assert np.all(np.isnan(got[:, f:]))
 
 
+@pytest.mark.parametrize("ch", [1, 2])
+def test_pcm_fast_paths(ctx, O, f9, ch):
+    """Uniform mono / stereo batches on 16-byte aligned planes take the 128-bit kernels (a thread owns 16 interleaved samples,
+    the payload crosses a warp-private slice of shared memory): ragged lengths around the group size, both directions, 24- and
+    16-bit input, mono duplicated into stereo; bit-identical to the oracle and to the byte-staged kernels (F9_PCM_BYTEWISE)."""
+    torch = pytest.importorskip("torch")
+    import ctypes as C
+    frames = [0, 1, 7, 8, 9, 15, 16, 17, 255, 256, 257, 4099, 44100, 441000, 8 * 32 * 8 + 3]
+    n = len(frames)
+    xs = [rnd((ch, f), 700 + i + ch, 1.2) for i, f in enumerate(frames)]
+    for x in xs:
+        if x.shape[1] >= 4:
+            x[0, :4] = [1.0, -1.0, 0.0, -0.0]
+    def pack(c):
+        stride = [(f + 3) // 4 * 4 + 4 for f in frames]
+        d_x = [torch.zeros((ch, st), dtype=torch.float32, device="cuda") for st in stride]
+        for t, x in zip(d_x, xs):
+            t[:, :x.shape[1]] = torch.from_numpy(x).cuda()
+        d_p = [torch.full((x.size * 3 + 32,), 0xAB, dtype=torch.uint8, device="cuda") for x in xs]
+        bufs = (f9.DevBuffer * n)(*[f9.DevBuffer(t.data_ptr(), st, ch, f) for t, st, f in zip(d_x, stride, frames)])
+        ptrs = (C.c_void_p * n)(*[t.data_ptr() for t in d_p])
+        torch.cuda.synchronize()
+        c._check(f9.lib().f9_dev_planar_to_pcm24_batch(c.handle, bufs, ptrs, n))
+        c.synchronize()
+        return [t.cpu().numpy() for t in d_p]
+    got = pack(ctx)
+    for x, g in zip(xs, got):
+        assert np.array_equal(g[:x.size * 3], O.planar_to_pcm24(x))
+        assert np.all(g[x.size * 3:] == 0xAB)
+    c2 = f9.Context(0)
+    try:
+        c2.set_option("F9_PCM_BYTEWISE", 1)
+        for a, b in zip(got, pack(c2)):
+            assert np.array_equal(a, b)
+    finally:
+        c2.close()
+    # payload -> planes: 24-bit and 16-bit, same channel count and (mono) duplicated into stereo
+    rng = np.random.default_rng(78 + ch)
+    for fmt, bps in ((3, 3), (2, 2)):
+        raws = [rng.integers(0, 256, bps * ch * f, dtype=np.uint8) for f in frames]
+        for dst_ch in ([1, 2] if ch == 1 else [2]):
+            d_raw = [torch.from_numpy(np.concatenate([r, np.zeros(16, np.uint8)])).cuda() for r in raws]
+            stride = [(f + 3) // 4 * 4 + 8 for f in frames]
+            d_out = [torch.full((dst_ch, st), float("nan"), dtype=torch.float32, device="cuda") for st in stride]
+            bufs = (f9.DevBuffer * n)(*[f9.DevBuffer(t.data_ptr(), st, dst_ch, f) for t, st, f in zip(d_out, stride, frames)])
+            ptrs = (C.c_void_p * n)(*[t.data_ptr() for t in d_raw])
+            torch.cuda.synchronize()
+            ctx._check(f9.lib().f9_dev_pcm_to_planar_batch(ctx.handle, ptrs, fmt, ch, bufs, n))
+            ctx.synchronize()
+            for r, t, f in zip(raws, d_out, frames):
+                g = t.cpu().numpy()
+                if f:
+                    assert np.array_equal(g[:, :f], O.pcm_to_planar(r, fmt, ch, dst_ch)), (fmt, dst_ch, f)
+                assert np.all(np.isnan(g[:, f:]))
+
+
 @pytest.mark.parametrize("ch,frames", [(1, 5), (2, 4099), (3, 70000), (64, 300)])
 def test_interleave_round_trip(ctx, O, ch, frames):
     x = rnd((ch, frames), 10 + ch)

@@ -1,6 +1,8 @@
 #!/usr/bin/env python
-"""Development check of the tensor-core FIR against the oracle: max-abs error and SNR per ratio / kind / signal."""
-import os, sys, time
+"""Error table of the WindowedSinc kernels (GPU, through the C ABI) against the oracle AND against the exact (double-accumulate)
+value, per ratio / signal / amplitude.  The oracle's own distance from the exact value is printed beside it: at 0 dBFS that
+distance alone exceeds 2^-20 for broadband signals, which bounds what ANY evaluation order can reach against the oracle."""
+import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -8,32 +10,43 @@ import __graft_entry__ as g
 f9 = g._load_pkg()
 from oracle import oracle as O
 
+U = 2.0 ** -20
+
 def snr_db(ref, got):
     err = np.sqrt(np.mean((ref.astype(np.float64) - got.astype(np.float64)) ** 2))
     sig = np.sqrt(np.mean(ref.astype(np.float64) ** 2))
     return np.inf if err == 0 else 20 * np.log10(sig / err)
 
+def signal(kind, n, amp, fs, seed):
+    t = np.arange(n) / fs
+    if kind == "noise":
+        return (np.random.default_rng(seed).uniform(-1, 1, n) * amp).astype(np.float32)
+    if kind == "sine":
+        return (amp * np.sin(2 * np.pi * 997.0 * t)).astype(np.float32)
+    if kind == "square":
+        return (amp * 0.999 * np.sign(np.sin(2 * np.pi * 441.0 * t))).astype(np.float32)
+    raise ValueError(kind)
+
 ctx = f9.Context(0)
-rng = np.random.default_rng(0)
-cases = [(96000, 44100), (44100, 48000), (48000, 192000), (48000, 96000), (24000, 192000), (12000, 192000), (96000, 48000), (192000, 48000), (88200, 48000), (44100, 96000), (48000, 44100)]
-n_in = int(sys.argv[1]) if len(sys.argv) > 1 else 60000
-bad = 0
-for kind in (0, 1, 2, 3):
-    for fs_in, fs_out in cases:
-        for amp in (0.5, 1e-3):
-            x = (rng.uniform(-1, 1, (2, n_in)) * amp).astype(np.float32)
-            t0 = time.time()
-            y = ctx.resample(x, fs_in, fs_out, kind)
-            n_out = y.shape[1]
-            ref = np.stack([O.resample_channel(kind, fs_in / fs_out, x[c], n_out)[0] for c in range(2)])
-            err = float(np.max(np.abs(y - ref))); s = snr_db(ref, y)
-            ok = err <= 2.0 ** -20 * max(amp * 2, 1e-3) * 2 and s >= 120
-            bad += not ok
-            print(f"kind {kind} {fs_in}->{fs_out} amp {amp:g}: max err {err:.3e} ({err / 2.0 ** -20:.3f} x 2^-20)  snr {s:.1f} dB {'ok' if ok else 'BAD'}", flush=True)
+cases = [(96000, 44100), (44100, 48000), (88200, 48000), (96000, 48000), (192000, 48000), (48000, 192000), (48000, 96000),
+         (24000, 192000), (44100, 96000), (48000, 44100)]
+n_in = int(sys.argv[1]) if len(sys.argv) > 1 else 120000
+print(f"{'ratio':>16s} {'signal':>7s} {'amp':>5s} | {'gpu-oracle':>10s} {'gpu-exact':>10s} {'oracle-exact':>12s} (x 2^-20, max abs) | {'snr vs oracle':>13s} | max|y|")
+worst = dict(go=0.0, ge=0.0, oe=0.0)
+for fs_in, fs_out in cases:
+    for kind in ("sine", "noise", "square"):
+        for amp in (0.5, 1.0):
+            x = signal(kind, n_in, amp, fs_in, 7)
+            y = ctx.resample(x[None, :], fs_in, fs_out, 0)[0]
+            ref = O.resample_channel(0, fs_in / fs_out, x, y.size)[0]
+            ex = O.resample_channel_exact(fs_in / fs_out, x, y.size)
+            go, ge, oe = np.abs(y - ref).max() / U, np.abs(y - ex).max() / U, np.abs(ref - ex).max() / U
+            if amp == 1.0:
+                worst["go"] = max(worst["go"], go); worst["ge"] = max(worst["ge"], ge); worst["oe"] = max(worst["oe"], oe)
+            print(f"{fs_in:>7d}->{fs_out:<7d} {kind:>7s} {amp:5.1f} | {go:10.3f} {ge:10.3f} {oe:12.3f} {'':22s} | {snr_db(ref, y):10.1f} dB | {np.abs(ex).max():.3f}", flush=True)
+print(f"worst at amp 1.0: gpu-oracle {worst['go']:.3f}, gpu-exact {worst['ge']:.3f}, oracle-exact {worst['oe']:.3f} (x 2^-20)")
 # out-of-range input -> fp32 redo
-x = (rng.uniform(-1, 1, (1, 20000))).astype(np.float32); x[0, 5000] = 70000.0
+x = (np.random.default_rng(0).uniform(-1, 1, (1, 20000))).astype(np.float32); x[0, 5000] = 70000.0
 y = ctx.resample(x, 96000, 44100, 0)
 ref = O.resample_channel(0, 96000 / 44100, x[0], y.shape[1])[0]
 print("overflow redo: max err", float(np.max(np.abs(y[0] - ref))))
-print("launches", ctx.launch_count, "bad", bad)
-sys.exit(1 if bad else 0)
