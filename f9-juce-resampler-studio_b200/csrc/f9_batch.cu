@@ -17,6 +17,7 @@ namespace {
 inline long long pad64(long long frames) { return (std::max<long long>(frames, 1) + 63) / 64 * 64; }
 
 struct JobPlan {
+    f9_job_ext ext;
     int latency_frames = 0, start = 0, copied = 0, out_frames = 0;
     bool convert = false;
     double ratio = 1.0;
@@ -28,14 +29,15 @@ struct JobPlan {
 
 inline int pcm_bps(int fmt) { return fmt == F9_PCM_U8 ? 1 : fmt == F9_PCM_S16LE ? 2 : fmt == F9_PCM_S24LE ? 3 : 4; }
 
-int validate(const f9_job& j) {
+int validate(const f9_job& j, const f9_job_ext& x) {
     if (j.numCh <= 0 || j.captured_frames < 0 || j.original_length < 0) return F9_ERR_INVALID;
     if (j.src_pcm) { if (j.src_fmt < F9_PCM_U8 || j.src_fmt > F9_PCM_F32LE || j.src_ch <= 0) return F9_ERR_INVALID; }
     else {
         if (!j.captured) return F9_ERR_INVALID;
         for (int c = 0; c < j.numCh; ++c) if (j.captured_frames > 0 && !j.captured[c]) return F9_ERR_INVALID;
     }
-    if (!j.out && !((j.flags & F9_JOB_PCM24) && j.out_pcm24)) return F9_ERR_INVALID;        // a job must deliver something
+    if (!x.tail_only && !j.out && !((j.flags & F9_JOB_PCM24) && j.out_pcm24)) return F9_ERR_INVALID;        // a job must deliver something
+    if (x.num_out < 0 || x.n0 < 0 || (x.num_out > 0 && (j.fs_in == j.fs_out || (j.flags & (F9_JOB_REMOVE_DC | F9_JOB_TAIL_SCAN))))) return F9_ERR_INVALID;
     if (!(j.fs_in > 0.0) || !(j.fs_out > 0.0)) return F9_ERR_INVALID;
     if (interp_memory(j.interp_kind) == 0) return F9_ERR_INVALID;
     if ((j.flags & F9_JOB_TAIL_SCAN) && (j.tail_window <= 0 || j.tail_hop <= 0 || j.tail_required <= 0 ||
@@ -172,7 +174,7 @@ int run_chunk(f9_context* ctx, const f9_job* jobs, f9_result* results, const std
         for (int t = 0; t < n; ++t) {
             const f9_job& J = jobs[idx[(size_t) t]];
             const JobPlan& P = plans[(size_t) t];
-            if (P.convert && !(J.flags & F9_JOB_REMOVE_DC)) continue;      // fused into the resampler by pointer offset
+            if (P.ext.tail_only || (P.convert && !(J.flags & F9_JOB_REMOVE_DC))) continue;      // fused into the resampler by pointer offset
             tc.push_back(P.cap); to.push_back(P.trimmed); lat.push_back(J.latency_samples);
             dcMask.push_back((J.flags & F9_JOB_REMOVE_DC) ? 1 : 0);
             maxCh = std::max(maxCh, J.numCh); maxFrames = std::max(maxFrames, J.original_length);
@@ -214,8 +216,8 @@ int run_chunk(f9_context* ctx, const f9_job* jobs, f9_result* results, const std
                 Seg S{};
                 if (J.flags & F9_JOB_REMOVE_DC) { S.in = P.trimmed.base + c * P.trimmed.chStride; S.inAvail = J.original_length; }
                 else { S.in = P.cap.base + c * P.cap.chStride + std::max(P.start, 0); S.inAvail = P.copied; }
-                S.inOffset = 0;
-                S.out = const_cast<float*>(P.out.base) + c * P.out.chStride; S.n0 = 0; S.numOut = P.out_frames;
+                S.inOffset = P.ext.num_out > 0 ? P.ext.in_offset : 0;
+                S.out = const_cast<float*>(P.out.base) + c * P.out.chStride; S.n0 = P.ext.num_out > 0 ? P.ext.n0 : 0; S.numOut = P.out_frames;
                 g.push_back(S);
             }
         }
@@ -271,6 +273,10 @@ int run_chunk(f9_context* ctx, const f9_job* jobs, f9_result* results, const std
 }  // namespace
 
 extern "C" int f9_process_batch(f9_context* ctx, const f9_job* jobs, int n_jobs, f9_result* results) {
+    return f9_process_batch_ext(ctx, jobs, nullptr, n_jobs, results);
+}
+
+int f9_process_batch_ext(f9_context* ctx, const f9_job* jobs, const f9_job_ext* ext, int n_jobs, f9_result* results) {
     if (!ctx) return F9_ERR_INVALID;
     if (n_jobs < 0 || (n_jobs > 0 && (!jobs || !results))) return ctx->fail(F9_ERR_INVALID, "bad job array");
     F9_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -312,9 +318,10 @@ extern "C" int f9_process_batch(f9_context* ctx, const f9_job* jobs, int n_jobs,
         const f9_job& J = jobs[i];
         f9_result& R = results[i];
         R = f9_result{}; R.tail_stop_frame = -1;
-        R.status = validate(J);
-        if (R.status) { worst = R.status; ctx->err = "invalid job"; continue; }
         JobPlan P;
+        if (ext) P.ext = ext[i];
+        R.status = validate(J, P.ext);
+        if (R.status) { worst = R.status; ctx->err = "invalid job"; continue; }
         // trimLatency arithmetic (Source/MainComponent.cpp:833-845)
         P.latency_frames = J.latency_samples / J.numCh;
         P.start = P.latency_frames;
@@ -324,6 +331,8 @@ extern "C" int f9_process_batch(f9_context* ctx, const f9_job* jobs, int n_jobs,
         P.convert = (J.fs_in != J.fs_out);
         P.ratio = J.fs_in / J.fs_out;
         P.out_frames = P.convert ? (int) f9_resampled_length(J.original_length, J.fs_in, J.fs_out) : J.original_length;
+        if (P.ext.num_out > 0) P.out_frames = (int) P.ext.num_out;       // a time segment of the conversion
+        if (P.ext.tail_only) { P.out_frames = 0; P.convert = false; }
         if (J.out && J.out_capacity < P.out_frames) { R.status = F9_ERR_INVALID; worst = R.status; ctx->err = "out_capacity too small"; continue; }
         if (J.flags & F9_JOB_TAIL_SCAN) {
             const long long startFrame = (long long) J.original_length + std::max(P.latency_frames, 0);

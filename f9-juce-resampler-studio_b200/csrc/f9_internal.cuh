@@ -398,6 +398,13 @@ struct f9_context {
     int   get_poly(int kind, long long p, long long q, f9::PolyDev* out);
 };
 
+// A job of f9_process_batch restricted to a time segment of its conversion (f9_multi.cpp: long files split over GPUs): the job's
+// `captured` window starts at sample in_offset of the trimmed channel (samples outside the window read as zero, as everywhere),
+// it produces outputs [n0, n0 + num_out) of the conversion into out[c][0 ..) / out_pcm24[0 ..).  num_out == 0: an ordinary job.
+// tail_only: the job only runs its reverb-tail scan (no trim, no conversion, no outputs).
+struct f9_job_ext { long long n0 = 0, num_out = 0, in_offset = 0; int tail_only = 0; };
+int f9_process_batch_ext(f9_context* ctx, const f9_job* jobs, const f9_job_ext* ext /* may be null */, int n_jobs, f9_result* results);
+
 #define F9_TRY_CUDA(ctx, call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return (ctx)->fail_cuda(e__, #call); } while (0)
 // end of a blocking entry point: wait for the stream, after which the arenas may be reused from offset 0
 #define F9_FINISH(ctx) do { cudaError_t e__ = cudaStreamSynchronize((ctx)->stream); \

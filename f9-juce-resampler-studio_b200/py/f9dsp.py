@@ -55,6 +55,11 @@ class Job(C.Structure):
                 ("src_pcm", C.c_void_p), ("src_fmt", C.c_int), ("src_ch", C.c_int)]
 
 
+class Unit(C.Structure):
+    _fields_ = [("job", C.c_int), ("device", C.c_int), ("ch0", C.c_int), ("num_ch", C.c_int), ("n0", C.c_longlong),
+                ("num_out", C.c_longlong), ("tail_only", C.c_int), ("reserved", C.c_int), ("cost", C.c_longlong)]
+
+
 class Result(C.Structure):
     _fields_ = [("status", C.c_int), ("latency_frames", C.c_int), ("trim_start", C.c_int), ("frames_copied", C.c_int),
                 ("out_frames", C.c_int), ("tail_stop_frame", C.c_longlong), ("tail_polls", C.c_int)]
@@ -123,6 +128,16 @@ SYMBOLS = [
     ("f9_sinc_table_get", _i, [_vp, _fp]),
     ("f9_resampled_length", _ll, [_ll, _d, _d]),
     ("f9_process_batch", _i, [_vp, C.POINTER(Job), _i, C.POINTER(Result)]),
+    ("f9_multi_create", _i, [_ip, _i, C.POINTER(_vp)]),
+    ("f9_multi_destroy", None, [_vp]),
+    ("f9_multi_device_count", _i, [_vp]),
+    ("f9_multi_context", _vp, [_vp, _i]),
+    ("f9_multi_last_error", C.c_char_p, [_vp]),
+    ("f9_multi_process_batch", _i, [_vp, C.POINTER(Job), _i, C.POINTER(Result), _ip]),
+    ("f9_shard_units", _i, [_llp, _i, _i, _ip]),
+    ("f9_multi_partition", _i, [C.POINTER(Job), _i, _i, _ll, C.POINTER(Unit), _i, _ip]),
+    ("f9_process_units", _i, [_vp, C.POINTER(Job), _i, C.POINTER(Unit), _i, _i, C.POINTER(Result)]),
+    ("f9_merge_unit_results", _i, [C.POINTER(Job), _i, C.POINTER(Unit), C.POINTER(Result), _i, C.POINTER(Result)]),
     ("f9_dev_find_peak_batch", _i, [_vp, C.POINTER(DevBuffer), _i, _f, _vp]),
     ("f9_measure_latency", _i, [_vp, _fpp, _i, _i, C.c_float, _ip, _fp]),
     ("f9_dev_latency_stats_batch", _i, [_vp, C.POINTER(DevBuffer), _i, C.c_float, _vp, _vp, _vp]),
@@ -225,6 +240,128 @@ def _chan_ptrs(a: np.ndarray):
 
 def _p(a: np.ndarray):
     return a.ctypes.data_as(_fp)
+
+
+class BuiltJobs:
+    """f9_job array built from job dicts, with everything it points to kept alive."""
+
+    def __init__(self, n):
+        self.n = n
+        self.J = (Job * max(n, 1))()
+        self.R = (Result * max(n, 1))()
+        self.keep, self.outs, self.pcms = [], [], []
+
+    def finish(self, rc, check):
+        R, n = self.R, self.n
+        res = [dict(status=R[i].status, latency_frames=R[i].latency_frames, trim_start=R[i].trim_start,
+                    frames_copied=R[i].frames_copied, out_frames=R[i].out_frames,
+                    tail_stop_frame=R[i].tail_stop_frame, tail_polls=R[i].tail_polls) for i in range(n)]
+        if rc < 0 and all(r["status"] == 0 for r in res):
+            check(rc)
+        outputs = [o[:, :f] for (o, f) in self.outs]
+        pcm_out = [None if p is None else p[: res[i]["out_frames"] * outputs[i].shape[0] * 3] for i, p in enumerate(self.pcms)]
+        return outputs, pcm_out, res
+
+
+def build_jobs(jobs: list[dict]) -> BuiltJobs:
+    B = BuiltJobs(len(jobs))
+    J, keep = B.J, B.keep
+    for i, j in enumerate(jobs):
+        fs_in, fs_out = float(j.get("fs_in", 44100.0)), float(j.get("fs_out", 44100.0))
+        out_frames = resampled_length(j["original_length"], fs_in, fs_out) if fs_in != fs_out else j["original_length"]
+        if "src_pcm" in j:          # the capture as file bytes: (raw uint8 array, fmt, src_ch[, numCh])
+            raw, fmt, src_ch = j["src_pcm"][:3]
+            raw = np.ascontiguousarray(raw).view(np.uint8).ravel()
+            num_ch = j["src_pcm"][3] if len(j["src_pcm"]) > 3 else src_ch
+            frames = raw.size // (_BYTES[fmt] * src_ch)
+            J[i].src_pcm, J[i].src_fmt, J[i].src_ch = raw.ctypes.data, fmt, src_ch
+            J[i].numCh, J[i].captured_frames = num_ch, frames
+            keep.append(raw)
+        else:
+            cap = _planar(j["captured"])
+            cp = _chan_ptrs(cap)
+            keep += [cap, cp]
+            num_ch = cap.shape[0]
+            J[i].captured, J[i].numCh, J[i].captured_frames = cp, cap.shape[0], cap.shape[1]
+        flags = 0
+        if j.get("no_float_out"):
+            out = np.zeros((num_ch, 0), dtype=np.float32)
+        else:
+            out = np.full((num_ch, max(out_frames, 1)), np.nan, dtype=np.float32)
+            op = _chan_ptrs(out)
+            keep += [out, op]
+            J[i].out, J[i].out_capacity = op, out.shape[1]
+        J[i].latency_samples, J[i].original_length = j["latency_samples"], j["original_length"]
+        J[i].fs_in, J[i].fs_out, J[i].interp_kind = fs_in, fs_out, j.get("kind", WINDOWED_SINC)
+        if "tail" in j:
+            w, h, r, m, has, nf, mg = j["tail"]
+            flags |= JOB_TAIL_SCAN
+            J[i].tail_window, J[i].tail_hop, J[i].tail_required, J[i].tail_mode = w, h, r, m
+            J[i].has_nf, J[i].nf_db, J[i].margin_pct = int(has), nf, mg
+        if j.get("remove_dc"):
+            flags |= JOB_REMOVE_DC
+        pcm = None
+        if j.get("pcm24"):
+            flags |= JOB_PCM24
+            pcm = np.zeros(max(out_frames, 1) * num_ch * 3, dtype=np.uint8)
+            J[i].out_pcm24 = pcm.ctypes.data
+            keep.append(pcm)
+        J[i].flags = flags
+        B.outs.append((out, out_frames if not j.get("no_float_out") else 0))
+        B.pcms.append(pcm)
+    return B
+
+
+class Multi:
+    """f9_multi: the batch job flow over several GPUs (one context and one host thread per device-list entry)."""
+
+    def __init__(self, devices):
+        devs = (C.c_int * len(devices))(*devices)
+        self._h = C.c_void_p(None)
+        rc = lib().f9_multi_create(devs, len(devices), C.byref(self._h))
+        if rc:
+            raise F9Error(rc, (lib().f9_last_error(None) or b"").decode())
+        self.devices = list(devices)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().f9_multi_destroy(self._h)
+            self._h = C.c_void_p(None)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc < 0:
+            raise F9Error(rc, (lib().f9_multi_last_error(self._h) or b"").decode())
+        return rc
+
+    def process_batch(self, jobs: list[dict]):
+        B = build_jobs(jobs)
+        dev = (C.c_int * max(B.n, 1))()
+        rc = lib().f9_multi_process_batch(self._h, B.J, B.n, B.R, dev)
+        outs, pcms, res = B.finish(rc, self._check)
+        for i, r in enumerate(res):
+            r["device"] = dev[i]
+        return outs, pcms, res
+
+
+def partition(J, n_jobs: int, n_devices: int, seg_out: int = 0):
+    """f9_multi_partition over an f9_job array: list of Unit."""
+    cap = n_jobs + 64
+    while True:
+        U = (Unit * cap)()
+        nu = C.c_int(0)
+        rc = lib().f9_multi_partition(J, n_jobs, n_devices, seg_out, U, cap, C.byref(nu))
+        if rc == ERR_NOMEM:
+            cap = nu.value
+            continue
+        if rc:
+            raise F9Error(rc, "partition failed")
+        return U, nu.value
 
 
 class Context:
@@ -406,65 +543,12 @@ class Context:
 
     # ---- E. batch flow
     def process_batch(self, jobs: list[dict]):
-        """jobs: dicts with captured (numCh x frames), latency_samples, original_length, fs_in, fs_out, kind, and optional
-        tail=(window, hop, required, mode, has_nf, nf_db, margin), remove_dc, pcm24.  Returns (outputs, pcm, results)."""
-        n = len(jobs)
-        J = (Job * max(n, 1))()
-        R = (Result * max(n, 1))()
-        keep = []
-        outs, pcms = [], []
-        for i, j in enumerate(jobs):
-            fs_in, fs_out = float(j.get("fs_in", 44100.0)), float(j.get("fs_out", 44100.0))
-            out_frames = resampled_length(j["original_length"], fs_in, fs_out) if fs_in != fs_out else j["original_length"]
-            if "src_pcm" in j:          # the capture as file bytes: (raw uint8 array, fmt, src_ch[, numCh])
-                raw, fmt, src_ch = j["src_pcm"][:3]
-                raw = np.ascontiguousarray(raw).view(np.uint8).ravel()
-                num_ch = j["src_pcm"][3] if len(j["src_pcm"]) > 3 else src_ch
-                frames = raw.size // (_BYTES[fmt] * src_ch)
-                J[i].src_pcm, J[i].src_fmt, J[i].src_ch = raw.ctypes.data, fmt, src_ch
-                J[i].numCh, J[i].captured_frames = num_ch, frames
-                keep.append(raw)
-            else:
-                cap = _planar(j["captured"])
-                cp = _chan_ptrs(cap)
-                keep += [cap, cp]
-                num_ch = cap.shape[0]
-                J[i].captured, J[i].numCh, J[i].captured_frames = cp, cap.shape[0], cap.shape[1]
-            flags = 0
-            if j.get("no_float_out"):
-                out = np.zeros((num_ch, 0), dtype=np.float32)
-            else:
-                out = np.full((num_ch, max(out_frames, 1)), np.nan, dtype=np.float32)
-                op = _chan_ptrs(out)
-                keep += [out, op]
-                J[i].out, J[i].out_capacity = op, out.shape[1]
-            J[i].latency_samples, J[i].original_length = j["latency_samples"], j["original_length"]
-            J[i].fs_in, J[i].fs_out, J[i].interp_kind = fs_in, fs_out, j.get("kind", WINDOWED_SINC)
-            if "tail" in j:
-                w, h, r, m, has, nf, mg = j["tail"]
-                flags |= JOB_TAIL_SCAN
-                J[i].tail_window, J[i].tail_hop, J[i].tail_required, J[i].tail_mode = w, h, r, m
-                J[i].has_nf, J[i].nf_db, J[i].margin_pct = int(has), nf, mg
-            if j.get("remove_dc"):
-                flags |= JOB_REMOVE_DC
-            pcm = None
-            if j.get("pcm24"):
-                flags |= JOB_PCM24
-                pcm = np.zeros(max(out_frames, 1) * num_ch * 3, dtype=np.uint8)
-                J[i].out_pcm24 = pcm.ctypes.data
-                keep.append(pcm)
-            J[i].flags = flags
-            outs.append((out, out_frames if not j.get("no_float_out") else 0))
-            pcms.append(pcm)
-        rc = lib().f9_process_batch(self._h, J, n, R)
-        res = [dict(status=R[i].status, latency_frames=R[i].latency_frames, trim_start=R[i].trim_start,
-                    frames_copied=R[i].frames_copied, out_frames=R[i].out_frames,
-                    tail_stop_frame=R[i].tail_stop_frame, tail_polls=R[i].tail_polls) for i in range(n)]
-        if rc < 0 and all(r["status"] == 0 for r in res):
-            self._check(rc)
-        outputs = [o[:, :f] for (o, f) in outs]
-        pcm_out = [None if p is None else p[: res[i]["out_frames"] * outputs[i].shape[0] * 3] for i, p in enumerate(pcms)]
-        return outputs, pcm_out, res
+        """jobs: dicts with captured (numCh x frames) or src_pcm=(raw bytes, fmt, src_ch[, numCh]), latency_samples, original_length,
+        fs_in, fs_out, kind, and optional tail=(window, hop, required, mode, has_nf, nf_db, margin), remove_dc, pcm24, no_float_out.
+        Returns (outputs, pcm, results)."""
+        B = build_jobs(jobs)
+        rc = lib().f9_process_batch(self._h, B.J, B.n, B.R)
+        return B.finish(rc, self._check)
 
     # ---- G. format convert
     def pcm_to_planar(self, raw, fmt: int, src_ch: int, dst_ch: int | None = None) -> np.ndarray:

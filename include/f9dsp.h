@@ -374,6 +374,41 @@ F9_API int f9_dev_pcm_to_planar_batch(f9_context* ctx, const void* const* d_srcs
                                       const f9_dev_buffer* dst, int n);
 F9_API int f9_dev_planar_to_pcm24_batch(f9_context* ctx, const f9_dev_buffer* src, unsigned char* const* d_dsts, int n);
 
+/* ===================== H. the batch job flow over several GPUs ===================== */
+/* The reference's batch loop is one process over AppState.files (Source/MainComponent.cpp:581-621, :705-805).  The path shards
+ * with no exchange step: unit of work = a file, or -- for a file that is large against one GPU's share -- a group of its channels
+ * and / or a time segment of its conversion (input window with its own halo, f9_resample_segment_input_range); units are packed
+ * greedily by output-sample count; one host thread and one f9_context per GPU; results are gathered on the host (no NCCL). */
+typedef struct f9_multi f9_multi;
+typedef struct f9_unit {
+    int job;                        /* index into the job array                                                          */
+    int device;                     /* 0 .. n_devices-1: position in the device list, set by f9_multi_partition          */
+    int ch0, num_ch;                /* channels [ch0, ch0 + num_ch) of the job                                           */
+    long long n0, num_out;          /* outputs [n0, n0 + num_out) of the conversion; num_out == 0: all of them           */
+    int tail_only;                  /* the job's reverb-tail scan alone (split jobs)                                     */
+    int reserved;
+    long long cost;                 /* output samples (packing weight)                                                   */
+} f9_unit;
+/* devices: CUDA ordinals, one context (and, inside f9_multi_process_batch, one host thread) each.  The same ordinal may appear
+ * more than once (two contexts sharing a GPU). */
+F9_API int  f9_multi_create(const int* devices, int n_devices, f9_multi** out);
+F9_API void f9_multi_destroy(f9_multi* m);
+F9_API int  f9_multi_device_count(const f9_multi* m);
+F9_API f9_context* f9_multi_context(f9_multi* m, int i);
+F9_API const char* f9_multi_last_error(const f9_multi* m);
+/* f9_process_batch over all the GPUs of m: partition, one thread per GPU, merge.  out_device (optional, n_jobs ints): the device
+ * list position the job (or its first unit) ran on. */
+F9_API int  f9_multi_process_batch(f9_multi* m, const f9_job* jobs, int n_jobs, f9_result* results, int* out_device);
+/* The pieces, for hosts that run one process per GPU (bench.py under torchrun): every process computes the same partition, runs
+ * the units of its own device on its own context and the per-job results are merged wherever they are gathered.
+ * f9_shard_units: greedy packing, largest first onto the least loaded bin (ties: lower index). */
+F9_API int  f9_shard_units(const long long* costs, int n, int world, int* out_bin);
+F9_API int  f9_multi_partition(const f9_job* jobs, int n_jobs, int n_devices, long long seg_out, f9_unit* units, int max_units, int* n_units);
+F9_API int  f9_process_units(f9_context* ctx, const f9_job* jobs, int n_jobs, const f9_unit* units, int n_units, int device,
+                             f9_result* unit_results);
+F9_API int  f9_merge_unit_results(const f9_job* jobs, int n_jobs, const f9_unit* units, const f9_result* unit_results, int n_units,
+                                  f9_result* results);
+
 #ifdef __cplusplus
 }
 #endif
