@@ -284,9 +284,13 @@ int f9_process_batch_ext(f9_context* ctx, const f9_job* jobs, const f9_job_ext* 
     F9_TRY_CUDA(ctx, cudaMemGetInfo(&freeB, &totalB));
     // Chunks are pipelined over two slots: while chunk k's kernels and downloads run on one stream, chunk k+1 uploads on
     // the other (PCIe is full duplex and the copy engines are independent), so a large batch costs about
-    // max(upload, download) instead of their sum.  A chunk is ~64 MB of device memory (option F9_BATCH_CHUNK_MB; measured best on B200 / PCIe 5,
-    // 48 ms against 60 ms unpipelined for 2.1 GB up + 0.9 GB down; smaller chunks pay the per-chunk synchronisation).
-    const size_t chunkMB = (size_t) std::max(1, ctx->diag.get("F9_BATCH_CHUNK_MB", 64));
+    // max(upload, download) instead of their sum.  Chunk size in device memory (option F9_BATCH_CHUNK_MB overrides), measured on
+    // B200 / PCIe 5 with config 2's 256 files (tools/e2e_probe.py): float planes up and down 64 MB (44.6 ms; 53.6 ms at 256 MB),
+    // file bytes up 256 MB (33.8 ms with the 24-bit payload down; 42.6 ms at 64 MB): a chunk costs a synchronisation and a
+    // pipeline bubble of its own upload + download, which the smaller payload of the byte form amortises later.
+    bool anyFloatIn = false;
+    for (int i = 0; i < n_jobs; ++i) anyFloatIn = anyFloatIn || !jobs[i].src_pcm;
+    const size_t chunkMB = (size_t) std::max(1, ctx->diag.get("F9_BATCH_CHUNK_MB", anyFloatIn ? 64 : 256));
     const size_t budget = std::min(std::max<size_t>((freeB + ctx->d_cap + ctx->parked.d_cap) / 4, 64u << 20), chunkMB << 20);
     if (!ctx->alt_stream) {
         F9_TRY_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->alt_stream, cudaStreamNonBlocking));

@@ -1,5 +1,5 @@
 """Worker of tests/test_sharding_cpu.py: run under torchrun with the gloo backend (CPU), one process per "GPU".
-Each rank takes its shard of a job list (workloads.shard_units: SURVEY 8(e), no data-path collective), computes the shard's
+Each rank takes its shard of a job list (f9_shard_units of the product: SURVEY 8(e), no data-path collective), computes the shard's
 scalar results with the oracle standing in for the device, and the results are gathered on rank 0 -- the same host-side
 flow bench.py and a multi-GPU host use around the library.  Rank 0 writes the gathered results as JSON to argv[1]."""
 import importlib.util
@@ -15,10 +15,19 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 from oracle import oracle as O  # noqa: E402
 
-spec = importlib.util.spec_from_file_location("f9workloads_w", os.path.join(ROOT, "f9-juce-resampler-studio_b200", "py", "workloads.py"))
-W = importlib.util.module_from_spec(spec)
-sys.modules["f9workloads_w"] = W
-spec.loader.exec_module(W)
+spec = importlib.util.spec_from_file_location("f9dsp_w", os.path.join(ROOT, "f9-juce-resampler-studio_b200", "py", "f9dsp.py"))
+F9 = importlib.util.module_from_spec(spec)
+sys.modules["f9dsp_w"] = F9
+spec.loader.exec_module(F9)
+
+
+def shard_units(costs, world):
+    """The product's greedy packing (f9_shard_units, host code of libf9dsp.so): bins of unit indices."""
+    import ctypes as C
+    n = len(costs)
+    bins = (C.c_int * n)()
+    assert F9.lib().f9_shard_units((C.c_longlong * n)(*costs), n, world, bins) == 0
+    return [[i for i in range(n) if bins[i] == r] for r in range(world)]
 
 
 def job(i):
@@ -35,7 +44,7 @@ def main():
     rank, world = dist.get_rank(), dist.get_world_size()
     n_jobs = 11
     costs = [job(i)[2] for i in range(n_jobs)]
-    mine = W.shard_units(costs, world)[rank]
+    mine = shard_units(costs, world)[rank]
     out = {}
     for i in mine:
         cap, lat, frames = job(i)
@@ -51,7 +60,7 @@ def main():
         merged = {}
         for g in gathered:
             merged.update({str(k): v for k, v in g.items()})
-        json.dump({"results": merged, "max_ms": float(t.item()), "world": world, "shards": W.shard_units(costs, world)}, open(sys.argv[1], "w"))
+        json.dump({"results": merged, "max_ms": float(t.item()), "world": world, "shards": shard_units(costs, world)}, open(sys.argv[1], "w"))
     dist.barrier()
     dist.destroy_process_group()
 
