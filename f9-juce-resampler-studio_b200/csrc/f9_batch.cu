@@ -176,7 +176,7 @@ int run_chunk(f9_context* ctx, const f9_job* jobs, f9_result* results, const std
             const JobPlan& P = plans[(size_t) t];
             if (P.ext.tail_only || (P.convert && !(J.flags & F9_JOB_REMOVE_DC))) continue;      // fused into the resampler by pointer offset
             tc.push_back(P.cap); to.push_back(P.trimmed); lat.push_back(J.latency_samples);
-            dcMask.push_back((J.flags & F9_JOB_REMOVE_DC) ? 1 : 0);
+            dcMask.push_back((J.flags & F9_JOB_REMOVE_DC) ? ((J.flags & F9_JOB_DC_REFERENCE_ORDER) ? 2 : 1) : 0);
             maxCh = std::max(maxCh, J.numCh); maxFrames = std::max(maxFrames, J.original_length);
         }
         if (!tc.empty()) {

@@ -461,6 +461,9 @@ int f9_trim_latency_swift(f9_context* ctx, const float* captured, long long coun
 }
 
 int f9_remove_dc_offset(f9_context* ctx, float* const* ch, int numCh, int numFrames) {
+    return f9_remove_dc_offset_ex(ctx, ch, numCh, numFrames, 1);      // the drop-in for MainComponent::removeDCOffset: its own arithmetic
+}
+int f9_remove_dc_offset_ex(f9_context* ctx, float* const* ch, int numCh, int numFrames, int reference_order) {
     int rc = check_planar(ctx, ch, numCh, numFrames); if (rc) return rc;
     if (numCh == 0 || numFrames == 0) return F9_OK;
     rc = ctx->arena_reserve(planar_bytes(numCh, numFrames) + sizeof(double) * (size_t) numCh * kDcPartials + 16384, 4096); if (rc) return rc;
@@ -469,7 +472,7 @@ int f9_remove_dc_offset(f9_context* ctx, float* const* ch, int numCh, int numFra
     DevBuf* d_b;
     rc = upload_array(ctx, &hb, 1, &d_b); if (rc) return rc;
     double* d_sums = (double*) ctx->d_alloc(sizeof(double) * (size_t) numCh * kDcPartials);
-    F9_TRY_CUDA(ctx, launch_remove_dc(d_b, 1, numCh, numFrames, d_sums, ctx->stream, &ctx->launches));
+    F9_TRY_CUDA(ctx, launch_remove_dc(d_b, 1, numCh, numFrames, d_sums, ctx->stream, &ctx->launches, reference_order ? 2 : 1));
     for (int c = 0; c < numCh; ++c)
         F9_TRY_CUDA(ctx, cudaMemcpyAsync(ch[c], hb.base + c * hb.chStride, sizeof(float) * (size_t) numFrames, cudaMemcpyDeviceToHost, ctx->stream));
     F9_FINISH(ctx);
@@ -864,7 +867,7 @@ int f9_dev_trim_batch(f9_context* ctx, const f9_dev_buffer* captured, const int*
     rc = upload_array(ctx, ho, (size_t) n, &d_o); if (rc) return rc;
     rc = upload_array(ctx, latency_samples, (size_t) n, &d_lat); if (rc) return rc;
     double* d_part = remove_dc ? (double*) ctx->d_alloc(sizeof(double) * (size_t) n * maxCh * kDcPartials) : nullptr;      // fused removeDCOffset
-    F9_TRY_CUDA(ctx, launch_trim(d_c, d_lat, d_o, n, maxFrames, maxCh, ctx->stream, &ctx->launches, d_part, nullptr));
+    F9_TRY_CUDA(ctx, launch_trim(d_c, d_lat, d_o, n, maxFrames, maxCh, ctx->stream, &ctx->launches, d_part, nullptr, remove_dc == 2 ? 2 : 1));
     return F9_OK;
 }
 

@@ -92,25 +92,55 @@ __device__ __forceinline__ void dc_partial(const float* __restrict__ x, int fram
         *dstPartial = t;
     }
 }
+// Reference order (mode 2): the reference's own accumulator -- one float, the channel's samples added one after the other
+// (Source/MainComponent.cpp:892-896).  That chain is sequential by definition, so one thread walks it (loads run ahead of the
+// adds); the sum lands in partial 0, the other partials are zero, and (float) total / frames below is the reference's dcOffset
+// bit for bit.  About 2 ms for a 10 s channel at 96 kHz, every channel of the batch at the same time.
+__device__ __forceinline__ void dc_sequential(const float* __restrict__ x, int frames, double* __restrict__ dstPartials) {
+    if (threadIdx.x != 0) return;
+    if (blockIdx.x != 0) { dstPartials[blockIdx.x] = 0.0; return; }
+    float sum = 0.0f;
+    int i = 0;
+    for (; i < frames && ((reinterpret_cast<uintptr_t>(x + i) & 15) != 0); ++i) sum = __fadd_rn(sum, __ldg(x + i));
+    const float4* __restrict__ xv = reinterpret_cast<const float4*>(x + i);
+    const int nv = (frames - i) >> 2;
+    int k = 0;
+    for (; k + 4 <= nv; k += 4) {                              // four independent loads in flight, then sixteen ordered adds
+        const float4 a = __ldg(xv + k), b = __ldg(xv + k + 1), c = __ldg(xv + k + 2), d = __ldg(xv + k + 3);
+        sum = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(sum, a.x), a.y), a.z), a.w);
+        sum = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(sum, b.x), b.y), b.z), b.w);
+        sum = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(sum, c.x), c.y), c.z), c.w);
+        sum = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(sum, d.x), d.y), d.z), d.w);
+    }
+    for (; k < nv; ++k) { const float4 a = __ldg(xv + k); sum = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(sum, a.x), a.y), a.z), a.w); }
+    for (i += 4 * nv; i < frames; ++i) sum = __fadd_rn(sum, __ldg(x + i));
+    dstPartials[0] = (double) sum;
+}
 // grid: (kDcPartials, channel, buffer)
 __global__ void __launch_bounds__(kThreads)
-dc_sum_kernel(const DevBuf* __restrict__ bufs, int maxCh, double* __restrict__ partials) {
+dc_sum_kernel(const DevBuf* __restrict__ bufs, int maxCh, double* __restrict__ partials, int mode) {
     const int b = blockIdx.z, ch = blockIdx.y;
     const DevBuf B = bufs[b];
     if (ch >= B.numCh) return;
-    dc_partial(B.base + (long long) ch * B.chStride, B.numFrames, partials + ((size_t) b * maxCh + ch) * kDcPartials + blockIdx.x);
+    double* dst = partials + ((size_t) b * maxCh + ch) * kDcPartials;
+    if (mode == 2) dc_sequential(B.base + (long long) ch * B.chStride, B.numFrames, dst);
+    else dc_partial(B.base + (long long) ch * B.chStride, B.numFrames, dst + blockIdx.x);
 }
 // The same over the region trimLatency copies (the zero padding adds nothing to the sum): the mean of the trimmed buffer
 // without materialising it first.
 __global__ void __launch_bounds__(kThreads)
 dc_sum_src_kernel(const DevBuf* __restrict__ cap, const int* __restrict__ latency, const DevBuf* __restrict__ out, int maxCh,
-                  double* __restrict__ partials) {
+                  double* __restrict__ partials, const int* __restrict__ dcMask, int dcDefault) {
     const int b = blockIdx.z, ch = blockIdx.y;
     const DevBuf C = cap[b];
     const DevBuf O = out[b];
     if (ch >= O.numCh) return;
+    const int mode = dcMask ? dcMask[b] : dcDefault;           // 0 no DC removal, 1 parallel double sum, 2 the reference's sequential float sum
+    if (mode == 0) return;
     const TrimGeom G = trim_geom(C, O, latency[b], ch);
-    dc_partial(G.src, G.n, partials + ((size_t) b * maxCh + ch) * kDcPartials + blockIdx.x);
+    double* dst = partials + ((size_t) b * maxCh + ch) * kDcPartials;
+    if (mode == 2) dc_sequential(G.src, G.n, dst);             // the zero padding after the copied region adds nothing to the chain
+    else dc_partial(G.src, G.n, dst + blockIdx.x);
 }
 __global__ void __launch_bounds__(kThreads)
 dc_sub_kernel(const DevBuf* __restrict__ bufs, int maxCh, const double* __restrict__ partials) {
@@ -406,7 +436,7 @@ cudaError_t allow_smem(K kernel, size_t bytes) {
 }  // namespace
 
 cudaError_t launch_trim(const DevBuf* d_captured, const int* d_latency, const DevBuf* d_out, int n, int maxOutFrames,
-                        int maxCh, cudaStream_t s, long long* launches, double* d_dc_partials, const int* d_dc_mask) {
+                        int maxCh, cudaStream_t s, long long* launches, double* d_dc_partials, const int* d_dc_mask, int dcDefault) {
     if (n <= 0 || maxCh <= 0) return cudaSuccess;
     const int tiles = std::max(1, std::min((maxOutFrames + kThreads * 16 - 1) / (kThreads * 16), 4096));
     for (int b0 = 0; b0 < n; b0 += 65535) {
@@ -414,7 +444,8 @@ cudaError_t launch_trim(const DevBuf* d_captured, const int* d_latency, const De
         dim3 grid(tiles, maxCh, nb);
         if (d_dc_partials) {                                   // fused removeDCOffset: mean of the copied region first
             double* part = d_dc_partials + (size_t) b0 * maxCh * kDcPartials;
-            dc_sum_src_kernel<<<dim3(kDcPartials, maxCh, nb), kThreads, 0, s>>>(d_captured + b0, d_latency + b0, d_out + b0, maxCh, part);
+            dc_sum_src_kernel<<<dim3(kDcPartials, maxCh, nb), kThreads, 0, s>>>(d_captured + b0, d_latency + b0, d_out + b0, maxCh, part,
+                                                                                d_dc_mask ? d_dc_mask + b0 : nullptr, dcDefault);
             ++*launches;
             trim_kernel<true><<<grid, kThreads, 0, s>>>(d_captured + b0, d_latency + b0, d_out + b0, part, d_dc_mask ? d_dc_mask + b0 : nullptr, maxCh);
         } else {
@@ -425,12 +456,12 @@ cudaError_t launch_trim(const DevBuf* d_captured, const int* d_latency, const De
     return cudaGetLastError();
 }
 
-cudaError_t launch_remove_dc(const DevBuf* d_bufs, int n, int maxCh, int maxFrames, double* d_partials, cudaStream_t s, long long* launches) {
+cudaError_t launch_remove_dc(const DevBuf* d_bufs, int n, int maxCh, int maxFrames, double* d_partials, cudaStream_t s, long long* launches, int mode) {
     if (n <= 0 || maxCh <= 0) return cudaSuccess;
     for (int b0 = 0; b0 < n; b0 += 65535) {
         const int nb = std::min(65535, n - b0);
         double* part = d_partials + (size_t) b0 * maxCh * kDcPartials;
-        dc_sum_kernel<<<dim3(kDcPartials, maxCh, nb), kThreads, 0, s>>>(d_bufs + b0, maxCh, part);
+        dc_sum_kernel<<<dim3(kDcPartials, maxCh, nb), kThreads, 0, s>>>(d_bufs + b0, maxCh, part, mode);
         ++*launches;
         const int tiles = std::max(1, std::min((maxFrames + kThreads * 16 - 1) / (kThreads * 16), 4096));
         dc_sub_kernel<<<dim3(tiles, maxCh, nb), kThreads, 0, s>>>(d_bufs + b0, maxCh, part);

@@ -101,9 +101,10 @@ cudaError_t launch_xcorr(const DevBuf* d_bufs, int n, int total_ctas, const int*
 constexpr int kDcPartials = 32;             // partial sums per (buffer, channel) of the DC passes: d_partials holds n * maxCh * kDcPartials doubles
 // d_dc_partials != nullptr: removeDCOffset fused into the trim (buffers with d_dc_mask[i] == 0 are copied unchanged; nullptr = all)
 cudaError_t launch_trim(const DevBuf* d_captured, const int* d_latency, const DevBuf* d_out, int n, int maxOutFrames,
-                        int maxCh, cudaStream_t s, long long* launches, double* d_dc_partials = nullptr, const int* d_dc_mask = nullptr);
+                        int maxCh, cudaStream_t s, long long* launches, double* d_dc_partials = nullptr, const int* d_dc_mask = nullptr,
+                        int dcDefault = 1 /* mode when there is no mask: 1 parallel double sum, 2 the reference's sequential float sum */);
 cudaError_t launch_remove_dc(const DevBuf* d_bufs /* writable */, int n, int maxCh, int maxFrames, double* d_partials /* n*maxCh*kDcPartials */,
-                             cudaStream_t s, long long* launches);
+                             cudaStream_t s, long long* launches, int mode = 1);
 cudaError_t launch_pcm_to_planar(const void* d_src, int fmt, int srcCh, long long frames, float* d_dst,
                                  long long dstStride, int dstCh, cudaStream_t s, long long* launches);
 // h_dsts / h_srcs: host copies of the payload pointer arrays (alignment check for the 128-bit fast paths; nullptr = byte-staged kernels)

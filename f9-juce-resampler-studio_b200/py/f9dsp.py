@@ -19,7 +19,7 @@ OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_NO_DEVICE, ERR_UNSUPPORTED = 0, -1, -2
 WINDOWED_SINC, LAGRANGE, CATMULL_ROM, LINEAR, ZERO_ORDER_HOLD = 0, 1, 2, 3, 4
 PCM_U8, PCM_S16LE, PCM_S24LE, PCM_S32LE, PCM_F32LE = 1, 2, 3, 4, 5
 TAIL_RMS, TAIL_PEAK = 0, 1
-JOB_TAIL_SCAN, JOB_REMOVE_DC, JOB_PCM24 = 1, 2, 4
+JOB_TAIL_SCAN, JOB_REMOVE_DC, JOB_PCM24, JOB_DC_REFERENCE_ORDER = 1, 2, 4, 8
 _BYTES = {PCM_U8: 1, PCM_S16LE: 2, PCM_S24LE: 3, PCM_S32LE: 4, PCM_F32LE: 4}
 
 _fp = C.POINTER(C.c_float)
@@ -97,6 +97,7 @@ SYMBOLS = [
     ("f9_trim_latency", _i, [_vp, _fpp, _i, _i, _i, _i, _fpp, _ip]),
     ("f9_trim_latency_swift", _i, [_vp, _fp, _ll, _ll, _ll, _i, _fp, _llp]),
     ("f9_remove_dc_offset", _i, [_vp, _fpp, _i, _i]),
+    ("f9_remove_dc_offset_ex", _i, [_vp, _fpp, _i, _i, _i]),
     ("f9_generate_impulse", _i, [_vp, _fpp, _i, _i]),
     ("f9_generate_sine_wave", _i, [_vp, _fpp, _i, _i, _f, _f, _f, _fp, _i]),
     ("f9_generate_sine_wave_swift", _i, [_vp, _fp, _i, _i, _d, _d, _f, _dp]),
@@ -300,6 +301,8 @@ def build_jobs(jobs: list[dict]) -> BuiltJobs:
             J[i].has_nf, J[i].nf_db, J[i].margin_pct = int(has), nf, mg
         if j.get("remove_dc"):
             flags |= JOB_REMOVE_DC
+            if j.get("remove_dc") == "reference":
+                flags |= JOB_DC_REFERENCE_ORDER
         pcm = None
         if j.get("pcm24"):
             flags |= JOB_PCM24
@@ -483,9 +486,9 @@ class Context:
         self._check(lib().f9_trim_latency_swift(self._h, _p(a), a.size, latency_samples, source_frames, channels, _p(out), C.byref(n)))
         return out[: n.value].copy()
 
-    def remove_dc_offset(self, buf) -> np.ndarray:
+    def remove_dc_offset(self, buf, reference_order: bool = True) -> np.ndarray:
         a = _planar(buf).copy()
-        self._check(lib().f9_remove_dc_offset(self._h, _chan_ptrs(a), a.shape[0], a.shape[1]))
+        self._check(lib().f9_remove_dc_offset_ex(self._h, _chan_ptrs(a), a.shape[0], a.shape[1], int(reference_order)))
         return a
 
     def generate_impulse(self, num_ch: int, num_frames: int) -> np.ndarray:

@@ -145,9 +145,14 @@ F9_API int f9_trim_latency(f9_context* ctx, const float* const* captured, int nu
  * source_frames*channels floats; *out_count = samples written. */
 F9_API int f9_trim_latency_swift(f9_context* ctx, const float* captured, long long count, long long latency_samples,
                                  long long source_frames, int channels, float* out, long long* out_count);
-/* MainComponent::removeDCOffset, Source/MainComponent.cpp:884-902 (in place).  Tolerance parity only:
- * the reference accumulates the mean sequentially in float. */
+/* MainComponent::removeDCOffset, Source/MainComponent.cpp:884-902 (in place).  The reference accumulates the channel's sum in ONE
+ * float, sample after sample (:892-896): on a long quiet capture that accumulator drifts from the true mean by far more than
+ * 2^-20 (a 60 s, 44.1 kHz capture with DC 0.003 and 1e-4 of noise: 2.5e-5).  f9_remove_dc_offset reproduces the reference's
+ * arithmetic BIT FOR BIT (the chain is walked in order by one thread per channel, ~2 ms per 10^6 frames, all channels at once).
+ * f9_remove_dc_offset_ex(..., reference_order = 0) subtracts the exactly rounded mean instead (parallel double sum: faster, and
+ * closer to the true mean than the reference is -- a deliberate accuracy deviation, bounded only by the reference's own drift). */
 F9_API int f9_remove_dc_offset(f9_context* ctx, float* const* ch, int numCh, int numFrames);
+F9_API int f9_remove_dc_offset_ex(f9_context* ctx, float* const* ch, int numCh, int numFrames, int reference_order);
 
 /* MainComponent::generateImpulse, Source/MainComponent.cpp:934-945 (Swift sendImpulse, LatencyMeasurementService.swift:130-145):
  * clears the buffer and writes 0.9 to sample 0 of every channel -- the stimulus of the latency measurement. */
@@ -265,7 +270,9 @@ typedef struct f9_job {
     int   src_ch;
 } f9_job;
 
-enum { F9_JOB_TAIL_SCAN = 1, F9_JOB_REMOVE_DC = 2, F9_JOB_PCM24 = 4 };
+enum { F9_JOB_TAIL_SCAN = 1, F9_JOB_REMOVE_DC = 2, F9_JOB_PCM24 = 4,
+       F9_JOB_DC_REFERENCE_ORDER = 8 };  /* with F9_JOB_REMOVE_DC: the reference's sequential float accumulator (bit-exact dcOffset; ~2 ms per
+                                          * 10^6 frames) instead of the exactly rounded mean (see f9_remove_dc_offset) */
 
 typedef struct f9_result {
     int status;                     /* F9_OK or an error for this job                               */
@@ -339,7 +346,8 @@ F9_API int f9_dev_tail_scan_batch(f9_context* ctx, const f9_dev_buffer* bufs, co
                                   long long* d_stop_frame, int* d_flags, int max_polls);
 
 /* fused trim (+ optional DC removal) on device: out buffer i = trimLatency(bufs[i], latency_samples[i],
- * original_length[i]); out numFrames must equal original_length[i]. */
+ * original_length[i]); out numFrames must equal original_length[i].  remove_dc: 0 no, 1 exactly rounded mean (parallel),
+ * 2 the reference's sequential float accumulator (bit-exact, see f9_remove_dc_offset). */
 F9_API int f9_dev_trim_batch(f9_context* ctx, const f9_dev_buffer* captured, const int* latency_samples,
                              const f9_dev_buffer* out, int n, int remove_dc);
 

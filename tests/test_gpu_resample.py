@@ -319,11 +319,11 @@ def test_batch_flow_no_conversion_with_dc(ctx, O):
     """The reference's own flow (44.1 kHz in and out): trimLatency + removeDCOffset, short capture zero padded."""
     cap = (np.random.default_rng(11).uniform(-0.3, 0.3, (2, 46000)) + 0.02).astype(np.float32)
     outs, _, res = ctx.process_batch([dict(captured=cap, latency_samples=1024, original_length=44100,
-                                           fs_in=44100, fs_out=44100, kind=0, remove_dc=True),
+                                           fs_in=44100, fs_out=44100, kind=0, remove_dc="reference"),
                                       dict(captured=cap[:, :30000], latency_samples=1024, original_length=44100,
                                            fs_in=44100, fs_out=44100, kind=0)])
     t0, _ = O.trim_latency(cap, 1024, 44100)
-    assert np.max(np.abs(outs[0] - O.remove_dc_offset(t0))) <= TOL
+    assert np.array_equal(outs[0], O.remove_dc_offset(t0))          # F9_JOB_DC_REFERENCE_ORDER: the reference's float accumulator, bit for bit
     t1, c1 = O.trim_latency(cap[:, :30000], 1024, 44100)
     assert np.array_equal(outs[1], t1) and res[1]["frames_copied"] == c1 == 30000 - 512
 
