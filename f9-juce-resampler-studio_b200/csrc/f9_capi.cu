@@ -284,7 +284,7 @@ int f9_measure_latency(f9_context* ctx, const float* const* ch, int numCh, int n
     double* d_psum = (double*) ctx->d_alloc(sizeof(double) * (size_t) total);
     double* d_res = (double*) ctx->d_alloc(2 * sizeof(double));              // [0] sum of squares, [1] (as int) position
     int* d_pos = reinterpret_cast<int*>(d_res + 1);
-    F9_TRY_CUDA(ctx, launch_find_peak(d_bufs, 1, total, d_prefix, threshold, d_part, d_pos, ctx->stream, &ctx->launches, d_psum, d_res, nullptr, ctx->diag.get("F9_RMS_FORCE_ORDER")));
+    F9_TRY_CUDA(ctx, launch_find_peak(d_bufs, 1, total, d_prefix, threshold, d_part, d_pos, ctx->stream, &ctx->launches, d_psum, d_res, nullptr, (ctx->diag.has("F9_RMS_TREE_SUM") ? -1 : ctx->diag.get("F9_RMS_FORCE_ORDER"))));
     double* h_res = (double*) ctx->h_alloc(2 * sizeof(double));
     F9_TRY_CUDA(ctx, cudaMemcpyAsync(h_res, d_res, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     F9_FINISH(ctx);
@@ -321,7 +321,7 @@ static int stats_one(f9_context* ctx, const float* const* ch, int numCh, int num
     float* d_pmax = (float*) ctx->d_alloc(sizeof(float) * kStatPartialsPerBuf);
     double* d_sum = (double*) ctx->d_alloc(sizeof(double));
     float* d_peak = (float*) ctx->d_alloc(sizeof(float));
-    F9_TRY_CUDA(ctx, launch_stats(d_bufs, 1, d_psum, d_pmax, d_sum, d_peak, ctx->stream, &ctx->launches, ctx->diag.get("F9_RMS_FORCE_ORDER")));
+    F9_TRY_CUDA(ctx, launch_stats(d_bufs, 1, d_psum, d_pmax, d_sum, d_peak, ctx->stream, &ctx->launches, (ctx->diag.has("F9_RMS_TREE_SUM") ? -1 : ctx->diag.get("F9_RMS_FORCE_ORDER"))));
     double* h_sum = (double*) ctx->h_alloc(sizeof(double));
     float* h_peak = (float*) ctx->h_alloc(sizeof(float));
     F9_TRY_CUDA(ctx, cudaMemcpyAsync(h_sum, d_sum, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -575,7 +575,9 @@ int f9_xcorr_peak(f9_context* ctx, const float* const* y, int numCh, int numFram
     DevBuf hb{}; hb.numCh = numCh; hb.numFrames = numFrames;
     std::vector<int> prefix;
     const int total = xcorr_prefix(&hb, 1, lag_min, lag_max, &prefix);
-    rc = ctx->arena_reserve(planar_bytes(numCh, numFrames) + sizeof(float) * (size_t) stim_len + sizeof(XcPartial) * ((size_t) total + 2) + 16384,
+    const bool fast = !ctx->diag.has("F9_XCORR_EXACT_ALL");
+    const size_t fastBytes = fast ? xcorr_fast_scratch_bytes(1, numCh, lag_min, lag_max) : 0;
+    rc = ctx->arena_reserve(planar_bytes(numCh, numFrames) + sizeof(float) * (size_t) stim_len + sizeof(XcPartial) * ((size_t) total + 2) + 16384 + fastBytes,
                             sizeof(float) * (size_t) stim_len + 8192);
     if (rc) return rc;
     rc = upload_planar(ctx, y, numCh, numFrames, &hb); if (rc) return rc;
@@ -586,6 +588,11 @@ int f9_xcorr_peak(f9_context* ctx, const float* const* y, int numCh, int numFram
     rc = upload_array(ctx, prefix.data(), prefix.size(), &d_prefix); if (rc) return rc;
     XcPartial* d_part = (XcPartial*) ctx->d_alloc(sizeof(XcPartial) * (size_t) total);
     XcPartial* d_best = (XcPartial*) ctx->d_alloc(sizeof(XcPartial));
+    if (fast) {
+        void* d_scr = ctx->d_alloc(fastBytes);
+        if (!d_scr) return ctx->fail(F9_ERR_NOMEM, "xcorr scratch");
+        F9_TRY_CUDA(ctx, launch_xcorr_fast(&hb, d_b, 1, total, d_prefix, d_stim, stim_len, lag_min, lag_max, d_part, d_best, d_scr, ctx->stream, &ctx->launches));
+    } else
     F9_TRY_CUDA(ctx, launch_xcorr(d_b, 1, total, d_prefix, d_stim, stim_len, lag_min, lag_max, d_part, d_best, ctx->stream, &ctx->launches));
     XcPartial* h_best = (XcPartial*) ctx->h_alloc(sizeof(XcPartial));
     F9_TRY_CUDA(ctx, cudaMemcpyAsync(h_best, d_best, sizeof(XcPartial), cudaMemcpyDeviceToHost, ctx->stream));
@@ -787,7 +794,7 @@ int f9_dev_latency_stats_batch(f9_context* ctx, const f9_dev_buffer* bufs, int n
     rc = upload_array(ctx, prefix.data(), prefix.size(), &d_prefix); if (rc) return rc;
     PeakPartial* d_part = (PeakPartial*) ctx->d_alloc(sizeof(PeakPartial) * (size_t) std::max(total, 1));
     double* d_psum = (double*) ctx->d_alloc(sizeof(double) * (size_t) std::max(total, 1));
-    F9_TRY_CUDA(ctx, launch_find_peak(d_b, n, total, d_prefix, threshold, d_part, d_out_pos, ctx->stream, &ctx->launches, d_psum, d_sumsq, d_peak, ctx->diag.get("F9_RMS_FORCE_ORDER")));
+    F9_TRY_CUDA(ctx, launch_find_peak(d_b, n, total, d_prefix, threshold, d_part, d_out_pos, ctx->stream, &ctx->launches, d_psum, d_sumsq, d_peak, (ctx->diag.has("F9_RMS_TREE_SUM") ? -1 : ctx->diag.get("F9_RMS_FORCE_ORDER"))));
     return F9_OK;
 }
 
@@ -802,7 +809,7 @@ int f9_dev_stats_batch(f9_context* ctx, const f9_dev_buffer* bufs, int n, double
     rc = upload_array(ctx, hb, (size_t) n, &d_b); if (rc) return rc;
     double* d_psum = (double*) ctx->d_alloc(sizeof(double) * kStatPartialsPerBuf * (size_t) n);
     float* d_pmax = (float*) ctx->d_alloc(sizeof(float) * kStatPartialsPerBuf * (size_t) n);
-    F9_TRY_CUDA(ctx, launch_stats(d_b, n, d_psum, d_pmax, d_sumsq, d_peak, ctx->stream, &ctx->launches, ctx->diag.get("F9_RMS_FORCE_ORDER")));
+    F9_TRY_CUDA(ctx, launch_stats(d_b, n, d_psum, d_pmax, d_sumsq, d_peak, ctx->stream, &ctx->launches, (ctx->diag.has("F9_RMS_TREE_SUM") ? -1 : ctx->diag.get("F9_RMS_FORCE_ORDER"))));
     return F9_OK;
 }
 
@@ -816,14 +823,39 @@ int f9_dev_xcorr_peak_batch(f9_context* ctx, const f9_dev_buffer* bufs, int n, c
     std::vector<int> prefix;
     const int total = xcorr_prefix(hb, n, lag_min, lag_max, &prefix);
     const size_t small = sizeof(DevBuf) * (size_t) n + sizeof(int) * (size_t) (n + 1) + 8192;
-    int rc = ctx->arena_reserve(small + sizeof(XcPartial) * (size_t) std::max(total, 1) + 16384, small, true);
-    if (rc) return rc;
-    DevBuf* d_b; int* d_prefix;
-    rc = upload_array(ctx, hb, (size_t) n, &d_b); if (rc) return rc;
-    rc = upload_array(ctx, prefix.data(), prefix.size(), &d_prefix); if (rc) return rc;
-    XcPartial* d_part = (XcPartial*) ctx->d_alloc(sizeof(XcPartial) * (size_t) std::max(total, 1));
-    F9_TRY_CUDA(ctx, launch_xcorr(d_b, n, total, d_prefix, d_stim, stim_len, lag_min, lag_max, d_part,
-                                  reinterpret_cast<XcPartial*>(d_out), ctx->stream, &ctx->launches));
+    if (ctx->diag.has("F9_XCORR_EXACT_ALL")) {                  // every lag in exact double sums (the round-1 path; tests compare the two)
+        int rc = ctx->arena_reserve(small + sizeof(XcPartial) * (size_t) std::max(total, 1) + 16384, small, true);
+        if (rc) return rc;
+        DevBuf* d_b; int* d_prefix;
+        rc = upload_array(ctx, hb, (size_t) n, &d_b); if (rc) return rc;
+        rc = upload_array(ctx, prefix.data(), prefix.size(), &d_prefix); if (rc) return rc;
+        XcPartial* d_part = (XcPartial*) ctx->d_alloc(sizeof(XcPartial) * (size_t) std::max(total, 1));
+        F9_TRY_CUDA(ctx, launch_xcorr(d_b, n, total, d_prefix, d_stim, stim_len, lag_min, lag_max, d_part,
+                                      reinterpret_cast<XcPartial*>(d_out), ctx->stream, &ctx->launches));
+        return F9_OK;
+    }
+    // candidates on the tensor cores + exact verification, in groups of buffers whose approximate correlations fit ~1 GB of scratch
+    int maxCh = 1;
+    for (int i = 0; i < n; ++i) maxCh = std::max(maxCh, hb[i].numCh);
+    const size_t perBuf = xcorr_fast_scratch_bytes(1, maxCh, lag_min, lag_max);
+    const int group = (int) std::max<size_t>(1, std::min<size_t>((size_t) n, (size_t(1) << 30) / perBuf));
+    for (int b0 = 0; b0 < n; b0 += group) {
+        const int nb = std::min(group, n - b0);
+        std::vector<int> pre((size_t) nb + 1);
+        for (int i = 0; i <= nb; ++i) pre[(size_t) i] = prefix[(size_t) (b0 + i)] - prefix[(size_t) b0];
+        const int tot = pre[(size_t) nb];
+        const size_t scr = xcorr_fast_scratch_bytes(nb, maxCh, lag_min, lag_max);
+        int rc = ctx->arena_reserve(small + sizeof(XcPartial) * (size_t) std::max(tot, 1) + scr + 16384, small, true);
+        if (rc) return rc;
+        DevBuf* d_b; int* d_prefix;
+        rc = upload_array(ctx, hb + b0, (size_t) nb, &d_b); if (rc) return rc;
+        rc = upload_array(ctx, pre.data(), pre.size(), &d_prefix); if (rc) return rc;
+        XcPartial* d_part = (XcPartial*) ctx->d_alloc(sizeof(XcPartial) * (size_t) std::max(tot, 1));
+        void* d_scr = ctx->d_alloc(scr);
+        if (!d_part || !d_scr) return ctx->fail(F9_ERR_NOMEM, "xcorr scratch");
+        F9_TRY_CUDA(ctx, launch_xcorr_fast(hb + b0, d_b, nb, tot, d_prefix, d_stim, stim_len, lag_min, lag_max, d_part,
+                                           reinterpret_cast<XcPartial*>(d_out) + b0, d_scr, ctx->stream, &ctx->launches));
+    }
     return F9_OK;
 }
 

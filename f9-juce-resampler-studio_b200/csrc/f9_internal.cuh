@@ -96,7 +96,11 @@ cudaError_t launch_tail_scan(const DevBuf* d_bufs, const TailParams* d_params, i
 int         xcorr_prefix(const DevBuf* h_bufs, int n, int lagMin, int lagMax, std::vector<int>* prefix);
 cudaError_t launch_xcorr(const DevBuf* d_bufs, int n, int total_ctas, const int* d_prefix, const float* d_stim, int stimLen,
                          int lagMin, int lagMax, XcPartial* d_partials /* total_ctas */, XcPartial* d_best /* n */,
-                         cudaStream_t s, long long* launches);
+                         cudaStream_t s, long long* launches, const int* d_need = nullptr /* per buffer: scan it (nullptr: all) */);
+// f9_xcorr.cu: approximate every lag on the tensor cores, verify the candidates exactly; results identical to launch_xcorr
+size_t      xcorr_fast_scratch_bytes(int n, int maxCh, int lagMin, int lagMax);
+cudaError_t launch_xcorr_fast(const DevBuf* h_bufs, const DevBuf* d_bufs, int n, int total_ctas, const int* d_prefix, const float* d_stim, int stimLen,
+                              int lagMin, int lagMax, XcPartial* d_partials, XcPartial* d_best, void* d_scratch, cudaStream_t s, long long* launches);
 
 constexpr int kDcPartials = 32;             // partial sums per (buffer, channel) of the DC passes: d_partials holds n * maxCh * kDcPartials doubles
 // d_dc_partials != nullptr: removeDCOffset fused into the trim (buffers with d_dc_mask[i] == 0 are copied unchanged; nullptr = all)

@@ -121,38 +121,162 @@ peak_partial_kernel(const DevBuf* __restrict__ bufs, const int* __restrict__ pre
 // The reference sums the squares sequentially in double (Source/MainComponent.cpp:985-997); the kernels sum them as a tree.
 // All terms are >= 0, so either order is within (n - 1) 2^-53 relative of the exact sum, the two sums within twice that of each
 // other, and sqrt(sum / n) within about (n + 4) 2^-53.  (float) sqrt(sum / n) -- what calculateRMS returns -- therefore only
-// depends on the order when the double value lies that close to a float rounding boundary: then, and only then, the sum is
-// redone in the reference's order by one thread (a few times in a thousand buffers), and the returned sum of squares is the
-// reference's own double.
-__device__ __forceinline__ bool rms_order_dependent(double s, long long count) {
+// depends on the order when the double value lies that close to a float rounding boundary (stage 1: about one buffer in a
+// thousand at 5 s stereo).  Stage 2 tightens the bound for those: partial sums never exceed the total, so a term that is a
+// multiple of the total's ulp is added WITHOUT rounding in either order (the terms are float squares: 24 significant bits);
+// only the `small` terms below that grid, the <= 64 steps where the running sum crosses a power of two, and the <= ~100 adds
+// of the tree's depth (~100 + n / 16384: a thread's own chain) can round at all, each by at most an ulp of the total, which moves
+// sqrt(sum / n) by half of that.  The CTA counts the small terms in parallel and re-tests with (small + 256 + n / 16384) 2^-53:
+// about one buffer in 10^4..10^5 is left, and only that one is re-summed in the reference's order by one thread.  The returned
+// sum of squares is then the reference's own double.
+__device__ __forceinline__ bool rms_rounds_differently(double s, long long count, double relBound) {
     if (!(s != 0.0)) return false;                               // all samples zero: every order gives exactly 0
     const double r = sqrt(s / (double) count);
-    const double d = (double) (count + 8) * 1.1102230246251565e-16;
-    return (float) (r * (1.0 - d)) != (float) (r * (1.0 + d));   // NaN compares unequal: redone in order, NaN again
+    return (float) (r * (1.0 - relBound)) != (float) (r * (1.0 + relBound));   // NaN compares unequal: redone in order, NaN again
 }
-__device__ __noinline__ double sum_squares_in_reference_order(const DevBuf& B) {
-    double ss = 0.0;
+__device__ __forceinline__ bool rms_order_dependent(double s, long long count) {
+    return rms_rounds_differently(s, count, (double) (count + 8) * 1.1102230246251565e-16);
+}
+// Terms of the buffer that can be rounded when added to a partial sum < 4 * 2^ilogb(s): float squares with bits below the ulp of
+// the binade above s.  Called by all threads of a CTA; returns this thread's count.  Integer arithmetic on the float's bits.
+__device__ __forceinline__ long long count_small_terms(const DevBuf& B, double s) {
+    const int Eb = (int) (((unsigned long long) __double_as_longlong(s)) >> 52) + 1;       // biased exponent of the binade above s
+    long long small = 0;
     for (int c = 0; c < B.numCh; ++c) {
         const float* __restrict__ x = B.base + (long long) c * B.chStride;
-        for (int k = 0; k < B.numFrames; ++k) { const float v = __ldg(x + k); ss = __dadd_rn(ss, (double) __fmul_rn(v, v)); }
+        for (int k = threadIdx.x; k < B.numFrames; k += blockDim.x) {
+            const float v = __ldg(x + k);
+            const unsigned pb = __float_as_uint(__fmul_rn(v, v));
+            const int ep = (int) (pb >> 23);
+            const unsigned mp = ep ? ((pb & 0x7fffffu) | 0x800000u) : (pb & 0x7fffffu);
+            const int shf = (ep ? ep : 1) - 150 - (Eb - 1075);                              // p / grid = mp * 2^shf
+            if (mp != 0u && shf < 0) small += (-shf >= 32 || (mp & ((1u << -shf) - 1u)) != 0u) ? 1 : 0;
+        }
     }
-    return ss;
+    return small;
+}
+// The reference's chain, s <- fl(s + p_k) in order, evaluated by one CTA without walking it term by term.  A chain of dependent
+// double additions costs ~35 clk per term on this part (measured: 8-12 ms for a 5 s stereo capture), but the chain has structure:
+// the terms are >= 0, so s only grows, and while s stays in one binade [2^E, 2^(E+1)) it is an integer M on the grid g = 2^(E-52)
+// and a step is integer arithmetic: p_k / g = q + f, M <- M + q + [f > 1/2] + [f == 1/2] ((M + q) mod 2) (round to nearest, ties
+// to even).  The increment depends on M only through its parity, so a term is a pair (increment if M is even, increment if M is
+// odd) and pairs compose associatively, order preserved.  Every warp reduces its own block of 256 terms on the grid of the
+// current binade (8 compositions per lane + a 5-step warp scan, all integer); the blocks' pairs are then applied in order while M
+// stays below 2^53 (s has not left the binade: the sum is monotone).  The block that crosses a binade -- at most ~60 per buffer --
+// is walked term by term by warp 0 with real double additions, and the next round starts behind it on the new grid.  Every
+// operation is exact, so the result IS the sequential sum, bit for bit (forced on every test buffer through F9_RMS_FORCE_ORDER).
+struct IncPair { long long e, o; };                              // increment of M when M is even / odd
+__device__ __forceinline__ IncPair inc_compose(IncPair a, IncPair c) {         // a first, then c
+    IncPair r;
+    r.e = a.e + ((a.e & 1) ? c.o : c.e);
+    r.o = a.o + (((1 + a.o) & 1) ? c.o : c.e);
+    return r;
+}
+constexpr int kSeqWarps = 8, kSeqPer = 8, kSeqBlock = 32 * kSeqPer;      // the final kernels run 256 threads
+struct SeqShared { IncPair pair[kSeqWarps]; int ok[kSeqWarps]; unsigned long long sb; };
+// Call with all kSeqWarps * 32 threads of the CTA; every thread returns the sum.
+__device__ __noinline__ double sum_squares_in_reference_order(const DevBuf& B, SeqShared& sh) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long total = (long long) B.numCh * B.numFrames;
+    unsigned long long sb = 0ull;                                // bits of the running sum s (a non-negative double)
+    long long b0 = 0;
+    while (b0 < total) {
+        // this warp's block of the round: terms in channel-major order (the reference's scan order), squared in float (:995)
+        const long long idx0 = b0 + (long long) warp * kSeqBlock + (long long) lane * kSeqPer;
+        float pf[kSeqPer];
+        {
+            long long c = idx0 < total ? idx0 / B.numFrames : 0;
+            long long off = idx0 - c * B.numFrames;
+            #pragma unroll
+            for (int j = 0; j < kSeqPer; ++j) {
+                const float v = (idx0 + j < total) ? __ldg(B.base + c * B.chStride + off) : 0.0f;
+                pf[j] = __fmul_rn(v, v);
+                if (++off == B.numFrames) { off = 0; ++c; }
+            }
+        }
+        const int Eb = (int) (sb >> 52);                          // biased exponent of s
+        bool ok = Eb >= 64 && Eb < 2046;                          // s normal and its grid a normal double too
+        IncPair mine{0, 0};
+        #pragma unroll
+        for (int j = 0; j < kSeqPer; ++j) {
+            const unsigned pb = __float_as_uint(pf[j]);
+            const int ep = (int) (pb >> 23);                      // biased float exponent (0: zero or subnormal)
+            const long long mp = ep ? (long long) ((pb & 0x7fffffu) | 0x800000u) : (long long) (pb & 0x7fffffu);
+            // p = mp * 2^(max(ep, 1) - 150);  grid g = 2^(Eb - 1075);  p / g = mp * 2^sh
+            const int shf = (ep ? ep : 1) - 150 - (Eb - 1075);
+            IncPair e{0, 0};
+            if (ep == 255) ok = false;                            // Inf / NaN: the plain chain reproduces them
+            if (shf >= 0) {
+                if (shf > 29) ok = false;                         // the term alone reaches the next binade
+                else { const long long q = mp << shf; e.e = q; e.o = q; }
+            } else if (-shf <= 25) {                              // (further down: below a quarter of the grid, rounds away)
+                const int k = -shf;
+                const long long q = mp >> k, rem = mp & ((1LL << k) - 1), half = 1LL << (k - 1);
+                if (rem < half) { e.e = q; e.o = q; }
+                else if (rem > half) { e.e = q + 1; e.o = q + 1; }
+                else { e.e = q + (q & 1); e.o = q + ((1 + q) & 1); }              // tie: to even
+            }
+            mine = inc_compose(mine, e);
+        }
+        ok = __all_sync(0xffffffffu, ok);
+        #pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {                  // ordered reduction over the lanes (inclusive scan)
+            IncPair prev;
+            prev.e = __shfl_up_sync(0xffffffffu, mine.e, off);
+            prev.o = __shfl_up_sync(0xffffffffu, mine.o, off);
+            if (lane >= off) mine = inc_compose(prev, mine);
+        }
+        if (lane == 31) { sh.pair[warp] = mine; sh.ok[warp] = ok ? 1 : 0; }
+        __syncthreads();
+        // apply the blocks in order while s stays in its binade (every thread does the same few integer steps)
+        long long M = (long long) ((sb & 0x000fffffffffffffull) | 0x0010000000000000ull);
+        int done = 0;
+        for (; done < kSeqWarps && b0 + (long long) done * kSeqBlock < total; ++done) {
+            if (!sh.ok[done]) break;
+            const IncPair pr = sh.pair[done];
+            const long long M2 = M + ((M & 1) ? pr.o : pr.e);
+            if (M2 >= (1LL << 53)) break;
+            M = M2;
+        }
+        if (done > 0) sb = ((unsigned long long) Eb << 52) | ((unsigned long long) M & 0x000fffffffffffffull);
+        const bool crossing = done < kSeqWarps && b0 + (long long) done * kSeqBlock < total;
+        if (crossing) {
+            // block `done` leaves the binade (or s is still zero / subnormal, or a term is not finite): the plain chain over its 256
+            // terms.  Warp `done` still holds them; it walks the chain (every lane the same s) and publishes the result.
+            if (warp == done) {
+                double s = __longlong_as_double((long long) sb);
+                #pragma unroll 1
+                for (int l = 0; l < 32; ++l) {
+                    #pragma unroll
+                    for (int j = 0; j < kSeqPer; ++j) s = __dadd_rn(s, (double) __shfl_sync(0xffffffffu, pf[j], l));
+                }
+                if (lane == 0) sh.sb = (unsigned long long) __double_as_longlong(s);
+            }
+            __syncthreads();
+            sb = sh.sb;
+            ++done;
+        }
+        __syncthreads();                                          // sh.pair / sh.ok / sh.sb are rewritten by the next round
+        b0 += (long long) done * kSeqBlock;
+    }
+    return __longlong_as_double((long long) sb);
 }
 
 // ---- stage 2: one CTA per buffer folds its partials in scan order ----------------------------------
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 peak_final_kernel(const PeakPartial* __restrict__ partials, const int* __restrict__ prefix, float threshold, int* __restrict__ out_pos,
                   const double* __restrict__ psum, double* __restrict__ sumsq, float* __restrict__ peakv, const DevBuf* __restrict__ bufs, int forceOrder) {
     const int b = blockIdx.x;
     const int p0 = prefix[b], p1 = prefix[b + 1];
     float bv = 0.0f; int bch = 0x7fffffff, bpos = 0x7fffffff;
     double sq = 0.0;
+    __shared__ double sTotal;
     for (int i = p0 + threadIdx.x; i < p1; i += blockDim.x) {
         const PeakPartial r = partials[i];
         if (r.pos >= 0 && peak_better(r.v, r.ch, r.pos, bv, bch, bpos)) { bv = r.v; bch = r.ch; bpos = r.pos; }
         if (psum) sq += psum[i];
     }
-    __shared__ double ssq[4];
+    __shared__ double ssq[8];
     if (psum) {
         #pragma unroll
         for (int off = 16; off > 0; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
@@ -165,7 +289,7 @@ peak_final_kernel(const PeakPartial* __restrict__ partials, const int* __restric
         const int op = __shfl_xor_sync(0xffffffffu, bpos, off);
         if (peak_better(ov, oc, op, bv, bch, bpos)) { bv = ov; bch = oc; bpos = op; }
     }
-    __shared__ float sv[4]; __shared__ int sc[4], sp[4];
+    __shared__ float sv[8]; __shared__ int sc[8], sp[8];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (lane == 0) { sv[warp] = bv; sc[warp] = bch; sp[warp] = bpos; }
     __syncthreads();
@@ -173,12 +297,27 @@ peak_final_kernel(const PeakPartial* __restrict__ partials, const int* __restric
         for (int w = 1; w < (int) blockDim.x / 32; ++w)
             if (peak_better(sv[w], sc[w], sp[w], bv, bch, bpos)) { bv = sv[w]; bch = sc[w]; bpos = sp[w]; }
         out_pos[b] = (bv > threshold && bpos != 0x7fffffff) ? bpos : -1;
-        if (psum) {
-            double total = (ssq[0] + ssq[1]) + (ssq[2] + ssq[3]);
-            const DevBuf B = bufs[b];
-            if (forceOrder || rms_order_dependent(total, (long long) B.numCh * B.numFrames)) total = sum_squares_in_reference_order(B);
-            sumsq[b] = total; if (peakv) peakv[b] = bv;
+        if (psum) { sTotal = ((ssq[0] + ssq[1]) + (ssq[2] + ssq[3])) + ((ssq[4] + ssq[5]) + (ssq[6] + ssq[7])); if (peakv) peakv[b] = bv; }
+    }
+    if (psum) {                                                  // bit-exact sum of squares: see rms_order_dependent (all threads of the CTA)
+        __syncthreads();
+        const DevBuf B = bufs[b];
+        const double total = sTotal;
+        const long long count = (long long) B.numCh * B.numFrames;
+        int redo = forceOrder > 0 ? 2 : (forceOrder == 0 && rms_order_dependent(total, count) ? 1 : 0);        // uniform across the CTA; forceOrder < 0: tree sum as it is
+        if (redo == 1) {
+            long long small = count_small_terms(B, total);
+            #pragma unroll
+            for (int off = 16; off > 0; off >>= 1) small += __shfl_xor_sync(0xffffffffu, small, off);
+            __shared__ long long ssm[8];
+            if ((threadIdx.x & 31) == 0) ssm[threadIdx.x >> 5] = small;
+            __syncthreads();
+            small = ((ssm[0] + ssm[1]) + (ssm[2] + ssm[3])) + ((ssm[4] + ssm[5]) + (ssm[6] + ssm[7]));
+            redo = rms_rounds_differently(total, count, (double) (small + 256 + count / 16384) * 1.1102230246251565e-16) ? 2 : 0;
         }
+        __shared__ SeqShared seq;
+        const double v = (redo == 2) ? sum_squares_in_reference_order(B, seq) : total;       // redo is uniform: the whole CTA takes the call
+        if (threadIdx.x == 0) sumsq[b] = v;
     }
 }
 
@@ -253,15 +392,30 @@ stats_partial_kernel(const DevBuf* __restrict__ bufs, double* __restrict__ psum,
         pmax[(size_t) blockIdx.y * maxChunks + blockIdx.x] = m;
     }
 }
-__global__ void stats_final_kernel(const double* __restrict__ psum, const float* __restrict__ pmax, int maxChunks,
-                                   double* __restrict__ sumsq, float* __restrict__ peak, int n, const DevBuf* __restrict__ bufs, int forceOrder) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+// One CTA per buffer (grid = n): fold the partials in index order, then the two-stage order test of rms_order_dependent.
+__global__ void __launch_bounds__(256)
+stats_final_kernel(const double* __restrict__ psum, const float* __restrict__ pmax, int maxChunks,
+                   double* __restrict__ sumsq, float* __restrict__ peak, int n, const DevBuf* __restrict__ bufs, int forceOrder) {
+    const int b = blockIdx.x;
     if (b >= n) return;
     double s = 0.0; float m = 0.0f;
-    for (int i = 0; i < maxChunks; ++i) { s += psum[(size_t) b * maxChunks + i]; m = fmaxf(m, pmax[(size_t) b * maxChunks + i]); }
+    for (int i = 0; i < maxChunks; ++i) { s += psum[(size_t) b * maxChunks + i]; m = fmaxf(m, pmax[(size_t) b * maxChunks + i]); }   // every thread: the same value
     const DevBuf B = bufs[b];
-    if (forceOrder || rms_order_dependent(s, (long long) B.numCh * B.numFrames)) s = sum_squares_in_reference_order(B);   // see rms_order_dependent
-    sumsq[b] = s; peak[b] = m;
+    const long long count = (long long) B.numCh * B.numFrames;
+    int redo = forceOrder > 0 ? 2 : (forceOrder == 0 && rms_order_dependent(s, count) ? 1 : 0);
+    if (redo == 1) {
+        long long small = count_small_terms(B, s);
+        #pragma unroll
+        for (int off = 16; off > 0; off >>= 1) small += __shfl_xor_sync(0xffffffffu, small, off);
+        __shared__ long long ssm[8];
+        if ((threadIdx.x & 31) == 0) ssm[threadIdx.x >> 5] = small;
+        __syncthreads();
+        small = ((ssm[0] + ssm[1]) + (ssm[2] + ssm[3])) + ((ssm[4] + ssm[5]) + (ssm[6] + ssm[7]));
+        redo = rms_rounds_differently(s, count, (double) (small + 256 + count / 16384) * 1.1102230246251565e-16) ? 2 : 0;
+    }
+    __shared__ SeqShared seq;
+    const double v = (redo == 2) ? sum_squares_in_reference_order(B, seq) : s;
+    if (threadIdx.x == 0) { sumsq[b] = v; peak[b] = m; }
 }
 
 // ---- reverb-tail windows ------------------------------------------------------------------------------
@@ -350,10 +504,11 @@ __device__ __forceinline__ bool xc_better(double v, int ch, int lag, double bv, 
 // float->double conversions per DFMA: 4.5 TFLOP/s).
 __global__ void __launch_bounds__(kXcThreads)
 xcorr_partial_kernel(const DevBuf* __restrict__ bufs, const int* __restrict__ prefix, int n,
-                     const float* __restrict__ stim, int stimLen, int lagMin, int lagMax, XcPartial* __restrict__ partials) {
+                     const float* __restrict__ stim, int stimLen, int lagMin, int lagMax, XcPartial* __restrict__ partials, const int* __restrict__ need) {
     int lo = 0, hi = n;
     const int bid = blockIdx.x;
     while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (prefix[mid] <= bid) lo = mid; else hi = mid; }
+    if (need && !need[lo]) return;                              // f9_xcorr.cu: only the buffers whose candidate list overflowed are scanned exactly
     const DevBuf B = bufs[lo];
     const int local = bid - prefix[lo];
     const int nLags = lagMax - lagMin + 1;
@@ -426,9 +581,10 @@ xcorr_partial_kernel(const DevBuf* __restrict__ bufs, const int* __restrict__ pr
     }
 }
 
-__global__ void xcorr_final_kernel(const XcPartial* __restrict__ partials, const int* __restrict__ prefix, int n, XcPartial* __restrict__ best) {
+__global__ void xcorr_final_kernel(const XcPartial* __restrict__ partials, const int* __restrict__ prefix, int n, XcPartial* __restrict__ best,
+                                   const int* __restrict__ need) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= n) return;
+    if (b >= n || (need && !need[b])) return;
     // "maxValue starts at 0, strict >": a candidate must be > 0 to register (bch = -1 otherwise)
     double bv = 0.0; int bch = -1, blag = 0;
     for (int i = prefix[b]; i < prefix[b + 1]; ++i) {
@@ -460,7 +616,7 @@ cudaError_t launch_find_peak(const DevBuf* d_bufs, int n, int total_ctas, const 
         else peak_partial_kernel<false><<<total_ctas, kPeakThreads, 0, s>>>(d_bufs, d_prefix, n, d_partials, nullptr);
         ++*launches;
     }
-    peak_final_kernel<<<n, 128, 0, s>>>(d_partials, d_prefix, threshold, d_out_pos, d_psum, d_sumsq, d_peakv, d_bufs, forceOrder);
+    peak_final_kernel<<<n, 256, 0, s>>>(d_partials, d_prefix, threshold, d_out_pos, d_psum, d_sumsq, d_peakv, d_bufs, forceOrder);
     ++*launches;
     return cudaGetLastError();
 }
@@ -471,7 +627,7 @@ cudaError_t launch_stats(const DevBuf* d_bufs, int n, double* d_psum, float* d_p
     dim3 grid(kStatPartials, n);
     stats_partial_kernel<<<grid, kStatThreads, 0, s>>>(d_bufs, d_psum, d_pmax, kStatPartials);
     ++*launches;
-    stats_final_kernel<<<(n + 127) / 128, 128, 0, s>>>(d_psum, d_pmax, kStatPartials, d_sumsq, d_peak, n, d_bufs, forceOrder);
+    stats_final_kernel<<<n, 256, 0, s>>>(d_psum, d_pmax, kStatPartials, d_sumsq, d_peak, n, d_bufs, forceOrder);
     ++*launches;
     return cudaGetLastError();
 }
@@ -497,13 +653,13 @@ int xcorr_prefix(const DevBuf* h_bufs, int n, int lagMin, int lagMax, std::vecto
 }
 
 cudaError_t launch_xcorr(const DevBuf* d_bufs, int n, int total_ctas, const int* d_prefix, const float* d_stim, int stimLen,
-                         int lagMin, int lagMax, XcPartial* d_partials, XcPartial* d_best, cudaStream_t s, long long* launches) {
+                         int lagMin, int lagMax, XcPartial* d_partials, XcPartial* d_best, cudaStream_t s, long long* launches, const int* d_need) {
     if (n <= 0) return cudaSuccess;
     if (total_ctas > 0) {
-        xcorr_partial_kernel<<<total_ctas, kXcThreads, 0, s>>>(d_bufs, d_prefix, n, d_stim, stimLen, lagMin, lagMax, d_partials);
+        xcorr_partial_kernel<<<total_ctas, kXcThreads, 0, s>>>(d_bufs, d_prefix, n, d_stim, stimLen, lagMin, lagMax, d_partials, d_need);
         ++*launches;
     }
-    xcorr_final_kernel<<<(n + 127) / 128, 128, 0, s>>>(d_partials, d_prefix, n, d_best);
+    xcorr_final_kernel<<<(n + 127) / 128, 128, 0, s>>>(d_partials, d_prefix, n, d_best, d_need);
     ++*launches;
     return cudaGetLastError();
 }

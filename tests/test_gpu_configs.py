@@ -172,6 +172,55 @@ def test_config4_latency_detection_512_recordings(ctx, O, f9):
     assert np.array_equal(out2["ch"], np.arange(m) % 2)
 
 
+def test_config4_sweep_all_512_fast_equals_exact(ctx, O, f9):
+    """Config 4 with the sweep stimulus on all 512 recordings (+-2^16 lags): the candidate path (tensor-core approximation of
+    every lag + exact verification of the lags that can still win) returns value, channel and lag IDENTICAL to the exact scan of
+    every lag (option F9_XCORR_EXACT_ALL) -- the value bit for bit --, and to the oracle on a few.  Includes exact ties (the same
+    sweep at two delays / in both channels), silent recordings and a periodic recording (candidate list overflows: exact fallback)."""
+    torch = pytest.importorskip("torch")
+    n, ch, frames, L = 512, 2, 240000, 4800
+    rng = np.random.default_rng(44)
+    delays = rng.integers(0, 65536, n)
+    tt = np.arange(L) / 48000.0
+    sweep = (0.5 * np.sin(2 * np.pi * (200.0 * tt + (8000.0 - 200.0) / (2 * tt[-1]) * tt * tt))).astype(np.float32)
+    d_sw = torch.from_numpy(sweep).cuda()
+    g = torch.Generator(device="cuda"); g.manual_seed(44)
+    rec = torch.randn((n, ch, frames), generator=g, device="cuda", dtype=torch.float32) * (10 ** (-80 / 20))
+    for i in range(n):
+        rec[i, i % 2, delays[i]:delays[i] + L] += d_sw
+    # ties: identical content at two delays (noise-free so the sums are equal bit for bit) and in both channels
+    rec[20] = 0.0; rec[20, 0, 3000:3000 + L] = d_sw; rec[20, 0, 50000:50000 + L] = d_sw
+    rec[21] = 0.0; rec[21, 1, 777:777 + L] = d_sw; rec[21, 0, 777:777 + L] = d_sw
+    rec[22] = 0.0                                                                      # silence
+    per = torch.sin(2 * np.pi * 1000.0 * torch.arange(frames, device="cuda", dtype=torch.float64) / 48000.0).to(torch.float32) * 0.3
+    rec[23, 0] = per; rec[23, 1] = per                                                 # periodic: thousands of near-maxima
+    bufs = (f9.DevBuffer * n)(*[f9.DevBuffer(rec[i].data_ptr(), frames, ch, frames) for i in range(n)])
+    dt = np.dtype([("value", "<f8"), ("ch", "<i4"), ("lag", "<i4"), ("pad", "<i4"), ("pad2", "<i4")])
+
+    def run(c):
+        raw = torch.zeros(n * 24, dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
+        assert f9.lib().f9_dev_xcorr_peak_batch(c.handle, bufs, n, d_sw.data_ptr(), L, -65536, 65536, raw.data_ptr()) == 0
+        c.synchronize()
+        return np.frombuffer(raw.cpu().numpy().tobytes(), dtype=dt)
+
+    fast = run(ctx)
+    c2 = f9.Context(0)
+    try:
+        c2.set_option("F9_XCORR_EXACT_ALL", 1)
+        exact = run(c2)
+    finally:
+        c2.close()
+    assert np.array_equal(fast["lag"], exact["lag"]) and np.array_equal(fast["ch"], exact["ch"])
+    assert fast["value"].tobytes() == exact["value"].tobytes()                         # the same double sums
+    ok = np.ones(n, bool); ok[[20, 21, 22, 23]] = False
+    assert np.array_equal(fast["lag"][ok], delays[ok].astype(np.int32)) and np.array_equal(fast["ch"][ok], (np.arange(n) % 2)[ok])
+    assert (fast["lag"][20], fast["ch"][20]) == (3000, 0) and (fast["lag"][21], fast["ch"][21]) == (777, 0) and fast["ch"][22] == -1
+    for i in (0, 20, 21, 23):
+        found, lag, chn, val = O.xcorr_peak(rec[i].cpu().numpy(), sweep, -65536, 65536, 0.01)
+        assert (lag, chn) == (int(fast["lag"][i]), int(fast["ch"][i])) and val == fast["value"][i], i
+
+
 # ------------------------------------------------------------------------------------------------ configs[4]
 @pytest.mark.parametrize("kind", [0, 1])
 def test_config5_mixed_rates_to_48k(ctx, O, f9, kind):

@@ -74,15 +74,27 @@ def main():
     stim = torch.zeros(256, dtype=torch.float32, device=dev); stim[0] = 0.9
     raw = torch.zeros(n * 24, dtype=torch.uint8, device=dev)
     ms = timed(lambda: ctx._check(L.f9_dev_xcorr_peak_batch(ctx.handle, bufs, n, stim.data_ptr(), 256, -65536, 65536, raw.data_ptr())), reps=5)
-    report("xcorr_partial/final, impulse stimulus (256 samples), +-2^16 lags", "config4: 512 x 2 x 240000", ms, 4.0 * n * ch * frames, n * ch * frames, "samples",
-           "direct form, FP64 sums: %.2f TFLOP/s (FP64 FMA) over 131073 lags x 256 taps" % (2.0 * n * ch * 131073 * 256 / (ms * 1e-3) / 1e12))
+    report("xc_approx + select + exact + pick, impulse stimulus (256 samples), +-2^16 lags", "config4: 512 x 2 x 240000", ms, 4.0 * n * ch * frames, n * ch * frames, "samples",
+           "candidates on the tensor cores, exact verification")
     tt = np.arange(4800) / 48000.0
     sweep = torch.from_numpy((0.5 * np.sin(2 * np.pi * (200.0 * tt + 7800.0 / (2 * tt[-1]) * tt * tt))).astype(np.float32)).to(dev)
+    # recordings of the sweep measurement: the delayed sweep over the same noise (the impulse removed)
+    rec[torch.arange(n, device=dev), 0, d] = 0.0
+    for i in range(n):
+        rec[i, i % 2, int(d[i]):int(d[i]) + 4800] += sweep
+    ms = timed(lambda: ctx._check(L.f9_dev_xcorr_peak_batch(ctx.handle, bufs, n, sweep.data_ptr(), 4800, -65536, 65536, raw.data_ptr())), reps=5, do_flush=False)
+    out = np.frombuffer(raw.cpu().numpy().tobytes(), dtype=np.dtype([("value", "<f8"), ("ch", "<i4"), ("lag", "<i4"), ("pad", "<i4"), ("pad2", "<i4")]))
+    assert np.array_equal(out["lag"], d.cpu().numpy().astype(np.int32))
+    report("xc_approx (mma.sync fp16, every lag) + xc_select + xc_exact (FP64 chains of the candidates) + xc_pick, sweep stimulus (4800 samples), +-2^16 lags",
+           "config4: 512 x 2 x 240000", ms, 4.0 * n * ch * frames, n * ch * frames, "samples",
+           "%.1f TFLOP/s of fp16 tensor work (2 x 131073 lags x 4800 taps per channel); argmax, channel and value identical to the exact scan" % (2.0 * n * ch * 131073 * 4800 / (ms * 1e-3) / 1e12))
     m = 64
+    cx = f9.Context(0); cx.set_stream(stream.cuda_stream); cx.set_option("F9_XCORR_EXACT_ALL", 1)
     bufs_s = (f9.DevBuffer * m)(*[f9.DevBuffer(rec[i].data_ptr(), frames, ch, frames) for i in range(m)])
-    ms = timed(lambda: ctx._check(L.f9_dev_xcorr_peak_batch(ctx.handle, bufs_s, m, sweep.data_ptr(), 4800, -65536, 65536, raw.data_ptr())), reps=3, do_flush=False)
-    report("xcorr_partial/final, sweep stimulus (4800 samples), +-2^16 lags", "config4 subset: 64 x 2 x 240000", ms, 4.0 * m * ch * frames, m * ch * frames, "samples",
-           "FP64-bound: %.2f TFLOP/s (FP64 FMA)" % (2.0 * m * ch * 131073 * 4800 / (ms * 1e-3) / 1e12))
+    ms = timed(lambda: cx._check(L.f9_dev_xcorr_peak_batch(cx.handle, bufs_s, m, sweep.data_ptr(), 4800, -65536, 65536, raw.data_ptr())), reps=3, do_flush=False)
+    report("xcorr_partial/final (exact FP64 sums of every lag: option F9_XCORR_EXACT_ALL, the fallback path), sweep stimulus (4800 samples), +-2^16 lags", "config4 subset: 64 x 2 x 240000", ms, 4.0 * m * ch * frames, m * ch * frames, "samples",
+           "FP64-bound: %.2f TFLOP/s (FP64 FMA); 512 recordings = 8x this" % (2.0 * m * ch * 131073 * 4800 / (ms * 1e-3) / 1e12))
+    cx.synchronize(); cx.close()
     del rec
 
     # ---------------- config 2: trim + tail scan over 256 stereo captures (96 kHz, 10 s + latency + 0.5 s)
