@@ -51,8 +51,9 @@ constexpr int kThreads = (kFirstLoader + kLoaderWarps) * 32;
 // TMA-fed kernels: warps 0-3 epilogue, 4 producer, 5..9 issue, 10.. convert (a quarter of the rows x (part of) one K step each)
 constexpr int kIssuersTma = kUmmaIssuersTma;
 constexpr int kFirstConv = 4 + 1 + kIssuersTma;
-constexpr int kConvSplit = 1;                    // converter warps per (row quarter, K step): 1 or 2 (8 or 16 samples per thread)
-constexpr int kConvWarps = 8 * kConvSplit;
+constexpr int kConvTeams = 2;                    // teams of four warps (one per TMEM lane quarter); team i takes the stages gs % kConvTeams == i
+constexpr int kConvWarps = 4 * kConvTeams;
+constexpr int kConvPerStage = 4;                 // warps that take part in one stage: its barriers count these
 constexpr int kThreadsTma = (kFirstConv + kConvWarps) * 32;
 constexpr uint32_t kParkNs = 1000;                // suspend-time hint of the TMA roles' barrier waits (a hot poll loop cost 40 % of the issue slots)
 constexpr int kSpin = 1 << 26;                   // bounded waits: a protocol bug must not hang the GPU
@@ -379,17 +380,19 @@ __device__ __forceinline__ void producer_role(const FeedArgs& A, const UmmaTma& 
     }
 }
 
+// Two teams of four warps (one per TMEM lane quarter) take the stages alternately: team 0 the even ones, team 1 the odd ones.  A
+// warp converts BOTH 16-sample K steps of its 32 rows and writes the whole operand slot with one tcgen05.st.32x32b.x32.  What
+// bounded the feed was not the converters' instruction count but the serial chain of a stage inside a warp -- wait for the box,
+// LDS, convert, wait for the slot, tcgen05.st, wait::st, arrive: ~900 clk, 17 times per tile in every warp (splitting a stage
+// over sixteen warps did not help: 0.74 ms, the chain stays).  With teams a warp walks that chain for every other stage only.
 __device__ __forceinline__ void converter_role(const FeedArgs& A, uint32_t tmem, int warp, int lane) {
-    constexpr int C = 4 / kConvSplit;                          // 16-byte chunks (4 samples) per thread and stage
-    const int quarter = warp & 3, part = (warp - kFirstConv) >> 2; // TMEM lane quarter (fixed by the warp id); K step of the stage and its part
-    const int h = part / kConvSplit, sub = part % kConvSplit;
+    const int quarter = warp & 3, team = (warp - kFirstConv) >> 2;             // TMEM lane quarter (fixed by the warp id); the team's stages
     const int rho = quarter * 32 + lane;                       // period row = TMEM lane = row of the box
-    const uint32_t tdst = tmem + ((uint32_t) (quarter * 32) << 16) + (uint32_t) (A.aCol + h * 16 + sub * 2 * C);
+    const uint32_t tdst = tmem + ((uint32_t) (quarter * 32) << 16) + (uint32_t) A.aCol;
     const uint32_t ringRow = smem_u32(A.ring) + (uint32_t) (rho * 128);
     const uint32_t sw = (uint32_t) (rho & 7);
-    __half2 hmax = __floats2half2_rn(0.f, 0.f);
     const int aMask = A.aMask, aShift = A.aShift;
-    int sIdx = 0; uint32_t sPh = 0; int gs = 0;
+    int sIdx = 0; uint32_t sPh = 0; int gs = 0;                // ring position / phase of the next TMA stage, global stage count
     struct TileIn { const float* in; long long l00, inAvail; bool viaTma, mask; };
     auto load_rec = [&](const UmmaTileRec* r) {
         TileIn T; T.in = ldg_ptr(&r->in); T.l00 = __ldg(&r->l00); T.inAvail = __ldg(&r->inAvail);
@@ -401,21 +404,25 @@ __device__ __forceinline__ void converter_role(const FeedArgs& A, uint32_t tmem,
     for (int t = 0; t < A.myTiles; ++t, rec += gridDim.x) {
         T = N;
         if (t + 1 < A.myTiles) N = load_rec(rec + gridDim.x);                  // consumed one tile later
-        const long long lrow = T.l00 + (long long) rho * A.p + h * 16 + sub * 4 * C;
+        const long long lrow = T.l00 + (long long) rho * A.p;
         for (int st = 0; st < A.nStages; ++st, ++gs) {
-            float4 v[C];
+            if (gs % kConvTeams != team) {                     // another team's stage: only the ring position moves
+                if (T.viaTma && ++sIdx == A.stages) { sIdx = 0; sPh ^= 1; }
+                continue;
+            }
+            float4 v[8];
             if (T.viaTma) {
                 mbar_wait_parked(A.full + sIdx, sPh, kParkNs);
                 const uint32_t a = ringRow + (uint32_t) (sIdx * kTmaStageBytes);
                 #pragma unroll
-                for (int c = 0; c < C; ++c)
+                for (int c = 0; c < 8; ++c)
                     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[c].x), "=f"(v[c].y), "=f"(v[c].z), "=f"(v[c].w)
-                                 : "r"(a + ((((uint32_t) (4 * h + C * sub + c)) ^ sw) << 4)) : "memory");
+                                 : "r"(a + ((((uint32_t) c) ^ sw) << 4)) : "memory");
                 if (T.mask) {                                  // the box left the window [0, inAvail): zero what lies outside
                     const long long l0 = lrow + st * 32;
                     const long long lo = -l0, hi = T.inAvail - l0;              // valid element indices e of this thread's samples: lo <= e < hi
                     #pragma unroll
-                    for (int c = 0; c < C; ++c) {
+                    for (int c = 0; c < 8; ++c) {
                         if (4 * c < lo || 4 * c >= hi) v[c].x = 0.f;
                         if (4 * c + 1 < lo || 4 * c + 1 >= hi) v[c].y = 0.f;
                         if (4 * c + 2 < lo || 4 * c + 2 >= hi) v[c].z = 0.f;
@@ -424,7 +431,7 @@ __device__ __forceinline__ void converter_role(const FeedArgs& A, uint32_t tmem,
                 }
             } else {
                 #pragma unroll
-                for (int c = 0; c < C; ++c) {
+                for (int c = 0; c < 8; ++c) {
                     const long long l = lrow + st * 32 + 4 * c;
                     const float* ptr = T.in + l;
                     if (l >= 0 && l + 3 < T.inAvail) v[c] = __ldg(reinterpret_cast<const float4*>(ptr));
@@ -434,25 +441,27 @@ __device__ __forceinline__ void converter_role(const FeedArgs& A, uint32_t tmem,
                     }
                 }
             }
-            uint32_t hd[2 * C], tl[2 * C];
+            // w[0..7] head of K step 0, w[8..15] its tail, w[16..23] head of K step 1, w[24..31] its tail: the slot's 32 columns
+            uint32_t w[32];
             #pragma unroll
-            for (int c = 0; c < C; ++c) {
+            for (int c = 0; c < 8; ++c) {
                 float4 xv = v[c];
                 xv.x *= kPreScale; xv.y *= kPreScale; xv.z *= kPreScale; xv.w *= kPreScale;
                 const __half2 h01 = __floats2half2_rn(xv.x, xv.y), h23 = __floats2half2_rn(xv.z, xv.w);
-                hmax = __hmax2_nan(hmax, __hmax2_nan(__habs2(h01), __habs2(h23)));
-                hd[2 * c] = *reinterpret_cast<const uint32_t*>(&h01); hd[2 * c + 1] = *reinterpret_cast<const uint32_t*>(&h23);
+                const uint32_t u01 = *reinterpret_cast<const uint32_t*>(&h01), u23 = *reinterpret_cast<const uint32_t*>(&h23);
                 // tail = (x' - head) * 2048, exact: one mixed-precision FMA, head * (-2048) + x' * 2048.  x' * 2048 is an exponent
                 // add on the integer pipe (x' = 0 becomes 2^-116, which the fp16 tail rounds to 0; non-finite x' takes the redo).
                 float t0, t1, t2, t3;
                 asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tfma.rn.f32.f16 %0, lo, %5, %3;\n\tfma.rn.f32.f16 %1, hi, %5, %4;\n\t}"
-                    : "=f"(t0), "=f"(t1) : "r"(hd[2 * c]), "f"(__int_as_float(__float_as_int(xv.x) + (11 << 23))),
+                    : "=f"(t0), "=f"(t1) : "r"(u01), "f"(__int_as_float(__float_as_int(xv.x) + (11 << 23))),
                       "f"(__int_as_float(__float_as_int(xv.y) + (11 << 23))), "h"((unsigned short) 0xE800));
                 asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tfma.rn.f32.f16 %0, lo, %5, %3;\n\tfma.rn.f32.f16 %1, hi, %5, %4;\n\t}"
-                    : "=f"(t2), "=f"(t3) : "r"(hd[2 * c + 1]), "f"(__int_as_float(__float_as_int(xv.z) + (11 << 23))),
+                    : "=f"(t2), "=f"(t3) : "r"(u23), "f"(__int_as_float(__float_as_int(xv.z) + (11 << 23))),
                       "f"(__int_as_float(__float_as_int(xv.w) + (11 << 23))), "h"((unsigned short) 0xE800));
                 const __half2 t01 = __floats2half2_rn(t0, t1), t23 = __floats2half2_rn(t2, t3);
-                tl[2 * c] = *reinterpret_cast<const uint32_t*>(&t01); tl[2 * c + 1] = *reinterpret_cast<const uint32_t*>(&t23);
+                const int base = (c >> 2) * 16 + (c & 3) * 2;                  // K step c / 4, words 2 (c % 4), + 1 of its head
+                w[base] = u01; w[base + 1] = u23;
+                w[base + 8] = *reinterpret_cast<const uint32_t*>(&t01); w[base + 9] = *reinterpret_cast<const uint32_t*>(&t23);
             }
             if (T.viaTma) {                                    // the stage's rows are in registers: the box may be refilled
                 __syncwarp();
@@ -461,23 +470,20 @@ __device__ __forceinline__ void converter_role(const FeedArgs& A, uint32_t tmem,
             }
             if (gs > aMask) mbar_wait_parked(A.slotFree + (gs & aMask), (uint32_t) (((gs >> aShift) - 1) & 1), kParkNs);   // the MMAs of the slot's previous stage are done
             tc_fence_after();
-            const uint32_t td = tdst + (uint32_t) ((gs & aMask) * 32);           // head columns; the tail sits 8 columns up
-            if constexpr (kConvSplit == 1) {
-                asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
-                             :: "r"(td), "r"(hd[0]), "r"(hd[1]), "r"(hd[2]), "r"(hd[3]), "r"(hd[4 % (2 * C)]), "r"(hd[5 % (2 * C)]), "r"(hd[6 % (2 * C)]), "r"(hd[7 % (2 * C)]),
-                                "r"(tl[0]), "r"(tl[1]), "r"(tl[2]), "r"(tl[3]), "r"(tl[4 % (2 * C)]), "r"(tl[5 % (2 * C)]), "r"(tl[6 % (2 * C)]), "r"(tl[7 % (2 * C)]) : "memory");
-            } else {
-                asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" :: "r"(td), "r"(hd[0]), "r"(hd[1]), "r"(hd[2]), "r"(hd[3]) : "memory");
-                asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" :: "r"(td + 8), "r"(tl[0]), "r"(tl[1]), "r"(tl[2]), "r"(tl[3]) : "memory");
-            }
+            const uint32_t td = tdst + (uint32_t) ((gs & aMask) * 32);
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+                         :: "r"(td), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]), "r"(w[8]), "r"(w[9]), "r"(w[10]), "r"(w[11]),
+                            "r"(w[12]), "r"(w[13]), "r"(w[14]), "r"(w[15]), "r"(w[16]), "r"(w[17]), "r"(w[18]), "r"(w[19]), "r"(w[20]), "r"(w[21]), "r"(w[22]), "r"(w[23]),
+                            "r"(w[24]), "r"(w[25]), "r"(w[26]), "r"(w[27]), "r"(w[28]), "r"(w[29]), "r"(w[30]), "r"(w[31]) : "memory");
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
             __syncwarp();
             if (lane == 0) { if (A.pair) mbar_arrive_leader(A.aReady + (gs & aMask)); else mbar_arrive(A.aReady + (gs & aMask)); }
         }
     }
-    const float2 hm = __half22float2(hmax);
-    if (!(hm.x < 32768.0f) || !(hm.y < 32768.0f)) atomicOr(A.ovf, 1u);
+    // Samples outside the fp16 split's range are not looked for here: |128 x| >= 65520, Inf and NaN become an infinite or NaN head,
+    // every product with it is Inf or NaN (0 * Inf included), so the outputs it reaches are not finite and the EPILOGUE raises the
+    // redo flag (one FFMA per output there against five half2 operations per four samples here, on the path that bounds the kernel).
 }
 
 // out = (D0A + D0B + D1 / 2048) / kPreScale: the scalings are powers of two, the only roundings are the two additions
@@ -519,10 +525,10 @@ umma_fir_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix
         if (threadIdx.x == 0) {
             // register loader: full <- 8 loader warps, empty <- the copy warp's commit, cpDone <- its commit
             // TMA feed:        full <- the producer's expect_tx, empty <- 8 converter warps, cpDone ("operand ready") <- 8 converter warps
-            for (int s = 0; s < stages; ++s) { mbar_init(sm.full + s, TMA ? 1 : kLoaderWarps); mbar_init(sm.empty + s, TMA ? kConvWarps : 1); }
+            for (int s = 0; s < stages; ++s) { mbar_init(sm.full + s, TMA ? 1 : kLoaderWarps); mbar_init(sm.empty + s, TMA ? kConvPerStage : 1); }
             // CTA pairs: "operand ready" and "accumulator drained" collect both CTAs' arrivals in the leader
             for (int g = 0; g < kUmmaMaxGroups; ++g) { mbar_init(sm.accFull + g, 1); mbar_init(sm.accEmpty + g, CTA2 ? 8 : 4); }
-            for (int i = 0; i < kASlotsMax; ++i) { mbar_init(sm.cpDone + i, TMA ? (CTA2 ? 2 : 1) * kConvWarps : 1); mbar_init(sm.slotFree + i, TMA ? kIssuersTma : kIssuers); }
+            for (int i = 0; i < kASlotsMax; ++i) { mbar_init(sm.cpDone + i, TMA ? (CTA2 ? 2 : 1) * kConvPerStage : 1); mbar_init(sm.slotFree + i, TMA ? kIssuersTma : kIssuers); }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         if (warp == 4) {
@@ -719,6 +725,7 @@ umma_fir_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix
         };
         TileOut ON = {nullptr, 0, 0};
         if (myTiles > 0) ON = load_out(tileId);
+        float sticky = 0.0f;                                   // stays 0 while every output is finite: fma(v, 0, sticky) turns Inf / NaN into NaN
         for (int t = 0; t < myTiles; ++t, tileId += gridDim.x) {
             const TileOut S = ON;
             if (t + 1 < myTiles) ON = load_out(tileId + (int) gridDim.x);     // consumed one tile later
@@ -751,9 +758,12 @@ umma_fir_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix
                     }
                     float4* dst = reinterpret_cast<float4*>(sm.epi + row0 * kEpiPitch);
                     #pragma unroll
-                    for (int c = 0; c < 4; ++c)
-                        dst[c] = make_float4(combine(v0[4 * c], vb[4 * c], v1[4 * c]), combine(v0[4 * c + 1], vb[4 * c + 1], v1[4 * c + 1]),
-                                             combine(v0[4 * c + 2], vb[4 * c + 2], v1[4 * c + 2]), combine(v0[4 * c + 3], vb[4 * c + 3], v1[4 * c + 3]));
+                    for (int c = 0; c < 4; ++c) {
+                        const float4 o4 = make_float4(combine(v0[4 * c], vb[4 * c], v1[4 * c]), combine(v0[4 * c + 1], vb[4 * c + 1], v1[4 * c + 1]),
+                                                      combine(v0[4 * c + 2], vb[4 * c + 2], v1[4 * c + 2]), combine(v0[4 * c + 3], vb[4 * c + 3], v1[4 * c + 3]));
+                        if (TMA) sticky = fmaf(o4.x, 0.0f, fmaf(o4.y, 0.0f, fmaf(o4.z, 0.0f, fmaf(o4.w, 0.0f, sticky))));
+                        dst[c] = o4;
+                    }
                     __syncwarp();
                     PROF_BEGIN(wst);
                     const int col = gl * NB + h * 16 + (lane & 15);           // slot inside the block
@@ -780,6 +790,7 @@ umma_fir_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix
                 }
             }
         }
+        if (TMA && !(sticky == 0.0f)) atomicOr(ovf, 1u);       // an input sample was outside the fp16 split's range (see converter_role)
         if (prof && warp == 0 && lane == 0) { prof[blockIdx.x * 16 + 5] = clock64() - pT0; prof[blockIdx.x * 16 + 6] = pW0; prof[blockIdx.x * 16 + 7] = pW2; }
     }
 
