@@ -597,6 +597,7 @@ int resample_build_tiles(ResampleLaunch& L, const Seg* segs, int n, std::vector<
                 int stages = 2;
                 const int maxStages = D.get("F9_UMMA_STAGES", 8);
                 while (stages < maxStages && umma_smem_bytes(L.um.maxEntries, L.um.NB, stages + 1, true, cta2) <= 227 * 1024) ++stages;
+                stages &= ~1;                                   // even: a ring position always belongs to the same converter team (f9_umma.cu)
                 if (umma_smem_bytes(L.um.maxEntries, L.um.NB, stages, true, cta2) <= 227 * 1024) {
                     L.um_tma = true; L.um_cta2 = cta2; L.um_stages = stages; L.um_smem = umma_smem_bytes(L.um.maxEntries, L.um.NB, stages, true, cta2);
                 }

@@ -56,7 +56,12 @@ constexpr int kConvWarps = 4 * kConvTeams;
 constexpr int kConvPerStage = 4;                 // warps that take part in one stage: its barriers count these
 constexpr int kThreadsTma = (kFirstConv + kConvWarps) * 32;
 constexpr uint32_t kParkNs = 1000;                // suspend-time hint of the TMA roles' barrier waits (a hot poll loop cost 40 % of the issue slots)
-constexpr int kSpin = 1 << 26;                   // bounded waits: a protocol bug must not hang the GPU
+#ifdef F9_DIAG
+constexpr int kSpin = 1 << 22;
+#else
+constexpr int kSpin = 1 << 26;
+#endif
+//                   // bounded waits: a protocol bug must not hang the GPU
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -71,10 +76,15 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
                  : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
+#ifdef F9_DIAG
+#define F9_TRAP(bar, parity) do { printf("[umma] wait timed out: block %d warp %d barrier +%u parity %u\n", (int) blockIdx.x, (int) (threadIdx.x >> 5), smem_u32(bar), (unsigned) (parity)); __trap(); } while (0)
+#else
+#define F9_TRAP(bar, parity) __trap()
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     #pragma unroll 1
     for (int i = 0; i < kSpin; ++i) if (mbar_try_wait(bar, parity)) return;
-    __trap();
+    F9_TRAP(bar, parity);
 }
 // Same, for waits that are expected to be long (epilogue): the hardware may park the thread for up to `ns` per attempt
 // instead of re-issuing the poll, which leaves the issue slots to the loader warps.
@@ -86,7 +96,7 @@ __device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity,
                      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(ns) : "memory");
         if (ok) return;
     }
-    __trap();
+    F9_TRAP(bar, parity);
 }
 __device__ __forceinline__ uint32_t elect_one() {
     uint32_t el;
@@ -129,7 +139,7 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
                      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(ns) : "memory");
         if (ok) return;
     }
-    __trap();
+    F9_TRAP(bar, parity);
 }
 __device__ __forceinline__ void umma2_commit_both(uint64_t* bar) {                  // arrives on the barrier at this offset in both CTAs
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
@@ -365,7 +375,13 @@ __device__ __forceinline__ void producer_role(const FeedArgs& A, const UmmaTma& 
             if (nxt.y >= 0) pf = reinterpret_cast<const char*>(ldg_ptr(&nr->in) + __ldg(&nr->l00));
         }
         if (cur.y < 0) {
-            if (pf) for (int st = 0; st < A.nStages; ++st) l2_prefetch(pf + (size_t) st * pfChunk, pfChunk);
+            // a tile read with guarded loads: its stages still take their ring positions (see converter_role), without a box
+            for (int st = 0; st < A.nStages; ++st) {
+                mbar_wait_parked(A.empty + sIdx, sPh ^ 1, kParkNs);
+                mbar_arrive(A.full + sIdx);
+                if (pf) l2_prefetch(pf + (size_t) st * pfChunk, pfChunk);
+                if (++sIdx == A.stages) { sIdx = 0; sPh ^= 1; }
+            }
         } else {
             const CUtensorMap* map = &TM.maps[cur.y];
             for (int st = 0; st < A.nStages; ++st) {
@@ -378,6 +394,110 @@ __device__ __forceinline__ void producer_role(const FeedArgs& A, const UmmaTma& 
         }
         cur = nxt;
     }
+}
+
+// Short windows (Lagrange and the other short kinds at integer decimation: a handful of stages per tile, almost no MMA work): all
+// eight converter warps share every stage, a warp converts one 16-sample K step of its 32 rows (tcgen05.st.x16).  The serial chain
+// of a stage is shorter this way, which is what matters when the feed is all there is (96 -> 48 k Lagrange: 0.48 ms against
+// 0.60 ms with teams).
+__device__ __forceinline__ void converter_role_split(const FeedArgs& A, uint32_t tmem, int warp, int lane) {
+    constexpr int kConvSplit = 1;
+    constexpr int C = 4 / kConvSplit;                          // 16-byte chunks (4 samples) per thread and stage
+    const int quarter = warp & 3, part = (warp - kFirstConv) >> 2; // TMEM lane quarter (fixed by the warp id); K step of the stage and its part
+    const int h = part / kConvSplit, sub = part % kConvSplit;
+    const int rho = quarter * 32 + lane;                       // period row = TMEM lane = row of the box
+    const uint32_t tdst = tmem + ((uint32_t) (quarter * 32) << 16) + (uint32_t) (A.aCol + h * 16 + sub * 2 * C);
+    const uint32_t ringRow = smem_u32(A.ring) + (uint32_t) (rho * 128);
+    const uint32_t sw = (uint32_t) (rho & 7);
+    __half2 hmax = __floats2half2_rn(0.f, 0.f);
+    const int aMask = A.aMask, aShift = A.aShift;
+    int sIdx = 0; uint32_t sPh = 0; int gs = 0;
+    struct TileIn { const float* in; long long l00, inAvail; bool viaTma, mask; };
+    auto load_rec = [&](const UmmaTileRec* r) {
+        TileIn T; T.in = ldg_ptr(&r->in); T.l00 = __ldg(&r->l00); T.inAvail = __ldg(&r->inAvail);
+        const int4 tail = ld_rec_tail(r); T.viaTma = tail.y >= 0; T.mask = tail.z != 0; return T;
+    };
+    const UmmaTileRec* rec = A.recs + blockIdx.x;
+    TileIn T = {nullptr, 0, 0, false, false}, N = T;
+    if (A.myTiles > 0) N = load_rec(rec);
+    for (int t = 0; t < A.myTiles; ++t, rec += gridDim.x) {
+        T = N;
+        if (t + 1 < A.myTiles) N = load_rec(rec + gridDim.x);                  // consumed one tile later
+        const long long lrow = T.l00 + (long long) rho * A.p + h * 16 + sub * 4 * C;
+        for (int st = 0; st < A.nStages; ++st, ++gs) {
+            float4 v[C];
+            mbar_wait_parked(A.full + sIdx, sPh, kParkNs);     // every stage takes a ring position (producer_role), fed by TMA or not
+            if (T.viaTma) {
+                const uint32_t a = ringRow + (uint32_t) (sIdx * kTmaStageBytes);
+                #pragma unroll
+                for (int c = 0; c < C; ++c)
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[c].x), "=f"(v[c].y), "=f"(v[c].z), "=f"(v[c].w)
+                                 : "r"(a + ((((uint32_t) (4 * h + C * sub + c)) ^ sw) << 4)) : "memory");
+                if (T.mask) {                                  // the box left the window [0, inAvail): zero what lies outside
+                    const long long l0 = lrow + st * 32;
+                    const long long lo = -l0, hi = T.inAvail - l0;              // valid element indices e of this thread's samples: lo <= e < hi
+                    #pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        if (4 * c < lo || 4 * c >= hi) v[c].x = 0.f;
+                        if (4 * c + 1 < lo || 4 * c + 1 >= hi) v[c].y = 0.f;
+                        if (4 * c + 2 < lo || 4 * c + 2 >= hi) v[c].z = 0.f;
+                        if (4 * c + 3 < lo || 4 * c + 3 >= hi) v[c].w = 0.f;
+                    }
+                }
+            } else {
+                #pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const long long l = lrow + st * 32 + 4 * c;
+                    const float* ptr = T.in + l;
+                    if (l >= 0 && l + 3 < T.inAvail) v[c] = __ldg(reinterpret_cast<const float4*>(ptr));
+                    else {
+                        v[c].x = (l >= 0 && l < T.inAvail) ? __ldg(ptr) : 0.f;             v[c].y = (l + 1 >= 0 && l + 1 < T.inAvail) ? __ldg(ptr + 1) : 0.f;
+                        v[c].z = (l + 2 >= 0 && l + 2 < T.inAvail) ? __ldg(ptr + 2) : 0.f; v[c].w = (l + 3 >= 0 && l + 3 < T.inAvail) ? __ldg(ptr + 3) : 0.f;
+                    }
+                }
+            }
+            uint32_t hd[2 * C], tl[2 * C];
+            #pragma unroll
+            for (int c = 0; c < C; ++c) {
+                float4 xv = v[c];
+                xv.x *= kPreScale; xv.y *= kPreScale; xv.z *= kPreScale; xv.w *= kPreScale;
+                const __half2 h01 = __floats2half2_rn(xv.x, xv.y), h23 = __floats2half2_rn(xv.z, xv.w);
+                hmax = __hmax2_nan(hmax, __hmax2_nan(__habs2(h01), __habs2(h23)));
+                hd[2 * c] = *reinterpret_cast<const uint32_t*>(&h01); hd[2 * c + 1] = *reinterpret_cast<const uint32_t*>(&h23);
+                // tail = (x' - head) * 2048, exact: one mixed-precision FMA, head * (-2048) + x' * 2048.  x' * 2048 is an exponent
+                // add on the integer pipe (x' = 0 becomes 2^-116, which the fp16 tail rounds to 0; non-finite x' takes the redo).
+                float t0, t1, t2, t3;
+                asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tfma.rn.f32.f16 %0, lo, %5, %3;\n\tfma.rn.f32.f16 %1, hi, %5, %4;\n\t}"
+                    : "=f"(t0), "=f"(t1) : "r"(hd[2 * c]), "f"(__int_as_float(__float_as_int(xv.x) + (11 << 23))),
+                      "f"(__int_as_float(__float_as_int(xv.y) + (11 << 23))), "h"((unsigned short) 0xE800));
+                asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tfma.rn.f32.f16 %0, lo, %5, %3;\n\tfma.rn.f32.f16 %1, hi, %5, %4;\n\t}"
+                    : "=f"(t2), "=f"(t3) : "r"(hd[2 * c + 1]), "f"(__int_as_float(__float_as_int(xv.z) + (11 << 23))),
+                      "f"(__int_as_float(__float_as_int(xv.w) + (11 << 23))), "h"((unsigned short) 0xE800));
+                const __half2 t01 = __floats2half2_rn(t0, t1), t23 = __floats2half2_rn(t2, t3);
+                tl[2 * c] = *reinterpret_cast<const uint32_t*>(&t01); tl[2 * c + 1] = *reinterpret_cast<const uint32_t*>(&t23);
+            }
+            __syncwarp();                                      // the stage's rows are in registers: the ring position may be refilled
+            if (lane == 0) mbar_arrive(A.empty + sIdx);
+            if (++sIdx == A.stages) { sIdx = 0; sPh ^= 1; }
+            if (gs > aMask) mbar_wait_parked(A.slotFree + (gs & aMask), (uint32_t) (((gs >> aShift) - 1) & 1), kParkNs);   // the MMAs of the slot's previous stage are done
+            tc_fence_after();
+            const uint32_t td = tdst + (uint32_t) ((gs & aMask) * 32);           // head columns; the tail sits 8 columns up
+            if constexpr (kConvSplit == 1) {
+                asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                             :: "r"(td), "r"(hd[0]), "r"(hd[1]), "r"(hd[2]), "r"(hd[3]), "r"(hd[4 % (2 * C)]), "r"(hd[5 % (2 * C)]), "r"(hd[6 % (2 * C)]), "r"(hd[7 % (2 * C)]),
+                                "r"(tl[0]), "r"(tl[1]), "r"(tl[2]), "r"(tl[3]), "r"(tl[4 % (2 * C)]), "r"(tl[5 % (2 * C)]), "r"(tl[6 % (2 * C)]), "r"(tl[7 % (2 * C)]) : "memory");
+            } else {
+                asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" :: "r"(td), "r"(hd[0]), "r"(hd[1]), "r"(hd[2]), "r"(hd[3]) : "memory");
+                asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" :: "r"(td + 8), "r"(tl[0]), "r"(tl[1]), "r"(tl[2]), "r"(tl[3]) : "memory");
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { if (A.pair) mbar_arrive_leader(A.aReady + (gs & aMask)); else mbar_arrive(A.aReady + (gs & aMask)); }
+        }
+    }
+    const float2 hm = __half22float2(hmax);
+    if (!(hm.x < 32768.0f) || !(hm.y < 32768.0f)) atomicOr(A.ovf, 1u);
 }
 
 // Two teams of four warps (one per TMEM lane quarter) take the stages alternately: team 0 the even ones, team 1 the odd ones.  A
@@ -407,12 +527,16 @@ __device__ __forceinline__ void converter_role(const FeedArgs& A, uint32_t tmem,
         const long long lrow = T.l00 + (long long) rho * A.p;
         for (int st = 0; st < A.nStages; ++st, ++gs) {
             if (gs % kConvTeams != team) {                     // another team's stage: only the ring position moves
-                if (T.viaTma && ++sIdx == A.stages) { sIdx = 0; sPh ^= 1; }
+                if (++sIdx == A.stages) { sIdx = 0; sPh ^= 1; }
                 continue;
             }
+            // EVERY stage takes a ring position, also those of a tile that is not fed by TMA (the producer then completes the
+            // position's "full" phase without a box).  The ring depth is even, so a ring position -- its full / empty barriers --
+            // always belongs to the same team, which therefore sees every phase of them: a parity wait only tells the current
+            // phase from the one before it, and a warp that saw every other phase could take a box still in flight for landed.
+            mbar_wait_parked(A.full + sIdx, sPh, kParkNs);
             float4 v[8];
             if (T.viaTma) {
-                mbar_wait_parked(A.full + sIdx, sPh, kParkNs);
                 const uint32_t a = ringRow + (uint32_t) (sIdx * kTmaStageBytes);
                 #pragma unroll
                 for (int c = 0; c < 8; ++c)
@@ -463,11 +587,9 @@ __device__ __forceinline__ void converter_role(const FeedArgs& A, uint32_t tmem,
                 w[base] = u01; w[base + 1] = u23;
                 w[base + 8] = *reinterpret_cast<const uint32_t*>(&t01); w[base + 9] = *reinterpret_cast<const uint32_t*>(&t23);
             }
-            if (T.viaTma) {                                    // the stage's rows are in registers: the box may be refilled
-                __syncwarp();
-                if (lane == 0) mbar_arrive(A.empty + sIdx);
-                if (++sIdx == A.stages) { sIdx = 0; sPh ^= 1; }
-            }
+            __syncwarp();                                      // the stage's rows are in registers: the ring position may be refilled
+            if (lane == 0) mbar_arrive(A.empty + sIdx);
+            if (++sIdx == A.stages) { sIdx = 0; sPh ^= 1; }
             if (gs > aMask) mbar_wait_parked(A.slotFree + (gs & aMask), (uint32_t) (((gs >> aShift) - 1) & 1), kParkNs);   // the MMAs of the slot's previous stage are done
             tc_fence_after();
             const uint32_t td = tdst + (uint32_t) ((gs & aMask) * 32);
@@ -506,6 +628,8 @@ umma_fir_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix
     const int NB = P.NB;                                       // slots per group: MMA N
     const int aMask = P.aSlots - 1, aShift = P.aSlots == 4 ? 2 : 1, aCol = 512 - 32 * P.aSlots;   // TMEM operand ring
     const int warp = __shfl_sync(0xffffffffu, (int) (threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    const bool teams = P.taps >= 64;                           // long windows: converter teams take the stages alternately (converter_role)
+    const int convPerStage = teams ? kConvPerStage : kConvWarps;       // converter warps that take part in one stage
     // slot block of this CTA: tile t belongs to block t % nGB; with CTA pairs tiles are dealt two at a time, (t / 2) % nGB, so
     // that both CTAs of a pair hold the same weights (the grid is a multiple of 2 * nGB: the block never changes)
     const int gb = CTA2 ? (int) (blockIdx.x >> 1) % P.nGB : (int) blockIdx.x % P.nGB;
@@ -525,10 +649,10 @@ umma_fir_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix
         if (threadIdx.x == 0) {
             // register loader: full <- 8 loader warps, empty <- the copy warp's commit, cpDone <- its commit
             // TMA feed:        full <- the producer's expect_tx, empty <- 8 converter warps, cpDone ("operand ready") <- 8 converter warps
-            for (int s = 0; s < stages; ++s) { mbar_init(sm.full + s, TMA ? 1 : kLoaderWarps); mbar_init(sm.empty + s, TMA ? kConvPerStage : 1); }
+            for (int s = 0; s < stages; ++s) { mbar_init(sm.full + s, TMA ? 1 : kLoaderWarps); mbar_init(sm.empty + s, TMA ? convPerStage : 1); }
             // CTA pairs: "operand ready" and "accumulator drained" collect both CTAs' arrivals in the leader
             for (int g = 0; g < kUmmaMaxGroups; ++g) { mbar_init(sm.accFull + g, 1); mbar_init(sm.accEmpty + g, CTA2 ? 8 : 4); }
-            for (int i = 0; i < kASlotsMax; ++i) { mbar_init(sm.cpDone + i, TMA ? (CTA2 ? 2 : 1) * kConvPerStage : 1); mbar_init(sm.slotFree + i, TMA ? kIssuersTma : kIssuers); }
+            for (int i = 0; i < kASlotsMax; ++i) { mbar_init(sm.cpDone + i, TMA ? (CTA2 ? 2 : 1) * convPerStage : 1); mbar_init(sm.slotFree + i, TMA ? kIssuersTma : kIssuers); }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         if (warp == 4) {
@@ -562,7 +686,8 @@ umma_fir_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix
         FA.nStages = nStages; FA.stages = stages; FA.myTiles = myTiles;
         FA.ring = sm.ring; FA.full = sm.full; FA.empty = sm.empty; FA.aReady = sm.cpDone; FA.slotFree = sm.slotFree; FA.ovf = ovf;
         if (warp == 4) { if (lane == 0) producer_role(FA, TM); }
-        else converter_role(FA, tmem, warp, lane);
+        else if (teams) converter_role(FA, tmem, warp, lane);
+        else converter_role_split(FA, tmem, warp, lane);
     } else if (!TMA && warp >= kFirstLoader) {
         // =========================================================== loaders
         LoaderArgs LA;
