@@ -138,7 +138,9 @@ def test_tail_scan_matches(ctx, O, mode):
     x = (0.5 * np.sin(2 * np.pi * 1000 * t) * np.exp(-t * 6.0)).astype(np.float32)
     x = np.stack([x, x * 0.7]).astype(np.float32)
     x += (rng.standard_normal(x.shape) * 10 ** (-96 / 20)).astype(np.float32)
-    for (win, hop, req, start) in ((4410, 2205, 3, 0), (2048, 256, 4, 30000), (2048, 1000, 2, 777), (4410, 2205, 3, n - 100)):
+    # window = 2, 8, 1 and 3 whole hops (per-hop partial sums), 9 hops and a non-multiple (windows summed directly)
+    for (win, hop, req, start) in ((4410, 2205, 3, 0), (2048, 256, 4, 30000), (2048, 1000, 2, 777), (4410, 2205, 3, n - 100),
+                                   (1024, 1024, 2, 5), (3072, 1024, 3, 100), (2304, 256, 2, 40000)):
         for has_nf, nf, mg in ((True, -93.0, -3.0), (True, -96.0, 10.0), (False, 0.0, 10.0)):
             gs, gf = ctx.tail_scan(x, start, win, hop, req, mode, has_nf, nf, mg)
             cs, cf = O.tail_scan(x, start, win, hop, req, mode, has_nf, nf, mg)
