@@ -46,21 +46,14 @@ int validate(const f9_job& j, const f9_job_ext& x) {
     return F9_OK;
 }
 
-// A chunk whose work has been enqueued on its slot's stream; harvest() waits for it and copies the scalar results out.
-struct PendingChunk { bool active = false; std::vector<int> idx; std::vector<int> tailJobs; long long* h_stop = nullptr; };
+// A chunk whose work has been enqueued on its slot's stream; its scalar results are copied out once the streams have been waited for.
+struct PendingChunk { std::vector<int> idx; std::vector<int> tailJobs; long long* h_stop = nullptr; };
 
-int harvest(f9_context* ctx, f9_result* results, PendingChunk* pc) {
-    if (!pc->active) return F9_OK;
-    pc->active = false;
-    F9_FINISH(ctx);
-    for (size_t i = 0; i < pc->tailJobs.size(); ++i) results[pc->idx[(size_t) pc->tailJobs[i]]].tail_stop_frame = pc->h_stop[i];
-    return F9_OK;
-}
-
-// Enqueue one chunk on the context's current slot (arena + stream); does not wait.
-int run_chunk(f9_context* ctx, const f9_job* jobs, f9_result* results, const std::vector<int>& idx, std::vector<JobPlan>& plans, PendingChunk* pc) {
+// Arena bytes of one chunk: device (reused by the slot's next chunk, in stream order) and pinned host staging (descriptor arrays
+// and scalar results: NOT reused inside a call, the copies that read or write them may still be queued).
+void chunk_bytes(const f9_job* jobs, const std::vector<int>& idx, const std::vector<JobPlan>& plans, size_t* d_out, size_t* h_out, int* maxPollsOut, int* nTailOut) {
     const int n = (int) idx.size();
-    size_t d_bytes = 1 << 20, h_bytes = 1 << 20;
+    size_t d_bytes = 1 << 20, h_bytes = 16 << 10;
     int maxPolls = 0, nTail = 0;
     for (int t = 0; t < n; ++t) {
         d_bytes += plans[(size_t) t].bytes;
@@ -72,7 +65,15 @@ int run_chunk(f9_context* ctx, const f9_job* jobs, f9_result* results, const std
     d_bytes += (size_t) n * widest * sizeof(double) * kDcPartials;       // DC partial sums: files x widest channel count
     d_bytes += totalCh * 1024 + d_bytes / 64;                  // per-tile records of the tensor-core resampler (64 B per >= 24 KB of output)
     h_bytes += (size_t) n * 2048 + (size_t) nTail * 16 + totalCh * 256;
-    int rc = ctx->arena_reserve(d_bytes, h_bytes); if (rc) return rc;
+    *d_out = d_bytes; *h_out = h_bytes; *maxPollsOut = maxPolls; *nTailOut = nTail;
+}
+
+// Enqueue one chunk on the context's current slot (arena + stream); does not wait.  The caller has reserved the arenas.
+int run_chunk(f9_context* ctx, const f9_job* jobs, const std::vector<int>& idx, std::vector<JobPlan>& plans, PendingChunk* pc) {
+    const int n = (int) idx.size();
+    size_t d_bytes = 0, h_bytes = 0;
+    int maxPolls = 0, nTail = 0, rc = F9_OK;
+    chunk_bytes(jobs, idx, plans, &d_bytes, &h_bytes, &maxPolls, &nTail);
     cudaStream_t s = ctx->stream;
 
     // ---- upload captures, carve outputs ----
@@ -265,8 +266,7 @@ int run_chunk(f9_context* ctx, const f9_job* jobs, f9_result* results, const std
             for (int c = 0; c < J.numCh; ++c)
                 F9_TRY_CUDA(ctx, cudaMemcpyAsync(J.out[c], P.out.base + c * P.out.chStride, sizeof(float) * (size_t) P.out_frames, cudaMemcpyDeviceToHost, s));
     }
-    pc->active = true; pc->idx = idx; pc->tailJobs = tailJobs; pc->h_stop = h_stop;
-    (void) results;
+    pc->idx = idx; pc->tailJobs = tailJobs; pc->h_stop = h_stop;
     return F9_OK;
 }
 
@@ -282,12 +282,15 @@ int f9_process_batch_ext(f9_context* ctx, const f9_job* jobs, const f9_job_ext* 
     F9_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
     size_t freeB = 0, totalB = 0;
     F9_TRY_CUDA(ctx, cudaMemGetInfo(&freeB, &totalB));
-    // Chunks are pipelined over two slots: while chunk k's kernels and downloads run on one stream, chunk k+1 uploads on
-    // the other (PCIe is full duplex and the copy engines are independent), so a large batch costs about
-    // max(upload, download) instead of their sum.  Chunk size in device memory (option F9_BATCH_CHUNK_MB overrides), measured on
-    // B200 / PCIe 5 with config 2's 256 files (tools/e2e_probe.py): float planes up and down 64 MB (44.6 ms; 53.6 ms at 256 MB),
-    // file bytes up 256 MB (33.8 ms with the 24-bit payload down; 42.6 ms at 64 MB): a chunk costs a synchronisation and a
-    // pipeline bubble of its own upload + download, which the smaller payload of the byte form amortises later.
+    // Chunks are pipelined over two slots (arena + stream each): while chunk k's kernels and downloads run on one stream, chunk
+    // k+1 uploads on the other (PCIe is full duplex and the copy engines are independent), so a large batch costs about
+    // max(upload, download) instead of their sum.  The whole call is ENQUEUED without waiting for anything: chunk k+2 reuses the
+    // device arena of chunk k behind it on the same stream (stream order is the only ordering the device arena needs), the pinned
+    // staging of descriptors and scalar results is not reused inside a call, and the host waits once, at the end.  With a wait per
+    // chunk (the first version) every chunk exposed the pipeline to the host thread's wake-up latency: on a shared host a step of
+    // config 2 took anything from 33 to 107 ms (tools/e2e_numa_probe.sh), and smaller chunks made it worse.
+    // Chunk size in device memory (option F9_BATCH_CHUNK_MB overrides), measured on B200 / PCIe 5 with config 2's 256 files
+    // (tools/e2e_probe.py): float planes up and down 64 MB, file bytes up 256 MB.
     bool anyFloatIn = false;
     for (int i = 0; i < n_jobs; ++i) anyFloatIn = anyFloatIn || !jobs[i].src_pcm;
     const size_t chunkMB = (size_t) std::max(1, ctx->diag.get("F9_BATCH_CHUNK_MB", anyFloatIn ? 64 : 256));
@@ -303,19 +306,14 @@ int f9_process_batch_ext(f9_context* ctx, const f9_job* jobs, const f9_job_ext* 
         cudaEventRecord(ev, ctx->stream); cudaStreamWaitEvent(ctx->alt_stream, ev, 0); cudaEventDestroy(ev);
     }
 
+    struct Chunk { std::vector<int> idx; std::vector<JobPlan> plans; };
+    std::vector<Chunk> chunks;
     std::vector<int> idx; std::vector<JobPlan> plans; size_t used = 0;
-    PendingChunk pending[2];
-    int nChunks = 0, worstAsync = F9_OK;
-    auto flush = [&]() -> int {
-        if (idx.empty()) return F9_OK;
-        if (nChunks > 0) ctx->swap_slot();                     // alternate slots; the first chunk uses slot 0
-        int rc = harvest(ctx, results, &pending[ctx->cur_slot]);       // the chunk that used this slot two flushes ago
-        if (rc) worstAsync = rc;
-        rc = run_chunk(ctx, jobs, results, idx, plans, &pending[ctx->cur_slot]);
-        if (rc) for (int i : idx) results[i].status = rc;
-        ++nChunks;
+    auto flush = [&]() {
+        if (idx.empty()) return;
+        chunks.push_back(Chunk{});
+        chunks.back().idx.swap(idx); chunks.back().plans.swap(plans);
         idx.clear(); plans.clear(); used = 0;
-        return rc;
     };
     int worst = F9_OK;
     for (int i = 0; i < n_jobs; ++i) {
@@ -347,15 +345,47 @@ int f9_process_batch_ext(f9_context* ctx, const f9_job* jobs, const f9_job_ext* 
                   + (J.src_pcm ? (size_t) J.captured_frames * J.src_ch * pcm_bps(J.src_fmt) + 512 : 0);
         R.latency_frames = P.latency_frames; R.trim_start = P.start; R.frames_copied = P.copied;
         R.out_frames = P.out_frames; R.tail_polls = P.polls;
-        if (used + P.bytes > budget && !idx.empty()) { int rc = flush(); if (rc) worst = rc; }
+        if (used + P.bytes > budget && !idx.empty()) flush();
         idx.push_back(i); plans.push_back(P); used += P.bytes;
     }
-    int rc = flush(); if (rc) worst = rc;
-    for (int k = 0; k < 2; ++k) {                              // drain both slots, leave slot 0 current
-        rc = harvest(ctx, results, &pending[ctx->cur_slot]); if (rc) worst = rc;
+    flush();
+    // Reserve per slot: the largest of its chunks in device memory, the sum of its chunks in pinned staging (waits for whatever
+    // the slot's stream still has from an earlier asynchronous call, then resets the arenas).
+    for (int slot = 0; slot < 2; ++slot) {
+        size_t dMax = 0, hSum = 0;
+        for (size_t k = (size_t) slot; k < chunks.size(); k += 2) {
+            size_t d = 0, h = 0; int mp = 0, nt = 0;
+            chunk_bytes(jobs, chunks[k].idx, chunks[k].plans, &d, &h, &mp, &nt);
+            dMax = std::max(dMax, d); hSum += h;
+        }
+        int rc = (chunks.size() > (size_t) slot) ? ctx->arena_reserve(dMax, hSum) : F9_OK;
+        if (rc) {
+            for (size_t k = 0; k < chunks.size(); ++k) for (int i : chunks[k].idx) results[i].status = rc;
+            if (ctx->cur_slot) ctx->swap_slot();
+            return rc;
+        }
+        ctx->swap_slot();
+    }
+    std::vector<PendingChunk> pending(chunks.size());
+    std::vector<char> enqueued(chunks.size(), 0);
+    for (size_t k = 0; k < chunks.size(); ++k) {
+        if ((int) (k & 1) != ctx->cur_slot) ctx->swap_slot();
+        ctx->d_used = 0;                                       // behind the slot's previous chunk in stream order
+        const int rc = run_chunk(ctx, jobs, chunks[k].idx, chunks[k].plans, &pending[k]);
+        if (rc) { worst = rc; for (int i : chunks[k].idx) results[i].status = rc; }
+        else enqueued[k] = 1;
+    }
+    for (int k = 0; k < 2; ++k) {                              // the one wait of the call: both streams
+        const cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { worst = ctx->fail_cuda(e, "cudaStreamSynchronize"); for (auto& c : chunks) for (int i : c.idx) results[i].status = worst; }
+        ctx->quiescent = true;
         ctx->swap_slot();
     }
     if (ctx->cur_slot) ctx->swap_slot();
-    if (worstAsync) worst = worstAsync;
+    if (worst != F9_ERR_CUDA)
+        for (size_t k = 0; k < chunks.size(); ++k)
+            if (enqueued[k])
+                for (size_t i = 0; i < pending[k].tailJobs.size(); ++i)
+                    results[pending[k].idx[(size_t) pending[k].tailJobs[i]]].tail_stop_frame = pending[k].h_stop[i];
     return worst;
 }

@@ -139,19 +139,32 @@ __device__ __forceinline__ bool rms_order_dependent(double s, long long count) {
 }
 // Terms of the buffer that can be rounded when added to a partial sum < 4 * 2^ilogb(s): float squares with bits below the ulp of
 // the binade above s.  Called by all threads of a CTA; returns this thread's count.  Integer arithmetic on the float's bits.
+__device__ __forceinline__ int small_term(float v, int Eb) {
+    const unsigned pb = __float_as_uint(__fmul_rn(v, v));
+    const int ep = (int) (pb >> 23);
+    const unsigned mp = ep ? ((pb & 0x7fffffu) | 0x800000u) : (pb & 0x7fffffu);
+    const int shf = (ep ? ep : 1) - 150 - (Eb - 1075);                              // p / grid = mp * 2^shf
+    return (mp != 0u && shf < 0 && (-shf >= 32 || (mp & ((1u << -shf) - 1u)) != 0u)) ? 1 : 0;
+}
 __device__ __forceinline__ long long count_small_terms(const DevBuf& B, double s) {
     const int Eb = (int) (((unsigned long long) __double_as_longlong(s)) >> 52) + 1;       // biased exponent of the binade above s
-    long long small = 0;
+    int small = 0;                                               // per thread: < 2^31 terms
     for (int c = 0; c < B.numCh; ++c) {
+        // one CTA reads a whole channel: 128-bit loads, four of them in flight per thread (scalar loads one at a time made this
+        // pass, not the ordered sum behind it, the longest part of a flagged buffer)
         const float* __restrict__ x = B.base + (long long) c * B.chStride;
-        for (int k = threadIdx.x; k < B.numFrames; k += blockDim.x) {
-            const float v = __ldg(x + k);
-            const unsigned pb = __float_as_uint(__fmul_rn(v, v));
-            const int ep = (int) (pb >> 23);
-            const unsigned mp = ep ? ((pb & 0x7fffffu) | 0x800000u) : (pb & 0x7fffffu);
-            const int shf = (ep ? ep : 1) - 150 - (Eb - 1075);                              // p / grid = mp * 2^shf
-            if (mp != 0u && shf < 0) small += (-shf >= 32 || (mp & ((1u << -shf) - 1u)) != 0u) ? 1 : 0;
+        const int mis = (int) ((reinterpret_cast<uintptr_t>(x) >> 2) & 3);
+        const int head = min(B.numFrames, (4 - mis) & 3);
+        if ((int) threadIdx.x < head) small += small_term(__ldg(x + threadIdx.x), Eb);
+        const int nvec = (B.numFrames - head) >> 2;
+        const float4* __restrict__ xv = reinterpret_cast<const float4*>(x + head);
+        #pragma unroll 4
+        for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+            const float4 v = __ldg(xv + i);
+            small += small_term(v.x, Eb) + small_term(v.y, Eb) + small_term(v.z, Eb) + small_term(v.w, Eb);
         }
+        const int tail0 = head + 4 * nvec;
+        if (tail0 + (int) threadIdx.x < B.numFrames) small += small_term(__ldg(x + tail0 + threadIdx.x), Eb);
     }
     return small;
 }
@@ -172,28 +185,47 @@ __device__ __forceinline__ IncPair inc_compose(IncPair a, IncPair c) {         /
     r.o = a.o + (((1 + a.o) & 1) ? c.o : c.e);
     return r;
 }
-constexpr int kSeqWarps = 8, kSeqPer = 8, kSeqBlock = 32 * kSeqPer;      // the final kernels run 256 threads
-struct SeqShared { IncPair pair[kSeqWarps]; int ok[kSeqWarps]; unsigned long long sb; };
+constexpr int kSeqWarps = 8, kSeqPer = 32, kSeqBlock = 32 * kSeqPer;     // the final kernels run 256 threads; a round is 8192 terms
+struct SeqShared { IncPair pair[kSeqWarps]; int ok[kSeqWarps]; unsigned long long sb; int consumed; };
+// The kSeqPer terms of one lane, channel-major (the reference's scan order), squared in float (:995); zeros past the end.
+// All loads are issued before the first use and without a branch between them: a guarded load per term put every load in its own
+// basic block, each waiting for the one before it (a round cost one memory latency PER TERM: 3.8 us for 8 terms).
+__device__ __forceinline__ void seq_load_terms(const DevBuf& B, long long idx0, long long total, float (&pf)[kSeqPer]) {
+    long long c = idx0 < total ? idx0 / B.numFrames : 0;
+    long long off = idx0 < total ? idx0 - c * B.numFrames : 0;
+    float v[kSeqPer];
+    #pragma unroll
+    for (int j = 0; j < kSeqPer; ++j) {
+        const bool valid = idx0 + j < total;
+        const float* ptr = B.base + (valid ? c * B.chStride + off : 0);        // past the end: any address of the buffer
+        asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v[j]) : "l"(ptr));
+        const bool wrap = off + 1 == B.numFrames;
+        off = wrap ? 0 : off + 1;
+        c += wrap ? 1 : 0;
+    }
+    #pragma unroll
+    for (int j = 0; j < kSeqPer; ++j) pf[j] = (idx0 + j < total) ? __fmul_rn(v[j], v[j]) : 0.0f;
+}
 // Call with all kSeqWarps * 32 threads of the CTA; every thread returns the sum.
+// A round covers kSeqWarps blocks of kSeqBlock terms (32 per lane: the scan, the barriers and the in-order application are per round).  The loads of the next round are issued before this round's arithmetic (the round
+// almost always advances by all its blocks; a round that stops early reloads), and a block that leaves the binade is cut at the
+// LANE whose terms cross it: the lanes before it are applied as integers, that lane's terms take real double additions, and
+// the next round starts right behind them on the new grid (the first version walked the whole block and waited for every round's
+// loads: 0.66 ms per 5 s stereo capture, a third of it in the ~60 crossings).
 __device__ __noinline__ double sum_squares_in_reference_order(const DevBuf& B, SeqShared& sh) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long total = (long long) B.numCh * B.numFrames;
+    const long long mineOff = (long long) warp * kSeqBlock + (long long) lane * kSeqPer;
     unsigned long long sb = 0ull;                                // bits of the running sum s (a non-negative double)
-    long long b0 = 0;
+    long long b0 = 0, bNext = -1;                                // start of this round; start the prefetched terms belong to
+    float pf[kSeqPer], nf[kSeqPer];
     while (b0 < total) {
-        // this warp's block of the round: terms in channel-major order (the reference's scan order), squared in float (:995)
-        const long long idx0 = b0 + (long long) warp * kSeqBlock + (long long) lane * kSeqPer;
-        float pf[kSeqPer];
-        {
-            long long c = idx0 < total ? idx0 / B.numFrames : 0;
-            long long off = idx0 - c * B.numFrames;
+        if (bNext == b0) {
             #pragma unroll
-            for (int j = 0; j < kSeqPer; ++j) {
-                const float v = (idx0 + j < total) ? __ldg(B.base + c * B.chStride + off) : 0.0f;
-                pf[j] = __fmul_rn(v, v);
-                if (++off == B.numFrames) { off = 0; ++c; }
-            }
-        }
+            for (int j = 0; j < kSeqPer; ++j) pf[j] = nf[j];
+        } else seq_load_terms(B, b0 + mineOff, total, pf);
+        bNext = b0 + (long long) kSeqWarps * kSeqBlock;
+        if (bNext < total) seq_load_terms(B, bNext + mineOff, total, nf);      // in flight during the round
         const int Eb = (int) (sb >> 52);                          // biased exponent of s
         bool ok = Eb >= 64 && Eb < 2046;                          // s normal and its grid a normal double too
         IncPair mine{0, 0};
@@ -240,24 +272,43 @@ __device__ __noinline__ double sum_squares_in_reference_order(const DevBuf& B, S
         }
         if (done > 0) sb = ((unsigned long long) Eb << 52) | ((unsigned long long) M & 0x000fffffffffffffull);
         const bool crossing = done < kSeqWarps && b0 + (long long) done * kSeqBlock < total;
+        int consumed = 0;
         if (crossing) {
-            // block `done` leaves the binade (or s is still zero / subnormal, or a term is not finite): the plain chain over its 256
-            // terms.  Warp `done` still holds them; it walks the chain (every lane the same s) and publishes the result.
+            // Block `done` leaves the binade (or s is still zero / subnormal, or a term is not finite).  Warp `done` still holds its
+            // terms and its lanes' inclusive prefixes (`mine`), all on the old grid.
             if (warp == done) {
-                double s = __longlong_as_double((long long) sb);
-                #pragma unroll 1
-                for (int l = 0; l < 32; ++l) {
+                double s; int took;
+                if (ok) {
+                    // M after lane l's terms; the sum is monotone, so the first lane at or above 2^53 is the one whose terms cross
+                    const long long Ml = M + ((M & 1) ? mine.o : mine.e);
+                    const int L = __ffs((int) __ballot_sync(0xffffffffu, Ml >= (1LL << 53))) - 1;     // the block's total is >= 2^53: L >= 0
+                    long long Mprev = __shfl_up_sync(0xffffffffu, Ml, 1);
+                    if (lane == 0) Mprev = M;
+                    const long long Mstart = __shfl_sync(0xffffffffu, Mprev, L);                      // < 2^53: exact state in front of lane L
+                    s = __longlong_as_double((long long) (((unsigned long long) Eb << 52) | ((unsigned long long) Mstart & 0x000fffffffffffffull)));
                     #pragma unroll
-                    for (int j = 0; j < kSeqPer; ++j) s = __dadd_rn(s, (double) __shfl_sync(0xffffffffu, pf[j], l));
+                    for (int j = 0; j < kSeqPer; ++j) s = __dadd_rn(s, (double) __shfl_sync(0xffffffffu, pf[j], L));
+                    took = (L + 1) * kSeqPer;
+                } else {
+                    // the plain chain over the block's terms (every lane the same s)
+                    s = __longlong_as_double((long long) sb);
+                    bool zeros = true;                            // leading digital silence: s + 0 = s, nothing to walk
+                    #pragma unroll
+                    for (int j = 0; j < kSeqPer; ++j) zeros = zeros && pf[j] == 0.0f;
+                    #pragma unroll 1
+                    for (int l = 0; l < (__all_sync(0xffffffffu, zeros) ? 0 : 32); ++l) {
+                        #pragma unroll
+                        for (int j = 0; j < kSeqPer; ++j) s = __dadd_rn(s, (double) __shfl_sync(0xffffffffu, pf[j], l));
+                    }
+                    took = kSeqBlock;
                 }
-                if (lane == 0) sh.sb = (unsigned long long) __double_as_longlong(s);
+                if (lane == 0) { sh.sb = (unsigned long long) __double_as_longlong(s); sh.consumed = took; }
             }
             __syncthreads();
-            sb = sh.sb;
-            ++done;
+            sb = sh.sb; consumed = sh.consumed;
         }
         __syncthreads();                                          // sh.pair / sh.ok / sh.sb are rewritten by the next round
-        b0 += (long long) done * kSeqBlock;
+        b0 += (long long) done * kSeqBlock + consumed;
     }
     return __longlong_as_double((long long) sb);
 }

@@ -62,6 +62,17 @@ constexpr int kSpin = 1 << 22;
 constexpr int kSpin = 1 << 26;
 #endif
 //                   // bounded waits: a protocol bug must not hang the GPU
+// -DF9_DIAG builds: event trace of the TMA-fed kernel's roles (F9_UMMA_TRACE=k traces launch k): per warp of CTAs 0 and 1 a list of
+// (event, index, clock) for the tiles kTrTile0 .. kTrTile1 - 1 of the CTA, dumped by launch_umma (tools/umma_trace.py reads it).
+constexpr int kTrCap = 1024, kTrTile0 = 6, kTrTile1 = 10, kTrWarps = 18;
+#ifdef F9_DIAG
+#define TR_INIT(prof, warp) long long* trBuf = ((prof) && blockIdx.x < 2) ? (prof) + ((size_t) blockIdx.x * kTrWarps + (warp)) * kTrCap : nullptr; int trN = 0
+#define TR_EV(t, ev, idx) do { if (trBuf && (t) >= kTrTile0 && (t) < kTrTile1 && trN < kTrCap) \
+    trBuf[trN++] = ((long long) (ev) << 56) | ((long long) ((idx) & 0xffff) << 40) | (clock64() & 0xffffffffffll); } while (0)
+#else
+#define TR_INIT(prof, warp) do {} while (0)
+#define TR_EV(t, ev, idx) do {} while (0)
+#endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -357,7 +368,7 @@ __device__ __forceinline__ int4 ld_rec_tail(const UmmaTileRec* r) { return __ldg
 
 struct FeedArgs {
     const UmmaTileRec* recs; int p, nStages, stages, myTiles, aCol, aMask, aShift; bool pair;
-    uint8_t* ring; uint64_t *full, *empty, *aReady, *slotFree; unsigned* ovf;
+    uint8_t* ring; uint64_t *full, *empty, *aReady, *slotFree; unsigned* ovf; long long* prof; int dbg;
 };
 __device__ __forceinline__ void producer_role(const FeedArgs& A, const UmmaTma& TM) {
     int sIdx = 0; uint32_t sPh = 0;
@@ -366,6 +377,7 @@ __device__ __forceinline__ void producer_role(const FeedArgs& A, const UmmaTma& 
     const uint32_t pfChunk = (tileBytes / (uint32_t) A.nStages + 15u) & ~15u;
     const UmmaTileRec* rec = A.recs + blockIdx.x;
     int4 cur = A.myTiles > 0 ? ld_rec_tail(rec) : make_int4(0, -1, 0, 0);
+    TR_INIT(A.prof, 4);
     for (int t = 0; t < A.myTiles; ++t, rec += gridDim.x) {
         // the next tile: its record (x0, mapIdx) for the next iteration and its input range for the L2 prefetch
         int4 nxt = make_int4(0, -1, 0, 0); const char* pf = nullptr;
@@ -374,6 +386,15 @@ __device__ __forceinline__ void producer_role(const FeedArgs& A, const UmmaTma& 
             nxt = ld_rec_tail(nr);
             if (nxt.y >= 0) pf = reinterpret_cast<const char*>(ldg_ptr(&nr->in) + __ldg(&nr->l00));
         }
+#ifdef F9_DIAG
+        if (A.dbg & 8) pf = nullptr;                           // no L2 prefetch
+        if ((A.dbg & 16) && t + 2 < A.myTiles) {               // prefetch two tiles ahead
+            const UmmaTileRec* nr = rec + 2 * gridDim.x;
+            pf = ld_rec_tail(nr).y >= 0 ? reinterpret_cast<const char*>(ldg_ptr(&nr->in) + __ldg(&nr->l00)) : nullptr;
+        }
+        if ((A.dbg & 64) && cur.y >= 0) cur.x -= (int) (((TM.base0 >> 2) + (unsigned long long) cur.x) & 31ull);     // rows on 128-byte lines (shifted data)
+        if (A.dbg & 32) { const int4 f = ld_rec_tail(A.recs + blockIdx.x); if (f.y >= 0 && cur.y >= 0) { cur.x = f.x; cur.y = f.y; } }   // every tile re-reads the CTA's first tile: L2 hits only
+#endif
         if (cur.y < 0) {
             // a tile read with guarded loads: its stages still take their ring positions (see converter_role), without a box
             for (int st = 0; st < A.nStages; ++st) {
@@ -386,6 +407,10 @@ __device__ __forceinline__ void producer_role(const FeedArgs& A, const UmmaTma& 
             const CUtensorMap* map = &TM.maps[cur.y];
             for (int st = 0; st < A.nStages; ++st) {
                 mbar_wait_parked(A.empty + sIdx, sPh ^ 1, kParkNs);
+                TR_EV(t, 1, st);
+#ifdef F9_DIAG
+                if (A.dbg & 128) { mbar_arrive(A.full + sIdx); if (++sIdx == A.stages) { sIdx = 0; sPh ^= 1; } continue; }   // no box: the converters read stale shared memory
+#endif
                 mbar_expect_tx(A.full + sIdx, (uint32_t) kTmaStageBytes);
                 tma_load_2d(ring0 + (uint32_t) (sIdx * kTmaStageBytes), map, cur.x + st * 32, 0, A.full + sIdx);
                 if (pf) l2_prefetch(pf + (size_t) st * pfChunk, pfChunk);
@@ -519,6 +544,7 @@ __device__ __forceinline__ void converter_role(const FeedArgs& A, uint32_t tmem,
         const int4 tail = ld_rec_tail(r); T.viaTma = tail.y >= 0; T.mask = tail.z != 0; return T;
     };
     const UmmaTileRec* rec = A.recs + blockIdx.x;
+    TR_INIT(lane == 0 ? A.prof : nullptr, warp);
     TileIn T = {nullptr, 0, 0, false, false}, N = T;
     if (A.myTiles > 0) N = load_rec(rec);
     for (int t = 0; t < A.myTiles; ++t, rec += gridDim.x) {
@@ -534,8 +560,15 @@ __device__ __forceinline__ void converter_role(const FeedArgs& A, uint32_t tmem,
             // position's "full" phase without a box).  The ring depth is even, so a ring position -- its full / empty barriers --
             // always belongs to the same team, which therefore sees every phase of them: a parity wait only tells the current
             // phase from the one before it, and a warp that saw every other phase could take a box still in flight for landed.
-            mbar_wait_parked(A.full + sIdx, sPh, kParkNs);
+            mbar_wait(A.full + sIdx, sPh);                     // plain polls here and on the slot: -2.5 % against parked waits (the teams are
+            TR_EV(t, 10, st);                                  // the pair's pace-setters; the other roles keep their suspend hints)
             float4 v[8];
+#ifdef F9_DIAG
+            if (A.dbg & 256) {                                 // no LDS: constant samples
+                #pragma unroll
+                for (int c = 0; c < 8; ++c) v[c] = make_float4(0.25f, 0.25f, 0.25f, 0.25f);
+            } else
+#endif
             if (T.viaTma) {
                 const uint32_t a = ringRow + (uint32_t) (sIdx * kTmaStageBytes);
                 #pragma unroll
@@ -588,10 +621,12 @@ __device__ __forceinline__ void converter_role(const FeedArgs& A, uint32_t tmem,
                 w[base + 8] = *reinterpret_cast<const uint32_t*>(&t01); w[base + 9] = *reinterpret_cast<const uint32_t*>(&t23);
             }
             __syncwarp();                                      // the stage's rows are in registers: the ring position may be refilled
+            TR_EV(t, 11, st);
             if (lane == 0) mbar_arrive(A.empty + sIdx);
             if (++sIdx == A.stages) { sIdx = 0; sPh ^= 1; }
-            if (gs > aMask) mbar_wait_parked(A.slotFree + (gs & aMask), (uint32_t) (((gs >> aShift) - 1) & 1), kParkNs);   // the MMAs of the slot's previous stage are done
+            if (gs > aMask) mbar_wait(A.slotFree + (gs & aMask), (uint32_t) (((gs >> aShift) - 1) & 1));   // the MMAs of the slot's previous stage are done
             tc_fence_after();
+            TR_EV(t, 12, st);
             const uint32_t td = tdst + (uint32_t) ((gs & aMask) * 32);
             asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
                          :: "r"(td), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]), "r"(w[8]), "r"(w[9]), "r"(w[10]), "r"(w[11]),
@@ -600,7 +635,9 @@ __device__ __forceinline__ void converter_role(const FeedArgs& A, uint32_t tmem,
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
             __syncwarp();
+            TR_EV(t, 13, st);
             if (lane == 0) { if (A.pair) mbar_arrive_leader(A.aReady + (gs & aMask)); else mbar_arrive(A.aReady + (gs & aMask)); }
+            TR_EV(t, 14, st);
         }
     }
     // Samples outside the fp16 split's range are not looked for here: |128 x| >= 65520, Inf and NaN become an infinite or NaN head,
@@ -668,6 +705,10 @@ umma_fir_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix
         tc_fence_before();
         __syncthreads();
         if (CTA2) cluster_sync_all();                          // the peer's barriers and weights are ready before anything crosses over
+#ifdef F9_DIAG
+        if (TMA && prof && blockIdx.x < 2 && threadIdx.x == 0)  // both CTAs leave the cluster barrier together: offset between their clocks
+            prof[((size_t) blockIdx.x * kTrWarps + 4) * kTrCap + kTrCap - 1] = (0x7fll << 56) | (clock64() & 0xffffffffffll);
+#endif
         tc_fence_after();
     }
     const uint32_t tmem = *sm.tmemSlot;
@@ -684,7 +725,7 @@ umma_fir_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix
         FeedArgs FA;
         FA.recs = recs; FA.p = p; FA.aCol = aCol; FA.aMask = aMask; FA.aShift = aShift; FA.pair = CTA2;
         FA.nStages = nStages; FA.stages = stages; FA.myTiles = myTiles;
-        FA.ring = sm.ring; FA.full = sm.full; FA.empty = sm.empty; FA.aReady = sm.cpDone; FA.slotFree = sm.slotFree; FA.ovf = ovf;
+        FA.ring = sm.ring; FA.full = sm.full; FA.empty = sm.empty; FA.aReady = sm.cpDone; FA.slotFree = sm.slotFree; FA.ovf = ovf; FA.prof = prof; FA.dbg = dbg;
         if (warp == 4) { if (lane == 0) producer_role(FA, TM); }
         else if (teams) converter_role(FA, tmem, warp, lane);
         else converter_role_split(FA, tmem, warp, lane);
@@ -747,9 +788,9 @@ umma_fir_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix
         // (fetched an entry ahead) and one block of predicated tcgen05 instructions.  A single thread's instruction latency is
         // what bounds this role: ~100 instructions per entry (flag decoding, 64-bit descriptor arithmetic) cost ~360 clk.
         uint4* ops = sm.ops + (TMA ? BI.opStartT[w] : BI.opStart[w]);
-        const int nOps = TMA ? BI.opStartT[w + 1] - BI.opStartT[w] : BI.opStart[w + 1] - BI.opStart[w];
+        int nOps = TMA ? BI.opStartT[w + 1] - BI.opStartT[w] : BI.opStart[w + 1] - BI.opStart[w];
         const uint32_t wLo = (uint32_t) (wDesc0 & 0xffffffffull), wHi = (uint32_t) (wDesc0 >> 32);
-        enum : uint32_t { fA0 = 1, fA1 = 2, fM = 4, fDrain = 8, fPool = 16, fPrev = 32, fLast = 64, fH = 128 };
+        enum : uint32_t { fA0 = 1, fA1 = 2, fM = 4, fDrain = 8, fPool = 16, fPrev = 32, fLast = 64, fH = 128, fPair = 0x1000 };   // gl sits in bits 8-11
         for (int i = lane; i < nOps; i += 32) {
             const uint4 o = ops[i];
             const uint32_t d1c = o.x & 0xffffu, poolc = o.x >> 16, hh = (o.z >> 8) & 0xffu, gl = (o.z >> 16) & 0xffu, fl = o.z >> 24;
@@ -766,15 +807,43 @@ umma_fir_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix
                                 f | (gl << 8) | ((o.w & 0xffu) << 16) | ((o.z & 0xffu) << 24));
         }
         __syncwarp();
+        // CTA pairs: the two K steps of a stage that a group takes back to back become ONE record (six MMAs under one decode).
+        // The single issuing thread's instruction latency bounds this role and, through the operand ring, the kernel: an event
+        // trace of a -DF9_DIAG build (tools/umma_trace.py) showed ~500 clk per record against ~100 clk of tensor time, two records
+        // per warp and stage, and every other role waiting for it (with boxes, conversion, MMAs and stores all switched off the
+        // kernel took as long as with them).
+        const uint32_t tileUnits = CTA2 ? 2 * nb : 4 * nb;     // weight tile pitch in 16-byte units (tiles are stored group-major)
+        if (CTA2) {
+            int nNew = 0;
+            if (lane == 0) {
+                int i = 0;
+                while (i < nOps) {
+                    uint4 a = ops[i];
+                    if (i + 1 < nOps) {
+                        const uint4 b = ops[i + 1];
+                        const bool pair = !(a.w & fH) && (b.w & fH) && (a.w >> 24) == (b.w >> 24) && ((a.w >> 8) & 0xfu) == ((b.w >> 8) & 0xfu) &&
+                                          !(b.w & (fDrain | fPool)) && b.x == a.x && b.y == a.y && b.z == a.z + tileUnits &&
+                                          (b.w & fA0) && (b.w & fA1) && !(a.w & fLast);
+                        if (pair) { a.w |= fPair | (b.w & fLast); ops[nNew++] = a; i += 2; continue; }
+                    }
+                    ops[nNew++] = a; ++i;
+                }
+            }
+            nOps = __shfl_sync(0xffffffffu, nNew, 0);
+            __syncwarp();
+        }
+        const uint32_t go = (dbg & 1) ? 0u : 1u;
         const uint32_t w1Off = CTA2 ? nb / 2 : nb;             // the w1 rows of a tile, in 16-byte units
         const uint32_t accFull0 = smem_u32(sm.accFull);
         int gs = 0;
+        TR_INIT((TMA && el) ? prof : nullptr, warp);
         for (int t = 0; t < myTiles; ++t) {
             int k = 0;
             uint4 nx = nOps > 0 ? ops[0] : make_uint4(0, 0, 0, 0xff000000u);
             for (int st = 0; st < nStages; ++st, ++gs) {
                 { PROF_BEGIN(wq); if (CTA2) mbar_wait_cluster(sm.cpDone + (gs & aMask), (uint32_t) ((gs >> aShift) & 1), kParkNs); else if (TMA) mbar_wait_parked(sm.cpDone + (gs & aMask), (uint32_t) ((gs >> aShift) & 1), kParkNs); else mbar_wait(sm.cpDone + (gs & aMask), (uint32_t) ((gs >> aShift) & 1)); PROF_END(pW0, wq); }
                 tc_fence_after();
+                TR_EV(t, 20, st);
                 PROF_BEGIN(wi);
                 const uint32_t aSlot = tmem + (uint32_t) aCol + (uint32_t) ((gs & aMask) * 32);
                 while (k < nOps && (int) (nx.w >> 24) == st) {
@@ -782,31 +851,39 @@ umma_fir_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix
                     ++k;
                     nx = ops[k < nOps ? k : 0];
                     if (o.w & (fDrain | fPool)) {                               // rare: first K step of a group / first step past the split
-                        const uint32_t gl = (o.w >> 8) & 0xffu, waitGl = (o.w >> 16) & 0xffu;
+                        const uint32_t gl = (o.w >> 8) & 0xfu, waitGl = (o.w >> 16) & 0xffu;
                         uint64_t* bar = sm.accEmpty + ((o.w & fDrain) ? gl : waitGl);
                         const uint32_t par = ((o.w & fDrain) || (o.w & fPrev)) ? (uint32_t) ((t & 1) ^ 1) : (uint32_t) (t & 1);
+                        TR_EV(t, 22, st);
                         PROF_BEGIN(wd); if (CTA2) mbar_wait_cluster(bar, par, 200); else mbar_wait(bar, par); PROF_END(pW1, wd);
                         tc_fence_after();
+                        TR_EV(t, 23, st);
                     }
                     // x0 * w0 -> D0 (N = 2 NB over [D0 | D1] when merged), x0 * w1 -> D1 (unless merged), x1 * w0 -> D1, "group done"
                     // (issued under the elected lane's branch: a per-lane predicate on these warp-uniform instructions makes the
                     // compiler serialise them with an election loop)
-                    const uint32_t go = (dbg & 1) ? 0u : 1u;
                     const uint32_t aHi = aSlot + ((o.w & fH) ? 16u : 0u);
-                    const uint32_t lastBar = accFull0 + ((o.w >> 8) & 0xffu) * 8u;
+                    const uint32_t lastBar = accFull0 + ((o.w >> 8) & 0xfu) * 8u;
                     if (!el) continue;
                     if (CTA2)
-                        asm volatile("{\n\t.reg .pred pe, pa0, pa1, pl;\n\t.reg .b32 t;\n\t.reg .b64 b0, b1;\n\t"
+                        // K step h (or 0 of a pair): x0 w0 -> D0, x0 w1 -> D1, x1 w0 -> D1; a pair: the same for K step 1 (operand 16
+                        // columns up, the group's next weight tile), always accumulating; then "group done"
+                        asm volatile("{\n\t.reg .pred pe, pp, pa0, pa1, pl;\n\t.reg .b32 t;\n\t.reg .b64 b0, b1, b2, b3;\n\t"
                                      "setp.ne.b32 pe, %0, 0;\n\t"
                                      "and.b32 t, %1, 1;\n\tsetp.ne.b32 pa0, t, 0;\n\tand.b32 t, %1, 2;\n\tsetp.ne.b32 pa1, t, 0;\n\t"
-                                     "setp.ne.b32 pl, %10, 0;\n\tand.b32 t, %1, 64;\n\tsetp.ne.and.b32 pl, t, 0, pl;\n\t"
+                                     "and.b32 t, %1, 4096;\n\tsetp.ne.and.b32 pp, t, 0, pe;\n\t"
+                                     "and.b32 t, %1, 64;\n\tsetp.ne.b32 pl, t, 0;\n\t"
                                      "mov.b64 b0, {%2, %3};\n\tadd.u32 t, %2, %4;\n\tmov.b64 b1, {t, %3};\n\t"
+                                     "add.u32 t, %2, %10;\n\tmov.b64 b2, {t, %3};\n\tadd.u32 t, t, %4;\n\tmov.b64 b3, {t, %3};\n\t"
                                      "@pe tcgen05.mma.cta_group::2.kind::f16 [%5], [%7], b0, %9, pa0;\n\t"
                                      "@pe tcgen05.mma.cta_group::2.kind::f16 [%6], [%7], b1, %9, pa1;\n\t"
                                      "@pe tcgen05.mma.cta_group::2.kind::f16 [%6], [%8], b0, %9, 1;\n\t"
+                                     "@pp tcgen05.mma.cta_group::2.kind::f16 [%5], [%13], b2, %9, 1;\n\t"
+                                     "@pp tcgen05.mma.cta_group::2.kind::f16 [%6], [%13], b3, %9, 1;\n\t"
+                                     "@pp tcgen05.mma.cta_group::2.kind::f16 [%6], [%14], b2, %9, 1;\n\t"
                                      "@pl tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%11], %12;\n\t}"
                                      :: "r"(go), "r"(o.w), "r"(o.z), "r"(wHi), "r"(w1Off), "r"(o.x), "r"(o.y), "r"(aHi), "r"(aHi + 8u), "r"(idescN),
-                                        "r"(1u), "r"(lastBar), "h"((uint16_t) 3) : "memory");
+                                        "r"(tileUnits), "r"(lastBar), "h"((uint16_t) 3), "r"(aHi + 16u), "r"(aHi + 24u) : "memory");
                     else
                         asm volatile("{\n\t.reg .pred pe, pn, pa0, pa1, pm, pl;\n\t.reg .b32 t, id;\n\t.reg .b64 b0, b1;\n\t"
                                      "setp.ne.b32 pe, %0, 0;\n\t"
@@ -822,6 +899,7 @@ umma_fir_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix
                                         "r"(1u), "r"(lastBar), "r"(idesc2N) : "memory");
                 }
                 if (el) { if (CTA2) umma2_commit_both(sm.slotFree + (gs & aMask)); else umma_commit(sm.slotFree + (gs & aMask)); }   // arrives once this warp's MMAs on the slot have completed
+                TR_EV(t, 21, st);
                 __syncwarp();
                 PROF_END(pI, wi);
             }
@@ -850,6 +928,7 @@ umma_fir_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix
         };
         TileOut ON = {nullptr, 0, 0};
         if (myTiles > 0) ON = load_out(tileId);
+        TR_INIT((TMA && lane == 0) ? prof : nullptr, warp);
         float sticky = 0.0f;                                   // stays 0 while every output is finite: fma(v, 0, sticky) turns Inf / NaN into NaN
         for (int t = 0; t < myTiles; ++t, tileId += gridDim.x) {
             const TileOut S = ON;
@@ -861,6 +940,7 @@ umma_fir_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix
             for (int gl = 0; gl < BI.nGroups; ++gl) {
                 { PROF_BEGIN(w); mbar_wait_parked(sm.accFull + gl, t & 1, 2000); PROF_END(pW0, w); }
                 tc_fence_after();
+                TR_EV(t, 30, gl);
                 for (int h = 0; h < chunks; ++h) {
                     uint32_t v0[16], v1[16], vb[16];
                     const uint32_t c0 = tmem + laneBase + (uint32_t) (gl * 2 * NB + h * 16);
@@ -913,6 +993,7 @@ umma_fir_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix
                     __syncwarp();
                     PROF_END(pW2, wst);
                 }
+                TR_EV(t, 31, gl);
             }
         }
         if (TMA && !(sticky == 0.0f)) atomicOr(ovf, 1u);       // an input sample was outside the fp16 split's range (see converter_role)
@@ -1090,11 +1171,17 @@ cudaError_t launch_umma(const ResampleLaunch& L, cudaStream_t s, long long* laun
     const bool doProf = profEnv != nullptr && prof_calls++ == atoi(profEnv);
     if (doProf) { cudaMalloc((void**) &d_prof, sizeof(long long) * 16 * grid); cudaMemsetAsync(d_prof, 0, sizeof(long long) * 16 * grid, s); }
     const int dbg = getenv("F9_UMMA_DBG") ? atoi(getenv("F9_UMMA_DBG")) : 0;
+    static long long* d_trace = nullptr; static int trace_calls = 0;
+    const char* trEnv = getenv("F9_UMMA_TRACE");
+    const bool doTrace = trEnv != nullptr && L.um_tma && trace_calls++ == atoi(trEnv);
+    const size_t trWords = (size_t) 2 * kTrWarps * kTrCap;
+    if (doTrace) { cudaMalloc((void**) &d_trace, sizeof(long long) * trWords); cudaMemsetAsync(d_trace, 0, sizeof(long long) * trWords, s); }
 #else
+    long long* const d_trace = nullptr; const bool doTrace = false;
     long long* const d_prof = nullptr; const bool doProf = false; const int dbg = 0;
 #endif
     #define F9_UMMA_LAUNCH(MERGED, TMA) umma_fir_kernel<MERGED, TMA, false><<<grid, TMA ? kThreadsTma : kThreads, L.um_smem, s>>>(L.d_segs, L.d_tile_prefix, L.n_segs, L.n_tiles, \
-        L.um, L.um_maps, L.d_tile_recs, L.um_stages, L.um_aligned ? 1 : 0, L.d_ovf, doProf ? d_prof : nullptr, dbg)
+        L.um, L.um_maps, L.d_tile_recs, L.um_stages, L.um_aligned ? 1 : 0, L.d_ovf, doTrace ? d_trace : (doProf ? d_prof : nullptr), dbg)
     if (L.um_tma) {
         if (!L.d_tile_recs) return cudaErrorInvalidValue;
         if (!L.recs_ready) {
@@ -1114,7 +1201,7 @@ cudaError_t launch_umma(const ResampleLaunch& L, cudaStream_t s, long long* laun
                 fprintf(stderr, "[umma pairs] grid %d smem %zu stages %d max active clusters %d (%s)\n", grid, L.um_smem, L.um_stages, nc, cudaGetErrorString(qe));
             }
             e = cudaLaunchKernelEx(&cfg, umma_fir_kernel<false, true, true>, L.d_segs, L.d_tile_prefix, L.n_segs, L.n_tiles, L.um, L.um_maps,
-                                   (const UmmaTileRec*) L.d_tile_recs, L.um_stages, L.um_aligned ? 1 : 0, L.d_ovf, (long long*) nullptr, dbg);
+                                   (const UmmaTileRec*) L.d_tile_recs, L.um_stages, L.um_aligned ? 1 : 0, L.d_ovf, doTrace ? d_trace : (long long*) nullptr, dbg);
             if (e != cudaSuccess) return e;
         }
         else if (L.um.poolN == 0) F9_UMMA_LAUNCH(true, true); else F9_UMMA_LAUNCH(false, true);
@@ -1132,6 +1219,15 @@ cudaError_t launch_umma(const ResampleLaunch& L, cudaStream_t s, long long* laun
         fprintf(stderr, "[umma prof] tiles/CTA %.1f stages/tile %d | loader total %.0f wait-free %.0f | copy total %.0f wait-full %.0f wait-slot %.0f | epilogue total %.0f wait-done %.0f stores %.0f | copy: fence %.0f cp-issue %.0f | issuer0: wait-cp %.0f issue %.0f (wait-drained %.0f)\n",
                 (double) L.n_tiles / grid, L.um.blk[0].nStages, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[11], a[12]);
     }
+#ifdef F9_DIAG
+    if (doTrace) {
+        std::vector<long long> h(trWords);
+        cudaStreamSynchronize(s); cudaMemcpy(h.data(), d_trace, sizeof(long long) * trWords, cudaMemcpyDeviceToHost);
+        const char* path = getenv("F9_UMMA_TRACE_FILE");
+        if (FILE* f = fopen(path ? path : "umma_trace.bin", "wb")) { fwrite(h.data(), sizeof(long long), trWords, f); fclose(f); }
+        fprintf(stderr, "[umma trace] grid %d tiles %d stages/tile %d ring %d aSlots %d pairs %d\n", grid, L.n_tiles, L.um.blk[0].nStages, L.um_stages, L.um.aSlots, (int) pairs);
+    }
+#endif
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     ++*launches;
     umma_redo_kernel<<<std::min(L.n_tiles, 8 * L.sm_count), 256, 0, s>>>(L.d_segs, L.d_tile_prefix, L.n_segs, L.n_tiles, L.um.nGB, L.um.q,

@@ -11,6 +11,15 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+if os.environ.get("BIND"):          # run (and first-touch the pinned buffers) on the CPUs of GPU 0's NUMA node
+    import pynvml
+    pynvml.nvmlInit()
+    words = (os.cpu_count() + 63) // 64
+    mask = pynvml.nvmlDeviceGetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(0), words)
+    cpus = {64 * w + b for w in range(words) for b in range(64) if (mask[w] >> b) & 1} & os.sched_getaffinity(0)
+    print("bind: gpu0 cpus", sorted(cpus), "of", sorted(os.sched_getaffinity(0)), flush=True)
+    if cpus:
+        os.sched_setaffinity(0, cpus)
 import __graft_entry__ as g
 f9 = g._load_pkg()
 L = f9.lib()
@@ -47,16 +56,17 @@ def jobs_for(mode):
     return J, keep
 
 
-for mode in ("pp", "ff", "pf", "fp"):
+for mode in (os.environ.get("MODES", "pp,ff,pf,fp").split(",")):
     J, keep = jobs_for(mode)
     R = (f9.Result * files)()
-    for chunk in (16, 32, 64, 128, 256, 512):
+    for chunk in [int(c) for c in os.environ.get("CHUNKS", "16,32,64,128,256,512").split(",")]:
         ctx = f9.Context(0)
         ctx.set_option("F9_BATCH_CHUNK_MB", chunk)
         for _ in range(2):
             assert L.f9_process_batch(ctx.handle, J, files, R) == 0
         ts = []
-        for _ in range(4):
+        for _ in range(int(os.environ.get("REPS", "4"))):
             t = time.perf_counter(); assert L.f9_process_batch(ctx.handle, J, files, R) == 0; ts.append(1e3 * (time.perf_counter() - t))
-        print(f"in/out {mode} chunk {chunk:4d} MB: best {min(ts):7.2f} ms  mean {np.mean(ts):7.2f} ms   ({files * ch * n_out / min(ts) / 1e6:.2f} Gsamples/s)", flush=True)
+        print(f"in/out {mode} chunk {chunk:4d} MB: best {min(ts):7.2f} ms  mean {np.mean(ts):7.2f} ms   ({files * ch * n_out / min(ts) / 1e6:.2f} Gsamples/s)  each "
+              + " ".join(f"{t:.1f}" for t in ts), flush=True)
         ctx.close()

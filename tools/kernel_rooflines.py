@@ -68,6 +68,15 @@ def main():
     sumsq = torch.empty(n, dtype=torch.float64, device=dev); pk = torch.empty(n, dtype=torch.float32, device=dev)
     ms = timed(lambda: ctx._check(L.f9_dev_stats_batch(ctx.handle, bufs, n, sumsq.data_ptr(), pk.data_ptr())))
     report("stats_partial/final (calculateRMS / noise floor)", "config4: 512 x 2 x 240000", ms, 4.0 * n * ch * frames, n * ch * frames, "samples")
+    ctx.set_option("F9_RMS_TREE_SUM", 1)
+    ms = timed(lambda: ctx._check(L.f9_dev_stats_batch(ctx.handle, bufs, n, sumsq.data_ptr(), pk.data_ptr())))
+    report("stats_partial/final, option F9_RMS_TREE_SUM (the tree sum as it is: no order test)", "config4: 512 x 2 x 240000", ms, 4.0 * n * ch * frames, n * ch * frames, "samples")
+    ctx.clear_options()
+    ctx.set_option("F9_RMS_FORCE_ORDER", 1)
+    ms = timed(lambda: ctx._check(L.f9_dev_stats_batch(ctx.handle, bufs, n, sumsq.data_ptr(), pk.data_ptr())), reps=3)
+    report("stats_partial/final, option F9_RMS_FORCE_ORDER (EVERY buffer re-summed in the reference's order)", "config4: 512 x 2 x 240000", ms, 4.0 * n * ch * frames, n * ch * frames, "samples",
+           "one CTA per buffer: the cost of one ordered re-sum is this time / ceil(512 / resident CTAs)")
+    ctx.clear_options()
     ms = timed(lambda: ctx._check(L.f9_dev_latency_stats_batch(ctx.handle, bufs, n, 0.1, pos.data_ptr(), sumsq.data_ptr(), pk.data_ptr())))
     report("peak_partial<STATS>/final (findPeakPosition + calculateNoiseFloorDb, one read)", "config4: 512 x 2 x 240000", ms, 4.0 * n * ch * frames, n * ch * frames, "samples",
            "the latency measurement's two passes over a capture (MainComponent.cpp:270-279) as one")

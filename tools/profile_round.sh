@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-end measurement on the GPU box (run under gpurun): tests, bench (both arms), per-kernel rooflines, ncu launch list and
 # one --set full capture of each dominant kernel.  Everything lands in gpurun_out/<tag>_*.  Usage: tools/profile_round.sh <tag>
-tag=${1:-r01_v4}
+tag=${1:-r02}
 out=gpurun_out
 mkdir -p $out
 (time timeout 900 python -m pytest tests -m gpu -x -q) > $out/${tag}_tests.log 2>&1

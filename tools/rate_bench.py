@@ -3,9 +3,14 @@ sys.path.insert(0, "/root/repo")
 import torch
 import __graft_entry__ as g
 f9 = g._load_pkg()
+if os.environ.get("F9DSP_DIAG_LIB"):          # development: the -DF9_DIAG build (make -C f9-juce-resampler-studio_b200 DIAG=1)
+    f9.LIB_PATH = os.path.join(os.path.dirname(os.path.dirname(f9.LIB_PATH)), "lib_diag", "libf9dsp.so")
 dev = torch.device("cuda", 0)
 ctx = f9.Context(0); stream = torch.cuda.Stream(dev); torch.cuda.set_stream(stream); ctx.set_stream(stream.cuda_stream)
 L = f9.lib()
+for kv in os.environ.get("OPTS", "").split(","):          # e.g. OPTS=F9_UMMA_STAGES=4,F9_UMMA_NOCTA2=1
+    if kv:
+        ctx.set_option(kv.split("=")[0], int(kv.split("=")[1]) if "=" in kv else 1)
 gen = torch.Generator(device=dev); gen.manual_seed(1)
 def plan_time(kind, fs_in, fs_out, nch, n_in):
     x = torch.randn((nch, n_in), generator=gen, device=dev, dtype=torch.float32) * 0.25
