@@ -518,7 +518,7 @@ def run_gpu(args, rank: int, local_rank: int, world: int):
             if rc:
                 ctx._check(rc)
 
-        e2e_steps = max(2, min(args.steps, 5))
+        e2e_steps = max(2, min(args.steps, 10))
         for _ in range(3):
             e2e_step()
         barrier()

@@ -191,20 +191,20 @@ struct SeqShared { IncPair pair[kSeqWarps]; int ok[kSeqWarps]; unsigned long lon
 // All loads are issued before the first use and without a branch between them: a guarded load per term put every load in its own
 // basic block, each waiting for the one before it (a round cost one memory latency PER TERM: 3.8 us for 8 terms).
 __device__ __forceinline__ void seq_load_terms(const DevBuf& B, long long idx0, long long total, float (&pf)[kSeqPer]) {
-    long long c = idx0 < total ? idx0 / B.numFrames : 0;
-    long long off = idx0 < total ? idx0 - c * B.numFrames : 0;
+    int c = idx0 < total ? (int) (idx0 / B.numFrames) : 0;
+    int off = idx0 < total ? (int) (idx0 - (long long) c * B.numFrames) : 0;
+    const int left = (int) max(0LL, min((long long) kSeqPer, total - idx0));    // terms of this lane that exist
     float v[kSeqPer];
     #pragma unroll
     for (int j = 0; j < kSeqPer; ++j) {
-        const bool valid = idx0 + j < total;
-        const float* ptr = B.base + (valid ? c * B.chStride + off : 0);        // past the end: any address of the buffer
+        const float* ptr = B.base + (j < left ? (long long) c * B.chStride + off : 0LL);      // past the end: any address of the buffer
         asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v[j]) : "l"(ptr));
         const bool wrap = off + 1 == B.numFrames;
         off = wrap ? 0 : off + 1;
         c += wrap ? 1 : 0;
     }
     #pragma unroll
-    for (int j = 0; j < kSeqPer; ++j) pf[j] = (idx0 + j < total) ? __fmul_rn(v[j], v[j]) : 0.0f;
+    for (int j = 0; j < kSeqPer; ++j) pf[j] = j < left ? __fmul_rn(v[j], v[j]) : 0.0f;
 }
 // Call with all kSeqWarps * 32 threads of the CTA; every thread returns the sum.
 // A round covers kSeqWarps blocks of kSeqBlock terms (32 per lane: the scan, the barriers and the in-order application are per round).  The loads of the next round are issued before this round's arithmetic (the round
@@ -231,23 +231,19 @@ __device__ __noinline__ double sum_squares_in_reference_order(const DevBuf& B, S
         IncPair mine{0, 0};
         #pragma unroll
         for (int j = 0; j < kSeqPer; ++j) {
+            // p = mp * 2^(max(ep, 1) - 150);  grid g = 2^(Eb - 1075);  p / g = mp * 2^shf.  Branch-free (the lanes' exponents differ:
+            // the branchy form diverged at every term, ~300 instructions per term) and 32-bit except for the final shift.
             const unsigned pb = __float_as_uint(pf[j]);
-            const int ep = (int) (pb >> 23);                      // biased float exponent (0: zero or subnormal)
-            const long long mp = ep ? (long long) ((pb & 0x7fffffu) | 0x800000u) : (long long) (pb & 0x7fffffu);
-            // p = mp * 2^(max(ep, 1) - 150);  grid g = 2^(Eb - 1075);  p / g = mp * 2^sh
-            const int shf = (ep ? ep : 1) - 150 - (Eb - 1075);
-            IncPair e{0, 0};
-            if (ep == 255) ok = false;                            // Inf / NaN: the plain chain reproduces them
-            if (shf >= 0) {
-                if (shf > 29) ok = false;                         // the term alone reaches the next binade
-                else { const long long q = mp << shf; e.e = q; e.o = q; }
-            } else if (-shf <= 25) {                              // (further down: below a quarter of the grid, rounds away)
-                const int k = -shf;
-                const long long q = mp >> k, rem = mp & ((1LL << k) - 1), half = 1LL << (k - 1);
-                if (rem < half) { e.e = q; e.o = q; }
-                else if (rem > half) { e.e = q + 1; e.o = q + 1; }
-                else { e.e = q + (q & 1); e.o = q + ((1 + q) & 1); }              // tie: to even
-            }
+            const int ep = (int) ((pb >> 23) & 0xffu);            // biased float exponent (0: zero or subnormal)
+            const unsigned mp = (pb & 0x7fffffu) | (ep ? 0x800000u : 0u);
+            const int shf = max(ep, 1) - 150 - (Eb - 1075);
+            ok = ok && ep != 255 && shf <= 29;                    // Inf / NaN: the plain chain reproduces them; shf > 29: the term alone reaches the next binade
+            const int k = min(max(-shf, 0), 31), ls = min(max(shf, 0), 29);     // k >= 26: below a quarter of the grid, rounds away (q = 0, rem < half)
+            const unsigned q = mp >> k, rem = mp & ((1u << k) - 1u), half = (1u << k) >> 1;
+            const unsigned up = rem > half ? 1u : 0u, tie = (rem == half && k > 0) ? 1u : 0u;    // tie: to even
+            IncPair e;
+            e.e = (long long) ((unsigned long long) (q + up + (tie & q & 1u)) << ls);
+            e.o = (long long) ((unsigned long long) (q + up + (tie & ~q & 1u)) << ls);
             mine = inc_compose(mine, e);
         }
         ok = __all_sync(0xffffffffu, ok);

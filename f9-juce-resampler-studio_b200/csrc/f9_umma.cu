@@ -55,6 +55,7 @@ constexpr int kConvTeams = 2;                    // teams of four warps (one per
 constexpr int kConvWarps = 4 * kConvTeams;
 constexpr int kConvPerStage = 4;                 // warps that take part in one stage: its barriers count these
 constexpr int kThreadsTma = (kFirstConv + kConvWarps) * 32;
+constexpr uint32_t kSleepProducerNs = 100, kSleepEpilogueNs = 200;   // mbar_wait_sleep: roles with slack
 constexpr uint32_t kParkNs = 1000;                // suspend-time hint of the TMA roles' barrier waits (a hot poll loop cost 40 % of the issue slots)
 #ifdef F9_DIAG
 constexpr int kSpin = 1 << 22;
@@ -106,6 +107,17 @@ __device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity,
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(ns) : "memory");
         if (ok) return;
+    }
+    F9_TRAP(bar, parity);
+}
+// For the roles that are NOT on the pair's critical path (producer: a ring of boxes ahead; epilogue: a group every few stages):
+// poll, then really sleep.  The suspend hint of try_wait compiles to NANOSLEEP.SYNCS, which returns on any barrier traffic of the SM
+// (~23 clk per poll measured: 26 polls per wait), so a dozen waiting warps took a third of the issue slots from the converters.
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, uint32_t ns) {
+    #pragma unroll 1
+    for (int i = 0; i < kSpin; ++i) {
+        if (mbar_try_wait(bar, parity)) return;
+        asm volatile("nanosleep.u32 %0;" :: "r"(ns));
     }
     F9_TRAP(bar, parity);
 }
@@ -398,7 +410,7 @@ __device__ __forceinline__ void producer_role(const FeedArgs& A, const UmmaTma& 
         if (cur.y < 0) {
             // a tile read with guarded loads: its stages still take their ring positions (see converter_role), without a box
             for (int st = 0; st < A.nStages; ++st) {
-                mbar_wait_parked(A.empty + sIdx, sPh ^ 1, kParkNs);
+                mbar_wait_sleep(A.empty + sIdx, sPh ^ 1, kSleepProducerNs);
                 mbar_arrive(A.full + sIdx);
                 if (pf) l2_prefetch(pf + (size_t) st * pfChunk, pfChunk);
                 if (++sIdx == A.stages) { sIdx = 0; sPh ^= 1; }
@@ -406,7 +418,7 @@ __device__ __forceinline__ void producer_role(const FeedArgs& A, const UmmaTma& 
         } else {
             const CUtensorMap* map = &TM.maps[cur.y];
             for (int st = 0; st < A.nStages; ++st) {
-                mbar_wait_parked(A.empty + sIdx, sPh ^ 1, kParkNs);
+                mbar_wait_sleep(A.empty + sIdx, sPh ^ 1, kSleepProducerNs);
                 TR_EV(t, 1, st);
 #ifdef F9_DIAG
                 if (A.dbg & 128) { mbar_arrive(A.full + sIdx); if (++sIdx == A.stages) { sIdx = 0; sPh ^= 1; } continue; }   // no box: the converters read stale shared memory
@@ -938,7 +950,7 @@ umma_fir_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix
             const bool rowsInside = oBase >= 0 && oBase + (long long) (kRows - 1) * q + blockSlots <= S.numOut;
             float* outG = reinterpret_cast<float*>(__cvta_generic_to_global(S.out));
             for (int gl = 0; gl < BI.nGroups; ++gl) {
-                { PROF_BEGIN(w); mbar_wait_parked(sm.accFull + gl, t & 1, 2000); PROF_END(pW0, w); }
+                { PROF_BEGIN(w); if (TMA) mbar_wait_sleep(sm.accFull + gl, t & 1, kSleepEpilogueNs); else mbar_wait_parked(sm.accFull + gl, t & 1, 2000); PROF_END(pW0, w); }
                 tc_fence_after();
                 TR_EV(t, 30, gl);
                 for (int h = 0; h < chunks; ++h) {
