@@ -12,6 +12,7 @@ import sys
 import numpy as np
 
 CAP, WARPS = 1024, 18
+ISS, CONV = range(5, 10), range(10, 18)        # warps 0-3 epilogue, 4 producer, 5-9 issuers, 10-17 converters (two teams of four)
 raw = np.fromfile(sys.argv[1], dtype=np.int64).reshape(2, WARPS, CAP)
 cta = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 sync = [int(raw[c, 4, CAP - 1] & 0xffffffffff) for c in range(2)]       # each CTA's clock as it left the start-up cluster barrier
@@ -58,7 +59,7 @@ def s(x):
 
 print(f"CTA {cta}: clocks relative to the first event; all figures in SM clocks")
 print("producer   box-to-box              ", s(period(4, 1)))
-for w in range(10, 18):
+for w in CONV:
     if not ev[w]:
         continue
     print(f"converter {w}: stage period        ", s(period(w, 10)))
@@ -67,7 +68,7 @@ for w in range(10, 18):
     print(f"             convert (10 -> 11)   ", s(deltas(w, 10, 11)))
     print(f"             slot wait (11 -> 12) ", s(deltas(w, 11, 12)))
     print(f"             store (12 -> 13)     ", s(deltas(w, 12, 13)))
-for w in range(5, 10):
+for w in ISS:
     if not ev[w]:
         continue
     print(f"issuer {w}:   stage period         ", s(period(w, 20)))
