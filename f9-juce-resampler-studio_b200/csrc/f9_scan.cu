@@ -178,6 +178,10 @@ __device__ __forceinline__ long long count_small_terms(const DevBuf& B, double s
 // stays below 2^53 (s has not left the binade: the sum is monotone).  The block that crosses a binade -- at most ~60 per buffer --
 // is walked term by term by warp 0 with real double additions, and the next round starts behind it on the new grid.  Every
 // operation is exact, so the result IS the sequential sum, bit for bit (forced on every test buffer through F9_RMS_FORCE_ORDER).
+// A sum of squares is never negative: the sign bit marks "re-sum this buffer in the reference's order" between the final kernels
+// and order_resum_kernel (a NaN sum is marked too and comes out as the chain's NaN).
+__device__ __forceinline__ double mark_for_resum(double s) { return __longlong_as_double(__double_as_longlong(s) | (long long) 0x8000000000000000ull); }
+__device__ __forceinline__ bool marked_for_resum(double s) { return __double_as_longlong(s) < 0; }
 struct IncPair { long long e, o; };                              // increment of M when M is even / odd
 __device__ __forceinline__ IncPair inc_compose(IncPair a, IncPair c) {         // a first, then c
     IncPair r;
@@ -185,8 +189,8 @@ __device__ __forceinline__ IncPair inc_compose(IncPair a, IncPair c) {         /
     r.o = a.o + (((1 + a.o) & 1) ? c.o : c.e);
     return r;
 }
-constexpr int kSeqWarps = 8, kSeqPer = 32, kSeqBlock = 32 * kSeqPer;     // the final kernels run 256 threads; a round is 8192 terms
-struct SeqShared { IncPair pair[kSeqWarps]; int ok[kSeqWarps]; unsigned long long sb; int consumed; };
+constexpr int kSeqWarps = 32, kSeqPer = 8, kSeqBlock = 32 * kSeqPer;     // order_resum_kernel: 1024 threads, 8 terms per lane; a round is 8192 terms
+struct SeqShared { IncPair pair[kSeqWarps]; int ok[kSeqWarps]; unsigned long long sb; int consumed, nDone; long long Mend; };
 // The kSeqPer terms of one lane, channel-major (the reference's scan order), squared in float (:995); zeros past the end.
 // All loads are issued before the first use and without a branch between them: a guarded load per term put every load in its own
 // basic block, each waiting for the one before it (a round cost one memory latency PER TERM: 3.8 us for 8 terms).
@@ -256,16 +260,30 @@ __device__ __noinline__ double sum_squares_in_reference_order(const DevBuf& B, S
         }
         if (lane == 31) { sh.pair[warp] = mine; sh.ok[warp] = ok ? 1 : 0; }
         __syncthreads();
-        // apply the blocks in order while s stays in its binade (every thread does the same few integer steps)
-        long long M = (long long) ((sb & 0x000fffffffffffffull) | 0x0010000000000000ull);
-        int done = 0;
-        for (; done < kSeqWarps && b0 + (long long) done * kSeqBlock < total; ++done) {
-            if (!sh.ok[done]) break;
-            const IncPair pr = sh.pair[done];
-            const long long M2 = M + ((M & 1) ? pr.o : pr.e);
-            if (M2 >= (1LL << 53)) break;
-            M = M2;
+        // apply the blocks in order while s stays in its binade: a lane per block, an inclusive scan of the pairs (composition is
+        // associative), the first block that cannot be applied found with a ballot -- by warp 0 alone, then published (with every
+        // thread walking the blocks one after the other this loop was 40 % of the kernel's instructions)
+        const long long M0 = (long long) ((sb & 0x000fffffffffffffull) | 0x0010000000000000ull);
+        if (warp == 0) {
+            const bool live = lane < kSeqWarps && b0 + (long long) lane * kSeqBlock < total;
+            IncPair pr = live ? sh.pair[lane] : IncPair{0, 0};
+            const bool okb = live && sh.ok[lane] != 0;
+            #pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                IncPair prev;
+                prev.e = __shfl_up_sync(0xffffffffu, pr.e, off);
+                prev.o = __shfl_up_sync(0xffffffffu, pr.o, off);
+                if (lane >= off) pr = inc_compose(prev, pr);
+            }
+            const long long Ml = M0 + ((M0 & 1) ? pr.o : pr.e);           // M after blocks 0 .. lane (monotone in the lane)
+            const unsigned bad = __ballot_sync(0xffffffffu, !okb || Ml >= (1LL << 53));    // (blocks past the end count as bad: they stop the run)
+            const int nd = bad ? __ffs((int) bad) - 1 : 32;
+            const long long Mend = __shfl_sync(0xffffffffu, Ml, nd > 0 ? nd - 1 : 0);
+            if (lane == 0) { sh.nDone = nd; sh.Mend = nd > 0 ? Mend : M0; }
         }
+        __syncthreads();
+        const int done = sh.nDone;
+        const long long M = sh.Mend;
         if (done > 0) sb = ((unsigned long long) Eb << 52) | ((unsigned long long) M & 0x000fffffffffffffull);
         const bool crossing = done < kSeqWarps && b0 + (long long) done * kSeqBlock < total;
         int consumed = 0;
@@ -362,9 +380,7 @@ peak_final_kernel(const PeakPartial* __restrict__ partials, const int* __restric
             small = ((ssm[0] + ssm[1]) + (ssm[2] + ssm[3])) + ((ssm[4] + ssm[5]) + (ssm[6] + ssm[7]));
             redo = rms_rounds_differently(total, count, (double) (small + 256 + count / 16384) * 1.1102230246251565e-16) ? 2 : 0;
         }
-        __shared__ SeqShared seq;
-        const double v = (redo == 2) ? sum_squares_in_reference_order(B, seq) : total;       // redo is uniform: the whole CTA takes the call
-        if (threadIdx.x == 0) sumsq[b] = v;
+        if (threadIdx.x == 0) sumsq[b] = (redo == 2) ? mark_for_resum(total) : total;        // order_resum_kernel replaces a marked sum
     }
 }
 
@@ -460,9 +476,21 @@ stats_final_kernel(const double* __restrict__ psum, const float* __restrict__ pm
         small = ((ssm[0] + ssm[1]) + (ssm[2] + ssm[3])) + ((ssm[4] + ssm[5]) + (ssm[6] + ssm[7]));
         redo = rms_rounds_differently(s, count, (double) (small + 256 + count / 16384) * 1.1102230246251565e-16) ? 2 : 0;
     }
+    if (threadIdx.x == 0) { sumsq[b] = (redo == 2) ? mark_for_resum(s) : s; peak[b] = m; }
+}
+
+// The buffers whose sum the final kernels marked, re-summed in the reference's order: one CTA of 1024 threads each (the walk is
+// bound by its own instruction stream: 32 warps take 0.2 ms for a 5 s stereo capture where the final kernels' 8 took 0.6 ms), all
+// other CTAs leave at once.
+__global__ void __launch_bounds__(kSeqWarps * 32)
+order_resum_kernel(const DevBuf* __restrict__ bufs, double* __restrict__ sumsq) {
+    const int b = blockIdx.x;
+    if (!marked_for_resum(sumsq[b])) return;                     // uniform across the CTA
     __shared__ SeqShared seq;
-    const double v = (redo == 2) ? sum_squares_in_reference_order(B, seq) : s;
-    if (threadIdx.x == 0) { sumsq[b] = v; peak[b] = m; }
+    const DevBuf B = bufs[b];
+    __syncthreads();                                             // every thread has read the mark before thread 0 overwrites it
+    const double v = sum_squares_in_reference_order(B, seq);
+    if (threadIdx.x == 0) sumsq[b] = v;
 }
 
 // ---- reverb-tail windows ------------------------------------------------------------------------------
@@ -665,6 +693,7 @@ cudaError_t launch_find_peak(const DevBuf* d_bufs, int n, int total_ctas, const 
     }
     peak_final_kernel<<<n, 256, 0, s>>>(d_partials, d_prefix, threshold, d_out_pos, d_psum, d_sumsq, d_peakv, d_bufs, forceOrder);
     ++*launches;
+    if (d_psum && forceOrder >= 0) { order_resum_kernel<<<n, kSeqWarps * 32, 0, s>>>(d_bufs, d_sumsq); ++*launches; }
     return cudaGetLastError();
 }
 
@@ -676,6 +705,7 @@ cudaError_t launch_stats(const DevBuf* d_bufs, int n, double* d_psum, float* d_p
     ++*launches;
     stats_final_kernel<<<n, 256, 0, s>>>(d_psum, d_pmax, kStatPartials, d_sumsq, d_peak, n, d_bufs, forceOrder);
     ++*launches;
+    if (forceOrder >= 0) { order_resum_kernel<<<n, kSeqWarps * 32, 0, s>>>(d_bufs, d_sumsq); ++*launches; }
     return cudaGetLastError();
 }
 
