@@ -85,7 +85,7 @@ ras_biquad_kernel(const float* src, long long srcStride, float* dst, long long d
 // 33: conflict-free).  With one thread streaming its own chunk from global memory every load touched 32 different lines and
 // every store wrote 4 bytes of a sector (8 ms for 512 channels of 10 s; this form is bound by the FP64 recurrence).
 constexpr int kRasT = 32;                        // samples per chunk and step
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 6)
 ras_biquad_tiled_kernel(const float* __restrict__ src, long long srcStride, float* __restrict__ dst, long long dstStride,
                         long long n, long long nValid, int chunk, int warm, RasCoef k) {
     __shared__ float tile[128][kRasT + 1];
@@ -98,24 +98,46 @@ ras_biquad_tiled_kernel(const float* __restrict__ src, long long srcStride, floa
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
     const long long c0 = (cb + t) * (long long) chunk;             // this thread's chunk [c0, c0 + chunk)
     double x1 = 0, x2 = 0, y1 = 0, y2 = 0;
-    // relative sample index r runs over [-warm, chunk) in steps of kRasT (warm and chunk are multiples of kRasT)
-    for (int r0 = -warm; r0 < chunk; r0 += kRasT) {
-        for (int j = w; j < 128; j += 4) {                           // chunk row j: 32 consecutive samples, one line per warp instruction
-            const long long g = (cb + j) * (long long) chunk + r0 + lane;
-            tile[j][lane] = (g >= 0 && g < nValid) ? in[g] : 0.0f;
+    // relative sample index r runs over [-warm, chunk) in steps of kRasT (warm and chunk are multiples of kRasT).  The 32 row pieces a
+    // warp brings in per step are loaded a step ahead into registers, all 32 loads back to back: with a load and its shared-memory
+    // store per loop iteration the stores waited for one memory latency each (ncu: 48 % of all stalls on the first STS), and the
+    // recurrence of the step now runs while the next step's loads are in flight.
+    float nx[32];
+    const long long g00 = (cb + w) * (long long) chunk + lane;   // row w of the CTA, this lane's sample of a step at r0 = 0
+    auto fetch = [&](int r0) {
+        const long long g0 = g00 + r0;
+        const float* p0 = in + g0;
+        const bool inside = g0 >= 0 && g0 + 124LL * chunk < nValid;            // every row's sample of this lane exists
+        if (inside) {
+            #pragma unroll
+            for (int k = 0; k < 32; ++k) nx[k] = __ldg(p0 + (size_t) (4 * k) * (size_t) chunk);
+        } else {
+            #pragma unroll
+            for (int k = 0; k < 32; ++k) {
+                const long long g = g0 + (long long) (4 * k) * chunk;
+                nx[k] = (g >= 0 && g < nValid) ? __ldg(in + g) : 0.0f;
+            }
         }
+    };
+    fetch(-warm);
+    for (int r0 = -warm; r0 < chunk; r0 += kRasT) {
+        #pragma unroll
+        for (int k = 0; k < 32; ++k) tile[w + 4 * k][lane] = nx[k];
         __syncthreads();
+        if (r0 + kRasT < chunk) fetch(r0 + kRasT);
         const bool live = c0 + r0 >= 0 && c0 < n;                   // before sample 0 the state is the reset state: nothing to run
         if (live) {
             #pragma unroll 4
             for (int i = 0; i < kRasT; ++i) tile[t][i] = (float) ras_step(k, (double) tile[t][i], x1, x2, y1, y2);
         }
         __syncthreads();
-        if (r0 >= 0)
+        if (r0 >= 0) {
+            #pragma unroll 8
             for (int j = w; j < 128; j += 4) {
                 const long long g = (cb + j) * (long long) chunk + r0 + lane;
                 if (g < n && (cb + j) < chunksPer) out[g] = tile[j][lane];
             }
+        }
         __syncthreads();
     }
 }
