@@ -221,7 +221,8 @@ struct UmmaDev {
     int aSlots = 2;
     const uint8_t* W = nullptr;
 };
-bool build_umma(int kind, const float* sinc_table, long long p, long long q, int NB, int GBL, UmmaHost* out);
+// shift (0 .. 3): the plan for segments whose first sample sits `shift` floats past a 16-byte boundary (K origins = -shift mod 16)
+bool build_umma(int kind, const float* sinc_table, long long p, long long q, int NB, int GBL, UmmaHost* out, int shift = 0);
 size_t umma_smem_bytes(int maxEntries, int NB, int stages, bool tma = false, bool cta2 = false);
 // TMA feed of the tensor-core FIR: the input rows of a tile (128 periods, p floats apart, 32 samples per stage) are one box of a
 // rank-2 tensor map whose row stride is p floats, i.e. the rows overlap in memory.  One map covers 4 GiB from its base (box
@@ -270,6 +271,7 @@ int hankel_tile_elems(int L, int KS);
 struct ResampleLaunch {
     int kind = 0;
     const DiagOpts* diag = nullptr;   // the context's variant switches (never null after prepare_resample)
+    f9_context* ctx = nullptr;        // the planning context (resample_build_tiles fetches address-shifted tables through it)
     bool hankel = false;           // integer upsampling on the Hankel-operand kernel (takes priority)
     HankelDev hk;
     // tensor-core path (takes priority over banded when set; never used with adding)
@@ -350,12 +352,12 @@ struct f9_context {
         return std::tie(kind, p, q, TK, Gpad, epoch) < std::tie(o.kind, o.p, o.q, o.TK, o.Gpad, o.epoch); } };
     std::map<BandKey, f9::BandedDev> band_cache;
     int   get_banded(int kind, long long p, long long q, int TK, int Gpad, f9::BandedDev* out);
-    struct UmmaKey { int kind; long long p, q; int NB, GBL; unsigned epoch; bool operator<(const UmmaKey& o) const {
-        return std::tie(kind, p, q, NB, GBL, epoch) < std::tie(o.kind, o.p, o.q, o.NB, o.GBL, o.epoch); } };
+    struct UmmaKey { int kind; long long p, q; int NB, GBL; unsigned epoch; int shift; bool operator<(const UmmaKey& o) const {
+        return std::tie(kind, p, q, NB, GBL, epoch, shift) < std::tie(o.kind, o.p, o.q, o.NB, o.GBL, o.epoch, o.shift); } };
     std::map<UmmaKey, f9::UmmaDev> umma_cache;
     std::map<std::tuple<int, int, unsigned>, f9::HankelDev> hankel_cache;      // (kind, L, sinc epoch)
     int   get_hankel(int kind, int L, f9::HankelDev* out);
-    int   get_umma(int kind, long long p, long long q, int NB, int GBL, f9::UmmaDev* out);
+    int   get_umma(int kind, long long p, long long q, int NB, int GBL, f9::UmmaDev* out, int shift = 0);
     // Choose kernel + tables for (kind, ratio, pos0); fills everything in L except the segment table.
     int   prepare_resample(int kind, double ratio, double pos0, bool allow_rational, f9::ResampleLaunch* L);
 

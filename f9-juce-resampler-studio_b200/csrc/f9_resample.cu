@@ -578,12 +578,25 @@ int resample_build_tiles(ResampleLaunch& L, const Seg* segs, int n, std::vector<
     if (L.umma) {
         // row pieces start at in + (n0/q + 128*pb + row)*p + U0 - inOffset floats: all on 16 bytes iff p % 4 == 0 (U0 is a
         // multiple of 16) and every segment's (in - inOffset) is
+        // ... or every segment's is the same 1 .. 3 floats past one: the tables built for that shift (K origins = -shift mod 16)
+        // put the rows back on 16 bytes, where the plain tables would leave the launch to the register loader (1.50 ms against
+        // 0.64 ms on config 2's batch with untrimmed captures on 16 bytes: bench.py --unaligned)
         bool aligned = (L.um.p & 3) == 0;
-        for (int i = 0; i < n && aligned; ++i)
-            if (segs[i].numOut > 0 && ((((long long) (reinterpret_cast<uintptr_t>(segs[i].in) >> 2) - segs[i].inOffset) & 3) != 0 ||
-                                       (reinterpret_cast<uintptr_t>(segs[i].in) & 3) != 0)) aligned = false;
+        int shift = -1;
+        for (int i = 0; i < n && aligned; ++i) {
+            if (segs[i].numOut <= 0) continue;
+            if ((reinterpret_cast<uintptr_t>(segs[i].in) & 3) != 0) { aligned = false; break; }
+            const int m = (int) (((long long) (reinterpret_cast<uintptr_t>(segs[i].in) >> 2) - segs[i].inOffset) & 3);
+            if (shift < 0) shift = m; else if (shift != m) aligned = false;
+        }
         static const DiagOpts kNoDiag;
         const DiagOpts& D = L.diag ? *L.diag : kNoDiag;
+        if (aligned && shift > 0) {
+            UmmaDev shifted;
+            if (L.ctx && !D.has("F9_UMMA_NOSHIFT") && L.ctx->get_umma(L.kind, L.um.p, L.um.q, L.um.NB, L.um.GBL, &shifted, shift) == F9_OK &&
+                (shifted.poolN > 0) == (L.um.poolN > 0) && shifted.nGB == L.um.nGB) L.um = shifted;
+            else aligned = false;
+        }
         L.um_aligned = aligned && !D.has("F9_UMMA_UNALIGNED");
         // TMA feed (aligned rows only): tensor maps over the address range the segments read, ring of raw fp32 boxes
         L.um_tma = false;
@@ -669,12 +682,12 @@ cudaError_t launch_resample(const ResampleLaunch& L, cudaStream_t s, long long* 
 // ------------------------------------------------------------------------------------------------ planning (host)
 using namespace f9;
 
-int f9_context::get_umma(int kind, long long p, long long q, int NB, int GBL, UmmaDev* out) {
-    UmmaKey key{kind, p, q, NB, GBL, sinc_epoch};
+int f9_context::get_umma(int kind, long long p, long long q, int NB, int GBL, UmmaDev* out, int shift) {
+    UmmaKey key{kind, p, q, NB, GBL, sinc_epoch, shift};
     auto it = umma_cache.find(key);
     if (it != umma_cache.end()) { *out = it->second; return F9_OK; }
     UmmaHost H;
-    if (!build_umma(kind, sinc_table.data(), p, q, NB, GBL, &H)) return fail(F9_ERR_INVALID, "umma table build failed");
+    if (!build_umma(kind, sinc_table.data(), p, q, NB, GBL, &H, shift)) return fail(F9_ERR_INVALID, "umma table build failed");
     UmmaDev D; D.p = H.p; D.q = H.q; D.taps = H.taps; D.NB = H.NB; D.G = H.G; D.GBL = H.GBL; D.nGB = H.nGB; D.maxEntries = H.maxEntries; D.maxNK = H.maxNK;
     for (int b = 0; b < kUmmaMaxBlocks; ++b) D.blk[b] = H.blk[b];
     std::memcpy(D.gStart, H.gStart, sizeof(D.gStart)); std::memcpy(D.gSteps, H.gSteps, sizeof(D.gSteps)); std::memcpy(D.gTile, H.gTile, sizeof(D.gTile));
@@ -730,7 +743,7 @@ int f9_context::prepare_resample(int kind, double ratio, double pos0, bool allow
     if (interp_memory(kind) == 0) return fail(F9_ERR_INVALID, "unknown interpolator kind");
     if (!(ratio > 0.0) || !std::isfinite(ratio)) return fail(F9_ERR_INVALID, "speed ratio must be positive and finite");
     *L = ResampleLaunch();
-    L->kind = kind; L->ratio = ratio; L->pos0 = pos0; L->diag = &diag;
+    L->kind = kind; L->ratio = ratio; L->pos0 = pos0; L->diag = &diag; L->ctx = this;
     const DiagOpts& D = diag;
     L->d_sinc_table = d_sinc_table;
     L->tile_out = choose_tile_out(ratio);

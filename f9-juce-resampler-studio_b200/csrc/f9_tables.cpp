@@ -304,11 +304,14 @@ float f16_bits_to_f32(uint16_t h) {
 }
 inline long long floor16(long long x) { return x >= 0 ? (x / 16) * 16 : -(((-x) + 15) / 16) * 16; }
 
-struct GroupGeom { long long t0; int ksteps; long long wend; };   // K origin of the group's first step (multiple of 16), steps, window end
+// Address shift of the plan being built (build_umma's `shift`, 0 .. 3): K origins are congruent to -shift modulo 16, so that rows
+// of segments whose first sample sits `shift` floats past a 16-byte boundary still start on 16 bytes (TMA feed, aligned loads).
+static thread_local int t_geomShift = 0;
+struct GroupGeom { long long t0; int ksteps; long long wend; };   // K origin of the group's first step (multiple of 16 minus the shift), steps, window end
 void group_geom(long long p, long long q, int taps, int NB, int g, GroupGeom* out) {
     const long long k0 = (long long) NB * g, k1 = std::min<long long>(q, k0 + NB) - 1;
     const long long wmin = (k0 * p) / q - (taps - 1), wend = (k1 * p) / q + 1;
-    out->t0 = floor16(wmin);
+    out->t0 = floor16(wmin + t_geomShift) - t_geomShift;
     out->ksteps = (int) ((wend - out->t0 + 15) / 16);
     out->wend = wend;
 }
@@ -461,7 +464,8 @@ void umma_choose_plan(int taps, long long p, long long q, long long* m_out, int*
     }
 }
 
-bool build_umma(int kind, const float* sinc_table, long long p, long long q, int NB, int GBL, UmmaHost* out) {
+bool build_umma(int kind, const float* sinc_table, long long p, long long q, int NB, int GBL, UmmaHost* out, int shift) {
+    struct ShiftGuard { ShiftGuard(int v) { t_geomShift = v; } ~ShiftGuard() { t_geomShift = 0; } } guard(shift & 3);
     const int taps = interp_memory(kind);
     if (NB != 16 && NB != 32) return false;
     const int G = (int) ((q + NB - 1) / NB);

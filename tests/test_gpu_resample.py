@@ -534,6 +534,36 @@ def test_umma_feed_variants_are_bit_identical(ctx, O, f9, monkeypatch, kind):
             assert np.array_equal(a, b), FEEDS[i]
 
 
+@pytest.mark.parametrize("shift", [1, 2, 3])
+@pytest.mark.parametrize("fs", [(96000, 44100), (192000, 48000), (88200, 48000)])
+def test_umma_uniformly_shifted_windows(ctx, O, f9, shift, fs):
+    """Windows that all start `shift` floats past a 16-byte boundary (captures on 16 bytes, an odd latency trimmed off) take the
+    tables built for that shift (K origins = -shift mod 16) and stay on the TMA feed: within tolerance of the oracle, nothing
+    outside a window leaks in (the neighbourhood is poisoned), and the register loader (option F9_UMMA_NOSHIFT) agrees within
+    the tolerance as well -- not bit for bit: the taps fall into other K steps, so the accumulators truncate elsewhere."""
+    torch = pytest.importorskip("torch")
+    fs_in, fs_out = fs
+    x = signal(400000, 47 + shift)
+    windows = [(shift, 70001), (70004 + shift, 1), (70008 + shift, 26000), (96008 + shift, 131000), (227008 + shift, 19), (227028 + shift, 150000)]
+    xp = x.copy()
+    mask = np.ones(x.size, bool)
+    for off, n in windows:
+        mask[off:off + n] = False
+    xp[mask] = np.nan
+    d = torch.from_numpy(xp).cuda()
+    got = _plan_resample_many(ctx, f9, d, windows, 0, fs_in, fs_out)
+    ctx.set_option("F9_UMMA_NOSHIFT", 1)
+    try:
+        plain = _plan_resample_many(ctx, f9, d, windows, 0, fs_in, fs_out)
+    finally:
+        ctx.clear_options()
+    for (off, n), y, z in zip(windows, got, plain):
+        assert np.all(np.isfinite(y)), (off, n)
+        ref, _ = O.resample_channel(0, fs_in / fs_out, x[off:off + n], y.shape[0])
+        assert np.max(np.abs(y - ref)) <= TOL, (off, n)
+        assert np.max(np.abs(z - ref)) <= TOL, (off, n)
+
+
 @pytest.mark.parametrize("kind", [1, 2, 3, 4])
 @pytest.mark.parametrize("fs", RATIONAL + [(48000, 48000), (44100, 88200), (32000, 48000)])
 def test_short_kernel_windows(ctx, O, f9, monkeypatch, kind, fs):
