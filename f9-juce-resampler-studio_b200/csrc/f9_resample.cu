@@ -781,6 +781,7 @@ int f9_context::prepare_resample(int kind, double ratio, double pos0, bool allow
         if (!D.has("F9_NO_UMMA") && interp_memory(kind) >= 2) {
             long long bm = 0; int bGBL = 0, bNB = 0;
             umma_choose_plan(interp_memory(kind), p, q, &bm, &bNB, &bGBL, D.get("F9_UMMA_NB", 0));
+            if (bm > 0 && D.has("F9_UMMA_GBL")) bGBL = std::max(1, std::min(D.get("F9_UMMA_GBL"), kUmmaMaxGroups));     // experiments: groups per slot block
             if (bm > 0) {
                 rc = get_umma(kind, p * bm, q * bm, bNB, bGBL, &L->um);
                 if (rc == F9_OK) {

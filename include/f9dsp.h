@@ -203,7 +203,9 @@ F9_API int   f9_interp_process_adding(f9_interp* h, double speed_ratio, const fl
 F9_API int   f9_interp_process_wrap(f9_interp* h, double speed_ratio, const float* in, float* out,
                                     int num_out, int num_in_available, int wrap_around);
 /* WindowedSincTraits::lookupTable[10001].  JUCE's literal table is not in the reference; the built-in
- * default is sinc*Hann.  A host that has JUCE can install the real table here. */
+ * default is sinc*Hann.  A host that has JUCE can install the real table here.  Call it before creating plans
+ * and interpolators: those created earlier keep the table they were built with (their polyphase tables stay cached until the
+ * context is destroyed); everything created afterwards uses the new one. */
 F9_API int   f9_sinc_table_set(f9_context* ctx, const float* table10001);
 F9_API int   f9_sinc_table_get(const f9_context* ctx, float* table10001);
 
