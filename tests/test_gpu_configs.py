@@ -65,6 +65,43 @@ def test_config2_full_length_files_through_the_job_flow(ctx, O, f9):
             assert np.max(np.abs(outs[i][1][n0:n0 + 12000] - ref)) <= TOL, (f, n0)
 
 
+def test_job_flow_in_many_chunks_equals_one_chunk(ctx, O, f9):
+    """f9_process_batch enqueues every chunk without a host wait: chunk k + 2 reuses chunk k's device arena behind it in stream
+    order.  Twelve files of mixed shape (float planes and 24-bit file bytes in, float and 24-bit payload out, tail scans, DC
+    removal, two ratios) cut into one-file chunks (F9_BATCH_CHUNK_MB = 1) give the results of the single-chunk call bit for bit."""
+    rng = np.random.default_rng(11)
+    jobs = []
+    for i in range(12):
+        ch = 1 + i % 2
+        src = 40000 + 977 * i
+        lat = 3 + 5 * i
+        cap = (rng.uniform(-0.4, 0.4, (ch, src + lat + 12000)) * np.exp(-np.arange(src + lat + 12000) / 9000.0)).astype(np.float32)
+        fs = [(96000, 44100), (48000, 44100), (48000, 48000)][i % 3]
+        j = dict(latency_samples=lat * ch, original_length=src, fs_in=fs[0], fs_out=fs[1], kind=i % 2,
+                 tail=(4800, 2400, 3, f9.TAIL_RMS, True, -60.0, 0.0), pcm24=(i % 4 != 1), remove_dc=(i % 5 == 2))
+        if i % 3 == 1:
+            q = np.clip(np.round(cap.astype(np.float64) * 8388608.0), -8388608, 8388607).astype(np.int32)
+            inter = q.T.reshape(-1)
+            raw = np.stack([(inter >> (8 * b)) & 0xff for b in range(3)], axis=-1).astype(np.uint8).reshape(-1)
+            j["src_pcm"] = (raw, f9.PCM_S24LE, ch)
+        else:
+            j["captured"] = cap
+        jobs.append(j)
+    one = ctx.process_batch(jobs)
+    ctx.set_option("F9_BATCH_CHUNK_MB", 1)
+    try:
+        many = ctx.process_batch(jobs)
+        again = ctx.process_batch(jobs)                    # and once more on the arenas the call before left behind
+    finally:
+        ctx.clear_options()
+    for got in (many, again):
+        for i in range(len(jobs)):
+            assert got[2][i] == one[2][i], i
+            assert np.array_equal(got[0][i], one[0][i]), i
+            if jobs[i]["pcm24"]:
+                assert np.array_equal(got[1][i], one[1][i]), i
+
+
 # ------------------------------------------------------------------------------------------------ configs[2]
 def test_config3_64ch_10min_time_segmented(ctx, O, f9):
     """64 channels, 48 kHz -> 192 kHz, 10 minutes: 36.9 GB resident, every channel split into 8 time segments that carry their
