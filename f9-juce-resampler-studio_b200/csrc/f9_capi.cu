@@ -620,6 +620,7 @@ struct f9_interp {
 
 struct f9_plan {
     f9_context* ctx = nullptr;
+    std::vector<f9_plan*> parts;       // segments of mixed 16-byte alignment: one sub-plan per alignment class (this plan then launches nothing itself)
     ResampleLaunch L;
     Seg* d_segs = nullptr;
     int* d_prefix = nullptr;           // n_segs + 1 tile counts, then the plan's own overflow flag
@@ -918,6 +919,30 @@ int f9_resample_plan_create(f9_context* ctx, int kind, double speed_ratio, const
         if (hs[i].numOut < 0 || hs[i].n0 < 0 || hs[i].inAvail < 0 || (hs[i].numOut > 0 && (!hs[i].out || (hs[i].inAvail > 0 && !hs[i].in)))) {
             delete P; return ctx->fail(F9_ERR_INVALID, "bad resample segment");
         }
+    // Tensor-core plans feed through TMA when every segment's first sample sits on a 16-byte boundary or all of them sit the same
+    // 1-3 floats past one (resample_build_tiles: shifted tables).  Segments of MIXED alignment are planned per alignment class,
+    // each class on the fast feed, instead of sending the whole plan to the register loader.
+    if (P->L.umma && (P->L.um.p & 3) == 0 && !ctx->diag.has("F9_UMMA_NOSHIFT")) {
+        std::vector<Seg> cls[4]; bool all4 = true;
+        for (int i = 0; i < n_segs; ++i) {
+            if (hs[i].numOut <= 0) continue;
+            if (reinterpret_cast<uintptr_t>(hs[i].in) & 3) { all4 = false; break; }
+            cls[(int) (((long long) (reinterpret_cast<uintptr_t>(hs[i].in) >> 2) - hs[i].inOffset) & 3)].push_back(hs[i]);
+        }
+        int used = 0;
+        for (int c = 0; c < 4; ++c) used += cls[c].empty() ? 0 : 1;
+        if (all4 && used > 1) {
+            for (int c = 0; c < 4; ++c) {
+                if (cls[c].empty()) continue;
+                f9_plan* sub = nullptr;
+                rc = f9_resample_plan_create(ctx, kind, speed_ratio, reinterpret_cast<const f9_resample_seg*>(cls[c].data()), (int) cls[c].size(), &sub);
+                if (rc) { f9_plan_destroy(P); return rc; }
+                P->parts.push_back(sub);
+            }
+            *out = P;
+            return F9_OK;
+        }
+    }
     std::vector<int> prefix;
     const int tiles = resample_build_tiles(P->L, hs, n_segs, &prefix);
     if (tiles < 0) { delete P; return ctx->fail(F9_ERR_INVALID, "too many tiles"); }
@@ -941,6 +966,10 @@ int f9_resample_plan_create(f9_context* ctx, int kind, double speed_ratio, const
 int f9_resample_plan_run(f9_plan* plan) {
     if (!plan) return F9_ERR_INVALID;
     f9_context* ctx = plan->ctx;
+    if (!plan->parts.empty()) {
+        for (f9_plan* sub : plan->parts) { const int rc = f9_resample_plan_run(sub); if (rc) return rc; }
+        return F9_OK;
+    }
     F9_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
     if (plan->L.recs_stream != ctx->stream) plan->L.recs_ready = false;
     F9_TRY_CUDA(ctx, launch_resample(plan->L, ctx->stream, &ctx->launches));
@@ -950,6 +979,8 @@ int f9_resample_plan_run(f9_plan* plan) {
 }
 void f9_plan_destroy(f9_plan* plan) {
     if (!plan) return;
+    for (f9_plan* sub : plan->parts) f9_plan_destroy(sub);
+    plan->parts.clear();
     cudaSetDevice(plan->ctx->device);
     cudaStreamSynchronize(plan->ctx->stream);
     if (plan->d_segs) cudaFree(plan->d_segs);

@@ -564,6 +564,25 @@ def test_umma_uniformly_shifted_windows(ctx, O, f9, shift, fs):
         assert np.max(np.abs(z - ref)) <= TOL, (off, n)
 
 
+def test_umma_windows_of_mixed_alignment(ctx, O, f9):
+    """One plan over windows at every 16-byte misalignment: planned per alignment class (each on the TMA feed with the tables of
+    its shift); within tolerance of the oracle, nothing outside a window leaks in."""
+    torch = pytest.importorskip("torch")
+    x = signal(400000, 53)
+    windows = [(0, 70001), (70005, 1), (70010, 26000), (96011, 131000), (227012, 19), (227033, 150000), (377040, 5000), (382046, 9000)]
+    xp = x.copy()
+    mask = np.ones(x.size, bool)
+    for off, n in windows:
+        mask[off:off + n] = False
+    xp[mask] = np.nan
+    d = torch.from_numpy(xp).cuda()
+    got = _plan_resample_many(ctx, f9, d, windows, 0, 96000, 44100)
+    for (off, n), y in zip(windows, got):
+        assert np.all(np.isfinite(y)), (off, n)
+        ref, _ = O.resample_channel(0, 96000 / 44100, x[off:off + n], y.shape[0])
+        assert np.max(np.abs(y - ref)) <= TOL, (off, n)
+
+
 @pytest.mark.parametrize("kind", [1, 2, 3, 4])
 @pytest.mark.parametrize("fs", RATIONAL + [(48000, 48000), (44100, 88200), (32000, 48000)])
 def test_short_kernel_windows(ctx, O, f9, monkeypatch, kind, fs):
