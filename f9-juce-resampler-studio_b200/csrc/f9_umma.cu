@@ -65,7 +65,11 @@ constexpr int kSpin = 1 << 26;
 //                   // bounded waits: a protocol bug must not hang the GPU
 // -DF9_DIAG builds: event trace of the TMA-fed kernel's roles (F9_UMMA_TRACE=k traces launch k): per warp of CTAs 0 and 1 a list of
 // (event, index, clock) for the tiles kTrTile0 .. kTrTile1 - 1 of the CTA, dumped by launch_umma (tools/umma_trace.py reads it).
-constexpr int kTrCap = 1024, kTrTile0 = 6, kTrTile1 = 10, kTrWarps = 18;
+constexpr int kTrCap = 1024, kTrWarps = 18;
+#ifndef F9_TR_TILE0
+#define F9_TR_TILE0 6
+#endif
+constexpr int kTrTile0 = F9_TR_TILE0, kTrTile1 = F9_TR_TILE0 + 4;
 #ifdef F9_DIAG
 #define TR_INIT(prof, warp) long long* trBuf = ((prof) && blockIdx.x < 2) ? (prof) + ((size_t) blockIdx.x * kTrWarps + (warp)) * kTrCap : nullptr; int trN = 0
 #define TR_EV(t, ev, idx) do { if (trBuf && (t) >= kTrTile0 && (t) < kTrTile1 && trN < kTrCap) \
@@ -672,6 +676,10 @@ umma_fir_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix
                 const __grid_constant__ UmmaDev P, const __grid_constant__ UmmaTma TM, const UmmaTileRec* __restrict__ recs, int stages, int alignedAll,
                 unsigned* __restrict__ ovf, long long* __restrict__ prof, int dbg) {
     extern __shared__ __align__(128) uint8_t smem[];
+#ifdef F9_DIAG
+    if (TMA && prof && blockIdx.x < 2 && threadIdx.x == 0)      // kernel entry of the traced CTAs
+        prof[((size_t) blockIdx.x * kTrWarps + 4) * kTrCap + kTrCap - 2] = (0x7ell << 56) | (clock64() & 0xffffffffffll);
+#endif
     const SmemMap sm = carve(smem, P.maxEntries, P.NB, stages, TMA, CTA2);
     const uint32_t rank = CTA2 ? cluster_rank() : 0u;        // 0: leader (issues the MMAs)
     const int NB = P.NB;                                       // slots per group: MMA N
@@ -690,9 +698,19 @@ umma_fir_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix
 
     // ---- one-time setup: weights into shared memory, barriers, TMEM
     {
+        // 90 - 180 KB of weights per CTA: eight 16-byte loads in flight per thread.  One load per loop iteration waited for one L2
+        // latency twenty times over: 15 500 clk (7.9 us) from kernel entry to the end of this set-up in an event trace of config 1,
+        // a quarter of that launch.
         const uint4* src = reinterpret_cast<const uint4*>(P.W + (CTA2 ? BI.w2Off[rank] : BI.wOff));
         uint4* dst = reinterpret_cast<uint4*>(sm.W);
-        for (int i = threadIdx.x; i < BI.nEntries * NB * (CTA2 ? 2 : 4); i += blockDim.x) dst[i] = __ldg(src + i);
+        const int nW16 = BI.nEntries * NB * (CTA2 ? 2 : 4);
+        for (int i0 = threadIdx.x; i0 < nW16; i0 += 8 * (int) blockDim.x) {
+            uint4 r[8];
+            #pragma unroll
+            for (int k = 0; k < 8; ++k) { const int i = i0 + k * (int) blockDim.x; r[k] = i < nW16 ? __ldg(src + i) : make_uint4(0u, 0u, 0u, 0u); }
+            #pragma unroll
+            for (int k = 0; k < 8; ++k) { const int i = i0 + k * (int) blockDim.x; if (i < nW16) dst[i] = r[k]; }
+        }
         const uint4* osrc = reinterpret_cast<const uint4*>(P.W + (TMA ? BI.opOffT : BI.opOff));
         for (int i = threadIdx.x; i < BI.nEntries; i += blockDim.x) sm.ops[i] = __ldg(osrc + i);
         if (threadIdx.x == 0) {
@@ -718,7 +736,7 @@ umma_fir_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix
         __syncthreads();
         if (CTA2) cluster_sync_all();                          // the peer's barriers and weights are ready before anything crosses over
 #ifdef F9_DIAG
-        if (TMA && prof && blockIdx.x < 2 && threadIdx.x == 0)  // both CTAs leave the cluster barrier together: offset between their clocks
+        if (TMA && prof && blockIdx.x < 2 && threadIdx.x == 0)  // end of the set-up; both CTAs of a pair leave the cluster barrier together: offset between their clocks
             prof[((size_t) blockIdx.x * kTrWarps + 4) * kTrCap + kTrCap - 1] = (0x7fll << 56) | (clock64() & 0xffffffffffll);
 #endif
         tc_fence_after();
@@ -1014,6 +1032,10 @@ umma_fir_kernel(const Seg* __restrict__ segs, const int* __restrict__ tilePrefix
 
     tc_fence_before();
     __syncthreads();
+#ifdef F9_DIAG
+    if (TMA && prof && blockIdx.x < 2 && threadIdx.x == 0)      // all roles of the CTA are done
+        prof[((size_t) blockIdx.x * kTrWarps + 4) * kTrCap + kTrCap - 3] = (0x7dll << 56) | (clock64() & 0xffffffffffll);
+#endif
     if (CTA2) cluster_sync_all();                              // the peer may still read this CTA's weights / signal its barriers
     tc_fence_after();
     if (warp == 4) {
