@@ -214,7 +214,7 @@ def emit(line: dict):
 # command (not measured by this run: a number taken under a profiler is never a bench value, and ncu is not available inside a
 # timed run).  Keyed by (workload, files per GPU); None when no capture of that shape is committed.
 TRAFFIC = {
-    ("config2_256x_stereo_96k_to_44k1_trim_tail", 256): (2.033642e9 + 873.455104e6, "profiles/r02c_umma_full.txt (ncu --set full of this command at 256 files, round 2's kernel: dram__bytes_read + dram__bytes_write of the FIR launch)"),
+    ("config2_256x_stereo_96k_to_44k1_trim_tail", 256): (2.035183e9 + 873.595136e6, "profiles/r02d_umma_full.txt (ncu --set full of this command at 256 files, round 2's kernel: dram__bytes_read + dram__bytes_write of the FIR launch)"),
 }
 
 
