@@ -3,9 +3,12 @@
 //     capture -> [reverb-tail scan] -> trimLatency -> [removeDCOffset] -> [sample-rate conversion] -> float / 24-bit PCM
 // One H2D pass per capture, batched kernels over the whole chunk, one D2H pass per output.
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <map>
 
 #include "f9_internal.cuh"
@@ -68,13 +71,25 @@ void chunk_bytes(const f9_job* jobs, const std::vector<int>& idx, const std::vec
     *d_out = d_bytes; *h_out = h_bytes; *maxPollsOut = maxPolls; *nTailOut = nTail;
 }
 
-// Enqueue one chunk on the context's current slot (arena + stream); does not wait.  The caller has reserved the arenas.
-int run_chunk(f9_context* ctx, const f9_job* jobs, const std::vector<int>& idx, std::vector<JobPlan>& plans, PendingChunk* pc) {
+// The three engines of the pipeline each get ONE stream, so that each engine's work is a single in-order queue: uploads (payloads,
+// then the chunk's descriptor arrays), kernels, downloads; events carry a chunk from one to the next, and from a chunk's download to
+// the upload that reuses its arena.  (The step-to-step variance of the e2e leg that this layout was first suspected of -- 33.6 ms
+// or anything up to 178 ms per step of config 2, while the same bytes as 512 plain copies with event hand-offs took 32.6-34.8 ms in
+// the same process, tools/copy_granularity_probe.py -- was the host's: cudaMemGetInfo at the top of every call, see there.)
+struct ChunkStreams { cudaStream_t up, comp, down; cudaEvent_t evUp, evComp, evDown; };
+
+// Enqueue one chunk on the context's current slot (arena); does not wait.  The caller has reserved the arenas.
+int run_chunk(f9_context* ctx, const f9_job* jobs, const std::vector<int>& idx, std::vector<JobPlan>& plans, PendingChunk* pc, const ChunkStreams& CS) {
     const int n = (int) idx.size();
     size_t d_bytes = 0, h_bytes = 0;
     int maxPolls = 0, nTail = 0, rc = F9_OK;
     chunk_bytes(jobs, idx, plans, &d_bytes, &h_bytes, &maxPolls, &nTail);
-    cudaStream_t s = ctx->stream;
+    const cudaStream_t sUp = CS.up, s = CS.comp, sDown = CS.down;
+    long long* const launches = &ctx->launches;
+    struct DescCopy { void* d; const void* h; size_t bytes; };
+    std::vector<DescCopy> desc;                                // descriptor arrays: uploaded behind the payloads, before any kernel
+    std::vector<std::function<cudaError_t()>> work;            // the chunk's launches, in order, enqueued once the uploads are
+    std::vector<DevBuf> pb; std::vector<unsigned char*> pd;    // (read by a launch below: function scope)
 
     // ---- upload captures, carve outputs ----
     // Captures given as file bytes (f9_job::src_pcm): the payload is uploaded as it is and deinterleaved / converted on the device,
@@ -98,7 +113,7 @@ int run_chunk(f9_context* ctx, const f9_job* jobs, const std::vector<int>& idx, 
                 const int lead = std::min(J.captured_frames, (4 - padA) & 3);
                 const size_t off = (16 - (lead * frameBytes) % 16) % 16;
                 unsigned char* d_src = (unsigned char*) ctx->d_alloc(bytes + 48) + off;
-                F9_TRY_CUDA(ctx, cudaMemcpyAsync(d_src, J.src_pcm, bytes, cudaMemcpyHostToDevice, s));
+                F9_TRY_CUDA(ctx, cudaMemcpyAsync(d_src, J.src_pcm, bytes, cudaMemcpyHostToDevice, sUp));
                 const auto key = std::make_pair(J.src_fmt, J.src_ch);
                 if (lead > 0) { pcmHead[key].src.push_back(d_src); pcmHead[key].dst.push_back(DevBuf{d_cap, cs, J.numCh, lead}); }
                 if (J.captured_frames > lead) {
@@ -109,7 +124,7 @@ int run_chunk(f9_context* ctx, const f9_job* jobs, const std::vector<int>& idx, 
         } else
         for (int c = 0; c < J.numCh; ++c)
             if (J.captured_frames > 0)
-                F9_TRY_CUDA(ctx, cudaMemcpyAsync(d_cap + c * cs, J.captured[c], sizeof(float) * (size_t) J.captured_frames, cudaMemcpyHostToDevice, s));
+                F9_TRY_CUDA(ctx, cudaMemcpyAsync(d_cap + c * cs, J.captured[c], sizeof(float) * (size_t) J.captured_frames, cudaMemcpyHostToDevice, sUp));
         P.cap = DevBuf{d_cap, cs, J.numCh, J.captured_frames};
         const bool needTrimmed = !P.convert || (J.flags & F9_JOB_REMOVE_DC);
         if (P.convert && needTrimmed) {
@@ -130,14 +145,16 @@ int run_chunk(f9_context* ctx, const f9_job* jobs, const std::vector<int>& idx, 
             const unsigned char** h_p = (const unsigned char**) ctx->h_alloc(sizeof(void*) * m); DevBuf* h_b = (DevBuf*) ctx->h_alloc(sizeof(DevBuf) * m);
             if (!d_p || !d_b || !h_p || !h_b) return ctx->fail(F9_ERR_NOMEM, "arena");
             std::memcpy(h_p, G.src.data(), sizeof(void*) * m); std::memcpy(h_b, G.dst.data(), sizeof(DevBuf) * m);
-            F9_TRY_CUDA(ctx, cudaMemcpyAsync(d_p, h_p, sizeof(void*) * m, cudaMemcpyHostToDevice, s));
-            F9_TRY_CUDA(ctx, cudaMemcpyAsync(d_b, h_b, sizeof(DevBuf) * m, cudaMemcpyHostToDevice, s));
-            F9_TRY_CUDA(ctx, launch_pcm_to_planar_batch(d_p, kv.first.first, kv.first.second, G.dst.data(), d_b, (int) m, s, &ctx->launches,
-                                                        pass ? nullptr : G.src.data()));
+            desc.push_back(DescCopy{d_p, h_p, sizeof(void*) * m});
+            desc.push_back(DescCopy{d_b, h_b, sizeof(DevBuf) * m});
+            const int fmt = kv.first.first, sch = kv.first.second;
+            const DevBuf* hostDst = G.dst.data(); const unsigned char* const* hostSrc = pass ? nullptr : G.src.data();     // the maps outlive the launches
+            work.push_back([=]() { return launch_pcm_to_planar_batch(d_p, fmt, sch, hostDst, d_b, (int) m, s, launches, hostSrc); });
         }
 
     // ---- reverb-tail scan (Swift :423-453): starts once source + latency frames are captured ----
     long long* h_stop = nullptr; std::vector<int> tailJobs;
+    const long long* d_stop_out = nullptr; size_t stopBytes = 0;
     if (nTail > 0) {
         std::vector<DevBuf> tb; std::vector<TailParams> tp;
         for (int t = 0; t < n; ++t) {
@@ -159,13 +176,14 @@ int run_chunk(f9_context* ctx, const f9_job* jobs, const std::vector<int>& idx, 
         TailParams* h_tp = (TailParams*) ctx->h_alloc(sizeof(TailParams) * tp.size());
         std::memcpy(h_tb, tb.data(), sizeof(DevBuf) * tb.size());
         std::memcpy(h_tp, tp.data(), sizeof(TailParams) * tp.size());
-        F9_TRY_CUDA(ctx, cudaMemcpyAsync(d_tb, h_tb, sizeof(DevBuf) * tb.size(), cudaMemcpyHostToDevice, s));
-        F9_TRY_CUDA(ctx, cudaMemcpyAsync(d_tp, h_tp, sizeof(TailParams) * tp.size(), cudaMemcpyHostToDevice, s));
+        desc.push_back(DescCopy{d_tb, h_tb, sizeof(DevBuf) * tb.size()});
+        desc.push_back(DescCopy{d_tp, h_tp, sizeof(TailParams) * tp.size()});
         int* d_flags = (int*) ctx->d_alloc(sizeof(int) * (size_t) std::max(maxPolls, 1) * tb.size());
         long long* d_stop = (long long*) ctx->d_alloc(sizeof(long long) * tb.size());
-        F9_TRY_CUDA(ctx, launch_tail_scan(d_tb, d_tp, (int) tb.size(), maxPolls, d_stop, d_flags, s, &ctx->launches));
+        const int nTb = (int) tb.size();
+        work.push_back([=]() { return launch_tail_scan(d_tb, d_tp, nTb, maxPolls, d_stop, d_flags, s, launches); });
         h_stop = (long long*) ctx->h_alloc(sizeof(long long) * tb.size());
-        F9_TRY_CUDA(ctx, cudaMemcpyAsync(h_stop, d_stop, sizeof(long long) * tb.size(), cudaMemcpyDeviceToHost, s));
+        d_stop_out = d_stop; stopBytes = sizeof(long long) * tb.size();
     }
 
     // ---- trim (+DC) where a trimmed buffer is materialised ----
@@ -187,9 +205,9 @@ int run_chunk(f9_context* ctx, const f9_job* jobs, const std::vector<int>& idx, 
             DevBuf* h_c = (DevBuf*) ctx->h_alloc(sizeof(DevBuf) * m); DevBuf* h_o = (DevBuf*) ctx->h_alloc(sizeof(DevBuf) * m);
             int* h_l = (int*) ctx->h_alloc(sizeof(int) * m);
             std::memcpy(h_c, tc.data(), sizeof(DevBuf) * m); std::memcpy(h_o, to.data(), sizeof(DevBuf) * m); std::memcpy(h_l, lat.data(), sizeof(int) * m);
-            F9_TRY_CUDA(ctx, cudaMemcpyAsync(d_c, h_c, sizeof(DevBuf) * m, cudaMemcpyHostToDevice, s));
-            F9_TRY_CUDA(ctx, cudaMemcpyAsync(d_o, h_o, sizeof(DevBuf) * m, cudaMemcpyHostToDevice, s));
-            F9_TRY_CUDA(ctx, cudaMemcpyAsync(d_l, h_l, sizeof(int) * m, cudaMemcpyHostToDevice, s));
+            desc.push_back(DescCopy{d_c, h_c, sizeof(DevBuf) * m});
+            desc.push_back(DescCopy{d_o, h_o, sizeof(DevBuf) * m});
+            desc.push_back(DescCopy{d_l, h_l, sizeof(int) * m});
             // removeDCOffset is fused into the trim for the files that asked for it (mask), so their trimmed buffer is written once
             bool anyDc = false;
             for (size_t i = 0; i < m; ++i) anyDc = anyDc || dcMask[i] != 0;
@@ -199,9 +217,9 @@ int run_chunk(f9_context* ctx, const f9_job* jobs, const std::vector<int>& idx, 
                 d_mask = (int*) ctx->d_alloc(sizeof(int) * m);
                 int* h_mask = (int*) ctx->h_alloc(sizeof(int) * m);
                 std::memcpy(h_mask, dcMask.data(), sizeof(int) * m);
-                F9_TRY_CUDA(ctx, cudaMemcpyAsync(d_mask, h_mask, sizeof(int) * m, cudaMemcpyHostToDevice, s));
+                desc.push_back(DescCopy{d_mask, h_mask, sizeof(int) * m});
             }
-            F9_TRY_CUDA(ctx, launch_trim(d_c, d_l, d_o, (int) m, maxFrames, maxCh, s, &ctx->launches, d_part, d_mask));
+            work.push_back([=]() { return launch_trim(d_c, d_l, d_o, (int) m, maxFrames, maxCh, s, launches, d_part, d_mask); });
         }
     }
 
@@ -231,18 +249,17 @@ int run_chunk(f9_context* ctx, const f9_job* jobs, const std::vector<int>& idx, 
             Seg* d_s = (Seg*) ctx->d_alloc(sizeof(Seg) * segs.size()); int* d_p = (int*) ctx->d_alloc(sizeof(int) * prefix.size());
             Seg* h_s = (Seg*) ctx->h_alloc(sizeof(Seg) * segs.size()); int* h_p = (int*) ctx->h_alloc(sizeof(int) * prefix.size());
             std::memcpy(h_s, segs.data(), sizeof(Seg) * segs.size()); std::memcpy(h_p, prefix.data(), sizeof(int) * prefix.size());
-            F9_TRY_CUDA(ctx, cudaMemcpyAsync(d_s, h_s, sizeof(Seg) * segs.size(), cudaMemcpyHostToDevice, s));
-            F9_TRY_CUDA(ctx, cudaMemcpyAsync(d_p, h_p, sizeof(int) * prefix.size(), cudaMemcpyHostToDevice, s));
+            desc.push_back(DescCopy{d_s, h_s, sizeof(Seg) * segs.size()});
+            desc.push_back(DescCopy{d_p, h_p, sizeof(int) * prefix.size()});
             L.d_segs = d_s; L.d_tile_prefix = d_p; L.n_segs = (int) segs.size(); L.n_tiles = prefix.back();
             if (const size_t sb = resample_scratch_bytes(L, L.n_tiles)) L.d_tile_recs = (UmmaTileRec*) ctx->d_alloc(sb);
             if (resample_needs_ovf(L)) L.d_ovf = (unsigned*) ctx->d_alloc(sizeof(unsigned));
-            F9_TRY_CUDA(ctx, launch_resample(L, s, &ctx->launches));
+            work.push_back([=]() { return launch_resample(L, s, launches); });
         }
     }
 
     // ---- 24-bit payload + downloads ----
     {   // one launch packs every file that asked for the WAV payload
-        std::vector<DevBuf> pb; std::vector<unsigned char*> pd;
         for (int t = 0; t < n; ++t) {
             const f9_job& J = jobs[idx[(size_t) t]];
             const JobPlan& P = plans[(size_t) t];
@@ -252,20 +269,30 @@ int run_chunk(f9_context* ctx, const f9_job* jobs, const std::vector<int>& idx, 
             DevBuf* d_b = (DevBuf*) ctx->d_alloc(sizeof(DevBuf) * pb.size()); unsigned char** d_p = (unsigned char**) ctx->d_alloc(sizeof(void*) * pd.size());
             DevBuf* h_b = (DevBuf*) ctx->h_alloc(sizeof(DevBuf) * pb.size()); unsigned char** h_p = (unsigned char**) ctx->h_alloc(sizeof(void*) * pd.size());
             std::memcpy(h_b, pb.data(), sizeof(DevBuf) * pb.size()); std::memcpy(h_p, pd.data(), sizeof(void*) * pd.size());
-            F9_TRY_CUDA(ctx, cudaMemcpyAsync(d_b, h_b, sizeof(DevBuf) * pb.size(), cudaMemcpyHostToDevice, s));
-            F9_TRY_CUDA(ctx, cudaMemcpyAsync(d_p, h_p, sizeof(void*) * pd.size(), cudaMemcpyHostToDevice, s));
-            F9_TRY_CUDA(ctx, launch_planar_to_pcm24_batch(pb.data(), d_b, d_p, (int) pb.size(), s, &ctx->launches, pd.data()));
+            desc.push_back(DescCopy{d_b, h_b, sizeof(DevBuf) * pb.size()});
+            desc.push_back(DescCopy{d_p, h_p, sizeof(void*) * pd.size()});
+            const DevBuf* hostB = pb.data(); unsigned char* const* hostP = pd.data(); const int nPb = (int) pb.size();
+            work.push_back([=]() { return launch_planar_to_pcm24_batch(hostB, d_b, d_p, nPb, s, launches, hostP); });
         }
     }
+    // uploads done -> kernels -> downloads
+    for (const DescCopy& dc : desc) F9_TRY_CUDA(ctx, cudaMemcpyAsync(dc.d, dc.h, dc.bytes, cudaMemcpyHostToDevice, sUp));
+    F9_TRY_CUDA(ctx, cudaEventRecord(CS.evUp, sUp));
+    F9_TRY_CUDA(ctx, cudaStreamWaitEvent(s, CS.evUp, 0));
+    for (auto& fn : work) F9_TRY_CUDA(ctx, fn());
+    F9_TRY_CUDA(ctx, cudaEventRecord(CS.evComp, s));
+    F9_TRY_CUDA(ctx, cudaStreamWaitEvent(sDown, CS.evComp, 0));
+    if (h_stop) F9_TRY_CUDA(ctx, cudaMemcpyAsync(h_stop, d_stop_out, stopBytes, cudaMemcpyDeviceToHost, sDown));
     for (int t = 0; t < n; ++t) {
         const f9_job& J = jobs[idx[(size_t) t]];
         const JobPlan& P = plans[(size_t) t];
         if ((J.flags & F9_JOB_PCM24) && P.out_frames > 0)
-            F9_TRY_CUDA(ctx, cudaMemcpyAsync(J.out_pcm24, P.d_pcm, (size_t) P.out_frames * J.numCh * 3, cudaMemcpyDeviceToHost, s));
+            F9_TRY_CUDA(ctx, cudaMemcpyAsync(J.out_pcm24, P.d_pcm, (size_t) P.out_frames * J.numCh * 3, cudaMemcpyDeviceToHost, sDown));
         if (J.out && P.out_frames > 0)
             for (int c = 0; c < J.numCh; ++c)
-                F9_TRY_CUDA(ctx, cudaMemcpyAsync(J.out[c], P.out.base + c * P.out.chStride, sizeof(float) * (size_t) P.out_frames, cudaMemcpyDeviceToHost, s));
+                F9_TRY_CUDA(ctx, cudaMemcpyAsync(J.out[c], P.out.base + c * P.out.chStride, sizeof(float) * (size_t) P.out_frames, cudaMemcpyDeviceToHost, sDown));
     }
+    F9_TRY_CUDA(ctx, cudaEventRecord(CS.evDown, sDown));
     pc->idx = idx; pc->tailJobs = tailJobs; pc->h_stop = h_stop;
     return F9_OK;
 }
@@ -279,31 +306,51 @@ extern "C" int f9_process_batch(f9_context* ctx, const f9_job* jobs, int n_jobs,
 int f9_process_batch_ext(f9_context* ctx, const f9_job* jobs, const f9_job_ext* ext, int n_jobs, f9_result* results) {
     if (!ctx) return F9_ERR_INVALID;
     if (n_jobs < 0 || (n_jobs > 0 && (!jobs || !results))) return ctx->fail(F9_ERR_INVALID, "bad job array");
+    const auto tCall = std::chrono::steady_clock::now();
     F9_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
-    size_t freeB = 0, totalB = 0;
-    F9_TRY_CUDA(ctx, cudaMemGetInfo(&freeB, &totalB));
-    // Chunks are pipelined over two slots (arena + stream each): while chunk k's kernels and downloads run on one stream, chunk
-    // k+1 uploads on the other (PCIe is full duplex and the copy engines are independent), so a large batch costs about
-    // max(upload, download) instead of their sum.  The whole call is ENQUEUED without waiting for anything: chunk k+2 reuses the
-    // device arena of chunk k behind it on the same stream (stream order is the only ordering the device arena needs), the pinned
-    // staging of descriptors and scalar results is not reused inside a call, and the host waits once, at the end.  With a wait per
-    // chunk (the first version) every chunk exposed the pipeline to the host thread's wake-up latency: on a shared host a step of
-    // config 2 took anything from 33 to 107 ms (tools/e2e_numa_probe.sh), and smaller chunks made it worse.
+    // Free device memory, asked ONCE per context: cudaMemGetInfo goes through the resource manager, and on a shared host that call
+    // sometimes took 10-90 ms (the whole enqueue is 2 ms otherwise: option F9_BATCH_TIMING) -- the step-to-step variance of the
+    // e2e leg.  The figure only caps the chunk size on small devices; the arenas themselves report failure if memory runs out.
+    if (ctx->free_mem_seen == 0) {
+        size_t freeNow = 0, totalB = 0;
+        F9_TRY_CUDA(ctx, cudaMemGetInfo(&freeNow, &totalB));
+        ctx->free_mem_seen = std::max<size_t>(freeNow + ctx->d_cap + ctx->parked.d_cap, 1);
+    }
+    const size_t freeB = ctx->free_mem_seen;
+    // Chunks are pipelined over two arenas and three streams (uploads, kernels, downloads: see ChunkStreams): chunk k + 1 uploads
+    // while chunk k computes and downloads (PCIe is full duplex and the copy engines are independent), so a large batch costs about
+    // max(upload, download) instead of their sum.  The whole call is ENQUEUED without waiting for anything: chunk k + 2's uploads
+    // wait for the event behind chunk k's downloads before they reuse its device arena, the pinned staging of descriptors and scalar
+    // results is not reused inside a call, and the host waits once, at the end (with a wait per chunk, the first version, every chunk
+    // exposed the pipeline to the host thread's wake-up latency).
     // Chunk size in device memory (option F9_BATCH_CHUNK_MB overrides), measured on B200 / PCIe 5 with config 2's 256 files
     // (tools/e2e_probe.py): float planes up and down 64 MB, file bytes up 256 MB.
     bool anyFloatIn = false;
     for (int i = 0; i < n_jobs; ++i) anyFloatIn = anyFloatIn || !jobs[i].src_pcm;
     const size_t chunkMB = (size_t) std::max(1, ctx->diag.get("F9_BATCH_CHUNK_MB", anyFloatIn ? 64 : 256));
-    const size_t budget = std::min(std::max<size_t>((freeB + ctx->d_cap + ctx->parked.d_cap) / 4, 64u << 20), chunkMB << 20);
+    const size_t budget = std::min(std::max<size_t>(freeB / 4, 64u << 20), chunkMB << 20);
+    // streams: kernels on the context's stream (slot 0's), uploads and downloads on two streams of the context's own
+    if (ctx->cur_slot) ctx->swap_slot();
     if (!ctx->alt_stream) {
         F9_TRY_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->alt_stream, cudaStreamNonBlocking));
-        (ctx->cur_slot == 0 ? ctx->parked.stream : ctx->stream) = ctx->alt_stream;
+        ctx->parked.stream = ctx->alt_stream;
     }
-    if (ctx->cur_slot) ctx->swap_slot();
-    {   // the second stream starts after whatever the caller already enqueued on the first
-        cudaEvent_t ev;
-        F9_TRY_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-        cudaEventRecord(ev, ctx->stream); cudaStreamWaitEvent(ctx->alt_stream, ev, 0); cudaEventDestroy(ev);
+    if (!ctx->down_stream) F9_TRY_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->down_stream, cudaStreamNonBlocking));
+    const cudaStream_t sComp = ctx->stream, sUp = ctx->alt_stream, sDown = ctx->down_stream;
+    auto event_at = [&](size_t i) -> cudaEvent_t {
+        while (ctx->ev_pool.size() <= i) {
+            cudaEvent_t e = nullptr;
+            if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+            ctx->ev_pool.push_back(e);
+        }
+        return ctx->ev_pool[i];
+    };
+    {   // the upload and download streams start after whatever the caller already enqueued on the context's stream
+        cudaEvent_t ev = event_at(0);
+        if (!ev) return ctx->fail(F9_ERR_CUDA, "cudaEventCreate");
+        F9_TRY_CUDA(ctx, cudaEventRecord(ev, sComp));
+        F9_TRY_CUDA(ctx, cudaStreamWaitEvent(sUp, ev, 0));
+        F9_TRY_CUDA(ctx, cudaStreamWaitEvent(sDown, ev, 0));
     }
 
     struct Chunk { std::vector<int> idx; std::vector<JobPlan> plans; };
@@ -370,18 +417,31 @@ int f9_process_batch_ext(f9_context* ctx, const f9_job* jobs, const f9_job_ext* 
     std::vector<char> enqueued(chunks.size(), 0);
     for (size_t k = 0; k < chunks.size(); ++k) {
         if ((int) (k & 1) != ctx->cur_slot) ctx->swap_slot();
-        ctx->d_used = 0;                                       // behind the slot's previous chunk in stream order
-        const int rc = run_chunk(ctx, jobs, chunks[k].idx, chunks[k].plans, &pending[k]);
-        if (rc) { worst = rc; for (int i : chunks[k].idx) results[i].status = rc; }
-        else enqueued[k] = 1;
+        ctx->d_used = 0;                                       // the arena of chunk k - 2: reused once that chunk's download is done
+        ChunkStreams CS{sUp, sComp, sDown, event_at(1 + 3 * k), event_at(2 + 3 * k), event_at(3 + 3 * k)};
+        int rc = (CS.evUp && CS.evComp && CS.evDown) ? F9_OK : ctx->fail(F9_ERR_CUDA, "cudaEventCreate");
+        if (!rc && k >= 2 && enqueued[k - 2] && cudaStreamWaitEvent(sUp, event_at(3 + 3 * (k - 2)), 0) != cudaSuccess) rc = ctx->fail(F9_ERR_CUDA, "cudaStreamWaitEvent");
+        if (!rc) rc = run_chunk(ctx, jobs, chunks[k].idx, chunks[k].plans, &pending[k], CS);
+        if (rc) {
+            // a chunk that failed half-way may have left work on the streams that the next user of its arena must not overtake
+            worst = rc; for (int i : chunks[k].idx) results[i].status = rc;
+            cudaStreamSynchronize(sUp); cudaStreamSynchronize(sComp); cudaStreamSynchronize(sDown);
+        } else enqueued[k] = 1;
     }
-    for (int k = 0; k < 2; ++k) {                              // the one wait of the call: both streams
-        const cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    const auto tEnq = std::chrono::steady_clock::now();
+    {   // the one wait of the call: the three streams
+        cudaError_t e = cudaStreamSynchronize(sUp);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(sComp);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(sDown);
         if (e != cudaSuccess) { worst = ctx->fail_cuda(e, "cudaStreamSynchronize"); for (auto& c : chunks) for (int i : c.idx) results[i].status = worst; }
-        ctx->quiescent = true;
-        ctx->swap_slot();
+        ctx->quiescent = true; ctx->parked.quiescent = true;
     }
     if (ctx->cur_slot) ctx->swap_slot();
+    if (ctx->diag.has("F9_BATCH_TIMING")) {                    // development: where a call's time goes (host enqueue against the wait)
+        const auto tEnd = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[f9_process_batch] %zu chunks: enqueue %.2f ms, wait %.2f ms\n", chunks.size(),
+                     std::chrono::duration<double, std::milli>(tEnq - tCall).count(), std::chrono::duration<double, std::milli>(tEnd - tEnq).count());
+    }
     if (worst != F9_ERR_CUDA)
         for (size_t k = 0; k < chunks.size(); ++k)
             if (enqueued[k])

@@ -121,6 +121,8 @@ void f9_context_destroy(f9_context* ctx) {
     if (ctx->d_sinc_table) cudaFree(ctx->d_sinc_table);
     if (ctx->cur_slot) ctx->swap_slot();
     if (ctx->alt_stream) { cudaStreamSynchronize(ctx->alt_stream); cudaStreamDestroy(ctx->alt_stream); }
+    if (ctx->down_stream) { cudaStreamSynchronize(ctx->down_stream); cudaStreamDestroy(ctx->down_stream); }
+    for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     ctx->arena_reset(); ctx->swap_slot(); ctx->arena_reset(); ctx->swap_slot();      // frees both slots' spill allocations
     if (ctx->parked.d_arena) cudaFree(ctx->parked.d_arena);
     if (ctx->parked.h_arena) cudaFreeHost(ctx->parked.h_arena);

@@ -370,7 +370,10 @@ struct f9_context {
     // kernels and the download of chunk k; swap_slot() exchanges the current arena / stream with the parked one.
     struct ParkedSlot { char* d_arena = nullptr; size_t d_cap = 0, d_used = 0; char* h_arena = nullptr; size_t h_cap = 0, h_used = 0;
                         cudaStream_t stream = nullptr; bool quiescent = true; std::vector<void*> d_spill, h_spill; } parked;
-    cudaStream_t alt_stream = nullptr;  // owned; the parked slot's stream
+    cudaStream_t alt_stream = nullptr;  // owned; the parked slot's stream = f9_process_batch's upload stream
+    cudaStream_t down_stream = nullptr; // owned; f9_process_batch's download stream
+    size_t free_mem_seen = 0;           // free device memory + own arenas at f9_process_batch's first call (never asked again: see there)
+    std::vector<cudaEvent_t> ev_pool;   // f9_process_batch's events (three per chunk), created on demand, reused by every call
     int   cur_slot = 0;
     void  swap_slot() {
         std::swap(d_arena, parked.d_arena); std::swap(d_cap, parked.d_cap); std::swap(d_used, parked.d_used);

@@ -41,8 +41,8 @@ def jobs_for(mode):
         j = J[i]
         lat = 128 * (i % 256) + 7
         j.numCh, j.captured_frames, j.latency_samples, j.original_length = ch, cap, lat * ch, src
-        j.fs_in, j.fs_out, j.interp_kind = float(fs_in), float(fs_out), 0
-        j.flags = f9.JOB_TAIL_SCAN
+        j.fs_in, j.fs_out, j.interp_kind = float(fs_in), float(fs_out), int(os.environ.get("KIND", "0"))
+        j.flags = f9.JOB_TAIL_SCAN if not os.environ.get("NOTAIL") else 0
         j.tail_window, j.tail_hop, j.tail_required, j.tail_mode = 9600, 4800, 3, 0
         j.has_nf, j.nf_db, j.margin_pct = 1, -90.0, 0.0
         if mode[0] == "p":
@@ -62,6 +62,9 @@ for mode in (os.environ.get("MODES", "pp,ff,pf,fp").split(",")):
     for chunk in [int(c) for c in os.environ.get("CHUNKS", "16,32,64,128,256,512").split(",")]:
         ctx = f9.Context(0)
         ctx.set_option("F9_BATCH_CHUNK_MB", chunk)
+        for kv in os.environ.get("OPTS", "").split(","):
+            if kv:
+                ctx.set_option(kv.split("=")[0], int(kv.split("=")[1]) if "=" in kv else 1)
         for _ in range(2):
             assert L.f9_process_batch(ctx.handle, J, files, R) == 0
         ts = []
