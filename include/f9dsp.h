@@ -288,6 +288,10 @@ typedef struct f9_result {
 
 /* Output length of a conversion of n_in frames: ceil(n_in * fs_out / fs_in) in exact integers. */
 F9_API long long f9_resampled_length(long long n_in, double fs_in, double fs_out);
+/* Blocking.  The batch is cut into chunks of device memory and pipelined: uploads, kernels and downloads of different chunks overlap
+ * (three streams of the context, event hand-offs, no host wait between chunks).  Host buffers given as pinned (page-locked) memory
+ * are transferred by DMA straight from / into them; all of them must stay valid and untouched until the call returns.  Returns
+ * the worst job status; results[i] is filled for every job. */
 F9_API int f9_process_batch(f9_context* ctx, const f9_job* jobs, int n_jobs, f9_result* results);
 
 /* ============== F. device-resident entry points (pointers in HBM) =========== */
