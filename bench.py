@@ -551,7 +551,7 @@ def run_gpu(args, rank: int, local_rank: int, world: int):
                "achieved_h2d_gbs": round(h2d / step_s / 1e9, 2), "achieved_d2h_gbs": round(d2h / step_s / 1e9, 2),
                "frac_of_probe_both": round((h2d + d2h) / step_s / 1e9 / pcie["both_gbs"], 3) if pcie and pcie["both_gbs"] else None,
                "api": "f9_process_batch: f9_job::src_pcm (24-bit interleaved file payload, pinned) -> tail scan, trimLatency, WindowedSinc -> "
-                      "F9_JOB_PCM24 payload (pinned); chunks pipelined over two streams; per rank"}
+                      "F9_JOB_PCM24 payload (pinned); chunks pipelined over upload / kernel / download streams, one host wait per call; per rank"}
 
     if rank == 0:
         per_step_ms = ms / args.steps
