@@ -324,10 +324,9 @@ int f9_process_batch_ext(f9_context* ctx, const f9_job* jobs, const f9_job_ext* 
     // results is not reused inside a call, and the host waits once, at the end (with a wait per chunk, the first version, every chunk
     // exposed the pipeline to the host thread's wake-up latency).
     // Chunk size in device memory (option F9_BATCH_CHUNK_MB overrides), measured on B200 / PCIe 5 with config 2's 256 files
-    // (tools/e2e_probe.py): float planes up and down 64 MB, file bytes up 256 MB.
-    bool anyFloatIn = false;
-    for (int i = 0; i < n_jobs; ++i) anyFloatIn = anyFloatIn || !jobs[i].src_pcm;
-    const size_t chunkMB = (size_t) std::max(1, ctx->diag.get("F9_BATCH_CHUNK_MB", anyFloatIn ? 64 : 256));
+    // (tools/e2e_probe.py, ms per call at 64 / 128 / 256 / 512 / 1024 MB): file bytes in and out 37.5 / 35.2 / 33.4 / 33.4 / 33.9,
+    // float planes in and out 47.2 / 46.6 / 46.3 / 46.4 / 47.2.
+    const size_t chunkMB = (size_t) std::max(1, ctx->diag.get("F9_BATCH_CHUNK_MB", 256));
     const size_t budget = std::min(std::max<size_t>(freeB / 4, 64u << 20), chunkMB << 20);
     // streams: kernels on the context's stream (slot 0's), uploads and downloads on two streams of the context's own
     if (ctx->cur_slot) ctx->swap_slot();
