@@ -98,6 +98,38 @@ int run_chunk(f9_context* ctx, const f9_job* jobs, const std::vector<int>& idx, 
     // 128-bit kernels serve everything but the `lead` <= 3 frames in front of it (those go through the byte-staged kernel).
     struct PcmGroup { std::vector<const unsigned char*> src; std::vector<DevBuf> dst; };
     std::map<std::pair<int, int>, PcmGroup> pcmMain, pcmHead;
+    // File payloads that follow one another in host memory (a reader that holds its files in one buffer: less than 64 bytes between
+    // the end of one and the start of the next) go up as ONE copy when the device placement each of them needs (below) is the one the
+    // host spacing gives: a copy costs the engine ~8 us whatever its size, 2 ms for config 2's 256 files against 29 ms of transfer.
+    std::vector<unsigned char*> dSrcOf((size_t) n, nullptr);
+    {
+        struct Run { int t0, t1; const unsigned char* h0; const unsigned char* hEnd; size_t off0; };
+        std::vector<Run> runs;
+        for (int t = 0; t < n; ++t) {
+            const f9_job& J = jobs[idx[(size_t) t]];
+            const JobPlan& P = plans[(size_t) t];
+            if (!J.src_pcm || J.captured_frames <= 0) continue;
+            const int padA = (P.convert && P.start > 0) ? ((4 - (P.start & 3)) & 3) : 0;
+            const size_t frameBytes = (size_t) J.src_ch * pcm_bps(J.src_fmt), bytes = frameBytes * (size_t) J.captured_frames;
+            const int lead = std::min(J.captured_frames, (4 - padA) & 3);
+            const size_t off = (16 - (lead * frameBytes) % 16) % 16;             // the payload's device address modulo 16
+            const unsigned char* h = (const unsigned char*) J.src_pcm;
+            if (!runs.empty() && runs.back().t1 == t && h >= runs.back().hEnd && (size_t) (h - runs.back().hEnd) < 64 &&
+                (runs.back().off0 + (size_t) (h - runs.back().h0)) % 16 == off) { runs.back().t1 = t + 1; runs.back().hEnd = h + bytes; }
+            else runs.push_back(Run{t, t + 1, h, h + bytes, off});
+        }
+        for (const Run& R : runs) {
+            const size_t span = (size_t) (R.hEnd - R.h0);
+            unsigned char* d0 = (unsigned char*) ctx->d_alloc(span + 48);
+            if (!d0) return ctx->fail(F9_ERR_NOMEM, "arena");
+            d0 += R.off0;
+            F9_TRY_CUDA(ctx, cudaMemcpyAsync(d0, R.h0, span, cudaMemcpyHostToDevice, sUp));
+            for (int t = R.t0; t < R.t1; ++t) {
+                const f9_job& J = jobs[idx[(size_t) t]];
+                if (J.src_pcm && J.captured_frames > 0) dSrcOf[(size_t) t] = d0 + ((const unsigned char*) J.src_pcm - R.h0);
+            }
+        }
+    }
     for (int t = 0; t < n; ++t) {
         const f9_job& J = jobs[idx[(size_t) t]];
         JobPlan& P = plans[(size_t) t];
@@ -111,9 +143,8 @@ int run_chunk(f9_context* ctx, const f9_job* jobs, const std::vector<int>& idx, 
             if (J.captured_frames > 0) {
                 const size_t frameBytes = (size_t) J.src_ch * pcm_bps(J.src_fmt), bytes = frameBytes * (size_t) J.captured_frames;
                 const int lead = std::min(J.captured_frames, (4 - padA) & 3);
-                const size_t off = (16 - (lead * frameBytes) % 16) % 16;
-                unsigned char* d_src = (unsigned char*) ctx->d_alloc(bytes + 48) + off;
-                F9_TRY_CUDA(ctx, cudaMemcpyAsync(d_src, J.src_pcm, bytes, cudaMemcpyHostToDevice, sUp));
+                unsigned char* d_src = dSrcOf[(size_t) t];     // placed (with the copy of its run) above
+                (void) bytes;
                 const auto key = std::make_pair(J.src_fmt, J.src_ch);
                 if (lead > 0) { pcmHead[key].src.push_back(d_src); pcmHead[key].dst.push_back(DevBuf{d_cap, cs, J.numCh, lead}); }
                 if (J.captured_frames > lead) {

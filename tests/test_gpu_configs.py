@@ -102,6 +102,42 @@ def test_job_flow_in_many_chunks_equals_one_chunk(ctx, O, f9):
                 assert np.array_equal(got[1][i], one[1][i]), i
 
 
+def test_job_flow_adjacent_payloads_go_up_as_one_copy(ctx, O, f9):
+    """File payloads that follow one another in host memory (64-byte padded slots of one buffer, as a reader holding its files in
+    one block has them) are uploaded run by run; latencies of every residue modulo 4 (different placements on the device: a run
+    breaks where the placement the next file needs is not the one the host spacing gives) and a mono file in between.  Results equal
+    those of the same payloads in separate buffers, bit for bit."""
+    rng = np.random.default_rng(17)
+    specs = [(2, 30000, 8), (2, 31001, 9), (2, 29003, 9), (1, 30500, 10), (2, 30007, 11), (2, 30011, 11), (2, 30013, 7), (2, 30017, 3)]
+    raws, jobs_sep = [], []
+    for ch, src, lat in specs:
+        cap = (rng.uniform(-0.4, 0.4, (ch, src + lat + 9000)) * np.exp(-np.arange(src + lat + 9000) / 7000.0)).astype(np.float32)
+        q = np.clip(np.round(cap.astype(np.float64) * 8388608.0), -8388608, 8388607).astype(np.int32)
+        inter = q.T.reshape(-1)
+        raws.append(np.stack([(inter >> (8 * b)) & 0xff for b in range(3)], axis=-1).astype(np.uint8).reshape(-1))
+        jobs_sep.append(dict(src_pcm=(raws[-1], f9.PCM_S24LE, ch), latency_samples=lat * ch, original_length=src, fs_in=96000, fs_out=44100,
+                             kind=0, tail=(4800, 2400, 3, f9.TAIL_RMS, True, -60.0, 0.0), pcm24=True))
+    offs = np.concatenate([[0], np.cumsum([(r.size + 63) // 64 * 64 for r in raws])]).astype(np.int64)
+    block = np.zeros(int(offs[-1]) + 64, dtype=np.uint8)
+    jobs_adj = []
+    for i, (r, j) in enumerate(zip(raws, jobs_sep)):
+        block[offs[i]:offs[i] + r.size] = r
+        k = dict(j); k["src_pcm"] = (block[offs[i]:offs[i] + r.size], f9.PCM_S24LE, specs[i][0])
+        jobs_adj.append(k)
+    sep = ctx.process_batch(jobs_sep)
+    adj = ctx.process_batch(jobs_adj)
+    for i in range(len(specs)):
+        assert adj[2][i] == sep[2][i], i
+        assert np.array_equal(adj[0][i], sep[0][i]), i
+        assert np.array_equal(adj[1][i], sep[1][i]), i
+    # and against the oracle for one file
+    cap0 = O.pcm_to_planar(raws[0], f9.PCM_S24LE, 2) if hasattr(O, "pcm_to_planar") else None
+    if cap0 is not None:
+        trimmed, _ = O.trim_latency(cap0, 2 * specs[0][2], specs[0][1])
+        ref, _ = O.resample_channel(0, 96000 / 44100, trimmed[0], adj[0][0].shape[1])
+        assert np.max(np.abs(adj[0][0][0] - ref)) <= TOL
+
+
 # ------------------------------------------------------------------------------------------------ configs[2]
 def test_config3_64ch_10min_time_segmented(ctx, O, f9):
     """64 channels, 48 kHz -> 192 kHz, 10 minutes: 36.9 GB resident, every channel split into 8 time segments that carry their
